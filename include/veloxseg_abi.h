@@ -1,0 +1,186 @@
+/* libveloxseg_sm100 — C ABI of the VeloxSeg hot path for NVIDIA B200 (sm_100a).
+ *
+ * The reference (JinPLu/VeloxSeg) has no FFI boundary: its hot path is the Python nn.Module surface of
+ * model/components/ (SURVEY.md §8b).  These entry points are what a torch custom-op wrapper binds for that
+ * path; every function names the reference code it replaces (path:line into the reference repository).
+ *
+ * Conventions
+ *  - all tensors are device pointers to fp32, NCDHW contiguous, owned by the caller;
+ *  - `in` / `out` are arrays of device pointers in the order documented per function;
+ *  - the library never allocates, never synchronises and never throws: it enqueues kernels on `stream`
+ *    and returns 0 or a negative vx_status (text via vx_last_error_string());
+ *  - `workspace` is caller-allocated scratch of at least vx_<op>_workspace(desc) bytes, 256-B aligned;
+ *  - there is no CPU implementation behind this ABI.
+ */
+#ifndef VELOXSEG_ABI_H_
+#define VELOXSEG_ABI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vx_stream_t; /* cudaStream_t */
+
+typedef enum {
+  VX_OK = 0,
+  VX_ERR_BAD_DESC = -1,
+  VX_ERR_WORKSPACE = -2,
+  VX_ERR_LAUNCH = -3,
+  VX_ERR_UNSUPPORTED = -4
+} vx_status;
+
+#define VX_MAX_MODAL 4  /* modalities per PWA block / streams per mixer */
+#define VX_MAX_SCALES 6 /* paired-window scales per PWA level          */
+
+int vx_version(void);
+const char* vx_last_error_string(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * JLC block — replaces JLC.forward, model/components/conv_blocks.py:41-75 (and autograd's backward of it).
+ *   o = x + sum_{k in {1,3,5}} GELU(IN(gconv_k(x) + b_k));   y = o + Dropout(W2 GELU(W1 IN(o) + b1) + b2)
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, C, D, H, W;   /* x is (B, C, D, H, W)                                   */
+  int32_t groups;          /* conv groups; c_g = C / groups in {4, 8, 16}            */
+  int32_t expansion;       /* e: channel_conv hidden width = e * C                   */
+  float eps;               /* InstanceNorm eps (1e-5)                                */
+  float drop_p;            /* dropout on the channel_conv output (0 disables)        */
+  int32_t training;        /* dropout is applied only when training != 0            */
+  uint64_t seed;           /* counter-based RNG key for this call's dropout mask     */
+} vx_jlc_desc;
+
+/* fwd  in : x, w1,b1, w3,b3, w5,b5 (grouped conv weights (C, c_g, k,k,k) + bias (C)), fw1 (eC, C), fb1 (eC),
+ *           fw2 (C, eC), fb2 (C)                                               [11 pointers]
+ *      out: y (B,C,S), z (3,B,C,S) raw conv outputs, o (B,C,S), hpre (B,eC,S), stats (4, B*C, 2) = (mean, rstd)
+ *           of z1,z3,z5,o                                                       [5 pointers]
+ * bwd  in : dy, x, z, o, hpre, stats, w1,w3,w5, fw1, fb1, fw2                    [12 pointers]
+ *      out: dx, dw1,db1, dw3,db3, dw5,db5, dfw1,dfb1, dfw2,dfb2                  [11 pointers]         */
+size_t vx_jlc_workspace(const vx_jlc_desc* d);
+int vx_jlc_fwd(const vx_jlc_desc* d, const void* const* in, void* const* out, void* workspace,
+               size_t workspace_bytes, vx_stream_t stream);
+int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* const* out, void* workspace,
+               size_t workspace_bytes, vx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Modal mixer — replaces `attn2conv_i(torch.cat(attn_i, 1))` and the `+` that follows, model/Encoder.py:334-337,
+ * 344-361; also serves the identical RC adapters `enc2rc_i(concat(attn, enc))`, model/Decoder.py:54-57,80-83.
+ *   y = [addend +] IN(W . cat_m(a_m) + b)
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, S;                     /* S = D*H*W                                           */
+  int32_t n_streams;                /* M                                                   */
+  int32_t stream_ch[VX_MAX_MODAL];  /* channels of each stream; K = sum                    */
+  int32_t C_out;                    /* N                                                   */
+  int32_t has_addend;               /* 1: y = addend + IN(...)                             */
+  float eps;
+} vx_mixer_desc;
+
+/* fwd  in : a_0..a_{M-1}, W (C_out, K), b (C_out), addend or NULL      out: y, t (B,C_out,S) pre-norm, stats (B*C_out,2)
+ * bwd  in : dy, a_0..a_{M-1}, W, t, stats                               out: da_0..da_{M-1}, dW, db
+ *      (the addend's gradient is dy itself; the caller routes it)                                          */
+size_t vx_mixer_workspace(const vx_mixer_desc* d);
+int vx_mixer_fwd(const vx_mixer_desc* d, const void* const* in, void* const* out, void* workspace,
+                 size_t workspace_bytes, vx_stream_t stream);
+int vx_mixer_bwd(const vx_mixer_desc* d, const void* const* in, void* const* out, void* workspace,
+                 size_t workspace_bytes, vx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * InstanceNorm3d(affine=False) — the norm behind DownConv / UpConv, model/components/conv_blocks.py:19-21,37-39,
+ * model/components/common_function.py:62-66.   y = IN(x) [+ addend]
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t rows;  /* B*C */
+  int32_t S;
+  float eps;
+  int32_t has_addend;
+} vx_inorm_desc;
+/* fwd in: x, addend|NULL   out: y, stats (rows, 2)         bwd in: dy, x, stats   out: dx */
+int vx_inorm_fwd(const vx_inorm_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
+int vx_inorm_bwd(const vx_inorm_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * PWA block — replaces Paired_Windows_TransformerBlock.forward, model/components/PWA.py:433-439, i.e.
+ * MultiModal_Paired_Windows_Attention.forward (PWA.py:329-379: LN, Q/K/V 1x1, window_gathering_3d :106-140,
+ * attention_operation :308-327, window_scattering_3d :177-200, mix 1x1, residual) plus the LN + FFN tail
+ * (attention_utils.py:29-71).  Window geometry is the output of get_window_sizes (PWA.py:56-85).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, M, C;                 /* modalities, channels per modality                     */
+  int32_t D, H, W;                 /* spatial extent of this level (reference names h,w,d)   */
+  int32_t heads, n_scales;
+  int32_t big[VX_MAX_SCALES][3];   /* big window per scale                                   */
+  int32_t small[VX_MAX_SCALES][3]; /* small (pooled) window per scale                        */
+  int32_t c_qk, c_v;               /* TOTAL q/k and v channels (= n_scales*heads*per-head)   */
+  int32_t ffn_expansion;
+  float ln_eps;                    /* 1e-6                                                   */
+  float attn_drop, proj_drop;      /* dropout on softmax weights / on mix + FFN outputs      */
+  int32_t training;
+  uint64_t seed;
+} vx_pwa_desc;
+
+/* Per-modality parameter block, in this order (16 pointers):
+ *   ln1_w, ln1_b, wq, bq, wk, bk, wv, bv, wmix, bmix, ln2_w, ln2_b, w1, b1, w2, b2
+ * fwd  in : x_0..x_{M-1}, params_0 .. params_{M-1}, bias_table ((2n-1)^3, heads), rel_index (l, l) int64
+ *      out: z_0..z_{M-1} (block outputs), then the saved-for-backward buffers listed by vx_pwa_saved_layout()
+ * bwd  in : dz_0..dz_{M-1}, x_0.., params.., bias_table, rel_index, saved buffers
+ *      out: dx_0..dx_{M-1}, dparams_0 .. dparams_{M-1} (same 16-slot order), dbias_table                    */
+typedef struct {
+  int32_t n_saved;
+  size_t saved_bytes[24];
+} vx_pwa_saved;
+int vx_pwa_saved_layout(const vx_pwa_desc* d, vx_pwa_saved* layout);
+size_t vx_pwa_workspace(const vx_pwa_desc* d);
+int vx_pwa_block_fwd(const vx_pwa_desc* d, const void* const* in, void* const* out, void* workspace,
+                     size_t workspace_bytes, vx_stream_t stream);
+int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, void* const* out, void* workspace,
+                     size_t workspace_bytes, vx_stream_t stream);
+
+/* Integer window partition only (bit-exact check of PWA.py:106-140): tokens (B, heads, Ns, l, c) gathered from
+ * x (B, n_scales*heads*c, D,H,W) with the max-pool arg-max voxel index per token element. */
+int vx_pwa_gather(const vx_pwa_desc* d, int32_t channels_total, const void* x, void* tokens, void* argmax,
+                  vx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * SDKT — Gram matrix, model/components/common_function.py:8-14, and the feature loss, utils/loss.py:58-64.
+ *   G[b,m,n] = sum_s x[b,m,s] x[b,n,s] / (C*S);      L = sum_t mean((G_s - G_t)^2) / T
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, C, S;
+} vx_gram_desc;
+size_t vx_gram_workspace(const vx_gram_desc* d);
+/* fwd in: x   out: G (B,C,C)          bwd in: dG, x   out: dx */
+int vx_gram_fwd(const vx_gram_desc* d, const void* const* in, void* const* out, void* workspace,
+                size_t workspace_bytes, vx_stream_t stream);
+int vx_gram_bwd(const vx_gram_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
+
+typedef struct {
+  int32_t n_elem;     /* B*C*C       */
+  int32_t n_teachers; /* T <= VX_MAX_MODAL */
+} vx_sdkt_loss_desc;
+/* fwd in: G_s, G_t0..   out: loss (1)       bwd in: dloss (1), G_s, G_t0..   out: dG_s, dG_t0.. */
+int vx_sdkt_loss_fwd(const vx_sdkt_loss_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
+int vx_sdkt_loss_bwd(const vx_sdkt_loss_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Channel-first LayerNorm + 1x1 conv — the PatchMerging tail, model/components/attention_utils.py:163-168
+ * (the 2x2x2 space-to-depth gather stays a view/cat on the caller side).    y = W . LN(x)     (no bias)
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, C_in, C_out, S;
+  float eps;
+} vx_lnpw_desc;
+/* fwd in: x, ln_w, ln_b, W   out: y, xhat (B,C_in,S), rstd (B,S)
+ * bwd in: dy, xhat, rstd, ln_w, W, ln_b   out: dx, dln_w, dln_b, dW                                        */
+size_t vx_lnpw_workspace(const vx_lnpw_desc* d);
+int vx_lnpw_fwd(const vx_lnpw_desc* d, const void* const* in, void* const* out, void* workspace,
+                size_t workspace_bytes, vx_stream_t stream);
+int vx_lnpw_bwd(const vx_lnpw_desc* d, const void* const* in, void* const* out, void* workspace,
+                size_t workspace_bytes, vx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VELOXSEG_ABI_H_ */

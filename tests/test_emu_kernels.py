@@ -1,0 +1,129 @@
+"""Developer check (opt-in, VX_EMU=1): the kernel sources compiled for the CPU shim in tools/emu, compared with the
+oracle.  Catches indexing mistakes without a GPU.  The real parity tests are the -m gpu ones."""
+import os
+
+import pytest
+import torch
+
+from tests._util import close, jlc_param_dict, jlc_params, rel_err
+
+pytestmark = pytest.mark.emu
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from veloxseg_b200._lib import VxLib
+    from veloxseg_b200.csrc.build import build_emu
+    return VxLib(build_emu())
+
+
+def _oracle():
+    from oracle import veloxseg_oracle as O
+    return O
+
+
+@pytest.mark.parametrize("C,groups,e,shape,B", [(8, 2, 3, (5, 6, 8), 2), (16, 2, 2, (3, 4, 7), 1), (32, 2, 2, (3, 3, 3), 2),
+                                                  (8, 2, 3, (9, 7, 12), 1)])
+def test_jlc(emu, C, groups, e, shape, B):
+    from veloxseg_b200 import ops
+    O = _oracle()
+    torch.manual_seed(1)
+    x = torch.randn(B, C, *shape)
+    params = jlc_params(C, groups, e, seed=3)
+    y, z, o, hpre, stats = ops.jlc_fwd_raw(emu, 0, x, params, groups, e)
+    xr = x.clone().requires_grad_(True)
+    pr = [p.clone().requires_grad_(True) for p in params]
+    yr = O.jlc(xr, jlc_param_dict(pr), "", groups)
+    assert rel_err(y, yr) < 2e-5, rel_err(y, yr)
+    dy = torch.randn_like(y)
+    grads = torch.autograd.grad(yr, [xr] + pr, dy)
+    got = ops.jlc_bwd_raw(emu, 0, dy, x, z, o, hpre, stats, params, groups, e)
+    for i, (g, r) in enumerate(zip(got, grads)):
+        assert close(g, r, rtol=2e-4, atol=2e-5), (i, rel_err(g, r), float(r.norm()))
+
+
+def test_jlc_dropout_consistency(emu):
+    """train-mode dropout: backward must use the mask forward used (finite-difference-free check: linearity in dy)."""
+    from veloxseg_b200 import ops
+    torch.manual_seed(2)
+    C, groups, e = 8, 2, 2
+    x = torch.randn(1, C, 4, 4, 8)
+    params = jlc_params(C, groups, e, seed=5)
+    y0, z, o, hpre, stats = ops.jlc_fwd_raw(emu, 0, x, params, groups, e, 0.0, False, 0)
+    y1, *_ = ops.jlc_fwd_raw(emu, 0, x, params, groups, e, 0.5, True, 1234)
+    y2, *_ = ops.jlc_fwd_raw(emu, 0, x, params, groups, e, 0.5, True, 1234)
+    assert torch.allclose(y1, y2, rtol=1e-5, atol=1e-6)
+    # y = o + mask*2*(W2 h + b2): elements are either o (dropped) or o + 2*(y0 - o)
+    d0, d1 = (y0 - o), (y1 - o)
+    dropped = d1.abs() < 1e-12
+    frac = dropped.float().mean().item()
+    assert 0.35 < frac < 0.65, frac
+    assert torch.allclose(d1[~dropped], 2 * d0[~dropped], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("chs,Co,S,B,addend", [((16, 16), 16, (5, 6, 7), 2, True), ((8,), 24, (4, 4, 4), 1, False),
+                                                ((32, 16, 8), 20, (3, 5, 9), 2, True)])
+def test_mixer(emu, chs, Co, S, B, addend):
+    from veloxseg_b200 import ops
+    O = _oracle()
+    torch.manual_seed(0)
+    streams = [torch.randn(B, c, *S) for c in chs]
+    W = torch.randn(Co, sum(chs)) * 0.2
+    b = torch.randn(Co) * 0.1
+    add = torch.randn(B, Co, *S) if addend else None
+    y, t, stats = ops.mixer_fwd_raw(emu, 0, streams, W, b, add)
+    sr = [s.clone().requires_grad_(True) for s in streams]
+    Wr, br = W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = O.modal_mixer(sr, Wr, br, add)
+    assert rel_err(y, yr) < 1e-5
+    dy = torch.randn_like(y)
+    grads = torch.autograd.grad(yr, sr + [Wr, br], dy)
+    got = ops.mixer_bwd_raw(emu, 0, dy, streams, W, t, stats)
+    for i, (g, r) in enumerate(zip(got, grads)):
+        assert close(g, r, rtol=2e-4, atol=2e-5), (i, rel_err(g, r))
+
+
+def test_inorm_gram_sdkt_lnpw(emu):
+    from veloxseg_b200 import ops
+    O = _oracle()
+    torch.manual_seed(0)
+    x = torch.randn(2, 6, 5, 6, 7) * 2 + 0.5
+    add = torch.randn_like(x)
+    y, stats = ops.inorm_fwd_raw(emu, 0, x, add)
+    xr = x.clone().requires_grad_(True)
+    yr = O.instance_norm(xr) + add
+    assert rel_err(y, yr) < 1e-5
+    dy = torch.randn_like(y)
+    assert close(ops.inorm_bwd_raw(emu, 0, dy, x, stats), torch.autograd.grad(yr, xr, dy)[0], rtol=1e-4)
+
+    f = torch.randn(2, 16, 7, 9, 11)
+    G = ops.gram_fwd_raw(emu, 0, f)
+    fr = f.clone().requires_grad_(True)
+    Gr = O.gram(fr)
+    assert rel_err(G, Gr) < 1e-5
+    dG = torch.randn_like(G)
+    assert close(ops.gram_bwd_raw(emu, 0, dG, f), torch.autograd.grad(Gr, fr, dG)[0], rtol=1e-4)
+    f12 = torch.randn(1, 12, 4, 4, 4)
+    assert rel_err(ops.gram_fwd_raw(emu, 0, f12), O.gram(f12)) < 1e-5
+
+    gs = torch.randn(2, 16, 16).requires_grad_(True)
+    gts = [torch.randn(2, 16, 16).requires_grad_(True) for _ in range(2)]
+    L = ops.sdkt_loss_fwd_raw(emu, 0, gs.detach(), [g.detach() for g in gts])
+    Lr = O.sdkt_loss(gs, gts)
+    assert abs(float(L) - float(Lr)) < 1e-5 * abs(float(Lr))
+    gr = torch.autograd.grad(Lr, [gs] + gts, torch.tensor(1.7))
+    got = ops.sdkt_loss_bwd_raw(emu, 0, torch.tensor(1.7), gs.detach(), [g.detach() for g in gts])
+    for g, r in zip(got, gr):
+        assert close(g, r, rtol=1e-5)
+
+    x = torch.randn(2, 24, 3, 4, 5)
+    lw, lb, W = torch.randn(24) * 0.3 + 1, torch.randn(24) * 0.2, torch.randn(10, 24) * 0.2
+    y, xhat, rstd = ops.lnpw_fwd_raw(emu, 0, x, lw, lb, W)
+    xr, lwr, lbr, Wr = [t.clone().requires_grad_(True) for t in (x, lw, lb, W)]
+    yr = O.pointwise(O.layer_norm_cf(xr, lwr, lbr), Wr, None)
+    assert rel_err(y, yr) < 1e-5
+    dy = torch.randn_like(y)
+    gr = torch.autograd.grad(yr, [xr, lwr, lbr, Wr], dy)
+    got = ops.lnpw_bwd_raw(emu, 0, dy, xhat, rstd, lw, lb, W)
+    for i, (g, r) in enumerate(zip(got, gr)):
+        assert close(g, r, rtol=2e-4, atol=2e-5), (i, rel_err(g, r))

@@ -1,0 +1,144 @@
+"""ctypes binding of libveloxseg_sm100.so (include/veloxseg_abi.h).
+
+The product loads exactly one library — the in-tree sm_100a build — and raises if it is missing: there is no
+CPU or PyTorch fallback behind these ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+VX_MAX_MODAL = 4
+VX_MAX_SCALES = 6
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libveloxseg_sm100.so")
+
+
+class JlcDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("C", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("groups", C.c_int32), ("expansion", C.c_int32), ("eps", C.c_float), ("drop_p", C.c_float),
+                ("training", C.c_int32), ("seed", C.c_uint64)]
+
+
+class MixerDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("S", C.c_int32), ("n_streams", C.c_int32), ("stream_ch", C.c_int32 * VX_MAX_MODAL),
+                ("C_out", C.c_int32), ("has_addend", C.c_int32), ("eps", C.c_float)]
+
+
+class InormDesc(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("S", C.c_int32), ("eps", C.c_float), ("has_addend", C.c_int32)]
+
+
+class PwaDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("M", C.c_int32), ("C", C.c_int32), ("D", C.c_int32), ("H", C.c_int32),
+                ("W", C.c_int32), ("heads", C.c_int32), ("n_scales", C.c_int32),
+                ("big", (C.c_int32 * 3) * VX_MAX_SCALES), ("small", (C.c_int32 * 3) * VX_MAX_SCALES),
+                ("c_qk", C.c_int32), ("c_v", C.c_int32), ("ffn_expansion", C.c_int32), ("ln_eps", C.c_float),
+                ("attn_drop", C.c_float), ("proj_drop", C.c_float), ("training", C.c_int32), ("seed", C.c_uint64)]
+
+
+class PwaSaved(C.Structure):
+    _fields_ = [("n_saved", C.c_int32), ("saved_bytes", C.c_size_t * 24)]
+
+
+class GramDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("C", C.c_int32), ("S", C.c_int32)]
+
+
+class SdktLossDesc(C.Structure):
+    _fields_ = [("n_elem", C.c_int32), ("n_teachers", C.c_int32)]
+
+
+class LnpwDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("C_in", C.c_int32), ("C_out", C.c_int32), ("S", C.c_int32), ("eps", C.c_float)]
+
+
+# every symbol include/veloxseg_abi.h declares
+SYMBOLS = [
+    "vx_version", "vx_last_error_string",
+    "vx_jlc_workspace", "vx_jlc_fwd", "vx_jlc_bwd",
+    "vx_mixer_workspace", "vx_mixer_fwd", "vx_mixer_bwd",
+    "vx_inorm_fwd", "vx_inorm_bwd",
+    "vx_pwa_saved_layout", "vx_pwa_workspace", "vx_pwa_block_fwd", "vx_pwa_block_bwd", "vx_pwa_gather",
+    "vx_gram_workspace", "vx_gram_fwd", "vx_gram_bwd",
+    "vx_sdkt_loss_fwd", "vx_sdkt_loss_bwd",
+    "vx_lnpw_workspace", "vx_lnpw_fwd", "vx_lnpw_bwd",
+]
+
+_WS_OPS = {"jlc", "mixer", "pwa_block", "gram_fwd", "lnpw"}
+
+
+def ptr_array(tensors):
+    """void*[] from a list of tensors / None / raw ints."""
+    vals = []
+    for t in tensors:
+        if t is None:
+            vals.append(None)
+        elif isinstance(t, int):
+            vals.append(t)
+        else:
+            vals.append(t.data_ptr())
+    return (C.c_void_p * max(len(vals), 1))(*vals)
+
+
+class VxLib:
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"veloxseg_b200: native library {path} is missing. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). There is no fallback path.")
+        self.path = path
+        self.c = C.CDLL(path)
+        self.c.vx_last_error_string.restype = C.c_char_p
+        self.c.vx_version.restype = C.c_int
+        for name in ("vx_jlc_workspace", "vx_mixer_workspace", "vx_pwa_workspace", "vx_gram_workspace",
+                     "vx_lnpw_workspace"):
+            getattr(self.c, name).restype = C.c_size_t
+            getattr(self.c, name).argtypes = [C.c_void_p]
+        vp, sz = C.c_void_p, C.c_size_t
+        for name in ("vx_jlc_fwd", "vx_jlc_bwd", "vx_mixer_fwd", "vx_mixer_bwd", "vx_pwa_block_fwd", "vx_pwa_block_bwd",
+                     "vx_gram_fwd", "vx_lnpw_fwd", "vx_lnpw_bwd"):
+            f = getattr(self.c, name)
+            f.restype = C.c_int
+            f.argtypes = [vp, vp, vp, vp, sz, vp]
+        for name in ("vx_inorm_fwd", "vx_inorm_bwd", "vx_gram_bwd", "vx_sdkt_loss_fwd", "vx_sdkt_loss_bwd"):
+            f = getattr(self.c, name)
+            f.restype = C.c_int
+            f.argtypes = [vp, vp, vp, vp]
+        self.c.vx_pwa_saved_layout.restype = C.c_int
+        self.c.vx_pwa_saved_layout.argtypes = [vp, vp]
+        self.c.vx_pwa_gather.restype = C.c_int
+        self.c.vx_pwa_gather.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
+
+    def last_error(self) -> str:
+        s = self.c.vx_last_error_string()
+        return s.decode() if s else ""
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError(f"veloxseg_b200: {what} failed (status {rc}): {self.last_error()}")
+
+    def workspace(self, op: str, desc) -> int:
+        return int(getattr(self.c, f"vx_{op}_workspace")(C.byref(desc)))
+
+    def call_ws(self, name: str, desc, ins, outs, ws, stream: int):
+        """fwd/bwd entry points that take a workspace."""
+        rc = getattr(self.c, name)(C.byref(desc), ptr_array(ins), ptr_array(outs),
+                                   ws.data_ptr() if ws is not None else None,
+                                   ws.numel() * ws.element_size() if ws is not None else 0, stream)
+        self.check(rc, name)
+
+    def call(self, name: str, desc, ins, outs, stream: int):
+        rc = getattr(self.c, name)(C.byref(desc), ptr_array(ins), ptr_array(outs), stream)
+        self.check(rc, name)
+
+
+_lib = None
+
+
+def get_lib() -> VxLib:
+    global _lib
+    if _lib is None:
+        _lib = VxLib(LIB_PATH)
+    return _lib

@@ -1,0 +1,848 @@
+// JLC block (reference: model/components/conv_blocks.py:41-75) for sm_100a, fp32.
+//
+//   o = x + sum_{k in 1,3,5} GELU(IN(gconv_k(x) + b_k));      y = o + Dropout(W2 GELU(W1 IN(o) + b1) + b2)
+//
+// Kernels
+//   jlc_conv_fwd_kernel   one shared 5^3-halo tile of x per (b, group, spatial tile) feeds all three branches: the
+//                         k=3 / k=1 taps are sub-cubes of the k=5 footprint, so x is staged once and each tap row
+//                         is read from shared memory once for up to three accumulator sets.  A thread owns VX
+//                         consecutive voxels x 4 output channels x 3 branches in registers; weights are float4
+//                         broadcasts.  Epilogue: bias, coalesced stores of the raw conv outputs, and per-tile
+//                         (sum, sumsq) partials for the InstanceNorm that follows (deterministic two-level reduce).
+//   jlc_combine_kernel    o = x + sum_k GELU(IN(z_k)), with partial stats of o.
+//   jlc_conv_dgrad_kernel transposed (flipped-weight) correlation of the three branch gradients into dx.
+//   jlc_conv_wgrad_kernel per-tile weight-gradient partials, thread = (ci, dz, dy) x 4 output channels with the
+//                         5 (or 3, 1) dx taps in registers; folded with fp32 atomics.
+//   jlc_bwd_{a,b,c}       element-wise InstanceNorm / GELU backward with block-level partial reductions.
+// The channel_conv FFN runs on the generic channel-contraction kernels in pointwise.cu.
+#include "vx_kernels.h"
+
+#ifdef VX_EMU
+#define __grid_constant__
+#endif
+
+namespace vx {
+
+struct ConvTile { int TZ, TY, TX, ntz, nty, ntx, VX, threads; };
+
+static ConvTile pick_tile(int B, int groups, int CG, int D, int H, int W, int max_threads, size_t max_smem_floats,
+                          int smem_kind) {
+  // smem_kind 0: fwd/dgrad (4 * halo tile), 1: wgrad (4 * halo tile + 3 * CG * tile)
+  ConvTile best{};
+  double best_cost = 1e300;
+  const int VX = (W % 8 == 0) ? 8 : 4;
+  const int TX = ((W < 32 ? W : 32) + VX - 1) / VX * VX;
+  const int cand[] = {8, 6, 4, 3, 2, 1};
+  for (int tz : cand) {
+    if (tz > D && tz != 1) continue;
+    for (int ty : cand) {
+      if (ty > H && ty != 1) continue;
+      const int npos = tz * ty * (TX / VX);
+      const int threads = npos * (CG / 4);
+      if (smem_kind == 0 && (threads > max_threads || threads < 1)) continue;
+      const int TXP = (TX + 4 + 3) & ~3;
+      size_t fl = (size_t)4 * (tz + 4) * (ty + 4) * TXP;
+      if (smem_kind == 1) fl += (size_t)3 * CG * tz * ty * TX;
+      if (fl > max_smem_floats) continue;
+      const int ntz = cdiv(D, tz), nty = cdiv(H, ty), ntx = cdiv(W, TX);
+      const long long ncta = (long long)ntz * nty * ntx * groups * B;
+      const double waves = (double)((ncta + kSMs - 1) / kSMs);
+      // per-CTA work ~ padded outputs plus the halo staging cost
+      const double work = (double)tz * ty * TX * 153.0 * CG + 6.0 * (tz + 4) * (ty + 4) * TXP;
+      double cost = waves * work;
+      if (smem_kind == 0 && threads < 64) cost *= 64.0 / threads;
+      if (cost < best_cost) { best_cost = cost; best = ConvTile{tz, ty, TX, ntz, nty, ntx, VX, threads}; }
+    }
+  }
+  return best;
+}
+
+struct ConvFwdArgs {
+  const float* x; const float* w1; const float* b1; const float* w3; const float* b3; const float* w5; const float* b5;
+  float* z;      // (3, B, C, S): branch k=1, 3, 5
+  float* part;   // (3, B*C, ntiles, 2)
+  int B, C, D, H, W;
+  ConvTile t;
+  int uniform_warps;
+};
+
+template <int CG, int VX>
+__global__ void __launch_bounds__(256) jlc_conv_fwd_kernel(const __grid_constant__ ConvFwdArgs A) {
+  constexpr int NCB = CG / 4;
+  const int g = blockIdx.y, b = blockIdx.z;
+  const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;
+  const int tile = blockIdx.x;
+  const int tx_i = tile % A.t.ntx, ty_i = (tile / A.t.ntx) % A.t.nty, tz_i = tile / (A.t.ntx * A.t.nty);
+  const int z0 = tz_i * TZ, y0 = ty_i * TY, x0 = tx_i * TX;
+  const int HZ = TZ + 4, HY = TY + 4, TXP = (TX + 4 + 3) & ~3;
+  const int D = A.D, H = A.H, W = A.W, C = A.C;
+  const size_t S = (size_t)D * H * W;
+
+  VX_DYN_SMEM(float, sm);
+  float* xs = sm;                                   // [4][HZ][HY][TXP]
+  float* ws5 = xs + (size_t)4 * HZ * HY * TXP;      // [4][125][CG]
+  float* ws3 = ws5 + 4 * 125 * CG;                  // [4][27][CG]
+  float* ws1 = ws3 + 4 * 27 * CG;                   // [4][CG]
+  float* sst = ws1 + 4 * CG;                        // [3][CG][2]
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int NXQ = TX / VX;
+  const int NPOS = TZ * TY * NXQ;
+  const int pos = tid % NPOS, cb = tid / NPOS;
+  const int xq = pos % NXQ, ty = (pos / NXQ) % TY, tz = pos / (NXQ * TY);
+
+  float a5[VX][4], a3[VX][4], a1[VX][4];
+#pragma unroll
+  for (int v = 0; v < VX; ++v)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { a5[v][c] = 0.f; a3[v][c] = 0.f; a1[v][c] = 0.f; }
+
+  for (int i = tid; i < 3 * CG * 2; i += nthr) sst[i] = 0.f;
+
+  for (int chunk = 0; chunk < NCB; ++chunk) {
+    if (chunk > 0) __syncthreads();
+    // stage 4 input channels of the group with a 2-voxel zero halo
+    const int cin0 = g * CG + chunk * 4;
+    for (int idx = tid; idx < 4 * HZ * HY * TXP; idx += nthr) {
+      const int hx = idx % TXP, hy = (idx / TXP) % HY, hz = (idx / (TXP * HY)) % HZ, ci = idx / (TXP * HY * HZ);
+      const int gz = z0 + hz - 2, gy = y0 + hy - 2, gx = x0 + hx - 2;
+      float v = 0.f;
+      if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
+        v = __ldg(A.x + ((size_t)b * C + cin0 + ci) * S + ((size_t)gz * H + gy) * W + gx);
+      xs[idx] = v;
+    }
+    // weights of this ci-chunk, transposed to [ci][tap][co]
+    for (int idx = tid; idx < CG * 4 * 125; idx += nthr) {
+      const int tap = idx % 125, ci = (idx / 125) % 4, co = idx / 500;
+      ws5[(ci * 125 + tap) * CG + co] = __ldg(A.w5 + ((size_t)(g * CG + co) * CG + chunk * 4 + ci) * 125 + tap);
+    }
+    for (int idx = tid; idx < CG * 4 * 27; idx += nthr) {
+      const int tap = idx % 27, ci = (idx / 27) % 4, co = idx / 108;
+      ws3[(ci * 27 + tap) * CG + co] = __ldg(A.w3 + ((size_t)(g * CG + co) * CG + chunk * 4 + ci) * 27 + tap);
+    }
+    for (int idx = tid; idx < CG * 4; idx += nthr) {
+      const int ci = idx % 4, co = idx / 4;
+      ws1[ci * CG + co] = __ldg(A.w1 + (size_t)(g * CG + co) * CG + chunk * 4 + ci);
+    }
+    __syncthreads();
+
+    if (cb < NCB) {
+      for (int ci = 0; ci < 4; ++ci) {
+        for (int dz = 0; dz < 5; ++dz) {
+          const float* xrow = xs + ((size_t)(ci * HZ + tz + dz) * HY + ty) * TXP + xq * VX;
+          const bool mid_z = dz >= 1 && dz <= 3;
+#pragma unroll
+          for (int dy = 0; dy < 5; ++dy) {
+            float xr[VX + 4];
+#pragma unroll
+            for (int q = 0; q < (VX + 4) / 4; ++q) {
+              const float4 t4 = *reinterpret_cast<const float4*>(xrow + dy * TXP + 4 * q);
+              xr[4 * q] = t4.x; xr[4 * q + 1] = t4.y; xr[4 * q + 2] = t4.z; xr[4 * q + 3] = t4.w;
+            }
+            const float* w5p = ws5 + (size_t)(ci * 125 + (dz * 5 + dy) * 5) * CG + cb * 4;
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) {
+              const float4 w = *reinterpret_cast<const float4*>(w5p + dx * CG);
+#pragma unroll
+              for (int v = 0; v < VX; ++v) {
+                a5[v][0] = fmaf(w.x, xr[v + dx], a5[v][0]); a5[v][1] = fmaf(w.y, xr[v + dx], a5[v][1]);
+                a5[v][2] = fmaf(w.z, xr[v + dx], a5[v][2]); a5[v][3] = fmaf(w.w, xr[v + dx], a5[v][3]);
+              }
+            }
+            if (dy >= 1 && dy <= 3) {
+              if (mid_z) {
+                const float* w3p = ws3 + (size_t)(ci * 27 + ((dz - 1) * 3 + (dy - 1)) * 3) * CG + cb * 4;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                  const float4 w = *reinterpret_cast<const float4*>(w3p + dx * CG);
+#pragma unroll
+                  for (int v = 0; v < VX; ++v) {
+                    a3[v][0] = fmaf(w.x, xr[v + 1 + dx], a3[v][0]); a3[v][1] = fmaf(w.y, xr[v + 1 + dx], a3[v][1]);
+                    a3[v][2] = fmaf(w.z, xr[v + 1 + dx], a3[v][2]); a3[v][3] = fmaf(w.w, xr[v + 1 + dx], a3[v][3]);
+                  }
+                }
+              }
+              if (dy == 2 && dz == 2) {
+                const float4 w = *reinterpret_cast<const float4*>(ws1 + ci * CG + cb * 4);
+#pragma unroll
+                for (int v = 0; v < VX; ++v) {
+                  a1[v][0] = fmaf(w.x, xr[v + 2], a1[v][0]); a1[v][1] = fmaf(w.y, xr[v + 2], a1[v][1]);
+                  a1[v][2] = fmaf(w.z, xr[v + 2], a1[v][2]); a1[v][3] = fmaf(w.w, xr[v + 2], a1[v][3]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // epilogue: bias, store, stats
+  const int gz = z0 + tz, gy = y0 + ty, gx0 = x0 + xq * VX;
+  const bool row_ok = cb < NCB && gz < D && gy < H;
+  const size_t BCS = (size_t)A.B * C * S;
+  const int lane = tid & 31;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int co = cb < NCB ? g * CG + cb * 4 + c : 0;
+    const float bias[3] = {__ldg(A.b1 + co), __ldg(A.b3 + co), __ldg(A.b5 + co)};
+    float s[3] = {0.f, 0.f, 0.f}, q[3] = {0.f, 0.f, 0.f};
+    if (row_ok) {
+      const size_t o = ((size_t)b * C + co) * S + ((size_t)gz * H + gy) * W + gx0;
+#pragma unroll
+      for (int v = 0; v < VX; ++v) {
+        if (gx0 + v < W) {
+          const float r1 = a1[v][c] + bias[0], r3 = a3[v][c] + bias[1], r5 = a5[v][c] + bias[2];
+          A.z[o + v] = r1; A.z[BCS + o + v] = r3; A.z[2 * BCS + o + v] = r5;
+          s[0] += r1; q[0] = fmaf(r1, r1, q[0]);
+          s[1] += r3; q[1] = fmaf(r3, r3, q[1]);
+          s[2] += r5; q[2] = fmaf(r5, r5, q[2]);
+        }
+      }
+    }
+    if (A.uniform_warps) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float ss = warp_sum(s[k]), qq = warp_sum(q[k]);
+        if (lane == 0 && cb < NCB) {
+          atomicAdd(sst + ((k * CG) + cb * 4 + c) * 2, ss);
+          atomicAdd(sst + ((k * CG) + cb * 4 + c) * 2 + 1, qq);
+        }
+      }
+    } else if (row_ok) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        atomicAdd(sst + ((k * CG) + cb * 4 + c) * 2, s[k]);
+        atomicAdd(sst + ((k * CG) + cb * 4 + c) * 2 + 1, q[k]);
+      }
+    }
+  }
+  __syncthreads();
+  const int ntiles = gridDim.x;
+  for (int i = tid; i < 3 * CG; i += nthr) {
+    const int k = i / CG, c = i % CG;
+    const size_t row = (size_t)k * A.B * C + (size_t)b * C + g * CG + c;
+    float* p = A.part + (row * ntiles + tile) * 2;
+    p[0] = sst[i * 2]; p[1] = sst[i * 2 + 1];
+  }
+}
+
+// stats[row] = (mean, rstd) from tile partials; optionally the (a, c) affine used as a contraction prologue
+__global__ void jlc_finalize_kernel(const float* __restrict__ part, int rows, int npart, float n, float eps,
+                                    float* __restrict__ stats, float* __restrict__ a, float* __restrict__ c) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float mean, rstd;
+  finalize_stats(part, r, npart, n, eps, mean, rstd);
+  stats[2 * r] = mean; stats[2 * r + 1] = rstd;
+  if (a) { a[r] = rstd; c[r] = -mean * rstd; }
+}
+
+// o = x + sum_k GELU((z_k - mean_k) * rstd_k);  partial (sum, sumsq) of o per (row, chunk)
+__global__ void __launch_bounds__(256) jlc_combine_kernel(const float* __restrict__ x, const float* __restrict__ z,
+                                                          const float* __restrict__ stats, float* __restrict__ o,
+                                                          float* __restrict__ part_o, int rows, int S, int chunk) {
+  __shared__ float red[33];
+  const int row = blockIdx.y, ck = blockIdx.x;
+  const size_t RS = (size_t)rows * S;
+  float m[3], r[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { m[k] = stats[2 * (k * rows + row)]; r[k] = stats[2 * (k * rows + row) + 1]; }
+  const size_t base = (size_t)row * S;
+  const int lo = ck * chunk, hi = min(S, lo + chunk);
+  float s = 0.f, q = 0.f;
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    float v = x[base + i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v += gelu_f((z[k * RS + base + i] - m[k]) * r[k]);
+    o[base + i] = v;
+    s += v; q = fmaf(v, v, q);
+  }
+  s = block_sum(s, red);
+  q = block_sum(q, red);
+  if (threadIdx.x == 0) {
+    float* p = part_o + ((size_t)row * gridDim.x + ck) * 2;
+    p[0] = s; p[1] = q;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward element-wise stages
+// ---------------------------------------------------------------------------------------------------
+// a: acc[row] += (sum dohat, sum dohat * ohat)
+__global__ void __launch_bounds__(256) jlc_bwd_a_kernel(const float* __restrict__ dohat, const float* __restrict__ o,
+                                                        const float* __restrict__ stats_o, float* __restrict__ acc,
+                                                        int S, int chunk) {
+  __shared__ float red[33];
+  const int row = blockIdx.y;
+  const float mean = stats_o[2 * row], rstd = stats_o[2 * row + 1];
+  const size_t base = (size_t)row * S;
+  const int lo = blockIdx.x * chunk, hi = min(S, lo + chunk);
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float g = dohat[base + i];
+    s1 += g; s2 = fmaf(g, (o[base + i] - mean) * rstd, s2);
+  }
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  if (threadIdx.x == 0) { atomicAdd(acc + 2 * row, s1); atomicAdd(acc + 2 * row + 1, s2); }
+}
+
+// b: dO = dy + rstd_o (dohat - m1 - ohat m2);  acc2[k][row] += (sum g_k, sum g_k zhat_k), g_k = dO * GELU'(zhat_k)
+__global__ void __launch_bounds__(256) jlc_bwd_b_kernel(const float* __restrict__ dy, const float* __restrict__ dohat,
+                                                        const float* __restrict__ o, const float* __restrict__ z,
+                                                        const float* __restrict__ stats, const float* __restrict__ acc,
+                                                        float* __restrict__ dO, float* __restrict__ acc2, int rows,
+                                                        int S, int chunk) {
+  __shared__ float red[33];
+  const int row = blockIdx.y;
+  const size_t RS = (size_t)rows * S;
+  const float mo = stats[2 * (3 * rows + row)], ro = stats[2 * (3 * rows + row) + 1];
+  const float m1 = acc[2 * row] / (float)S, m2 = acc[2 * row + 1] / (float)S;
+  float m[3], r[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { m[k] = stats[2 * (k * rows + row)]; r[k] = stats[2 * (k * rows + row) + 1]; }
+  const size_t base = (size_t)row * S;
+  const int lo = blockIdx.x * chunk, hi = min(S, lo + chunk);
+  float s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f};
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float oh = (o[base + i] - mo) * ro;
+    const float d = dy[base + i] + ro * (dohat[base + i] - m1 - oh * m2);
+    dO[base + i] = d;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float zh = (z[k * RS + base + i] - m[k]) * r[k];
+      const float g = d * gelu_grad_f(zh);
+      s1[k] += g; s2[k] = fmaf(g, zh, s2[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float t1 = block_sum(s1[k], red), t2 = block_sum(s2[k], red);
+    if (threadIdx.x == 0) {
+      atomicAdd(acc2 + 2 * ((size_t)k * rows + row), t1);
+      atomicAdd(acc2 + 2 * ((size_t)k * rows + row) + 1, t2);
+    }
+  }
+}
+
+// c: gz_k = rstd_k (g_k - mean(g_k) - zhat_k mean(g_k zhat_k))
+__global__ void __launch_bounds__(256) jlc_bwd_c_kernel(const float* __restrict__ dO, const float* __restrict__ z,
+                                                        const float* __restrict__ stats, const float* __restrict__ acc2,
+                                                        float* __restrict__ gz, int rows, int S) {
+  const int row = blockIdx.y;
+  const size_t RS = (size_t)rows * S;
+  float m[3], r[3], m1[3], m2[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    m[k] = stats[2 * (k * rows + row)]; r[k] = stats[2 * (k * rows + row) + 1];
+    m1[k] = acc2[2 * ((size_t)k * rows + row)] / (float)S; m2[k] = acc2[2 * ((size_t)k * rows + row) + 1] / (float)S;
+  }
+  const size_t base = (size_t)row * S;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
+    const float d = dO[base + i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float zh = (z[k * RS + base + i] - m[k]) * r[k];
+      const float g = d * gelu_grad_f(zh);
+      gz[k * RS + base + i] = r[k] * (g - m1[k] - zh * m2[k]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// conv dgrad:  dx[ci] = dO[ci] + sum_k sum_co sum_t w_k[co][ci][K-1-t] gz_k[co][u + t - p]
+// The three branches are processed one after the other through the same shared tile (halo 2, 1, 0).
+// ---------------------------------------------------------------------------------------------------
+struct ConvDgradArgs {
+  const float* gz;   // (3, B, C, S)
+  const float* dO;   // (B, C, S)
+  const float* w1; const float* w3; const float* w5;
+  float* dx;
+  int B, C, D, H, W;
+  ConvTile t;
+};
+
+template <int CG, int VX, int K>
+VX_DEV void dgrad_branch(const ConvDgradArgs& A, const float* __restrict__ gzk, const float* __restrict__ wk, float* xs,
+                         float* ws, float (&acc)[VX][4], int g, int b, int z0, int y0, int x0, int tz, int ty, int xq,
+                         int cb) {
+  constexpr int NCB = CG / 4, P = K / 2, K3 = K * K * K;
+  const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;
+  const int HZ = TZ + 2 * P, HY = TY + 2 * P, TXP = (TX + 4 + 3) & ~3;   // x keeps the 2-voxel halo for alignment
+  const int D = A.D, H = A.H, W = A.W, C = A.C;
+  const size_t S = (size_t)D * H * W;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int chunk = 0; chunk < NCB; ++chunk) {
+    __syncthreads();
+    const int c0 = g * CG + chunk * 4;     // 4 "input" channels of this correlation = conv output channels
+    for (int idx = tid; idx < 4 * HZ * HY * TXP; idx += nthr) {
+      const int hx = idx % TXP, hy = (idx / TXP) % HY, hz = (idx / (TXP * HY)) % HZ, ci = idx / (TXP * HY * HZ);
+      const int gz_ = z0 + hz - P, gy = y0 + hy - P, gx = x0 + hx - 2;
+      float v = 0.f;
+      if (gz_ >= 0 && gz_ < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
+        v = __ldg(gzk + ((size_t)b * C + c0 + ci) * S + ((size_t)gz_ * H + gy) * W + gx);
+      xs[idx] = v;
+    }
+    // ws[co_local(4)][tap'][ci_out(CG)] = w[co][ci][K3-1-tap']
+    for (int idx = tid; idx < 4 * CG * K3; idx += nthr) {
+      const int tap = idx % K3, cio = (idx / K3) % CG, col = idx / (K3 * CG);
+      ws[(col * K3 + (K3 - 1 - tap)) * CG + cio] = __ldg(wk + ((size_t)(c0 + col) * CG + cio) * K3 + tap);
+    }
+    __syncthreads();
+    if (cb < NCB) {
+      for (int ci = 0; ci < 4; ++ci) {
+        for (int dz = 0; dz < K; ++dz) {
+          const float* xrow = xs + ((size_t)(ci * HZ + tz + dz) * HY + ty) * TXP + xq * VX;
+#pragma unroll
+          for (int dy = 0; dy < K; ++dy) {
+            float xr[VX + 4];
+#pragma unroll
+            for (int q = 0; q < (VX + 4) / 4; ++q) {
+              const float4 t4 = *reinterpret_cast<const float4*>(xrow + dy * TXP + 4 * q);
+              xr[4 * q] = t4.x; xr[4 * q + 1] = t4.y; xr[4 * q + 2] = t4.z; xr[4 * q + 3] = t4.w;
+            }
+            const float* wp = ws + (size_t)(ci * K3 + (dz * K + dy) * K) * CG + cb * 4;
+#pragma unroll
+            for (int dx = 0; dx < K; ++dx) {
+              const float4 w = *reinterpret_cast<const float4*>(wp + dx * CG);
+#pragma unroll
+              for (int v = 0; v < VX; ++v) {
+                const float xv = xr[v + dx + 2 - P];
+                acc[v][0] = fmaf(w.x, xv, acc[v][0]); acc[v][1] = fmaf(w.y, xv, acc[v][1]);
+                acc[v][2] = fmaf(w.z, xv, acc[v][2]); acc[v][3] = fmaf(w.w, xv, acc[v][3]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int CG, int VX>
+__global__ void __launch_bounds__(256) jlc_conv_dgrad_kernel(const __grid_constant__ ConvDgradArgs A) {
+  constexpr int NCB = CG / 4;
+  const int g = blockIdx.y, b = blockIdx.z;
+  const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;
+  const int tile = blockIdx.x;
+  const int tx_i = tile % A.t.ntx, ty_i = (tile / A.t.ntx) % A.t.nty, tz_i = tile / (A.t.ntx * A.t.nty);
+  const int z0 = tz_i * TZ, y0 = ty_i * TY, x0 = tx_i * TX;
+  const int TXP = (TX + 4 + 3) & ~3;
+  VX_DYN_SMEM(float, sm);
+  float* xs = sm;
+  float* ws = sm + (size_t)4 * (TZ + 4) * (TY + 4) * TXP;   // [4][125][CG] (largest branch)
+  const int tid = threadIdx.x;
+  const int NXQ = TX / VX, NPOS = TZ * TY * NXQ;
+  const int pos = tid % NPOS, cb = tid / NPOS;
+  const int xq = pos % NXQ, ty = (pos / NXQ) % TY, tz = pos / (NXQ * TY);
+  const size_t S = (size_t)A.D * A.H * A.W;
+  const size_t BCS = (size_t)A.B * A.C * S;
+
+  float acc[VX][4];
+#pragma unroll
+  for (int v = 0; v < VX; ++v)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[v][c] = 0.f;
+
+  dgrad_branch<CG, VX, 5>(A, A.gz + 2 * BCS, A.w5, xs, ws, acc, g, b, z0, y0, x0, tz, ty, xq, cb);
+  dgrad_branch<CG, VX, 3>(A, A.gz + BCS, A.w3, xs, ws, acc, g, b, z0, y0, x0, tz, ty, xq, cb);
+  dgrad_branch<CG, VX, 1>(A, A.gz, A.w1, xs, ws, acc, g, b, z0, y0, x0, tz, ty, xq, cb);
+
+  const int gz = z0 + tz, gy = y0 + ty, gx0 = x0 + xq * VX;
+  if (cb < NCB && gz < A.D && gy < A.H) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int ci = g * CG + cb * 4 + c;
+      const size_t o = ((size_t)b * A.C + ci) * S + ((size_t)gz * A.H + gy) * A.W + gx0;
+#pragma unroll
+      for (int v = 0; v < VX; ++v)
+        if (gx0 + v < A.W) A.dx[o + v] = acc[v][c] + A.dO[o + v];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// conv wgrad:  dw_k[co][ci][t] += sum_{b,u} gz_k[b,co,u] * x[b,ci,u + t - p];   db_k[co] += sum gz_k[b,co,u]
+// ---------------------------------------------------------------------------------------------------
+struct ConvWgradArgs {
+  const float* x; const float* gz;
+  float* dw1; float* db1; float* dw3; float* db3; float* dw5; float* db5;
+  int B, C, D, H, W;
+  ConvTile t;
+};
+
+template <int CG, int K>
+VX_DEV void wgrad_items(const ConvWgradArgs& A, const float* xs, const float* gsk, float* __restrict__ dwk, int g,
+                        int chunk, int item0, int nitems_before, int HZ, int HY, int TXP) {
+  // item = (ci in chunk (4), dz, dy, co-block); accumulators: K dx taps x 4 output channels
+  constexpr int NCB = CG / 4, P = K / 2, K3 = K * K * K;
+  const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;
+  const int nitems = 4 * K * K * NCB;
+  for (int it = item0 - nitems_before; it < nitems; it += blockDim.x) {
+    if (it < 0) continue;
+    const int cb = it % NCB, dy = (it / NCB) % K, dz = (it / (NCB * K)) % K, ci = it / (NCB * K * K);
+    float acc[K][4];
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+    for (int z = 0; z < TZ; ++z) {
+      for (int y = 0; y < TY; ++y) {
+        const float* xrow = xs + ((size_t)(ci * HZ + z + dz + 2 - P) * HY + (y + dy + 2 - P)) * TXP;
+        const float* grow = gsk + ((size_t)(cb * 4) * TZ + z) * TY * TX + (size_t)y * TX;
+        for (int x = 0; x < TX; x += 4) {
+          const float4 xa = *reinterpret_cast<const float4*>(xrow + x);
+          const float4 xb = *reinterpret_cast<const float4*>(xrow + x + 4);
+          const float xr[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 gv = *reinterpret_cast<const float4*>(grow + (size_t)c * TZ * TY * TX + x);
+            const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+#pragma unroll
+              for (int v = 0; v < 4; ++v) acc[i][c] = fmaf(gg[v], xr[v + i + 2 - P], acc[i][c]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int co = g * CG + cb * 4 + c;
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+        atomicAdd(dwk + ((size_t)co * CG + chunk * 4 + ci) * K3 + (dz * K + dy) * K + i, acc[i][c]);
+    }
+  }
+}
+
+template <int CG>
+__global__ void __launch_bounds__(256) jlc_conv_wgrad_kernel(const __grid_constant__ ConvWgradArgs A) {
+  constexpr int NCB = CG / 4;
+  const int g = blockIdx.y, b = blockIdx.z;
+  const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;
+  const int tile = blockIdx.x;
+  const int tx_i = tile % A.t.ntx, ty_i = (tile / A.t.ntx) % A.t.nty, tz_i = tile / (A.t.ntx * A.t.nty);
+  const int z0 = tz_i * TZ, y0 = ty_i * TY, x0 = tx_i * TX;
+  const int HZ = TZ + 4, HY = TY + 4, TXP = (TX + 4 + 3) & ~3;
+  const int D = A.D, H = A.H, W = A.W, C = A.C;
+  const size_t S = (size_t)D * H * W;
+  const size_t BCS = (size_t)A.B * C * S;
+  VX_DYN_SMEM(float, sm);
+  float* xs = sm;                                // [4][HZ][HY][TXP], x halo tile of one ci-chunk
+  float* gs = sm + (size_t)4 * HZ * HY * TXP;    // [3][CG][TZ][TY][TX]
+  __shared__ float sdb[3 * 16];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int tvol = TZ * TY * TX;
+
+  if (tid < 3 * 16) sdb[tid] = 0.f;
+  for (int idx = tid; idx < 3 * CG * tvol; idx += nthr) {
+    const int x = idx % TX, y = (idx / TX) % TY, z = (idx / (TX * TY)) % TZ, co = (idx / tvol) % CG, k = idx / (tvol * CG);
+    const int gz_ = z0 + z, gy = y0 + y, gx = x0 + x;
+    float v = 0.f;
+    if (gz_ < D && gy < H && gx < W)
+      v = __ldg(A.gz + k * BCS + ((size_t)b * C + g * CG + co) * S + ((size_t)gz_ * H + gy) * W + gx);
+    gs[idx] = v;
+  }
+  __syncthreads();
+  // db partials: one warp-strided pass per (k, co)
+  for (int r = tid >> 5; r < 3 * CG; r += nthr >> 5) {
+    float s = 0.f;
+    for (int i = tid & 31; i < tvol; i += 32) s += gs[(size_t)r * tvol + i];
+    s = warp_sum(s);
+    if ((tid & 31) == 0) sdb[r] = s;
+  }
+
+  for (int chunk = 0; chunk < NCB; ++chunk) {
+    __syncthreads();
+    const int cin0 = g * CG + chunk * 4;
+    for (int idx = tid; idx < 4 * HZ * HY * TXP; idx += nthr) {
+      const int hx = idx % TXP, hy = (idx / TXP) % HY, hz = (idx / (TXP * HY)) % HZ, ci = idx / (TXP * HY * HZ);
+      const int gz_ = z0 + hz - 2, gy = y0 + hy - 2, gx = x0 + hx - 2;
+      float v = 0.f;
+      if (gz_ >= 0 && gz_ < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
+        v = __ldg(A.x + ((size_t)b * C + cin0 + ci) * S + ((size_t)gz_ * H + gy) * W + gx);
+      xs[idx] = v;
+    }
+    __syncthreads();
+    // a flat item list: k=5 items first (heaviest), then k=3, then k=1
+    const int n5 = 4 * 25 * NCB, n3 = 4 * 9 * NCB;
+    wgrad_items<CG, 5>(A, xs, gs + (size_t)2 * CG * tvol, A.dw5, g, chunk, tid, 0, HZ, HY, TXP);
+    wgrad_items<CG, 3>(A, xs, gs + (size_t)1 * CG * tvol, A.dw3, g, chunk, tid, n5, HZ, HY, TXP);
+    wgrad_items<CG, 1>(A, xs, gs, A.dw1, g, chunk, tid, n5 + n3, HZ, HY, TXP);
+  }
+  __syncthreads();
+  if (tid < 3 * CG) {
+    const int k = tid / CG, co = g * CG + tid % CG;
+    float* db = k == 0 ? A.db1 : (k == 1 ? A.db3 : A.db5);
+    atomicAdd(db + co, sdb[tid]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------------
+static inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+struct JlcLayout {
+  size_t S, BCS, rows;
+  ConvTile tf, tw;
+  int nchunk, chunk;
+  size_t off_part_z, off_part_o, off_a, off_c;                       // forward scratch
+  size_t off_dh, off_dohat, off_dO, off_gz, off_acc, off_acc2;      // backward scratch
+  size_t total;
+};
+
+static int jlc_layout(const vx_jlc_desc* d, JlcLayout& L) {
+  if (!d || d->B <= 0 || d->C <= 0 || d->groups <= 0 || d->C % d->groups) { set_error("jlc: bad descriptor"); return VX_ERR_BAD_DESC; }
+  const int CG = d->C / d->groups;
+  if (CG != 4 && CG != 8 && CG != 16) { set_error("jlc: channels per group %d not in {4,8,16}", CG); return VX_ERR_UNSUPPORTED; }
+  if (d->expansion <= 0 || d->expansion * d->C > 4096) { set_error("jlc: bad expansion"); return VX_ERR_BAD_DESC; }
+  L.S = (size_t)d->D * d->H * d->W;
+  L.rows = (size_t)d->B * d->C;
+  L.BCS = L.rows * L.S;
+  L.tf = pick_tile(d->B, d->groups, CG, d->D, d->H, d->W, 256, 40 * 1024, 0);
+  L.tw = pick_tile(d->B, d->groups, CG, d->D, d->H, d->W, 256, 44 * 1024, 1);
+  if (L.tf.threads == 0 || L.tw.TZ == 0) { set_error("jlc: no tile fits"); return VX_ERR_UNSUPPORTED; }
+  L.chunk = 2048;
+  L.nchunk = cdiv((long long)L.S, L.chunk);
+  const int ntiles = L.tf.ntz * L.tf.nty * L.tf.ntx;
+  size_t off = 0;
+  L.off_part_z = off; off += align256(sizeof(float) * 3 * L.rows * ntiles * 2);
+  L.off_part_o = off; off += align256(sizeof(float) * L.rows * L.nchunk * 2);
+  L.off_a = off; off += align256(sizeof(float) * L.rows);
+  L.off_c = off; off += align256(sizeof(float) * L.rows);
+  L.off_dh = off; off += align256(sizeof(float) * (size_t)d->B * d->expansion * d->C * L.S);
+  L.off_dohat = off; off += align256(sizeof(float) * L.BCS);
+  L.off_dO = off; off += align256(sizeof(float) * L.BCS);
+  L.off_gz = off; off += align256(sizeof(float) * 3 * L.BCS);
+  L.off_acc = off; off += align256(sizeof(float) * L.rows * 2);
+  L.off_acc2 = off; off += align256(sizeof(float) * 3 * L.rows * 2);
+  L.total = off;
+  return VX_OK;
+}
+
+template <int CG>
+static int launch_conv_fwd(const ConvFwdArgs& A, int groups, cudaStream_t st) {
+  const ConvTile& t = A.t;
+  const int TXP = (t.TX + 4 + 3) & ~3;
+  const size_t smem = sizeof(float) * ((size_t)4 * (t.TZ + 4) * (t.TY + 4) * TXP + 4 * 153 * CG + 3 * CG * 2);
+  dim3 grid(t.ntz * t.nty * t.ntx, groups, A.B);
+  if (t.VX == 8) {
+    VX_SET_SMEM((jlc_conv_fwd_kernel<CG, 8>), smem);
+    VX_LAUNCH((jlc_conv_fwd_kernel<CG, 8>), grid, dim3(t.threads), smem, st, A);
+  } else {
+    VX_SET_SMEM((jlc_conv_fwd_kernel<CG, 4>), smem);
+    VX_LAUNCH((jlc_conv_fwd_kernel<CG, 4>), grid, dim3(t.threads), smem, st, A);
+  }
+  return check_launch("jlc_conv_fwd_kernel");
+}
+
+template <int CG>
+static int launch_conv_dgrad(const ConvDgradArgs& A, int groups, cudaStream_t st) {
+  const ConvTile& t = A.t;
+  const int TXP = (t.TX + 4 + 3) & ~3;
+  const size_t smem = sizeof(float) * ((size_t)4 * (t.TZ + 4) * (t.TY + 4) * TXP + 4 * 125 * CG);
+  dim3 grid(t.ntz * t.nty * t.ntx, groups, A.B);
+  if (t.VX == 8) {
+    VX_SET_SMEM((jlc_conv_dgrad_kernel<CG, 8>), smem);
+    VX_LAUNCH((jlc_conv_dgrad_kernel<CG, 8>), grid, dim3(t.threads), smem, st, A);
+  } else {
+    VX_SET_SMEM((jlc_conv_dgrad_kernel<CG, 4>), smem);
+    VX_LAUNCH((jlc_conv_dgrad_kernel<CG, 4>), grid, dim3(t.threads), smem, st, A);
+  }
+  return check_launch("jlc_conv_dgrad_kernel");
+}
+
+template <int CG>
+static int launch_conv_wgrad(const ConvWgradArgs& A, int groups, cudaStream_t st) {
+  const ConvTile& t = A.t;
+  const int TXP = (t.TX + 4 + 3) & ~3;
+  const size_t smem = sizeof(float) * ((size_t)4 * (t.TZ + 4) * (t.TY + 4) * TXP + (size_t)3 * CG * t.TZ * t.TY * t.TX);
+  dim3 grid(t.ntz * t.nty * t.ntx, groups, A.B);
+  VX_SET_SMEM((jlc_conv_wgrad_kernel<CG>), smem);
+  VX_LAUNCH((jlc_conv_wgrad_kernel<CG>), grid, dim3(256), smem, st, A);
+  return check_launch("jlc_conv_wgrad_kernel");
+}
+
+#define VX_TRY(expr) do { int _rc = (expr); if (_rc != VX_OK) return _rc; } while (0)
+
+}  // namespace vx
+
+using namespace vx;
+
+extern "C" size_t vx_jlc_workspace(const vx_jlc_desc* d) {
+  JlcLayout L;
+  if (jlc_layout(d, L) != VX_OK) return 0;
+  return L.total;
+}
+
+extern "C" int vx_jlc_fwd(const vx_jlc_desc* d, const void* const* in, void* const* out, void* workspace,
+                          size_t workspace_bytes, vx_stream_t stream) {
+  JlcLayout L;
+  VX_TRY(jlc_layout(d, L));
+  if (!workspace || workspace_bytes < L.total) { set_error("jlc_fwd: workspace %zu < %zu", workspace_bytes, L.total); return VX_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const int CG = d->C / d->groups, eC = d->expansion * d->C;
+  const float* x = (const float*)in[0];
+  float* y = (float*)out[0];
+  float* z = (float*)out[1];
+  float* o = (float*)out[2];
+  float* hpre = (float*)out[3];
+  float* stats = (float*)out[4];
+  float* part_z = (float*)(ws + L.off_part_z);
+  float* part_o = (float*)(ws + L.off_part_o);
+  float* aff_a = (float*)(ws + L.off_a);
+  float* aff_c = (float*)(ws + L.off_c);
+  const int rows = (int)L.rows, S = (int)L.S;
+
+  ConvFwdArgs A{};
+  A.x = x; A.w1 = (const float*)in[1]; A.b1 = (const float*)in[2]; A.w3 = (const float*)in[3]; A.b3 = (const float*)in[4];
+  A.w5 = (const float*)in[5]; A.b5 = (const float*)in[6];
+  A.z = z; A.part = part_z; A.B = d->B; A.C = d->C; A.D = d->D; A.H = d->H; A.W = d->W; A.t = L.tf;
+  const int npos = L.tf.TZ * L.tf.TY * (L.tf.TX / L.tf.VX);
+  A.uniform_warps = (npos % 32 == 0) ? 1 : 0;
+  if (CG == 4) VX_TRY(launch_conv_fwd<4>(A, d->groups, st));
+  else if (CG == 8) VX_TRY(launch_conv_fwd<8>(A, d->groups, st));
+  else VX_TRY(launch_conv_fwd<16>(A, d->groups, st));
+
+  const int ntiles = L.tf.ntz * L.tf.nty * L.tf.ntx;
+  VX_LAUNCH(jlc_finalize_kernel, dim3(cdiv(3 * rows, 128)), dim3(128), 0, st, (const float*)part_z, 3 * rows, ntiles,
+            (float)S, d->eps, stats, (float*)nullptr, (float*)nullptr);
+  VX_TRY(check_launch("jlc_finalize_kernel"));
+  VX_LAUNCH(jlc_combine_kernel, dim3(L.nchunk, rows), dim3(256), 0, st, x, (const float*)z, (const float*)stats, o,
+            part_o, rows, S, L.chunk);
+  VX_TRY(check_launch("jlc_combine_kernel"));
+  VX_LAUNCH(jlc_finalize_kernel, dim3(cdiv(rows, 128)), dim3(128), 0, st, (const float*)part_o, rows, L.nchunk,
+            (float)S, d->eps, stats + (size_t)2 * 3 * rows, aff_a, aff_c);
+  VX_TRY(check_launch("jlc_finalize_kernel"));
+
+  // hpre = W1 IN(o) + b1
+  PwBatch pb{};
+  pb.nprob = 1; pb.B = d->B; pb.S = S;
+  PwProblem& p1 = pb.p[0];
+  p1.src[0] = PwSrc{o, d->C}; p1.nsrc = 1; p1.Ci = d->C;
+  p1.seg[0] = PwSeg{(const float*)in[7], (const float*)in[8], d->C, eC, hpre}; p1.nseg = 1; p1.Co = eC;
+  p1.pro = PRO_AFFINE; p1.pro_a = aff_a; p1.pro_c = aff_c; p1.pro_bstride = d->C;
+  VX_TRY(pw_forward(pb, st));
+  // y = o + Dropout(W2 GELU(hpre) + b2)
+  PwBatch pb2{};
+  pb2.nprob = 1; pb2.B = d->B; pb2.S = S;
+  PwProblem& p2 = pb2.p[0];
+  p2.src[0] = PwSrc{hpre, eC}; p2.nsrc = 1; p2.Ci = eC;
+  p2.seg[0] = PwSeg{(const float*)in[9], (const float*)in[10], eC, d->C, y}; p2.nseg = 1; p2.Co = d->C;
+  p2.pro = PRO_GELU;
+  if (d->training && d->drop_p > 0.f) { p2.drop_p = d->drop_p; p2.seed = d->seed; p2.site = 1; }
+  p2.res = o; p2.res_scale = 1.f;
+  VX_TRY(pw_forward(pb2, st));
+  return VX_OK;
+}
+
+extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* const* out, void* workspace,
+                          size_t workspace_bytes, vx_stream_t stream) {
+  JlcLayout L;
+  VX_TRY(jlc_layout(d, L));
+  if (!workspace || workspace_bytes < L.total) { set_error("jlc_bwd: workspace %zu < %zu", workspace_bytes, L.total); return VX_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const int CG = d->C / d->groups, eC = d->expansion * d->C, C = d->C;
+  const int rows = (int)L.rows, S = (int)L.S;
+  const float* dy = (const float*)in[0];
+  const float* x = (const float*)in[1];
+  const float* z = (const float*)in[2];
+  const float* o = (const float*)in[3];
+  const float* hpre = (const float*)in[4];
+  const float* stats = (const float*)in[5];
+  const float* w1 = (const float*)in[6];
+  const float* w3 = (const float*)in[7];
+  const float* w5 = (const float*)in[8];
+  const float* fw1 = (const float*)in[9];
+  const float* fw2 = (const float*)in[11];
+  float* dx = (float*)out[0];
+  float* dw1 = (float*)out[1]; float* db1 = (float*)out[2];
+  float* dw3 = (float*)out[3]; float* db3 = (float*)out[4];
+  float* dw5 = (float*)out[5]; float* db5 = (float*)out[6];
+  float* dfw1 = (float*)out[7]; float* dfb1 = (float*)out[8];
+  float* dfw2 = (float*)out[9]; float* dfb2 = (float*)out[10];
+  float* aff_a = (float*)(ws + L.off_a);
+  float* aff_c = (float*)(ws + L.off_c);
+  float* dh = (float*)(ws + L.off_dh);
+  float* dohat = (float*)(ws + L.off_dohat);
+  float* dO = (float*)(ws + L.off_dO);
+  float* gz = (float*)(ws + L.off_gz);
+  float* acc = (float*)(ws + L.off_acc);
+  float* acc2 = (float*)(ws + L.off_acc2);
+  const float* stats_o = stats + (size_t)2 * 3 * rows;
+  const bool drop = d->training && d->drop_p > 0.f;
+
+  cudaMemsetAsync(acc, 0, sizeof(float) * rows * 2, st);
+  cudaMemsetAsync(acc2, 0, sizeof(float) * 3 * rows * 2, st);
+  cudaMemsetAsync(dw1, 0, sizeof(float) * (size_t)C * CG, st);
+  cudaMemsetAsync(dw3, 0, sizeof(float) * (size_t)C * CG * 27, st);
+  cudaMemsetAsync(dw5, 0, sizeof(float) * (size_t)C * CG * 125, st);
+  cudaMemsetAsync(db1, 0, sizeof(float) * C, st);
+  cudaMemsetAsync(db3, 0, sizeof(float) * C, st);
+  cudaMemsetAsync(db5, 0, sizeof(float) * C, st);
+  cudaMemsetAsync(dfw1, 0, sizeof(float) * (size_t)eC * C, st);
+  cudaMemsetAsync(dfb1, 0, sizeof(float) * eC, st);
+  cudaMemsetAsync(dfw2, 0, sizeof(float) * (size_t)eC * C, st);
+  cudaMemsetAsync(dfb2, 0, sizeof(float) * C, st);
+  VX_TRY(stats_to_affine(stats_o, aff_a, aff_c, rows, st));
+
+  // dh = (W2^T (dy * mask)) * GELU'(hpre)
+  {
+    PwBatch pb{}; pb.nprob = 1; pb.B = d->B; pb.S = S;
+    PwProblem& p = pb.p[0];
+    p.src[0] = PwSrc{dy, C}; p.nsrc = 1; p.Ci = C;
+    p.seg[0] = PwSeg{fw2, nullptr, eC, C, dh}; p.nseg = 1; p.Co = eC; p.transposed = 1;
+    if (drop) { p.pro = PRO_DROPOUT; p.pro_drop_p = d->drop_p; p.pro_seed = d->seed; p.pro_site = 1; }
+    p.mulgrad = hpre;
+    VX_TRY(pw_forward(pb, st));
+  }
+  // dohat = W1^T dh
+  {
+    PwBatch pb{}; pb.nprob = 1; pb.B = d->B; pb.S = S;
+    PwProblem& p = pb.p[0];
+    p.src[0] = PwSrc{dh, eC}; p.nsrc = 1; p.Ci = eC;
+    p.seg[0] = PwSeg{fw1, nullptr, C, eC, dohat}; p.nseg = 1; p.Co = C; p.transposed = 1;
+    VX_TRY(pw_forward(pb, st));
+  }
+  // dW2 = (dy*mask) GELU(hpre)^T ; dW1 = dh IN(o)^T
+  {
+    WgBatch wb{}; wb.nprob = 2; wb.B = d->B; wb.S = S;
+    WgProblem& a = wb.p[0];
+    a.dY = dy; a.Co = C; a.src[0] = PwSrc{hpre, eC}; a.nsrc = 1; a.Ci = eC; a.xpro = PRO_GELU;
+    if (drop) { a.y_drop_p = d->drop_p; a.y_seed = d->seed; a.y_site = 1; }
+    a.dW = dfw2; a.ld = eC; a.db = dfb2;
+    WgProblem& b2 = wb.p[1];
+    b2.dY = dh; b2.Co = eC; b2.src[0] = PwSrc{o, C}; b2.nsrc = 1; b2.Ci = C; b2.xpro = PRO_AFFINE;
+    b2.xa = aff_a; b2.xc = aff_c; b2.x_bstride = C;
+    b2.dW = dfw1; b2.ld = C; b2.db = dfb1;
+    VX_TRY(pw_wgrad(wb, st));
+  }
+  VX_LAUNCH(jlc_bwd_a_kernel, dim3(L.nchunk, rows), dim3(256), 0, st, (const float*)dohat, o, stats_o, acc, S, L.chunk);
+  VX_TRY(check_launch("jlc_bwd_a_kernel"));
+  VX_LAUNCH(jlc_bwd_b_kernel, dim3(L.nchunk, rows), dim3(256), 0, st, dy, (const float*)dohat, o, z, stats,
+            (const float*)acc, dO, acc2, rows, S, L.chunk);
+  VX_TRY(check_launch("jlc_bwd_b_kernel"));
+  VX_LAUNCH(jlc_bwd_c_kernel, dim3(cdiv(S, 1024), rows), dim3(256), 0, st, (const float*)dO, z, stats,
+            (const float*)acc2, gz, rows, S);
+  VX_TRY(check_launch("jlc_bwd_c_kernel"));
+
+  ConvDgradArgs G{};
+  G.gz = gz; G.dO = dO; G.w1 = w1; G.w3 = w3; G.w5 = w5; G.dx = dx;
+  G.B = d->B; G.C = C; G.D = d->D; G.H = d->H; G.W = d->W; G.t = L.tf;
+  if (CG == 4) VX_TRY(launch_conv_dgrad<4>(G, d->groups, st));
+  else if (CG == 8) VX_TRY(launch_conv_dgrad<8>(G, d->groups, st));
+  else VX_TRY(launch_conv_dgrad<16>(G, d->groups, st));
+
+  ConvWgradArgs Wg{};
+  Wg.x = x; Wg.gz = gz; Wg.dw1 = dw1; Wg.db1 = db1; Wg.dw3 = dw3; Wg.db3 = db3; Wg.dw5 = dw5; Wg.db5 = db5;
+  Wg.B = d->B; Wg.C = C; Wg.D = d->D; Wg.H = d->H; Wg.W = d->W; Wg.t = L.tw;
+  if (CG == 4) VX_TRY(launch_conv_wgrad<4>(Wg, d->groups, st));
+  else if (CG == 8) VX_TRY(launch_conv_wgrad<8>(Wg, d->groups, st));
+  else VX_TRY(launch_conv_wgrad<16>(Wg, d->groups, st));
+  return VX_OK;
+}

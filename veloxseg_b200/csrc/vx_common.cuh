@@ -1,0 +1,114 @@
+// Shared device helpers for libveloxseg_sm100.  sm_100a only.
+//
+// VX_EMU is a *test-only* build mode (tools/emu): the same kernel sources are compiled by g++ against a
+// thread-per-lane CPU shim so indexing logic can be checked in a container that has no GPU.  The product
+// library is never built with VX_EMU and has no CPU path.
+#pragma once
+#ifdef VX_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+#include <stddef.h>
+#include <math.h>
+
+#include "../../include/veloxseg_abi.h"
+
+#ifdef VX_EMU
+#define VX_LAUNCH(kern, grid, block, smem, stream, ...)                                   \
+  do { auto _k = kern; vx_emu::launch(_k, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__); } while (0)
+#define VX_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(vx_emu::dyn_smem())
+#define VX_SET_SMEM(kern, bytes) do { } while (0)
+#else
+#define VX_LAUNCH(kern, grid, block, smem, stream, ...)                                   \
+  do { auto _k = kern; _k<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); } while (0)
+#define VX_DYN_SMEM(type, name)                                                           \
+  extern __shared__ __align__(16) unsigned char vx_dsm_[];                                \
+  type* name = reinterpret_cast<type*>(vx_dsm_)
+#define VX_SET_SMEM(kern, bytes)                                                          \
+  do { auto _k = kern; if ((bytes) > 48 * 1024)                                           \
+         cudaFuncSetAttribute(_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); } while (0)
+#endif
+
+#define VX_DEV __device__ __forceinline__
+
+namespace vx {
+
+constexpr int kSMs = 148;
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);   // cudaGetLastError -> vx_status
+
+VX_DEV float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// d/dx GELU(x) = Phi(x) + x * phi(x)
+VX_DEV float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+VX_DEV float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+VX_DEV float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum of up to 32 warps; every thread gets the result.  `red` is >= 33 floats of shared memory.
+VX_DEV float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) { t = warp_sum(t); if (lane == 0) red[32] = t; }
+  __syncthreads();
+  return red[32];
+}
+
+// Counter-based RNG for dropout masks (Philox-4x32-10).  Keyed by (seed, element index): forward and backward
+// regenerate the same keep/drop decision without storing a mask.
+VX_DEV uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+VX_DEV uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint32_t ctr_hi) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = ctr_hi, c3 = 0x5eed5eedu;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  uint4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3; return o;
+}
+// keep-scale for element `idx` of dropout site `site`: 0 (dropped) or 1/(1-p).
+VX_DEV float dropout_scale(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep) {
+  const uint4 r = philox4x32(seed, idx >> 2, site);
+  const uint32_t sel = (uint32_t)(idx & 3);
+  const uint32_t bits = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
+  const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);      // [0,1)
+  return u < p ? 0.f : inv_keep;
+}
+
+// mean / rstd from partial sums laid out [row][npart][2] (sum, sumsq); n = element count behind the full row.
+VX_DEV void finalize_stats(const float* __restrict__ part, int row, int npart, float n, float eps,
+                           float& mean, float& rstd) {
+  double s = 0.0, q = 0.0;
+  const float* p = part + (size_t)row * npart * 2;
+  for (int i = 0; i < npart; ++i) { s += (double)p[2 * i]; q += (double)p[2 * i + 1]; }
+  const double m = s / (double)n;
+  double var = q / (double)n - m * m;
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace vx

@@ -1,0 +1,76 @@
+// Internal host-side launchers shared by the op translation units of libveloxseg_sm100.
+#pragma once
+#include "vx_common.cuh"
+
+namespace vx {
+
+// ---------------------------------------------------------------------------------------------------
+// Channel contraction ("1x1x1 conv") over NCDHW:  Y[b,co,s] = epi( sum_ci W[co,ci] * pro(X[b,ci,s]) + bias[co] )
+// ---------------------------------------------------------------------------------------------------
+enum { PRO_NONE = 0, PRO_AFFINE = 1, PRO_GELU = 2, PRO_DROPOUT = 3 };
+
+struct PwSrc { const float* ptr; int C; };                 // input segment (B, C, S)
+struct PwSeg { const float* W; const float* bias; int ld; int n; float* out; };
+
+struct PwProblem {
+  PwSrc src[4]; int nsrc; int Ci;
+  // forward orientation: segments split the OUTPUT channels; seg.W is (n, Ci) with row stride ld, each segment
+  // writes its own tensor seg.out (B, n, S).
+  // transposed orientation: segments split the INPUT channels (same order as src); seg.W is (n, Co) with row
+  // stride ld and the logical weight is W^T; the single output is seg[0].out (B, Co, S).
+  PwSeg seg[3]; int nseg; int Co;
+  int transposed;
+  int pro;                        // PRO_*
+  const float* pro_a; const float* pro_c; int pro_bstride;   // PRO_AFFINE: x*a[b*bstride+ci] + c[b*bstride+ci]
+  float pro_drop_p; uint64_t pro_seed; uint32_t pro_site;    // PRO_DROPOUT (mask indexed like the input tensor)
+  int act;                        // 1: GELU on the output
+  const float* mulgrad;           // if set: out *= GELU'(mulgrad[b,co,s])
+  float drop_p; uint64_t seed; uint32_t site;                // dropout on (acc + bias), before the residual
+  const float* res; float res_scale;                         // out += res_scale * res[b,co,s]
+  const float* res2;                                         // out += res2[b,co,s]
+};
+
+struct PwBatch { PwProblem p[VX_MAX_MODAL]; int nprob; int B; int S; };
+
+int pw_forward(const PwBatch& batch, cudaStream_t stream);
+
+// dW[co, ci] += sum_{b,s} ypro(dY[b,co,s]) * xpro(X[b,ci,s]);   db[co] += sum ypro(dY)
+struct WgProblem {
+  const float* dY; int Co;
+  PwSrc src[4]; int nsrc; int Ci;
+  int xpro; const float* xa; const float* xc; int x_bstride;  // PRO_NONE / PRO_AFFINE / PRO_GELU on X
+  float y_drop_p; uint64_t y_seed; uint32_t y_site;           // dropout mask on dY (0 disables)
+  float* dW; int ld;                                          // accumulated with atomics: caller zeroes
+  float* db;                                                  // may be null
+};
+struct WgBatch { WgProblem p[VX_MAX_MODAL * 3]; int nprob; int B; int S; };
+int pw_wgrad(const WgBatch& batch, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------------
+// norms
+// ---------------------------------------------------------------------------------------------------
+// InstanceNorm rows: y = (x-mean)*rstd [+ addend]; stats[row] = (mean, rstd)
+int inorm_rows_fwd(const float* x, const float* addend, float* y, float* stats, int rows, int S, float eps,
+                   cudaStream_t stream);
+// dx = rstd*(dy - mean(dy) - xhat*mean(dy*xhat)) [+ dx_add]
+int inorm_rows_bwd(const float* dy, const float* x, const float* stats, const float* dx_add, float* dx, int rows,
+                   int S, cudaStream_t stream);
+// per-(b,c) affine (a = rstd, c = -mean*rstd) from (mean, rstd) stats
+int stats_to_affine(const float* stats, float* a, float* c, int rows, cudaStream_t stream);
+
+// channel-first LayerNorm core: xhat = (x-mean_c)*rstd ; rstd (B,S).  Batched over up to VX_MAX_MODAL tensors.
+struct LnBatch {
+  const float* x[VX_MAX_MODAL]; float* xhat[VX_MAX_MODAL]; float* rstd[VX_MAX_MODAL];
+  int n; int B; int C; int S; float eps;
+};
+int ln_forward(const LnBatch& b, cudaStream_t stream);
+// g = gamma*dout ; dx = rstd*(g - mean_c(g) - xhat*mean_c(g*xhat)) + dx_add ; dgamma += sum dout*xhat ; dbeta += sum dout
+struct LnBwdBatch {
+  const float* dout[VX_MAX_MODAL]; const float* xhat[VX_MAX_MODAL]; const float* rstd[VX_MAX_MODAL];
+  const float* gamma[VX_MAX_MODAL]; const float* dx_add[VX_MAX_MODAL]; float dx_add_scale;
+  float* dx[VX_MAX_MODAL]; float* dgamma[VX_MAX_MODAL]; float* dbeta[VX_MAX_MODAL];
+  int n; int B; int C; int S;
+};
+int ln_backward(const LnBwdBatch& b, cudaStream_t stream);
+
+}  // namespace vx
