@@ -50,15 +50,15 @@ def test_jlc_dropout_consistency(emu):
     x = torch.randn(1, C, 4, 4, 8)
     params = jlc_params(C, groups, e, seed=5)
     y0, z, o, hpre, stats = ops.jlc_fwd_raw(emu, 0, x, params, groups, e, 0.0, False, 0)
-    y1, *_ = ops.jlc_fwd_raw(emu, 0, x, params, groups, e, 0.5, True, 1234)
+    y1, _, o1, *_ = ops.jlc_fwd_raw(emu, 0, x, params, groups, e, 0.5, True, 1234)
     y2, *_ = ops.jlc_fwd_raw(emu, 0, x, params, groups, e, 0.5, True, 1234)
     assert torch.allclose(y1, y2, rtol=1e-5, atol=1e-6)
     # y = o + mask*2*(W2 h + b2): elements are either o (dropped) or o + 2*(y0 - o)
-    d0, d1 = (y0 - o), (y1 - o)
-    dropped = d1.abs() < 1e-12
+    d0, d1 = (y0 - o), (y1 - o1)
+    dropped = d1 == 0
     frac = dropped.float().mean().item()
     assert 0.35 < frac < 0.65, frac
-    assert torch.allclose(d1[~dropped], 2 * d0[~dropped], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(d1[~dropped], 2 * d0[~dropped], rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.parametrize("chs,Co,S,B,addend", [((16, 16), 16, (5, 6, 7), 2, True), ((8,), 24, (4, 4, 4), 1, False),
@@ -127,3 +127,63 @@ def test_inorm_gram_sdkt_lnpw(emu):
     got = ops.lnpw_bwd_raw(emu, 0, dy, xhat, rstd, lw, lb, W)
     for i, (g, r) in enumerate(zip(got, gr)):
         assert close(g, r, rtol=2e-4, atol=2e-5), (i, rel_err(g, r))
+
+
+PWA_CASES = [
+    # size, C, min_big, min_small, heads, min_dim_head, M, e, B
+    ((6, 6, 6), 8, [3, 3, 3], [1, 1, 1], 1, 4, 2, 2, 1),
+    ((8, 8, 4), 16, [4, 4, 2], [1, 1, 1], 2, 4, 2, 2, 1),
+    ((12, 12, 12), 16, [3, 3, 3], [1, 1, 1], 1, 4, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("size,C,mb,ms,heads,mdh,M,e,B", PWA_CASES)
+def test_pwa_gather_bit_exact(emu, size, C, mb, ms, heads, mdh, M, e, B):
+    from veloxseg_b200 import ops
+    O = _oracle()
+    geo = O.pwa_geometry(size, C, mb, ms, 2, heads, mdh)
+    torch.manual_seed(0)
+    x = torch.randn(B, geo["cv"], *size)
+    tok, arg = ops.pwa_gather_raw(emu, 0, x, geo)
+    ref, _, _ = O.gather_tokens(x, heads, geo["bws"], geo["sws"])
+    assert torch.equal(tok, ref)
+    # arg-max voxel indices must point at the values that were gathered
+    flat = x.reshape(B, geo["cv"], -1)
+    cper = geo["cv"] // (heads * len(geo["bws"]))
+    Ns_off = 0
+    for j, bw in enumerate(geo["bws"]):
+        Nj = (size[0] // bw[0]) * (size[1] // bw[1]) * (size[2] // bw[2])
+        for h in range(heads):
+            for c in range(cper):
+                ch = (j * heads + h) * cper + c
+                a = arg[:, h, Ns_off:Ns_off + Nj, :, c].reshape(B, -1).long()
+                v = torch.gather(flat[:, ch], 1, a)
+                assert torch.equal(v, tok[:, h, Ns_off:Ns_off + Nj, :, c].reshape(B, -1))
+        Ns_off += Nj
+
+
+@pytest.mark.parametrize("size,C,mb,ms,heads,mdh,M,e,B", PWA_CASES)
+def test_pwa_block(emu, size, C, mb, ms, heads, mdh, M, e, B):
+    from tests._util import pwa_params
+    from veloxseg_b200 import ops
+    O = _oracle()
+    geo = O.pwa_geometry(size, C, mb, ms, 2, heads, mdh)
+    torch.manual_seed(1)
+    xs = [torch.randn(B, C, *size) for _ in range(M)]
+    flat, pd, table, index = pwa_params(M, C, geo, e, seed=2)
+    zs, saved = ops.pwa_block_fwd_raw(emu, 0, xs, flat, table, index, geo, e)
+    xr = [x.clone().requires_grad_(True) for x in xs]
+    pr = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in pd.items()}
+    zr = O.pwa_block(xr, pr, "", geo)
+    for m in range(M):
+        assert rel_err(zs[m], zr[m]) < 2e-5, (m, rel_err(zs[m], zr[m]))
+    dzs = [torch.randn_like(z) for z in zs]
+    from tests._util import PWA_PARAM_NAMES
+    plist = [pr[n.format(m=m)] for m in range(M) for n in PWA_PARAM_NAMES]
+    tab = pr["attn.position_embedding.relative_position_bias_table"]
+    grads = torch.autograd.grad(zr, xr + plist + [tab], dzs)
+    dxs, dps, dtable = ops.pwa_block_bwd_raw(emu, 0, dzs, xs, flat, table, index, saved, geo, e)
+    got = list(dxs) + list(dps) + [dtable]
+    names = [f"dx{m}" for m in range(M)] + [n.format(m=m) for m in range(M) for n in PWA_PARAM_NAMES] + ["table"]
+    bad = [(n, rel_err(g, r)) for n, g, r in zip(names, got, grads) if not close(g, r, rtol=3e-4, atol=2e-5)]
+    assert not bad, bad

@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(PW_THREADS) pw_kernel(const __grid_constant__ 
 #pragma unroll
   for (int j = 0; j < PW_CO; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
 
-  const float pinv = P.pro == PRO_DROPOUT ? 1.0f / (1.0f - P.pro_drop_p) : 1.f;
+  const bool pro_drop = P.pro == PRO_DROPOUT || P.pro == PRO_GELU_DROPOUT;
+  const float pinv = pro_drop ? 1.0f / (1.0f - P.pro_drop_p) : 1.f;
   int cg = 0;
   for (int s = 0; s < P.nsrc; ++s) {
     const int Cs = P.src[s].C;
@@ -86,8 +87,8 @@ __global__ void __launch_bounds__(PW_THREADS) pw_kernel(const __grid_constant__ 
     for (int c = 0; c < Cs; ++c, ++cg) {
       float x0 = ok0 ? __ldg(xp + (size_t)c * S + v0) : 0.f;
       float x1 = ok1 ? __ldg(xp + (size_t)c * S + v1) : 0.f;
-      if (P.pro == PRO_GELU) { x0 = gelu_f(x0); x1 = gelu_f(x1); }
-      else if (P.pro == PRO_DROPOUT) {
+      if (P.pro == PRO_GELU || P.pro == PRO_GELU_DROPOUT) { x0 = gelu_f(x0); x1 = gelu_f(x1); }
+      if (pro_drop) {
         const uint64_t base = ((uint64_t)b * Ci + cg) * (uint64_t)S;
         x0 *= dropout_scale(P.pro_seed, P.pro_site, base + v0, P.pro_drop_p, pinv);
         x1 *= dropout_scale(P.pro_seed, P.pro_site, base + v1, P.pro_drop_p, pinv);
@@ -206,6 +207,9 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_kernel(const __grid_const
             val = fmaf(val, P.xa[k], P.xc[k]);
           } else if (P.xpro == PRO_GELU) {
             val = gelu_f(val);
+          } else if (P.xpro == PRO_GELU_DROPOUT) {
+            val = gelu_f(val) * dropout_scale(P.x_seed, P.x_site, ((uint64_t)b * Ci + cg0 + c) * (uint64_t)S + gv, P.x_drop_p,
+                                              1.0f / (1.0f - P.x_drop_p));
           }
         }
         sX[v * CiP + cg0 + c] = val;

@@ -1,8 +1,948 @@
-// placeholder until the PWA kernels land
+// PWA block (reference: model/components/PWA.py:329-379 + 433-439, attention_utils.py:29-71) for sm_100a, fp32.
+//
+// Forward pipeline (M modality streams processed together, one launch per stage):
+//   ln_forward        xhat = LN(x)                                    (pointwise.cu)
+//   pw_forward        q,k,v = [Wq;Wk;Wv] (g*xhat + b) + bias          (one pass over xhat for all three)
+//   pwa_gather        window partition + small-window max-pool -> tokens (B, h, Ns, M*l, c), arg-max kept
+//   pwa_attn_fwd      per window: S = QK^T/sqrt(c) + bias, online softmax, (dropout), O = PV; scores never leave
+//                     the SM (K/V of the window live in shared memory, one thread owns a query row)
+//   pwa_scatter       per-window trilinear (align_corners) up-sampling of tokens back to NCDHW
+//   pw_forward        y = 2x + Drop(Wmix a + b)                       (double residual of PWA.py:377,436)
+//   ln_forward, pw_forward x2   z = y + Drop(W2 Drop(GELU(W1 LN(y) + b1)) + b2)
+// Backward mirrors it; softmax is recomputed from the saved row log-sum-exp (no L x L tensor is ever stored).
 #include "vx_kernels.h"
+
+#ifdef VX_EMU
+#define __grid_constant__
+#endif
+
+#define VX_TRY(expr) do { int _rc = (expr); if (_rc != VX_OK) return _rc; } while (0)
+
+namespace vx {
+static inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+struct PwaGeo {
+  int B, M, D, H, W, S, heads, nb;
+  int big[VX_MAX_SCALES][3], small[VX_MAX_SCALES][3];
+  int Nw[VX_MAX_SCALES][3];   // windows per axis
+  int Noff[VX_MAX_SCALES];    // first window index of the scale
+  int vol[VX_MAX_SCALES];     // voxels per small window
+  int Ns, n[3], l, L;
+};
+
+static int make_geo(const vx_pwa_desc* d, PwaGeo& G) {
+  if (!d || d->B <= 0 || d->M <= 0 || d->M > VX_MAX_MODAL || d->C <= 0 || d->heads <= 0 || d->n_scales <= 0 ||
+      d->n_scales > VX_MAX_SCALES) { set_error("pwa: bad descriptor"); return VX_ERR_BAD_DESC; }
+  G.B = d->B; G.M = d->M; G.D = d->D; G.H = d->H; G.W = d->W; G.S = d->D * d->H * d->W;
+  G.heads = d->heads; G.nb = d->n_scales;
+  const int dims[3] = {d->D, d->H, d->W};
+  int off = 0;
+  for (int j = 0; j < G.nb; ++j) {
+    int vol = 1;
+    for (int a = 0; a < 3; ++a) {
+      G.big[j][a] = d->big[j][a]; G.small[j][a] = d->small[j][a];
+      if (G.big[j][a] <= 0 || G.small[j][a] <= 0 || G.big[j][a] % G.small[j][a] || dims[a] % G.big[j][a]) {
+        set_error("pwa: window %d axis %d (big %d small %d) does not tile extent %d", j, a, G.big[j][a], G.small[j][a], dims[a]);
+        return VX_ERR_BAD_DESC;
+      }
+      G.Nw[j][a] = dims[a] / G.big[j][a];
+      const int na = G.big[j][a] / G.small[j][a];
+      if (j == 0) G.n[a] = na;
+      else if (G.n[a] != na) { set_error("pwa: scales disagree on tokens per window"); return VX_ERR_BAD_DESC; }
+      vol *= G.small[j][a];
+    }
+    G.vol[j] = vol;
+    G.Noff[j] = off;
+    off += G.Nw[j][0] * G.Nw[j][1] * G.Nw[j][2];
+  }
+  G.Ns = off;
+  G.l = G.n[0] * G.n[1] * G.n[2];
+  G.L = G.l * G.M;
+  if (d->c_qk % (G.nb * G.heads) || d->c_v % (G.nb * G.heads)) { set_error("pwa: channels do not split into scales x heads"); return VX_ERR_BAD_DESC; }
+  return VX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// gather: tokens + arg-max.  grid (blocks, scale, kind*M); small windows of >= 32 voxels use a warp per element.
+// ---------------------------------------------------------------------------------------------------
+struct GatherArgs {
+  const float* src[3][VX_MAX_MODAL];   // [kind][m] (B, Ct, S)
+  float* tok[3];                       // (B, h, Ns, L, cper)
+  int* arg[3];
+  int Ct[3], cper[3];
+  int nkind;
+};
+
+VX_DEV void token_coords(const PwaGeo& G, int j, int Nloc, int t, int& z0, int& y0, int& x0) {
+  const int wx = Nloc % G.Nw[j][2], wy = (Nloc / G.Nw[j][2]) % G.Nw[j][1], wz = Nloc / (G.Nw[j][2] * G.Nw[j][1]);
+  const int c = t % G.n[2], b = (t / G.n[2]) % G.n[1], a = t / (G.n[2] * G.n[1]);
+  z0 = wz * G.big[j][0] + a * G.small[j][0];
+  y0 = wy * G.big[j][1] + b * G.small[j][1];
+  x0 = wx * G.big[j][2] + c * G.small[j][2];
+}
+
+__global__ void __launch_bounds__(256) pwa_gather_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ GatherArgs A) {
+  const int j = blockIdx.y;
+  const int kind = blockIdx.z / G.M, m = blockIdx.z % G.M;
+  const int cper = A.cper[kind], Ct = A.Ct[kind];
+  const int Nj = G.Nw[j][0] * G.Nw[j][1] * G.Nw[j][2];
+  const long long total = (long long)G.B * G.heads * Nj * G.l * cper;
+  const bool warp_mode = G.vol[j] >= 32;
+  const int lane = threadIdx.x & 31;
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (warp_mode) e >>= 5;
+  const long long stride = warp_mode ? ((long long)gridDim.x * blockDim.x) >> 5 : (long long)gridDim.x * blockDim.x;
+  const float* src = A.src[kind][m];
+  const int s0 = G.small[j][0], s1 = G.small[j][1], s2 = G.small[j][2];
+  for (; e < total; e += stride) {
+    const int c = (int)(e % cper);
+    const int t = (int)((e / cper) % G.l);
+    const int Nloc = (int)((e / ((long long)cper * G.l)) % Nj);
+    const int head = (int)((e / ((long long)cper * G.l * Nj)) % G.heads);
+    const int b = (int)(e / ((long long)cper * G.l * Nj * G.heads));
+    int z0, y0, x0;
+    token_coords(G, j, Nloc, t, z0, y0, x0);
+    const int ch = (j * G.heads + head) * cper + c;
+    const float* p = src + ((size_t)b * Ct + ch) * G.S;
+    float best = -INFINITY;
+    int bidx = (z0 * G.H + y0) * G.W + x0;
+    if (!warp_mode) {
+      for (int dz = 0; dz < s0; ++dz)
+        for (int dy = 0; dy < s1; ++dy)
+          for (int dx = 0; dx < s2; ++dx) {
+            const int idx = ((z0 + dz) * G.H + (y0 + dy)) * G.W + x0 + dx;
+            const float v = __ldg(p + idx);
+            if (v > best) { best = v; bidx = idx; }
+          }
+    } else {
+      int myidx = 0x7fffffff;
+      for (int q = lane; q < G.vol[j]; q += 32) {
+        const int dx = q % s2, dy = (q / s2) % s1, dz = q / (s2 * s1);
+        const int idx = ((z0 + dz) * G.H + (y0 + dy)) * G.W + x0 + dx;
+        const float v = __ldg(p + idx);
+        if (v > best) { best = v; myidx = idx; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, myidx, o);
+        if (ov > best || (ov == best && oi < myidx)) { best = ov; myidx = oi; }
+      }
+      bidx = myidx;
+    }
+    if (!warp_mode || lane == 0) {
+      const size_t o = ((((size_t)b * G.heads + head) * G.Ns + G.Noff[j] + Nloc) * G.L + (size_t)m * G.l + t) * cper + c;
+      A.tok[kind][o] = best;
+      if (A.arg[kind]) A.arg[kind][o] = bidx;
+    }
+  }
+}
+
+static int launch_gather(const PwaGeo& G, const GatherArgs& A, cudaStream_t st) {
+  long long maxtotal = 0;
+  for (int j = 0; j < G.nb; ++j)
+    for (int k = 0; k < A.nkind; ++k) {
+      long long t = (long long)G.B * G.heads * G.Nw[j][0] * G.Nw[j][1] * G.Nw[j][2] * G.l * A.cper[k];
+      if (G.vol[j] >= 32) t *= 32;
+      maxtotal = t > maxtotal ? t : maxtotal;
+    }
+  int blocks = cdiv(maxtotal, 256);
+  if (blocks > kSMs * 16) blocks = kSMs * 16;
+  if (blocks < 1) blocks = 1;
+  VX_LAUNCH(pwa_gather_kernel, dim3(blocks, G.nb, A.nkind * G.M), dim3(256), 0, st, G, A);
+  return check_launch("pwa_gather_kernel");
+}
+
+// backward of the gather: full-resolution gradient; a voxel receives its token's gradient iff it was the arg-max.
+struct GatherBwdArgs {
+  const float* dtok[3]; const int* arg[3];
+  float* dst[3][VX_MAX_MODAL];   // (B, Ct, S)
+  int Ct[3], cper[3];
+};
+
+__global__ void __launch_bounds__(256) pwa_gather_bwd_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ GatherBwdArgs A) {
+  const int kind = blockIdx.z / G.M, m = blockIdx.z % G.M;
+  const int cper = A.cper[kind], Ct = A.Ct[kind];
+  const long long total = (long long)G.B * Ct * G.S;
+  float* dst = A.dst[kind][m];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int idx = (int)(e % G.S);
+    const int ch = (int)((e / G.S) % Ct);
+    const int b = (int)(e / ((long long)G.S * Ct));
+    const int c = ch % cper, head = (ch / cper) % G.heads, j = ch / (cper * G.heads);
+    const int x = idx % G.W, y = (idx / G.W) % G.H, z = idx / (G.W * G.H);
+    const int wz = z / G.big[j][0], wy = y / G.big[j][1], wx = x / G.big[j][2];
+    const int a = (z % G.big[j][0]) / G.small[j][0], bb = (y % G.big[j][1]) / G.small[j][1], cc = (x % G.big[j][2]) / G.small[j][2];
+    const int Nloc = (wz * G.Nw[j][1] + wy) * G.Nw[j][2] + wx;
+    const int t = (a * G.n[1] + bb) * G.n[2] + cc;
+    const size_t o = ((((size_t)b * G.heads + head) * G.Ns + G.Noff[j] + Nloc) * G.L + (size_t)m * G.l + t) * cper + c;
+    float g = 0.f;
+    if (G.vol[j] == 1 || A.arg[kind][o] == idx) g = A.dtok[kind][o];
+    dst[e] = g;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// relative-position bias:  biasT[h][tk][tq] = table[index[tq][tk]][h]      (attention_utils.py:120-125)
+// ---------------------------------------------------------------------------------------------------
+__global__ void pwa_bias_kernel(const float* __restrict__ table, const long long* __restrict__ index,
+                                float* __restrict__ biasT, int heads, int l) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= heads * l * l) return;
+  const int tq = e % l, tk = (e / l) % l, h = e / (l * l);
+  biasT[e] = table[(size_t)index[(size_t)tq * l + tk] * heads + h];
+}
+
+// dtable[index[tq][tk]][h] += dbiasT[h][tk][tq]
+__global__ void pwa_bias_bwd_kernel(const float* __restrict__ dbiasT, const long long* __restrict__ index,
+                                    float* __restrict__ dtable, int heads, int l) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= heads * l * l) return;
+  const int tq = e % l, tk = (e / l) % l, h = e / (l * l);
+  atomicAdd(dtable + (size_t)index[(size_t)tq * l + tk] * heads + h, dbiasT[e]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// attention
+// ---------------------------------------------------------------------------------------------------
+struct AttnArgs {
+  const float* Q; const float* K; const float* V; const float* biasT;
+  float* O; float* lse;
+  // backward
+  const float* dO; float* dQ; float* dK; float* dV; float* dbiasT;
+  int B, heads, Ns, L, l;
+  float scale, drop_p;
+  uint64_t seed;
+};
+
+constexpr int ATT_THREADS = 128;
+constexpr uint32_t ATT_SITE = 7;
+
+// keep-scales of 4 consecutive keys of one (window,row): one Philox call per 4 score elements
+VX_DEV void attn_drop4(const AttnArgs& A, size_t row, int k4, float inv_keep, float (&ms)[4]) {
+  const int nk4 = (A.L + 3) >> 2;
+  const uint4 r = philox4x32(A.seed, (uint64_t)row * nk4 + k4, ATT_SITE);
+  const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ms[i] = ((float)(bits[i] >> 8) * (1.0f / 16777216.0f) < A.drop_p) ? 0.f : inv_keep;
+}
+
+template <int CQ, int CV>
+__global__ void __launch_bounds__(ATT_THREADS) pwa_attn_fwd_kernel(const __grid_constant__ AttnArgs A) {
+  const int N = blockIdx.y, bh = blockIdx.z, head = bh % A.heads;
+  const int L = A.L, l = A.l;
+  VX_DYN_SMEM(float, sm);
+  float* Ks = sm;            // [L][CQ]
+  float* Vs = sm + L * CQ;   // [L][CV]
+  const size_t wbase = (size_t)bh * A.Ns + N;
+  const float* Kg = A.K + wbase * L * CQ;
+  const float* Vg = A.V + wbase * L * CV;
+  for (int i = threadIdx.x; i < L * CQ; i += ATT_THREADS) Ks[i] = __ldg(Kg + i);
+  for (int i = threadIdx.x; i < L * CV; i += ATT_THREADS) Vs[i] = __ldg(Vg + i);
+  __syncthreads();
+  const int i = blockIdx.x * ATT_THREADS + threadIdx.x;
+  if (i >= L) return;
+  float q[CQ];
+#pragma unroll
+  for (int c = 0; c < CQ; ++c) q[c] = __ldg(A.Q + (wbase * L + i) * CQ + c) * A.scale;
+  const float* bT = A.biasT + (size_t)head * l * l + (i % l);
+  const bool drop = A.drop_p > 0.f;
+  const float inv_keep = drop ? 1.0f / (1.0f - A.drop_p) : 1.f;
+  const size_t row = wbase * L + i;
+  float mx = -INFINITY, ssum = 0.f;
+  float acc[CV];
+#pragma unroll
+  for (int c = 0; c < CV; ++c) acc[c] = 0.f;
+  for (int k0 = 0; k0 < L; k0 += 4) {
+    float ms[4] = {1.f, 1.f, 1.f, 1.f};
+    if (drop) attn_drop4(A, row, k0 >> 2, inv_keep, ms);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = k0 + kk;
+      if (k >= L) break;
+      float s = __ldg(bT + (size_t)(k % l) * l);
+#pragma unroll
+      for (int c = 0; c < CQ; ++c) s = fmaf(q[c], Ks[k * CQ + c], s);
+      if (s > mx) {
+        const float corr = expf(mx - s);
+        ssum *= corr;
+#pragma unroll
+        for (int c = 0; c < CV; ++c) acc[c] *= corr;
+        mx = s;
+      }
+      const float p = expf(s - mx);
+      ssum += p;
+      const float pm = p * ms[kk];
+#pragma unroll
+      for (int c = 0; c < CV; ++c) acc[c] = fmaf(pm, Vs[k * CV + c], acc[c]);
+    }
+  }
+  const float inv = 1.0f / ssum;
+#pragma unroll
+  for (int c = 0; c < CV; ++c) A.O[row * CV + c] = acc[c] * inv;
+  A.lse[row] = mx + logf(ssum);
+}
+
+template <int CQ, int CV>
+__global__ void __launch_bounds__(ATT_THREADS) pwa_attn_bwd_kernel(const __grid_constant__ AttnArgs A) {
+  const int N = blockIdx.y, bh = blockIdx.z, head = bh % A.heads;
+  const int L = A.L, l = A.l;
+  VX_DYN_SMEM(float, sm);
+  float* Ks = sm;                 // [L][CQ]
+  float* Vs = Ks + L * CQ;        // [L][CV]
+  float* Qs = Vs + L * CV;        // [L][CQ]  (pre-scaled)
+  float* dOs = Qs + L * CQ;       // [L][CV]
+  float* lses = dOs + L * CV;     // [L]
+  float* Dv = lses + L;           // [L]
+  const size_t wbase = (size_t)bh * A.Ns + N;
+  for (int i = threadIdx.x; i < L * CQ; i += ATT_THREADS) {
+    Ks[i] = __ldg(A.K + wbase * L * CQ + i);
+    Qs[i] = __ldg(A.Q + wbase * L * CQ + i) * A.scale;
+  }
+  for (int i = threadIdx.x; i < L * CV; i += ATT_THREADS) {
+    Vs[i] = __ldg(A.V + wbase * L * CV + i);
+    dOs[i] = __ldg(A.dO + wbase * L * CV + i);
+  }
+  for (int i = threadIdx.x; i < L; i += ATT_THREADS) {
+    lses[i] = __ldg(A.lse + wbase * L + i);
+    float d = 0.f;
+    for (int c = 0; c < CV; ++c) d = fmaf(__ldg(A.dO + (wbase * L + i) * CV + c), __ldg(A.O + (wbase * L + i) * CV + c), d);
+    Dv[i] = d;
+  }
+  __syncthreads();
+  const bool drop = A.drop_p > 0.f;
+  const float inv_keep = drop ? 1.0f / (1.0f - A.drop_p) : 1.f;
+  const int r = blockIdx.x * ATT_THREADS + threadIdx.x;
+  if (r >= L) return;
+  const float* bTh = A.biasT + (size_t)head * l * l;
+
+  // phase A: this thread owns query row r -> dQ_r and the bias gradient of its row
+  {
+    float q[CQ], dq[CQ], dO[CV];
+#pragma unroll
+    for (int c = 0; c < CQ; ++c) { q[c] = Qs[r * CQ + c]; dq[c] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < CV; ++c) dO[c] = dOs[r * CV + c];
+    const float lse = lses[r], Dr = Dv[r];
+    const size_t row = wbase * L + r;
+    const int tq = r % l;
+    float* dbrow = A.dbiasT + (size_t)head * l * l + tq;
+    for (int k0 = 0; k0 < L; k0 += 4) {
+      float ms[4] = {1.f, 1.f, 1.f, 1.f};
+      if (drop) attn_drop4(A, row, k0 >> 2, inv_keep, ms);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = k0 + kk;
+        if (k >= L) break;
+        const int tk = k % l;
+        float s = __ldg(bTh + (size_t)tk * l + tq);
+#pragma unroll
+        for (int c = 0; c < CQ; ++c) s = fmaf(q[c], Ks[k * CQ + c], s);
+        const float p = expf(s - lse);
+        float dp = 0.f;
+#pragma unroll
+        for (int c = 0; c < CV; ++c) dp = fmaf(dO[c], Vs[k * CV + c], dp);
+        const float ds = p * (dp * ms[kk] - Dr);
+#pragma unroll
+        for (int c = 0; c < CQ; ++c) dq[c] = fmaf(ds, Ks[k * CQ + c], dq[c]);
+        atomicAdd(dbrow + (size_t)tk * l, ds);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CQ; ++c) A.dQ[row * CQ + c] = dq[c] * A.scale;
+  }
+  // phase B: this thread owns key row r -> dK_r, dV_r
+  {
+    float kx[CQ], dk[CQ], v[CV], dv[CV];
+#pragma unroll
+    for (int c = 0; c < CQ; ++c) { kx[c] = Ks[r * CQ + c]; dk[c] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < CV; ++c) { v[c] = Vs[r * CV + c]; dv[c] = 0.f; }
+    const int tk = r % l;
+    for (int i = 0; i < L; ++i) {
+      float s = __ldg(bTh + (size_t)tk * l + (i % l));
+#pragma unroll
+      for (int c = 0; c < CQ; ++c) s = fmaf(Qs[i * CQ + c], kx[c], s);
+      const float p = expf(s - lses[i]);
+      float msk = 1.f;
+      if (drop) {
+        float ms[4];
+        attn_drop4(A, wbase * L + i, r >> 2, inv_keep, ms);
+        msk = ms[r & 3];
+      }
+      float dp = 0.f;
+#pragma unroll
+      for (int c = 0; c < CV; ++c) dp = fmaf(dOs[i * CV + c], v[c], dp);
+      const float pm = p * msk;
+#pragma unroll
+      for (int c = 0; c < CV; ++c) dv[c] = fmaf(pm, dOs[i * CV + c], dv[c]);
+      const float ds = p * (dp * msk - Dv[i]);
+#pragma unroll
+      for (int c = 0; c < CQ; ++c) dk[c] = fmaf(ds, Qs[i * CQ + c], dk[c]);   // Qs carries the 1/sqrt(c) scale
+    }
+    const size_t row = wbase * L + r;
+#pragma unroll
+    for (int c = 0; c < CQ; ++c) A.dK[row * CQ + c] = dk[c];
+#pragma unroll
+    for (int c = 0; c < CV; ++c) A.dV[row * CV + c] = dv[c];
+  }
+}
+
+template <int CQ, int CV>
+static int launch_attn(const AttnArgs& A, bool bwd, cudaStream_t st) {
+  dim3 grid(cdiv(A.L, ATT_THREADS), A.Ns, A.B * A.heads);
+  if (!bwd) {
+    const size_t smem = sizeof(float) * (size_t)A.L * (CQ + CV);
+    VX_SET_SMEM((pwa_attn_fwd_kernel<CQ, CV>), smem);
+    VX_LAUNCH((pwa_attn_fwd_kernel<CQ, CV>), grid, dim3(ATT_THREADS), smem, st, A);
+    return check_launch("pwa_attn_fwd_kernel");
+  }
+  const size_t smem = sizeof(float) * (size_t)A.L * (2 * CQ + 2 * CV + 2);
+  VX_SET_SMEM((pwa_attn_bwd_kernel<CQ, CV>), smem);
+  VX_LAUNCH((pwa_attn_bwd_kernel<CQ, CV>), grid, dim3(ATT_THREADS), smem, st, A);
+  return check_launch("pwa_attn_bwd_kernel");
+}
+
+static int dispatch_attn(const AttnArgs& A, int cq, int cv, bool bwd, cudaStream_t st) {
+#define VX_ATT(a, b) if (cq == a && cv == b) return launch_attn<a, b>(A, bwd, st)
+  VX_ATT(4, 4); VX_ATT(4, 8); VX_ATT(8, 8); VX_ATT(8, 16); VX_ATT(16, 16); VX_ATT(16, 32);
+#undef VX_ATT
+  set_error("pwa: per-head dims (%d, %d) not instantiated", cq, cv);
+  return VX_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// scatter: tokens -> NCDHW with per-window trilinear up-sampling (align_corners=True), PWA.py:177-200
+// ---------------------------------------------------------------------------------------------------
+VX_DEV void lerp_coef(int p, int n, int out, int& i0, int& i1, float& w1) {
+  // F.interpolate(align_corners=True): src = p * (n-1)/(out-1)
+  if (out <= 1 || n <= 1) { i0 = 0; i1 = 0; w1 = 0.f; return; }
+  const float scale = (float)(n - 1) / (float)(out - 1);
+  const float src = scale * (float)p;
+  i0 = (int)src;
+  if (i0 > n - 1) i0 = n - 1;
+  i1 = i0 < n - 1 ? i0 + 1 : i0;
+  w1 = src - (float)i0;
+}
+
+struct ScatterArgs {
+  const float* tok;               // (B, h, Ns, L, cper)
+  float* dst[VX_MAX_MODAL];       // (B, Ct, S)
+  int Ct, cper;
+};
+
+__global__ void __launch_bounds__(256) pwa_scatter_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ ScatterArgs A) {
+  const int m = blockIdx.z;
+  const int cper = A.cper, Ct = A.Ct;
+  const long long total = (long long)G.B * Ct * G.S;
+  float* dst = A.dst[m];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int idx = (int)(e % G.S);
+    const int ch = (int)((e / G.S) % Ct);
+    const int b = (int)(e / ((long long)G.S * Ct));
+    const int c = ch % cper, head = (ch / cper) % G.heads, j = ch / (cper * G.heads);
+    const int x = idx % G.W, y = (idx / G.W) % G.H, z = idx / (G.W * G.H);
+    const int wz = z / G.big[j][0], wy = y / G.big[j][1], wx = x / G.big[j][2];
+    const int Nloc = (wz * G.Nw[j][1] + wy) * G.Nw[j][2] + wx;
+    const float* tp = A.tok + ((((size_t)b * G.heads + head) * G.Ns + G.Noff[j] + Nloc) * G.L + (size_t)m * G.l) * cper + c;
+    float val;
+    if (G.vol[j] == 1) {
+      const int t = ((z % G.big[j][0]) * G.n[1] + (y % G.big[j][1])) * G.n[2] + (x % G.big[j][2]);
+      val = __ldg(tp + (size_t)t * cper);
+    } else {
+      int a0, a1, b0, b1, c0, c1;
+      float wa, wb, wc;
+      lerp_coef(z % G.big[j][0], G.n[0], G.big[j][0], a0, a1, wa);
+      lerp_coef(y % G.big[j][1], G.n[1], G.big[j][1], b0, b1, wb);
+      lerp_coef(x % G.big[j][2], G.n[2], G.big[j][2], c0, c1, wc);
+      const int n1 = G.n[1], n2 = G.n[2];
+#define VX_T(a, bq, cq_) __ldg(tp + (size_t)(((a) * n1 + (bq)) * n2 + (cq_)) * cper)
+      const float v000 = VX_T(a0, b0, c0), v001 = VX_T(a0, b0, c1), v010 = VX_T(a0, b1, c0), v011 = VX_T(a0, b1, c1);
+      const float v100 = VX_T(a1, b0, c0), v101 = VX_T(a1, b0, c1), v110 = VX_T(a1, b1, c0), v111 = VX_T(a1, b1, c1);
+#undef VX_T
+      const float ua = 1.f - wa, ub = 1.f - wb, uc = 1.f - wc;
+      val = ua * (ub * (uc * v000 + wc * v001) + wb * (uc * v010 + wc * v011)) +
+            wa * (ub * (uc * v100 + wc * v101) + wb * (uc * v110 + wc * v111));
+    }
+    dst[e] = val;
+  }
+}
+
+// adjoint: dtok[token] = sum over the window's voxels of weight * dA.  Thread per token element for small
+// windows, warp per token element (lanes along the contiguous axis) when the big window is >= 8 wide.
+struct ScatterBwdArgs {
+  const float* src[VX_MAX_MODAL];   // dA (B, Ct, S)
+  float* dtok;                      // (B, h, Ns, L, cper)
+  int Ct, cper;
+};
+
+VX_DEV float lerp_weight(int p, int n, int out, int a) {
+  int i0, i1; float w1;
+  lerp_coef(p, n, out, i0, i1, w1);
+  float w = 0.f;
+  if (i0 == a) w += 1.f - w1;
+  if (i1 == a) w += w1;
+  return w;
+}
+
+__global__ void __launch_bounds__(256) pwa_scatter_bwd_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ ScatterBwdArgs A) {
+  const int j = blockIdx.y, m = blockIdx.z;
+  const int cper = A.cper, Ct = A.Ct;
+  const int Nj = G.Nw[j][0] * G.Nw[j][1] * G.Nw[j][2];
+  const long long total = (long long)G.B * G.heads * Nj * G.l * cper;
+  const bool warp_mode = G.big[j][2] >= 8 && G.vol[j] > 1;
+  const int lane = threadIdx.x & 31;
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (warp_mode) e >>= 5;
+  const long long stride = warp_mode ? ((long long)gridDim.x * blockDim.x) >> 5 : (long long)gridDim.x * blockDim.x;
+  const int B0 = G.big[j][0], B1 = G.big[j][1], B2 = G.big[j][2];
+  for (; e < total; e += stride) {
+    const int c = (int)(e % cper);
+    const int t = (int)((e / cper) % G.l);
+    const int Nloc = (int)((e / ((long long)cper * G.l)) % Nj);
+    const int head = (int)((e / ((long long)cper * G.l * Nj)) % G.heads);
+    const int b = (int)(e / ((long long)cper * G.l * Nj * G.heads));
+    const int wx = Nloc % G.Nw[j][2], wy = (Nloc / G.Nw[j][2]) % G.Nw[j][1], wz = Nloc / (G.Nw[j][2] * G.Nw[j][1]);
+    const int cc = t % G.n[2], bb = (t / G.n[2]) % G.n[1], a = t / (G.n[2] * G.n[1]);
+    const int ch = (j * G.heads + head) * cper + c;
+    const float* p = A.src[m] + ((size_t)b * Ct + ch) * G.S + ((size_t)(wz * B0) * G.H + wy * B1) * G.W + wx * B2;
+    float acc = 0.f;
+    if (G.vol[j] == 1) {
+      acc = __ldg(p + ((size_t)a * G.H + bb) * G.W + cc);
+    } else if (!warp_mode) {
+      for (int pz = 0; pz < B0; ++pz) {
+        const float wzv = lerp_weight(pz, G.n[0], B0, a);
+        if (wzv == 0.f) continue;
+        for (int py = 0; py < B1; ++py) {
+          const float wyv = lerp_weight(py, G.n[1], B1, bb);
+          if (wyv == 0.f) continue;
+          for (int px = 0; px < B2; ++px) {
+            const float wxv = lerp_weight(px, G.n[2], B2, cc);
+            if (wxv != 0.f) acc = fmaf(wzv * wyv * wxv, __ldg(p + ((size_t)pz * G.H + py) * G.W + px), acc);
+          }
+        }
+      }
+    } else {
+      for (int pz = 0; pz < B0; ++pz) {
+        const float wzv = lerp_weight(pz, G.n[0], B0, a);
+        if (wzv == 0.f) continue;
+        for (int py = 0; py < B1; ++py) {
+          const float wyv = lerp_weight(py, G.n[1], B1, bb);
+          if (wyv == 0.f) continue;
+          for (int px = lane; px < B2; px += 32) {
+            const float wxv = lerp_weight(px, G.n[2], B2, cc);
+            if (wxv != 0.f) acc = fmaf(wzv * wyv * wxv, __ldg(p + ((size_t)pz * G.H + py) * G.W + px), acc);
+          }
+        }
+      }
+      acc = warp_sum(acc);
+    }
+    if (!warp_mode || lane == 0)
+      A.dtok[((((size_t)b * G.heads + head) * G.Ns + G.Noff[j] + Nloc) * G.L + (size_t)m * G.l + t) * cper + c] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// buffer layouts
+// ---------------------------------------------------------------------------------------------------
+enum { SV_XHAT1 = 0, SV_RSTD1, SV_A, SV_Y, SV_XHAT2, SV_RSTD2, SV_HPRE, SV_QT, SV_KT, SV_VT, SV_ARGQ, SV_ARGK, SV_ARGV,
+       SV_LSE, SV_OT, SV_COUNT };
+
+struct PwaLayout {
+  PwaGeo G;
+  int C, cqk, cv, cq_h, cv_h, eC;
+  size_t saved[SV_COUNT];
+  size_t tokq, tokv;                       // element counts
+  // workspace offsets (bytes)
+  size_t off_qkv, off_biasT, off_dh, off_dln2, off_dy, off_dA, off_dOt, off_dQt, off_dKt, off_dVt, off_dqkv, off_dln1,
+      off_dbiasT, total;
+};
+
+static int pwa_layout(const vx_pwa_desc* d, PwaLayout& P) {
+  VX_TRY(make_geo(d, P.G));
+  const PwaGeo& G = P.G;
+  P.C = d->C; P.cqk = d->c_qk; P.cv = d->c_v; P.eC = d->ffn_expansion * d->C;
+  P.cq_h = d->c_qk / (G.nb * G.heads); P.cv_h = d->c_v / (G.nb * G.heads);
+  if (d->ffn_expansion <= 0) { set_error("pwa: bad ffn expansion"); return VX_ERR_BAD_DESC; }
+  const size_t MB = (size_t)G.M * G.B, S = G.S;
+  P.tokq = (size_t)G.B * G.heads * G.Ns * G.L * P.cq_h;
+  P.tokv = (size_t)G.B * G.heads * G.Ns * G.L * P.cv_h;
+  const size_t rows = (size_t)G.B * G.heads * G.Ns * G.L;
+  P.saved[SV_XHAT1] = 4 * MB * P.C * S;  P.saved[SV_RSTD1] = 4 * MB * S;
+  P.saved[SV_A] = 4 * MB * P.cv * S;     P.saved[SV_Y] = 4 * MB * P.C * S;
+  P.saved[SV_XHAT2] = 4 * MB * P.C * S;  P.saved[SV_RSTD2] = 4 * MB * S;
+  P.saved[SV_HPRE] = 4 * MB * P.eC * S;
+  P.saved[SV_QT] = 4 * P.tokq; P.saved[SV_KT] = 4 * P.tokq; P.saved[SV_VT] = 4 * P.tokv;
+  P.saved[SV_ARGQ] = 4 * P.tokq; P.saved[SV_ARGK] = 4 * P.tokq; P.saved[SV_ARGV] = 4 * P.tokv;
+  P.saved[SV_LSE] = 4 * rows; P.saved[SV_OT] = 4 * P.tokv;
+  size_t off = 0;
+  const size_t cqkv = (size_t)2 * P.cqk + P.cv;
+  P.off_qkv = off;    off += align256(4 * MB * cqkv * S);
+  P.off_biasT = off;  off += align256(4 * (size_t)G.heads * G.l * G.l);
+  P.off_dh = off;     off += align256(4 * MB * P.eC * S);
+  P.off_dln2 = off;   off += align256(4 * MB * P.C * S);
+  P.off_dy = off;     off += align256(4 * MB * P.C * S);
+  P.off_dA = off;     off += align256(4 * MB * P.cv * S);
+  P.off_dOt = off;    off += align256(4 * P.tokv);
+  P.off_dQt = off;    off += align256(4 * P.tokq);
+  P.off_dKt = off;    off += align256(4 * P.tokq);
+  P.off_dVt = off;    off += align256(4 * P.tokv);
+  P.off_dqkv = off;   off += align256(4 * MB * cqkv * S);
+  P.off_dln1 = off;   off += align256(4 * MB * P.C * S);
+  P.off_dbiasT = off; off += align256(4 * (size_t)G.heads * G.l * G.l);
+  P.total = off;
+  return VX_OK;
+}
+
+enum { PP_LN1W = 0, PP_LN1B, PP_WQ, PP_BQ, PP_WK, PP_BK, PP_WV, PP_BV, PP_WMIX, PP_BMIX, PP_LN2W, PP_LN2B, PP_W1, PP_B1,
+       PP_W2, PP_B2, PP_COUNT };
+constexpr uint32_t SITE_MIX = 3, SITE_FFN1 = 4, SITE_FFN2 = 5;
+
+}  // namespace vx
+
 using namespace vx;
-extern "C" int vx_pwa_saved_layout(const vx_pwa_desc*, vx_pwa_saved*) { set_error("pwa: not built"); return VX_ERR_UNSUPPORTED; }
-extern "C" size_t vx_pwa_workspace(const vx_pwa_desc*) { return 0; }
-extern "C" int vx_pwa_block_fwd(const vx_pwa_desc*, const void* const*, void* const*, void*, size_t, vx_stream_t) { set_error("pwa: not built"); return VX_ERR_UNSUPPORTED; }
-extern "C" int vx_pwa_block_bwd(const vx_pwa_desc*, const void* const*, void* const*, void*, size_t, vx_stream_t) { set_error("pwa: not built"); return VX_ERR_UNSUPPORTED; }
-extern "C" int vx_pwa_gather(const vx_pwa_desc*, int32_t, const void*, void*, void*, vx_stream_t) { set_error("pwa: not built"); return VX_ERR_UNSUPPORTED; }
+
+extern "C" int vx_pwa_saved_layout(const vx_pwa_desc* d, vx_pwa_saved* layout) {
+  PwaLayout P;
+  VX_TRY(pwa_layout(d, P));
+  layout->n_saved = SV_COUNT;
+  for (int i = 0; i < SV_COUNT; ++i) layout->saved_bytes[i] = P.saved[i];
+  return VX_OK;
+}
+
+extern "C" size_t vx_pwa_workspace(const vx_pwa_desc* d) {
+  PwaLayout P;
+  if (pwa_layout(d, P) != VX_OK) return 0;
+  return P.total;
+}
+
+extern "C" int vx_pwa_gather(const vx_pwa_desc* d, int32_t channels_total, const void* x, void* tokens, void* argmax,
+                             vx_stream_t stream) {
+  PwaGeo G;
+  VX_TRY(make_geo(d, G));
+  if (channels_total % (G.nb * G.heads)) { set_error("pwa_gather: channels do not split"); return VX_ERR_BAD_DESC; }
+  G.M = 1; G.L = G.l;
+  GatherArgs A{};
+  A.nkind = 1; A.src[0][0] = (const float*)x; A.tok[0] = (float*)tokens; A.arg[0] = (int*)argmax;
+  A.Ct[0] = channels_total; A.cper[0] = channels_total / (G.nb * G.heads);
+  return launch_gather(G, A, (cudaStream_t)stream);
+}
+
+extern "C" int vx_pwa_block_fwd(const vx_pwa_desc* d, const void* const* in, void* const* out, void* workspace,
+                                size_t workspace_bytes, vx_stream_t stream) {
+  PwaLayout P;
+  VX_TRY(pwa_layout(d, P));
+  if (!workspace || workspace_bytes < P.total) { set_error("pwa_fwd: workspace %zu < %zu", workspace_bytes, P.total); return VX_ERR_WORKSPACE; }
+  const PwaGeo& G = P.G;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const int M = G.M, B = G.B, S = G.S, C = P.C;
+  const size_t BS = (size_t)B * S;
+  auto X = [&](int m) { return (const float*)in[m]; };
+  auto PRM = [&](int m, int k) { return (const float*)in[M + m * PP_COUNT + k]; };
+  const float* table = (const float*)in[M + M * PP_COUNT];
+  const long long* index = (const long long*)in[M + M * PP_COUNT + 1];
+  auto Z = [&](int m) { return (float*)out[m]; };
+  auto SV = [&](int k) { return (float*)out[M + k]; };
+  const bool train = d->training != 0;
+  const float attn_p = train ? d->attn_drop : 0.f, proj_p = train ? d->proj_drop : 0.f;
+
+  float* qkv = (float*)(ws + P.off_qkv);
+  float* biasT = (float*)(ws + P.off_biasT);
+  const size_t cqkv = (size_t)2 * P.cqk + P.cv;
+  auto Qf = [&](int m) { return qkv + (size_t)m * cqkv * BS; };
+  auto Kf = [&](int m) { return Qf(m) + (size_t)P.cqk * BS; };
+  auto Vf = [&](int m) { return Qf(m) + (size_t)2 * P.cqk * BS; };
+
+  // LN1
+  LnBatch L1{}; L1.n = M; L1.B = B; L1.C = C; L1.S = S; L1.eps = d->ln_eps;
+  for (int m = 0; m < M; ++m) { L1.x[m] = X(m); L1.xhat[m] = SV(SV_XHAT1) + (size_t)m * C * BS; L1.rstd[m] = SV(SV_RSTD1) + (size_t)m * BS; }
+  VX_TRY(ln_forward(L1, st));
+  // q, k, v
+  {
+    PwBatch pb{}; pb.nprob = M; pb.B = B; pb.S = S;
+    for (int m = 0; m < M; ++m) {
+      PwProblem& p = pb.p[m];
+      p.src[0] = PwSrc{L1.xhat[m], C}; p.nsrc = 1; p.Ci = C;
+      p.seg[0] = PwSeg{PRM(m, PP_WQ), PRM(m, PP_BQ), C, P.cqk, Qf(m)};
+      p.seg[1] = PwSeg{PRM(m, PP_WK), PRM(m, PP_BK), C, P.cqk, Kf(m)};
+      p.seg[2] = PwSeg{PRM(m, PP_WV), PRM(m, PP_BV), C, P.cv, Vf(m)};
+      p.nseg = 3; p.Co = (int)cqkv;
+      p.pro = PRO_AFFINE; p.pro_a = PRM(m, PP_LN1W); p.pro_c = PRM(m, PP_LN1B); p.pro_bstride = 0;
+    }
+    VX_TRY(pw_forward(pb, st));
+  }
+  // tokens
+  {
+    GatherArgs A{}; A.nkind = 3;
+    for (int m = 0; m < M; ++m) { A.src[0][m] = Qf(m); A.src[1][m] = Kf(m); A.src[2][m] = Vf(m); }
+    A.tok[0] = SV(SV_QT); A.tok[1] = SV(SV_KT); A.tok[2] = SV(SV_VT);
+    A.arg[0] = (int*)SV(SV_ARGQ); A.arg[1] = (int*)SV(SV_ARGK); A.arg[2] = (int*)SV(SV_ARGV);
+    A.Ct[0] = A.Ct[1] = P.cqk; A.Ct[2] = P.cv; A.cper[0] = A.cper[1] = P.cq_h; A.cper[2] = P.cv_h;
+    VX_TRY(launch_gather(G, A, st));
+  }
+  // attention
+  {
+    const int nb = G.heads * G.l * G.l;
+    VX_LAUNCH(pwa_bias_kernel, dim3(cdiv(nb, 256)), dim3(256), 0, st, table, index, biasT, G.heads, G.l);
+    VX_TRY(check_launch("pwa_bias_kernel"));
+    AttnArgs A{};
+    A.Q = SV(SV_QT); A.K = SV(SV_KT); A.V = SV(SV_VT); A.biasT = biasT; A.O = SV(SV_OT); A.lse = SV(SV_LSE);
+    A.B = B; A.heads = G.heads; A.Ns = G.Ns; A.L = G.L; A.l = G.l;
+    A.scale = 1.0f / sqrtf((float)P.cq_h); A.drop_p = attn_p; A.seed = d->seed;
+    VX_TRY(dispatch_attn(A, P.cq_h, P.cv_h, false, st));
+  }
+  // scatter
+  {
+    ScatterArgs A{}; A.tok = SV(SV_OT); A.Ct = P.cv; A.cper = P.cv_h;
+    for (int m = 0; m < M; ++m) A.dst[m] = SV(SV_A) + (size_t)m * P.cv * BS;
+    int blocks = cdiv((long long)B * P.cv * S, 256);
+    if (blocks > kSMs * 16) blocks = kSMs * 16;
+    VX_LAUNCH(pwa_scatter_kernel, dim3(blocks, 1, M), dim3(256), 0, st, G, A);
+    VX_TRY(check_launch("pwa_scatter_kernel"));
+  }
+  // y = 2x + Drop(Wmix a + b)
+  {
+    PwBatch pb{}; pb.nprob = M; pb.B = B; pb.S = S;
+    for (int m = 0; m < M; ++m) {
+      PwProblem& p = pb.p[m];
+      p.src[0] = PwSrc{SV(SV_A) + (size_t)m * P.cv * BS, P.cv}; p.nsrc = 1; p.Ci = P.cv;
+      p.seg[0] = PwSeg{PRM(m, PP_WMIX), PRM(m, PP_BMIX), P.cv, C, SV(SV_Y) + (size_t)m * C * BS}; p.nseg = 1; p.Co = C;
+      if (proj_p > 0.f) { p.drop_p = proj_p; p.seed = d->seed + 0x1000 * (m + 1); p.site = SITE_MIX; }
+      p.res = X(m); p.res_scale = 2.f;
+    }
+    VX_TRY(pw_forward(pb, st));
+  }
+  // LN2, FFN
+  LnBatch L2{}; L2.n = M; L2.B = B; L2.C = C; L2.S = S; L2.eps = d->ln_eps;
+  for (int m = 0; m < M; ++m) { L2.x[m] = SV(SV_Y) + (size_t)m * C * BS; L2.xhat[m] = SV(SV_XHAT2) + (size_t)m * C * BS; L2.rstd[m] = SV(SV_RSTD2) + (size_t)m * BS; }
+  VX_TRY(ln_forward(L2, st));
+  {
+    PwBatch pb{}; pb.nprob = M; pb.B = B; pb.S = S;
+    for (int m = 0; m < M; ++m) {
+      PwProblem& p = pb.p[m];
+      p.src[0] = PwSrc{L2.xhat[m], C}; p.nsrc = 1; p.Ci = C;
+      p.seg[0] = PwSeg{PRM(m, PP_W1), PRM(m, PP_B1), C, P.eC, SV(SV_HPRE) + (size_t)m * P.eC * BS}; p.nseg = 1; p.Co = P.eC;
+      p.pro = PRO_AFFINE; p.pro_a = PRM(m, PP_LN2W); p.pro_c = PRM(m, PP_LN2B); p.pro_bstride = 0;
+    }
+    VX_TRY(pw_forward(pb, st));
+  }
+  {
+    PwBatch pb{}; pb.nprob = M; pb.B = B; pb.S = S;
+    for (int m = 0; m < M; ++m) {
+      PwProblem& p = pb.p[m];
+      p.src[0] = PwSrc{SV(SV_HPRE) + (size_t)m * P.eC * BS, P.eC}; p.nsrc = 1; p.Ci = P.eC;
+      p.seg[0] = PwSeg{PRM(m, PP_W2), PRM(m, PP_B2), P.eC, C, Z(m)}; p.nseg = 1; p.Co = C;
+      p.pro = PRO_GELU;
+      if (proj_p > 0.f) {
+        p.pro = PRO_GELU_DROPOUT; p.pro_drop_p = proj_p; p.pro_seed = d->seed + 0x1000 * (m + 1); p.pro_site = SITE_FFN1;
+        p.drop_p = proj_p; p.seed = d->seed + 0x1000 * (m + 1); p.site = SITE_FFN2;
+      }
+      p.res = SV(SV_Y) + (size_t)m * C * BS; p.res_scale = 1.f;
+    }
+    VX_TRY(pw_forward(pb, st));
+  }
+  return VX_OK;
+}
+
+extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, void* const* out, void* workspace,
+                                size_t workspace_bytes, vx_stream_t stream) {
+  PwaLayout P;
+  VX_TRY(pwa_layout(d, P));
+  if (!workspace || workspace_bytes < P.total) { set_error("pwa_bwd: workspace %zu < %zu", workspace_bytes, P.total); return VX_ERR_WORKSPACE; }
+  const PwaGeo& G = P.G;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const int M = G.M, B = G.B, S = G.S, C = P.C;
+  const size_t BS = (size_t)B * S;
+  auto DZ = [&](int m) { return (const float*)in[m]; };
+  auto PRM = [&](int m, int k) { return (const float*)in[2 * M + m * PP_COUNT + k]; };
+  const int base = 2 * M + M * PP_COUNT;
+  const float* table = (const float*)in[base];
+  const long long* index = (const long long*)in[base + 1];
+  auto SV = [&](int k) { return (const float*)in[base + 2 + k]; };
+  auto DX = [&](int m) { return (float*)out[m]; };
+  auto DP = [&](int m, int k) { return (float*)out[M + m * PP_COUNT + k]; };
+  float* dtable = (float*)out[M + M * PP_COUNT];
+  const bool train = d->training != 0;
+  const float attn_p = train ? d->attn_drop : 0.f, proj_p = train ? d->proj_drop : 0.f;
+  const size_t cqkv = (size_t)2 * P.cqk + P.cv;
+
+  float* biasT = (float*)(ws + P.off_biasT);
+  float* dh = (float*)(ws + P.off_dh);
+  float* dln2 = (float*)(ws + P.off_dln2);
+  float* dy = (float*)(ws + P.off_dy);
+  float* dA = (float*)(ws + P.off_dA);
+  float* dOt = (float*)(ws + P.off_dOt);
+  float* dQt = (float*)(ws + P.off_dQt);
+  float* dKt = (float*)(ws + P.off_dKt);
+  float* dVt = (float*)(ws + P.off_dVt);
+  float* dqkv = (float*)(ws + P.off_dqkv);
+  float* dln1 = (float*)(ws + P.off_dln1);
+  float* dbiasT = (float*)(ws + P.off_dbiasT);
+
+  // zero everything that is accumulated with atomics
+  const size_t psz[PP_COUNT] = {(size_t)C, (size_t)C, (size_t)P.cqk * C, (size_t)P.cqk, (size_t)P.cqk * C, (size_t)P.cqk,
+                                (size_t)P.cv * C, (size_t)P.cv, (size_t)C * P.cv, (size_t)C, (size_t)C, (size_t)C,
+                                (size_t)P.eC * C, (size_t)P.eC, (size_t)C * P.eC, (size_t)C};
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < PP_COUNT; ++k) cudaMemsetAsync(DP(m, k), 0, sizeof(float) * psz[k], st);
+  const int nbias = G.heads * G.l * G.l;
+  cudaMemsetAsync(dbiasT, 0, sizeof(float) * nbias, st);
+  {
+    // table rows = prod(2n-1)
+    const size_t rows = (size_t)(2 * G.n[0] - 1) * (2 * G.n[1] - 1) * (2 * G.n[2] - 1);
+    cudaMemsetAsync(dtable, 0, sizeof(float) * rows * G.heads, st);
+  }
+  VX_LAUNCH(pwa_bias_kernel, dim3(cdiv(nbias, 256)), dim3(256), 0, st, table, index, biasT, G.heads, G.l);
+  VX_TRY(check_launch("pwa_bias_kernel"));
+
+  auto seedm = [&](int m) { return d->seed + 0x1000 * (uint64_t)(m + 1); };
+
+  // ---- FFN backward
+  {
+    PwBatch pb{}; pb.nprob = M; pb.B = B; pb.S = S;     // dh = (W2^T (dz*m2)) * GELU'(hpre) * m1
+    for (int m = 0; m < M; ++m) {
+      PwProblem& p = pb.p[m];
+      p.src[0] = PwSrc{DZ(m), C}; p.nsrc = 1; p.Ci = C;
+      p.seg[0] = PwSeg{PRM(m, PP_W2), nullptr, P.eC, C, dh + (size_t)m * P.eC * BS}; p.nseg = 1; p.Co = P.eC; p.transposed = 1;
+      p.mulgrad = SV(SV_HPRE) + (size_t)m * P.eC * BS;
+      if (proj_p > 0.f) {
+        p.pro = PRO_DROPOUT; p.pro_drop_p = proj_p; p.pro_seed = seedm(m); p.pro_site = SITE_FFN2;
+        p.drop_p = proj_p; p.seed = seedm(m); p.site = SITE_FFN1;
+      }
+    }
+    VX_TRY(pw_forward(pb, st));
+  }
+  {
+    PwBatch pb{}; pb.nprob = M; pb.B = B; pb.S = S;     // dln2 = W1^T dh
+    for (int m = 0; m < M; ++m) {
+      PwProblem& p = pb.p[m];
+      p.src[0] = PwSrc{dh + (size_t)m * P.eC * BS, P.eC}; p.nsrc = 1; p.Ci = P.eC;
+      p.seg[0] = PwSeg{PRM(m, PP_W1), nullptr, C, P.eC, dln2 + (size_t)m * C * BS}; p.nseg = 1; p.Co = C; p.transposed = 1;
+    }
+    VX_TRY(pw_forward(pb, st));
+  }
+  {
+    WgBatch wb{}; wb.nprob = 2 * M; wb.B = B; wb.S = S;
+    for (int m = 0; m < M; ++m) {
+      WgProblem& a = wb.p[2 * m];        // dW2 = (dz*m2) (GELU(hpre)*m1)^T
+      a.dY = DZ(m); a.Co = C; a.src[0] = PwSrc{SV(SV_HPRE) + (size_t)m * P.eC * BS, P.eC}; a.nsrc = 1; a.Ci = P.eC;
+      a.xpro = PRO_GELU;
+      if (proj_p > 0.f) {
+        a.xpro = PRO_GELU_DROPOUT; a.x_drop_p = proj_p; a.x_seed = seedm(m); a.x_site = SITE_FFN1;
+        a.y_drop_p = proj_p; a.y_seed = seedm(m); a.y_site = SITE_FFN2;
+      }
+      a.dW = DP(m, PP_W2); a.ld = P.eC; a.db = DP(m, PP_B2);
+      WgProblem& b1 = wb.p[2 * m + 1];   // dW1 = dh (g2*yhat + b2)^T
+      b1.dY = dh + (size_t)m * P.eC * BS; b1.Co = P.eC; b1.src[0] = PwSrc{SV(SV_XHAT2) + (size_t)m * C * BS, C}; b1.nsrc = 1; b1.Ci = C;
+      b1.xpro = PRO_AFFINE; b1.xa = PRM(m, PP_LN2W); b1.xc = PRM(m, PP_LN2B); b1.x_bstride = 0;
+      b1.dW = DP(m, PP_W1); b1.ld = C; b1.db = DP(m, PP_B1);
+    }
+    VX_TRY(pw_wgrad(wb, st));
+  }
+  {
+    LnBwdBatch Lb{}; Lb.n = M; Lb.B = B; Lb.C = C; Lb.S = S; Lb.dx_add_scale = 1.f;   // dy = dz + LN2_bwd(dln2)
+    for (int m = 0; m < M; ++m) {
+      Lb.dout[m] = dln2 + (size_t)m * C * BS; Lb.xhat[m] = SV(SV_XHAT2) + (size_t)m * C * BS; Lb.rstd[m] = SV(SV_RSTD2) + (size_t)m * BS;
+      Lb.gamma[m] = PRM(m, PP_LN2W); Lb.dx_add[m] = DZ(m); Lb.dx[m] = dy + (size_t)m * C * BS;
+      Lb.dgamma[m] = DP(m, PP_LN2W); Lb.dbeta[m] = DP(m, PP_LN2B);
+    }
+    VX_TRY(ln_backward(Lb, st));
+  }
+  // ---- mix backward
+  {
+    PwBatch pb{}; pb.nprob = M; pb.B = B; pb.S = S;     // dA = Wmix^T (dy*mask)
+    for (int m = 0; m < M; ++m) {
+      PwProblem& p = pb.p[m];
+      p.src[0] = PwSrc{dy + (size_t)m * C * BS, C}; p.nsrc = 1; p.Ci = C;
+      p.seg[0] = PwSeg{PRM(m, PP_WMIX), nullptr, P.cv, C, dA + (size_t)m * P.cv * BS}; p.nseg = 1; p.Co = P.cv; p.transposed = 1;
+      if (proj_p > 0.f) { p.pro = PRO_DROPOUT; p.pro_drop_p = proj_p; p.pro_seed = seedm(m); p.pro_site = SITE_MIX; }
+    }
+    VX_TRY(pw_forward(pb, st));
+    WgBatch wb{}; wb.nprob = M; wb.B = B; wb.S = S;
+    for (int m = 0; m < M; ++m) {
+      WgProblem& a = wb.p[m];
+      a.dY = dy + (size_t)m * C * BS; a.Co = C; a.src[0] = PwSrc{SV(SV_A) + (size_t)m * P.cv * BS, P.cv}; a.nsrc = 1; a.Ci = P.cv;
+      if (proj_p > 0.f) { a.y_drop_p = proj_p; a.y_seed = seedm(m); a.y_site = SITE_MIX; }
+      a.dW = DP(m, PP_WMIX); a.ld = P.cv; a.db = DP(m, PP_BMIX);
+    }
+    VX_TRY(pw_wgrad(wb, st));
+  }
+  // ---- scatter adjoint
+  {
+    ScatterBwdArgs A{}; A.dtok = dOt; A.Ct = P.cv; A.cper = P.cv_h;
+    for (int m = 0; m < M; ++m) A.src[m] = dA + (size_t)m * P.cv * BS;
+    long long maxtotal = 0;
+    for (int j = 0; j < G.nb; ++j) {
+      long long t = (long long)B * G.heads * G.Nw[j][0] * G.Nw[j][1] * G.Nw[j][2] * G.l * P.cv_h;
+      if (G.big[j][2] >= 8 && G.vol[j] > 1) t *= 32;
+      maxtotal = t > maxtotal ? t : maxtotal;
+    }
+    int blocks = cdiv(maxtotal, 256);
+    if (blocks > kSMs * 16) blocks = kSMs * 16;
+    VX_LAUNCH(pwa_scatter_bwd_kernel, dim3(blocks, G.nb, M), dim3(256), 0, st, G, A);
+    VX_TRY(check_launch("pwa_scatter_bwd_kernel"));
+  }
+  // ---- attention backward
+  {
+    AttnArgs A{};
+    A.Q = SV(SV_QT); A.K = SV(SV_KT); A.V = SV(SV_VT); A.biasT = biasT; A.O = (float*)SV(SV_OT); A.lse = (float*)SV(SV_LSE);
+    A.dO = dOt; A.dQ = dQt; A.dK = dKt; A.dV = dVt; A.dbiasT = dbiasT;
+    A.B = B; A.heads = G.heads; A.Ns = G.Ns; A.L = G.L; A.l = G.l;
+    A.scale = 1.0f / sqrtf((float)P.cq_h); A.drop_p = attn_p; A.seed = d->seed;
+    VX_TRY(dispatch_attn(A, P.cq_h, P.cv_h, true, st));
+    VX_LAUNCH(pwa_bias_bwd_kernel, dim3(cdiv(nbias, 256)), dim3(256), 0, st, (const float*)dbiasT, index, dtable, G.heads, G.l);
+    VX_TRY(check_launch("pwa_bias_bwd_kernel"));
+  }
+  // ---- gather adjoint -> full-resolution dq, dk, dv
+  auto dQf = [&](int m) { return dqkv + (size_t)m * cqkv * BS; };
+  auto dKf = [&](int m) { return dQf(m) + (size_t)P.cqk * BS; };
+  auto dVf = [&](int m) { return dQf(m) + (size_t)2 * P.cqk * BS; };
+  {
+    GatherBwdArgs A{};
+    A.dtok[0] = dQt; A.dtok[1] = dKt; A.dtok[2] = dVt;
+    A.arg[0] = (const int*)SV(SV_ARGQ); A.arg[1] = (const int*)SV(SV_ARGK); A.arg[2] = (const int*)SV(SV_ARGV);
+    for (int m = 0; m < M; ++m) { A.dst[0][m] = dQf(m); A.dst[1][m] = dKf(m); A.dst[2][m] = dVf(m); }
+    A.Ct[0] = A.Ct[1] = P.cqk; A.Ct[2] = P.cv; A.cper[0] = A.cper[1] = P.cq_h; A.cper[2] = P.cv_h;
+    const int cmax = P.cqk > P.cv ? P.cqk : P.cv;
+    int blocks = cdiv((long long)B * cmax * S, 256);
+    if (blocks > kSMs * 16) blocks = kSMs * 16;
+    VX_LAUNCH(pwa_gather_bwd_kernel, dim3(blocks, 1, 3 * M), dim3(256), 0, st, G, A);
+    VX_TRY(check_launch("pwa_gather_bwd_kernel"));
+  }
+  // ---- projection backward
+  {
+    PwBatch pb{}; pb.nprob = M; pb.B = B; pb.S = S;     // dln1 = Wq^T dq + Wk^T dk + Wv^T dv
+    for (int m = 0; m < M; ++m) {
+      PwProblem& p = pb.p[m];
+      p.src[0] = PwSrc{dQf(m), P.cqk}; p.src[1] = PwSrc{dKf(m), P.cqk}; p.src[2] = PwSrc{dVf(m), P.cv}; p.nsrc = 3; p.Ci = (int)cqkv;
+      p.seg[0] = PwSeg{PRM(m, PP_WQ), nullptr, C, P.cqk, dln1 + (size_t)m * C * BS};
+      p.seg[1] = PwSeg{PRM(m, PP_WK), nullptr, C, P.cqk, nullptr};
+      p.seg[2] = PwSeg{PRM(m, PP_WV), nullptr, C, P.cv, nullptr};
+      p.nseg = 3; p.Co = C; p.transposed = 1;
+    }
+    VX_TRY(pw_forward(pb, st));
+    WgBatch wb{}; wb.nprob = 3 * M; wb.B = B; wb.S = S;
+    for (int m = 0; m < M; ++m) {
+      const float* dsrc[3] = {dQf(m), dKf(m), dVf(m)};
+      const int co[3] = {P.cqk, P.cqk, P.cv};
+      const int wi[3] = {PP_WQ, PP_WK, PP_WV};
+      for (int k = 0; k < 3; ++k) {
+        WgProblem& a = wb.p[3 * m + k];
+        a.dY = dsrc[k]; a.Co = co[k]; a.src[0] = PwSrc{SV(SV_XHAT1) + (size_t)m * C * BS, C}; a.nsrc = 1; a.Ci = C;
+        a.xpro = PRO_AFFINE; a.xa = PRM(m, PP_LN1W); a.xc = PRM(m, PP_LN1B); a.x_bstride = 0;
+        a.dW = DP(m, wi[k]); a.ld = C; a.db = DP(m, wi[k] + 1);
+      }
+    }
+    VX_TRY(pw_wgrad(wb, st));
+    LnBwdBatch Lb{}; Lb.n = M; Lb.B = B; Lb.C = C; Lb.S = S; Lb.dx_add_scale = 2.f;   // dx = LN1_bwd(dln1) + 2 dy
+    for (int m = 0; m < M; ++m) {
+      Lb.dout[m] = dln1 + (size_t)m * C * BS; Lb.xhat[m] = SV(SV_XHAT1) + (size_t)m * C * BS; Lb.rstd[m] = SV(SV_RSTD1) + (size_t)m * BS;
+      Lb.gamma[m] = PRM(m, PP_LN1W); Lb.dx_add[m] = dy + (size_t)m * C * BS; Lb.dx[m] = DX(m);
+      Lb.dgamma[m] = DP(m, PP_LN1W); Lb.dbeta[m] = DP(m, PP_LN1B);
+    }
+    VX_TRY(ln_backward(Lb, st));
+  }
+  return VX_OK;
+}

@@ -7,7 +7,7 @@ namespace vx {
 // ---------------------------------------------------------------------------------------------------
 // Channel contraction ("1x1x1 conv") over NCDHW:  Y[b,co,s] = epi( sum_ci W[co,ci] * pro(X[b,ci,s]) + bias[co] )
 // ---------------------------------------------------------------------------------------------------
-enum { PRO_NONE = 0, PRO_AFFINE = 1, PRO_GELU = 2, PRO_DROPOUT = 3 };
+enum { PRO_NONE = 0, PRO_AFFINE = 1, PRO_GELU = 2, PRO_DROPOUT = 3, PRO_GELU_DROPOUT = 4 };
 
 struct PwSrc { const float* ptr; int C; };                 // input segment (B, C, S)
 struct PwSeg { const float* W; const float* bias; int ld; int n; float* out; };
@@ -22,7 +22,7 @@ struct PwProblem {
   int transposed;
   int pro;                        // PRO_*
   const float* pro_a; const float* pro_c; int pro_bstride;   // PRO_AFFINE: x*a[b*bstride+ci] + c[b*bstride+ci]
-  float pro_drop_p; uint64_t pro_seed; uint32_t pro_site;    // PRO_DROPOUT (mask indexed like the input tensor)
+  float pro_drop_p; uint64_t pro_seed; uint32_t pro_site;    // PRO_DROPOUT / PRO_GELU_DROPOUT (mask indexed like the input)
   int act;                        // 1: GELU on the output
   const float* mulgrad;           // if set: out *= GELU'(mulgrad[b,co,s])
   float drop_p; uint64_t seed; uint32_t site;                // dropout on (acc + bias), before the residual
@@ -38,7 +38,8 @@ int pw_forward(const PwBatch& batch, cudaStream_t stream);
 struct WgProblem {
   const float* dY; int Co;
   PwSrc src[4]; int nsrc; int Ci;
-  int xpro; const float* xa; const float* xc; int x_bstride;  // PRO_NONE / PRO_AFFINE / PRO_GELU on X
+  int xpro; const float* xa; const float* xc; int x_bstride;  // PRO_NONE / PRO_AFFINE / PRO_GELU[_DROPOUT] on X
+  float x_drop_p; uint64_t x_seed; uint32_t x_site;
   float y_drop_p; uint64_t y_seed; uint32_t y_site;           // dropout mask on dY (0 disables)
   float* dW; int ld;                                          // accumulated with atomics: caller zeroes
   float* db;                                                  // may be null
