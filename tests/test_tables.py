@@ -1,0 +1,58 @@
+"""Integer paths, bit-exact: window pyramids, channel counts, relative-position index, gather order (PWA.py:56-140,
+attention_utils.py:89-117) against tables minted from the reference; sliding-window slice enumeration properties."""
+import pytest
+import torch
+
+from oracle import veloxseg_oracle as O
+from tests import _golden as G
+from veloxseg_b200.configs import MODEL_CONFIGS
+
+TABLES = G.load("tables.pt")
+
+
+@pytest.mark.parametrize("name", list(MODEL_CONFIGS))
+def test_window_tables(name):
+    from veloxseg_b200.nn import VeloxSeg
+    torch.manual_seed(0)
+    m = VeloxSeg(**MODEL_CONFIGS[name])
+    spec = O.ModelSpec(MODEL_CONFIGS[name])
+    for i, ref in enumerate(TABLES[name]):
+        a = m.encoder.encoder_attn.layers[i].blocks[0].attn
+        geo = spec.geo[i]
+        for got in (dict(big=a.big_window_size, small=a.small_window_size, cqk=a.channels_qk, cv=a.channels_v, n=a.n_hwd),
+                    dict(big=geo["bws"], small=geo["sws"], cqk=geo["cqk"], cv=geo["cv"], n=geo["n"])):
+            assert got["big"] == ref["big"] and got["small"] == ref["small"]
+            assert got["cqk"] == ref["channels_qk"] and got["cv"] == ref["channels_v"] and list(got["n"]) == ref["n"]
+        idx = a.position_embedding.relative_position_index
+        assert idx.dtype == torch.int64
+        assert G.sha_int32(idx) == ref["rel_index_sha"]
+        assert G.sha_int32(O.relative_position_index(ref["n"])) == ref["rel_index_sha"]
+        if ref["rel_index"] is not None:
+            assert torch.equal(idx, ref["rel_index"])
+        # gather order on a voxel-index ramp
+        h, w, d = ref["input_size"]
+        cqk = ref["channels_qk"]
+        ramp = torch.arange(h * w * d, dtype=torch.float32).view(1, 1, h, w, d).repeat(1, cqk, 1, 1, 1)
+        ramp = ramp + torch.arange(cqk, dtype=torch.float32).view(1, -1, 1, 1, 1) * (h * w * d)
+        tok, Ns, n = O.gather_tokens(ramp, a.num_heads, ref["big"], ref["small"])
+        assert Ns == ref["Ns"] and n == ref["n"]
+        assert G.sha_int32(tok) == ref["gather_ramp_sha"]
+
+
+def test_sliding_window_slices():
+    # MONAI 1.5.0 dense_patch_slices restated (parity unpinned: MONAI is not installable here); properties instead
+    for image, roi in [((320, 320, 256), (128, 128, 64)), ((96, 96, 96), (96, 96, 96)), ((100, 130, 70), (96, 96, 96)),
+                       ((512, 512, 384), (128, 128, 64)), ((97, 96, 200), (96, 96, 96))]:
+        img = [max(i, r) for i, r in zip(image, roi)]
+        sl = O.sw_slices(img, roi, 0.25)
+        assert sl[0] == (0, 0, 0)
+        cover = torch.zeros(img, dtype=torch.int32)
+        for a, b, c in sl:
+            assert 0 <= a <= img[0] - roi[0] and 0 <= b <= img[1] - roi[1] and 0 <= c <= img[2] - roi[2]
+            cover[a:a + roi[0], b:b + roi[1], c:c + roi[2]] += 1
+        assert int(cover.min()) >= 1                      # no gaps
+        assert sl == sorted(sl)                           # first spatial axis slowest
+        assert max(s[0] for s in sl) == img[0] - roi[0]   # last window ends at the border
+    assert len(O.sw_slices((320, 320, 256), (128, 128, 64), 0.25)) == 45      # 3 x 3 x 5
+    assert len(O.sw_slices((512, 512, 384), (128, 128, 64), 0.25)) == 200
+    assert O.sw_scan_interval((320, 320, 256), (128, 128, 64), 0.25) == [96, 96, 48]

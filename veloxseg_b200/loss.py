@@ -1,0 +1,73 @@
+"""Training loss of the reference (utils/loss.py:17-66, utils/runtime.py:125-174) on top of the SDKT op.
+
+seg = sum_i w_i (CE(out_i, y) + Dice(out_i, y)), w = deep_Loss_weight normalised;  + 0.5 * MSE(rcs, inputs)
++ 2.0 * sum_m MSE(G_s, G_t^m) / M  (teacher Grams are NOT detached).  CE / Dice / MSE stay torch ops (SURVEY.md
+section 8f, row 3); the Gram feature loss is `ops.sdkt_loss`.  DiceLoss restates monai.losses.DiceLoss(
+include_background=False, to_onehot_y=True, softmax=True) — MONAI 1.5.0 is an un-vendored dependency.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+def veloxseg_output_layout(output_count: int, num_modal: int) -> dict:
+    """utils/runtime.py:158-174."""
+    tail = 2 + int(num_modal)
+    if output_count <= tail:
+        raise ValueError(f"VeloxSeg output count {output_count} is too small for {num_modal} modality "
+                         "reconstruction outputs")
+    n = output_count - tail
+    return {"seg": (0, n), "reconstruction": n, "decoder_gram": n + 1,
+            "teacher_grams": tuple(range(n + 2, n + 2 + int(num_modal)))}
+
+
+def normalized_deep_loss_weights(configured, output_count: int):
+    """utils/runtime.py:125-144."""
+    if output_count <= 0:
+        raise ValueError("output_count must be greater than 0")
+    w = [float(v) for v in configured]
+    if not w:
+        raise ValueError("deep_Loss_weight must contain at least one value")
+    if sum(w) == 0:
+        raise ValueError("deep_Loss_weight sum must be non-zero")
+    if len(w) != output_count:
+        if all(v == w[0] for v in w):
+            return [1.0 / output_count] * output_count
+        raise ValueError("deep_Loss_weight length must match model deep-supervision outputs unless all configured "
+                         "weights are equal")
+    return [v / sum(w) for v in w]
+
+
+def dice_loss(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    C = logits.shape[1]
+    prob = torch.softmax(logits, 1)[:, 1:]
+    onehot = F.one_hot(target.squeeze(1).long(), C).movedim(-1, 1).to(prob.dtype)[:, 1:]
+    dims = tuple(range(2, logits.dim()))
+    inter = (prob * onehot).sum(dims)
+    den = prob.sum(dims) + onehot.sum(dims)
+    return (1.0 - (2.0 * inter + 1e-5) / (den + 1e-5)).mean()
+
+
+class Loss(torch.nn.Module):
+    def __init__(self, num_modal: int = 2, deep_weights: Sequence[float] = (1, 1, 1, 1), rc_weight: float = 0.5,
+                 feature_weight: float = 2.0):
+        super().__init__()
+        self.num_modal, self.deep_weights = num_modal, list(deep_weights)
+        self.rc_weight, self.feature_weight = rc_weight, feature_weight
+
+    def forward(self, output, labels, sr_labels):
+        lay = veloxseg_output_layout(len(output), self.num_modal)
+        s0, s1 = lay["seg"]
+        w = normalized_deep_loss_weights(self.deep_weights, s1 - s0)
+        y = labels.squeeze(1).long()
+        seg = output[0].new_zeros(())
+        for wi, o in zip(w, output[s0:s1]):
+            seg = seg + wi * (F.cross_entropy(o, y) + dice_loss(o, labels))
+        rc = F.mse_loss(output[lay["reconstruction"]], sr_labels)
+        feat = ops.sdkt_loss(output[lay["decoder_gram"]], [output[i] for i in lay["teacher_grams"]])
+        return seg + self.rc_weight * rc + self.feature_weight * feat
