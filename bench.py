@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): VeloxSeg AutoPET-II training step, 4 patches (2 x 96^3) per GPU per step
+(train_config_bs4.json: batch_size 2 x num_samples 2), full loss (CE + Dice over 4 deep outputs, 0.5 MSE
+reconstruction, 2.0 SDKT), backward, AdamW.  Synthetic inputs, seeded He-init weights.  One rank per GPU; weak
+scaling (every rank steps its own 4 patches, gradients all-reduced in buckets during backward).
+
+value   patches/s with the batch resident in HBM (CUDA events per step, L2 flushed between steps, max over ranks)
+e2e     the same step through veloxseg_b200.train.TrainStep.step with pinned HOST batches: H2D copy of inputs and
+        labels and the D2H read of the loss are inside the timed region
+roofline  the kernel with the largest share of the step, timed live by the library's event profiler
+cpu_baseline / --impl reference   the oracle port of the reference's CPU path (torch fp32 on the host cores)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+CFG_NAME = "autopetii"
+PATCHES = 4
+METRIC = "train patches/s"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def synth_batch(cfg, B, seed):
+    """randn inputs (speed_test.py style) + labels from seeded ellipsoids (fg a few %)."""
+    g = torch.Generator().manual_seed(seed)
+    size = cfg["input_size"]
+    x = torch.randn(B, sum(cfg["in_ch"]), *size, generator=g)
+    zz, yy, xx = torch.meshgrid(*[torch.arange(s, dtype=torch.float32) for s in size], indexing="ij")
+    y = torch.zeros(B, 1, *size, dtype=torch.int64)
+    for b in range(B):
+        for _ in range(3):
+            c = torch.rand(3, generator=g) * torch.tensor(size, dtype=torch.float32)
+            r = 6 + torch.rand(3, generator=g) * 10
+            cls = int(torch.randint(1, cfg["n_classes"], (1,), generator=g))
+            y[b, 0][((zz - c[0]) / r[0]) ** 2 + ((yy - c[1]) / r[1]) ** 2 + ((xx - c[2]) / r[2]) ** 2 < 1] = cls
+    return x, y
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+# algorithmic bytes of ONE launch of a kernel, from the profiler scope "op Bx Cx Sx ..." 
+def kernel_alg_bytes(scope, kernel):
+    f = {}
+    for tok in scope.split()[1:]:
+        k = "".join(c for c in tok if c.isalpha())
+        v = "".join(c for c in tok if c.isdigit())
+        if v:
+            f[k] = int(v)
+    B, C, S = f.get("B", 1), f.get("C", 0), f.get("S", 0)
+    act = 4 * B * C * S
+    if "jlc_conv_fwd" in kernel:
+        return act + 3 * act          # read x, write z1,z3,z5
+    if "jlc_conv_dgrad" in kernel:
+        return 3 * act + act + act    # read gz (3), dO; write dx
+    if "jlc_conv_wgrad" in kernel:
+        return act + 3 * act          # read x, gz
+    if "jlc_combine" in kernel:
+        return 4 * act + act
+    if "jlc_bwd_b" in kernel:
+        return 6 * act + act
+    if "jlc_bwd_c" in kernel:
+        return 4 * act + 3 * act
+    if "jlc_bwd_a" in kernel:
+        return 2 * act
+    return None
+
+
+def run_ours(args, rank, world, local_rank):
+    from veloxseg_b200 import _lib
+    from veloxseg_b200.configs import MODEL_CONFIGS, TRAIN
+    from veloxseg_b200.nn import VeloxSeg
+    from veloxseg_b200.train import TrainStep
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = os.environ.get("VX_CUDNN_BENCHMARK", "1") == "1"
+    cfg = MODEL_CONFIGS[CFG_NAME]
+    torch.manual_seed(12345)
+    model = VeloxSeg(**cfg)
+    ts = TrainStep(model, len(cfg["in_ch"]), dev, lr=TRAIN["lr"], weight_decay=TRAIN["weight_decay"],
+                   deep_weights=TRAIN["deep_Loss_weight"], rc_weight=TRAIN["RC_Loss_weight"],
+                   feature_weight=TRAIN["Feature_Loss_weight"])
+    lib = _lib.get_lib()
+    x_h, y_h = synth_batch(cfg, PATCHES, 1000 + rank)
+    x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
+    x_d, y_d = x_h.to(dev), y_h.to(dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        ts.step(x_d, y_d)
+    barrier()
+    # ---- device-resident timing
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    n0 = lib.c.vx_launch_count()
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            ts.step(x_d, y_d)
+            b.record()
+        barrier()
+    launches = int(lib.c.vx_launch_count() - n0)
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    if os.environ.get("VX_NCU") == "1":        # ncu --profile-from-start off: capture exactly one steady-state step
+        torch.cuda.profiler.start()
+        ts.step(x_d, y_d)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+    # ---- end to end (host batches)
+    for _ in range(2):
+        ts.step(x_h, y_h, sync=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        last_loss = ts.step(x_h, y_h, sync=True)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    # ---- per-kernel profile of one step (separate pass, not the timed one)
+    roof, table = None, []
+    if rank == 0:
+        lib.profile(True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nprof = 3
+        ev0.record()
+        for _ in range(nprof):
+            ts.step(x_d, y_d)
+        ev1.record()
+        torch.cuda.synchronize()
+        rows = lib.profile_report()
+        lib.profile(False)
+        step_ms_prof = ev0.elapsed_time(ev1) / nprof
+        rows.sort(key=lambda r: -r[3])
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "kernel_table.json"), "w") as f:
+            json.dump({"steps": nprof, "step_ms": step_ms_prof,
+                       "rows": [dict(scope=r[0], kernel=r[1], launches=r[2], ms=r[3]) for r in rows]}, f, indent=1)
+        ours_ms = sum(r[3] for r in rows) / nprof
+        table = [dict(scope=r[0], kernel=r[1], launches_per_step=r[2] / nprof, ms_per_step=r[3] / nprof) for r in rows[:12]]
+        hbm, _, how = peaks()
+        top = rows[0]
+        alg = kernel_alg_bytes(top[0], top[1])
+        if alg is not None:
+            dur = top[3] / top[2] * 1e-3
+            ach = alg / dur / 1e9
+            roof = {"bound": "hbm", "kernel": top[1].strip("()"), "scope": top[0], "achieved": round(ach, 1), "peak": hbm,
+                    "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": None, "peak_source": how,
+                    "kernel_ms": round(top[3] / top[2], 4), "share_of_step": round(top[3] / nprof / step_ms_prof, 4),
+                    "own_kernels_share_of_step": round(ours_ms / step_ms_prof, 4)}
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        return
+    total_patches = PATCHES * world * args.steps
+    line = {
+        "metric": METRIC, "value": round(total_patches / (ms_total * 1e-3), 3), "unit": "patches/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "VeloxSeg AutoPET-II train step (models_config_autopetii + train_config_bs4): 4 patches "
+                               "of 2x96^3 per GPU, CE+Dice x4 deep, 0.5 MSE recon, 2.0 SDKT, AdamW",
+                   "patches_per_gpu": PATCHES, "global_patches": PATCHES * world, "parallelism": f"dp{world}",
+                   "cache": "L2 flushed (256 MiB memset) between timed steps"},
+        "e2e": {"value": round(total_patches / e2e_s, 3), "unit": "patches/s",
+                "h2d_bytes_per_step": int(x_h.numel() * x_h.element_size() + y_h.numel() * y_h.element_size()),
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "loss": last_loss, "top_kernels": table,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_port(steps=1, patches=1, threads=None)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_port(steps, patches, threads):
+    """The oracle's restatement of the reference CPU path: train step (fwd + full loss + bwd + AdamW) on host cores."""
+    from oracle import veloxseg_oracle as O
+    from veloxseg_b200.configs import MODEL_CONFIGS, TRAIN
+    from veloxseg_b200.nn import VeloxSeg
+    cores = threads or (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    cfg = MODEL_CONFIGS[CFG_NAME]
+    torch.manual_seed(12345)
+    m = VeloxSeg(**cfg)
+    p = {k: (v.detach().clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in m.state_dict().items()}
+    leaves = [v for v in p.values() if v.dtype.is_floating_point]
+    opt = torch.optim.AdamW(leaves, lr=TRAIN["lr"], weight_decay=TRAIN["weight_decay"])
+    spec = O.ModelSpec(cfg)
+    x, y = synth_batch(cfg, patches, 1000)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        outs = O.forward(x, p, spec, training=True)
+        loss = O.total_loss(outs, y, x, spec.M, TRAIN["deep_Loss_weight"], TRAIN["RC_Loss_weight"], TRAIN["Feature_Loss_weight"])
+        loss.backward()
+        opt.step()
+        return float(loss)
+    step()      # warm-up (allocator, thread pool)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": round(steps * patches / dt, 4), "unit": "patches/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} train step(s) of {patches} patch(es) (2x96^3, fp32, dropout off) after 1 warm-up step, "
+                      f"torch CPU with {cores} threads"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    patches = 1
+    steps = max(1, min(args.steps, 5))
+    base = cpu_port(steps=steps, patches=patches, threads=None)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "patches/s", "n_gpus": world,
+            "steps": steps, "warmup": 1, "ms_per_step": round(1e3 * patches / base["value"], 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "VeloxSeg AutoPET-II train step (models_config_autopetii + train_config_bs4), CPU path; "
+                                   "each step a bounded sample of 1 of the 4 patches", "parallelism": "host cores"},
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "patches/s", "h2d_bytes_per_step": 0,
+                                          "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,14 @@ typedef enum {
 
 int vx_version(void);
 const char* vx_last_error_string(void);
+/* number of kernels this library has enqueued since it was loaded (all threads, all streams) */
+uint64_t vx_launch_count(void);
+/* Per-kernel timing with CUDA events on the launching stream (diagnostics for bench.py; off by default).
+ * vx_profile_enable(1) brackets every subsequent launch with an event pair; vx_profile_report() synchronises those
+ * events and writes one line per (scope, kernel): "scope|kernel|launches|total_ms\n"; returns the bytes needed. */
+int vx_profile_enable(int on);
+void vx_profile_reset(void);
+size_t vx_profile_report(char* buf, size_t cap);
 
 /* ---------------------------------------------------------------------------------------------------
  * JLC block — replaces JLC.forward, model/components/conv_blocks.py:41-75 (and autograd's backward of it).
@@ -179,6 +187,21 @@ int vx_lnpw_fwd(const vx_lnpw_desc* d, const void* const* in, void* const* out, 
                 size_t workspace_bytes, vx_stream_t stream);
 int vx_lnpw_bwd(const vx_lnpw_desc* d, const void* const* in, void* const* out, void* workspace,
                 size_t workspace_bytes, vx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Trilinear resize, align_corners=True — VeloxSeg.scale_prediction, model/VeloxSeg.py:177-184 (applied to the four
+ * deep-supervision outputs in training, VeloxSeg.py:200-202).   y (planes, D,H,W) = resize(x (planes, d,h,w))
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t planes;      /* B * C               */
+  int32_t d, h, w;     /* source extent       */
+  int32_t D, H, W;     /* destination extent  */
+} vx_resize_desc;
+size_t vx_resize_workspace(const vx_resize_desc* d);
+/* fwd in: x   out: y            bwd in: dy   out: dx (needs the workspace) */
+int vx_resize_trilinear_fwd(const vx_resize_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
+int vx_resize_trilinear_bwd(const vx_resize_desc* d, const void* const* in, void* const* out, void* workspace,
+                            size_t workspace_bytes, vx_stream_t stream);
 
 #ifdef __cplusplus
 }

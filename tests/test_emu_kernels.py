@@ -187,3 +187,17 @@ def test_pwa_block(emu, size, C, mb, ms, heads, mdh, M, e, B):
     names = [f"dx{m}" for m in range(M)] + [n.format(m=m) for m in range(M) for n in PWA_PARAM_NAMES] + ["table"]
     bad = [(n, rel_err(g, r)) for n, g, r in zip(names, got, grads) if not close(g, r, rtol=3e-4, atol=2e-5)]
     assert not bad, bad
+
+
+@pytest.mark.parametrize("src,dst", [((3, 3, 3), (12, 12, 12)), ((2, 5, 4), (8, 10, 8)), ((6, 6, 6), (12, 12, 12)), ((1, 3, 2), (4, 6, 8))])
+def test_resize_trilinear(emu, src, dst):
+    import torch.nn.functional as F
+    from veloxseg_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, *src)
+    y = ops.resize_fwd_raw(emu, 0, x, dst)
+    xr = x.clone().requires_grad_(True)
+    yr = F.interpolate(xr, size=dst, mode="trilinear", align_corners=True)
+    assert rel_err(y, yr) < 1e-6
+    dy = torch.randn_like(yr)
+    assert close(ops.resize_bwd_raw(emu, 0, dy, src), torch.autograd.grad(yr, xr, dy)[0], rtol=1e-5, atol=1e-6)

@@ -1,0 +1,62 @@
+"""Whole-model parity on the GPU: veloxseg_b200.nn.VeloxSeg (custom ops) against vectors produced by the unmodified
+reference for the three reference configs (+ a miniature), fp32: eval logits, train-mode outputs, loss and
+per-parameter gradients within the north_star tolerance (1e-3 relative; atol for structurally-zero gradients)."""
+import pytest
+import torch
+
+from tests import _golden as G
+from veloxseg_b200.configs import MODEL_CONFIGS
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _model(name):
+    from veloxseg_b200.nn import VeloxSeg
+    torch.manual_seed(G.MODEL_SEED)
+    m = VeloxSeg(**MODEL_CONFIGS[name])
+    G.zero_dropout(m)
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("name", ["tiny", "autopetii", "hecktor2022", "brats2021"])
+def test_whole_model_vs_reference(name):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    fx = G.load(f"model_{name}.pt")
+    cfg = MODEL_CONFIGS[name]
+    m = _model(name)
+    x = G.model_input(cfg, fx["B"]).to(DEV)
+    m.eval()
+    with torch.no_grad():
+        G.check_sample(m(x), fx["eval"], rtol=1e-3, what="eval logits")
+    m.train()
+    outs = m(x)
+    assert len(outs) == len(fx["train_outputs"])          # [seg x4, rcs, gram_s, gram_t x M]
+    for i, (o, r) in enumerate(zip(outs, fx["train_outputs"])):
+        G.check_sample(o, r, rtol=1e-3, atol=1e-7, what=f"train output {i}")
+    loss = sum((o * c.to(DEV)).sum() for o, c in zip(outs, G.cotangents(outs)))
+    assert abs(float(loss.detach()) - fx["loss"]) < 1e-3 * max(1.0, abs(fx["loss"]))
+    loss.backward()
+    bad = []
+    for k, p in m.named_parameters():
+        try:
+            G.check_sample(p.grad if p.grad is not None else torch.zeros_like(p), fx["grads"][k], rtol=1e-3, atol=1e-5, what=k)
+        except AssertionError as e:
+            bad.append(str(e))
+    assert not bad, bad[:10]
+
+
+def test_dropout_train_mode_runs_and_differs():
+    """Train mode with the config's dropout rates: finite outputs, different masks per step, eval unaffected."""
+    from veloxseg_b200.nn import VeloxSeg
+    torch.manual_seed(0)
+    m = VeloxSeg(**MODEL_CONFIGS["tiny"]).to(DEV)
+    x = torch.randn(2, 2, 64, 64, 64, device=DEV)
+    m.train()
+    a = m(x)[0]
+    b = m(x)[0]
+    assert torch.isfinite(a).all() and not torch.equal(a, b)
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m(x), m(x))

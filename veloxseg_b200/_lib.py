@@ -50,13 +50,19 @@ class SdktLossDesc(C.Structure):
     _fields_ = [("n_elem", C.c_int32), ("n_teachers", C.c_int32)]
 
 
+class ResizeDesc(C.Structure):
+    _fields_ = [("planes", C.c_int32), ("d", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("D", C.c_int32),
+                ("H", C.c_int32), ("W", C.c_int32)]
+
+
 class LnpwDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("C_in", C.c_int32), ("C_out", C.c_int32), ("S", C.c_int32), ("eps", C.c_float)]
 
 
 # every symbol include/veloxseg_abi.h declares
 SYMBOLS = [
-    "vx_version", "vx_last_error_string",
+    "vx_version", "vx_last_error_string", "vx_launch_count", "vx_profile_enable", "vx_profile_reset",
+    "vx_profile_report",
     "vx_jlc_workspace", "vx_jlc_fwd", "vx_jlc_bwd",
     "vx_mixer_workspace", "vx_mixer_fwd", "vx_mixer_bwd",
     "vx_inorm_fwd", "vx_inorm_bwd",
@@ -64,6 +70,7 @@ SYMBOLS = [
     "vx_gram_workspace", "vx_gram_fwd", "vx_gram_bwd",
     "vx_sdkt_loss_fwd", "vx_sdkt_loss_bwd",
     "vx_lnpw_workspace", "vx_lnpw_fwd", "vx_lnpw_bwd",
+    "vx_resize_workspace", "vx_resize_trilinear_fwd", "vx_resize_trilinear_bwd",
 ]
 
 _WS_OPS = {"jlc", "mixer", "pwa_block", "gram_fwd", "lnpw"}
@@ -92,17 +99,21 @@ class VxLib:
         self.c = C.CDLL(path)
         self.c.vx_last_error_string.restype = C.c_char_p
         self.c.vx_version.restype = C.c_int
+        self.c.vx_launch_count.restype = C.c_uint64
+        self.c.vx_profile_report.restype = C.c_size_t
+        self.c.vx_profile_report.argtypes = [C.c_char_p, C.c_size_t]
         for name in ("vx_jlc_workspace", "vx_mixer_workspace", "vx_pwa_workspace", "vx_gram_workspace",
-                     "vx_lnpw_workspace"):
+                     "vx_lnpw_workspace", "vx_resize_workspace"):
             getattr(self.c, name).restype = C.c_size_t
             getattr(self.c, name).argtypes = [C.c_void_p]
         vp, sz = C.c_void_p, C.c_size_t
         for name in ("vx_jlc_fwd", "vx_jlc_bwd", "vx_mixer_fwd", "vx_mixer_bwd", "vx_pwa_block_fwd", "vx_pwa_block_bwd",
-                     "vx_gram_fwd", "vx_lnpw_fwd", "vx_lnpw_bwd"):
+                     "vx_gram_fwd", "vx_lnpw_fwd", "vx_lnpw_bwd", "vx_resize_trilinear_bwd"):
             f = getattr(self.c, name)
             f.restype = C.c_int
             f.argtypes = [vp, vp, vp, vp, sz, vp]
-        for name in ("vx_inorm_fwd", "vx_inorm_bwd", "vx_gram_bwd", "vx_sdkt_loss_fwd", "vx_sdkt_loss_bwd"):
+        for name in ("vx_inorm_fwd", "vx_inorm_bwd", "vx_gram_bwd", "vx_sdkt_loss_fwd", "vx_sdkt_loss_bwd",
+                     "vx_resize_trilinear_fwd"):
             f = getattr(self.c, name)
             f.restype = C.c_int
             f.argtypes = [vp, vp, vp, vp]
@@ -110,6 +121,21 @@ class VxLib:
         self.c.vx_pwa_saved_layout.argtypes = [vp, vp]
         self.c.vx_pwa_gather.restype = C.c_int
         self.c.vx_pwa_gather.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
+
+    def profile(self, on: bool):
+        self.c.vx_profile_reset()
+        self.c.vx_profile_enable(int(on))
+
+    def profile_report(self):
+        """[(scope, kernel, launches, total_ms)] since the last profile(True)."""
+        n = self.c.vx_profile_report(None, 0)
+        buf = C.create_string_buffer(int(n) + 16)
+        self.c.vx_profile_report(buf, len(buf))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            scope, kern, cnt, ms = line.rsplit("|", 3)
+            rows.append((scope, kern, int(cnt), float(ms)))
+        return rows
 
     def last_error(self) -> str:
         s = self.c.vx_last_error_string()

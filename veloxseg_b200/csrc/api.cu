@@ -3,10 +3,17 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 namespace vx {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -24,7 +31,73 @@ int check_launch(const char* what) {
   return VX_OK;
 }
 
+static thread_local char g_scope[96] = "";
+void prof_scope(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_scope, sizeof(g_scope), fmt, ap);
+  va_end(ap);
+}
+
+#ifndef VX_EMU
+struct ProfRec { std::string key; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static int g_prof_on = 0;
+
+int prof_begin(const char* kernel, cudaStream_t st) {
+  if (!g_prof_on) return -1;
+  ProfRec r;
+  r.key = std::string(g_scope) + "|" + kernel;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  return (int)g_prof.size() - 1;
+}
+
+void prof_end(int slot, cudaStream_t st) {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[slot].b, st);
+}
+#endif
+
 }  // namespace vx
 
+#ifndef VX_EMU
+extern "C" int vx_profile_enable(int on) { const int prev = vx::g_prof_on; vx::g_prof_on = on; return prev; }
+extern "C" void vx_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(vx::g_prof_mu);
+  for (auto& r : vx::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  vx::g_prof.clear();
+}
+extern "C" size_t vx_profile_report(char* buf, size_t cap) {
+  std::lock_guard<std::mutex> lk(vx::g_prof_mu);
+  std::map<std::string, std::pair<int, double>> agg;
+  for (auto& r : vx::g_prof) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
+    auto& e = agg[r.key];
+    e.first += 1; e.second += ms;
+  }
+  std::string out;
+  char line[64];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof(line), "|%d|%.6f\n", kv.second.first, kv.second.second);
+    out += kv.first + line;
+  }
+  if (buf && cap > 0) { const size_t n = out.size() < cap - 1 ? out.size() : cap - 1; memcpy(buf, out.data(), n); buf[n] = 0; }
+  return out.size() + 1;
+}
+#else
+extern "C" int vx_profile_enable(int) { return 0; }
+extern "C" void vx_profile_reset(void) {}
+extern "C" size_t vx_profile_report(char*, size_t) { return 0; }
+#endif
+
 extern "C" int vx_version(void) { return 100; }
+extern "C" uint64_t vx_launch_count(void) { return __atomic_load_n(&vx::g_launches, __ATOMIC_RELAXED); }
 extern "C" const char* vx_last_error_string(void) { return vx::g_err; }

@@ -682,6 +682,7 @@ extern "C" int vx_jlc_fwd(const vx_jlc_desc* d, const void* const* in, void* con
                           size_t workspace_bytes, vx_stream_t stream) {
   JlcLayout L;
   VX_TRY(jlc_layout(d, L));
+  prof_scope("jlc_fwd B%d C%d S%d", d->B, d->C, d->D * d->H * d->W);
   if (!workspace || workspace_bytes < L.total) { set_error("jlc_fwd: workspace %zu < %zu", workspace_bytes, L.total); return VX_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
@@ -744,6 +745,7 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
                           size_t workspace_bytes, vx_stream_t stream) {
   JlcLayout L;
   VX_TRY(jlc_layout(d, L));
+  prof_scope("jlc_bwd B%d C%d S%d", d->B, d->C, d->D * d->H * d->W);
   if (!workspace || workspace_bytes < L.total) { set_error("jlc_bwd: workspace %zu < %zu", workspace_bytes, L.total); return VX_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;

@@ -137,6 +137,7 @@ extern "C" int vx_mixer_fwd(const vx_mixer_desc* d, const void* const* in, void*
                             size_t workspace_bytes, vx_stream_t stream) {
   int K;
   VX_TRY(mixer_check(d, K));
+  prof_scope("mixer_fwd B%d K%d N%d S%d", d->B, K, d->C_out, d->S);
   (void)workspace; (void)workspace_bytes;
   cudaStream_t st = (cudaStream_t)stream;
   const int M = d->n_streams;
@@ -159,6 +160,7 @@ extern "C" int vx_mixer_bwd(const vx_mixer_desc* d, const void* const* in, void*
                             size_t workspace_bytes, vx_stream_t stream) {
   int K;
   VX_TRY(mixer_check(d, K));
+  prof_scope("mixer_bwd B%d K%d N%d S%d", d->B, K, d->C_out, d->S);
   const size_t need = vx_mixer_workspace(d);
   if (!workspace || workspace_bytes < need) { set_error("mixer_bwd: workspace %zu < %zu", workspace_bytes, need); return VX_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -195,12 +197,14 @@ extern "C" int vx_mixer_bwd(const vx_mixer_desc* d, const void* const* in, void*
 // ---------------------------------------------------------------------------------------------------
 extern "C" int vx_inorm_fwd(const vx_inorm_desc* d, const void* const* in, void* const* out, vx_stream_t stream) {
   if (!d || d->rows <= 0 || d->S <= 0) { set_error("inorm: bad descriptor"); return VX_ERR_BAD_DESC; }
+  prof_scope("inorm_fwd R%d S%d", d->rows, d->S);
   return inorm_rows_fwd((const float*)in[0], d->has_addend ? (const float*)in[1] : nullptr, (float*)out[0],
                         (float*)out[1], d->rows, d->S, d->eps, (cudaStream_t)stream);
 }
 
 extern "C" int vx_inorm_bwd(const vx_inorm_desc* d, const void* const* in, void* const* out, vx_stream_t stream) {
   if (!d || d->rows <= 0 || d->S <= 0) { set_error("inorm: bad descriptor"); return VX_ERR_BAD_DESC; }
+  prof_scope("inorm_bwd R%d S%d", d->rows, d->S);
   return inorm_rows_bwd((const float*)in[0], (const float*)in[1], (const float*)in[2], nullptr, (float*)out[0], d->rows,
                         d->S, (cudaStream_t)stream);
 }
@@ -219,6 +223,7 @@ extern "C" int vx_gram_fwd(const vx_gram_desc* d, const void* const* in, void* c
   if (!need || d->C > 64) { set_error("gram: bad descriptor"); return VX_ERR_BAD_DESC; }
   if (!workspace || workspace_bytes < need) { set_error("gram_fwd: workspace %zu < %zu", workspace_bytes, need); return VX_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
+  prof_scope("gram_fwd B%d C%d S%d", d->B, d->C, d->S);
   const int nchunk = cdiv(d->S, GRAM_TV), CC = d->C * d->C;
   const size_t smem = sizeof(float) * (size_t)GRAM_TV * (d->C + 1);
   VX_SET_SMEM(gram_partial_kernel, smem);
@@ -232,6 +237,7 @@ extern "C" int vx_gram_fwd(const vx_gram_desc* d, const void* const* in, void* c
 extern "C" int vx_gram_bwd(const vx_gram_desc* d, const void* const* in, void* const* out, vx_stream_t stream) {
   if (!d || d->B <= 0 || d->C <= 0 || d->C > 64 || d->S <= 0) { set_error("gram: bad descriptor"); return VX_ERR_BAD_DESC; }
   cudaStream_t st = (cudaStream_t)stream;
+  prof_scope("gram_bwd B%d C%d S%d", d->B, d->C, d->S);
   const size_t smem = sizeof(float) * (size_t)d->C * d->C;
   const float scale = 1.0f / ((float)d->C * (float)d->S);
   dim3 grid(cdiv(d->S, 128), d->B);
@@ -254,6 +260,7 @@ extern "C" int vx_sdkt_loss_fwd(const vx_sdkt_loss_desc* d, const void* const* i
   A.gs = (const float*)in[0];
   for (int t = 0; t < A.T; ++t) A.gt[t] = (const float*)in[1 + t];
   A.loss = (float*)out[0];
+  prof_scope("sdkt_loss_fwd");
   VX_LAUNCH(sdkt_loss_fwd_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, A);
   return check_launch("sdkt_loss_fwd_kernel");
 }
@@ -265,6 +272,7 @@ extern "C" int vx_sdkt_loss_bwd(const vx_sdkt_loss_desc* d, const void* const* i
   A.gs = (const float*)in[1];
   for (int t = 0; t < A.T; ++t) { A.gt[t] = (const float*)in[2 + t]; A.dgt[t] = (float*)out[1 + t]; }
   A.dgs = (float*)out[0];
+  prof_scope("sdkt_loss_bwd");
   VX_LAUNCH(sdkt_loss_bwd_kernel, dim3(cdiv(A.n, 256)), dim3(256), 0, (cudaStream_t)stream, A);
   return check_launch("sdkt_loss_bwd_kernel");
 }
@@ -281,6 +289,7 @@ extern "C" int vx_lnpw_fwd(const vx_lnpw_desc* d, const void* const* in, void* c
                            size_t workspace_bytes, vx_stream_t stream) {
   if (!vx_lnpw_workspace(d)) { set_error("lnpw: bad descriptor"); return VX_ERR_BAD_DESC; }
   (void)workspace; (void)workspace_bytes;
+  prof_scope("lnpw_fwd B%d Ci%d Co%d S%d", d->B, d->C_in, d->C_out, d->S);
   cudaStream_t st = (cudaStream_t)stream;
   float* y = (float*)out[0];
   float* xhat = (float*)out[1];
@@ -301,6 +310,7 @@ extern "C" int vx_lnpw_bwd(const vx_lnpw_desc* d, const void* const* in, void* c
   const size_t need = vx_lnpw_workspace(d);
   if (!need) { set_error("lnpw: bad descriptor"); return VX_ERR_BAD_DESC; }
   if (!workspace || workspace_bytes < need) { set_error("lnpw_bwd: workspace %zu < %zu", workspace_bytes, need); return VX_ERR_WORKSPACE; }
+  prof_scope("lnpw_bwd B%d Ci%d Co%d S%d", d->B, d->C_in, d->C_out, d->S);
   cudaStream_t st = (cudaStream_t)stream;
   const float* dy = (const float*)in[0];
   const float* xhat = (const float*)in[1];

@@ -632,6 +632,7 @@ extern "C" int vx_pwa_block_fwd(const vx_pwa_desc* d, const void* const* in, voi
                                 size_t workspace_bytes, vx_stream_t stream) {
   PwaLayout P;
   VX_TRY(pwa_layout(d, P));
+  prof_scope("pwa_fwd B%d M%d C%d S%d L%d", d->B, d->M, d->C, P.G.S, P.G.L);
   if (!workspace || workspace_bytes < P.total) { set_error("pwa_fwd: workspace %zu < %zu", workspace_bytes, P.total); return VX_ERR_WORKSPACE; }
   const PwaGeo& G = P.G;
   cudaStream_t st = (cudaStream_t)stream;
@@ -749,6 +750,7 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
                                 size_t workspace_bytes, vx_stream_t stream) {
   PwaLayout P;
   VX_TRY(pwa_layout(d, P));
+  prof_scope("pwa_bwd B%d M%d C%d S%d L%d", d->B, d->M, d->C, P.G.S, P.G.L);
   if (!workspace || workspace_bytes < P.total) { set_error("pwa_bwd: workspace %zu < %zu", workspace_bytes, P.total); return VX_ERR_WORKSPACE; }
   const PwaGeo& G = P.G;
   cudaStream_t st = (cudaStream_t)stream;

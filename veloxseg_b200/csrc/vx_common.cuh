@@ -22,7 +22,8 @@
 #define VX_SET_SMEM(kern, bytes) do { } while (0)
 #else
 #define VX_LAUNCH(kern, grid, block, smem, stream, ...)                                   \
-  do { auto _k = kern; _k<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); } while (0)
+  do { auto _k = kern; const int _pi = vx::prof_begin(#kern, (stream));                  \
+       _k<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); vx::count_launch(); vx::prof_end(_pi, (stream)); } while (0)
 #define VX_DYN_SMEM(type, name)                                                           \
   extern __shared__ __align__(16) unsigned char vx_dsm_[];                                \
   type* name = reinterpret_cast<type*>(vx_dsm_)
@@ -38,6 +39,12 @@ namespace vx {
 constexpr int kSMs = 148;
 
 void set_error(const char* fmt, ...);
+void count_launch();
+#ifndef VX_EMU
+int prof_begin(const char* kernel, cudaStream_t st);   // -1 when profiling is off
+void prof_end(int slot, cudaStream_t st);
+#endif
+void prof_scope(const char* fmt, ...);                 // names the op whose kernels follow (thread-local)
 int check_launch(const char* what);   // cudaGetLastError -> vx_status
 
 VX_DEV float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }

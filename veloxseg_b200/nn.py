@@ -15,7 +15,7 @@ Reference files (path:line into the reference repository):
   PixelShuffle                             model/components/superpixel.py:4-17
   Encoder / Seg_Decoder / RC_Decoder / VeloxSeg   model/Encoder.py, model/Decoder.py, model/VeloxSeg.py
 What stays on library kernels (SURVEY.md section 8f "next" rows): the strided DownConv / ConvTranspose UpConv /
-PatchEmbed stems, the dense 3x3x3 output convs, trilinear `scale_prediction`.
+PatchEmbed stems and the dense 3x3x3 output convs.
 """
 from __future__ import annotations
 
@@ -612,7 +612,7 @@ class VeloxSeg(nn.Module):
         self.apply(InitWeights_He(neg_slope=1e-2))
 
     def scale_prediction(self, pred):
-        return F.interpolate(pred, size=tuple(self.size), mode="trilinear", align_corners=True)
+        return ops.resize_trilinear(pred, tuple(self.size))
 
     def forward(self, x):
         if self.training:

@@ -17,8 +17,8 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (GramDesc, InormDesc, JlcDesc, LnpwDesc, MixerDesc, PwaDesc, PwaSaved, SdktLossDesc, VX_MAX_MODAL,
-                   VX_MAX_SCALES)
+from ._lib import (GramDesc, InormDesc, JlcDesc, LnpwDesc, MixerDesc, PwaDesc, PwaSaved, ResizeDesc, SdktLossDesc,
+                   VX_MAX_MODAL, VX_MAX_SCALES)
 
 Tensor = torch.Tensor
 _f32 = torch.float32
@@ -196,6 +196,31 @@ def lnpw_bwd_raw(lib, stream, dy, xhat, rstd, ln_w, ln_b, W):
 
 
 # ----------------------------------------------------------------------------------------------------
+# trilinear resize (align_corners=True)
+# ----------------------------------------------------------------------------------------------------
+def resize_fwd_raw(lib, stream, x, size: Sequence[int]):
+    x = _chk(x, "x")
+    B, Cc, d, h, w = x.shape
+    D, H, W = [int(v) for v in size]
+    desc = ResizeDesc(B * Cc, d, h, w, D, H, W)
+    y = torch.empty((B, Cc, D, H, W), dtype=_f32, device=x.device)
+    lib.call("vx_resize_trilinear_fwd", desc, [x], [y], stream)
+    return y
+
+
+def resize_bwd_raw(lib, stream, dy, size: Sequence[int]):
+    """dy (B, C, D, H, W) -> dx (B, C, *size)."""
+    dy = _chk(dy, "dy")
+    B, Cc, D, H, W = dy.shape
+    d, h, w = [int(v) for v in size]
+    desc = ResizeDesc(B * Cc, d, h, w, D, H, W)
+    dx = torch.empty((B, Cc, d, h, w), dtype=_f32, device=dy.device)
+    ws = _ws(lib, "resize", desc, dy)
+    lib.call_ws("vx_resize_trilinear_bwd", desc, [dy], [dx], ws, stream)
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------------
 # PWA block
 # ----------------------------------------------------------------------------------------------------
 PWA_PARAMS_PER_MODALITY = 16   # ln1_w, ln1_b, wq, bq, wk, bk, wv, bv, wmix, bmix, ln2_w, ln2_b, w1, b1, w2, b2
@@ -283,6 +308,8 @@ _L.define("gram_fwd(Tensor x) -> Tensor")
 _L.define("gram_bwd(Tensor dG, Tensor x) -> Tensor")
 _L.define("sdkt_loss_fwd(Tensor gs, Tensor[] gts) -> Tensor")
 _L.define("sdkt_loss_bwd(Tensor dloss, Tensor gs, Tensor[] gts) -> Tensor[]")
+_L.define("resize_fwd(Tensor x, int[] size) -> Tensor")
+_L.define("resize_bwd(Tensor dy, int[] size) -> Tensor")
 _L.define("lnpw_fwd(Tensor x, Tensor ln_w, Tensor ln_b, Tensor W) -> Tensor[]")
 _L.define("lnpw_bwd(Tensor dy, Tensor xhat, Tensor rstd, Tensor ln_w, Tensor ln_b, Tensor W) -> Tensor[]")
 
@@ -304,6 +331,8 @@ _L.impl("gram_fwd", _cuda(gram_fwd_raw), "CUDA")
 _L.impl("gram_bwd", _cuda(gram_bwd_raw), "CUDA")
 _L.impl("sdkt_loss_fwd", _cuda(sdkt_loss_fwd_raw), "CUDA")
 _L.impl("sdkt_loss_bwd", _cuda(sdkt_loss_bwd_raw), "CUDA")
+_L.impl("resize_fwd", _cuda(resize_fwd_raw), "CUDA")
+_L.impl("resize_bwd", _cuda(resize_bwd_raw), "CUDA")
 _L.impl("lnpw_fwd", _cuda(lnpw_fwd_raw), "CUDA")
 _L.impl("lnpw_bwd", _cuda(lnpw_bwd_raw), "CUDA")
 
@@ -428,6 +457,26 @@ def ln_pointwise(x: Tensor, ln_w: Tensor, ln_b: Tensor, W: Tensor) -> Tensor:
     """W . LayerNorm_channels_first(x)   (no bias);  W (Co, Ci) or (Co, Ci, 1, 1, 1)."""
     Wm = W.reshape(W.shape[0], -1)
     return _LnPw.apply(x.contiguous(), ln_w, ln_b, Wm)
+
+
+class _Resize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size):
+        ctx.in_size = tuple(x.shape[2:])
+        return _vx.resize_fwd(x, list(size))
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _vx.resize_bwd(dy.contiguous(), list(ctx.in_size)), None
+
+
+def resize_trilinear(x: Tensor, size: Sequence[int]) -> Tensor:
+    """F.interpolate(x, size=size, mode='trilinear', align_corners=True).  Same-size requests are the identity
+    (source coordinate == destination index exactly), so the input is returned as is."""
+    size = tuple(int(v) for v in size)
+    if tuple(x.shape[2:]) == size:
+        return x
+    return _Resize.apply(x.contiguous(), size)
 
 
 class _PwaBlock(torch.autograd.Function):

@@ -1,0 +1,101 @@
+"""Data-parallel training step (new capability; the reference trains on one device, utils/train_autopet.py:219-268).
+
+Step semantics follow the reference loop: inputs = cat(modalities) (B, sum(in_ch), *patch) -> model(train) ->
+Loss(output, labels, sr_labels=inputs) -> backward -> AdamW step (lr 2.5e-4, wd 0.01).  One process per GPU; every
+norm in the model is per-sample, so ranks exchange nothing but gradients: `GradBuckets` lays the parameters out in a
+few flat fp32 buckets (reverse registration order ~ backward completion order), exposes `.grad` as views into them and
+launches one asynchronous all-reduce per bucket from the autograd hooks while the rest of backward is still running.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .loss import Loss
+
+
+class GradBuckets:
+    """Flat gradient buckets with all-reduce launched as each bucket's last gradient is produced."""
+
+    def __init__(self, params: List[torch.nn.Parameter], bucket_bytes: int = 4 << 20, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        order = list(reversed(self.params))                 # decoders finish first in backward
+        self.buckets: List[torch.Tensor] = []
+        self.bucket_of, self.pending, self.total = {}, [], []
+        cur, cur_bytes = [], 0
+        groups = []
+        for p in order:
+            cur.append(p)
+            cur_bytes += p.numel() * p.element_size()
+            if cur_bytes >= bucket_bytes:
+                groups.append(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            groups.append(cur)
+        for bi, g in enumerate(groups):
+            flat = torch.zeros(sum(p.numel() for p in g), dtype=g[0].dtype, device=g[0].device)
+            off = 0
+            for p in g:
+                p.grad = flat[off:off + p.numel()].view_as(p)        # gradients accumulate straight into the bucket
+                off += p.numel()
+                self.bucket_of[p] = bi
+            self.buckets.append(flat)
+            self.total.append(len(g))
+        self.pending = list(self.total)
+        self.works: List[Optional[object]] = [None] * len(self.buckets)
+        self.comm_stream = None
+        if self.world > 1:
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._ready)
+
+    def zero(self):
+        for b in self.buckets:
+            b.zero_()
+        self.pending = list(self.total)
+        self.works = [None] * len(self.buckets)
+
+    def _ready(self, p):
+        bi = self.bucket_of[p]
+        self.pending[bi] -= 1
+        if self.pending[bi] == 0:
+            self.works[bi] = dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self):
+        """Wait for the outstanding all-reduces and turn sums into means (equal B_local on every rank)."""
+        if self.world == 1:
+            return
+        for bi, w in enumerate(self.works):
+            if w is None:       # a bucket whose parameters received no gradient this step
+                w = dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            w.wait()
+            self.buckets[bi].div_(self.world)
+
+
+class TrainStep:
+    """`step(inputs, labels)` = one optimisation step; accepts host (pinned) or device tensors and returns the loss
+    as a Python float only when asked (`sync=True`), mirroring the reference's per-step `loss.item()`."""
+
+    def __init__(self, model: torch.nn.Module, num_modal: int, device, lr: float = 2.5e-4, weight_decay: float = 0.01,
+                 deep_weights=(1, 1, 1, 1), rc_weight: float = 0.5, feature_weight: float = 2.0,
+                 bucket_bytes: int = 4 << 20):
+        self.device = torch.device(device)
+        self.model = model.to(self.device).train()
+        self.loss_fn = Loss(num_modal, deep_weights, rc_weight, feature_weight)
+        self.buckets = GradBuckets(list(self.model.parameters()), bucket_bytes)
+        fused = self.device.type == "cuda"
+        self.opt = torch.optim.AdamW(self.model.parameters(), lr=lr, weight_decay=weight_decay, fused=fused)
+
+    def step(self, inputs: torch.Tensor, labels: torch.Tensor, sync: bool = False):
+        x = inputs.to(self.device, non_blocking=True)
+        y = labels.to(self.device, non_blocking=True)
+        self.buckets.zero()
+        out = self.model(x)
+        loss = self.loss_fn(out, y, x)
+        loss.backward()
+        self.buckets.finish()
+        self.opt.step()
+        return float(loss.item()) if sync else loss.detach()
