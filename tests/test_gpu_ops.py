@@ -157,14 +157,15 @@ def test_jlc_dropout_mask_consistency(ops):
     lib, st = _lib.get_lib(), torch.cuda.current_stream().cuda_stream
     y0, z, o, hpre, stats = ops.jlc_fwd_raw(lib, st, x, params, groups, e, 0.0, False, 0)
     y1, _, o1, *_ = ops.jlc_fwd_raw(lib, st, x, params, groups, e, 0.5, True, 1234)
-    y2, *_ = ops.jlc_fwd_raw(lib, st, x, params, groups, e, 0.5, True, 1234)
-    y3, *_ = ops.jlc_fwd_raw(lib, st, x, params, groups, e, 0.5, True, 99)
-    # same seed -> same mask (values agree to rounding: the InstanceNorm partial sums use fp32 atomics)
-    assert torch.equal(y1 == o1, y2 == o1) and torch.allclose(y1, y2, rtol=1e-5, atol=1e-6) and not torch.equal(y1 == o1, y3 == o1)
+    y2, _, o2, *_ = ops.jlc_fwd_raw(lib, st, x, params, groups, e, 0.5, True, 1234)
+    y3, _, o3, *_ = ops.jlc_fwd_raw(lib, st, x, params, groups, e, 0.5, True, 99)
+    # same seed -> same mask (values agree to rounding only: the InstanceNorm partial sums use fp32 atomics)
+    assert torch.equal(y1 == o1, y2 == o2) and torch.allclose(y1, y2, rtol=1e-4, atol=1e-5)
+    assert not torch.equal(y1 == o1, y3 == o3)
     d0, d1 = (y0 - o), (y1 - o1)
     dropped = d1 == 0
     assert 0.45 < dropped.float().mean().item() < 0.55
-    assert torch.allclose(d1[~dropped], 2 * d0[~dropped], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(d1[~dropped], 2 * d0[~dropped], rtol=1e-3, atol=1e-4)
     # backward uses the same mask: d(sum y)/d(fb2) = kept fraction * 2 per channel
     xg = x.clone().requires_grad_(True)
     pg = [p.clone().requires_grad_(True) for p in params]

@@ -45,14 +45,23 @@ static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 static int g_prof_on = 0;
 
+static std::vector<cudaEvent_t> g_pool;   // events are created once and recycled (creation costs tens of microseconds)
+
+static cudaEvent_t pool_get() {
+  if (g_pool.empty()) { cudaEvent_t e; cudaEventCreate(&e); return e; }
+  cudaEvent_t e = g_pool.back();
+  g_pool.pop_back();
+  return e;
+}
+
 int prof_begin(const char* kernel, cudaStream_t st) {
   if (!g_prof_on) return -1;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   ProfRec r;
   r.key = std::string(g_scope) + "|" + kernel;
-  cudaEventCreate(&r.a);
-  cudaEventCreate(&r.b);
+  r.a = pool_get();
+  r.b = pool_get();
   cudaEventRecord(r.a, st);
-  std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof.push_back(r);
   return (int)g_prof.size() - 1;
 }
@@ -67,10 +76,18 @@ void prof_end(int slot, cudaStream_t st) {
 }  // namespace vx
 
 #ifndef VX_EMU
-extern "C" int vx_profile_enable(int on) { const int prev = vx::g_prof_on; vx::g_prof_on = on; return prev; }
+extern "C" int vx_profile_enable(int on) {
+  const int prev = vx::g_prof_on;
+  if (on && !prev) {     // pre-create a pool so that the profiled pass does not pay for event creation
+    std::lock_guard<std::mutex> lk(vx::g_prof_mu);
+    while (vx::g_pool.size() < 8192) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) break; vx::g_pool.push_back(e); }
+  }
+  vx::g_prof_on = on;
+  return prev;
+}
 extern "C" void vx_profile_reset(void) {
   std::lock_guard<std::mutex> lk(vx::g_prof_mu);
-  for (auto& r : vx::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto& r : vx::g_prof) { vx::g_pool.push_back(r.a); vx::g_pool.push_back(r.b); }
   vx::g_prof.clear();
 }
 extern "C" size_t vx_profile_report(char* buf, size_t cap) {

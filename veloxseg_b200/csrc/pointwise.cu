@@ -14,19 +14,20 @@
 namespace vx {
 
 constexpr int PW_THREADS = 128;
-constexpr int PW_TV = 256;
-constexpr int PW_CO = 16;
+constexpr int PW_TS = 64;    // voxels per CTA tile
+constexpr int PW_TC = 64;    // output channels per CTA tile
+constexpr int PW_KC = 16;    // input channels per staged chunk
 
 VX_DEV float pw_weight(const PwProblem& P, int co, int ci) {
   int off = 0;
   if (!P.transposed) {
     for (int s = 0; s < P.nseg; ++s) {
-      if (co < off + P.seg[s].n) return P.seg[s].W[(size_t)(co - off) * P.seg[s].ld + ci];
+      if (co < off + P.seg[s].n) return __ldg(P.seg[s].W + (size_t)(co - off) * P.seg[s].ld + ci);
       off += P.seg[s].n;
     }
   } else {
     for (int s = 0; s < P.nseg; ++s) {
-      if (ci < off + P.seg[s].n) return P.seg[s].W[(size_t)(ci - off) * P.seg[s].ld + co];
+      if (ci < off + P.seg[s].n) return __ldg(P.seg[s].W + (size_t)(ci - off) * P.seg[s].ld + co);
       off += P.seg[s].n;
     }
   }
@@ -37,118 +38,160 @@ VX_DEV float pw_bias(const PwProblem& P, int co) {
   if (P.transposed) return 0.f;
   int off = 0;
   for (int s = 0; s < P.nseg; ++s) {
-    if (co < off + P.seg[s].n) return P.seg[s].bias ? P.seg[s].bias[co - off] : 0.f;
+    if (co < off + P.seg[s].n) return P.seg[s].bias ? __ldg(P.seg[s].bias + co - off) : 0.f;
     off += P.seg[s].n;
   }
   return 0.f;
 }
 
+// Raw load of one input element (the prologue is applied later, when the value is committed to shared memory, so the
+// global loads of chunk k+1 stay in flight while chunk k is being multiplied).
+VX_DEV float pw_fetch_x(const PwProblem& P, int b, int cg, int v, int S) {
+  int c = cg, s = 0;
+  while (s < P.nsrc - 1 && c >= P.src[s].C) { c -= P.src[s].C; ++s; }
+  return __ldg(P.src[s].ptr + ((size_t)b * P.src[s].C + c) * S + v);
+}
+VX_DEV float pw_prologue(const PwProblem& P, float x, int b, int cg, int v, int S, float pinv) {
+  if (P.pro == PRO_AFFINE) {
+    const int k = b * P.pro_bstride + cg;
+    x = fmaf(x, __ldg(P.pro_a + k), __ldg(P.pro_c + k));
+  } else if (P.pro == PRO_GELU || P.pro == PRO_GELU_DROPOUT) {
+    x = gelu_f(x);
+  }
+  if (P.pro == PRO_DROPOUT || P.pro == PRO_GELU_DROPOUT)
+    x *= dropout_scale(P.pro_seed, P.pro_site, ((uint64_t)b * P.Ci + cg) * (uint64_t)S + v, P.pro_drop_p, pinv);
+  return x;
+}
+
+// Y[b, co, v] = epi( sum_ci W[co, ci] * pro(X[b, ci, v]) + bias[co] ) as a register-tiled GEMM: CTA tile = 64 voxels x
+// 64 output channels, K staged 16 channels at a time through double-buffered shared memory; a thread owns 4 voxels x
+// 8 channels (32 accumulators, 3 LDS.128 per 32 FMA).  Warp = 16 voxel groups x 2 channel groups, so the X reads of a
+// warp are two 128-B wavefronts and the W reads are broadcasts.
 __global__ void __launch_bounds__(PW_THREADS) pw_kernel(const __grid_constant__ PwBatch batch) {
   const int pi = blockIdx.z / batch.B, b = blockIdx.z % batch.B;
   const PwProblem& P = batch.p[pi];
   const int S = batch.S, Ci = P.Ci, Co = P.Co;
-  const int co0 = blockIdx.y * PW_CO;
+  const int co0 = blockIdx.y * PW_TC, v0 = blockIdx.x * PW_TS;
   if (co0 >= Co) return;
-  VX_DYN_SMEM(float, sm);
-  float* Ws = sm;              // [Ci][16], prologue-folded
-  float* bf = Ws + Ci * PW_CO; // [16] folded bias
+  __align__(16) __shared__ float Xs[2][PW_KC][PW_TS];
+  __align__(16) __shared__ float Ws[2][PW_KC][PW_TC];
   const int tid = threadIdx.x;
-
-  for (int idx = tid; idx < Ci * PW_CO; idx += PW_THREADS) {
-    const int ci = idx / PW_CO, j = idx % PW_CO, co = co0 + j;
-    float w = co < Co ? pw_weight(P, co, ci) : 0.f;
-    if (P.pro == PRO_AFFINE) w *= P.pro_a[b * P.pro_bstride + ci];
-    Ws[idx] = w;
-  }
-  if (tid < PW_CO) {
-    const int co = co0 + tid;
-    float bb = 0.f;
-    if (co < Co) {
-      bb = pw_bias(P, co);
-      if (P.pro == PRO_AFFINE)
-        for (int ci = 0; ci < Ci; ++ci) bb += pw_weight(P, co, ci) * P.pro_c[b * P.pro_bstride + ci];
-    }
-    bf[tid] = bb;
-  }
-  __syncthreads();
-
-  const int v0 = blockIdx.x * PW_TV + tid, v1 = v0 + PW_THREADS;
-  const bool ok0 = v0 < S, ok1 = v1 < S;
-  float acc0[PW_CO], acc1[PW_CO];
-#pragma unroll
-  for (int j = 0; j < PW_CO; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
-
+  const int vg = tid & 15, cgp = tid >> 4;            // voxel group (4 voxels), channel group (8 channels)
   const bool pro_drop = P.pro == PRO_DROPOUT || P.pro == PRO_GELU_DROPOUT;
   const float pinv = pro_drop ? 1.0f / (1.0f - P.pro_drop_p) : 1.f;
-  int cg = 0;
-  for (int s = 0; s < P.nsrc; ++s) {
-    const int Cs = P.src[s].C;
-    const float* xp = P.src[s].ptr + (size_t)b * Cs * S;
-    for (int c = 0; c < Cs; ++c, ++cg) {
-      float x0 = ok0 ? __ldg(xp + (size_t)c * S + v0) : 0.f;
-      float x1 = ok1 ? __ldg(xp + (size_t)c * S + v1) : 0.f;
-      if (P.pro == PRO_GELU || P.pro == PRO_GELU_DROPOUT) { x0 = gelu_f(x0); x1 = gelu_f(x1); }
-      if (pro_drop) {
-        const uint64_t base = ((uint64_t)b * Ci + cg) * (uint64_t)S;
-        x0 *= dropout_scale(P.pro_seed, P.pro_site, base + v0, P.pro_drop_p, pinv);
-        x1 *= dropout_scale(P.pro_seed, P.pro_site, base + v1, P.pro_drop_p, pinv);
-      }
-      const float4* w4 = reinterpret_cast<const float4*>(Ws + cg * PW_CO);
+
+  float acc[8][4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 w = w4[q];
-        acc0[4 * q + 0] = fmaf(w.x, x0, acc0[4 * q + 0]); acc1[4 * q + 0] = fmaf(w.x, x1, acc1[4 * q + 0]);
-        acc0[4 * q + 1] = fmaf(w.y, x0, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(w.y, x1, acc1[4 * q + 1]);
-        acc0[4 * q + 2] = fmaf(w.z, x0, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(w.z, x1, acc1[4 * q + 2]);
-        acc0[4 * q + 3] = fmaf(w.w, x0, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(w.w, x1, acc1[4 * q + 3]);
-      }
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+
+  // staging maps: X chunk 16 x 64 -> 8 elements per thread (voxel fastest: coalesced), W chunk 16 x 64 likewise
+  float xr[8], wr[8];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int e = r * PW_THREADS + tid;
+      const int v = e & (PW_TS - 1), k = e >> 6;
+      xr[r] = (k0 + k < Ci && v0 + v < S) ? pw_fetch_x(P, b, k0 + k, v0 + v, S) : 0.f;
     }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int e = r * PW_THREADS + tid;
+      // forward orientation reads W[co][ci] (ci contiguous): k fastest; transposed reads W[ci][co]: co fastest
+      const int k = P.transposed ? (e >> 6) : (e & (PW_KC - 1));
+      const int c = P.transposed ? (e & (PW_TC - 1)) : (e >> 4);
+      wr[r] = (k0 + k < Ci && co0 + c < Co) ? pw_weight(P, co0 + c, k0 + k) : 0.f;
+    }
+  };
+  auto commit = [&](int buf, int k0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int e = r * PW_THREADS + tid;
+      const int v = e & (PW_TS - 1), k = e >> 6;
+      float x = xr[r];
+      if (P.pro != PRO_NONE && k0 + k < Ci && v0 + v < S) x = pw_prologue(P, x, b, k0 + k, v0 + v, S, pinv);
+      Xs[buf][k][v] = x;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int e = r * PW_THREADS + tid;
+      const int k = P.transposed ? (e >> 6) : (e & (PW_KC - 1));
+      const int c = P.transposed ? (e & (PW_TC - 1)) : (e >> 4);
+      Ws[buf][k][c] = wr[r];
+    }
+  };
+
+  const int nchunk = (Ci + PW_KC - 1) / PW_KC;
+  fetch(0);
+  commit(0, 0);
+  __syncthreads();
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunk) fetch((ch + 1) * PW_KC);
+#pragma unroll
+    for (int k = 0; k < PW_KC; ++k) {
+      const float4 x = *reinterpret_cast<const float4*>(&Xs[buf][k][vg * 4]);
+      const float4 wa = *reinterpret_cast<const float4*>(&Ws[buf][k][cgp * 8]);
+      const float4 wb = *reinterpret_cast<const float4*>(&Ws[buf][k][cgp * 8 + 4]);
+      const float xs[4] = {x.x, x.y, x.z, x.w};
+      const float ws[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(ws[j], xs[i], acc[j][i]);
+    }
+    if (ch + 1 < nchunk) commit(buf ^ 1, (ch + 1) * PW_KC);
+    __syncthreads();
   }
 
+  // epilogue
   const float dinv = P.drop_p > 0.f ? 1.0f / (1.0f - P.drop_p) : 1.f;
-  // output segment bookkeeping (forward orientation may write several tensors)
-  int seg = 0, seg_off = 0;
+  const int vb = v0 + vg * 4;
+  const bool vec = ((S & 3) == 0) && (vb + 3 < S);
 #pragma unroll
-  for (int j = 0; j < PW_CO; ++j) {
-    const int co = co0 + j;
+  for (int j = 0; j < 8; ++j) {
+    const int co = co0 + cgp * 8 + j;
     if (co >= Co) break;
     float* outp;
     if (!P.transposed) {
+      int seg = 0, seg_off = 0;
       while (co >= seg_off + P.seg[seg].n) { seg_off += P.seg[seg].n; ++seg; }
       outp = P.seg[seg].out + ((size_t)b * P.seg[seg].n + (co - seg_off)) * S;
     } else {
       outp = P.seg[0].out + ((size_t)b * Co + co) * S;
     }
     const size_t lbase = ((size_t)b * Co + co) * S;   // index in the logical (B, Co, S) tensor
-    float y0 = acc0[j] + bf[j], y1 = acc1[j] + bf[j];
-    if (P.act == 1) { y0 = gelu_f(y0); y1 = gelu_f(y1); }
-    if (P.mulgrad) {
-      if (ok0) y0 *= gelu_grad_f(P.mulgrad[lbase + v0]);
-      if (ok1) y1 *= gelu_grad_f(P.mulgrad[lbase + v1]);
+    const float bias = pw_bias(P, co);
+    float y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int v = vb + i;
+      float t = acc[j][i] + bias;
+      if (v < S) {
+        if (P.act == 1) t = gelu_f(t);
+        if (P.mulgrad) t *= gelu_grad_f(__ldg(P.mulgrad + lbase + v));
+        if (P.drop_p > 0.f) t *= dropout_scale(P.seed, P.site, lbase + v, P.drop_p, dinv);
+        if (P.res) t = fmaf(P.res_scale, __ldg(P.res + lbase + v), t);
+        if (P.res2) t += __ldg(P.res2 + lbase + v);
+      }
+      y[i] = t;
     }
-    if (P.drop_p > 0.f) {
-      y0 *= dropout_scale(P.seed, P.site, lbase + v0, P.drop_p, dinv);
-      y1 *= dropout_scale(P.seed, P.site, lbase + v1, P.drop_p, dinv);
+    if (vec) {
+      *reinterpret_cast<float4*>(outp + vb) = make_float4(y[0], y[1], y[2], y[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (vb + i < S) outp[vb + i] = y[i];
     }
-    if (P.res) {
-      if (ok0) y0 = fmaf(P.res_scale, P.res[lbase + v0], y0);
-      if (ok1) y1 = fmaf(P.res_scale, P.res[lbase + v1], y1);
-    }
-    if (P.res2) {
-      if (ok0) y0 += P.res2[lbase + v0];
-      if (ok1) y1 += P.res2[lbase + v1];
-    }
-    if (ok0) outp[v0] = y0;
-    if (ok1) outp[v1] = y1;
   }
 }
 
 int pw_forward(const PwBatch& batch, cudaStream_t stream) {
-  int maxCo = 0, maxCi = 0;
+  int maxCo = 0;
   for (int i = 0; i < batch.nprob; ++i) {
     const PwProblem& P = batch.p[i];
     maxCo = P.Co > maxCo ? P.Co : maxCo;
-    maxCi = P.Ci > maxCi ? P.Ci : maxCi;
     int cs = 0;
     for (int s = 0; s < P.nsrc; ++s) cs += P.src[s].C;
     if (cs != P.Ci) { set_error("pw_forward: source channels %d != Ci %d", cs, P.Ci); return VX_ERR_BAD_DESC; }
@@ -157,10 +200,8 @@ int pw_forward(const PwBatch& batch, cudaStream_t stream) {
     }
   }
   if (batch.nprob <= 0 || batch.B <= 0 || batch.S <= 0) return VX_OK;
-  const size_t smem = (size_t)(maxCi * PW_CO + PW_CO) * sizeof(float);
-  VX_SET_SMEM(pw_kernel, smem);
-  dim3 grid(cdiv(batch.S, PW_TV), cdiv(maxCo, PW_CO), batch.nprob * batch.B);
-  VX_LAUNCH(pw_kernel, grid, dim3(PW_THREADS), smem, stream, batch);
+  dim3 grid(cdiv(batch.S, PW_TS), cdiv(maxCo, PW_TC), batch.nprob * batch.B);
+  VX_LAUNCH(pw_kernel, grid, dim3(PW_THREADS), 0, stream, batch);
   return check_launch("pw_kernel");
 }
 
@@ -169,10 +210,14 @@ int pw_forward(const PwBatch& batch, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------------
 constexpr int WG_THREADS = 256;
 
+// CTA = persistent over voxel chunks (blockIdx.x strides the chunk list) of one (problem, batch item).  Per chunk the
+// dY and X tiles are transposed into shared memory ([voxel][channel], channel padded to 4 * odd so that the float4 reads
+// of 4 consecutive channels are conflict-free) and every thread accumulates one 4x4 block of dW in registers over a
+// slice of the chunk's voxels.  The voxel slices are folded in shared memory and each CTA issues ONE global atomic per
+// dW element, so the number of atomics per address is the (small) grid size, not the number of voxel chunks.
 __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_kernel(const __grid_constant__ WgBatch batch, int TV) {
   const WgProblem& P = batch.p[blockIdx.z];
   const int b = blockIdx.y, S = batch.S;
-  const int vbase = blockIdx.x * TV;
   const int Co = P.Co, Ci = P.Ci;
   const int Co4 = (Co + 3) & ~3, Ci4 = (Ci + 1 + 3) & ~3;    // +1: the all-ones row that yields db
   const int CoP = Co4 + 4, CiP = Ci4 + 4;
@@ -180,83 +225,116 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_kernel(const __grid_const
   float* sY = sm;                     // [TV][CoP]
   float* sX = sm + (size_t)TV * CoP;  // [TV][CiP]
   const int tid = threadIdx.x;
-
-  const float yinv = P.y_drop_p > 0.f ? 1.0f / (1.0f - P.y_drop_p) : 1.f;
-  for (int idx = tid; idx < Co4 * TV; idx += WG_THREADS) {
-    const int co = idx / TV, v = idx % TV, gv = vbase + v;
-    float val = 0.f;
-    if (co < Co && gv < S) {
-      const size_t gi = ((size_t)b * Co + co) * S + gv;
-      val = __ldg(P.dY + gi);
-      if (P.y_drop_p > 0.f) val *= dropout_scale(P.y_seed, P.y_site, gi, P.y_drop_p, yinv);
-    }
-    sY[v * CoP + co] = val;
-  }
-  {
-    int cg0 = 0;
-    for (int s = 0; s < P.nsrc; ++s) {
-      const int Cs = P.src[s].C;
-      const float* xp = P.src[s].ptr + (size_t)b * Cs * S;
-      for (int idx = tid; idx < Cs * TV; idx += WG_THREADS) {
-        const int c = idx / TV, v = idx % TV, gv = vbase + v;
-        float val = 0.f;
-        if (gv < S) {
-          val = __ldg(xp + (size_t)c * S + gv);
-          if (P.xpro == PRO_AFFINE) {
-            const int k = b * P.x_bstride + cg0 + c;
-            val = fmaf(val, P.xa[k], P.xc[k]);
-          } else if (P.xpro == PRO_GELU) {
-            val = gelu_f(val);
-          } else if (P.xpro == PRO_GELU_DROPOUT) {
-            val = gelu_f(val) * dropout_scale(P.x_seed, P.x_site, ((uint64_t)b * Ci + cg0 + c) * (uint64_t)S + gv, P.x_drop_p,
-                                              1.0f / (1.0f - P.x_drop_p));
-          }
-        }
-        sX[v * CiP + cg0 + c] = val;
-      }
-      cg0 += Cs;
-    }
-    for (int idx = tid; idx < (Ci4 - Ci) * TV; idx += WG_THREADS) {
-      const int c = Ci + idx / TV, v = idx % TV;
-      sX[v * CiP + c] = (c == Ci && vbase + v < S) ? 1.f : 0.f;
-    }
-  }
-  __syncthreads();
-
   const int nCo4 = Co4 >> 2, nCi4 = Ci4 >> 2, ntiles = nCo4 * nCi4;
   // When there are fewer 4x4 tiles than threads, split the voxel range between thread groups.
   int G = 1;
   while (G * 2 * ntiles <= WG_THREADS && (TV / (G * 2)) >= 8) G *= 2;
   const int span = TV / G;
-  for (int t = tid; t < ntiles * G; t += WG_THREADS) {
-    const int tile = t % ntiles, grp = t / ntiles;
+  const int npass = (ntiles * G + WG_THREADS - 1) / WG_THREADS;    // tiles per thread (1 unless Co*Ci is large)
+  const float yinv = P.y_drop_p > 0.f ? 1.0f / (1.0f - P.y_drop_p) : 1.f;
+  const int nchunks = (S + TV - 1) / TV;
+
+  for (int pass = 0; pass < npass; ++pass) {
+    const int t = pass * WG_THREADS + tid;
+    const bool active = t < ntiles * G;
+    const int tile = active ? t % ntiles : 0, grp = active ? t / ntiles : 0;
     const int co4 = tile % nCo4, ci4 = tile / nCo4;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const float* py = sY + (size_t)grp * span * CoP + co4 * 4;
-    const float* px = sX + (size_t)grp * span * CiP + ci4 * 4;
-    for (int v = 0; v < span; ++v) {
-      const float4 y = *reinterpret_cast<const float4*>(py + (size_t)v * CoP);
-      const float4 x = *reinterpret_cast<const float4*>(px + (size_t)v * CiP);
-      const float yy[4] = {y.x, y.y, y.z, y.w};
-      const float xx[4] = {x.x, x.y, x.z, x.w};
+
+    for (int ck = blockIdx.x; ck < nchunks; ck += gridDim.x) {
+      const int vbase = ck * TV;
+      __syncthreads();
+      for (int idx = tid; idx < Co4 * TV; idx += WG_THREADS) {
+        const int co = idx / TV, v = idx % TV, gv = vbase + v;
+        float val = 0.f;
+        if (co < Co && gv < S) {
+          const size_t gi = ((size_t)b * Co + co) * S + gv;
+          val = __ldg(P.dY + gi);
+          if (P.y_drop_p > 0.f) val *= dropout_scale(P.y_seed, P.y_site, gi, P.y_drop_p, yinv);
+        }
+        sY[v * CoP + co] = val;
+      }
+      int cg0 = 0;
+      for (int s = 0; s < P.nsrc; ++s) {
+        const int Cs = P.src[s].C;
+        const float* xp = P.src[s].ptr + (size_t)b * Cs * S;
+        for (int idx = tid; idx < Cs * TV; idx += WG_THREADS) {
+          const int c = idx / TV, v = idx % TV, gv = vbase + v;
+          float val = 0.f;
+          if (gv < S) {
+            val = __ldg(xp + (size_t)c * S + gv);
+            if (P.xpro == PRO_AFFINE) {
+              const int k = b * P.x_bstride + cg0 + c;
+              val = fmaf(val, P.xa[k], P.xc[k]);
+            } else if (P.xpro == PRO_GELU) {
+              val = gelu_f(val);
+            } else if (P.xpro == PRO_GELU_DROPOUT) {
+              val = gelu_f(val) * dropout_scale(P.x_seed, P.x_site, ((uint64_t)b * Ci + cg0 + c) * (uint64_t)S + gv, P.x_drop_p,
+                                                1.0f / (1.0f - P.x_drop_p));
+            }
+          }
+          sX[v * CiP + cg0 + c] = val;
+        }
+        cg0 += Cs;
+      }
+      for (int idx = tid; idx < (Ci4 - Ci) * TV; idx += WG_THREADS) {
+        const int c = Ci + idx / TV, v = idx % TV;
+        sX[v * CiP + c] = (c == Ci && vbase + v < S) ? 1.f : 0.f;
+      }
+      __syncthreads();
+      if (active) {
+        const float* py = sY + (size_t)grp * span * CoP + co4 * 4;
+        const float* px = sX + (size_t)grp * span * CiP + ci4 * 4;
+#pragma unroll 4
+        for (int v = 0; v < span; ++v) {
+          const float4 y = *reinterpret_cast<const float4*>(py + (size_t)v * CoP);
+          const float4 x = *reinterpret_cast<const float4*>(px + (size_t)v * CiP);
+          const float yy[4] = {y.x, y.y, y.z, y.w};
+          const float xx[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(yy[i], xx[j], acc[i][j]);
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(yy[i], xx[j], acc[i][j]);
+        }
+      }
     }
+    // fold the G voxel slices through shared memory (reusing sY), then one global atomic per element
+    __syncthreads();
+    float* fold = sY;                  // [ntiles_in_pass][16]
+    const int tiles_here = min(ntiles * G - pass * WG_THREADS, WG_THREADS);
+    if (G > 1) {
+      for (int i = tid; i < ntiles * 16; i += WG_THREADS) fold[i] = 0.f;
+      __syncthreads();
+      if (active) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int co = co4 * 4 + i;
-      if (co >= Co) continue;
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ci = ci4 * 4 + j;
-        if (ci < Ci) atomicAdd(P.dW + (size_t)co * P.ld + ci, acc[i][j]);
-        else if (ci == Ci && P.db) atomicAdd(P.db + co, acc[i][j]);
+          for (int j = 0; j < 4; ++j) atomicAdd(fold + tile * 16 + i * 4 + j, acc[i][j]);
+      }
+      __syncthreads();
+      for (int e = tid; e < ntiles * 16; e += WG_THREADS) {
+        const int tl = e >> 4, i = (e >> 2) & 3, j = e & 3;
+        const int co = (tl % nCo4) * 4 + i, ci = (tl / nCo4) * 4 + j;
+        if (co >= Co) continue;
+        if (ci < Ci) atomicAdd(P.dW + (size_t)co * P.ld + ci, fold[e]);
+        else if (ci == Ci && P.db) atomicAdd(P.db + co, fold[e]);
+      }
+    } else if (active) {
+      (void)tiles_here;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int co = co4 * 4 + i;
+        if (co >= Co) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ci = ci4 * 4 + j;
+          if (ci < Ci) atomicAdd(P.dW + (size_t)co * P.ld + ci, acc[i][j]);
+          else if (ci == Ci && P.db) atomicAdd(P.db + co, acc[i][j]);
+        }
       }
     }
   }
@@ -279,7 +357,12 @@ int pw_wgrad(const WgBatch& batch, cudaStream_t stream) {
   const size_t smem = (size_t)TV * maxsum * sizeof(float);
   if (smem > 200 * 1024) { set_error("pw_wgrad: channel count too large (%d)", maxsum); return VX_ERR_UNSUPPORTED; }
   VX_SET_SMEM(pw_wgrad_kernel, smem);
-  dim3 grid(cdiv(batch.S, TV), batch.B, batch.nprob);
+  // about two CTAs per SM in total; each CTA walks its share of the voxel chunks
+  const int nchunks = cdiv(batch.S, TV);
+  int nsplit = (2 * kSMs) / (batch.B * batch.nprob);
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > nchunks) nsplit = nchunks;
+  dim3 grid(nsplit, batch.B, batch.nprob);
   VX_LAUNCH(pw_wgrad_kernel, grid, dim3(WG_THREADS), smem, stream, batch, TV);
   return check_launch("pw_wgrad_kernel");
 }
@@ -381,51 +464,56 @@ int ln_forward(const LnBatch& L, cudaStream_t stream) {
   return check_launch("ln_fwd_kernel");
 }
 
-__global__ void __launch_bounds__(128) ln_bwd_kernel(const __grid_constant__ LnBwdBatch L) {
+// Backward of the channel-first LayerNorm.  CTA = 32 consecutive voxels (lanes) x 8 warps striding the channel axis:
+// every global access is a coalesced run along the voxel axis, a channel is owned by exactly one warp of the CTA (its
+// dgamma / dbeta partial is one warp reduction + one global atomic), and the per-voxel means are combined through
+// shared memory.
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const __grid_constant__ LnBwdBatch L) {
   const int t = blockIdx.z, b = blockIdx.y;
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int v = blockIdx.x * 32 + lane;
   const int C = L.C, S = L.S;
   const bool ok = v < S;
-  VX_DYN_SMEM(float, acc);   // [2C]: dgamma, dbeta partials of this CTA
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) acc[i] = 0.f;
-  __syncthreads();
+  __shared__ float red[2][8][32];
   const size_t off = (size_t)b * C * S + (ok ? v : 0);
   const float* dout = L.dout[t] + off;
   const float* xh = L.xhat[t] + off;
   const float* gamma = L.gamma[t];
-  const int lane = threadIdx.x & 31;
   float m1 = 0.f, m2 = 0.f;
-  for (int c = 0; c < C; ++c) {
-    const float d = ok ? dout[(size_t)c * S] : 0.f;
-    const float h = ok ? xh[(size_t)c * S] : 0.f;
-    const float g = gamma[c] * d;
+  for (int c = w; c < C; c += 8) {
+    const float d = ok ? __ldg(dout + (size_t)c * S) : 0.f;
+    const float h = ok ? __ldg(xh + (size_t)c * S) : 0.f;
+    const float g = __ldg(gamma + c) * d;
     m1 += g;
     m2 = fmaf(g, h, m2);
     const float sg = warp_sum(d * h), sb = warp_sum(d);
-    if (lane == 0) { atomicAdd(acc + c, sg); atomicAdd(acc + C + c, sb); }
+    if (lane == 0) {
+      if (L.dgamma[t]) atomicAdd(L.dgamma[t] + c, sg);
+      if (L.dbeta[t]) atomicAdd(L.dbeta[t] + c, sb);
+    }
   }
+  red[0][w][lane] = m1;
+  red[1][w][lane] = m2;
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    if (L.dgamma[t]) atomicAdd(L.dgamma[t] + i, acc[i]);
-    if (L.dbeta[t]) atomicAdd(L.dbeta[t] + i, acc[C + i]);
-  }
+  m1 = 0.f; m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { m1 += red[0][i][lane]; m2 += red[1][i][lane]; }
   if (!ok) return;
   m1 /= (float)C; m2 /= (float)C;
   const float rstd = L.rstd[t][(size_t)b * S + v];
   float* dx = L.dx[t] + off;
   const float* add = L.dx_add[t] ? L.dx_add[t] + off : nullptr;
-  for (int c = 0; c < C; ++c) {
-    const float g = gamma[c] * dout[(size_t)c * S];
-    float r = rstd * (g - m1 - xh[(size_t)c * S] * m2);
-    if (add) r = fmaf(L.dx_add_scale, add[(size_t)c * S], r);
+  for (int c = w; c < C; c += 8) {
+    const float g = __ldg(gamma + c) * __ldg(dout + (size_t)c * S);
+    float r = rstd * (g - m1 - __ldg(xh + (size_t)c * S) * m2);
+    if (add) r = fmaf(L.dx_add_scale, __ldg(add + (size_t)c * S), r);
     dx[(size_t)c * S] = r;
   }
 }
 
 int ln_backward(const LnBwdBatch& L, cudaStream_t stream) {
   if (L.n <= 0) return VX_OK;
-  const size_t smem = (size_t)2 * L.C * sizeof(float);
-  VX_LAUNCH(ln_bwd_kernel, dim3(cdiv(L.S, 128), L.B, L.n), dim3(128), smem, stream, L);
+  VX_LAUNCH(ln_bwd_kernel, dim3(cdiv(L.S, 32), L.B, L.n), dim3(256), 0, stream, L);
   return check_launch("ln_bwd_kernel");
 }
 
