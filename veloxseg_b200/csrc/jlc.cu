@@ -127,11 +127,14 @@ __global__ void __launch_bounds__(256) jlc_conv_fwd_kernel(const __grid_constant
     __syncthreads();
 
     if (cb < NCB) {
+      // (ci, dz) stay rolled: the unrolled (dy, dx, v) body is ~20 KB of SASS and must stay instruction-cache resident
+#pragma unroll 1
       for (int ci = 0; ci < 4; ++ci) {
+#pragma unroll 1
         for (int dz = 0; dz < 5; ++dz) {
           const float* xrow = xs + ((size_t)(ci * HZ + tz + dz) * HY + ty) * TXP + xq * VX;
           const bool mid_z = dz >= 1 && dz <= 3;
-#pragma unroll
+#pragma unroll 1
           for (int dy = 0; dy < 5; ++dy) {
             float xr[VX + 4];
 #pragma unroll
@@ -391,10 +394,12 @@ VX_DEV void dgrad_branch(const ConvDgradArgs& A, const float* __restrict__ gzk, 
     }
     __syncthreads();
     if (cb < NCB) {
+#pragma unroll 1
       for (int ci = 0; ci < 4; ++ci) {
+#pragma unroll 1
         for (int dz = 0; dz < K; ++dz) {
           const float* xrow = xs + ((size_t)(ci * HZ + tz + dz) * HY + ty) * TXP + xq * VX;
-#pragma unroll
+#pragma unroll 1
           for (int dy = 0; dy < K; ++dy) {
             float xr[VX + 4];
 #pragma unroll

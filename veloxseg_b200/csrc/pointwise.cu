@@ -18,38 +18,26 @@ constexpr int PW_TS = 64;    // voxels per CTA tile
 constexpr int PW_TC = 64;    // output channels per CTA tile
 constexpr int PW_KC = 16;    // input channels per staged chunk
 
-VX_DEV float pw_weight(const PwProblem& P, int co, int ci) {
+// Address of one input element of the (possibly multi-source) X operand.
+VX_DEV const float* pw_x_ptr(const PwProblem& P, int b, int cg, int v, int S) {
+  int c = cg, s = 0;
+  while (s < P.nsrc - 1 && c >= P.src[s].C) { c -= P.src[s].C; ++s; }
+  return P.src[s].ptr + ((size_t)b * P.src[s].C + c) * S + v;
+}
+VX_DEV const float* pw_w_ptr(const PwProblem& P, int co, int ci) {
   int off = 0;
   if (!P.transposed) {
     for (int s = 0; s < P.nseg; ++s) {
-      if (co < off + P.seg[s].n) return __ldg(P.seg[s].W + (size_t)(co - off) * P.seg[s].ld + ci);
+      if (co < off + P.seg[s].n) return P.seg[s].W + (size_t)(co - off) * P.seg[s].ld + ci;
       off += P.seg[s].n;
     }
   } else {
     for (int s = 0; s < P.nseg; ++s) {
-      if (ci < off + P.seg[s].n) return __ldg(P.seg[s].W + (size_t)(ci - off) * P.seg[s].ld + co);
+      if (ci < off + P.seg[s].n) return P.seg[s].W + (size_t)(ci - off) * P.seg[s].ld + co;
       off += P.seg[s].n;
     }
   }
-  return 0.f;
-}
-
-VX_DEV float pw_bias(const PwProblem& P, int co) {
-  if (P.transposed) return 0.f;
-  int off = 0;
-  for (int s = 0; s < P.nseg; ++s) {
-    if (co < off + P.seg[s].n) return P.seg[s].bias ? __ldg(P.seg[s].bias + co - off) : 0.f;
-    off += P.seg[s].n;
-  }
-  return 0.f;
-}
-
-// Raw load of one input element (the prologue is applied later, when the value is committed to shared memory, so the
-// global loads of chunk k+1 stay in flight while chunk k is being multiplied).
-VX_DEV float pw_fetch_x(const PwProblem& P, int b, int cg, int v, int S) {
-  int c = cg, s = 0;
-  while (s < P.nsrc - 1 && c >= P.src[s].C) { c -= P.src[s].C; ++s; }
-  return __ldg(P.src[s].ptr + ((size_t)b * P.src[s].C + c) * S + v);
+  return P.seg[0].W;
 }
 VX_DEV float pw_prologue(const PwProblem& P, float x, int b, int cg, int v, int S, float pinv) {
   if (P.pro == PRO_AFFINE) {
@@ -64,17 +52,21 @@ VX_DEV float pw_prologue(const PwProblem& P, float x, int b, int cg, int v, int 
 }
 
 // Y[b, co, v] = epi( sum_ci W[co, ci] * pro(X[b, ci, v]) + bias[co] ) as a register-tiled GEMM: CTA tile = 64 voxels x
-// 64 output channels, K staged 16 channels at a time through double-buffered shared memory; a thread owns 4 voxels x
-// 8 channels (32 accumulators, 3 LDS.128 per 32 FMA).  Warp = 16 voxel groups x 2 channel groups, so the X reads of a
-// warp are two 128-B wavefronts and the W reads are broadcasts.
+// 64 output channels, K staged 16 channels at a time through double-buffered shared memory with cp.async (the copies
+// of chunk k+1 fly while chunk k is multiplied); a thread owns 4 voxels x 8 channels (32 accumulators, 3 LDS.128 per
+// 32 FMA).  Warp = 16 voxel groups x 2 channel groups: X reads are two 128-B wavefronts, W reads are broadcasts.
+// Code size is a first-class constraint here (a kernel runs once per thread, so SASS beyond the 32 KB instruction
+// cache is fetch-bound): staging and epilogue are ROLLED loops with a single copy of the address / prologue /
+// epilogue logic, and the epilogue reads the accumulator tile back from shared memory.
 __global__ void __launch_bounds__(PW_THREADS) pw_kernel(const __grid_constant__ PwBatch batch) {
   const int pi = blockIdx.z / batch.B, b = blockIdx.z % batch.B;
   const PwProblem& P = batch.p[pi];
   const int S = batch.S, Ci = P.Ci, Co = P.Co;
   const int co0 = blockIdx.y * PW_TC, v0 = blockIdx.x * PW_TS;
   if (co0 >= Co) return;
-  __align__(16) __shared__ float Xs[2][PW_KC][PW_TS];
-  __align__(16) __shared__ float Ws[2][PW_KC][PW_TC];
+  __align__(16) __shared__ float smem[2 * PW_KC * PW_TS + 2 * PW_KC * PW_TC];
+  float (*Xs)[PW_KC][PW_TS] = reinterpret_cast<float (*)[PW_KC][PW_TS]>(smem);
+  float (*Ws)[PW_KC][PW_TC] = reinterpret_cast<float (*)[PW_KC][PW_TC]>(smem + 2 * PW_KC * PW_TS);
   const int tid = threadIdx.x;
   const int vg = tid & 15, cgp = tid >> 4;            // voxel group (4 voxels), channel group (8 channels)
   const bool pro_drop = P.pro == PRO_DROPOUT || P.pro == PRO_GELU_DROPOUT;
@@ -87,48 +79,43 @@ __global__ void __launch_bounds__(PW_THREADS) pw_kernel(const __grid_constant__ 
     for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 
   // staging maps: X chunk 16 x 64 -> 8 elements per thread (voxel fastest: coalesced), W chunk 16 x 64 likewise
-  float xr[8], wr[8];
-  auto fetch = [&](int k0) {
-#pragma unroll
+  auto stage = [&](int buf, int k0) {
+#pragma unroll 1
     for (int r = 0; r < 8; ++r) {
       const int e = r * PW_THREADS + tid;
       const int v = e & (PW_TS - 1), k = e >> 6;
-      xr[r] = (k0 + k < Ci && v0 + v < S) ? pw_fetch_x(P, b, k0 + k, v0 + v, S) : 0.f;
+      const bool ok = k0 + k < Ci && v0 + v < S;
+      vx_cp_async4(&Xs[buf][k][v], ok ? pw_x_ptr(P, b, k0 + k, v0 + v, S) : P.src[0].ptr, ok);
     }
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < 8; ++r) {
       const int e = r * PW_THREADS + tid;
       // forward orientation reads W[co][ci] (ci contiguous): k fastest; transposed reads W[ci][co]: co fastest
       const int k = P.transposed ? (e >> 6) : (e & (PW_KC - 1));
       const int c = P.transposed ? (e & (PW_TC - 1)) : (e >> 4);
-      wr[r] = (k0 + k < Ci && co0 + c < Co) ? pw_weight(P, co0 + c, k0 + k) : 0.f;
+      const bool ok = k0 + k < Ci && co0 + c < Co;
+      vx_cp_async4(&Ws[buf][k][c], ok ? pw_w_ptr(P, co0 + c, k0 + k) : P.seg[0].W, ok);
     }
+    vx_cp_async_commit();
   };
-  auto commit = [&](int buf, int k0) {
-#pragma unroll
+  auto prologue = [&](int buf, int k0) {     // in place, on the elements this thread staged
+    if (P.pro == PRO_NONE) return;
+#pragma unroll 1
     for (int r = 0; r < 8; ++r) {
       const int e = r * PW_THREADS + tid;
       const int v = e & (PW_TS - 1), k = e >> 6;
-      float x = xr[r];
-      if (P.pro != PRO_NONE && k0 + k < Ci && v0 + v < S) x = pw_prologue(P, x, b, k0 + k, v0 + v, S, pinv);
-      Xs[buf][k][v] = x;
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int e = r * PW_THREADS + tid;
-      const int k = P.transposed ? (e >> 6) : (e & (PW_KC - 1));
-      const int c = P.transposed ? (e & (PW_TC - 1)) : (e >> 4);
-      Ws[buf][k][c] = wr[r];
+      if (k0 + k < Ci && v0 + v < S) Xs[buf][k][v] = pw_prologue(P, Xs[buf][k][v], b, k0 + k, v0 + v, S, pinv);
     }
   };
 
   const int nchunk = (Ci + PW_KC - 1) / PW_KC;
-  fetch(0);
-  commit(0, 0);
+  stage(0, 0);
+  vx_cp_async_wait_all();
+  prologue(0, 0);
   __syncthreads();
   for (int ch = 0; ch < nchunk; ++ch) {
     const int buf = ch & 1;
-    if (ch + 1 < nchunk) fetch((ch + 1) * PW_KC);
+    if (ch + 1 < nchunk) stage(buf ^ 1, (ch + 1) * PW_KC);
 #pragma unroll
     for (int k = 0; k < PW_KC; ++k) {
       const float4 x = *reinterpret_cast<const float4*>(&Xs[buf][k][vg * 4]);
@@ -141,43 +128,64 @@ __global__ void __launch_bounds__(PW_THREADS) pw_kernel(const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(ws[j], xs[i], acc[j][i]);
     }
-    if (ch + 1 < nchunk) commit(buf ^ 1, (ch + 1) * PW_KC);
+    if (ch + 1 < nchunk) {
+      vx_cp_async_wait_all();
+      prologue(buf ^ 1, (ch + 1) * PW_KC);
+    }
     __syncthreads();
   }
 
-  // epilogue
-  const float dinv = P.drop_p > 0.f ? 1.0f / (1.0f - P.drop_p) : 1.f;
-  const int vb = v0 + vg * 4;
-  const bool vec = ((S & 3) == 0) && (vb + 3 < S);
+  // accumulator tile -> shared memory [co][v] (the staging buffers are free now), then a rolled epilogue
+  float (*Cs)[PW_TS] = reinterpret_cast<float (*)[PW_TS]>(smem);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int co = co0 + cgp * 8 + j;
-    if (co >= Co) break;
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(&Cs[cgp * 8 + j][vg * 4]) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+  __syncthreads();
+  const float dinv = P.drop_p > 0.f ? 1.0f / (1.0f - P.drop_p) : 1.f;
+#pragma unroll 1
+  for (int r = 0; r < (PW_TC * PW_TS / 4) / PW_THREADS; ++r) {
+    const int it = r * PW_THREADS + tid;
+    const int col = it >> 4, vq = it & 15;
+    const int co = co0 + col, vb = v0 + vq * 4;
+    if (co >= Co || vb >= S) continue;
     float* outp;
+    float bias = 0.f;
     if (!P.transposed) {
       int seg = 0, seg_off = 0;
       while (co >= seg_off + P.seg[seg].n) { seg_off += P.seg[seg].n; ++seg; }
       outp = P.seg[seg].out + ((size_t)b * P.seg[seg].n + (co - seg_off)) * S;
+      if (P.seg[seg].bias) bias = __ldg(P.seg[seg].bias + co - seg_off);
     } else {
       outp = P.seg[0].out + ((size_t)b * Co + co) * S;
     }
     const size_t lbase = ((size_t)b * Co + co) * S;   // index in the logical (B, Co, S) tensor
-    const float bias = pw_bias(P, co);
-    float y[4];
+    const float4 a4 = *reinterpret_cast<const float4*>(&Cs[col][vq * 4]);
+    float y[4] = {a4.x + bias, a4.y + bias, a4.z + bias, a4.w + bias};
+    if (P.act == 1) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int v = vb + i;
-      float t = acc[j][i] + bias;
-      if (v < S) {
-        if (P.act == 1) t = gelu_f(t);
-        if (P.mulgrad) t *= gelu_grad_f(__ldg(P.mulgrad + lbase + v));
-        if (P.drop_p > 0.f) t *= dropout_scale(P.seed, P.site, lbase + v, P.drop_p, dinv);
-        if (P.res) t = fmaf(P.res_scale, __ldg(P.res + lbase + v), t);
-        if (P.res2) t += __ldg(P.res2 + lbase + v);
-      }
-      y[i] = t;
+      for (int i = 0; i < 4; ++i) y[i] = gelu_f(y[i]);
     }
-    if (vec) {
+    if (P.mulgrad) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] *= (vb + i < S) ? gelu_grad_f(__ldg(P.mulgrad + lbase + vb + i)) : 0.f;
+    }
+    if (P.drop_p > 0.f) {
+      float ms[4];
+      dropout_scale4(P.seed, P.site, lbase + vb, P.drop_p, dinv, ms);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] *= ms[i];
+    }
+    if (P.res) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (vb + i < S) y[i] = fmaf(P.res_scale, __ldg(P.res + lbase + vb + i), y[i]);
+    }
+    if (P.res2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (vb + i < S) y[i] += __ldg(P.res2 + lbase + vb + i);
+    }
+    if (((S & 3) == 0) && (vb + 3 < S)) {
       *reinterpret_cast<float4*>(outp + vb) = make_float4(y[0], y[1], y[2], y[3]);
     } else {
 #pragma unroll

@@ -34,6 +34,21 @@
 
 #define VX_DEV __device__ __forceinline__
 
+// 4-byte asynchronous global -> shared copy (LDGSTS); `ok == false` zero-fills.
+#ifdef VX_EMU
+static inline void vx_cp_async4(float* dst, const float* src, bool ok) { *dst = ok ? *src : 0.f; }
+static inline void vx_cp_async_commit() {}
+static inline void vx_cp_async_wait_all() {}
+#else
+VX_DEV void vx_cp_async4(float* dst, const float* src, bool ok) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int n = ok ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+VX_DEV void vx_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+VX_DEV void vx_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+#endif
+
 namespace vx {
 
 constexpr int kSMs = 148;
@@ -94,9 +109,51 @@ VX_DEV uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint32_t ctr_hi) {
   }
   uint4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3; return o;
 }
+#ifdef VX_EMU
+#define VX_NOINLINE
+#else
+#define VX_NOINLINE __noinline__
+#endif
+// Out-of-line copies for kernels whose code size matters (a kernel runs once per thread: unrolled call sites of the
+// 10-round Philox or of erff/expf multiply the SASS far beyond the 32 KB instruction cache and the kernel becomes
+// instruction-fetch bound -- measured: 68 % of pw_kernel's stall samples were `no_instructions` at 200 KB of SASS).
+static __device__ VX_NOINLINE uint4 philox4x32_call(uint64_t seed, uint64_t ctr_lo, uint32_t ctr_hi) {
+  return philox4x32(seed, ctr_lo, ctr_hi);
+}
+static __device__ VX_NOINLINE float4 gelu_grad4_call(float4 x) {
+  return make_float4(gelu_grad_f(x.x), gelu_grad_f(x.y), gelu_grad_f(x.z), gelu_grad_f(x.w));
+}
+static __device__ VX_NOINLINE float4 gelu4_call(float4 x) {
+  return make_float4(gelu_f(x.x), gelu_f(x.y), gelu_f(x.z), gelu_f(x.w));
+}
+VX_DEV float keep_from_bits(uint32_t bits, float p, float inv_keep) {
+  return ((float)(bits >> 8) * (1.0f / 16777216.0f) < p) ? 0.f : inv_keep;
+}
+// keep-scales of the 4 consecutive elements idx .. idx+3 (same values as dropout_scale element by element): one Philox
+// block when idx is a multiple of 4, two otherwise.
+VX_DEV void dropout_scale4(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep, float (&ms)[4]) {
+  const uint4 r0 = philox4x32_call(seed, idx >> 2, site);
+  const uint32_t b0[4] = {r0.x, r0.y, r0.z, r0.w};
+  const int sh = (int)(idx & 3);
+  if (sh == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ms[i] = keep_from_bits(b0[i], p, inv_keep);
+  } else {
+    const uint4 r1 = philox4x32_call(seed, (idx >> 2) + 1, site);
+    const uint32_t b1[4] = {r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = sh + i;
+      uint32_t bits = 0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { if (q == t) bits = b0[t]; if (q == t + 4) bits = b1[t]; }
+      ms[i] = keep_from_bits(bits, p, inv_keep);
+    }
+  }
+}
 // keep-scale for element `idx` of dropout site `site`: 0 (dropped) or 1/(1-p).
 VX_DEV float dropout_scale(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep) {
-  const uint4 r = philox4x32(seed, idx >> 2, site);
+  const uint4 r = philox4x32_call(seed, idx >> 2, site);
   const uint32_t sel = (uint32_t)(idx & 3);
   const uint32_t bits = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
   const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);      // [0,1)
