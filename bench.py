@@ -173,6 +173,12 @@ def run_ours(args, rank, world, local_rank):
         ts.step(x_d, y_d)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+    # ---- host-side enqueue time of one step (queue empty at the start; the GPU is still busy when step() returns)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ts.step(x_d, y_d)
+    enqueue_ms = (time.perf_counter() - t0) * 1e3
+    torch.cuda.synchronize()
     # ---- end to end (host batches)
     for _ in range(2):
         ts.step(x_h, y_h, sync=True)
@@ -233,7 +239,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": round(total_patches / e2e_s, 3), "unit": "patches/s",
                 "h2d_bytes_per_step": int(x_h.numel() * x_h.element_size() + y_h.numel() * y_h.element_size()),
                 "d2h_bytes_per_step": 4},
-        "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "loss": last_loss, "top_kernels": table,
+        "gpu_launches": launches, "host_enqueue_ms_per_step": round(enqueue_ms, 2), "clocks": clk.summary(), "roofline": roof, "loss": last_loss, "top_kernels": table,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_port(steps=1, patches=1, threads=None)

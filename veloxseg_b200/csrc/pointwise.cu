@@ -218,160 +218,162 @@ int pw_forward(const PwBatch& batch, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------------
 constexpr int WG_THREADS = 256;
 
-// CTA = persistent over voxel chunks (blockIdx.x strides the chunk list) of one (problem, batch item).  Per chunk the
-// dY and X tiles are transposed into shared memory ([voxel][channel], channel padded to 4 * odd so that the float4 reads
-// of 4 consecutive channels are conflict-free) and every thread accumulates one 4x4 block of dW in registers over a
-// slice of the chunk's voxels.  The voxel slices are folded in shared memory and each CTA issues ONE global atomic per
-// dW element, so the number of atomics per address is the (small) grid size, not the number of voxel chunks.
-__global__ void __launch_bounds__(WG_THREADS) pw_wgrad_kernel(const __grid_constant__ WgBatch batch, int TV) {
+// dW = dY X^T is a small-output GEMM whose reduction axis is (batch, voxel).  A CTA owns a block of 4x4 output tiles
+// (all output channels x a strip of input channels) and walks its share of the (batch, voxel-chunk) list: blockIdx.x
+// splits that list only as far as needed to fill the machine, so problems with many channels and few voxels (levels 3-4)
+// run without any atomics, and large-voxel problems (level 1) issue grid.x atomics per element.  Per chunk the dY and X
+// tiles are transposed into shared memory ([voxel][channel], rows padded to 4*odd words so the float4 reads of 4
+// consecutive channels are conflict-free); when the tile block has fewer tiles than threads the voxels of a chunk are
+// split between thread groups and folded through shared memory at the end.
+__global__ void __launch_bounds__(WG_THREADS) pw_wgrad_kernel(const __grid_constant__ WgBatch batch, int TV, int nK) {
   const WgProblem& P = batch.p[blockIdx.z];
-  const int b = blockIdx.y, S = batch.S;
+  const int S = batch.S, B = batch.B;
   const int Co = P.Co, Ci = P.Ci;
   const int Co4 = (Co + 3) & ~3, Ci4 = (Ci + 1 + 3) & ~3;    // +1: the all-ones row that yields db
-  const int CoP = Co4 + 4, CiP = Ci4 + 4;
+  const int nCo4 = Co4 >> 2, nCi4 = Ci4 >> 2;
+  const int WCI = max(1, WG_THREADS / nCo4);                  // input-channel tiles per CTA
+  const int ci4_0 = blockIdx.y * WCI;
+  if (ci4_0 >= nCi4) return;
+  const int width = min(WCI, nCi4 - ci4_0);
+  const int nt = nCo4 * width;                                // tiles of this CTA (<= WG_THREADS)
+  int G = 1;
+  while (G * 2 * nt <= WG_THREADS && (TV / (G * 2)) >= 4) G *= 2;
+  const int span = TV / G;
+  const int CoP = Co4 + 4, CiP = WCI * 4 + 4;
   VX_DYN_SMEM(float, sm);
   float* sY = sm;                     // [TV][CoP]
-  float* sX = sm + (size_t)TV * CoP;  // [TV][CiP]
+  float* sX = sm + (size_t)TV * CoP;  // [TV][CiP]   (only this CTA's input-channel strip)
   const int tid = threadIdx.x;
-  const int nCo4 = Co4 >> 2, nCi4 = Ci4 >> 2, ntiles = nCo4 * nCi4;
-  // When there are fewer 4x4 tiles than threads, split the voxel range between thread groups.
-  int G = 1;
-  while (G * 2 * ntiles <= WG_THREADS && (TV / (G * 2)) >= 8) G *= 2;
-  const int span = TV / G;
-  const int npass = (ntiles * G + WG_THREADS - 1) / WG_THREADS;    // tiles per thread (1 unless Co*Ci is large)
+  const bool active = tid < nt * G;
+  const int tile = active ? tid % nt : 0, grp = active ? tid / nt : 0;
+  const int co4 = tile % nCo4, ci4l = tile / nCo4;
+  const int cbeg = ci4_0 * 4, ccount = width * 4;             // global input-channel range [cbeg, cbeg + ccount)
   const float yinv = P.y_drop_p > 0.f ? 1.0f / (1.0f - P.y_drop_p) : 1.f;
+  const float xinv = P.x_drop_p > 0.f ? 1.0f / (1.0f - P.x_drop_p) : 1.f;
   const int nchunks = (S + TV - 1) / TV;
 
-  for (int pass = 0; pass < npass; ++pass) {
-    const int t = pass * WG_THREADS + tid;
-    const bool active = t < ntiles * G;
-    const int tile = active ? t % ntiles : 0, grp = active ? t / ntiles : 0;
-    const int co4 = tile % nCo4, ci4 = tile / nCo4;
-    float acc[4][4];
+  float acc[4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    for (int ck = blockIdx.x; ck < nchunks; ck += gridDim.x) {
-      const int vbase = ck * TV;
-      __syncthreads();
-      for (int idx = tid; idx < Co4 * TV; idx += WG_THREADS) {
-        const int co = idx / TV, v = idx % TV, gv = vbase + v;
-        float val = 0.f;
-        if (co < Co && gv < S) {
-          const size_t gi = ((size_t)b * Co + co) * S + gv;
-          val = __ldg(P.dY + gi);
-          if (P.y_drop_p > 0.f) val *= dropout_scale(P.y_seed, P.y_site, gi, P.y_drop_p, yinv);
-        }
-        sY[v * CoP + co] = val;
-      }
-      int cg0 = 0;
-      for (int s = 0; s < P.nsrc; ++s) {
-        const int Cs = P.src[s].C;
-        const float* xp = P.src[s].ptr + (size_t)b * Cs * S;
-        for (int idx = tid; idx < Cs * TV; idx += WG_THREADS) {
-          const int c = idx / TV, v = idx % TV, gv = vbase + v;
-          float val = 0.f;
-          if (gv < S) {
-            val = __ldg(xp + (size_t)c * S + gv);
-            if (P.xpro == PRO_AFFINE) {
-              const int k = b * P.x_bstride + cg0 + c;
-              val = fmaf(val, P.xa[k], P.xc[k]);
-            } else if (P.xpro == PRO_GELU) {
-              val = gelu_f(val);
-            } else if (P.xpro == PRO_GELU_DROPOUT) {
-              val = gelu_f(val) * dropout_scale(P.x_seed, P.x_site, ((uint64_t)b * Ci + cg0 + c) * (uint64_t)S + gv, P.x_drop_p,
-                                                1.0f / (1.0f - P.x_drop_p));
-            }
-          }
-          sX[v * CiP + cg0 + c] = val;
-        }
-        cg0 += Cs;
-      }
-      for (int idx = tid; idx < (Ci4 - Ci) * TV; idx += WG_THREADS) {
-        const int c = Ci + idx / TV, v = idx % TV;
-        sX[v * CiP + c] = (c == Ci && vbase + v < S) ? 1.f : 0.f;
-      }
-      __syncthreads();
-      if (active) {
-        const float* py = sY + (size_t)grp * span * CoP + co4 * 4;
-        const float* px = sX + (size_t)grp * span * CiP + ci4 * 4;
-#pragma unroll 4
-        for (int v = 0; v < span; ++v) {
-          const float4 y = *reinterpret_cast<const float4*>(py + (size_t)v * CoP);
-          const float4 x = *reinterpret_cast<const float4*>(px + (size_t)v * CiP);
-          const float yy[4] = {y.x, y.y, y.z, y.w};
-          const float xx[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(yy[i], xx[j], acc[i][j]);
-        }
-      }
-    }
-    // fold the G voxel slices through shared memory (reusing sY), then one global atomic per element
+  for (int ck = blockIdx.x; ck < B * nchunks; ck += nK) {
+    const int b = ck / nchunks, vbase = (ck % nchunks) * TV;
     __syncthreads();
-    float* fold = sY;                  // [ntiles_in_pass][16]
-    const int tiles_here = min(ntiles * G - pass * WG_THREADS, WG_THREADS);
-    if (G > 1) {
-      for (int i = tid; i < ntiles * 16; i += WG_THREADS) fold[i] = 0.f;
-      __syncthreads();
-      if (active) {
+#pragma unroll 1
+    for (int idx = tid; idx < Co4 * TV; idx += WG_THREADS) {
+      const int co = idx / TV, v = idx % TV, gv = vbase + v;
+      float val = 0.f;
+      if (co < Co && gv < S) {
+        const size_t gi = ((size_t)b * Co + co) * S + gv;
+        val = __ldg(P.dY + gi);
+        if (P.y_drop_p > 0.f) val *= dropout_scale(P.y_seed, P.y_site, gi, P.y_drop_p, yinv);
+      }
+      sY[v * CoP + co] = val;
+    }
+#pragma unroll 1
+    for (int idx = tid; idx < ccount * TV; idx += WG_THREADS) {
+      const int cl = idx / TV, v = idx % TV, gv = vbase + v;
+      const int cg = cbeg + cl;
+      float val = 0.f;
+      if (gv < S) {
+        if (cg < Ci) {
+          int c = cg, s2 = 0;
+          while (s2 < P.nsrc - 1 && c >= P.src[s2].C) { c -= P.src[s2].C; ++s2; }
+          val = __ldg(P.src[s2].ptr + ((size_t)b * P.src[s2].C + c) * S + gv);
+          if (P.xpro == PRO_AFFINE) {
+            const int k = b * P.x_bstride + cg;
+            val = fmaf(val, __ldg(P.xa + k), __ldg(P.xc + k));
+          } else if (P.xpro == PRO_GELU) {
+            val = gelu_f(val);
+          } else if (P.xpro == PRO_GELU_DROPOUT) {
+            val = gelu_f(val) * dropout_scale(P.x_seed, P.x_site, ((uint64_t)b * Ci + cg) * (uint64_t)S + gv, P.x_drop_p, xinv);
+          }
+        } else if (cg == Ci) {
+          val = 1.f;
+        }
+      }
+      sX[v * CiP + cl] = val;
+    }
+    __syncthreads();
+    if (active) {
+      const float* py = sY + (size_t)grp * span * CoP + co4 * 4;
+      const float* px = sX + (size_t)grp * span * CiP + ci4l * 4;
+#pragma unroll 4
+      for (int v = 0; v < span; ++v) {
+        const float4 y = *reinterpret_cast<const float4*>(py + (size_t)v * CoP);
+        const float4 x = *reinterpret_cast<const float4*>(px + (size_t)v * CiP);
+        const float yy[4] = {y.x, y.y, y.z, y.w};
+        const float xx[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) atomicAdd(fold + tile * 16 + i * 4 + j, acc[i][j]);
-      }
-      __syncthreads();
-      for (int e = tid; e < ntiles * 16; e += WG_THREADS) {
-        const int tl = e >> 4, i = (e >> 2) & 3, j = e & 3;
-        const int co = (tl % nCo4) * 4 + i, ci = (tl / nCo4) * 4 + j;
-        if (co >= Co) continue;
-        if (ci < Ci) atomicAdd(P.dW + (size_t)co * P.ld + ci, fold[e]);
-        else if (ci == Ci && P.db) atomicAdd(P.db + co, fold[e]);
-      }
-    } else if (active) {
-      (void)tiles_here;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int co = co4 * 4 + i;
-        if (co >= Co) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int ci = ci4 * 4 + j;
-          if (ci < Ci) atomicAdd(P.dW + (size_t)co * P.ld + ci, acc[i][j]);
-          else if (ci == Ci && P.db) atomicAdd(P.db + co, acc[i][j]);
-        }
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(yy[i], xx[j], acc[i][j]);
       }
     }
+  }
+  // fold the G voxel slices through shared memory, then one global update per element
+  __syncthreads();
+  float* fold = sm;                  // [nt][16]
+  if (G > 1) {
+    for (int i = tid; i < nt * 16; i += WG_THREADS) fold[i] = 0.f;
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(fold + tile * 16 + i * 4 + j, acc[i][j]);
+    }
+  } else if (active) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) fold[tile * 16 + i * 4 + j] = acc[i][j];
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int e = tid; e < nt * 16; e += WG_THREADS) {
+    const int tl = e >> 4, i = (e >> 2) & 3, j = e & 3;
+    const int co = (tl % nCo4) * 4 + i, ci = cbeg + (tl / nCo4) * 4 + j;
+    if (co >= Co) continue;
+    if (ci < Ci) atomicAdd(P.dW + (size_t)co * P.ld + ci, fold[e]);
+    else if (ci == Ci && P.db) atomicAdd(P.db + co, fold[e]);
   }
 }
 
 int pw_wgrad(const WgBatch& batch, cudaStream_t stream) {
   if (batch.nprob <= 0) return VX_OK;
-  int maxsum = 0;
+  int maxrow = 0, maxblocks = 1, maxfold = 0;
   for (int i = 0; i < batch.nprob; ++i) {
     const WgProblem& P = batch.p[i];
     int cs = 0;
     for (int s = 0; s < P.nsrc; ++s) cs += P.src[s].C;
     if (cs != P.Ci) { set_error("pw_wgrad: source channels %d != Ci %d", cs, P.Ci); return VX_ERR_BAD_DESC; }
-    const int tot = ((P.Co + 3) & ~3) + 4 + ((P.Ci + 4) & ~3) + 4;
-    maxsum = tot > maxsum ? tot : maxsum;
+    const int Co4 = (P.Co + 3) & ~3, nCo4 = Co4 >> 2, nCi4 = ((P.Ci + 4) & ~3) >> 2;
+    if (nCo4 > WG_THREADS) { set_error("pw_wgrad: %d output channels not supported", P.Co); return VX_ERR_UNSUPPORTED; }
+    const int WCI = WG_THREADS / nCo4 > 0 ? WG_THREADS / nCo4 : 1;
+    const int row = (Co4 + 4) + (WCI * 4 + 4);
+    maxrow = row > maxrow ? row : maxrow;
+    const int blocks = cdiv(nCi4, WCI);
+    maxblocks = blocks > maxblocks ? blocks : maxblocks;
+    const int fold = WG_THREADS * 16;
+    maxfold = fold > maxfold ? fold : maxfold;
   }
-  int TV = 512;
-  while (TV > 32 && (size_t)TV * maxsum * sizeof(float) > 96 * 1024) TV >>= 1;
-  while (TV > 32 && TV / 2 >= batch.S) TV >>= 1;
-  const size_t smem = (size_t)TV * maxsum * sizeof(float);
-  if (smem > 200 * 1024) { set_error("pw_wgrad: channel count too large (%d)", maxsum); return VX_ERR_UNSUPPORTED; }
+  int TV = 128;
+  while (TV > 16 && (size_t)TV * maxrow * sizeof(float) > 64 * 1024) TV >>= 1;
+  while (TV > 16 && TV / 2 >= batch.S) TV >>= 1;
+  size_t smem = (size_t)TV * maxrow * sizeof(float);
+  if (smem < (size_t)maxfold * sizeof(float)) smem = (size_t)maxfold * sizeof(float);
+  if (smem > 200 * 1024) { set_error("pw_wgrad: channel count too large"); return VX_ERR_UNSUPPORTED; }
   VX_SET_SMEM(pw_wgrad_kernel, smem);
-  // about two CTAs per SM in total; each CTA walks its share of the voxel chunks
-  const int nchunks = cdiv(batch.S, TV);
-  int nsplit = (2 * kSMs) / (batch.B * batch.nprob);
-  if (nsplit < 1) nsplit = 1;
-  if (nsplit > nchunks) nsplit = nchunks;
-  dim3 grid(nsplit, batch.B, batch.nprob);
-  VX_LAUNCH(pw_wgrad_kernel, grid, dim3(WG_THREADS), smem, stream, batch, TV);
+  // split the (batch, chunk) list only as far as needed to put ~2 CTAs on every SM
+  const int nchunks = batch.B * cdiv(batch.S, TV);
+  int nK = (2 * kSMs) / (maxblocks * batch.nprob);
+  if (nK < 1) nK = 1;
+  if (nK > nchunks) nK = nchunks;
+  dim3 grid(nK, maxblocks, batch.nprob);
+  VX_LAUNCH(pw_wgrad_kernel, grid, dim3(WG_THREADS), smem, stream, batch, TV, nK);
   return check_launch("pw_wgrad_kernel");
 }
 

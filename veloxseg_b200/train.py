@@ -26,6 +26,9 @@ class GradBuckets:
         order = list(reversed(self.params))                 # decoders finish first in backward
         self.buckets: List[torch.Tensor] = []
         self.bucket_of, self.pending, self.total = {}, [], []
+        if self.world == 1:          # nothing to exchange: leave .grad to autograd (no accumulate kernels at all)
+            self.works = []
+            return
         cur, cur_bytes = [], 0
         groups = []
         for p in order:
@@ -53,6 +56,10 @@ class GradBuckets:
                 p.register_post_accumulate_grad_hook(self._ready)
 
     def zero(self):
+        if self.world == 1:
+            for p in self.params:
+                p.grad = None
+            return
         for b in self.buckets:
             b.zero_()
         self.pending = list(self.total)
