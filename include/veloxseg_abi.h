@@ -58,6 +58,8 @@ typedef struct {
   float drop_p;            /* dropout on the channel_conv output (0 disables)        */
   int32_t training;        /* dropout is applied only when training != 0            */
   uint64_t seed;           /* counter-based RNG key for this call's dropout mask     */
+  const uint64_t* seed_offset; /* optional DEVICE pointer: the kernels add *seed_offset to `seed`, so a captured
+                              CUDA graph draws a fresh mask on every replay (NULL: no offset)            */
 } vx_jlc_desc;
 
 /* fwd  in : x, w1,b1, w3,b3, w5,b5 (grouped conv weights (C, c_g, k,k,k) + bias (C)), fw1 (eC, C), fb1 (eC),
@@ -127,6 +129,7 @@ typedef struct {
   float attn_drop, proj_drop;      /* dropout on softmax weights / on mix + FFN outputs      */
   int32_t training;
   uint64_t seed;
+  const uint64_t* seed_offset;     /* optional device pointer added to `seed` by the kernels (see vx_jlc_desc) */
 } vx_pwa_desc;
 
 /* Per-modality parameter block, in this order (16 pointers):

@@ -60,3 +60,27 @@ def test_dropout_train_mode_runs_and_differs():
     m.eval()
     with torch.no_grad():
         assert torch.equal(m(x), m(x))
+
+
+def test_train_step_graph_matches_eager_and_redraws_dropout():
+    """TrainStep: the CUDA-graph replay is the same computation as the eager step (dropout off), capture leaves the
+    model untouched, and with dropout on successive replays draw different masks."""
+    from veloxseg_b200.nn import VeloxSeg
+    from veloxseg_b200.train import TrainStep
+    cfg = MODEL_CONFIGS["tiny"]
+    x = torch.randn(2, 2, 64, 64, 64)
+    y = (torch.rand(2, 1, 64, 64, 64) > 0.9).long()
+    losses = {}
+    for mode in (False, True):
+        torch.manual_seed(3)
+        m = VeloxSeg(**cfg)
+        G.zero_dropout(m)
+        ts = TrainStep(m, 2, DEV, use_graph=mode)
+        losses[mode] = [ts.step(x, y, sync=True) for _ in range(3)]
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) <= 2e-3 * abs(a), (losses[False], losses[True])
+    assert losses[True][2] < losses[True][0]            # it trains
+    torch.manual_seed(3)
+    ts = TrainStep(VeloxSeg(**cfg), 2, DEV, lr=0.0, weight_decay=0.0, use_graph=True)     # dropout on, no parameter change
+    l = [ts.step(x, y, sync=True) for _ in range(3)]
+    assert len({round(v, 6) for v in l}) == 3, l        # same weights, same batch, different masks

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libveloxseg_sm100.so")
 class JlcDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("C", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                 ("groups", C.c_int32), ("expansion", C.c_int32), ("eps", C.c_float), ("drop_p", C.c_float),
-                ("training", C.c_int32), ("seed", C.c_uint64)]
+                ("training", C.c_int32), ("seed", C.c_uint64), ("seed_offset", C.c_void_p)]
 
 
 class MixerDesc(C.Structure):
@@ -35,7 +35,8 @@ class PwaDesc(C.Structure):
                 ("W", C.c_int32), ("heads", C.c_int32), ("n_scales", C.c_int32),
                 ("big", (C.c_int32 * 3) * VX_MAX_SCALES), ("small", (C.c_int32 * 3) * VX_MAX_SCALES),
                 ("c_qk", C.c_int32), ("c_v", C.c_int32), ("ffn_expansion", C.c_int32), ("ln_eps", C.c_float),
-                ("attn_drop", C.c_float), ("proj_drop", C.c_float), ("training", C.c_int32), ("seed", C.c_uint64)]
+                ("attn_drop", C.c_float), ("proj_drop", C.c_float), ("training", C.c_int32), ("seed", C.c_uint64),
+                ("seed_offset", C.c_void_p)]
 
 
 class PwaSaved(C.Structure):

@@ -31,6 +31,10 @@ int check_launch(const char* what) {
   return VX_OK;
 }
 
+static thread_local const void* g_seed_dev = nullptr;
+void set_seed_dev(const void* p) { g_seed_dev = p; }
+const unsigned long long* get_seed_dev() { return (const unsigned long long*)g_seed_dev; }
+
 static thread_local char g_scope[96] = "";
 void prof_scope(const char* fmt, ...) {
   va_list ap;

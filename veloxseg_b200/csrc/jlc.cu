@@ -688,6 +688,7 @@ extern "C" int vx_jlc_fwd(const vx_jlc_desc* d, const void* const* in, void* con
   JlcLayout L;
   VX_TRY(jlc_layout(d, L));
   prof_scope("jlc_fwd B%d C%d S%d", d->B, d->C, d->D * d->H * d->W);
+  set_seed_dev(d->seed_offset);
   if (!workspace || workspace_bytes < L.total) { set_error("jlc_fwd: workspace %zu < %zu", workspace_bytes, L.total); return VX_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
@@ -751,6 +752,7 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
   JlcLayout L;
   VX_TRY(jlc_layout(d, L));
   prof_scope("jlc_bwd B%d C%d S%d", d->B, d->C, d->D * d->H * d->W);
+  set_seed_dev(d->seed_offset);
   if (!workspace || workspace_bytes < L.total) { set_error("jlc_bwd: workspace %zu < %zu", workspace_bytes, L.total); return VX_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;

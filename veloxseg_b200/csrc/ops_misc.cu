@@ -137,6 +137,7 @@ extern "C" int vx_mixer_fwd(const vx_mixer_desc* d, const void* const* in, void*
                             size_t workspace_bytes, vx_stream_t stream) {
   int K;
   VX_TRY(mixer_check(d, K));
+  set_seed_dev(nullptr);
   prof_scope("mixer_fwd B%d K%d N%d S%d", d->B, K, d->C_out, d->S);
   (void)workspace; (void)workspace_bytes;
   cudaStream_t st = (cudaStream_t)stream;
@@ -160,6 +161,7 @@ extern "C" int vx_mixer_bwd(const vx_mixer_desc* d, const void* const* in, void*
                             size_t workspace_bytes, vx_stream_t stream) {
   int K;
   VX_TRY(mixer_check(d, K));
+  set_seed_dev(nullptr);
   prof_scope("mixer_bwd B%d K%d N%d S%d", d->B, K, d->C_out, d->S);
   const size_t need = vx_mixer_workspace(d);
   if (!workspace || workspace_bytes < need) { set_error("mixer_bwd: workspace %zu < %zu", workspace_bytes, need); return VX_ERR_WORKSPACE; }
@@ -289,6 +291,7 @@ extern "C" int vx_lnpw_fwd(const vx_lnpw_desc* d, const void* const* in, void* c
                            size_t workspace_bytes, vx_stream_t stream) {
   if (!vx_lnpw_workspace(d)) { set_error("lnpw: bad descriptor"); return VX_ERR_BAD_DESC; }
   (void)workspace; (void)workspace_bytes;
+  set_seed_dev(nullptr);
   prof_scope("lnpw_fwd B%d Ci%d Co%d S%d", d->B, d->C_in, d->C_out, d->S);
   cudaStream_t st = (cudaStream_t)stream;
   float* y = (float*)out[0];
@@ -310,6 +313,7 @@ extern "C" int vx_lnpw_bwd(const vx_lnpw_desc* d, const void* const* in, void* c
   const size_t need = vx_lnpw_workspace(d);
   if (!need) { set_error("lnpw: bad descriptor"); return VX_ERR_BAD_DESC; }
   if (!workspace || workspace_bytes < need) { set_error("lnpw_bwd: workspace %zu < %zu", workspace_bytes, need); return VX_ERR_WORKSPACE; }
+  set_seed_dev(nullptr);
   prof_scope("lnpw_bwd B%d Ci%d Co%d S%d", d->B, d->C_in, d->C_out, d->S);
   cudaStream_t st = (cudaStream_t)stream;
   const float* dy = (const float*)in[0];

@@ -39,7 +39,7 @@ VX_DEV const float* pw_w_ptr(const PwProblem& P, int co, int ci) {
   }
   return P.seg[0].W;
 }
-VX_DEV float pw_prologue(const PwProblem& P, float x, int b, int cg, int v, int S, float pinv) {
+VX_DEV float pw_prologue(const PwProblem& P, float x, int b, int cg, int v, int S, float pinv, uint64_t soff) {
   if (P.pro == PRO_AFFINE) {
     const int k = b * P.pro_bstride + cg;
     x = fmaf(x, __ldg(P.pro_a + k), __ldg(P.pro_c + k));
@@ -47,7 +47,7 @@ VX_DEV float pw_prologue(const PwProblem& P, float x, int b, int cg, int v, int 
     x = gelu_f(x);
   }
   if (P.pro == PRO_DROPOUT || P.pro == PRO_GELU_DROPOUT)
-    x *= dropout_scale(P.pro_seed, P.pro_site, ((uint64_t)b * P.Ci + cg) * (uint64_t)S + v, P.pro_drop_p, pinv);
+    x *= dropout_scale(P.pro_seed + soff, P.pro_site, ((uint64_t)b * P.Ci + cg) * (uint64_t)S + v, P.pro_drop_p, pinv);
   return x;
 }
 
@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(PW_THREADS) pw_kernel(const __grid_constant__ 
   const int vg = tid & 15, cgp = tid >> 4;            // voxel group (4 voxels), channel group (8 channels)
   const bool pro_drop = P.pro == PRO_DROPOUT || P.pro == PRO_GELU_DROPOUT;
   const float pinv = pro_drop ? 1.0f / (1.0f - P.pro_drop_p) : 1.f;
+  const uint64_t soff = batch.seed_dev ? (uint64_t)__ldg(batch.seed_dev) : 0;
 
   float acc[8][4];
 #pragma unroll
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(PW_THREADS) pw_kernel(const __grid_constant__ 
     for (int r = 0; r < 8; ++r) {
       const int e = r * PW_THREADS + tid;
       const int v = e & (PW_TS - 1), k = e >> 6;
-      if (k0 + k < Ci && v0 + v < S) Xs[buf][k][v] = pw_prologue(P, Xs[buf][k][v], b, k0 + k, v0 + v, S, pinv);
+      if (k0 + k < Ci && v0 + v < S) Xs[buf][k][v] = pw_prologue(P, Xs[buf][k][v], b, k0 + k, v0 + v, S, pinv, soff);
     }
   };
 
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(PW_THREADS) pw_kernel(const __grid_constant__ 
     }
     if (P.drop_p > 0.f) {
       float ms[4];
-      dropout_scale4(P.seed, P.site, lbase + vb, P.drop_p, dinv, ms);
+      dropout_scale4(P.seed + soff, P.site, lbase + vb, P.drop_p, dinv, ms);
 #pragma unroll
       for (int i = 0; i < 4; ++i) y[i] *= ms[i];
     }
@@ -209,7 +210,9 @@ int pw_forward(const PwBatch& batch, cudaStream_t stream) {
   }
   if (batch.nprob <= 0 || batch.B <= 0 || batch.S <= 0) return VX_OK;
   dim3 grid(cdiv(batch.S, PW_TS), cdiv(maxCo, PW_TC), batch.nprob * batch.B);
-  VX_LAUNCH(pw_kernel, grid, dim3(PW_THREADS), 0, stream, batch);
+  PwBatch launch = batch;
+  launch.seed_dev = get_seed_dev();
+  VX_LAUNCH(pw_kernel, grid, dim3(PW_THREADS), 0, stream, launch);
   return check_launch("pw_kernel");
 }
 
@@ -251,6 +254,7 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_kernel(const __grid_const
   const float yinv = P.y_drop_p > 0.f ? 1.0f / (1.0f - P.y_drop_p) : 1.f;
   const float xinv = P.x_drop_p > 0.f ? 1.0f / (1.0f - P.x_drop_p) : 1.f;
   const int nchunks = (S + TV - 1) / TV;
+  const uint64_t soff = batch.seed_dev ? (uint64_t)__ldg(batch.seed_dev) : 0;
 
   float acc[4][4];
 #pragma unroll
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_kernel(const __grid_const
       if (co < Co && gv < S) {
         const size_t gi = ((size_t)b * Co + co) * S + gv;
         val = __ldg(P.dY + gi);
-        if (P.y_drop_p > 0.f) val *= dropout_scale(P.y_seed, P.y_site, gi, P.y_drop_p, yinv);
+        if (P.y_drop_p > 0.f) val *= dropout_scale(P.y_seed + soff, P.y_site, gi, P.y_drop_p, yinv);
       }
       sY[v * CoP + co] = val;
     }
@@ -288,7 +292,7 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_kernel(const __grid_const
           } else if (P.xpro == PRO_GELU) {
             val = gelu_f(val);
           } else if (P.xpro == PRO_GELU_DROPOUT) {
-            val = gelu_f(val) * dropout_scale(P.x_seed, P.x_site, ((uint64_t)b * Ci + cg) * (uint64_t)S + gv, P.x_drop_p, xinv);
+            val = gelu_f(val) * dropout_scale(P.x_seed + soff, P.x_site, ((uint64_t)b * Ci + cg) * (uint64_t)S + gv, P.x_drop_p, xinv);
           }
         } else if (cg == Ci) {
           val = 1.f;
@@ -373,7 +377,9 @@ int pw_wgrad(const WgBatch& batch, cudaStream_t stream) {
   if (nK < 1) nK = 1;
   if (nK > nchunks) nK = nchunks;
   dim3 grid(nK, maxblocks, batch.nprob);
-  VX_LAUNCH(pw_wgrad_kernel, grid, dim3(WG_THREADS), smem, stream, batch, TV, nK);
+  WgBatch launch = batch;
+  launch.seed_dev = get_seed_dev();
+  VX_LAUNCH(pw_wgrad_kernel, grid, dim3(WG_THREADS), smem, stream, launch, TV, nK);
   return check_launch("pw_wgrad_kernel");
 }
 

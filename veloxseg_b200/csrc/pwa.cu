@@ -213,6 +213,7 @@ struct AttnArgs {
   int B, heads, Ns, L, l;
   float scale, drop_p;
   uint64_t seed;
+  const unsigned long long* seed_dev;
 };
 
 constexpr int ATT_THREADS = 128;
@@ -221,7 +222,8 @@ constexpr uint32_t ATT_SITE = 7;
 // keep-scales of 4 consecutive keys of one (window,row): one Philox call per 4 score elements
 VX_DEV void attn_drop4(const AttnArgs& A, size_t row, int k4, float inv_keep, float (&ms)[4]) {
   const int nk4 = (A.L + 3) >> 2;
-  const uint4 r = philox4x32(A.seed, (uint64_t)row * nk4 + k4, ATT_SITE);
+  const uint64_t soff = A.seed_dev ? (uint64_t)__ldg(A.seed_dev) : 0;
+  const uint4 r = philox4x32_call(A.seed + soff, (uint64_t)row * nk4 + k4, ATT_SITE);
   const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) ms[i] = ((float)(bits[i] >> 8) * (1.0f / 16777216.0f) < A.drop_p) ? 0.f : inv_keep;
@@ -633,6 +635,7 @@ extern "C" int vx_pwa_block_fwd(const vx_pwa_desc* d, const void* const* in, voi
   PwaLayout P;
   VX_TRY(pwa_layout(d, P));
   prof_scope("pwa_fwd B%d M%d C%d S%d L%d", d->B, d->M, d->C, P.G.S, P.G.L);
+  set_seed_dev(d->seed_offset);
   if (!workspace || workspace_bytes < P.total) { set_error("pwa_fwd: workspace %zu < %zu", workspace_bytes, P.total); return VX_ERR_WORKSPACE; }
   const PwaGeo& G = P.G;
   cudaStream_t st = (cudaStream_t)stream;
@@ -690,7 +693,7 @@ extern "C" int vx_pwa_block_fwd(const vx_pwa_desc* d, const void* const* in, voi
     AttnArgs A{};
     A.Q = SV(SV_QT); A.K = SV(SV_KT); A.V = SV(SV_VT); A.biasT = biasT; A.O = SV(SV_OT); A.lse = SV(SV_LSE);
     A.B = B; A.heads = G.heads; A.Ns = G.Ns; A.L = G.L; A.l = G.l;
-    A.scale = 1.0f / sqrtf((float)P.cq_h); A.drop_p = attn_p; A.seed = d->seed;
+    A.scale = 1.0f / sqrtf((float)P.cq_h); A.drop_p = attn_p; A.seed = d->seed; A.seed_dev = get_seed_dev();
     VX_TRY(dispatch_attn(A, P.cq_h, P.cv_h, false, st));
   }
   // scatter
@@ -751,6 +754,7 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
   PwaLayout P;
   VX_TRY(pwa_layout(d, P));
   prof_scope("pwa_bwd B%d M%d C%d S%d L%d", d->B, d->M, d->C, P.G.S, P.G.L);
+  set_seed_dev(d->seed_offset);
   if (!workspace || workspace_bytes < P.total) { set_error("pwa_bwd: workspace %zu < %zu", workspace_bytes, P.total); return VX_ERR_WORKSPACE; }
   const PwaGeo& G = P.G;
   cudaStream_t st = (cudaStream_t)stream;
@@ -892,7 +896,7 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
     A.Q = SV(SV_QT); A.K = SV(SV_KT); A.V = SV(SV_VT); A.biasT = biasT; A.O = (float*)SV(SV_OT); A.lse = (float*)SV(SV_LSE);
     A.dO = dOt; A.dQ = dQt; A.dK = dKt; A.dV = dVt; A.dbiasT = dbiasT;
     A.B = B; A.heads = G.heads; A.Ns = G.Ns; A.L = G.L; A.l = G.l;
-    A.scale = 1.0f / sqrtf((float)P.cq_h); A.drop_p = attn_p; A.seed = d->seed;
+    A.scale = 1.0f / sqrtf((float)P.cq_h); A.drop_p = attn_p; A.seed = d->seed; A.seed_dev = get_seed_dev();
     VX_TRY(dispatch_attn(A, P.cq_h, P.cv_h, true, st));
     VX_LAUNCH(pwa_bias_bwd_kernel, dim3(cdiv(nbias, 256)), dim3(256), 0, st, (const float*)dbiasT, index, dtable, G.heads, G.l);
     VX_TRY(check_launch("pwa_bias_bwd_kernel"));

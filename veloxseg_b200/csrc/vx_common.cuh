@@ -28,8 +28,9 @@
   extern __shared__ __align__(16) unsigned char vx_dsm_[];                                \
   type* name = reinterpret_cast<type*>(vx_dsm_)
 #define VX_SET_SMEM(kern, bytes)                                                          \
-  do { auto _k = kern; if ((bytes) > 48 * 1024)                                           \
-         cudaFuncSetAttribute(_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); } while (0)
+  do { auto _k = kern; static size_t _have = 48 * 1024;   /* one static per call site = per kernel instantiation */ \
+       if ((size_t)(bytes) > _have) {                                                     \
+         cudaFuncSetAttribute(_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); _have = (bytes); } } while (0)
 #endif
 
 #define VX_DEV __device__ __forceinline__

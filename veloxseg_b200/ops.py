@@ -24,6 +24,33 @@ Tensor = torch.Tensor
 _f32 = torch.float32
 
 
+_seed_offset = {}
+
+
+def seed_offset_tensor(device) -> Optional[Tensor]:
+    """Device-resident uint64 (stored as int64) that every dropout kernel adds to its per-call seed.  `advance_seed`
+    bumps it with a kernel, so a CUDA graph that captured one training step draws fresh masks on every replay."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        return None
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _seed_offset:
+        _seed_offset[key] = torch.zeros(1, dtype=torch.int64, device=torch.device("cuda", key))
+    return _seed_offset[key]
+
+
+def seed_offset_ptr(device):
+    t = seed_offset_tensor(device)
+    return t.data_ptr() if t is not None else None
+
+
+def advance_seed(device):
+    """Call once per training step (capturable: a single in-place add on the current stream)."""
+    t = seed_offset_tensor(device)
+    if t is not None:
+        t.add_(0x632BE59BD9B4E019)
+
+
 def _stream(t: Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
@@ -46,7 +73,8 @@ def _chk(t: Tensor, name: str) -> Tensor:
 # ----------------------------------------------------------------------------------------------------
 def jlc_desc(x: Tensor, groups: int, expansion: int, drop_p: float, training: bool, seed: int) -> JlcDesc:
     B, Cc, D, H, W = x.shape
-    return JlcDesc(B, Cc, D, H, W, groups, expansion, 1e-5, float(drop_p), int(bool(training)), int(seed))
+    return JlcDesc(B, Cc, D, H, W, groups, expansion, 1e-5, float(drop_p), int(bool(training)), int(seed),
+                   seed_offset_ptr(x.device) if training else None)
 
 
 def jlc_fwd_raw(lib, stream, x, params: Sequence[Tensor], groups, expansion, drop_p=0.0, training=False, seed=0):
@@ -239,7 +267,8 @@ def pwa_desc(xs: Sequence[Tensor], geo: dict, ffn_expansion: int, attn_drop=0.0,
             big[j][a] = int(geo["bws"][j][a])
             small[j][a] = int(geo["sws"][j][a])
     return PwaDesc(B, len(xs), Cc, D, H, W, int(geo["heads"]), nb, big, small, int(geo["cqk"]), int(geo["cv"]),
-                   int(ffn_expansion), 1e-6, float(attn_drop), float(proj_drop), int(bool(training)), int(seed))
+                   int(ffn_expansion), 1e-6, float(attn_drop), float(proj_drop), int(bool(training)), int(seed),
+                   seed_offset_ptr(xs[0].device) if training else None)
 
 
 def pwa_saved_sizes(lib, d: PwaDesc) -> List[int]:

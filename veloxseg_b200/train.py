@@ -84,25 +84,76 @@ class GradBuckets:
 
 class TrainStep:
     """`step(inputs, labels)` = one optimisation step; accepts host (pinned) or device tensors and returns the loss
-    as a Python float only when asked (`sync=True`), mirroring the reference's per-step `loss.item()`."""
+    as a Python float only when asked (`sync=True`), mirroring the reference's per-step `loss.item()`.
+
+    On a single CUDA device the whole step (forward, loss, backward, AdamW) is captured once into a CUDA graph and
+    replayed: ~1 200 kernel launches per step collapse into one graph launch, which matters because the fused step is
+    short enough for host launch overhead to dominate.  Dropout stays random across replays because the kernels add a
+    device-resident offset (ops.advance_seed, captured in the graph) to their seeds."""
 
     def __init__(self, model: torch.nn.Module, num_modal: int, device, lr: float = 2.5e-4, weight_decay: float = 0.01,
                  deep_weights=(1, 1, 1, 1), rc_weight: float = 0.5, feature_weight: float = 2.0,
-                 bucket_bytes: int = 4 << 20):
+                 bucket_bytes: int = 4 << 20, use_graph: Optional[bool] = None):
         self.device = torch.device(device)
         self.model = model.to(self.device).train()
         self.loss_fn = Loss(num_modal, deep_weights, rc_weight, feature_weight)
         self.buckets = GradBuckets(list(self.model.parameters()), bucket_bytes)
-        fused = self.device.type == "cuda"
-        self.opt = torch.optim.AdamW(self.model.parameters(), lr=lr, weight_decay=weight_decay, fused=fused)
+        cuda = self.device.type == "cuda"
+        self.use_graph = (cuda and self.buckets.world == 1) if use_graph is None else bool(use_graph)
+        self.opt = torch.optim.AdamW(self.model.parameters(), lr=lr, weight_decay=weight_decay, fused=cuda,
+                                     capturable=cuda and self.use_graph)
+        self._graph = None
+        self.graph_launches = 0        # kernels of libveloxseg_sm100 recorded in the captured step
 
-    def step(self, inputs: torch.Tensor, labels: torch.Tensor, sync: bool = False):
-        x = inputs.to(self.device, non_blocking=True)
-        y = labels.to(self.device, non_blocking=True)
+    def _step_eager(self, x, y):
+        from . import ops
         self.buckets.zero()
+        ops.advance_seed(self.device)
         out = self.model(x)
         loss = self.loss_fn(out, y, x)
         loss.backward()
         self.buckets.finish()
         self.opt.step()
-        return float(loss.item()) if sync else loss.detach()
+        return loss.detach()
+
+    def _capture(self, inputs, labels):
+        from . import _lib
+        self._sx = torch.empty(inputs.shape, dtype=inputs.dtype, device=self.device)
+        self._sy = torch.empty(labels.shape, dtype=labels.dtype, device=self.device)
+        self._sx.copy_(inputs)
+        self._sy.copy_(labels)
+        # the warm-up iterations below are real optimiser steps: snapshot and restore so that capture is side-effect free
+        snap_p = [p.detach().clone() for p in self.model.parameters()]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._step_eager(self._sx, self._sy)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        lib = _lib.get_lib()
+        n0 = lib.c.vx_launch_count()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._sloss = self._step_eager(self._sx, self._sy)
+        self.graph_launches = int(lib.c.vx_launch_count() - n0)
+        with torch.no_grad():
+            for p, q in zip(self.model.parameters(), snap_p):
+                p.copy_(q)
+            for st in self.opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        torch.cuda.synchronize(self.device)
+
+    def step(self, inputs: torch.Tensor, labels: torch.Tensor, sync: bool = False):
+        if self.use_graph:
+            if self._graph is None:
+                self._capture(inputs, labels)
+            self._sx.copy_(inputs, non_blocking=True)
+            self._sy.copy_(labels, non_blocking=True)
+            self._graph.replay()
+            loss = self._sloss
+        else:
+            loss = self._step_eager(inputs.to(self.device, non_blocking=True), labels.to(self.device, non_blocking=True))
+        return float(loss.item()) if sync else loss
