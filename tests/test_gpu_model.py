@@ -84,3 +84,28 @@ def test_train_step_graph_matches_eager_and_redraws_dropout():
     ts = TrainStep(VeloxSeg(**cfg), 2, DEV, lr=0.0, weight_decay=0.0, use_graph=True)     # dropout on, no parameter change
     l = [ts.step(x, y, sync=True) for _ in range(3)]
     assert len({round(v, 6) for v in l}) == 3, l        # same weights, same batch, different masks
+
+
+def test_parallel_branches_match_serial():
+    """Forked decoder streams (eager and graph-captured) compute the same loss and gradients as the serial schedule."""
+    from veloxseg_b200.nn import VeloxSeg
+    cfg = MODEL_CONFIGS["tiny"]
+    x = torch.randn(2, 2, 64, 64, 64, device=DEV)
+    res = {}
+    for par in (False, True):
+        torch.manual_seed(3)
+        m = VeloxSeg(**cfg)
+        G.zero_dropout(m)
+        m = m.to(DEV).train()
+        m.parallel_branches = par
+        for rep in range(3):       # repeat: a race would show up as run-to-run differences
+            m.zero_grad(set_to_none=True)
+            outs = m(x)
+            loss = sum((o * o).mean() for o in outs)
+            loss.backward()
+            torch.cuda.synchronize()
+            res[(par, rep)] = (float(loss), torch.cat([p.grad.flatten() for p in m.parameters()]).clone())
+    ref_loss, ref_g = res[(False, 0)]
+    for k, (l, g) in res.items():
+        assert abs(l - ref_loss) <= 1e-5 * abs(ref_loss), (k, l, ref_loss)
+        assert float((g - ref_g).norm()) <= 1e-4 * float(ref_g.norm()), k

@@ -614,15 +614,43 @@ class VeloxSeg(nn.Module):
     def scale_prediction(self, pred):
         return ops.resize_trilinear(pred, tuple(self.size))
 
+    # Independent branches of the training graph (segmentation student, one reconstruction teacher per modality) are
+    # issued on forked CUDA streams: their kernels are small (most occupy a fraction of the 148 SMs), so running the
+    # branches side by side -- in forward and, because autograd replays every node on its forward stream, in backward
+    # too -- fills the machine.  Under CUDA-graph capture the forks become parallel graph branches.
+    parallel_branches = True
+
+    def _side_streams(self, device):
+        if getattr(self, "_streams_dev", None) != device:
+            self._streams = [torch.cuda.Stream(device=device) for _ in range(self.num_modalities)]
+            self._streams_dev = device
+        return self._streams
+
     def forward(self, x):
         if self.training:
             attns, encs = self.encoder(x)
+            fork = self.parallel_branches and x.is_cuda
+            rcs, rc_prams = [None] * self.num_modalities, [None] * self.num_modalities
+            if fork:
+                main = torch.cuda.current_stream(x.device)
+                streams = self._side_streams(x.device)
+                for m, st in enumerate(streams):
+                    st.wait_stream(main)
+                    with torch.cuda.stream(st):
+                        feats = [[attns[i][m], encs[i]] for i in range(4)]
+                        for a, e in feats:          # produced on `main`, consumed here: tell the caching allocator
+                            a.record_stream(st)
+                            e.record_stream(st)
+                        rcs[m], rc_prams[m] = self.rc_decoders[m](*feats)
             pred, dec_pram = self.decoder(*encs)
             pred = [self.scale_prediction(p) for p in (pred if isinstance(pred, (list, tuple)) else [pred])]
-            rcs, rc_prams = [], []
-            for m in range(self.num_modalities):
-                rc, g = self.rc_decoders[m](*[[attns[i][m], encs[i]] for i in range(4)])
-                rcs.append(rc)
-                rc_prams.append(g)
+            if fork:
+                for m, st in enumerate(streams):
+                    main.wait_stream(st)
+                    rcs[m].record_stream(main)
+                    rc_prams[m].record_stream(main)
+            else:
+                for m in range(self.num_modalities):
+                    rcs[m], rc_prams[m] = self.rc_decoders[m](*[[attns[i][m], encs[i]] for i in range(4)])
             return pred + [torch.cat(rcs, dim=1)] + [dec_pram] + rc_prams
         return self.decoder(*self.encoder(x))
