@@ -38,6 +38,11 @@ def count_map(image: Sequence[int], roi: Sequence[int], starts, device, dtype=to
     return cnt
 
 
+def _logits(y):
+    """Net.forward of the reference's inference wrapper takes outputs[0] of a list (utils/inference_petct.py:46-51)."""
+    return y[0] if isinstance(y, (list, tuple)) else y
+
+
 @torch.no_grad()
 def sliding_window_predict(inputs: torch.Tensor, predictor: Callable, roi_size: Sequence[int], sw_batch_size: int = 2,
                            overlap: float = 0.25, group=None, shard: bool = True) -> torch.Tensor:
@@ -61,9 +66,7 @@ def sliding_window_predict(inputs: torch.Tensor, predictor: Callable, roi_size: 
         win = torch.cat([inputs[i // nwin:i // nwin + 1, :, starts[i % nwin][0]:starts[i % nwin][0] + roi_size[0],
                                 starts[i % nwin][1]:starts[i % nwin][1] + roi_size[1],
                                 starts[i % nwin][2]:starts[i % nwin][2] + roi_size[2]] for i in ids])
-        y = predictor(win)
-        if isinstance(y, (list, tuple)):
-            y = y[0]
+        y = _logits(predictor(win))
         if out is None:
             out = torch.zeros((B, y.shape[1]) + tuple(image), dtype=y.dtype, device=y.device)
         for k, i in enumerate(ids):
@@ -71,7 +74,7 @@ def sliding_window_predict(inputs: torch.Tensor, predictor: Callable, roi_size: 
             out[i // nwin, :, a:a + roi_size[0], b:b + roi_size[1], c:c + roi_size[2]] += y[k]
     if world > 1:
         if out is None:     # more ranks than windows
-            n_cls = predictor(inputs[:1, :, :roi_size[0], :roi_size[1], :roi_size[2]]).shape[1]
+            n_cls = _logits(predictor(inputs[:1, :, :roi_size[0], :roi_size[1], :roi_size[2]])).shape[1]
             out = torch.zeros((B, n_cls) + tuple(image), dtype=inputs.dtype, device=inputs.device)
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
     out = out / count_map(image, roi_size, starts, out.device, out.dtype)
