@@ -37,11 +37,18 @@ typedef enum {
 
 int vx_version(void);
 const char* vx_last_error_string(void);
+/* Process-wide switches (diagnostics / A-B measurements; defaults give the production path).
+ *   VX_OPT_PW_TENSOR_CORES  1 (default): 1x1 contractions with >= 512 voxels run on the tcgen05 3xTF32 kernel;
+ *                           0: every contraction uses the fp32 SIMT kernels.
+ *   VX_OPT_PW_SMALL_MAX_S   voxel count below which the warp-per-(32 voxels x 4 channels) kernel is used (tuning probe).
+ *   VX_OPT_PW_TC_MIN_S      voxel count from which the tensor-core kernel is used (tuning probe). */
+enum { VX_OPT_PW_TENSOR_CORES = 1, VX_OPT_PW_SMALL_MAX_S = 2, VX_OPT_PW_TC_MIN_S = 3 };
+int vx_set_option(int option, int value);
 /* number of kernels this library has enqueued since it was loaded (all threads, all streams) */
 uint64_t vx_launch_count(void);
 /* Per-kernel timing with CUDA events on the launching stream (diagnostics for bench.py; off by default).
  * vx_profile_enable(1) brackets every subsequent launch with an event pair; vx_profile_report() synchronises those
- * events and writes one line per (scope, kernel): "scope|kernel|launches|total_ms\n"; returns the bytes needed. */
+ * events and writes one line per (scope, kernel): "scope|kernel|launches|total_ms|algorithmic_bytes\n"; returns the bytes needed. */
 int vx_profile_enable(int on);
 void vx_profile_reset(void);
 size_t vx_profile_report(char* buf, size_t cap);

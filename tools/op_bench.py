@@ -42,6 +42,11 @@ def main():
     ap.add_argument("--profile", action="store_true", help="print the library's per-kernel event table per op")
     args = ap.parse_args()
     lib, st = _lib.get_lib(), torch.cuda.current_stream().cuda_stream
+    lib.set_option(1, int(os.environ.get("VX_PW_TC", "1") == "1"))
+    if "VX_PW_SMALL_MAX_S" in os.environ:
+        lib.set_option(2, int(os.environ["VX_PW_SMALL_MAX_S"]))
+    if "VX_PW_TC_MIN_S" in os.environ:
+        lib.set_option(3, int(os.environ["VX_PW_TC_MIN_S"]))
     B, res = args.B, []
     torch.manual_seed(0)
 

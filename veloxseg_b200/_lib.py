@@ -62,7 +62,7 @@ class LnpwDesc(C.Structure):
 
 # every symbol include/veloxseg_abi.h declares
 SYMBOLS = [
-    "vx_version", "vx_last_error_string", "vx_launch_count", "vx_profile_enable", "vx_profile_reset",
+    "vx_version", "vx_last_error_string", "vx_launch_count", "vx_set_option", "vx_profile_enable", "vx_profile_reset",
     "vx_profile_report",
     "vx_jlc_workspace", "vx_jlc_fwd", "vx_jlc_bwd",
     "vx_mixer_workspace", "vx_mixer_fwd", "vx_mixer_bwd",
@@ -128,15 +128,18 @@ class VxLib:
         self.c.vx_profile_enable(int(on))
 
     def profile_report(self):
-        """[(scope, kernel, launches, total_ms)] since the last profile(True)."""
+        """[(scope, kernel, launches, total_ms, algorithmic_bytes)] since the last profile(True)."""
         n = self.c.vx_profile_report(None, 0)
         buf = C.create_string_buffer(int(n) + 16)
         self.c.vx_profile_report(buf, len(buf))
         rows = []
         for line in buf.value.decode().splitlines():
-            scope, kern, cnt, ms = line.rsplit("|", 3)
-            rows.append((scope, kern, int(cnt), float(ms)))
+            scope, kern, cnt, ms, nbytes = line.rsplit("|", 4)
+            rows.append((scope, kern, int(cnt), float(ms), float(nbytes)))
         return rows
+
+    def set_option(self, option: int, value: int):
+        self.check(self.c.vx_set_option(int(option), int(value)), "vx_set_option")
 
     def last_error(self) -> str:
         s = self.c.vx_last_error_string()

@@ -44,7 +44,8 @@ void prof_scope(const char* fmt, ...) {
 }
 
 #ifndef VX_EMU
-struct ProfRec { std::string key; cudaEvent_t a, b; };
+struct ProfRec { std::string key; cudaEvent_t a, b; double bytes; };
+static thread_local double g_next_bytes = 0.0;
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 static int g_prof_on = 0;
@@ -65,10 +66,14 @@ int prof_begin(const char* kernel, cudaStream_t st) {
   r.key = std::string(g_scope) + "|" + kernel;
   r.a = pool_get();
   r.b = pool_get();
+  r.bytes = g_next_bytes;
+  g_next_bytes = 0.0;
   cudaEventRecord(r.a, st);
   g_prof.push_back(r);
   return (int)g_prof.size() - 1;
 }
+
+void prof_bytes(double b) { g_next_bytes = b; }
 
 void prof_end(int slot, cudaStream_t st) {
   if (slot < 0) return;
@@ -96,29 +101,41 @@ extern "C" void vx_profile_reset(void) {
 }
 extern "C" size_t vx_profile_report(char* buf, size_t cap) {
   std::lock_guard<std::mutex> lk(vx::g_prof_mu);
-  std::map<std::string, std::pair<int, double>> agg;
+  struct Agg { int n = 0; double ms = 0.0, bytes = 0.0; };
+  std::map<std::string, Agg> agg;
   for (auto& r : vx::g_prof) {
     cudaEventSynchronize(r.b);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
     auto& e = agg[r.key];
-    e.first += 1; e.second += ms;
+    e.n += 1; e.ms += ms; e.bytes += r.bytes;
   }
   std::string out;
-  char line[64];
+  char line[96];
   for (auto& kv : agg) {
-    snprintf(line, sizeof(line), "|%d|%.6f\n", kv.second.first, kv.second.second);
+    snprintf(line, sizeof(line), "|%d|%.6f|%.0f\n", kv.second.n, kv.second.ms, kv.second.bytes);
     out += kv.first + line;
   }
   if (buf && cap > 0) { const size_t n = out.size() < cap - 1 ? out.size() : cap - 1; memcpy(buf, out.data(), n); buf[n] = 0; }
   return out.size() + 1;
 }
 #else
+namespace vx { void prof_bytes(double) {} }
 extern "C" int vx_profile_enable(int) { return 0; }
 extern "C" void vx_profile_reset(void) {}
 extern "C" size_t vx_profile_report(char*, size_t) { return 0; }
 #endif
 
-extern "C" int vx_version(void) { return 100; }
+extern "C" int vx_set_option(int option, int value) {
+#ifndef VX_EMU
+  if (option == VX_OPT_PW_TENSOR_CORES) { vx::pw_tc_set(value ? 1 : 0); return VX_OK; }
+  if (option == VX_OPT_PW_SMALL_MAX_S) { vx::pw_set_thresholds(value, -1); return VX_OK; }
+  if (option == VX_OPT_PW_TC_MIN_S) { vx::pw_set_thresholds(-1, value); return VX_OK; }
+#endif
+  vx::set_error("vx_set_option: unknown option %d", option);
+  return VX_ERR_BAD_DESC;
+}
+
+extern "C" int vx_version(void) { return 101; }
 extern "C" uint64_t vx_launch_count(void) { return __atomic_load_n(&vx::g_launches, __ATOMIC_RELAXED); }
 extern "C" const char* vx_last_error_string(void) { return vx::g_err; }

@@ -711,6 +711,7 @@ extern "C" int vx_jlc_fwd(const vx_jlc_desc* d, const void* const* in, void* con
   A.z = z; A.part = part_z; A.B = d->B; A.C = d->C; A.D = d->D; A.H = d->H; A.W = d->W; A.t = L.tf;
   const int npos = L.tf.TZ * L.tf.TY * (L.tf.TX / L.tf.VX);
   A.uniform_warps = (npos % 32 == 0) ? 1 : 0;
+  prof_bytes(4.0 * sizeof(float) * (double)L.BCS);       // x in, z1 z3 z5 out
   if (CG == 4) VX_TRY(launch_conv_fwd<4>(A, d->groups, st));
   else if (CG == 8) VX_TRY(launch_conv_fwd<8>(A, d->groups, st));
   else VX_TRY(launch_conv_fwd<16>(A, d->groups, st));
@@ -719,6 +720,7 @@ extern "C" int vx_jlc_fwd(const vx_jlc_desc* d, const void* const* in, void* con
   VX_LAUNCH(jlc_finalize_kernel, dim3(cdiv(3 * rows, 128)), dim3(128), 0, st, (const float*)part_z, 3 * rows, ntiles,
             (float)S, d->eps, stats, (float*)nullptr, (float*)nullptr);
   VX_TRY(check_launch("jlc_finalize_kernel"));
+  prof_bytes(5.0 * sizeof(float) * (double)L.BCS);       // x, z1 z3 z5 in, o out
   VX_LAUNCH(jlc_combine_kernel, dim3(L.nchunk, rows), dim3(256), 0, st, x, (const float*)z, (const float*)stats, o,
             part_o, rows, S, L.chunk);
   VX_TRY(check_launch("jlc_combine_kernel"));
@@ -831,11 +833,14 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
     b2.dW = dfw1; b2.ld = C; b2.db = dfb1;
     VX_TRY(pw_wgrad(wb, st));
   }
+  prof_bytes(2.0 * sizeof(float) * (double)L.BCS);
   VX_LAUNCH(jlc_bwd_a_kernel, dim3(L.nchunk, rows), dim3(256), 0, st, (const float*)dohat, o, stats_o, acc, S, L.chunk);
   VX_TRY(check_launch("jlc_bwd_a_kernel"));
+  prof_bytes(7.0 * sizeof(float) * (double)L.BCS);       // dy, dohat, o, z(3) in, dO out
   VX_LAUNCH(jlc_bwd_b_kernel, dim3(L.nchunk, rows), dim3(256), 0, st, dy, (const float*)dohat, o, z, stats,
             (const float*)acc, dO, acc2, rows, S, L.chunk);
   VX_TRY(check_launch("jlc_bwd_b_kernel"));
+  prof_bytes(7.0 * sizeof(float) * (double)L.BCS);       // dO, z(3) in, gz(3) out
   VX_LAUNCH(jlc_bwd_c_kernel, dim3(cdiv(S, 1024), rows), dim3(256), 0, st, (const float*)dO, z, stats,
             (const float*)acc2, gz, rows, S);
   VX_TRY(check_launch("jlc_bwd_c_kernel"));
@@ -843,6 +848,7 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
   ConvDgradArgs G{};
   G.gz = gz; G.dO = dO; G.w1 = w1; G.w3 = w3; G.w5 = w5; G.dx = dx;
   G.B = d->B; G.C = C; G.D = d->D; G.H = d->H; G.W = d->W; G.t = L.tf;
+  prof_bytes(5.0 * sizeof(float) * (double)L.BCS);       // gz(3), dO in, dx out
   if (CG == 4) VX_TRY(launch_conv_dgrad<4>(G, d->groups, st));
   else if (CG == 8) VX_TRY(launch_conv_dgrad<8>(G, d->groups, st));
   else VX_TRY(launch_conv_dgrad<16>(G, d->groups, st));
@@ -850,6 +856,7 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
   ConvWgradArgs Wg{};
   Wg.x = x; Wg.gz = gz; Wg.dw1 = dw1; Wg.db1 = db1; Wg.dw3 = dw3; Wg.db3 = db3; Wg.dw5 = dw5; Wg.db5 = db5;
   Wg.B = d->B; Wg.C = C; Wg.D = d->D; Wg.H = d->H; Wg.W = d->W; Wg.t = L.tw;
+  prof_bytes(4.0 * sizeof(float) * (double)L.BCS);       // x, gz(3) in (weight gradients are KBs)
   if (CG == 4) VX_TRY(launch_conv_wgrad<4>(Wg, d->groups, st));
   else if (CG == 8) VX_TRY(launch_conv_wgrad<8>(Wg, d->groups, st));
   else VX_TRY(launch_conv_wgrad<16>(Wg, d->groups, st));

@@ -18,37 +18,13 @@ constexpr int PW_TS = 64;    // voxels per CTA tile
 constexpr int PW_TC = 64;    // output channels per CTA tile
 constexpr int PW_KC = 16;    // input channels per staged chunk
 
-// Address of one input element of the (possibly multi-source) X operand.
-VX_DEV const float* pw_x_ptr(const PwProblem& P, int b, int cg, int v, int S) {
-  int c = cg, s = 0;
-  while (s < P.nsrc - 1 && c >= P.src[s].C) { c -= P.src[s].C; ++s; }
-  return P.src[s].ptr + ((size_t)b * P.src[s].C + c) * S + v;
-}
-VX_DEV const float* pw_w_ptr(const PwProblem& P, int co, int ci) {
-  int off = 0;
-  if (!P.transposed) {
-    for (int s = 0; s < P.nseg; ++s) {
-      if (co < off + P.seg[s].n) return P.seg[s].W + (size_t)(co - off) * P.seg[s].ld + ci;
-      off += P.seg[s].n;
-    }
-  } else {
-    for (int s = 0; s < P.nseg; ++s) {
-      if (ci < off + P.seg[s].n) return P.seg[s].W + (size_t)(ci - off) * P.seg[s].ld + co;
-      off += P.seg[s].n;
-    }
-  }
-  return P.seg[0].W;
-}
 VX_DEV float pw_prologue(const PwProblem& P, float x, int b, int cg, int v, int S, float pinv, uint64_t soff) {
   if (P.pro == PRO_AFFINE) {
     const int k = b * P.pro_bstride + cg;
-    x = fmaf(x, __ldg(P.pro_a + k), __ldg(P.pro_c + k));
-  } else if (P.pro == PRO_GELU || P.pro == PRO_GELU_DROPOUT) {
-    x = gelu_f(x);
+    return fmaf(x, __ldg(P.pro_a + k), __ldg(P.pro_c + k));
   }
-  if (P.pro == PRO_DROPOUT || P.pro == PRO_GELU_DROPOUT)
-    x *= dropout_scale(P.pro_seed + soff, P.pro_site, ((uint64_t)b * P.Ci + cg) * (uint64_t)S + v, P.pro_drop_p, pinv);
-  return x;
+  if (P.pro == PRO_NONE) return x;
+  return pw_pro_heavy(P.pro, x, P.pro_seed + soff, P.pro_site, ((uint64_t)b * P.Ci + cg) * (uint64_t)S + v, P.pro_drop_p, pinv);
 }
 
 // Y[b, co, v] = epi( sum_ci W[co, ci] * pro(X[b, ci, v]) + bias[co] ) as a register-tiled GEMM: CTA tile = 64 voxels x
@@ -196,8 +172,170 @@ __global__ void __launch_bounds__(PW_THREADS) pw_kernel(const __grid_constant__ 
   }
 }
 
+// Small-voxel variant (levels 3-4: S = 216 / 27).  pw_kernel's 64 x 64 CTA tile leaves 8-32 CTAs with one warp per
+// scheduler walking a serial K loop -- pure instruction latency (85 us for 3.5 MFLOP at level 4).  Here the batch and
+// voxel axes are flattened (f = b * S + v) and a warp owns 32 flattened voxels x 4 output channels with the whole K loop
+// in registers: 4x-16x more warps, no shared memory, no barriers.  X reads are coalesced along the voxel axis, weight
+// reads are warp-uniform 16-byte loads (the four rows co..co+3, four k at a time) served by L1.
+//
+// The K axis is additionally split over the KS = blockDim.y warps of a CTA (8-channel steps dealt round-robin), so that
+// a level-4 problem (K = 256..512) is 8 short latency chains instead of one long one; partial sums meet in shared memory.
+constexpr int PWS_MAX_KS = 8;
+
+__global__ void __launch_bounds__(32 * PWS_MAX_KS) pw_small_kernel(const __grid_constant__ PwBatch batch) {
+  const PwProblem& P = batch.p[blockIdx.z];
+  const int S = batch.S, Co = P.Co;
+  const int lane = threadIdx.x, ks = threadIdx.y, KS = blockDim.y;
+  const int f = blockIdx.x * 32 + lane;
+  const int co0 = blockIdx.y * 4;
+  __shared__ float part[PWS_MAX_KS][4][32];
+  if (co0 >= Co) return;
+  const bool ok = f < batch.B * S;
+  const int b = ok ? f / S : 0, v = ok ? f % S : 0;
+  const bool pro_drop = P.pro == PRO_DROPOUT || P.pro == PRO_GELU_DROPOUT;
+  const float pinv = pro_drop ? 1.0f / (1.0f - P.pro_drop_p) : 1.f;
+  const uint64_t soff = batch.seed_dev ? (uint64_t)__ldg(batch.seed_dev) : 0;
+  const bool quad = co0 + 3 < Co;
+
+  // forward orientation: the four weight rows of this warp (a row never crosses an output segment)
+  const float* rp[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool rows_vec = quad && !P.transposed;
+  if (!P.transposed) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int ld;
+      rp[j] = pw_w_row(P, quad ? co0 + j : co0, 0, ld);
+      rows_vec = rows_vec && (((uintptr_t)rp[j] & 15) == 0) && ((ld & 3) == 0);
+    }
+  }
+
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int cg = 0;                                             // channel index in the concatenated input
+  int step = 0;                                           // work-item counter for the round-robin K split
+#pragma unroll 1
+  for (int s = 0; s < P.nsrc; ++s) {
+    const int Cs = P.src[s].C;
+    const float* xp = P.src[s].ptr + (size_t)b * Cs * S + v;
+    int c = 0;
+    // 8 input channels per step: every load of the step is issued before the first FMA (the kernel is latency-bound:
+    // one or two warps per scheduler), 8 coalesced X loads + 8 warp-uniform 16-byte weight loads in flight
+#pragma unroll 1
+    for (; c + 8 <= Cs; c += 8, cg += 8) {
+      const float* w0 = nullptr;
+      int ld = 0;
+      bool vec;
+      if (!P.transposed) {
+        vec = rows_vec && (cg & 3) == 0;
+      } else {
+        int ld7;
+        w0 = pw_w_row(P, co0, cg, ld);
+        vec = quad && (((uintptr_t)w0 & 15) == 0) && ((ld & 3) == 0) && pw_w_row(P, co0, cg + 7, ld7) == w0 + (size_t)7 * ld;
+      }
+      if (!vec) break;                                   // odd shapes: the scalar loop below finishes this source
+      if ((step++) % KS != ks) continue;
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = ok ? __ldg(xp + (size_t)(c + i) * S) : 0.f;
+      float4 w[8];
+      if (!P.transposed) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {      // w[2j], w[2j+1] = row j, k 0..3 and 4..7
+          w[2 * j] = __ldg(reinterpret_cast<const float4*>(rp[j] + cg));
+          w[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(rp[j] + cg + 4));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(w0 + (size_t)i * ld));   // row k = i
+      }
+      if (P.pro == PRO_AFFINE) {
+        const int q = b * P.pro_bstride + cg;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], __ldg(P.pro_a + q + i), __ldg(P.pro_c + q + i));
+      } else if (P.pro != PRO_NONE) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          x[i] = pw_pro_heavy(P.pro, x[i], P.pro_seed + soff, P.pro_site, ((uint64_t)b * P.Ci + cg + i) * (uint64_t)S + v,
+                              P.pro_drop_p, pinv);
+      }
+      if (!P.transposed) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 a = w[2 * j], q = w[2 * j + 1];
+          acc[j] = fmaf(a.x, x[0], acc[j]); acc[j] = fmaf(a.y, x[1], acc[j]); acc[j] = fmaf(a.z, x[2], acc[j]);
+          acc[j] = fmaf(a.w, x[3], acc[j]); acc[j] = fmaf(q.x, x[4], acc[j]); acc[j] = fmaf(q.y, x[5], acc[j]);
+          acc[j] = fmaf(q.z, x[6], acc[j]); acc[j] = fmaf(q.w, x[7], acc[j]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[0] = fmaf(w[i].x, x[i], acc[0]); acc[1] = fmaf(w[i].y, x[i], acc[1]);
+          acc[2] = fmaf(w[i].z, x[i], acc[2]); acc[3] = fmaf(w[i].w, x[i], acc[3]);
+        }
+      }
+    }
+#pragma unroll 1
+    for (; c < Cs; ++c, ++cg) {
+      if ((step++) % KS != ks) continue;
+      float x = ok ? __ldg(xp + (size_t)c * S) : 0.f;
+      if (P.pro != PRO_NONE) x = pw_prologue(P, x, b, cg, v, S, pinv, soff);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (co0 + j < Co) acc[j] = fmaf(__ldg(pw_w_ptr(P, co0 + j, cg)), x, acc[j]);
+    }
+  }
+  if (KS > 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) part[ks][j][lane] = acc[j];
+    __syncthreads();
+    if (ks != 0) return;
+#pragma unroll 1
+    for (int k2 = 1; k2 < KS; ++k2)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] += part[k2][j][lane];
+  }
+  if (!ok) return;
+  // epilogue: gather every input first, then compute, then store
+  const float dinv = P.drop_p > 0.f ? 1.0f / (1.0f - P.drop_p) : 1.f;
+  const bool heavy = P.act == 1 || P.mulgrad || P.drop_p > 0.f;
+  float* outp[4];
+  size_t li[4];
+  float bias[4], mg[4], r1[4], r2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int co = co0 + j < Co ? co0 + j : co0;
+    bias[j] = 0.f;
+    if (!P.transposed) {
+      int seg = 0, seg_off = 0;
+      while (co >= seg_off + P.seg[seg].n) { seg_off += P.seg[seg].n; ++seg; }
+      outp[j] = P.seg[seg].out + ((size_t)b * P.seg[seg].n + (co - seg_off)) * S + v;
+      if (P.seg[seg].bias) bias[j] = __ldg(P.seg[seg].bias + co - seg_off);
+    } else {
+      outp[j] = P.seg[0].out + ((size_t)b * Co + co) * S + v;
+    }
+    li[j] = ((size_t)b * Co + co) * S + v;
+    mg[j] = P.mulgrad ? __ldg(P.mulgrad + li[j]) : 0.f;
+    r1[j] = P.res ? __ldg(P.res + li[j]) : 0.f;
+    r2[j] = P.res2 ? __ldg(P.res2 + li[j]) : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (co0 + j >= Co) break;
+    float y = acc[j] + bias[j];
+    if (heavy) y = pw_epi_heavy(y, P.act, P.mulgrad != nullptr, mg[j], P.drop_p, P.seed + soff, P.site, li[j], dinv);
+    if (P.res) y = fmaf(P.res_scale, r1[j], y);
+    if (P.res2) y += r2[j];
+    *outp[j] = y;
+  }
+}
+
+static int g_small_max_s = 512, g_tc_min_s = 4096;
+void pw_set_thresholds(int small_max_s, int tc_min_s) {
+  if (small_max_s >= 0) g_small_max_s = small_max_s;
+  if (tc_min_s >= 0) g_tc_min_s = tc_min_s;
+}
+
 int pw_forward(const PwBatch& batch, cudaStream_t stream) {
   int maxCo = 0;
+  double bytes = 0.0;
   for (int i = 0; i < batch.nprob; ++i) {
     const PwProblem& P = batch.p[i];
     maxCo = P.Co > maxCo ? P.Co : maxCo;
@@ -207,11 +345,31 @@ int pw_forward(const PwBatch& batch, cudaStream_t stream) {
     if (!P.transposed && P.nseg > 1 && (P.res || P.mulgrad || P.drop_p > 0.f || P.res2)) {
       set_error("pw_forward: epilogue tensors need a single output segment"); return VX_ERR_BAD_DESC;
     }
+    // algorithmic bytes: X in, Y out, epilogue tensors in, weights
+    bytes += 4.0 * batch.B * batch.S * (P.Ci + P.Co * (1.0 + (P.res ? 1 : 0) + (P.res2 ? 1 : 0) + (P.mulgrad ? 1 : 0))) +
+             4.0 * P.Ci * P.Co;
   }
   if (batch.nprob <= 0 || batch.B <= 0 || batch.S <= 0) return VX_OK;
-  dim3 grid(cdiv(batch.S, PW_TS), cdiv(maxCo, PW_TC), batch.nprob * batch.B);
+#ifndef VX_EMU
+  if (batch.S >= g_tc_min_s && batch.S >= g_small_max_s) {
+    prof_bytes(bytes);
+    const int rc = pw_tc_forward(batch, stream);
+    if (rc <= 0) return rc;
+  }
+#endif
   PwBatch launch = batch;
   launch.seed_dev = get_seed_dev();
+  prof_bytes(bytes);
+  if (batch.S < g_small_max_s) {
+    int maxCi = 0;
+    for (int i = 0; i < batch.nprob; ++i) maxCi = batch.p[i].Ci > maxCi ? batch.p[i].Ci : maxCi;
+    int KS = 1;
+    while (KS < PWS_MAX_KS && maxCi / (8 * KS * 2) >= 2) KS *= 2;      // >= 2 eight-channel steps per warp
+    dim3 grid(cdiv((long long)batch.B * batch.S, 32), cdiv(maxCo, 4), batch.nprob);
+    VX_LAUNCH(pw_small_kernel, grid, dim3(32, KS), 0, stream, launch);
+    return check_launch("pw_small_kernel");
+  }
+  dim3 grid(cdiv(batch.S, PW_TS), cdiv(maxCo, PW_TC), batch.nprob * batch.B);
   VX_LAUNCH(pw_kernel, grid, dim3(PW_THREADS), 0, stream, launch);
   return check_launch("pw_kernel");
 }
@@ -379,6 +537,12 @@ int pw_wgrad(const WgBatch& batch, cudaStream_t stream) {
   dim3 grid(nK, maxblocks, batch.nprob);
   WgBatch launch = batch;
   launch.seed_dev = get_seed_dev();
+  {
+    double bytes = 0.0;
+    for (int i = 0; i < batch.nprob; ++i)
+      bytes += 4.0 * batch.B * batch.S * (batch.p[i].Ci + batch.p[i].Co) + 4.0 * batch.p[i].Ci * batch.p[i].Co;
+    prof_bytes(bytes);
+  }
   VX_LAUNCH(pw_wgrad_kernel, grid, dim3(WG_THREADS), smem, stream, launch, TV, nK);
   return check_launch("pw_wgrad_kernel");
 }
@@ -409,6 +573,7 @@ __global__ void __launch_bounds__(256) inorm_rows_fwd_kernel(const float* __rest
 int inorm_rows_fwd(const float* x, const float* addend, float* y, float* stats, int rows, int S, float eps,
                    cudaStream_t stream) {
   if (rows <= 0) return VX_OK;
+  prof_bytes(4.0 * rows * (double)S * (addend ? 3 : 2));
   VX_LAUNCH(inorm_rows_fwd_kernel, dim3(rows), dim3(256), 0, stream, x, addend, y, stats, S, eps);
   return check_launch("inorm_rows_fwd_kernel");
 }
@@ -439,6 +604,7 @@ __global__ void __launch_bounds__(256) inorm_rows_bwd_kernel(const float* __rest
 int inorm_rows_bwd(const float* dy, const float* x, const float* stats, const float* dx_add, float* dx, int rows,
                    int S, cudaStream_t stream) {
   if (rows <= 0) return VX_OK;
+  prof_bytes(4.0 * rows * (double)S * (dx_add ? 4 : 3));
   VX_LAUNCH(inorm_rows_bwd_kernel, dim3(rows), dim3(256), 0, stream, dy, x, stats, dx_add, dx, S);
   return check_launch("inorm_rows_bwd_kernel");
 }
@@ -476,6 +642,7 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const __grid_constant__ LnB
 
 int ln_forward(const LnBatch& L, cudaStream_t stream) {
   if (L.n <= 0) return VX_OK;
+  prof_bytes(4.0 * L.n * L.B * (double)L.S * (2.0 * L.C + 1));
   VX_LAUNCH(ln_fwd_kernel, dim3(cdiv(L.S, 128), L.B, L.n), dim3(128), 0, stream, L);
   return check_launch("ln_fwd_kernel");
 }
@@ -529,6 +696,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __grid_constant__ LnB
 
 int ln_backward(const LnBwdBatch& L, cudaStream_t stream) {
   if (L.n <= 0) return VX_OK;
+  prof_bytes(4.0 * L.n * L.B * (double)L.S * (3.0 * L.C + 1 + (L.dx_add[0] ? L.C : 0)));
   VX_LAUNCH(ln_bwd_kernel, dim3(cdiv(L.S, 32), L.B, L.n), dim3(256), 0, stream, L);
   return check_launch("ln_bwd_kernel");
 }

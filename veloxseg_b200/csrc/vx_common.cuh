@@ -60,6 +60,7 @@ void count_launch();
 int prof_begin(const char* kernel, cudaStream_t st);   // -1 when profiling is off
 void prof_end(int slot, cudaStream_t st);
 #endif
+void prof_bytes(double bytes);                         // algorithmic bytes of the NEXT launch (profiler only)
 void prof_scope(const char* fmt, ...);                 // names the op whose kernels follow (thread-local)
 int check_launch(const char* what);   // cudaGetLastError -> vx_status
 

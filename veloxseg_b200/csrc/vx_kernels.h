@@ -34,6 +34,74 @@ struct PwBatch { PwProblem p[VX_MAX_MODAL]; int nprob; int B; int S; const unsig
 
 int pw_forward(const PwBatch& batch, cudaStream_t stream);
 
+#if defined(__CUDACC__) || defined(VX_EMU)
+// Address of one input element of the (possibly multi-source) X operand.
+VX_DEV const float* pw_x_ptr(const PwProblem& P, int b, int cg, int v, int S) {
+  int c = cg, s = 0;
+  while (s < P.nsrc - 1 && c >= P.src[s].C) { c -= P.src[s].C; ++s; }
+  return P.src[s].ptr + ((size_t)b * P.src[s].C + c) * S + v;
+}
+VX_DEV const float* pw_w_ptr(const PwProblem& P, int co, int ci) {
+  int off = 0;
+  if (!P.transposed) {
+    for (int s = 0; s < P.nseg; ++s) {
+      if (co < off + P.seg[s].n) return P.seg[s].W + (size_t)(co - off) * P.seg[s].ld + ci;
+      off += P.seg[s].n;
+    }
+  } else {
+    for (int s = 0; s < P.nseg; ++s) {
+      if (ci < off + P.seg[s].n) return P.seg[s].W + (size_t)(ci - off) * P.seg[s].ld + co;
+      off += P.seg[s].n;
+    }
+  }
+  return P.seg[0].W;
+}
+#endif
+
+#if defined(__CUDACC__) || defined(VX_EMU)
+// Out-of-line pieces of the contraction prologue / epilogue.  GELU (erff), GELU' (erff + expf) and the Philox dropout mask
+// are tens to hundreds of instructions each; inlined at every unrolled use they push a kernel far beyond the instruction
+// caches and it becomes fetch-bound (measured: pw_tc_kernel at 94 KB of SASS stalled 3-5 warps per issue on
+// `no_instruction`).  One shared copy per kernel instead.
+static __device__ VX_NOINLINE float pw_pro_heavy(int pro, float x, uint64_t seed, uint32_t site, uint64_t idx, float p, float pinv) {
+  if (pro == PRO_GELU || pro == PRO_GELU_DROPOUT) x = gelu_f(x);
+  if (pro == PRO_DROPOUT || pro == PRO_GELU_DROPOUT) x *= dropout_scale(seed, site, idx, p, pinv);
+  return x;
+}
+static __device__ VX_NOINLINE float pw_epi_heavy(float y, int act, bool has_mg, float mg, float drop_p, uint64_t seed, uint32_t site,
+                                                 uint64_t idx, float dinv) {
+  if (act == 1) y = gelu_f(y);
+  if (has_mg) y *= gelu_grad_f(mg);
+  if (drop_p > 0.f) y *= dropout_scale(seed, site, idx, drop_p, dinv);
+  return y;
+}
+// Row of the weight operand that multiplies input channel ci for output channels co.. (transposed orientation) or the row
+// of output channel co starting at input channel ci (forward orientation), with the row stride of its segment.
+VX_DEV const float* pw_w_row(const PwProblem& P, int co, int ci, int& ld) {
+  int off = 0;
+  if (!P.transposed) {
+    for (int s = 0; s < P.nseg; ++s) {
+      if (co < off + P.seg[s].n) { ld = P.seg[s].ld; return P.seg[s].W + (size_t)(co - off) * P.seg[s].ld + ci; }
+      off += P.seg[s].n;
+    }
+  } else {
+    for (int s = 0; s < P.nseg; ++s) {
+      if (ci < off + P.seg[s].n) { ld = P.seg[s].ld; return P.seg[s].W + (size_t)(ci - off) * P.seg[s].ld + co; }
+      off += P.seg[s].n;
+    }
+  }
+  ld = P.seg[0].ld;
+  return P.seg[0].W;
+}
+#endif
+
+// Tensor-core (tcgen05, 3xTF32) variant of pw_forward for the large-voxel problems: returns 0 when launched, 1 when the
+// batch does not qualify (the caller then uses the SIMT kernels), negative on error.  pw_tc.cu.
+int pw_tc_forward(const PwBatch& batch, cudaStream_t stream);
+void pw_tc_set(int enabled);
+void pw_set_thresholds(int small_max_s, int tc_min_s);   // tuning probes; -1 keeps a value
+
+
 // dW[co, ci] += sum_{b,s} ypro(dY[b,co,s]) * xpro(X[b,ci,s]);   db[co] += sum ypro(dY)
 struct WgProblem {
   const float* dY; int Co;
