@@ -86,10 +86,17 @@ class TrainStep:
     """`step(inputs, labels)` = one optimisation step; accepts host (pinned) or device tensors and returns the loss
     as a Python float only when asked (`sync=True`), mirroring the reference's per-step `loss.item()`.
 
-    On a single CUDA device the whole step (forward, loss, backward, AdamW) is captured once into a CUDA graph and
-    replayed: ~1 200 kernel launches per step collapse into one graph launch, which matters because the fused step is
-    short enough for host launch overhead to dominate.  Dropout stays random across replays because the kernels add a
-    device-resident offset (ops.advance_seed, captured in the graph) to their seeds."""
+    On CUDA the step is captured once into CUDA graphs and replayed: ~1 200 kernel launches per step collapse into one
+    or two graph launches, which matters because the fused step is short enough for host launch overhead to dominate
+    (eager enqueue of one step takes about twice as long as the GPU needs to run it).  Dropout stays random across replays
+    because the kernels add a device-resident offset (ops.advance_seed, captured in the graph) to their seeds.
+
+      world == 1   one graph: forward, loss, backward, AdamW.
+      world  > 1   graph A: forward, loss, backward, gradients gathered into one flat fp32 buffer (9 MB);
+                   one NCCL all-reduce of that buffer (latency-bound over NVLink: tens of microseconds next to an 18 ms
+                   step, so nothing is gained by splitting it into buckets inside the graph);
+                   graph B: mean, scatter back into `.grad`, AdamW.
+    `use_graph=False` keeps the eager path, where `GradBuckets` overlaps bucketed all-reduces with backward."""
 
     def __init__(self, model: torch.nn.Module, num_modal: int, device, lr: float = 2.5e-4, weight_decay: float = 0.01,
                  deep_weights=(1, 1, 1, 1), rc_weight: float = 0.5, feature_weight: float = 2.0,
@@ -97,24 +104,52 @@ class TrainStep:
         self.device = torch.device(device)
         self.model = model.to(self.device).train()
         self.loss_fn = Loss(num_modal, deep_weights, rc_weight, feature_weight)
-        self.buckets = GradBuckets(list(self.model.parameters()), bucket_bytes)
         cuda = self.device.type == "cuda"
-        self.use_graph = (cuda and self.buckets.world == 1) if use_graph is None else bool(use_graph)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.use_graph = cuda if use_graph is None else bool(use_graph)
+        self.params = [p for p in self.model.parameters() if p.requires_grad]
+        # eager data-parallel path only: gradients accumulate straight into flat buckets, all-reduce from grad hooks
+        self.buckets = GradBuckets(self.params, bucket_bytes) if not self.use_graph else None
         self.opt = torch.optim.AdamW(self.model.parameters(), lr=lr, weight_decay=weight_decay, fused=cuda,
                                      capturable=cuda and self.use_graph)
         self._graph = None
+        self._graph_b = None
         self.graph_launches = 0        # kernels of libveloxseg_sm100 recorded in the captured step
 
-    def _step_eager(self, x, y):
+    # ---- pieces shared by the eager and the captured paths
+    def _fwd_bwd(self, x, y):
         from . import ops
-        self.buckets.zero()
         ops.advance_seed(self.device)
         out = self.model(x)
         loss = self.loss_fn(out, y, x)
         loss.backward()
-        self.buckets.finish()
-        self.opt.step()
         return loss.detach()
+
+    def _gather_grads(self):
+        self._gparams = [p for p in self.params if p.grad is not None]
+        grads = [p.grad for p in self._gparams]
+        return grads, torch.cat([g.reshape(-1) for g in grads])
+
+    def _scatter_mean(self, grads, flat):
+        flat.div_(self.world)
+        torch._foreach_copy_(grads, [f.view_as(g) for f, g in zip(flat.split([g.numel() for g in grads]), grads)])
+
+    def _step_eager(self, x, y):
+        """One full step without graphs (also the warm-up before capture and the profiler's per-kernel pass)."""
+        if self.buckets is not None:
+            self.buckets.zero()
+            loss = self._fwd_bwd(x, y)
+            self.buckets.finish()
+        else:
+            for p in self.params:
+                p.grad = None
+            loss = self._fwd_bwd(x, y)
+            if self.world > 1:
+                grads, flat = self._gather_grads()
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                self._scatter_mean(grads, flat)
+        self.opt.step()
+        return loss
 
     def _capture(self, inputs, labels):
         from . import _lib
@@ -134,8 +169,19 @@ class TrainStep:
         lib = _lib.get_lib()
         n0 = lib.c.vx_launch_count()
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._sloss = self._step_eager(self._sx, self._sy)
+        if self.world == 1:
+            with torch.cuda.graph(self._graph):
+                self._sloss = self._step_eager(self._sx, self._sy)
+        else:
+            for p in self.params:
+                p.grad = None
+            with torch.cuda.graph(self._graph):
+                self._sloss = self._fwd_bwd(self._sx, self._sy)
+                self._grads, self._flat = self._gather_grads()
+            self._graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_b, pool=self._graph.pool()):
+                self._scatter_mean(self._grads, self._flat)
+                self.opt.step()
         self.graph_launches = int(lib.c.vx_launch_count() - n0)
         with torch.no_grad():
             for p, q in zip(self.model.parameters(), snap_p):
@@ -153,6 +199,9 @@ class TrainStep:
             self._sx.copy_(inputs, non_blocking=True)
             self._sy.copy_(labels, non_blocking=True)
             self._graph.replay()
+            if self._graph_b is not None:
+                dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+                self._graph_b.replay()
             loss = self._sloss
         else:
             loss = self._step_eager(inputs.to(self.device, non_blocking=True), labels.to(self.device, non_blocking=True))
