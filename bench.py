@@ -209,6 +209,11 @@ def run_ours(args, rank, world, local_rank):
                     "own_kernels_share_of_step": round(ours_ms / step_ms_prof, 4),
                     "note": "event-timed launch by launch inside an eager step (launch gaps inflate step_ms; shares are "
                             "against that eager step); working sets are L2-resident at 4 patches, see DESIGN.md section 3"}
+    # ---- second headline metric: sliding-window inference (all ranks take part)
+    used_graph = ts.use_graph
+    del ts, model
+    torch.cuda.empty_cache()
+    infer = None if args.no_infer else run_infer(rank, world, dev)
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -222,7 +227,7 @@ def run_ours(args, rank, world, local_rank):
                                "of 2x96^3 per GPU, CE+Dice x4 deep, 0.5 MSE recon, 2.0 SDKT, AdamW",
                    "patches_per_gpu": PATCHES, "global_patches": PATCHES * world, "parallelism": f"dp{world}",
                    "cache": "L2 flushed (256 MiB memset) between timed steps",
-                   "launch": ("eager launches" if not ts.use_graph else "whole step replayed as one CUDA graph" if world == 1 else
+                   "launch": ("eager launches" if not used_graph else "whole step replayed as one CUDA graph" if world == 1 else
                               "CUDA graph (fwd+bwd) -> one NCCL all-reduce of the flat 9 MB gradient -> CUDA graph (AdamW)"),
                    "pointwise": "tcgen05 3xTF32 (fp32-accurate) for S>=512, fp32 SIMT below" if pw_tc else "fp32 SIMT"},
         "e2e": {"value": round(total_patches / e2e_s, 3), "unit": "patches/s",
@@ -230,9 +235,48 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "host_enqueue_ms_per_step": round(enqueue_ms, 2), "clocks": clk.summary(), "roofline": roof, "loss": last_loss, "top_kernels": table,
     }
+    if infer is not None:
+        line["infer"] = infer
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_port(steps=1, patches=1, threads=None)
     print(json.dumps(line), flush=True)
+
+
+def run_infer(rank, world, dev, reps=3):
+    """BASELINE.json configs[3]: Hecktor2022 sliding-window inference on one synthetic PET/CT volume (1,2,320,320,256),
+    roi (128,128,64), overlap 0.25 -> 45 windows, sharded round-robin over ranks, partial sums all-reduced."""
+    from veloxseg_b200.configs import MODEL_CONFIGS, TRAIN
+    from veloxseg_b200.inference import GraphedPredictor, sliding_window_predict, window_starts
+    from veloxseg_b200.nn import VeloxSeg
+    cfg = MODEL_CONFIGS["hecktor2022"]
+    torch.manual_seed(12345)
+    model = VeloxSeg(**cfg).to(dev).eval()
+    vol_shape = (1, sum(cfg["in_ch"]), 320, 320, 256)
+    vol_h = torch.randn(vol_shape, generator=torch.Generator().manual_seed(5)).pin_memory()
+    roi, sw = cfg["input_size"], 4
+    pred = GraphedPredictor(model, sw, vol_shape[1], roi, dev)
+    nwin = len(window_starts(vol_shape[2:], roi, TRAIN["sw_overlap"]))
+    times = []
+    for i in range(reps + 1):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        vol = vol_h.to(dev, non_blocking=True)                      # host volume in, host label map out
+        out = sliding_window_predict(vol, pred, roi, sw_batch_size=sw, overlap=TRAIN["sw_overlap"])
+        seg = out.argmax(1).to(torch.uint8).cpu()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i:
+            times.append(dt)
+    t = torch.tensor([min(times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"metric": "sliding-window infer ms/volume", "value": round(float(t.item()) * 1e3, 2), "unit": "ms/volume",
+            "higher_is_better": False, "scaling": "strong", "n_gpus": world,
+            "config": {"workload": "VeloxSeg Hecktor2022 eval, volume 2x320x320x256, roi 128x128x64, overlap 0.25",
+                       "windows": nwin, "sw_batch": sw, "timed": "H2D volume + windows + all-reduce + argmax + D2H labels, best of %d" % reps,
+                       "fg_voxels": int(seg.sum())}}
 
 
 def cpu_port(steps, patches, threads):
@@ -291,6 +335,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-infer", action="store_true", help="skip the sliding-window inference measurement")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
