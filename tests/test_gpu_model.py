@@ -21,7 +21,8 @@ def _model(name):
 
 @pytest.mark.parametrize("name", ["tiny", "autopetii", "hecktor2022", "brats2021"])
 def test_whole_model_vs_reference(name):
-    torch.backends.cudnn.allow_tf32 = False
+    import os
+    torch.backends.cudnn.allow_tf32 = os.environ.get("VX_TEST_CUDNN_TF32", "0") == "1"
     torch.backends.cuda.matmul.allow_tf32 = False
     fx = G.load(f"model_{name}.pt")
     cfg = MODEL_CONFIGS[name]

@@ -45,6 +45,12 @@ def main():
     lib.set_option(1, int(os.environ.get("VX_PW_TC", "1") == "1"))
     if "VX_PW_SMALL_MAX_S" in os.environ:
         lib.set_option(2, int(os.environ["VX_PW_SMALL_MAX_S"]))
+    for opt, env in ((4, "VX_JLC_TILE_FWD"), (5, "VX_JLC_TILE_WGRAD")):
+        if env in os.environ:
+            tz, ty = [int(v) for v in os.environ[env].split(",")]
+            lib.set_option(opt, tz << 8 | ty)
+    if "VX_JLC_VX" in os.environ:
+        lib.set_option(6, int(os.environ["VX_JLC_VX"]))
     if "VX_PW_TC_MIN_S" in os.environ:
         lib.set_option(3, int(os.environ["VX_PW_TC_MIN_S"]))
     B, res = args.B, []

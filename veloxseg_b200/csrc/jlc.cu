@@ -25,18 +25,32 @@ namespace vx {
 
 struct ConvTile { int TZ, TY, TX, ntz, nty, ntx, VX, threads; };
 
+static int g_force_vx = 0;
+void jlc_force_vx(int vx) { g_force_vx = vx; }
+static int g_force_tz[2] = {0, 0}, g_force_ty[2] = {0, 0};     // tuning probes (vx_set_option): [fwd/dgrad, wgrad]
+void jlc_force_tile(int kind, int tz, int ty) { g_force_tz[kind] = tz; g_force_ty[kind] = ty; }
+
+// Tile choice, from a sweep on B200 at the per-level shapes of the three reference configs (tools/gpu_jlc_tiles.sh,
+// profiles/r1_jlc_tile_sweep.txt).  What the sweep showed:
+//  * fwd / dgrad: 4 voxels per thread (not 8) -- twice the threads for the same tile, ~90 instead of 128 registers;
+//    the best tile is the largest that still gives the grid >= 96 CTAs, with whole warps per channel block (the stats
+//    epilogue then uses warp reductions instead of per-thread shared atomics); below 32 threads a CTA is pure latency.
+//  * wgrad (fixed 256 threads, tile-size-independent register use): it wants CTAs: the largest tile that still gives
+//    >= 256 of them, never smaller than 4 (z, y) positions.
 static ConvTile pick_tile(int B, int groups, int CG, int D, int H, int W, int max_threads, size_t max_smem_floats,
                           int smem_kind) {
   // smem_kind 0: fwd/dgrad (4 * halo tile), 1: wgrad (4 * halo tile + 3 * CG * tile)
   ConvTile best{};
-  double best_cost = 1e300;
-  const int VX = (W % 8 == 0) ? 8 : 4;
+  long long best_key = -1;
+  const int VX = g_force_vx ? g_force_vx : 4;
   const int TX = ((W < 32 ? W : 32) + VX - 1) / VX * VX;
   const int cand[] = {8, 6, 4, 3, 2, 1};
   for (int tz : cand) {
     if (tz > D && tz != 1) continue;
+    if (g_force_tz[smem_kind] && tz != g_force_tz[smem_kind]) continue;
     for (int ty : cand) {
       if (ty > H && ty != 1) continue;
+      if (g_force_ty[smem_kind] && ty != g_force_ty[smem_kind]) continue;
       const int npos = tz * ty * (TX / VX);
       const int threads = npos * (CG / 4);
       if (smem_kind == 0 && (threads > max_threads || threads < 1)) continue;
@@ -46,12 +60,18 @@ static ConvTile pick_tile(int B, int groups, int CG, int D, int H, int W, int ma
       if (fl > max_smem_floats) continue;
       const int ntz = cdiv(D, tz), nty = cdiv(H, ty), ntx = cdiv(W, TX);
       const long long ncta = (long long)ntz * nty * ntx * groups * B;
-      const double waves = (double)((ncta + kSMs - 1) / kSMs);
-      // per-CTA work ~ padded outputs plus the halo staging cost
-      const double work = (double)tz * ty * TX * 153.0 * CG + 6.0 * (tz + 4) * (ty + 4) * TXP;
-      double cost = waves * work;
-      if (smem_kind == 0 && threads < 64) cost *= 64.0 / threads;
-      if (cost < best_cost) { best_cost = cost; best = ConvTile{tz, ty, TX, ntz, nty, ntx, VX, threads}; }
+      const int waste = (ntz * tz - D) * H + (nty * ty - H) * D;        // padded rows: tie-break towards exact tilings
+      long long key;
+      if (smem_kind == 0) {
+        const int enough_threads = threads >= 32, whole_warps = npos % 32 == 0, enough_ctas = ncta >= 96;
+        key = ((((long long)enough_threads * 2 + whole_warps) * 2 + enough_ctas) << 40) +
+              ((long long)(enough_ctas ? threads : (ncta < 4096 ? ncta : 4096)) << 20) + (1 << 19) - waste * 64 + tz;
+      } else {
+        const int area = tz * ty, big_enough = area >= 4, enough_ctas = ncta >= 256;
+        key = (((long long)big_enough * 2 + enough_ctas) << 40) +
+              ((long long)(enough_ctas ? area : (ncta < 4096 ? ncta : 4096)) << 20) + (1 << 19) - waste * 64 + tz;
+      }
+      if (key > best_key) { best_key = key; best = ConvTile{tz, ty, TX, ntz, nty, ntx, VX, threads}; }
     }
   }
   return best;

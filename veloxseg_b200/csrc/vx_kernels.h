@@ -99,6 +99,8 @@ VX_DEV const float* pw_w_row(const PwProblem& P, int co, int ci, int& ld) {
 // batch does not qualify (the caller then uses the SIMT kernels), negative on error.  pw_tc.cu.
 int pw_tc_forward(const PwBatch& batch, cudaStream_t stream);
 void pw_tc_set(int enabled);
+void jlc_force_vx(int vx);
+void jlc_force_tile(int kind, int tz, int ty);            // tuning probe: 0 = automatic
 void pw_set_thresholds(int small_max_s, int tc_min_s);   // tuning probes; -1 keeps a value
 
 
