@@ -101,7 +101,11 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    torch.backends.cudnn.allow_tf32 = os.environ.get("VX_CUDNN_TF32", "0") == "1"     # A/B probe only; default fp32
+    # Library (cuDNN) convolutions OUTSIDE the section-8 path (out_conv1, Down/Up convs, patch-embed): tf32 tensor cores by
+    # default -- BASELINE.json names bf16 for this config, tf32 is above that, and the whole-model parity tests pass at
+    # the 1e-3 bar in this mode for the three reference configs.  Every libveloxseg kernel computes in fp32 (the
+    # tcgen05 contraction is 3xTF32 = fp32-accurate) in both modes.  --library-convs fp32 gives the all-fp32 number.
+    torch.backends.cudnn.allow_tf32 = args.library_convs == "tf32"
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = os.environ.get("VX_CUDNN_BENCHMARK", "1") == "1"
     cfg = MODEL_CONFIGS[CFG_NAME]
@@ -209,6 +213,30 @@ def run_ours(args, rank, world, local_rank):
                     "own_kernels_share_of_step": round(ours_ms / step_ms_prof, 4),
                     "note": "event-timed launch by launch inside an eager step (launch gaps inflate step_ms; shares are "
                             "against that eager step); working sets are L2-resident at 4 patches, see DESIGN.md section 3"}
+    # ---- the same device-resident measurement with the library convolutions in fp32 as well (reported beside the headline)
+    alt_ms = None
+    if args.library_convs == "tf32" and not args.no_alt:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.manual_seed(12345)
+        ts2 = TrainStep(VeloxSeg(**cfg), len(cfg["in_ch"]), dev, lr=TRAIN["lr"], weight_decay=TRAIN["weight_decay"],
+                        deep_weights=TRAIN["deep_Loss_weight"], rc_weight=TRAIN["RC_Loss_weight"],
+                        feature_weight=TRAIN["Feature_Loss_weight"])
+        for _ in range(3):
+            ts2.step(x_d, y_d)
+        barrier()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 5))]
+        for a, b in ev2:
+            flush.zero_()
+            a.record()
+            ts2.step(x_d, y_d)
+            b.record()
+        barrier()
+        t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2) / len(ev2)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        alt_ms = float(t2.item())
+        del ts2
+        torch.backends.cudnn.allow_tf32 = True
     # ---- second headline metric: sliding-window inference (all ranks take part)
     used_graph = ts.use_graph
     del ts, model
@@ -229,12 +257,16 @@ def run_ours(args, rank, world, local_rank):
                    "cache": "L2 flushed (256 MiB memset) between timed steps",
                    "launch": ("eager launches" if not used_graph else "whole step replayed as one CUDA graph" if world == 1 else
                               "CUDA graph (fwd+bwd) -> one NCCL all-reduce of the flat 9 MB gradient -> CUDA graph (AdamW)"),
-                   "pointwise": "tcgen05 3xTF32 (fp32-accurate) for S>=512, fp32 SIMT below" if pw_tc else "fp32 SIMT"},
+                   "pointwise": "tcgen05 3xTF32 (fp32-accurate) for S>=4096, fp32 SIMT below" if pw_tc else "fp32 SIMT",
+                   "library_convs_outside_path": args.library_convs},
         "e2e": {"value": round(total_patches / e2e_s, 3), "unit": "patches/s",
                 "h2d_bytes_per_step": int(x_h.numel() * x_h.element_size() + y_h.numel() * y_h.element_size()),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "host_enqueue_ms_per_step": round(enqueue_ms, 2), "clocks": clk.summary(), "roofline": roof, "loss": last_loss, "top_kernels": table,
     }
+    if alt_ms is not None:
+        line["all_fp32"] = {"ms_per_step": round(alt_ms, 3), "value": round(PATCHES * world / (alt_ms * 1e-3), 3), "unit": "patches/s",
+                            "note": "same step with the cuDNN convolutions outside the hot path in fp32 too"}
     if infer is not None:
         line["infer"] = infer
     if world == 1 and not args.no_cpu_baseline:
@@ -335,7 +367,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the secondary all-fp32 timing")
     ap.add_argument("--no-infer", action="store_true", help="skip the sliding-window inference measurement")
+    ap.add_argument("--library-convs", default="tf32", choices=["tf32", "fp32"],
+                    help="precision of the cuDNN convolutions outside the hot path (out_conv1, Down/Up convs, patch-embed)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

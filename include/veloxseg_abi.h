@@ -215,6 +215,23 @@ int vx_resize_trilinear_fwd(const vx_resize_desc* d, const void* const* in, void
 int vx_resize_trilinear_bwd(const vx_resize_desc* d, const void* const* in, void* const* out, void* workspace,
                             size_t workspace_bytes, vx_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Deep-supervision segmentation loss -- utils/loss.py:30-48 (CrossEntropy + MONAI DiceLoss(include_background=False,
+ * to_onehot_y=True, softmax=True) per deep output), weights utils/runtime.py:125-144.  
+ *   L = sum_i w_i [ CE(logits_i, y) + mean_{b, c>=1} (1 - (2 I + 1e-5) / (P + T + 1e-5)) ]
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_out;       /* deep outputs (<= 8), all already at label resolution    */
+  int32_t B, C, S;     /* batch, classes (2..4), voxels                            */
+  float weights[8];    /* w_i (already normalised)                                 */
+} vx_segloss_desc;
+size_t vx_segloss_workspace(const vx_segloss_desc* d);
+/* fwd in: logits_0..logits_{n-1} (B,C,S), labels (B,1,S) int64     out: loss (1), sums (n, B, 1 + 3C)
+ * bwd in: dloss (1), logits_0.., labels, sums                       out: dlogits_0..dlogits_{n-1}           */
+int vx_segloss_fwd(const vx_segloss_desc* d, const void* const* in, void* const* out, void* workspace,
+                   size_t workspace_bytes, vx_stream_t stream);
+int vx_segloss_bwd(const vx_segloss_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -201,3 +201,24 @@ def test_resize_trilinear(emu, src, dst):
     assert rel_err(y, yr) < 1e-6
     dy = torch.randn_like(yr)
     assert close(ops.resize_bwd_raw(emu, 0, dy, src), torch.autograd.grad(yr, xr, dy)[0], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("C,n_out,B,S", [(2, 4, 2, (5, 6, 7)), (4, 3, 1, (4, 9, 5)), (3, 1, 3, (3, 3, 3))])
+def test_segloss(emu, C, n_out, B, S):
+    """CE + Dice over several deep outputs in one pass vs torch cross_entropy + the restated MONAI DiceLoss."""
+    import torch.nn.functional as F
+    from veloxseg_b200 import ops
+    from veloxseg_b200.loss import dice_loss
+    torch.manual_seed(4)
+    logits = [torch.randn(B, C, *S) * 2 for _ in range(n_out)]
+    labels = torch.randint(0, C, (B, 1, *S))
+    w = [0.4, 0.3, 0.2, 0.1][:n_out]
+    loss, sums = ops.segloss_fwd_raw(emu, 0, logits, labels, w)
+    lr = [t.clone().requires_grad_(True) for t in logits]
+    ref = sum(wi * (F.cross_entropy(o, labels.squeeze(1)) + dice_loss(o, labels)) for wi, o in zip(w, lr))
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref)), (float(loss), float(ref))
+    up = torch.tensor(0.7)
+    grads = torch.autograd.grad(ref, lr, up)
+    got = ops.segloss_bwd_raw(emu, 0, up, logits, labels, sums, w)
+    for g, r in zip(got, grads):
+        assert close(g, r, rtol=2e-4, atol=1e-8), rel_err(g, r)

@@ -19,11 +19,15 @@ def _model(name):
     return m.to(DEV)
 
 
+@pytest.mark.parametrize("library_convs", ["fp32", "tf32"])
 @pytest.mark.parametrize("name", ["tiny", "autopetii", "hecktor2022", "brats2021"])
-def test_whole_model_vs_reference(name):
-    import os
-    torch.backends.cudnn.allow_tf32 = os.environ.get("VX_TEST_CUDNN_TF32", "0") == "1"
+def test_whole_model_vs_reference(name, library_convs):
+    """library_convs = precision of the cuDNN convolutions outside the hot path (out_conv1, Down/Up convs, patch-embed).
+    "tf32" is bench.py's default; the 1e-3 bar holds there too for the three reference configs (the miniature, whose
+    tensors are small enough for single rounding errors to show, is held to 2e-3 in that mode)."""
+    torch.backends.cudnn.allow_tf32 = library_convs == "tf32"
     torch.backends.cuda.matmul.allow_tf32 = False
+    gtol = 2e-3 if (library_convs == "tf32" and name == "tiny") else 1e-3
     fx = G.load(f"model_{name}.pt")
     cfg = MODEL_CONFIGS[name]
     m = _model(name)
@@ -42,9 +46,10 @@ def test_whole_model_vs_reference(name):
     bad = []
     for k, p in m.named_parameters():
         try:
-            G.check_sample(p.grad if p.grad is not None else torch.zeros_like(p), fx["grads"][k], rtol=1e-3, atol=1e-5, what=k)
+            G.check_sample(p.grad if p.grad is not None else torch.zeros_like(p), fx["grads"][k], rtol=gtol, atol=1e-5, what=k)
         except AssertionError as e:
             bad.append(str(e))
+    torch.backends.cudnn.allow_tf32 = False
     assert not bad, bad[:10]
 
 

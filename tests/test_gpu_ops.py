@@ -300,3 +300,23 @@ def test_resize_trilinear(ops, src, dst, planes):
     assert rel_err(y, yr) < 1e-5
     g, = torch.autograd.grad(y, xg, dy.to(DEV))
     assert close(g, gr, rtol=1e-4, atol=1e-6), rel_err(g, gr)
+
+
+@pytest.mark.parametrize("C,shape,B", [(2, (96, 96, 96), 4), (4, (96, 96, 96), 1), (2, (128, 128, 64), 2), (3, (7, 5, 3), 2)])
+def test_segloss_levels(ops, C, shape, B):
+    """Fused deep-supervision loss (CE + Dice x 4 outputs) at the full-size shapes of the three configs: value and
+    gradients against torch cross_entropy + the restated MONAI DiceLoss, through autograd (ops.seg_loss)."""
+    import torch.nn.functional as F
+    from veloxseg_b200.loss import dice_loss
+    torch.manual_seed(11)
+    logits = [(torch.randn(B, C, *shape, device=DEV) * 3).requires_grad_(True) for _ in range(4)]
+    labels = (torch.rand(B, 1, *shape, device=DEV) * C).long().clamp_(max=C - 1)
+    w = [0.25, 0.25, 0.25, 0.25]
+    loss = ops.seg_loss(logits, labels, w)
+    g = torch.autograd.grad(loss * 1.3, logits)
+    lr = [t.detach().double().requires_grad_(True) for t in logits]
+    ref = sum(wi * (F.cross_entropy(o, labels.squeeze(1)) + dice_loss(o, labels)) for wi, o in zip(w, lr))
+    gr = torch.autograd.grad(ref * 1.3, lr)
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref)), (float(loss), float(ref))
+    for a, b in zip(g, gr):
+        assert close(a, b, rtol=1e-4, atol=1e-12), rel_err(a, b)

@@ -56,6 +56,10 @@ class ResizeDesc(C.Structure):
                 ("H", C.c_int32), ("W", C.c_int32)]
 
 
+class SegLossDesc(C.Structure):
+    _fields_ = [("n_out", C.c_int32), ("B", C.c_int32), ("C", C.c_int32), ("S", C.c_int32), ("weights", C.c_float * 8)]
+
+
 class LnpwDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("C_in", C.c_int32), ("C_out", C.c_int32), ("S", C.c_int32), ("eps", C.c_float)]
 
@@ -72,9 +76,10 @@ SYMBOLS = [
     "vx_sdkt_loss_fwd", "vx_sdkt_loss_bwd",
     "vx_lnpw_workspace", "vx_lnpw_fwd", "vx_lnpw_bwd",
     "vx_resize_workspace", "vx_resize_trilinear_fwd", "vx_resize_trilinear_bwd",
+    "vx_segloss_workspace", "vx_segloss_fwd", "vx_segloss_bwd",
 ]
 
-_WS_OPS = {"jlc", "mixer", "pwa_block", "gram_fwd", "lnpw"}
+_WS_OPS = {"jlc", "mixer", "pwa_block", "gram_fwd", "lnpw", "segloss"}
 
 
 def ptr_array(tensors):
@@ -104,17 +109,17 @@ class VxLib:
         self.c.vx_profile_report.restype = C.c_size_t
         self.c.vx_profile_report.argtypes = [C.c_char_p, C.c_size_t]
         for name in ("vx_jlc_workspace", "vx_mixer_workspace", "vx_pwa_workspace", "vx_gram_workspace",
-                     "vx_lnpw_workspace", "vx_resize_workspace"):
+                     "vx_lnpw_workspace", "vx_resize_workspace", "vx_segloss_workspace"):
             getattr(self.c, name).restype = C.c_size_t
             getattr(self.c, name).argtypes = [C.c_void_p]
         vp, sz = C.c_void_p, C.c_size_t
         for name in ("vx_jlc_fwd", "vx_jlc_bwd", "vx_mixer_fwd", "vx_mixer_bwd", "vx_pwa_block_fwd", "vx_pwa_block_bwd",
-                     "vx_gram_fwd", "vx_lnpw_fwd", "vx_lnpw_bwd", "vx_resize_trilinear_bwd"):
+                     "vx_gram_fwd", "vx_lnpw_fwd", "vx_lnpw_bwd", "vx_resize_trilinear_bwd", "vx_segloss_fwd"):
             f = getattr(self.c, name)
             f.restype = C.c_int
             f.argtypes = [vp, vp, vp, vp, sz, vp]
         for name in ("vx_inorm_fwd", "vx_inorm_bwd", "vx_gram_bwd", "vx_sdkt_loss_fwd", "vx_sdkt_loss_bwd",
-                     "vx_resize_trilinear_fwd"):
+                     "vx_resize_trilinear_fwd", "vx_segloss_bwd"):
             f = getattr(self.c, name)
             f.restype = C.c_int
             f.argtypes = [vp, vp, vp, vp]

@@ -64,10 +64,14 @@ class Loss(torch.nn.Module):
         lay = veloxseg_output_layout(len(output), self.num_modal)
         s0, s1 = lay["seg"]
         w = normalized_deep_loss_weights(self.deep_weights, s1 - s0)
-        y = labels.squeeze(1).long()
-        seg = output[0].new_zeros(())
-        for wi, o in zip(w, output[s0:s1]):
-            seg = seg + wi * (F.cross_entropy(o, y) + dice_loss(o, labels))
+        outs = list(output[s0:s1])
+        if outs[0].is_cuda and len(outs) <= 8 and 2 <= outs[0].shape[1] <= 4 and all(o.shape == outs[0].shape for o in outs):
+            seg = ops.seg_loss(outs, labels.long(), w)        # one fused pass per direction (veloxseg_b200/csrc/segloss.cu)
+        else:                                                 # shapes the fused kernel does not cover: torch ops
+            y = labels.squeeze(1).long()
+            seg = outs[0].new_zeros(())
+            for wi, o in zip(w, outs):
+                seg = seg + wi * (F.cross_entropy(o, y) + dice_loss(o, labels))
         rc = F.mse_loss(output[lay["reconstruction"]], sr_labels)
         feat = ops.sdkt_loss(output[lay["decoder_gram"]], [output[i] for i in lay["teacher_grams"]])
         return seg + self.rc_weight * rc + self.feature_weight * feat

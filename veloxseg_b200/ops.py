@@ -17,7 +17,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (GramDesc, InormDesc, JlcDesc, LnpwDesc, MixerDesc, PwaDesc, PwaSaved, ResizeDesc, SdktLossDesc,
+from ._lib import (GramDesc, InormDesc, JlcDesc, LnpwDesc, MixerDesc, PwaDesc, PwaSaved, ResizeDesc, SdktLossDesc, SegLossDesc,
                    VX_MAX_MODAL, VX_MAX_SCALES)
 
 Tensor = torch.Tensor
@@ -198,6 +198,38 @@ def sdkt_loss_bwd_raw(lib, stream, dloss, gs, gts: Sequence[Tensor]):
 
 
 # ----------------------------------------------------------------------------------------------------
+# deep-supervision segmentation loss (CE + Dice per output, weighted)
+# ----------------------------------------------------------------------------------------------------
+def segloss_desc(logits: Sequence[Tensor], weights: Sequence[float]) -> SegLossDesc:
+    B, Cc = logits[0].shape[:2]
+    d = SegLossDesc(len(logits), B, Cc, logits[0][0, 0].numel())
+    for i, w in enumerate(weights):
+        d.weights[i] = float(w)
+    return d
+
+
+def segloss_fwd_raw(lib, stream, logits: Sequence[Tensor], labels: Tensor, weights: Sequence[float]):
+    logits = [_chk(t, "logits") for t in logits]
+    if labels.dtype != torch.int64:
+        raise TypeError(f"veloxseg: labels must be int64, got {labels.dtype}")
+    labels = labels.contiguous()
+    if any(t.shape != logits[0].shape for t in logits) or labels.numel() != logits[0].numel() // logits[0].shape[1]:
+        raise ValueError("veloxseg: seg_loss needs equally shaped logits and one label per voxel")
+    d = segloss_desc(logits, weights)
+    loss = torch.empty((), dtype=_f32, device=labels.device)
+    sums = torch.empty((d.n_out, d.B, 1 + 3 * d.C), dtype=_f32, device=labels.device)
+    lib.call_ws("vx_segloss_fwd", d, list(logits) + [labels], [loss, sums], _ws(lib, "segloss", d, labels), stream)
+    return loss, sums
+
+
+def segloss_bwd_raw(lib, stream, dloss, logits: Sequence[Tensor], labels: Tensor, sums: Tensor, weights: Sequence[float]):
+    d = segloss_desc(logits, weights)
+    outs = [torch.empty_like(t) for t in logits]
+    lib.call("vx_segloss_bwd", d, [_chk(dloss, "dloss")] + list(logits) + [labels, sums], outs, stream)
+    return outs
+
+
+# ----------------------------------------------------------------------------------------------------
 # LayerNorm(channels_first) + 1x1 (PatchMerging tail)
 # ----------------------------------------------------------------------------------------------------
 def lnpw_fwd_raw(lib, stream, x, ln_w, ln_b, W):
@@ -337,6 +369,8 @@ _L.define("gram_fwd(Tensor x) -> Tensor")
 _L.define("gram_bwd(Tensor dG, Tensor x) -> Tensor")
 _L.define("sdkt_loss_fwd(Tensor gs, Tensor[] gts) -> Tensor")
 _L.define("sdkt_loss_bwd(Tensor dloss, Tensor gs, Tensor[] gts) -> Tensor[]")
+_L.define("segloss_fwd(Tensor[] logits, Tensor labels, float[] weights) -> Tensor[]")
+_L.define("segloss_bwd(Tensor dloss, Tensor[] logits, Tensor labels, Tensor sums, float[] weights) -> Tensor[]")
 _L.define("resize_fwd(Tensor x, int[] size) -> Tensor")
 _L.define("resize_bwd(Tensor dy, int[] size) -> Tensor")
 _L.define("lnpw_fwd(Tensor x, Tensor ln_w, Tensor ln_b, Tensor W) -> Tensor[]")
@@ -360,6 +394,8 @@ _L.impl("gram_fwd", _cuda(gram_fwd_raw), "CUDA")
 _L.impl("gram_bwd", _cuda(gram_bwd_raw), "CUDA")
 _L.impl("sdkt_loss_fwd", _cuda(sdkt_loss_fwd_raw), "CUDA")
 _L.impl("sdkt_loss_bwd", _cuda(sdkt_loss_bwd_raw), "CUDA")
+_L.impl("segloss_fwd", _cuda(segloss_fwd_raw), "CUDA")
+_L.impl("segloss_bwd", _cuda(segloss_bwd_raw), "CUDA")
 _L.impl("resize_fwd", _cuda(resize_fwd_raw), "CUDA")
 _L.impl("resize_bwd", _cuda(resize_bwd_raw), "CUDA")
 _L.impl("lnpw_fwd", _cuda(lnpw_fwd_raw), "CUDA")
@@ -467,6 +503,25 @@ class _SdktLoss(torch.autograd.Function):
 
 def sdkt_loss(gs: Tensor, gts: Sequence[Tensor]) -> Tensor:
     return _SdktLoss.apply(gs.contiguous(), *[g.contiguous() for g in gts])
+
+
+class _SegLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, labels, weights, *logits):
+        loss, sums = _vx.segloss_fwd(list(logits), labels, list(weights))
+        ctx.save_for_backward(labels, sums, *logits)
+        ctx.weights = list(weights)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        labels, sums, *logits = ctx.saved_tensors
+        return (None, None) + tuple(_vx.segloss_bwd(dloss.contiguous(), logits, labels, sums, ctx.weights))
+
+
+def seg_loss(logits: Sequence[Tensor], labels: Tensor, weights: Sequence[float]) -> Tensor:
+    """sum_i w_i (CrossEntropy(logits_i, y) + Dice(logits_i, y)); labels (B, 1, *spatial) or (B, *spatial) int64."""
+    return _SegLoss.apply(labels.contiguous(), tuple(float(w) for w in weights), *[t.contiguous() for t in logits])
 
 
 class _LnPw(torch.autograd.Function):
