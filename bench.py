@@ -102,8 +102,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     # Library (cuDNN) convolutions OUTSIDE the section-8 path (out_conv1, Down/Up convs, patch-embed): tf32 tensor cores by
-    # default -- BASELINE.json names bf16 for this config, tf32 is above that, and the whole-model parity tests pass at
-    # the 1e-3 bar in this mode for the three reference configs.  Every libveloxseg kernel computes in fp32 (the
+    # default -- BASELINE.json names bf16 for this config, tf32 is above that, and the whole-model parity tests bound this
+    # mode at 3e-3 against the reference (measured ~1e-3).  Every libveloxseg kernel computes in fp32 (the
     # tcgen05 contraction is 3xTF32 = fp32-accurate) in both modes.  --library-convs fp32 gives the all-fp32 number.
     torch.backends.cudnn.allow_tf32 = args.library_convs == "tf32"
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -159,13 +159,16 @@ def run_ours(args, rank, world, local_rank):
     ts.step(x_d, y_d)
     enqueue_ms = (time.perf_counter() - t0) * 1e3
     torch.cuda.synchronize()
-    # ---- end to end (host batches)
-    for _ in range(2):
-        ts.step(x_h, y_h, sync=True)
+    # ---- end to end (host batches): every step copies ITS batch from pinned host memory (labels as uint8) and reads its
+    # loss back; the copy of the next batch is issued while the current step runs (two distinct host batches alternate)
+    xb = [x_h, x_h.clone().pin_memory()]
+    yb = [y_h.to(torch.uint8).pin_memory(), y_h.to(torch.uint8).pin_memory()]
+    for i in range(2):
+        ts.step(xb[i % 2], yb[i % 2], sync=True, prefetch=(xb[(i + 1) % 2], yb[(i + 1) % 2]))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        last_loss = ts.step(x_h, y_h, sync=True)
+    for i in range(args.steps):
+        last_loss = ts.step(xb[i % 2], yb[i % 2], sync=True, prefetch=(xb[(i + 1) % 2], yb[(i + 1) % 2]))
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -260,7 +263,7 @@ def run_ours(args, rank, world, local_rank):
                    "pointwise": "tcgen05 3xTF32 (fp32-accurate) for S>=4096, fp32 SIMT below" if pw_tc else "fp32 SIMT",
                    "library_convs_outside_path": args.library_convs},
         "e2e": {"value": round(total_patches / e2e_s, 3), "unit": "patches/s",
-                "h2d_bytes_per_step": int(x_h.numel() * x_h.element_size() + y_h.numel() * y_h.element_size()),
+                "h2d_bytes_per_step": int(xb[0].numel() * xb[0].element_size() + yb[0].numel() * yb[0].element_size()),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "host_enqueue_ms_per_step": round(enqueue_ms, 2), "clocks": clk.summary(), "roofline": roof, "loss": last_loss, "top_kernels": table,
     }

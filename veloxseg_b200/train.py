@@ -192,17 +192,53 @@ class TrainStep:
                         v.zero_()
         torch.cuda.synchronize(self.device)
 
-    def step(self, inputs: torch.Tensor, labels: torch.Tensor, sync: bool = False):
+    # ---- host -> device staging: pinned host batches are copied on a side stream into a staging pair, so the copy of
+    # batch i+1 (given as `prefetch=`) overlaps the replay of batch i; labels may arrive as uint8 (7/8 fewer bytes).
+    def _stage(self, inputs, labels):
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage_x = torch.empty_like(self._sx)
+            self._stage_y = torch.empty(self._sy.shape, dtype=labels.dtype, device=self.device)
+            self._stage_ev = torch.cuda.Event()
+            self._consumed_ev = None
+            self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))      # once: the blocks may be recycled ones
+        if self._stage_y.dtype != labels.dtype:
+            self._stage_y = torch.empty(self._sy.shape, dtype=labels.dtype, device=self.device)
+        cs = self._copy_stream
+        if self._consumed_ev is not None:
+            cs.wait_event(self._consumed_ev)      # the staging pair has been read out (NOT the whole step: the copy must overlap it)
+        with torch.cuda.stream(cs):
+            self._stage_x.copy_(inputs, non_blocking=True)
+            self._stage_y.copy_(labels, non_blocking=True)
+            self._stage_ev.record(cs)
+        self._staged = (inputs, labels)
+
+    def step(self, inputs: torch.Tensor, labels: torch.Tensor, sync: bool = False, prefetch=None):
+        """`prefetch=(next_inputs, next_labels)`: start copying the next host batch while this step runs."""
         if self.use_graph:
             if self._graph is None:
-                self._capture(inputs, labels)
-            self._sx.copy_(inputs, non_blocking=True)
-            self._sy.copy_(labels, non_blocking=True)
+                self._capture(inputs, labels.long() if labels.dtype != torch.int64 else labels)
+            staged = getattr(self, "_staged", None)
+            if staged is not None and staged[0] is inputs and staged[1] is labels:
+                torch.cuda.current_stream(self.device).wait_event(self._stage_ev)
+                self._sx.copy_(self._stage_x)
+                self._sy.copy_(self._stage_y)                          # uint8 -> int64 on the device
+                self._consumed_ev = torch.cuda.Event()
+                self._consumed_ev.record(torch.cuda.current_stream(self.device))
+                self._staged = None
+            else:
+                self._sx.copy_(inputs, non_blocking=True)
+                if labels.dtype != torch.int64 and not labels.is_cuda:
+                    self._sy.copy_(labels.to(self.device, non_blocking=True))
+                else:
+                    self._sy.copy_(labels, non_blocking=True)
             self._graph.replay()
             if self._graph_b is not None:
                 dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
                 self._graph_b.replay()
+            if prefetch is not None:
+                self._stage(*prefetch)
             loss = self._sloss
         else:
-            loss = self._step_eager(inputs.to(self.device, non_blocking=True), labels.to(self.device, non_blocking=True))
+            loss = self._step_eager(inputs.to(self.device, non_blocking=True), labels.to(self.device, non_blocking=True).long())
         return float(loss.item()) if sync else loss
