@@ -106,6 +106,7 @@ def test_parallel_branches_match_serial():
         G.zero_dropout(m)
         m = m.to(DEV).train()
         m.parallel_branches = par
+        m.encoder.pipeline_branches = par      # conv encoder one level behind the transformer encoder on a side stream
         for rep in range(3):       # repeat: a race would show up as run-to-run differences
             m.zero_grad(set_to_none=True)
             outs = m(x)

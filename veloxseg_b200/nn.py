@@ -179,7 +179,13 @@ class PatchMerging(nn.Module):
         self.norm = norm_layer(self.mid_ch, data_format="channels_first", dim=dim)
 
     def faeture_sample(self, x):   # (sic) reference method name
-        return torch.cat([x[:, :, i::2, j::2, k::2] for i in (0, 1) for j in (0, 1) for k in (0, 1)], dim=1)
+        """cat([x[:, :, i::2, j::2, k::2] for i, j, k in 000..111], 1) of the reference as ONE strided copy (the
+        reference's 8 slices + cat cost 1 + 16 kernels per call and direction under autograd)."""
+        B, C, D, H, W = x.shape
+        if (D | H | W) & 1:
+            return torch.cat([x[:, :, i::2, j::2, k::2] for i in (0, 1) for j in (0, 1) for k in (0, 1)], dim=1)
+        v = x.view(B, C, D // 2, 2, H // 2, 2, W // 2, 2)                 # (b, c, d, i, h, j, w, k)
+        return v.permute(0, 3, 5, 7, 1, 2, 4, 6).reshape(B, 8 * C, D // 2, H // 2, W // 2)
 
     def forward(self, x):
         return ops.ln_pointwise(self.faeture_sample(x), self.norm.weight, self.norm.bias, _w2(self.reduction))
@@ -447,10 +453,13 @@ class Transformer_Encoder(nn.Module):
                 qkv_bias=qkv_bias, do_downsample=i < self.num_layers - 1, dim=spatial_dim))
             size = [s // 2 for s in size]
 
-    def forward(self, xs):
+    def embed(self, xs):
         xs = torch.chunk(xs, self.num_modalities, dim=1)
         xs = [self.pos_drop(self.patch_embeds[m](xs[m])) for m in range(self.num_modalities)]
-        outs, cur = [], [x.contiguous() for x in xs]
+        return [x.contiguous() for x in xs]
+
+    def forward(self, xs):
+        outs, cur = [], self.embed(xs)
         for i in range(self.num_layers):
             attn, cur = self.layers[i](cur)
             outs.append(attn)
@@ -483,14 +492,46 @@ class Encoder(nn.Module):
             setattr(self, f"attn2conv_{i + 1}",
                     ModalMixer(attn_base_ch * 2 ** i * self.num_modalities, base_ch * 2 ** i))
 
+    # The conv branch at level i needs only attn_i; the transformer branch at level i+1 needs only attn_i too.  On CUDA the
+    # conv branch therefore runs on a side stream, one level behind the transformer branch (and the same in backward:
+    # autograd replays every op on the stream of its forward).  Levels 2-4 are small kernels that leave most of the 148
+    # SMs idle, so the two branches overlap almost for free.  Under graph capture the fork/join become graph edges.
+    pipeline_branches = True
+
+    def _conv_level(self, i, attn, t):
+        # x_i = IN(down_i(.)) + IN(W . cat_m(attn_i[m]) + b): the mixer kernel reads the M streams in place (no cat)
+        ec = self.encoder_conv
+        mixed = getattr(self, f"attn2conv_{i + 1}")(attn, addend=getattr(ec, f"down{i + 1}")(t))
+        return getattr(ec, f"layer{i + 1}")(mixed)
+
     def forward(self, x):
-        attns = self.encoder_attn(x)
-        ec, encs, t = self.encoder_conv, [], x
-        for i in range(4):
-            # x_i = IN(down_i(.)) + IN(W . cat_m(attn_i[m]) + b): the mixer kernel reads the M streams in place (no cat)
-            mixed = getattr(self, f"attn2conv_{i + 1}")(attns[i], addend=getattr(ec, f"down{i + 1}")(t))
-            t = getattr(ec, f"layer{i + 1}")(mixed)
-            encs.append(t)
+        encs, t = [], x
+        if self.pipeline_branches and x.is_cuda:
+            main = torch.cuda.current_stream(x.device)
+            if getattr(self, "_side_dev", None) != x.device:
+                self._side, self._side_dev = torch.cuda.Stream(device=x.device), x.device
+            side = self._side
+            side.wait_stream(main)
+            x.record_stream(side)
+            attns, cur = [], self.encoder_attn.embed(x)
+            for i in range(4):
+                attn, cur = self.encoder_attn.layers[i](cur)
+                attns.append(attn)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    for a in attn:
+                        a.record_stream(side)
+                    t = self._conv_level(i, attn, t)
+                    encs.append(t)
+            main.wait_stream(side)
+            for e in encs:
+                e.record_stream(main)
+            attns = tuple(attns)
+        else:
+            attns = self.encoder_attn(x)
+            for i in range(4):
+                t = self._conv_level(i, attns[i], t)
+                encs.append(t)
         if self.training:
             return [list(a) for a in attns], encs
         return tuple(encs)
