@@ -29,6 +29,9 @@ static int g_force_vx = 0;
 void jlc_force_vx(int vx) { g_force_vx = vx; }
 static int g_force_tz[2] = {0, 0}, g_force_ty[2] = {0, 0};     // tuning probes (vx_set_option): [fwd/dgrad, wgrad]
 void jlc_force_tile(int kind, int tz, int ty) { g_force_tz[kind] = tz; g_force_ty[kind] = ty; }
+static int g_small_max_s = 512;     // volumes up to this many voxels use the small-volume conv kernels (0 disables)
+void jlc_set_small_max(int s) { g_small_max_s = s; }
+static bool jlc_use_small(int D, int H, int W) { return g_small_max_s > 0 && D * H * W <= g_small_max_s; }
 
 // Tile choice, from a sweep on B200 at the per-level shapes of the three reference configs (tools/gpu_jlc_tiles.sh,
 // profiles/r1_jlc_tile_sweep.txt).  What the sweep showed:
@@ -126,24 +129,24 @@ __global__ void __launch_bounds__(256) jlc_conv_fwd_kernel(const __grid_constant
     for (int idx = tid; idx < 4 * HZ * HY * TXP; idx += nthr) {
       const int hx = idx % TXP, hy = (idx / TXP) % HY, hz = (idx / (TXP * HY)) % HZ, ci = idx / (TXP * HY * HZ);
       const int gz = z0 + hz - 2, gy = y0 + hy - 2, gx = x0 + hx - 2;
-      float v = 0.f;
-      if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
-        v = __ldg(A.x + ((size_t)b * C + cin0 + ci) * S + ((size_t)gz * H + gy) * W + gx);
-      xs[idx] = v;
+      const bool ok = gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      vx_cp_async4(xs + idx, ok ? A.x + ((size_t)b * C + cin0 + ci) * S + ((size_t)gz * H + gy) * W + gx : A.x, ok);
     }
     // weights of this ci-chunk, transposed to [ci][tap][co]
     for (int idx = tid; idx < CG * 4 * 125; idx += nthr) {
       const int tap = idx % 125, ci = (idx / 125) % 4, co = idx / 500;
-      ws5[(ci * 125 + tap) * CG + co] = __ldg(A.w5 + ((size_t)(g * CG + co) * CG + chunk * 4 + ci) * 125 + tap);
+      vx_cp_async4(ws5 + ((ci * 125 + tap) * CG + co), A.w5 + ((size_t)(g * CG + co) * CG + chunk * 4 + ci) * 125 + tap, true);
     }
     for (int idx = tid; idx < CG * 4 * 27; idx += nthr) {
       const int tap = idx % 27, ci = (idx / 27) % 4, co = idx / 108;
-      ws3[(ci * 27 + tap) * CG + co] = __ldg(A.w3 + ((size_t)(g * CG + co) * CG + chunk * 4 + ci) * 27 + tap);
+      vx_cp_async4(ws3 + ((ci * 27 + tap) * CG + co), A.w3 + ((size_t)(g * CG + co) * CG + chunk * 4 + ci) * 27 + tap, true);
     }
     for (int idx = tid; idx < CG * 4; idx += nthr) {
       const int ci = idx % 4, co = idx / 4;
-      ws1[ci * CG + co] = __ldg(A.w1 + (size_t)(g * CG + co) * CG + chunk * 4 + ci);
+      vx_cp_async4(ws1 + (ci * CG + co), A.w1 + (size_t)(g * CG + co) * CG + chunk * 4 + ci, true);
     }
+    vx_cp_async_commit();
+    vx_cp_async_wait_all();
     __syncthreads();
 
     if (cb < NCB) {
@@ -247,6 +250,149 @@ __global__ void __launch_bounds__(256) jlc_conv_fwd_kernel(const __grid_constant
     const size_t row = (size_t)k * A.B * C + (size_t)b * C + g * CG + c;
     float* p = A.part + (row * ntiles + tile) * 2;
     p[0] = sst[i * 2]; p[1] = sst[i * 2 + 1];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Small-volume variants (levels 3-4: S = 216 / 27, Hecktor 256 / 32).  The tiled kernels above leave 32-128 CTAs of
+// 36-64 threads walking a serial (ci, tap) loop -- 75-250 us of pure latency for a few MFLOP.  Here the whole padded
+// volume of a group lives in shared memory and the work is split three ways: CTA = (batch, group, 4 output channels,
+// voxel slab <= 128), thread = (voxel, slice of the reduction channels) -- warps are uniform in the slice, so every
+// weight read is a 16-byte broadcast -- and the slices meet in shared memory before the bias / store / stats epilogue.
+// ---------------------------------------------------------------------------------------------------
+struct SmallGeo { int nsplit, VP, KS, Dp, Hp, Wp, PV; };
+
+static SmallGeo small_geo(int CG, int D, int H, int W) {
+  SmallGeo g{};
+  const int S = D * H * W;
+  g.nsplit = (S + 127) / 128;
+  const int Vc = (S + g.nsplit - 1) / g.nsplit;
+  g.VP = (Vc + 31) & ~31;
+  g.KS = 256 / g.VP;
+  if (g.KS > CG) g.KS = CG;
+  while (CG % g.KS) --g.KS;
+  g.Dp = D + 4; g.Hp = H + 4; g.Wp = W + 4;
+  g.PV = g.Dp * g.Hp * g.Wp;
+  return g;
+}
+
+template <int CG>
+__global__ void __launch_bounds__(256) jlc_conv_small_fwd_kernel(const __grid_constant__ ConvFwdArgs A,
+                                                                 const __grid_constant__ SmallGeo G) {
+  constexpr int NQ = CG / 4;
+  const int split = blockIdx.x, g = blockIdx.y / NQ, q = blockIdx.y % NQ, b = blockIdx.z;
+  const int D = A.D, H = A.H, W = A.W, C = A.C;
+  const int S = D * H * W;
+  const int Hp = G.Hp, Wp = G.Wp, PV = G.PV, VP = G.VP, KS = G.KS;
+  VX_DYN_SMEM(float, sm);
+  float* xs = sm;                               // [CG][Dp][Hp][Wp], zero halo of 2
+  float* ws = xs + (size_t)CG * PV;             // [CG][153][4]: taps 0..124 k=5, 125..151 k=3, 152 k=1
+  float* red = ws + (size_t)CG * 153 * 4;       // [KS][12][VP]
+  __shared__ float sst[12 * 4 * 2];             // (sum, sumsq) per (branch * 4 + c, warp of the voxel slab): fixed-order fold
+  const int tid = threadIdx.x, nthr = blockDim.x;
+
+  for (int idx = tid; idx < CG * PV; idx += nthr) {
+    const int px = idx % Wp, py = (idx / Wp) % Hp, pz = (idx / (Wp * Hp)) % G.Dp, ci = idx / PV;
+    const int gz = pz - 2, gy = py - 2, gx = px - 2;
+    const bool ok = gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W;
+    vx_cp_async4(xs + idx, ok ? A.x + ((size_t)b * C + g * CG + ci) * S + ((size_t)gz * H + gy) * W + gx : A.x, ok);
+  }
+  const int co0 = g * CG + q * 4;
+  for (int idx = tid; idx < 4 * CG * 125; idx += nthr) {
+    const int tap = idx % 125, ci = (idx / 125) % CG, c = idx / (125 * CG);
+    vx_cp_async4(ws + ((ci * 153 + tap) * 4 + c), A.w5 + ((size_t)(co0 + c) * CG + ci) * 125 + tap, true);
+  }
+  for (int idx = tid; idx < 4 * CG * 27; idx += nthr) {
+    const int tap = idx % 27, ci = (idx / 27) % CG, c = idx / (27 * CG);
+    vx_cp_async4(ws + ((ci * 153 + 125 + tap) * 4 + c), A.w3 + ((size_t)(co0 + c) * CG + ci) * 27 + tap, true);
+  }
+  for (int idx = tid; idx < 4 * CG; idx += nthr) {
+    const int ci = idx % CG, c = idx / CG;
+    vx_cp_async4(ws + ((ci * 153 + 152) * 4 + c), A.w1 + (size_t)(co0 + c) * CG + ci, true);
+  }
+  vx_cp_async_commit();
+  vx_cp_async_wait_all();
+  __syncthreads();
+
+  const int vl = tid % VP, sl = tid / VP;
+  const int Vc = (S + G.nsplit - 1) / G.nsplit;
+  const int vox = split * Vc + vl;
+  const bool live = sl < KS && vl < Vc && vox < S;
+  float a5[4] = {0.f, 0.f, 0.f, 0.f}, a3[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    const int x = vox % W, y = (vox / W) % H, z = vox / (W * H);
+    const int per = CG / KS;
+#pragma unroll 1
+    for (int ci = sl * per; ci < (sl + 1) * per; ++ci) {
+      const float* xb = xs + (size_t)ci * PV + ((size_t)z * Hp + y) * Wp + x;
+      const float* wb = ws + (size_t)ci * 153 * 4;
+#pragma unroll 1
+      for (int dz = 0; dz < 5; ++dz) {
+        const bool mid_z = dz >= 1 && dz <= 3;
+#pragma unroll 1
+        for (int dy = 0; dy < 5; ++dy) {
+          const float* xr = xb + ((size_t)dz * Hp + dy) * Wp;
+          float xv[5];
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx) xv[dx] = xr[dx];
+          const float* w5p = wb + (size_t)((dz * 5 + dy) * 5) * 4;
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx) {
+            const float4 w = *reinterpret_cast<const float4*>(w5p + dx * 4);
+            a5[0] = fmaf(w.x, xv[dx], a5[0]); a5[1] = fmaf(w.y, xv[dx], a5[1]);
+            a5[2] = fmaf(w.z, xv[dx], a5[2]); a5[3] = fmaf(w.w, xv[dx], a5[3]);
+          }
+          if (mid_z && dy >= 1 && dy <= 3) {
+            const float* w3p = wb + (size_t)(125 + ((dz - 1) * 3 + (dy - 1)) * 3) * 4;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const float4 w = *reinterpret_cast<const float4*>(w3p + dx * 4);
+              a3[0] = fmaf(w.x, xv[dx + 1], a3[0]); a3[1] = fmaf(w.y, xv[dx + 1], a3[1]);
+              a3[2] = fmaf(w.z, xv[dx + 1], a3[2]); a3[3] = fmaf(w.w, xv[dx + 1], a3[3]);
+            }
+            if (dz == 2 && dy == 2) {
+              const float4 w = *reinterpret_cast<const float4*>(wb + 152 * 4);
+              a1[0] = fmaf(w.x, xv[2], a1[0]); a1[1] = fmaf(w.y, xv[2], a1[1]);
+              a1[2] = fmaf(w.z, xv[2], a1[2]); a1[3] = fmaf(w.w, xv[2], a1[3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (sl < KS) {
+    float* r = red + (size_t)sl * 12 * VP + vl;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { r[(size_t)c * VP] = a1[c]; r[(size_t)(4 + c) * VP] = a3[c]; r[(size_t)(8 + c) * VP] = a5[c]; }
+  }
+  __syncthreads();
+  // epilogue: item = (j = branch * 4 + c, voxel); VP is a multiple of 32, so a warp shares j
+  const size_t BCS = (size_t)A.B * C * S;
+  const int lane = tid & 31;
+  for (int it0 = 0; it0 < 12 * VP; it0 += nthr) {
+    const int it = it0 + tid;
+    const bool in = it < 12 * VP;
+    const int j = in ? it / VP : 0, v = in ? it % VP : 0;
+    const int gv = split * Vc + v;
+    const int k = j >> 2, co = co0 + (j & 3);
+    float val = 0.f;
+    const bool ok = in && v < Vc && gv < S;
+    if (ok) {
+      for (int s2 = 0; s2 < KS; ++s2) val += red[((size_t)s2 * 12 + j) * VP + v];
+      val += __ldg((k == 0 ? A.b1 : (k == 1 ? A.b3 : A.b5)) + co);
+      A.z[(size_t)k * BCS + ((size_t)b * C + co) * S + gv] = val;
+    }
+    const float ss = warp_sum(val), qq = warp_sum(val * val);
+    if (lane == 0 && in) { sst[(j * 4 + (v >> 5)) * 2] = ss; sst[(j * 4 + (v >> 5)) * 2 + 1] = qq; }
+  }
+  __syncthreads();
+  if (tid < 12) {
+    const int k = tid >> 2, co = co0 + (tid & 3);
+    const size_t row = (size_t)k * A.B * C + (size_t)b * C + co;
+    float ss = 0.f, qq = 0.f;
+    for (int w = 0; w < (VP >> 5); ++w) { ss += sst[(tid * 4 + w) * 2]; qq += sst[(tid * 4 + w) * 2 + 1]; }
+    float* p = A.part + (row * G.nsplit + split) * 2;
+    p[0] = ss; p[1] = qq;
   }
 }
 
@@ -402,16 +548,16 @@ VX_DEV void dgrad_branch(const ConvDgradArgs& A, const float* __restrict__ gzk, 
     for (int idx = tid; idx < 4 * HZ * HY * TXP; idx += nthr) {
       const int hx = idx % TXP, hy = (idx / TXP) % HY, hz = (idx / (TXP * HY)) % HZ, ci = idx / (TXP * HY * HZ);
       const int gz_ = z0 + hz - P, gy = y0 + hy - P, gx = x0 + hx - 2;
-      float v = 0.f;
-      if (gz_ >= 0 && gz_ < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
-        v = __ldg(gzk + ((size_t)b * C + c0 + ci) * S + ((size_t)gz_ * H + gy) * W + gx);
-      xs[idx] = v;
+      const bool ok = gz_ >= 0 && gz_ < D && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      vx_cp_async4(xs + idx, ok ? gzk + ((size_t)b * C + c0 + ci) * S + ((size_t)gz_ * H + gy) * W + gx : gzk, ok);
     }
     // ws[co_local(4)][tap'][ci_out(CG)] = w[co][ci][K3-1-tap']
     for (int idx = tid; idx < 4 * CG * K3; idx += nthr) {
       const int tap = idx % K3, cio = (idx / K3) % CG, col = idx / (K3 * CG);
-      ws[(col * K3 + (K3 - 1 - tap)) * CG + cio] = __ldg(wk + ((size_t)(c0 + col) * CG + cio) * K3 + tap);
+      vx_cp_async4(ws + ((col * K3 + (K3 - 1 - tap)) * CG + cio), wk + ((size_t)(c0 + col) * CG + cio) * K3 + tap, true);
     }
+    vx_cp_async_commit();
+    vx_cp_async_wait_all();
     __syncthreads();
     if (cb < NCB) {
 #pragma unroll 1
@@ -484,6 +630,113 @@ __global__ void __launch_bounds__(256) jlc_conv_dgrad_kernel(const __grid_consta
       for (int v = 0; v < VX; ++v)
         if (gx0 + v < A.W) A.dx[o + v] = acc[v][c] + A.dO[o + v];
     }
+  }
+}
+
+// Small-volume dgrad (same decomposition as jlc_conv_small_fwd_kernel): CTA = (batch, group, 4 input channels, voxel
+// slab), thread = (voxel, slice of the group's output channels); the three branch gradients sit in shared memory as
+// padded volumes (k=5 and k=3 share the halo-2 layout, k=1 is read at the centre), weights are staged flipped so the
+// loop is a plain correlation.
+template <int CG>
+__global__ void __launch_bounds__(256) jlc_conv_small_dgrad_kernel(const __grid_constant__ ConvDgradArgs A,
+                                                                   const __grid_constant__ SmallGeo G) {
+  constexpr int NQ = CG / 4;
+  const int split = blockIdx.x, g = blockIdx.y / NQ, q = blockIdx.y % NQ, b = blockIdx.z;
+  const int D = A.D, H = A.H, W = A.W, C = A.C;
+  const int S = D * H * W;
+  const int Hp = G.Hp, Wp = G.Wp, PV = G.PV, VP = G.VP, KS = G.KS;
+  const size_t BCS = (size_t)A.B * C * S;
+  VX_DYN_SMEM(float, sm);
+  float* gs = sm;                               // [3][CG][Dp][Hp][Wp]  (k = 1, 3, 5 like A.gz)
+  float* ws = gs + (size_t)3 * CG * PV;         // [CG co][153][4 ci]: flipped taps, 0..124 k=5, 125..151 k=3, 152 k=1
+  float* red = ws + (size_t)CG * 153 * 4;       // [KS][4][VP]
+  const int tid = threadIdx.x, nthr = blockDim.x;
+
+  for (int idx = tid; idx < 3 * CG * PV; idx += nthr) {
+    const int px = idx % Wp, py = (idx / Wp) % Hp, pz = (idx / (Wp * Hp)) % G.Dp, co = (idx / PV) % CG, k = idx / (PV * CG);
+    const int gz = pz - 2, gy = py - 2, gx = px - 2;
+    const bool ok = gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W;
+    vx_cp_async4(gs + idx, ok ? A.gz + (size_t)k * BCS + ((size_t)b * C + g * CG + co) * S + ((size_t)gz * H + gy) * W + gx : A.gz, ok);
+  }
+  const int ci0 = q * 4;                         // input channels (within the group) this CTA produces
+  for (int idx = tid; idx < CG * 4 * 125; idx += nthr) {
+    const int tap = idx % 125, c = (idx / 125) % 4, co = idx / 500;
+    vx_cp_async4(ws + ((co * 153 + (124 - tap)) * 4 + c), A.w5 + ((size_t)(g * CG + co) * CG + ci0 + c) * 125 + tap, true);
+  }
+  for (int idx = tid; idx < CG * 4 * 27; idx += nthr) {
+    const int tap = idx % 27, c = (idx / 27) % 4, co = idx / 108;
+    vx_cp_async4(ws + ((co * 153 + 125 + (26 - tap)) * 4 + c), A.w3 + ((size_t)(g * CG + co) * CG + ci0 + c) * 27 + tap, true);
+  }
+  for (int idx = tid; idx < CG * 4; idx += nthr) {
+    const int c = idx % 4, co = idx / 4;
+    vx_cp_async4(ws + ((co * 153 + 152) * 4 + c), A.w1 + (size_t)(g * CG + co) * CG + ci0 + c, true);
+  }
+  vx_cp_async_commit();
+  vx_cp_async_wait_all();
+  __syncthreads();
+
+  const int vl = tid % VP, sl = tid / VP;
+  const int Vc = (S + G.nsplit - 1) / G.nsplit;
+  const int vox = split * Vc + vl;
+  const bool live = sl < KS && vl < Vc && vox < S;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    const int x = vox % W, y = (vox / W) % H, z = vox / (W * H);
+    const int per = CG / KS;
+#pragma unroll 1
+    for (int co = sl * per; co < (sl + 1) * per; ++co) {
+      const size_t vo = ((size_t)z * Hp + y) * Wp + x;
+      const float* g1 = gs + (size_t)co * PV + vo;
+      const float* g3 = gs + (size_t)(CG + co) * PV + vo;
+      const float* g5 = gs + (size_t)(2 * CG + co) * PV + vo;
+      const float* wb = ws + (size_t)co * 153 * 4;
+#pragma unroll 1
+      for (int dz = 0; dz < 5; ++dz) {
+        const bool mid_z = dz >= 1 && dz <= 3;
+#pragma unroll 1
+        for (int dy = 0; dy < 5; ++dy) {
+          const size_t ro = ((size_t)dz * Hp + dy) * Wp;
+          const float* w5p = wb + (size_t)((dz * 5 + dy) * 5) * 4;
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx) {
+            const float xv = g5[ro + dx];
+            const float4 w = *reinterpret_cast<const float4*>(w5p + dx * 4);
+            acc[0] = fmaf(w.x, xv, acc[0]); acc[1] = fmaf(w.y, xv, acc[1]);
+            acc[2] = fmaf(w.z, xv, acc[2]); acc[3] = fmaf(w.w, xv, acc[3]);
+          }
+          if (mid_z && dy >= 1 && dy <= 3) {
+            const float* w3p = wb + (size_t)(125 + ((dz - 1) * 3 + (dy - 1)) * 3) * 4;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const float xv = g3[ro + dx + 1];
+              const float4 w = *reinterpret_cast<const float4*>(w3p + dx * 4);
+              acc[0] = fmaf(w.x, xv, acc[0]); acc[1] = fmaf(w.y, xv, acc[1]);
+              acc[2] = fmaf(w.z, xv, acc[2]); acc[3] = fmaf(w.w, xv, acc[3]);
+            }
+            if (dz == 2 && dy == 2) {
+              const float xv = g1[ro + 2];
+              const float4 w = *reinterpret_cast<const float4*>(wb + 152 * 4);
+              acc[0] = fmaf(w.x, xv, acc[0]); acc[1] = fmaf(w.y, xv, acc[1]);
+              acc[2] = fmaf(w.z, xv, acc[2]); acc[3] = fmaf(w.w, xv, acc[3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (sl < KS) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) red[((size_t)sl * 4 + c) * VP + vl] = acc[c];
+  }
+  __syncthreads();
+  for (int it = tid; it < 4 * VP; it += nthr) {
+    const int c = it / VP, v = it % VP;
+    const int gv = split * Vc + v;
+    if (v >= Vc || gv >= S) continue;
+    float val = 0.f;
+    for (int s2 = 0; s2 < KS; ++s2) val += red[((size_t)s2 * 4 + c) * VP + v];
+    const size_t o = ((size_t)b * C + g * CG + ci0 + c) * S + gv;
+    A.dx[o] = val + A.dO[o];
   }
 }
 
@@ -565,11 +818,11 @@ __global__ void __launch_bounds__(256) jlc_conv_wgrad_kernel(const __grid_consta
   for (int idx = tid; idx < 3 * CG * tvol; idx += nthr) {
     const int x = idx % TX, y = (idx / TX) % TY, z = (idx / (TX * TY)) % TZ, co = (idx / tvol) % CG, k = idx / (tvol * CG);
     const int gz_ = z0 + z, gy = y0 + y, gx = x0 + x;
-    float v = 0.f;
-    if (gz_ < D && gy < H && gx < W)
-      v = __ldg(A.gz + k * BCS + ((size_t)b * C + g * CG + co) * S + ((size_t)gz_ * H + gy) * W + gx);
-    gs[idx] = v;
+    const bool ok = gz_ < D && gy < H && gx < W;
+    vx_cp_async4(gs + idx, ok ? A.gz + k * BCS + ((size_t)b * C + g * CG + co) * S + ((size_t)gz_ * H + gy) * W + gx : A.gz, ok);
   }
+  vx_cp_async_commit();
+  vx_cp_async_wait_all();
   __syncthreads();
   // db partials: one warp-strided pass per (k, co)
   for (int r = tid >> 5; r < 3 * CG; r += nthr >> 5) {
@@ -585,11 +838,11 @@ __global__ void __launch_bounds__(256) jlc_conv_wgrad_kernel(const __grid_consta
     for (int idx = tid; idx < 4 * HZ * HY * TXP; idx += nthr) {
       const int hx = idx % TXP, hy = (idx / TXP) % HY, hz = (idx / (TXP * HY)) % HZ, ci = idx / (TXP * HY * HZ);
       const int gz_ = z0 + hz - 2, gy = y0 + hy - 2, gx = x0 + hx - 2;
-      float v = 0.f;
-      if (gz_ >= 0 && gz_ < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
-        v = __ldg(A.x + ((size_t)b * C + cin0 + ci) * S + ((size_t)gz_ * H + gy) * W + gx);
-      xs[idx] = v;
+      const bool ok = gz_ >= 0 && gz_ < D && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      vx_cp_async4(xs + idx, ok ? A.x + ((size_t)b * C + cin0 + ci) * S + ((size_t)gz_ * H + gy) * W + gx : A.x, ok);
     }
+    vx_cp_async_commit();
+    vx_cp_async_wait_all();
     __syncthreads();
     // a flat item list: k=5 items first (heaviest), then k=3, then k=1
     const int n5 = 4 * 25 * NCB, n3 = 4 * 9 * NCB;
@@ -613,6 +866,7 @@ static inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 struct JlcLayout {
   size_t S, BCS, rows;
   ConvTile tf, tw;
+  int small, ntiles_f;      // small-volume conv kernels; stats partials per row of the forward conv
   int nchunk, chunk;
   size_t off_part_z, off_part_o, off_a, off_c;                       // forward scratch
   size_t off_dh, off_dohat, off_dO, off_gz, off_acc, off_acc2;      // backward scratch
@@ -632,7 +886,10 @@ static int jlc_layout(const vx_jlc_desc* d, JlcLayout& L) {
   if (L.tf.threads == 0 || L.tw.TZ == 0) { set_error("jlc: no tile fits"); return VX_ERR_UNSUPPORTED; }
   L.chunk = 2048;
   L.nchunk = cdiv((long long)L.S, L.chunk);
-  const int ntiles = L.tf.ntz * L.tf.nty * L.tf.ntx;
+  L.small = jlc_use_small(d->D, d->H, d->W) &&
+            sizeof(float) * ((size_t)3 * CG * (d->D + 4) * (d->H + 4) * (d->W + 4) + (size_t)CG * 153 * 4 + 4096) <= 200 * 1024;
+  L.ntiles_f = L.small ? small_geo(CG, d->D, d->H, d->W).nsplit : L.tf.ntz * L.tf.nty * L.tf.ntx;
+  const int ntiles = L.ntiles_f;
   size_t off = 0;
   L.off_part_z = off; off += align256(sizeof(float) * 3 * L.rows * ntiles * 2);
   L.off_part_o = off; off += align256(sizeof(float) * L.rows * L.nchunk * 2);
@@ -678,6 +935,26 @@ static int launch_conv_dgrad(const ConvDgradArgs& A, int groups, cudaStream_t st
     VX_LAUNCH((jlc_conv_dgrad_kernel<CG, 4>), grid, dim3(t.threads), smem, st, A);
   }
   return check_launch("jlc_conv_dgrad_kernel");
+}
+
+template <int CG>
+static int launch_conv_small_fwd(const ConvFwdArgs& A, int groups, cudaStream_t st) {
+  const SmallGeo G = small_geo(CG, A.D, A.H, A.W);
+  const size_t smem = sizeof(float) * ((size_t)CG * G.PV + (size_t)CG * 153 * 4 + (size_t)G.KS * 12 * G.VP);
+  if (smem > 200 * 1024) { set_error("jlc small fwd: volume too large for shared memory"); return VX_ERR_UNSUPPORTED; }
+  VX_SET_SMEM((jlc_conv_small_fwd_kernel<CG>), smem);
+  VX_LAUNCH((jlc_conv_small_fwd_kernel<CG>), dim3(G.nsplit, groups * (CG / 4), A.B), dim3(256), smem, st, A, G);
+  return check_launch("jlc_conv_small_fwd_kernel");
+}
+
+template <int CG>
+static int launch_conv_small_dgrad(const ConvDgradArgs& A, int groups, cudaStream_t st) {
+  const SmallGeo G = small_geo(CG, A.D, A.H, A.W);
+  const size_t smem = sizeof(float) * ((size_t)3 * CG * G.PV + (size_t)CG * 153 * 4 + (size_t)G.KS * 4 * G.VP);
+  if (smem > 200 * 1024) { set_error("jlc small dgrad: volume too large for shared memory"); return VX_ERR_UNSUPPORTED; }
+  VX_SET_SMEM((jlc_conv_small_dgrad_kernel<CG>), smem);
+  VX_LAUNCH((jlc_conv_small_dgrad_kernel<CG>), dim3(G.nsplit, groups * (CG / 4), A.B), dim3(256), smem, st, A, G);
+  return check_launch("jlc_conv_small_dgrad_kernel");
 }
 
 template <int CG>
@@ -732,11 +1009,15 @@ extern "C" int vx_jlc_fwd(const vx_jlc_desc* d, const void* const* in, void* con
   const int npos = L.tf.TZ * L.tf.TY * (L.tf.TX / L.tf.VX);
   A.uniform_warps = (npos % 32 == 0) ? 1 : 0;
   prof_bytes(4.0 * sizeof(float) * (double)L.BCS);       // x in, z1 z3 z5 out
-  if (CG == 4) VX_TRY(launch_conv_fwd<4>(A, d->groups, st));
+  if (L.small) {
+    if (CG == 4) VX_TRY(launch_conv_small_fwd<4>(A, d->groups, st));
+    else if (CG == 8) VX_TRY(launch_conv_small_fwd<8>(A, d->groups, st));
+    else VX_TRY(launch_conv_small_fwd<16>(A, d->groups, st));
+  } else if (CG == 4) VX_TRY(launch_conv_fwd<4>(A, d->groups, st));
   else if (CG == 8) VX_TRY(launch_conv_fwd<8>(A, d->groups, st));
   else VX_TRY(launch_conv_fwd<16>(A, d->groups, st));
 
-  const int ntiles = L.tf.ntz * L.tf.nty * L.tf.ntx;
+  const int ntiles = L.ntiles_f;
   VX_LAUNCH(jlc_finalize_kernel, dim3(cdiv(3 * rows, 128)), dim3(128), 0, st, (const float*)part_z, 3 * rows, ntiles,
             (float)S, d->eps, stats, (float*)nullptr, (float*)nullptr);
   VX_TRY(check_launch("jlc_finalize_kernel"));
@@ -808,18 +1089,14 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
   const float* stats_o = stats + (size_t)2 * 3 * rows;
   const bool drop = d->training && d->drop_p > 0.f;
 
-  cudaMemsetAsync(acc, 0, sizeof(float) * rows * 2, st);
-  cudaMemsetAsync(acc2, 0, sizeof(float) * 3 * rows * 2, st);
-  cudaMemsetAsync(dw1, 0, sizeof(float) * (size_t)C * CG, st);
-  cudaMemsetAsync(dw3, 0, sizeof(float) * (size_t)C * CG * 27, st);
-  cudaMemsetAsync(dw5, 0, sizeof(float) * (size_t)C * CG * 125, st);
-  cudaMemsetAsync(db1, 0, sizeof(float) * C, st);
-  cudaMemsetAsync(db3, 0, sizeof(float) * C, st);
-  cudaMemsetAsync(db5, 0, sizeof(float) * C, st);
-  cudaMemsetAsync(dfw1, 0, sizeof(float) * (size_t)eC * C, st);
-  cudaMemsetAsync(dfb1, 0, sizeof(float) * eC, st);
-  cudaMemsetAsync(dfw2, 0, sizeof(float) * (size_t)eC * C, st);
-  cudaMemsetAsync(dfb2, 0, sizeof(float) * C, st);
+  {
+    ZeroList zl;
+    zl.add(acc, (size_t)rows * 2); zl.add(acc2, (size_t)3 * rows * 2);
+    zl.add(dw1, (size_t)C * CG); zl.add(dw3, (size_t)C * CG * 27); zl.add(dw5, (size_t)C * CG * 125);
+    zl.add(db1, C); zl.add(db3, C); zl.add(db5, C);
+    zl.add(dfw1, (size_t)eC * C); zl.add(dfb1, eC); zl.add(dfw2, (size_t)eC * C); zl.add(dfb2, C);
+    VX_TRY(zero_many(zl, st));
+  }
   VX_TRY(stats_to_affine(stats_o, aff_a, aff_c, rows, st));
 
   // dh = (W2^T (dy * mask)) * GELU'(hpre)
@@ -869,7 +1146,11 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
   G.gz = gz; G.dO = dO; G.w1 = w1; G.w3 = w3; G.w5 = w5; G.dx = dx;
   G.B = d->B; G.C = C; G.D = d->D; G.H = d->H; G.W = d->W; G.t = L.tf;
   prof_bytes(5.0 * sizeof(float) * (double)L.BCS);       // gz(3), dO in, dx out
-  if (CG == 4) VX_TRY(launch_conv_dgrad<4>(G, d->groups, st));
+  if (L.small) {
+    if (CG == 4) VX_TRY(launch_conv_small_dgrad<4>(G, d->groups, st));
+    else if (CG == 8) VX_TRY(launch_conv_small_dgrad<8>(G, d->groups, st));
+    else VX_TRY(launch_conv_small_dgrad<16>(G, d->groups, st));
+  } else if (CG == 4) VX_TRY(launch_conv_dgrad<4>(G, d->groups, st));
   else if (CG == 8) VX_TRY(launch_conv_dgrad<8>(G, d->groups, st));
   else VX_TRY(launch_conv_dgrad<16>(G, d->groups, st));
 

@@ -175,8 +175,7 @@ extern "C" int vx_mixer_bwd(const vx_mixer_desc* d, const void* const* in, void*
   float* db = (float*)out[M + 1];
   float* dt = (float*)workspace;
   VX_TRY(inorm_rows_bwd(dy, t, stats, nullptr, dt, d->B * Co, d->S, st));
-  cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)Co * K, st);
-  cudaMemsetAsync(db, 0, sizeof(float) * Co, st);
+  { ZeroList zl; zl.add(dW, (size_t)Co * K); zl.add(db, Co); VX_TRY(zero_many(zl, st)); }
   WgBatch wb{}; wb.nprob = 1; wb.B = d->B; wb.S = d->S;
   WgProblem& w = wb.p[0];
   w.dY = dt; w.Co = Co;
@@ -326,9 +325,7 @@ extern "C" int vx_lnpw_bwd(const vx_lnpw_desc* d, const void* const* in, void* c
   float* dbeta = (float*)out[2];
   float* dW = (float*)out[3];
   float* dln = (float*)workspace;
-  cudaMemsetAsync(dgamma, 0, sizeof(float) * d->C_in, st);
-  cudaMemsetAsync(dbeta, 0, sizeof(float) * d->C_in, st);
-  cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)d->C_in * d->C_out, st);
+  { ZeroList zl; zl.add(dgamma, d->C_in); zl.add(dbeta, d->C_in); zl.add(dW, (size_t)d->C_in * d->C_out); VX_TRY(zero_many(zl, st)); }
   PwBatch pb{}; pb.nprob = 1; pb.B = d->B; pb.S = d->S;
   PwProblem& p = pb.p[0];
   p.src[0] = PwSrc{dy, d->C_out}; p.nsrc = 1; p.Ci = d->C_out;

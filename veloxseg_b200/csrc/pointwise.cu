@@ -621,6 +621,35 @@ int stats_to_affine(const float* stats, float* a, float* c, int rows, cudaStream
 }
 
 // ---------------------------------------------------------------------------------------------------
+// zero_many: blockIdx.y = buffer, blockIdx.x strides its elements (16-byte stores where the buffer allows)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) zero_many_kernel(const __grid_constant__ ZeroList Z) {
+  float* p = Z.ptr[blockIdx.y];
+  const unsigned n = Z.n[blockIdx.y];
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+  if ((((uintptr_t)p) & 15) == 0) {
+    const unsigned n4 = n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    for (unsigned i = tid; i < n4; i += nthr) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (unsigned i = (n4 << 2) + tid; i < n; i += nthr) p[i] = 0.f;
+  } else {
+    for (unsigned i = tid; i < n; i += nthr) p[i] = 0.f;
+  }
+}
+
+int zero_many(const ZeroList& z, cudaStream_t stream) {
+  if (z.overflow) { set_error("zero_many: more than %d buffers", VX_ZERO_MAX); return VX_ERR_BAD_DESC; }
+  if (z.count == 0) return VX_OK;
+  unsigned nmax = 0;
+  for (int i = 0; i < z.count; ++i) nmax = z.n[i] > nmax ? z.n[i] : nmax;
+  int gx = cdiv(nmax, 256 * 4 * 4);          // <= 4 float4 per thread for the largest buffer
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  VX_LAUNCH(zero_many_kernel, dim3(gx, z.count), dim3(256), 0, stream, z);
+  return check_launch("zero_many_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // channel-first LayerNorm (thread per voxel, channel loop strides by S so every warp access is coalesced)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) ln_fwd_kernel(const __grid_constant__ LnBatch L) {

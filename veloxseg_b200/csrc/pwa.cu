@@ -791,14 +791,16 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
   const size_t psz[PP_COUNT] = {(size_t)C, (size_t)C, (size_t)P.cqk * C, (size_t)P.cqk, (size_t)P.cqk * C, (size_t)P.cqk,
                                 (size_t)P.cv * C, (size_t)P.cv, (size_t)C * P.cv, (size_t)C, (size_t)C, (size_t)C,
                                 (size_t)P.eC * C, (size_t)P.eC, (size_t)C * P.eC, (size_t)C};
-  for (int m = 0; m < M; ++m)
-    for (int k = 0; k < PP_COUNT; ++k) cudaMemsetAsync(DP(m, k), 0, sizeof(float) * psz[k], st);
   const int nbias = G.heads * G.l * G.l;
-  cudaMemsetAsync(dbiasT, 0, sizeof(float) * nbias, st);
   {
+    ZeroList zl;
+    for (int m = 0; m < M; ++m)
+      for (int k = 0; k < PP_COUNT; ++k) zl.add(DP(m, k), psz[k]);
+    zl.add(dbiasT, nbias);
     // table rows = prod(2n-1)
     const size_t rows = (size_t)(2 * G.n[0] - 1) * (2 * G.n[1] - 1) * (2 * G.n[2] - 1);
-    cudaMemsetAsync(dtable, 0, sizeof(float) * rows * G.heads, st);
+    zl.add(dtable, rows * G.heads);
+    VX_TRY(zero_many(zl, st));
   }
   VX_LAUNCH(pwa_bias_kernel, dim3(cdiv(nbias, 256)), dim3(256), 0, st, table, index, biasT, G.heads, G.l);
   VX_TRY(check_launch("pwa_bias_kernel"));

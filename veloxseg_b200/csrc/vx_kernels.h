@@ -100,6 +100,7 @@ VX_DEV const float* pw_w_row(const PwProblem& P, int co, int ci, int& ld) {
 int pw_tc_forward(const PwBatch& batch, cudaStream_t stream);
 void pw_tc_set(int enabled);
 void jlc_force_vx(int vx);
+void jlc_set_small_max(int s);                            // tuning probe: voxel threshold of the small-volume conv kernels
 void jlc_force_tile(int kind, int tz, int ty);            // tuning probe: 0 = automatic
 void pw_set_thresholds(int small_max_s, int tc_min_s);   // tuning probes; -1 keeps a value
 
@@ -121,6 +122,19 @@ struct WgBatch { WgProblem p[VX_MAX_MODAL * 3]; int nprob; int B; int S; const u
 void set_seed_dev(const void* p);
 const unsigned long long* get_seed_dev();
 int pw_wgrad(const WgBatch& batch, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------------
+// One launch that zeroes every atomically-accumulated gradient buffer of an op (the reference's autograd allocates them
+// zeroed; a cudaMemsetAsync per buffer is ~12-34 extra graph nodes per backward op).
+// ---------------------------------------------------------------------------------------------------
+constexpr int VX_ZERO_MAX = 72;     // >= VX_MAX_MODAL * 16 + 2 (PWA block backward)
+struct ZeroList {
+  float* ptr[VX_ZERO_MAX]; unsigned n[VX_ZERO_MAX]; int count;
+  ZeroList() : count(0) {}
+  void add(void* p, size_t nfloats) { if (p && nfloats && count < VX_ZERO_MAX) { ptr[count] = (float*)p; n[count] = (unsigned)nfloats; ++count; } else if (p && nfloats) overflow = 1; }
+  int overflow = 0;
+};
+int zero_many(const ZeroList& z, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------
 // norms
