@@ -222,3 +222,17 @@ def test_segloss(emu, C, n_out, B, S):
     got = ops.segloss_bwd_raw(emu, 0, up, logits, labels, sums, w)
     for g, r in zip(got, grads):
         assert close(g, r, rtol=2e-4, atol=1e-8), rel_err(g, r)
+
+
+def test_wgrad_tensor_core_layout(emu):
+    """pw_wgrad_tc.cu with the MMA replaced by its software model: staging layout (K-major core matrices, hi/lo split),
+    chunking over (batch, voxels), the all-ones bias row and the TMEM read-back, through the ops that use it."""
+    emu.set_option(9, 8)          # VX_OPT_WGRAD_TC_MIN_S: route every S % 4 == 0 problem to the tensor-core kernel
+    try:
+        test_jlc(emu, 8, 2, 3, (5, 6, 8), 2)
+        test_jlc(emu, 16, 2, 2, (4, 4, 7), 1)
+        test_mixer(emu, (16, 16), 16, (4, 6, 7), 2, True)
+        test_mixer(emu, (32, 16, 8), 20, (3, 5, 8), 2, True)
+        test_pwa_block(emu, *PWA_CASES[1])
+    finally:
+        emu.set_option(9, 512)

@@ -127,13 +127,14 @@ extern "C" size_t vx_profile_report(char*, size_t) { return 0; }
 #endif
 
 extern "C" int vx_set_option(int option, int value) {
+  if (option == VX_OPT_WGRAD_TC_MIN_S) { vx::pw_wgrad_tc_set(-1, value); return VX_OK; }
+  if (option == VX_OPT_JLC_SMALL_MAX_S) { vx::jlc_set_small_max(value); return VX_OK; }
 #ifndef VX_EMU
-  if (option == VX_OPT_PW_TENSOR_CORES) { vx::pw_tc_set(value ? 1 : 0); return VX_OK; }
+  if (option == VX_OPT_PW_TENSOR_CORES) { vx::pw_tc_set(value ? 1 : 0); vx::pw_wgrad_tc_set(value ? 1 : 0, -1); return VX_OK; }
   if (option == VX_OPT_PW_SMALL_MAX_S) { vx::pw_set_thresholds(value, -1); return VX_OK; }
   if (option == VX_OPT_PW_TC_MIN_S) { vx::pw_set_thresholds(-1, value); return VX_OK; }
   if (option == VX_OPT_JLC_TILE_FWD) { vx::jlc_force_tile(0, value >> 8, value & 255); return VX_OK; }
   if (option == 6) { vx::jlc_force_vx(value); return VX_OK; }     // voxels per thread of the JLC conv kernels (probe)
-  if (option == VX_OPT_JLC_SMALL_MAX_S) { vx::jlc_set_small_max(value); return VX_OK; }
   if (option == VX_OPT_JLC_TILE_WGRAD) { vx::jlc_force_tile(1, value >> 8, value & 255); return VX_OK; }
 #endif
   vx::set_error("vx_set_option: unknown option %d", option);

@@ -506,6 +506,10 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_kernel(const __grid_const
 
 int pw_wgrad(const WgBatch& batch, cudaStream_t stream) {
   if (batch.nprob <= 0) return VX_OK;
+  {
+    const int rc = pw_wgrad_tc(batch, stream);
+    if (rc <= 0) return rc;
+  }
   int maxrow = 0, maxblocks = 1, maxfold = 0;
   for (int i = 0; i < batch.nprob; ++i) {
     const WgProblem& P = batch.p[i];

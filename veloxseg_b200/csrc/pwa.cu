@@ -193,13 +193,13 @@ __global__ void pwa_bias_kernel(const float* __restrict__ table, const long long
   biasT[e] = table[(size_t)index[(size_t)tq * l + tk] * heads + h];
 }
 
-// dtable[index[tq][tk]][h] += dbiasT[h][tk][tq]
-__global__ void pwa_bias_bwd_kernel(const float* __restrict__ dbiasT, const long long* __restrict__ index,
+// dtable[index[tq][tk]][h] += dbias[h][tq][tk]     (the gradient buffer is query-major, unlike biasT)
+__global__ void pwa_bias_bwd_kernel(const float* __restrict__ dbias, const long long* __restrict__ index,
                                     float* __restrict__ dtable, int heads, int l) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= heads * l * l) return;
-  const int tq = e % l, tk = (e / l) % l, h = e / (l * l);
-  atomicAdd(dtable + (size_t)index[(size_t)tq * l + tk] * heads + h, dbiasT[e]);
+  const int tk = e % l, tq = (e / l) % l, h = e / (l * l);
+  atomicAdd(dtable + (size_t)index[(size_t)tq * l + tk] * heads + h, dbias[e]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -216,7 +216,8 @@ struct AttnArgs {
   const unsigned long long* seed_dev;
 };
 
-constexpr int ATT_THREADS = 128;
+constexpr int ATT_TS = 4;            // threads per attention row (the key / query loop is dealt to them in turns)
+constexpr int ATT_MAX_THREADS = 512;
 constexpr uint32_t ATT_SITE = 7;
 
 // keep-scales of 4 consecutive keys of one (window,row): one Philox call per 4 score elements
@@ -229,24 +230,42 @@ VX_DEV void attn_drop4(const AttnArgs& A, size_t row, int k4, float inv_keep, fl
   for (int i = 0; i < 4; ++i) ms[i] = ((float)(bits[i] >> 8) * (1.0f / 16777216.0f) < A.drop_p) ? 0.f : inv_keep;
 }
 
+VX_DEV void att_stage(float* dst, const float* src, int n, int tid, int nthr) {
+  for (int i = tid; i < n; i += nthr) vx_cp_async4(dst + i, src + i, true);
+}
+
+// dbias[tq][tk0 .. tk0+3] += v (16-byte vector reduction when the row is 4-element granular)
+VX_DEV void att_red4(float* p, const float (&v)[4]) {
+#ifndef VX_EMU
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+#else
+  for (int i = 0; i < 4; ++i) atomicAdd(p + i, v[i]);
+#endif
+}
+
+// Forward: CTA = one window x a block of query rows; K / V of the window in shared memory; ATT_TS threads share a query
+// row (each takes every ATT_TS-th quad of keys with its own online-softmax state, merged with two shuffle rounds).
 template <int CQ, int CV>
-__global__ void __launch_bounds__(ATT_THREADS) pwa_attn_fwd_kernel(const __grid_constant__ AttnArgs A) {
+__global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_fwd_kernel(const __grid_constant__ AttnArgs A) {
   const int N = blockIdx.y, bh = blockIdx.z, head = bh % A.heads;
   const int L = A.L, l = A.l;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   VX_DYN_SMEM(float, sm);
   float* Ks = sm;            // [L][CQ]
   float* Vs = sm + L * CQ;   // [L][CV]
   const size_t wbase = (size_t)bh * A.Ns + N;
-  const float* Kg = A.K + wbase * L * CQ;
-  const float* Vg = A.V + wbase * L * CV;
-  for (int i = threadIdx.x; i < L * CQ; i += ATT_THREADS) Ks[i] = __ldg(Kg + i);
-  for (int i = threadIdx.x; i < L * CV; i += ATT_THREADS) Vs[i] = __ldg(Vg + i);
-  __syncthreads();
-  const int i = blockIdx.x * ATT_THREADS + threadIdx.x;
-  if (i >= L) return;
+  att_stage(Ks, A.K + wbase * L * CQ, L * CQ, tid, nthr);
+  att_stage(Vs, A.V + wbase * L * CV, L * CV, tid, nthr);
+  vx_cp_async_commit();
+  const int rows = nthr / ATT_TS;
+  const int i_raw = blockIdx.x * rows + tid / ATT_TS, t = tid % ATT_TS;
+  const bool live = i_raw < L;
+  const int i = live ? i_raw : L - 1;
   float q[CQ];
 #pragma unroll
   for (int c = 0; c < CQ; ++c) q[c] = __ldg(A.Q + (wbase * L + i) * CQ + c) * A.scale;
+  vx_cp_async_wait_all();
+  __syncthreads();
   const float* bT = A.biasT + (size_t)head * l * l + (i % l);
   const bool drop = A.drop_p > 0.f;
   const float inv_keep = drop ? 1.0f / (1.0f - A.drop_p) : 1.f;
@@ -255,9 +274,11 @@ __global__ void __launch_bounds__(ATT_THREADS) pwa_attn_fwd_kernel(const __grid_
   float acc[CV];
 #pragma unroll
   for (int c = 0; c < CV; ++c) acc[c] = 0.f;
-  for (int k0 = 0; k0 < L; k0 += 4) {
+  const int nk4 = (L + 3) >> 2;
+  for (int qd = t; qd < nk4; qd += ATT_TS) {
+    const int k0 = qd * 4;
     float ms[4] = {1.f, 1.f, 1.f, 1.f};
-    if (drop) attn_drop4(A, row, k0 >> 2, inv_keep, ms);
+    if (drop) attn_drop4(A, row, qd, inv_keep, ms);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const int k = k0 + kk;
@@ -279,16 +300,37 @@ __global__ void __launch_bounds__(ATT_THREADS) pwa_attn_fwd_kernel(const __grid_
       for (int c = 0; c < CV; ++c) acc[c] = fmaf(pm, Vs[k * CV + c], acc[c]);
     }
   }
-  const float inv = 1.0f / ssum;
+  // merge the ATT_TS partial softmax states of the row
 #pragma unroll
-  for (int c = 0; c < CV; ++c) A.O[row * CV + c] = acc[c] * inv;
-  A.lse[row] = mx + logf(ssum);
+  for (int o = 1; o < ATT_TS; o <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, mx, o);
+    const float s2 = __shfl_xor_sync(0xffffffffu, ssum, o);
+    const float mn = fmaxf(mx, m2);
+    const float c1 = mx == -INFINITY ? 0.f : expf(mx - mn), c2 = m2 == -INFINITY ? 0.f : expf(m2 - mn);
+    ssum = ssum * c1 + s2 * c2;
+#pragma unroll
+    for (int c = 0; c < CV; ++c) {
+      const float a2 = __shfl_xor_sync(0xffffffffu, acc[c], o);
+      acc[c] = acc[c] * c1 + a2 * c2;
+    }
+    mx = mn;
+  }
+  if (live && t == 0) {
+    const float inv = 1.0f / ssum;
+#pragma unroll
+    for (int c = 0; c < CV; ++c) A.O[row * CV + c] = acc[c] * inv;
+    A.lse[row] = mx + logf(ssum);
+  }
 }
 
+// Backward: same CTA shape.  Phase A: a query row (ATT_TS threads, keys dealt in quads) -> dQ and the bias gradient
+// (dbias is laid out [head][tq][tk], so the 4 keys of a quad are one 16-byte reduction); phase B: a key row (queries
+// dealt in turns) -> dK, dV.  P is recomputed from the saved row log-sum-exp.
 template <int CQ, int CV>
-__global__ void __launch_bounds__(ATT_THREADS) pwa_attn_bwd_kernel(const __grid_constant__ AttnArgs A) {
+__global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __grid_constant__ AttnArgs A) {
   const int N = blockIdx.y, bh = blockIdx.z, head = bh % A.heads;
   const int L = A.L, l = A.l;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   VX_DYN_SMEM(float, sm);
   float* Ks = sm;                 // [L][CQ]
   float* Vs = Ks + L * CQ;        // [L][CV]
@@ -297,28 +339,32 @@ __global__ void __launch_bounds__(ATT_THREADS) pwa_attn_bwd_kernel(const __grid_
   float* lses = dOs + L * CV;     // [L]
   float* Dv = lses + L;           // [L]
   const size_t wbase = (size_t)bh * A.Ns + N;
-  for (int i = threadIdx.x; i < L * CQ; i += ATT_THREADS) {
-    Ks[i] = __ldg(A.K + wbase * L * CQ + i);
-    Qs[i] = __ldg(A.Q + wbase * L * CQ + i) * A.scale;
-  }
-  for (int i = threadIdx.x; i < L * CV; i += ATT_THREADS) {
-    Vs[i] = __ldg(A.V + wbase * L * CV + i);
-    dOs[i] = __ldg(A.dO + wbase * L * CV + i);
-  }
-  for (int i = threadIdx.x; i < L; i += ATT_THREADS) {
-    lses[i] = __ldg(A.lse + wbase * L + i);
+  att_stage(Ks, A.K + wbase * L * CQ, L * CQ, tid, nthr);
+  att_stage(Qs, A.Q + wbase * L * CQ, L * CQ, tid, nthr);
+  att_stage(Vs, A.V + wbase * L * CV, L * CV, tid, nthr);
+  att_stage(dOs, A.dO + wbase * L * CV, L * CV, tid, nthr);
+  att_stage(lses, A.lse + wbase * L, L, tid, nthr);
+  vx_cp_async_commit();
+  for (int i = tid; i < L; i += nthr) {
     float d = 0.f;
     for (int c = 0; c < CV; ++c) d = fmaf(__ldg(A.dO + (wbase * L + i) * CV + c), __ldg(A.O + (wbase * L + i) * CV + c), d);
     Dv[i] = d;
   }
+  vx_cp_async_wait_all();
+  __syncthreads();
+  for (int i = tid; i < L * CQ; i += nthr) Qs[i] *= A.scale;
   __syncthreads();
   const bool drop = A.drop_p > 0.f;
   const float inv_keep = drop ? 1.0f / (1.0f - A.drop_p) : 1.f;
-  const int r = blockIdx.x * ATT_THREADS + threadIdx.x;
-  if (r >= L) return;
+  const int rows = nthr / ATT_TS;
+  const int r_raw = blockIdx.x * rows + tid / ATT_TS, t = tid % ATT_TS;
+  const bool live = r_raw < L;
+  const int r = live ? r_raw : L - 1;
   const float* bTh = A.biasT + (size_t)head * l * l;
+  const int nk4 = (L + 3) >> 2;
+  const bool vec = (l & 3) == 0;
 
-  // phase A: this thread owns query row r -> dQ_r and the bias gradient of its row
+  // phase A: query row r -> dQ_r and the bias gradient of its row
   {
     float q[CQ], dq[CQ], dO[CV];
 #pragma unroll
@@ -328,10 +374,12 @@ __global__ void __launch_bounds__(ATT_THREADS) pwa_attn_bwd_kernel(const __grid_
     const float lse = lses[r], Dr = Dv[r];
     const size_t row = wbase * L + r;
     const int tq = r % l;
-    float* dbrow = A.dbiasT + (size_t)head * l * l + tq;
-    for (int k0 = 0; k0 < L; k0 += 4) {
+    float* dbrow = A.dbiasT + ((size_t)head * l + tq) * l;       // [head][tq][tk]
+    for (int qd = t; qd < nk4; qd += ATT_TS) {
+      const int k0 = qd * 4;
       float ms[4] = {1.f, 1.f, 1.f, 1.f};
-      if (drop) attn_drop4(A, row, k0 >> 2, inv_keep, ms);
+      if (drop) attn_drop4(A, row, qd, inv_keep, ms);
+      float dsv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const int k = k0 + kk;
@@ -347,13 +395,28 @@ __global__ void __launch_bounds__(ATT_THREADS) pwa_attn_bwd_kernel(const __grid_
         const float ds = p * (dp * ms[kk] - Dr);
 #pragma unroll
         for (int c = 0; c < CQ; ++c) dq[c] = fmaf(ds, Ks[k * CQ + c], dq[c]);
-        atomicAdd(dbrow + (size_t)tk * l, ds);
+        dsv[kk] = ds;
+      }
+      if (live) {
+        if (vec && k0 + 3 < L) {
+          att_red4(dbrow + (k0 % l), dsv);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            if (k0 + kk < L) atomicAdd(dbrow + ((k0 + kk) % l), dsv[kk]);
+        }
       }
     }
 #pragma unroll
-    for (int c = 0; c < CQ; ++c) A.dQ[row * CQ + c] = dq[c] * A.scale;
+    for (int o = 1; o < ATT_TS; o <<= 1)
+#pragma unroll
+      for (int c = 0; c < CQ; ++c) dq[c] += __shfl_xor_sync(0xffffffffu, dq[c], o);
+    if (live && t == 0) {
+#pragma unroll
+      for (int c = 0; c < CQ; ++c) A.dQ[row * CQ + c] = dq[c] * A.scale;
+    }
   }
-  // phase B: this thread owns key row r -> dK_r, dV_r
+  // phase B: key row r -> dK_r, dV_r
   {
     float kx[CQ], dk[CQ], v[CV], dv[CV];
 #pragma unroll
@@ -361,7 +424,7 @@ __global__ void __launch_bounds__(ATT_THREADS) pwa_attn_bwd_kernel(const __grid_
 #pragma unroll
     for (int c = 0; c < CV; ++c) { v[c] = Vs[r * CV + c]; dv[c] = 0.f; }
     const int tk = r % l;
-    for (int i = 0; i < L; ++i) {
+    for (int i = t; i < L; i += ATT_TS) {
       float s = __ldg(bTh + (size_t)tk * l + (i % l));
 #pragma unroll
       for (int c = 0; c < CQ; ++c) s = fmaf(Qs[i * CQ + c], kx[c], s);
@@ -382,26 +445,39 @@ __global__ void __launch_bounds__(ATT_THREADS) pwa_attn_bwd_kernel(const __grid_
 #pragma unroll
       for (int c = 0; c < CQ; ++c) dk[c] = fmaf(ds, Qs[i * CQ + c], dk[c]);   // Qs carries the 1/sqrt(c) scale
     }
-    const size_t row = wbase * L + r;
 #pragma unroll
-    for (int c = 0; c < CQ; ++c) A.dK[row * CQ + c] = dk[c];
+    for (int o = 1; o < ATT_TS; o <<= 1) {
 #pragma unroll
-    for (int c = 0; c < CV; ++c) A.dV[row * CV + c] = dv[c];
+      for (int c = 0; c < CQ; ++c) dk[c] += __shfl_xor_sync(0xffffffffu, dk[c], o);
+#pragma unroll
+      for (int c = 0; c < CV; ++c) dv[c] += __shfl_xor_sync(0xffffffffu, dv[c], o);
+    }
+    if (live && t == 0) {
+      const size_t row = wbase * L + r;
+#pragma unroll
+      for (int c = 0; c < CQ; ++c) A.dK[row * CQ + c] = dk[c];
+#pragma unroll
+      for (int c = 0; c < CV; ++c) A.dV[row * CV + c] = dv[c];
+    }
   }
 }
 
 template <int CQ, int CV>
 static int launch_attn(const AttnArgs& A, bool bwd, cudaStream_t st) {
-  dim3 grid(cdiv(A.L, ATT_THREADS), A.Ns, A.B * A.heads);
+  // rows per CTA: up to 128 (512 threads); short windows get one CTA of ceil32(L * ATT_TS) threads
+  int threads = ((A.L * ATT_TS + 31) / 32) * 32;
+  if (threads > ATT_MAX_THREADS) threads = ATT_MAX_THREADS;
+  const int rows = threads / ATT_TS;
+  dim3 grid(cdiv(A.L, rows), A.Ns, A.B * A.heads);
   if (!bwd) {
     const size_t smem = sizeof(float) * (size_t)A.L * (CQ + CV);
     VX_SET_SMEM((pwa_attn_fwd_kernel<CQ, CV>), smem);
-    VX_LAUNCH((pwa_attn_fwd_kernel<CQ, CV>), grid, dim3(ATT_THREADS), smem, st, A);
+    VX_LAUNCH((pwa_attn_fwd_kernel<CQ, CV>), grid, dim3(threads), smem, st, A);
     return check_launch("pwa_attn_fwd_kernel");
   }
   const size_t smem = sizeof(float) * (size_t)A.L * (2 * CQ + 2 * CV + 2);
   VX_SET_SMEM((pwa_attn_bwd_kernel<CQ, CV>), smem);
-  VX_LAUNCH((pwa_attn_bwd_kernel<CQ, CV>), grid, dim3(ATT_THREADS), smem, st, A);
+  VX_LAUNCH((pwa_attn_bwd_kernel<CQ, CV>), grid, dim3(threads), smem, st, A);
   return check_launch("pwa_attn_bwd_kernel");
 }
 
@@ -487,60 +563,71 @@ VX_DEV float lerp_weight(int p, int n, int out, int a) {
   return w;
 }
 
+// One CTA per (channel, batch, modality): the channel's gradient volume is staged in shared memory and reduced along x,
+// then y, then z with per-axis weight tables (the trilinear adjoint is separable inside a big window), so every voxel is
+// read once and the work per token no longer grows with the window volume.
 __global__ void __launch_bounds__(256) pwa_scatter_bwd_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ ScatterBwdArgs A) {
-  const int j = blockIdx.y, m = blockIdx.z;
+  const int ch = blockIdx.x, b = blockIdx.y, m = blockIdx.z;
   const int cper = A.cper, Ct = A.Ct;
-  const int Nj = G.Nw[j][0] * G.Nw[j][1] * G.Nw[j][2];
-  const long long total = (long long)G.B * G.heads * Nj * G.l * cper;
-  const bool warp_mode = G.big[j][2] >= 8 && G.vol[j] > 1;
-  const int lane = threadIdx.x & 31;
-  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (warp_mode) e >>= 5;
-  const long long stride = warp_mode ? ((long long)gridDim.x * blockDim.x) >> 5 : (long long)gridDim.x * blockDim.x;
+  const int c = ch % cper, head = (ch / cper) % G.heads, j = ch / (cper * G.heads);
+  const int D = G.D, H = G.H, W = G.W, S = G.S;
   const int B0 = G.big[j][0], B1 = G.big[j][1], B2 = G.big[j][2];
-  for (; e < total; e += stride) {
-    const int c = (int)(e % cper);
-    const int t = (int)((e / cper) % G.l);
-    const int Nloc = (int)((e / ((long long)cper * G.l)) % Nj);
-    const int head = (int)((e / ((long long)cper * G.l * Nj)) % G.heads);
-    const int b = (int)(e / ((long long)cper * G.l * Nj * G.heads));
-    const int wx = Nloc % G.Nw[j][2], wy = (Nloc / G.Nw[j][2]) % G.Nw[j][1], wz = Nloc / (G.Nw[j][2] * G.Nw[j][1]);
-    const int cc = t % G.n[2], bb = (t / G.n[2]) % G.n[1], a = t / (G.n[2] * G.n[1]);
-    const int ch = (j * G.heads + head) * cper + c;
-    const float* p = A.src[m] + ((size_t)b * Ct + ch) * G.S + ((size_t)(wz * B0) * G.H + wy * B1) * G.W + wx * B2;
-    float acc = 0.f;
-    if (G.vol[j] == 1) {
-      acc = __ldg(p + ((size_t)a * G.H + bb) * G.W + cc);
-    } else if (!warp_mode) {
-      for (int pz = 0; pz < B0; ++pz) {
-        const float wzv = lerp_weight(pz, G.n[0], B0, a);
-        if (wzv == 0.f) continue;
-        for (int py = 0; py < B1; ++py) {
-          const float wyv = lerp_weight(py, G.n[1], B1, bb);
-          if (wyv == 0.f) continue;
-          for (int px = 0; px < B2; ++px) {
-            const float wxv = lerp_weight(px, G.n[2], B2, cc);
-            if (wxv != 0.f) acc = fmaf(wzv * wyv * wxv, __ldg(p + ((size_t)pz * G.H + py) * G.W + px), acc);
-          }
-        }
-      }
-    } else {
-      for (int pz = 0; pz < B0; ++pz) {
-        const float wzv = lerp_weight(pz, G.n[0], B0, a);
-        if (wzv == 0.f) continue;
-        for (int py = 0; py < B1; ++py) {
-          const float wyv = lerp_weight(py, G.n[1], B1, bb);
-          if (wyv == 0.f) continue;
-          for (int px = lane; px < B2; px += 32) {
-            const float wxv = lerp_weight(px, G.n[2], B2, cc);
-            if (wxv != 0.f) acc = fmaf(wzv * wyv * wxv, __ldg(p + ((size_t)pz * G.H + py) * G.W + px), acc);
-          }
-        }
-      }
-      acc = warp_sum(acc);
+  const int n0 = G.n[0], n1 = G.n[1], n2 = G.n[2];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const float* src = A.src[m] + ((size_t)b * Ct + ch) * S;
+  float* dtok = A.dtok + ((((size_t)b * G.heads + head) * G.Ns + G.Noff[j]) * G.L + (size_t)m * G.l) * cper + c;
+  const size_t wstride = (size_t)G.L * cper;               // between windows of the scale
+  if (G.vol[j] == 1) {                                       // identity scale: a permuted copy
+    for (int idx = tid; idx < S; idx += nthr) {
+      const int x = idx % W, y = (idx / W) % H, z = idx / (W * H);
+      const int Nloc = ((z / B0) * G.Nw[j][1] + y / B1) * G.Nw[j][2] + x / B2;
+      const int t = ((z % B0) * n1 + (y % B1)) * n2 + (x % B2);
+      dtok[(size_t)Nloc * wstride + (size_t)t * cper] = __ldg(src + idx);
     }
-    if (!warp_mode || lane == 0)
-      A.dtok[((((size_t)b * G.heads + head) * G.Ns + G.Noff[j] + Nloc) * G.L + (size_t)m * G.l + t) * cper + c] = acc;
+    return;
+  }
+  const int W2 = G.Nw[j][2] * n2, H1 = G.Nw[j][1] * n1, D0 = G.Nw[j][0] * n0;   // token-grid extents of the volume
+  VX_DYN_SMEM(float, sm);
+  float* vin = sm;                           // [D][H][W]
+  float* t1 = vin + S;                       // [D][H][W2]
+  float* t2 = t1 + (size_t)D * H * W2;       // [D][H1][W2]
+  float* wX = t2 + (size_t)D * H1 * W2;      // [B2][n2]
+  float* wY = wX + B2 * n2;                  // [B1][n1]
+  float* wZ = wY + B1 * n1;                  // [B0][n0]
+  for (int i = tid; i < S; i += nthr) vx_cp_async4(vin + i, src + i, true);
+  vx_cp_async_commit();
+  for (int i = tid; i < B2 * n2; i += nthr) wX[i] = lerp_weight(i / n2, n2, B2, i % n2);
+  for (int i = tid; i < B1 * n1; i += nthr) wY[i] = lerp_weight(i / n1, n1, B1, i % n1);
+  for (int i = tid; i < B0 * n0; i += nthr) wZ[i] = lerp_weight(i / n0, n0, B0, i % n0);
+  vx_cp_async_wait_all();
+  __syncthreads();
+  for (int o = tid; o < D * H * W2; o += nthr) {
+    const int xo = o % W2, zy = o / W2;
+    const int wx = xo / n2, cc = xo % n2;
+    const float* p = vin + (size_t)zy * W + wx * B2;
+    float acc = 0.f;
+    for (int px = 0; px < B2; ++px) acc = fmaf(wX[px * n2 + cc], p[px], acc);
+    t1[o] = acc;
+  }
+  __syncthreads();
+  for (int o = tid; o < D * H1 * W2; o += nthr) {
+    const int xo = o % W2, yo = (o / W2) % H1, z = o / (W2 * H1);
+    const int wy = yo / n1, bb = yo % n1;
+    const float* p = t1 + ((size_t)z * H + wy * B1) * W2 + xo;
+    float acc = 0.f;
+    for (int py = 0; py < B1; ++py) acc = fmaf(wY[py * n1 + bb], p[(size_t)py * W2], acc);
+    t2[o] = acc;
+  }
+  __syncthreads();
+  for (int o = tid; o < D0 * H1 * W2; o += nthr) {
+    const int xo = o % W2, yo = (o / W2) % H1, zo = o / (W2 * H1);
+    const int wz = zo / n0, a = zo % n0;
+    const float* p = t2 + ((size_t)(wz * B0) * H1 + yo) * W2 + xo;
+    float acc = 0.f;
+    for (int pz = 0; pz < B0; ++pz) acc = fmaf(wZ[pz * n0 + a], p[(size_t)pz * H1 * W2], acc);
+    const int Nloc = (wz * G.Nw[j][1] + yo / n1) * G.Nw[j][2] + xo / n2;
+    const int t = (a * n1 + yo % n1) * n2 + xo % n2;
+    dtok[(size_t)Nloc * wstride + (size_t)t * cper] = acc;
   }
 }
 
@@ -881,15 +968,19 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
   {
     ScatterBwdArgs A{}; A.dtok = dOt; A.Ct = P.cv; A.cper = P.cv_h;
     for (int m = 0; m < M; ++m) A.src[m] = dA + (size_t)m * P.cv * BS;
-    long long maxtotal = 0;
+    // shared memory: the volume, its x- and (x, y)-reduced copies (largest for the smallest pooled window) and the tables
+    size_t fl = 0;
     for (int j = 0; j < G.nb; ++j) {
-      long long t = (long long)B * G.heads * G.Nw[j][0] * G.Nw[j][1] * G.Nw[j][2] * G.l * P.cv_h;
-      if (G.big[j][2] >= 8 && G.vol[j] > 1) t *= 32;
-      maxtotal = t > maxtotal ? t : maxtotal;
+      if (G.vol[j] == 1) continue;
+      const size_t W2 = (size_t)G.Nw[j][2] * G.n[2], H1 = (size_t)G.Nw[j][1] * G.n[1];
+      const size_t f = (size_t)S + (size_t)G.D * G.H * W2 + (size_t)G.D * H1 * W2 + (size_t)G.big[j][2] * G.n[2] +
+                       (size_t)G.big[j][1] * G.n[1] + (size_t)G.big[j][0] * G.n[0];
+      fl = f > fl ? f : fl;
     }
-    int blocks = cdiv(maxtotal, 256);
-    if (blocks > kSMs * 16) blocks = kSMs * 16;
-    VX_LAUNCH(pwa_scatter_bwd_kernel, dim3(blocks, G.nb, M), dim3(256), 0, st, G, A);
+    const size_t smem = fl * sizeof(float);
+    if (smem > 200 * 1024) { set_error("pwa_bwd: level of %d voxels too large for the scatter adjoint", S); return VX_ERR_UNSUPPORTED; }
+    VX_SET_SMEM(pwa_scatter_bwd_kernel, smem);
+    VX_LAUNCH(pwa_scatter_bwd_kernel, dim3(P.cv, B, M), dim3(256), smem, st, G, A);
     VX_TRY(check_launch("pwa_scatter_bwd_kernel"));
   }
   // ---- attention backward

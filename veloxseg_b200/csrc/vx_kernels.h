@@ -122,6 +122,9 @@ struct WgBatch { WgProblem p[VX_MAX_MODAL * 3]; int nprob; int B; int S; const u
 void set_seed_dev(const void* p);
 const unsigned long long* get_seed_dev();
 int pw_wgrad(const WgBatch& batch, cudaStream_t stream);
+// Tensor-core (tcgen05, 3xTF32) variant for the large-voxel problems: 0 = launched, 1 = does not qualify.  pw_wgrad_tc.cu.
+int pw_wgrad_tc(const WgBatch& batch, cudaStream_t stream);
+void pw_wgrad_tc_set(int enabled, int min_s);             // -1 keeps a value
 
 // ---------------------------------------------------------------------------------------------------
 // One launch that zeroes every atomically-accumulated gradient buffer of an op (the reference's autograd allocates them

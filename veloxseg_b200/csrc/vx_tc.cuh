@@ -1,0 +1,64 @@
+// tcgen05 / mbarrier PTX wrappers shared by the tensor-core kernels (pw_tc.cu, pw_wgrad_tc.cu).  kind::tf32, cta_group::1,
+// M = 128, K-major SWIZZLE_NONE operands: 8 x 16 B core matrices, the two K-halves of a k-step LBO bytes apart, groups of
+// 8 rows SBO bytes apart, one descriptor per k-step (8 tf32 along K).
+#pragma once
+#include "vx_common.cuh"
+
+#ifndef VX_EMU
+namespace vx {
+
+constexpr int TC_M = 128;
+
+VX_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// UMMA shared-memory matrix descriptor (SWIZZLE_NONE): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46
+VX_DEV uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// instruction descriptor, kind::tf32: D fp32 (bit 4), A/B tf32 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+VX_DEV uint32_t umma_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+}
+
+VX_DEV void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+VX_DEV void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+VX_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok, spins = 0;
+  do {
+    if (++spins > (1u << 24)) __trap();      // a lost commit must surface as a launch error, never as a hung GPU
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+VX_DEV void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
+
+}  // namespace vx
+#endif
