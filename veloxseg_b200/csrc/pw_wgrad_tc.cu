@@ -26,7 +26,8 @@
 
 namespace vx {
 
-constexpr int WT_THREADS = 128;
+constexpr int WT_THREADS = 256;
+constexpr int WT_U = 6;              // float4 loads in flight per thread and staging round
 constexpr int WT_KC = 64;            // voxels per chunk
 constexpr int WT_KSTEPS = WT_KC / 8;
 
@@ -99,13 +100,13 @@ __global__ void __launch_bounds__(WT_THREADS) pw_wgrad_tc_kernel(const __grid_co
     // ---- A = dY rows
     const int nA = rgA * 8 * (WT_KC / 4);
 #pragma unroll 1
-    for (int i0 = tid; i0 < nA; i0 += 4 * WT_THREADS) {
-      float4 v[4];
-      int so[4];
-      size_t gi[4];
-      bool ok[4];
+    for (int i0 = tid; i0 < nA; i0 += WT_U * WT_THREADS) {
+      float4 v[WT_U];
+      int so[WT_U];
+      size_t gi[WT_U];
+      bool ok[WT_U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < WT_U; ++u) {
         const int i = i0 + u * WT_THREADS;
         int row = 0, quad = 0;
         so[u] = -1; ok[u] = false; gi[u] = 0;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(WT_THREADS) pw_wgrad_tc_kernel(const __grid_co
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < WT_U; ++u) {
         if (so[u] < 0) continue;
         float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
         if (ok[u] && P.y_drop_p > 0.f) {
@@ -140,12 +141,12 @@ __global__ void __launch_bounds__(WT_THREADS) pw_wgrad_tc_kernel(const __grid_co
     // ---- B = X rows (+ the all-ones row)
     const int nBi = rgB * 8 * (WT_KC / 4);
 #pragma unroll 1
-    for (int i0 = tid; i0 < nBi; i0 += 4 * WT_THREADS) {
-      float4 v[4];
-      int so[4], cg[4], gvv[4];
-      bool ok[4];
+    for (int i0 = tid; i0 < nBi; i0 += WT_U * WT_THREADS) {
+      float4 v[WT_U];
+      int so[WT_U], cg[WT_U], gvv[WT_U];
+      bool ok[WT_U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < WT_U; ++u) {
         const int i = i0 + u * WT_THREADS;
         int quad = 0;
         so[u] = -1; ok[u] = false; cg[u] = 0; gvv[u] = 0;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(WT_THREADS) pw_wgrad_tc_kernel(const __grid_co
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < WT_U; ++u) {
         if (so[u] < 0) continue;
         float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
         if (ok[u]) {
@@ -237,16 +238,17 @@ __global__ void __launch_bounds__(WT_THREADS) pw_wgrad_tc_kernel(const __grid_co
 #else
     __syncthreads();
 #endif
-    const int co = warp * 32 + lane;
-    if (warp * 32 < Co) {
+    // a warp reads the 32 TMEM lanes of its quadrant (warp % 4); the two warps of a quadrant split the column groups
+    const int quad = warp & 3, co = quad * 32 + lane;
+    if (quad * 32 < Co) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < rgB * 8; c0 += 8) {
+      for (int c0 = (warp >> 2) * 8; c0 < rgB * 8; c0 += 16) {
         float r[8];
 #ifndef VX_EMU
         uint32_t q[8];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
-                     : "r"(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0)
+                     : "r"(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0)
                      : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll

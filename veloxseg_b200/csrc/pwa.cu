@@ -211,6 +211,7 @@ struct AttnArgs {
   // backward
   const float* dO; float* dQ; float* dK; float* dV; float* dbiasT;
   int B, heads, Ns, L, l;
+  int smem_bias, wpc;      // backward: bias gradient accumulated in shared memory over wpc windows per CTA
   float scale, drop_p;
   uint64_t seed;
   const unsigned long long* seed_dev;
@@ -323,12 +324,15 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_fwd_kernel(const __g
   }
 }
 
-// Backward: same CTA shape.  Phase A: a query row (ATT_TS threads, keys dealt in quads) -> dQ and the bias gradient
-// (dbias is laid out [head][tq][tk], so the 4 keys of a quad are one 16-byte reduction); phase B: a key row (queries
-// dealt in turns) -> dK, dV.  P is recomputed from the saved row log-sum-exp.
+// Backward: same CTA shape.  Phase A: a query row (ATT_TS threads, keys dealt in quads) -> dQ and the bias gradient;
+// phase B: a key row (queries dealt in turns) -> dK, dV.  P is recomputed from the saved row log-sum-exp.
+// Bias gradient (dbias is laid out [head][tq][tk]; L*L score gradients per window fold onto l*l entries):
+//  * l % 4 == 0 (level 2): a thread sums the M modality blocks of its key quad and issues one 16-byte reduction;
+//  * small tables (l*l <= 2048, every other level): the CTA accumulates in shared memory over A.wpc consecutive windows
+//    and flushes l*l coalesced atomics once -- 8-30x fewer L2 atomics than one per score element.
 template <int CQ, int CV>
 __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __grid_constant__ AttnArgs A) {
-  const int N = blockIdx.y, bh = blockIdx.z, head = bh % A.heads;
+  const int bh = blockIdx.z, head = bh % A.heads;
   const int L = A.L, l = A.l;
   const int tid = threadIdx.x, nthr = blockDim.x;
   VX_DYN_SMEM(float, sm);
@@ -338,22 +342,7 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
   float* dOs = Qs + L * CQ;       // [L][CV]
   float* lses = dOs + L * CV;     // [L]
   float* Dv = lses + L;           // [L]
-  const size_t wbase = (size_t)bh * A.Ns + N;
-  att_stage(Ks, A.K + wbase * L * CQ, L * CQ, tid, nthr);
-  att_stage(Qs, A.Q + wbase * L * CQ, L * CQ, tid, nthr);
-  att_stage(Vs, A.V + wbase * L * CV, L * CV, tid, nthr);
-  att_stage(dOs, A.dO + wbase * L * CV, L * CV, tid, nthr);
-  att_stage(lses, A.lse + wbase * L, L, tid, nthr);
-  vx_cp_async_commit();
-  for (int i = tid; i < L; i += nthr) {
-    float d = 0.f;
-    for (int c = 0; c < CV; ++c) d = fmaf(__ldg(A.dO + (wbase * L + i) * CV + c), __ldg(A.O + (wbase * L + i) * CV + c), d);
-    Dv[i] = d;
-  }
-  vx_cp_async_wait_all();
-  __syncthreads();
-  for (int i = tid; i < L * CQ; i += nthr) Qs[i] *= A.scale;
-  __syncthreads();
+  float* sdb = A.smem_bias ? Dv + L : nullptr;    // [l][l]
   const bool drop = A.drop_p > 0.f;
   const float inv_keep = drop ? 1.0f / (1.0f - A.drop_p) : 1.f;
   const int rows = nthr / ATT_TS;
@@ -362,29 +351,42 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
   const int r = live ? r_raw : L - 1;
   const float* bTh = A.biasT + (size_t)head * l * l;
   const int nk4 = (L + 3) >> 2;
-  const bool vec = (l & 3) == 0;
+  const bool vec = (l & 3) == 0 && !sdb;
+  const int tq = r % l;
+  float* dbrow = A.dbiasT + ((size_t)head * l + tq) * l;       // [head][tq][tk]
+  if (sdb) for (int i = tid; i < l * l; i += nthr) sdb[i] = 0.f;
 
-  // phase A: query row r -> dQ_r and the bias gradient of its row
-  {
-    float q[CQ], dq[CQ], dO[CV];
+  const int N1 = min(A.Ns, (int)(blockIdx.y + 1) * A.wpc);
+  for (int N = blockIdx.y * A.wpc; N < N1; ++N) {
+    const size_t wbase = (size_t)bh * A.Ns + N;
+    __syncthreads();
+    att_stage(Ks, A.K + wbase * L * CQ, L * CQ, tid, nthr);
+    att_stage(Qs, A.Q + wbase * L * CQ, L * CQ, tid, nthr);
+    att_stage(Vs, A.V + wbase * L * CV, L * CV, tid, nthr);
+    att_stage(dOs, A.dO + wbase * L * CV, L * CV, tid, nthr);
+    att_stage(lses, A.lse + wbase * L, L, tid, nthr);
+    vx_cp_async_commit();
+    for (int i = tid; i < L; i += nthr) {
+      float d = 0.f;
+      for (int c = 0; c < CV; ++c) d = fmaf(__ldg(A.dO + (wbase * L + i) * CV + c), __ldg(A.O + (wbase * L + i) * CV + c), d);
+      Dv[i] = d;
+    }
+    vx_cp_async_wait_all();
+    __syncthreads();
+    for (int i = tid; i < L * CQ; i += nthr) Qs[i] *= A.scale;
+    __syncthreads();
+
+    // phase A: query row r -> dQ_r and the bias gradient of its row
+    {
+      float q[CQ], dq[CQ], dO[CV];
 #pragma unroll
-    for (int c = 0; c < CQ; ++c) { q[c] = Qs[r * CQ + c]; dq[c] = 0.f; }
+      for (int c = 0; c < CQ; ++c) { q[c] = Qs[r * CQ + c]; dq[c] = 0.f; }
 #pragma unroll
-    for (int c = 0; c < CV; ++c) dO[c] = dOs[r * CV + c];
-    const float lse = lses[r], Dr = Dv[r];
-    const size_t row = wbase * L + r;
-    const int tq = r % l;
-    float* dbrow = A.dbiasT + ((size_t)head * l + tq) * l;       // [head][tq][tk]
-    for (int qd = t; qd < nk4; qd += ATT_TS) {
-      const int k0 = qd * 4;
-      float ms[4] = {1.f, 1.f, 1.f, 1.f};
-      if (drop) attn_drop4(A, row, qd, inv_keep, ms);
-      float dsv[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const int k = k0 + kk;
-        if (k >= L) break;
-        const int tk = k % l;
+      for (int c = 0; c < CV; ++c) dO[c] = dOs[r * CV + c];
+      const float lse = lses[r], Dr = Dv[r];
+      const size_t row = wbase * L + r;
+      // score gradient of key k (and its contribution to dq)
+      auto key = [&](int k, int tk, float mscale) -> float {
         float s = __ldg(bTh + (size_t)tk * l + tq);
 #pragma unroll
         for (int c = 0; c < CQ; ++c) s = fmaf(q[c], Ks[k * CQ + c], s);
@@ -392,73 +394,97 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
         float dp = 0.f;
 #pragma unroll
         for (int c = 0; c < CV; ++c) dp = fmaf(dO[c], Vs[k * CV + c], dp);
-        const float ds = p * (dp * ms[kk] - Dr);
+        const float ds = p * (dp * mscale - Dr);
 #pragma unroll
         for (int c = 0; c < CQ; ++c) dq[c] = fmaf(ds, Ks[k * CQ + c], dq[c]);
-        dsv[kk] = ds;
-      }
-      if (live) {
-        if (vec && k0 + 3 < L) {
-          att_red4(dbrow + (k0 % l), dsv);
-        } else {
+        return ds;
+      };
+      if (vec) {
+        const int lq = l >> 2, M = L / l;
+        for (int qd = t; qd < lq; qd += ATT_TS) {
+          float dsum[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int j = 0; j < M; ++j) {
+            const int k0 = j * l + qd * 4;
+            float ms[4] = {1.f, 1.f, 1.f, 1.f};
+            if (drop) attn_drop4(A, row, k0 >> 2, inv_keep, ms);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            if (k0 + kk < L) atomicAdd(dbrow + ((k0 + kk) % l), dsv[kk]);
+            for (int kk = 0; kk < 4; ++kk) dsum[kk] += key(k0 + kk, qd * 4 + kk, ms[kk]);
+          }
+          if (live) att_red4(dbrow + qd * 4, dsum);
+        }
+      } else {
+        for (int qd = t; qd < nk4; qd += ATT_TS) {
+          const int k0 = qd * 4;
+          float ms[4] = {1.f, 1.f, 1.f, 1.f};
+          if (drop) attn_drop4(A, row, qd, inv_keep, ms);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int k = k0 + kk;
+            if (k >= L) break;
+            const int tk = k % l;
+            const float ds = key(k, tk, ms[kk]);
+            if (live) atomicAdd(sdb ? sdb + tq * l + tk : dbrow + tk, ds);
+          }
         }
       }
+#pragma unroll
+      for (int o = 1; o < ATT_TS; o <<= 1)
+#pragma unroll
+        for (int c = 0; c < CQ; ++c) dq[c] += __shfl_xor_sync(0xffffffffu, dq[c], o);
+      if (live && t == 0) {
+#pragma unroll
+        for (int c = 0; c < CQ; ++c) A.dQ[row * CQ + c] = dq[c] * A.scale;
+      }
     }
+    // phase B: key row r -> dK_r, dV_r
+    {
+      float kx[CQ], dk[CQ], v[CV], dv[CV];
 #pragma unroll
-    for (int o = 1; o < ATT_TS; o <<= 1)
+      for (int c = 0; c < CQ; ++c) { kx[c] = Ks[r * CQ + c]; dk[c] = 0.f; }
 #pragma unroll
-      for (int c = 0; c < CQ; ++c) dq[c] += __shfl_xor_sync(0xffffffffu, dq[c], o);
-    if (live && t == 0) {
+      for (int c = 0; c < CV; ++c) { v[c] = Vs[r * CV + c]; dv[c] = 0.f; }
+      const int tk = r % l;
+      for (int i = t; i < L; i += ATT_TS) {
+        float s = __ldg(bTh + (size_t)tk * l + (i % l));
 #pragma unroll
-      for (int c = 0; c < CQ; ++c) A.dQ[row * CQ + c] = dq[c] * A.scale;
+        for (int c = 0; c < CQ; ++c) s = fmaf(Qs[i * CQ + c], kx[c], s);
+        const float p = expf(s - lses[i]);
+        float msk = 1.f;
+        if (drop) {
+          float ms[4];
+          attn_drop4(A, wbase * L + i, r >> 2, inv_keep, ms);
+          msk = ms[r & 3];
+        }
+        float dp = 0.f;
+#pragma unroll
+        for (int c = 0; c < CV; ++c) dp = fmaf(dOs[i * CV + c], v[c], dp);
+        const float pm = p * msk;
+#pragma unroll
+        for (int c = 0; c < CV; ++c) dv[c] = fmaf(pm, dOs[i * CV + c], dv[c]);
+        const float ds = p * (dp * msk - Dv[i]);
+#pragma unroll
+        for (int c = 0; c < CQ; ++c) dk[c] = fmaf(ds, Qs[i * CQ + c], dk[c]);   // Qs carries the 1/sqrt(c) scale
+      }
+#pragma unroll
+      for (int o = 1; o < ATT_TS; o <<= 1) {
+#pragma unroll
+        for (int c = 0; c < CQ; ++c) dk[c] += __shfl_xor_sync(0xffffffffu, dk[c], o);
+#pragma unroll
+        for (int c = 0; c < CV; ++c) dv[c] += __shfl_xor_sync(0xffffffffu, dv[c], o);
+      }
+      if (live && t == 0) {
+        const size_t row = wbase * L + r;
+#pragma unroll
+        for (int c = 0; c < CQ; ++c) A.dK[row * CQ + c] = dk[c];
+#pragma unroll
+        for (int c = 0; c < CV; ++c) A.dV[row * CV + c] = dv[c];
+      }
     }
   }
-  // phase B: key row r -> dK_r, dV_r
-  {
-    float kx[CQ], dk[CQ], v[CV], dv[CV];
-#pragma unroll
-    for (int c = 0; c < CQ; ++c) { kx[c] = Ks[r * CQ + c]; dk[c] = 0.f; }
-#pragma unroll
-    for (int c = 0; c < CV; ++c) { v[c] = Vs[r * CV + c]; dv[c] = 0.f; }
-    const int tk = r % l;
-    for (int i = t; i < L; i += ATT_TS) {
-      float s = __ldg(bTh + (size_t)tk * l + (i % l));
-#pragma unroll
-      for (int c = 0; c < CQ; ++c) s = fmaf(Qs[i * CQ + c], kx[c], s);
-      const float p = expf(s - lses[i]);
-      float msk = 1.f;
-      if (drop) {
-        float ms[4];
-        attn_drop4(A, wbase * L + i, r >> 2, inv_keep, ms);
-        msk = ms[r & 3];
-      }
-      float dp = 0.f;
-#pragma unroll
-      for (int c = 0; c < CV; ++c) dp = fmaf(dOs[i * CV + c], v[c], dp);
-      const float pm = p * msk;
-#pragma unroll
-      for (int c = 0; c < CV; ++c) dv[c] = fmaf(pm, dOs[i * CV + c], dv[c]);
-      const float ds = p * (dp * msk - Dv[i]);
-#pragma unroll
-      for (int c = 0; c < CQ; ++c) dk[c] = fmaf(ds, Qs[i * CQ + c], dk[c]);   // Qs carries the 1/sqrt(c) scale
-    }
-#pragma unroll
-    for (int o = 1; o < ATT_TS; o <<= 1) {
-#pragma unroll
-      for (int c = 0; c < CQ; ++c) dk[c] += __shfl_xor_sync(0xffffffffu, dk[c], o);
-#pragma unroll
-      for (int c = 0; c < CV; ++c) dv[c] += __shfl_xor_sync(0xffffffffu, dv[c], o);
-    }
-    if (live && t == 0) {
-      const size_t row = wbase * L + r;
-#pragma unroll
-      for (int c = 0; c < CQ; ++c) A.dK[row * CQ + c] = dk[c];
-#pragma unroll
-      for (int c = 0; c < CV; ++c) A.dV[row * CV + c] = dv[c];
-    }
+  if (sdb) {
+    __syncthreads();
+    float* gdb = A.dbiasT + (size_t)head * l * l;
+    for (int i = tid; i < l * l; i += nthr) atomicAdd(gdb + i, sdb[i]);
   }
 }
 
@@ -475,9 +501,19 @@ static int launch_attn(const AttnArgs& A, bool bwd, cudaStream_t st) {
     VX_LAUNCH((pwa_attn_fwd_kernel<CQ, CV>), grid, dim3(threads), smem, st, A);
     return check_launch("pwa_attn_fwd_kernel");
   }
-  const size_t smem = sizeof(float) * (size_t)A.L * (2 * CQ + 2 * CV + 2);
+  AttnArgs Ab = A;
+  Ab.smem_bias = (A.l * A.l <= 2048 && grid.x == 1) ? 1 : 0;      // a row block must see whole windows
+  Ab.wpc = 1;
+  if (Ab.smem_bias) {
+    const long long ctas = (long long)A.Ns * A.B * A.heads;
+    Ab.wpc = (int)(ctas / (2 * kSMs));
+    if (Ab.wpc < 1) Ab.wpc = 1;
+    if (Ab.wpc > 8) Ab.wpc = 8;
+    grid.y = cdiv(A.Ns, Ab.wpc);
+  }
+  const size_t smem = sizeof(float) * ((size_t)A.L * (2 * CQ + 2 * CV + 2) + (Ab.smem_bias ? (size_t)A.l * A.l : 0));
   VX_SET_SMEM((pwa_attn_bwd_kernel<CQ, CV>), smem);
-  VX_LAUNCH((pwa_attn_bwd_kernel<CQ, CV>), grid, dim3(threads), smem, st, A);
+  VX_LAUNCH((pwa_attn_bwd_kernel<CQ, CV>), grid, dim3(threads), smem, st, Ab);
   return check_launch("pwa_attn_bwd_kernel");
 }
 
