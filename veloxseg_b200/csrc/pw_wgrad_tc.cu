@@ -89,109 +89,100 @@ __global__ void __launch_bounds__(WT_THREADS) pw_wgrad_tc_kernel(const __grid_co
     soff_f = (quad >> 1) * BLK + rg * 64 + (q_lo & 1) * 32 + r_lo * 4;
   };
 
+  // One staging round = WT_U items per thread over the concatenated (A rows, B rows) item list: every global load of the
+  // round is issued before the first one is consumed.  When a chunk fits in one round (all level-1 shapes) the loads of the
+  // CTA's NEXT chunk are issued right after the MMAs of the current one, so their latency overlaps the tensor-core work.
+  const int nA = rgA * 8 * (WT_KC / 4), nAB = nA + rgB * 8 * (WT_KC / 4);
+  const int rounds = (nAB + WT_U * WT_THREADS - 1) / (WT_U * WT_THREADS);
+  float4 v[WT_U];
+  int so[WT_U], rw[WT_U], gvv[WT_U];       // shared offset (< 0: no item; B items carry bit 30), row / channel, first voxel
+  bool ok[WT_U];
+  auto load_round = [&](int b, int vbase, int rd) {
+#pragma unroll
+    for (int u = 0; u < WT_U; ++u) {
+      const int i = (rd * WT_U + u) * WT_THREADS + tid;
+      so[u] = -1; ok[u] = false; rw[u] = 0; gvv[u] = 0;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i >= nAB) continue;
+      int quad = 0;
+      if (i < nA) {
+        decode(i, BLKA, rw[u], quad, so[u]);
+        gvv[u] = vbase + quad * 4;
+        ok[u] = rw[u] < Co && gvv[u] < S;
+        if (ok[u]) v[u] = __ldg(reinterpret_cast<const float4*>(P.dY + ((size_t)b * Co + rw[u]) * S + gvv[u]));
+      } else {
+        decode(i - nA, BLKB, rw[u], quad, so[u]);
+        so[u] |= 1 << 30;
+        gvv[u] = vbase + quad * 4;
+        ok[u] = rw[u] < Ci && gvv[u] < S;
+        if (ok[u]) {
+          int c = rw[u], s2 = 0;
+          while (s2 < P.nsrc - 1 && c >= P.src[s2].C) { c -= P.src[s2].C; ++s2; }
+          v[u] = __ldg(reinterpret_cast<const float4*>(P.src[s2].ptr + ((size_t)b * P.src[s2].C + c) * S + gvv[u]));
+        } else if (rw[u] == Ci && P.db && gvv[u] < S) {
+          v[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+      }
+    }
+  };
+  auto store_round = [&](int b) {
+#pragma unroll
+    for (int u = 0; u < WT_U; ++u) {
+      if (so[u] < 0) continue;
+      const bool isB = (so[u] >> 30) & 1;
+      const int off = so[u] & ~(1 << 30);
+      float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      if (ok[u]) {
+        if (!isB) {
+          if (P.y_drop_p > 0.f) {
+            float ms[4];
+            dropout_scale4(P.y_seed + soff, P.y_site, ((uint64_t)b * Co + rw[u]) * (uint64_t)S + gvv[u], P.y_drop_p, yinv, ms);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] *= ms[e];
+          }
+        } else if (P.xpro == PRO_AFFINE) {
+          const int k = b * P.x_bstride + rw[u];
+          const float a = __ldg(P.xa + k), c = __ldg(P.xc + k);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = fmaf(x[e], a, c);
+        } else if (P.xpro == PRO_GELU || P.xpro == PRO_GELU_DROPOUT) {
+          const float4 gq = gelu4_call(make_float4(x[0], x[1], x[2], x[3]));
+          x[0] = gq.x; x[1] = gq.y; x[2] = gq.z; x[3] = gq.w;
+          if (P.xpro == PRO_GELU_DROPOUT) {
+            float ms[4];
+            dropout_scale4(P.x_seed + soff, P.x_site, ((uint64_t)b * Ci + rw[u]) * (uint64_t)S + gvv[u], P.x_drop_p, xinv, ms);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] *= ms[e];
+          }
+        }
+      }
+      float h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_tf32(x[e], h[e], l[e]);
+      *reinterpret_cast<float4*>((isB ? B_hi : A_hi) + off) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>((isB ? B_lo : A_lo) + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+  };
+
   int it = 0;
-  for (int ck = blockIdx.x; ck < B * nchunks; ck += gridDim.x, ++it) {
+  const int total_ck = B * nchunks;
+  bool prefetched = false;
+  if (rounds == 1 && (int)blockIdx.x < total_ck) {
+    load_round(blockIdx.x / nchunks, (blockIdx.x % nchunks) * WT_KC, 0);
+    prefetched = true;
+  }
+  for (int ck = blockIdx.x; ck < total_ck; ck += gridDim.x, ++it) {
     const int b = ck / nchunks, vbase = (ck % nchunks) * WT_KC;
 #ifndef VX_EMU
     if (it > 0) mbar_wait(smem_u32(&mbar), (uint32_t)((it - 1) & 1));     // the previous chunk's MMAs have read the tiles
 #else
     __syncthreads();
 #endif
-    // ---- A = dY rows
-    const int nA = rgA * 8 * (WT_KC / 4);
-#pragma unroll 1
-    for (int i0 = tid; i0 < nA; i0 += WT_U * WT_THREADS) {
-      float4 v[WT_U];
-      int so[WT_U];
-      size_t gi[WT_U];
-      bool ok[WT_U];
-#pragma unroll
-      for (int u = 0; u < WT_U; ++u) {
-        const int i = i0 + u * WT_THREADS;
-        int row = 0, quad = 0;
-        so[u] = -1; ok[u] = false; gi[u] = 0;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < nA) {
-          decode(i, BLKA, row, quad, so[u]);
-          const int gv = vbase + quad * 4;
-          ok[u] = row < Co && gv < S;
-          if (ok[u]) {
-            gi[u] = ((size_t)b * Co + row) * S + gv;
-            v[u] = __ldg(reinterpret_cast<const float4*>(P.dY + gi[u]));
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < WT_U; ++u) {
-        if (so[u] < 0) continue;
-        float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-        if (ok[u] && P.y_drop_p > 0.f) {
-          float ms[4];
-          dropout_scale4(P.y_seed + soff, P.y_site, gi[u], P.y_drop_p, yinv, ms);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) x[e] *= ms[e];
-        }
-        float h[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) split_tf32(x[e], h[e], l[e]);
-        *reinterpret_cast<float4*>(A_hi + so[u]) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4*>(A_lo + so[u]) = make_float4(l[0], l[1], l[2], l[3]);
-      }
+    for (int rd = 0; rd < rounds; ++rd) {
+      if (!(prefetched && rd == 0)) load_round(b, vbase, rd);
+      store_round(b);
     }
-    // ---- B = X rows (+ the all-ones row)
-    const int nBi = rgB * 8 * (WT_KC / 4);
-#pragma unroll 1
-    for (int i0 = tid; i0 < nBi; i0 += WT_U * WT_THREADS) {
-      float4 v[WT_U];
-      int so[WT_U], cg[WT_U], gvv[WT_U];
-      bool ok[WT_U];
-#pragma unroll
-      for (int u = 0; u < WT_U; ++u) {
-        const int i = i0 + u * WT_THREADS;
-        int quad = 0;
-        so[u] = -1; ok[u] = false; cg[u] = 0; gvv[u] = 0;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < nBi) {
-          decode(i, BLKB, cg[u], quad, so[u]);
-          gvv[u] = vbase + quad * 4;
-          ok[u] = cg[u] < Ci && gvv[u] < S;
-          if (ok[u]) {
-            int c = cg[u], s2 = 0;
-            while (s2 < P.nsrc - 1 && c >= P.src[s2].C) { c -= P.src[s2].C; ++s2; }
-            v[u] = __ldg(reinterpret_cast<const float4*>(P.src[s2].ptr + ((size_t)b * P.src[s2].C + c) * S + gvv[u]));
-          } else if (cg[u] == Ci && P.db && gvv[u] < S) {
-            v[u] = make_float4(1.f, 1.f, 1.f, 1.f);
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < WT_U; ++u) {
-        if (so[u] < 0) continue;
-        float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-        if (ok[u]) {
-          if (P.xpro == PRO_AFFINE) {
-            const int k = b * P.x_bstride + cg[u];
-            const float a = __ldg(P.xa + k), c = __ldg(P.xc + k);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] = fmaf(x[e], a, c);
-          } else if (P.xpro == PRO_GELU || P.xpro == PRO_GELU_DROPOUT) {
-            const float4 gq = gelu4_call(make_float4(x[0], x[1], x[2], x[3]));
-            x[0] = gq.x; x[1] = gq.y; x[2] = gq.z; x[3] = gq.w;
-            if (P.xpro == PRO_GELU_DROPOUT) {
-              float ms[4];
-              dropout_scale4(P.x_seed + soff, P.x_site, ((uint64_t)b * Ci + cg[u]) * (uint64_t)S + gvv[u], P.x_drop_p, xinv, ms);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] *= ms[e];
-            }
-          }
-        }
-        float h[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) split_tf32(x[e], h[e], l[e]);
-        *reinterpret_cast<float4*>(B_hi + so[u]) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4*>(B_lo + so[u]) = make_float4(l[0], l[1], l[2], l[3]);
-      }
-    }
+    prefetched = false;
 #ifndef VX_EMU
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -228,6 +219,11 @@ __global__ void __launch_bounds__(WT_THREADS) pw_wgrad_tc_kernel(const __grid_co
         }
     }
 #endif
+    if (rounds == 1 && ck + (int)gridDim.x < total_ck) {
+      const int nk = ck + gridDim.x;
+      load_round(nk / nchunks, (nk % nchunks) * WT_KC, 0);
+      prefetched = true;
+    }
   }
 
   // ---- fold the accumulator tile into global memory
