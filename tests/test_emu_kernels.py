@@ -237,3 +237,36 @@ def test_wgrad_tensor_core_layout(emu):
         test_pwa_block(emu, *PWA_CASES[1])
     finally:
         emu.set_option(9, 512)
+
+
+def test_inorm_register_cached(emu):
+    """Rows of >= 1024 voxels (S % 4 == 0) take the register-cached InstanceNorm kernels."""
+    from veloxseg_b200 import ops
+    O = _oracle()
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 8, 16, 12) * 2 + 0.5
+    add = torch.randn_like(x)
+    y, stats = ops.inorm_fwd_raw(emu, 0, x, add)
+    xr = x.clone().requires_grad_(True)
+    yr = O.instance_norm(xr) + add
+    assert rel_err(y, yr) < 1e-5
+    dy = torch.randn_like(y)
+    assert close(ops.inorm_bwd_raw(emu, 0, dy, x, stats), torch.autograd.grad(yr, xr, dy)[0], rtol=1e-4)
+
+
+def test_lnpw_wide_channels(emu):
+    """PatchMerging shapes of levels 3-4 (few voxels, >= 64 channels) take the channel-split LayerNorm kernel."""
+    from veloxseg_b200 import ops
+    O = _oracle()
+    torch.manual_seed(3)
+    x = torch.randn(2, 72, 3, 4, 5)
+    lw, lb, W = torch.randn(72) * 0.3 + 1, torch.randn(72) * 0.2, torch.randn(10, 72) * 0.2
+    y, xhat, rstd = ops.lnpw_fwd_raw(emu, 0, x, lw, lb, W)
+    xr, lwr, lbr, Wr = [t.clone().requires_grad_(True) for t in (x, lw, lb, W)]
+    yr = O.pointwise(O.layer_norm_cf(xr, lwr, lbr), Wr, None)
+    assert rel_err(y, yr) < 1e-5
+    dy = torch.randn_like(y)
+    gr = torch.autograd.grad(yr, [xr, lwr, lbr, Wr], dy)
+    got = ops.lnpw_bwd_raw(emu, 0, dy, xhat, rstd, lw, lb, W)
+    for i, (g, r) in enumerate(zip(got, gr)):
+        assert close(g, r, rtol=2e-4, atol=2e-5), (i, rel_err(g, r))

@@ -753,19 +753,22 @@ struct ConvWgradArgs {
 template <int CG, int K>
 VX_DEV void wgrad_items(const ConvWgradArgs& A, const float* xs, const float* gsk, float* __restrict__ dwk, int g,
                         int chunk, int item0, int nitems_before, int HZ, int HY, int TXP) {
-  // item = (ci in chunk (4), dz, dy, co-block); accumulators: K dx taps x 4 output channels
-  constexpr int NCB = CG / 4, P = K / 2, K3 = K * K * K;
+  // item = (ci in chunk (4), dz, dy, co-block) x z-split; accumulators: K dx taps x 4 output channels.  With few items
+  // (CG = 4: 140 per chunk) every item is dealt to VS threads that take a share of the tile's z planes each.
+  constexpr int NCB = CG / 4, P = K / 2, K3 = K * K * K, VS = CG == 4 ? 2 : 1;
   const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;
-  const int nitems = 4 * K * K * NCB;
-  for (int it = item0 - nitems_before; it < nitems; it += blockDim.x) {
-    if (it < 0) continue;
+  const int nitems = 4 * K * K * NCB * VS;
+  for (int it0 = item0 - nitems_before; it0 < nitems; it0 += blockDim.x) {
+    if (it0 < 0) continue;
+    const int zs = it0 % VS, it = it0 / VS;
+    const int zlo = zs * TZ / VS, zhi = (zs + 1) * TZ / VS;
     const int cb = it % NCB, dy = (it / NCB) % K, dz = (it / (NCB * K)) % K, ci = it / (NCB * K * K);
     float acc[K][4];
 #pragma unroll
     for (int i = 0; i < K; ++i)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
-    for (int z = 0; z < TZ; ++z) {
+    for (int z = zlo; z < zhi; ++z) {
       for (int y = 0; y < TY; ++y) {
         const float* xrow = xs + ((size_t)(ci * HZ + z + dz + 2 - P) * HY + (y + dy + 2 - P)) * TXP;
         const float* grow = gsk + ((size_t)(cb * 4) * TZ + z) * TY * TX + (size_t)y * TX;
@@ -795,8 +798,10 @@ VX_DEV void wgrad_items(const ConvWgradArgs& A, const float* xs, const float* gs
   }
 }
 
+constexpr int JW_THREADS = 320;      // 280 (item, z-split) tasks per ci-chunk for every CG: one balanced round
+
 template <int CG>
-__global__ void __launch_bounds__(256) jlc_conv_wgrad_kernel(const __grid_constant__ ConvWgradArgs A) {
+__global__ void __launch_bounds__(JW_THREADS) jlc_conv_wgrad_kernel(const __grid_constant__ ConvWgradArgs A) {
   constexpr int NCB = CG / 4;
   const int g = blockIdx.y, b = blockIdx.z;
   const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;
@@ -845,7 +850,8 @@ __global__ void __launch_bounds__(256) jlc_conv_wgrad_kernel(const __grid_consta
     vx_cp_async_wait_all();
     __syncthreads();
     // a flat item list: k=5 items first (heaviest), then k=3, then k=1
-    const int n5 = 4 * 25 * NCB, n3 = 4 * 9 * NCB;
+    constexpr int VS = CG == 4 ? 2 : 1;
+    const int n5 = 4 * 25 * NCB * VS, n3 = 4 * 9 * NCB * VS;
     wgrad_items<CG, 5>(A, xs, gs + (size_t)2 * CG * tvol, A.dw5, g, chunk, tid, 0, HZ, HY, TXP);
     wgrad_items<CG, 3>(A, xs, gs + (size_t)1 * CG * tvol, A.dw3, g, chunk, tid, n5, HZ, HY, TXP);
     wgrad_items<CG, 1>(A, xs, gs, A.dw1, g, chunk, tid, n5 + n3, HZ, HY, TXP);
@@ -964,7 +970,7 @@ static int launch_conv_wgrad(const ConvWgradArgs& A, int groups, cudaStream_t st
   const size_t smem = sizeof(float) * ((size_t)4 * (t.TZ + 4) * (t.TY + 4) * TXP + (size_t)3 * CG * t.TZ * t.TY * t.TX);
   dim3 grid(t.ntz * t.nty * t.ntx, groups, A.B);
   VX_SET_SMEM((jlc_conv_wgrad_kernel<CG>), smem);
-  VX_LAUNCH((jlc_conv_wgrad_kernel<CG>), grid, dim3(256), smem, st, A);
+  VX_LAUNCH((jlc_conv_wgrad_kernel<CG>), grid, dim3(JW_THREADS), smem, st, A);
   return check_launch("jlc_conv_wgrad_kernel");
 }
 

@@ -27,7 +27,7 @@
 
 namespace vx {
 
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;      // two warps per TMEM lane quadrant: they alternate channel groups / column groups
 
 struct PwTcShape { int Kpad, Npad, tmem_cols; };
 
@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
   const int Kpad = shp.Kpad, Npad = shp.Npad;
   const int v0 = blockIdx.x * TC_M;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wq = warp & 3, wp = warp >> 2;          // voxel quadrant (32 rows of the tile), half of the CTA
 
   VX_DYN_SMEM(float, sm);
   float* A_hi = sm;                                  // [Kpad/8][16 voxel groups][2 k-halves][8 voxels][4 k]
@@ -72,8 +73,9 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
     const int cw = ((lane >> 2) & 1) + 2 * (r >> 1);          // chunk within the warp's 4
     const int ngroups = Kpad >> 3;
     constexpr int U = 2;                                      // channel groups per batch of loads
+    const int gh = (ngroups + 1) >> 1, gbeg = wp * gh, gend = min(ngroups, gbeg + gh);   // this half's channel groups
 #pragma unroll 1
-    for (int g0 = 0; g0 < ngroups; g0 += U) {
+    for (int g0 = gbeg; g0 < gend; g0 += U) {
       float x[U][2][4];
       float pa[U], pc[U];
       bool live[U];
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int ci = (g0 + u) * 8 + k;
-        live[u] = (g0 + u) < ngroups && ci < Ci;
+        live[u] = (g0 + u) < gend && ci < Ci;
         const float* xrow = P.src[0].ptr;
         if (live[u]) {
           int c = ci, sidx = 0;
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
         }
 #pragma unroll
         for (int rep = 0; rep < 2; ++rep) {
-          const int v = v0 + (warp * 4 + cw + rep * 16) * 4;
+          const int v = v0 + (wq * 4 + cw + rep * 16) * 4;
 #pragma unroll
           for (int i = 0; i < 4; ++i) x[u][rep][i] = 0.f;
           if (live[u]) {
@@ -112,11 +114,11 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
       // phase 2: prologue, split, transposing stores
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (g0 + u >= ngroups) break;
+        if (g0 + u >= gend) break;
         const int ci = (g0 + u) * 8 + k;
 #pragma unroll
         for (int rep = 0; rep < 2; ++rep) {
-          const int chunk = warp * 4 + cw + rep * 16;
+          const int chunk = wq * 4 + cw + rep * 16;
           const int v = v0 + chunk * 4;
           float* xx = x[u][rep];
           if (live[u]) {
@@ -222,13 +224,13 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
   // global read first, then the arithmetic, then the stores (as far as the compiler knows the stores may alias the
   // residual tensors, so the order has to be explicit for the loads to overlap).
   {
-    const int v = v0 + warp * 32 + lane;
+    const int v = v0 + wq * 32 + lane;
     const bool vok = v < S;
     const float dinv = P.drop_p > 0.f ? 1.0f / (1.0f - P.drop_p) : 1.f;
     const bool heavy = P.act == 1 || P.mulgrad || P.drop_p > 0.f;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < Npad; c0 += 8) {
+    for (int c0 = wp * 8; c0 < Npad; c0 += 16) {
       uint32_t r[8];
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
