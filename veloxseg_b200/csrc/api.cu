@@ -44,6 +44,51 @@ void prof_scope(const char* fmt, ...) {
 }
 
 #ifndef VX_EMU
+// ---- weight-gradient side streams: one per (device, caller stream), created on first use
+struct SideCtx { cudaStream_t side; cudaEvent_t fork, join; bool forked; };
+static std::mutex g_side_mu;
+static std::map<std::pair<int, cudaStream_t>, SideCtx> g_side;
+static int g_side_on = 1;
+void side_set(int enabled) { g_side_on = enabled; }
+
+static SideCtx* side_ctx(cudaStream_t main) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  auto key = std::make_pair(dev, main);
+  auto it = g_side.find(key);
+  if (it == g_side.end()) {
+    SideCtx c{};
+    if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming);
+    c.forked = false;
+    it = g_side.emplace(key, c).first;
+  }
+  return &it->second;
+}
+
+cudaStream_t side_fork(cudaStream_t main) {
+  if (!g_side_on) return main;
+  SideCtx* c = side_ctx(main);
+  if (!c) return main;
+  if (cudaEventRecord(c->fork, main) != cudaSuccess || cudaStreamWaitEvent(c->side, c->fork, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return main;
+  }
+  c->forked = true;
+  return c->side;
+}
+
+void side_join(cudaStream_t main) {
+  if (!g_side_on) return;
+  SideCtx* c = side_ctx(main);
+  if (!c || !c->forked) return;
+  cudaEventRecord(c->join, c->side);
+  cudaStreamWaitEvent(main, c->join, 0);
+  c->forked = false;
+}
+
 struct ProfRec { std::string key; cudaEvent_t a, b; double bytes; };
 static thread_local double g_next_bytes = 0.0;
 static std::mutex g_prof_mu;
@@ -120,7 +165,12 @@ extern "C" size_t vx_profile_report(char* buf, size_t cap) {
   return out.size() + 1;
 }
 #else
-namespace vx { void prof_bytes(double) {} }
+namespace vx {
+void prof_bytes(double) {}
+cudaStream_t side_fork(cudaStream_t main) { return main; }
+void side_join(cudaStream_t) {}
+void side_set(int) {}
+}
 extern "C" int vx_profile_enable(int) { return 0; }
 extern "C" void vx_profile_reset(void) {}
 extern "C" size_t vx_profile_report(char*, size_t) { return 0; }
@@ -129,6 +179,7 @@ extern "C" size_t vx_profile_report(char*, size_t) { return 0; }
 extern "C" int vx_set_option(int option, int value) {
   if (option == VX_OPT_WGRAD_TC_MIN_S) { vx::pw_wgrad_tc_set(-1, value); return VX_OK; }
   if (option == VX_OPT_JLC_SMALL_MAX_S) { vx::jlc_set_small_max(value); return VX_OK; }
+  if (option == VX_OPT_SIDE_WGRAD) { vx::side_set(value ? 1 : 0); return VX_OK; }
 #ifndef VX_EMU
   if (option == VX_OPT_PW_TENSOR_CORES) { vx::pw_tc_set(value ? 1 : 0); vx::pw_wgrad_tc_set(value ? 1 : 0, -1); return VX_OK; }
   if (option == VX_OPT_PW_SMALL_MAX_S) { vx::pw_set_thresholds(value, -1); return VX_OK; }

@@ -1064,6 +1064,7 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
   set_seed_dev(d->seed_offset);
   if (!workspace || workspace_bytes < L.total) { set_error("jlc_bwd: workspace %zu < %zu", workspace_bytes, L.total); return VX_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
+  SideJoin side_guard(st);
   char* ws = (char*)workspace;
   const int CG = d->C / d->groups, eC = d->expansion * d->C, C = d->C;
   const int rows = (int)L.rows, S = (int)L.S;
@@ -1115,15 +1116,7 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
     p.mulgrad = hpre;
     VX_TRY(pw_forward(pb, st));
   }
-  // dohat = W1^T dh
-  {
-    PwBatch pb{}; pb.nprob = 1; pb.B = d->B; pb.S = S;
-    PwProblem& p = pb.p[0];
-    p.src[0] = PwSrc{dh, eC}; p.nsrc = 1; p.Ci = eC;
-    p.seg[0] = PwSeg{fw1, nullptr, C, eC, dohat}; p.nseg = 1; p.Co = C; p.transposed = 1;
-    VX_TRY(pw_forward(pb, st));
-  }
-  // dW2 = (dy*mask) GELU(hpre)^T ; dW1 = dh IN(o)^T
+  // dW2 = (dy*mask) GELU(hpre)^T ; dW1 = dh IN(o)^T   (side stream: overlaps everything below)
   {
     WgBatch wb{}; wb.nprob = 2; wb.B = d->B; wb.S = S;
     WgProblem& a = wb.p[0];
@@ -1135,6 +1128,14 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
     b2.xa = aff_a; b2.xc = aff_c; b2.x_bstride = C;
     b2.dW = dfw1; b2.ld = C; b2.db = dfb1;
     VX_TRY(pw_wgrad(wb, st));
+  }
+  // dohat = W1^T dh
+  {
+    PwBatch pb{}; pb.nprob = 1; pb.B = d->B; pb.S = S;
+    PwProblem& p = pb.p[0];
+    p.src[0] = PwSrc{dh, eC}; p.nsrc = 1; p.Ci = eC;
+    p.seg[0] = PwSeg{fw1, nullptr, C, eC, dohat}; p.nseg = 1; p.Co = C; p.transposed = 1;
+    VX_TRY(pw_forward(pb, st));
   }
   prof_bytes(2.0 * sizeof(float) * (double)L.BCS);
   VX_LAUNCH(jlc_bwd_a_kernel, dim3(L.nchunk, rows), dim3(256), 0, st, (const float*)dohat, o, stats_o, acc, S, L.chunk);
@@ -1148,6 +1149,16 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
             (const float*)acc2, gz, rows, S);
   VX_TRY(check_launch("jlc_bwd_c_kernel"));
 
+  // weight gradients first, on the side stream (forked here, after gz is complete): dgrad then runs beside them
+  cudaStream_t st_w = side_fork(st);
+  ConvWgradArgs Wg{};
+  Wg.x = x; Wg.gz = gz; Wg.dw1 = dw1; Wg.db1 = db1; Wg.dw3 = dw3; Wg.db3 = db3; Wg.dw5 = dw5; Wg.db5 = db5;
+  Wg.B = d->B; Wg.C = C; Wg.D = d->D; Wg.H = d->H; Wg.W = d->W; Wg.t = L.tw;
+  prof_bytes(4.0 * sizeof(float) * (double)L.BCS);       // x, gz(3) in (weight gradients are KBs)
+  if (CG == 4) VX_TRY(launch_conv_wgrad<4>(Wg, d->groups, st_w));
+  else if (CG == 8) VX_TRY(launch_conv_wgrad<8>(Wg, d->groups, st_w));
+  else VX_TRY(launch_conv_wgrad<16>(Wg, d->groups, st_w));
+
   ConvDgradArgs G{};
   G.gz = gz; G.dO = dO; G.w1 = w1; G.w3 = w3; G.w5 = w5; G.dx = dx;
   G.B = d->B; G.C = C; G.D = d->D; G.H = d->H; G.W = d->W; G.t = L.tf;
@@ -1160,12 +1171,5 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
   else if (CG == 8) VX_TRY(launch_conv_dgrad<8>(G, d->groups, st));
   else VX_TRY(launch_conv_dgrad<16>(G, d->groups, st));
 
-  ConvWgradArgs Wg{};
-  Wg.x = x; Wg.gz = gz; Wg.dw1 = dw1; Wg.db1 = db1; Wg.dw3 = dw3; Wg.db3 = db3; Wg.dw5 = dw5; Wg.db5 = db5;
-  Wg.B = d->B; Wg.C = C; Wg.D = d->D; Wg.H = d->H; Wg.W = d->W; Wg.t = L.tw;
-  prof_bytes(4.0 * sizeof(float) * (double)L.BCS);       // x, gz(3) in (weight gradients are KBs)
-  if (CG == 4) VX_TRY(launch_conv_wgrad<4>(Wg, d->groups, st));
-  else if (CG == 8) VX_TRY(launch_conv_wgrad<8>(Wg, d->groups, st));
-  else VX_TRY(launch_conv_wgrad<16>(Wg, d->groups, st));
   return VX_OK;
 }

@@ -166,6 +166,7 @@ extern "C" int vx_mixer_bwd(const vx_mixer_desc* d, const void* const* in, void*
   const size_t need = vx_mixer_workspace(d);
   if (!workspace || workspace_bytes < need) { set_error("mixer_bwd: workspace %zu < %zu", workspace_bytes, need); return VX_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
+  SideJoin side_guard(st);
   const int M = d->n_streams, Co = d->C_out;
   const float* dy = (const float*)in[0];
   const float* W = (const float*)in[M + 1];
@@ -315,6 +316,7 @@ extern "C" int vx_lnpw_bwd(const vx_lnpw_desc* d, const void* const* in, void* c
   set_seed_dev(nullptr);
   prof_scope("lnpw_bwd B%d Ci%d Co%d S%d", d->B, d->C_in, d->C_out, d->S);
   cudaStream_t st = (cudaStream_t)stream;
+  SideJoin side_guard(st);
   const float* dy = (const float*)in[0];
   const float* xhat = (const float*)in[1];
   const float* rstd = (const float*)in[2];

@@ -504,8 +504,9 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_kernel(const __grid_const
   }
 }
 
-int pw_wgrad(const WgBatch& batch, cudaStream_t stream) {
+int pw_wgrad(const WgBatch& batch, cudaStream_t main_stream) {
   if (batch.nprob <= 0) return VX_OK;
+  cudaStream_t stream = side_fork(main_stream);      // joined by the SideJoin of the calling backward op
   {
     const int rc = pw_wgrad_tc(batch, stream);
     if (rc <= 0) return rc;

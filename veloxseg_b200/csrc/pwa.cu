@@ -881,6 +881,7 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
   if (!workspace || workspace_bytes < P.total) { set_error("pwa_bwd: workspace %zu < %zu", workspace_bytes, P.total); return VX_ERR_WORKSPACE; }
   const PwaGeo& G = P.G;
   cudaStream_t st = (cudaStream_t)stream;
+  SideJoin side_guard(st);
   char* ws = (char*)workspace;
   const int M = G.M, B = G.B, S = G.S, C = P.C;
   const size_t BS = (size_t)B * S;

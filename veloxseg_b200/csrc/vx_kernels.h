@@ -127,6 +127,22 @@ int pw_wgrad_tc(const WgBatch& batch, cudaStream_t stream);
 void pw_wgrad_tc_set(int enabled, int min_s);             // -1 keeps a value
 
 // ---------------------------------------------------------------------------------------------------
+// Weight-gradient side stream.  Inside a backward op the weight gradients are leaves (nothing in the op consumes them)
+// while the data gradients form the chain the next op waits for, and every kernel here is a sub-wave grid.  side_fork()
+// returns a library-owned stream that has been made to wait for everything enqueued on `main` so far; the weight-gradient
+// launchers run there.  SideJoin (one per backward entry point) makes `main` wait for it before the op returns, so callers
+// see ordinary single-stream semantics; under CUDA-graph capture the fork/join become parallel graph branches.
+// ---------------------------------------------------------------------------------------------------
+cudaStream_t side_fork(cudaStream_t main);
+void side_join(cudaStream_t main);
+void side_set(int enabled);
+struct SideJoin {
+  cudaStream_t st;
+  explicit SideJoin(cudaStream_t s) : st(s) {}
+  ~SideJoin() { side_join(st); }
+};
+
+// ---------------------------------------------------------------------------------------------------
 // One launch that zeroes every atomically-accumulated gradient buffer of an op (the reference's autograd allocates them
 // zeroed; a cudaMemsetAsync per buffer is ~12-34 extra graph nodes per backward op).
 // ---------------------------------------------------------------------------------------------------
