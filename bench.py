@@ -189,7 +189,11 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
     if rank == 0:
         rows = lib.profile_report()          # (scope, kernel, launches, total_ms, algorithmic_bytes)
+        tl = lib.profile_timeline()
         lib.profile(False)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "timeline.json"), "w") as f:      # tools/timeline_digest.py reads it
+            json.dump(tl, f)
         rows.sort(key=lambda r: -r[3])
         ours_ms = sum(r[3] for r in rows) / nprof
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -59,6 +59,8 @@ uint64_t vx_launch_count(void);
 int vx_profile_enable(int on);
 void vx_profile_reset(void);
 size_t vx_profile_report(char* buf, size_t cap);
+/* one line per recorded launch: "scope|kernel|start_us|dur_us" (device timeline over all streams used) */
+size_t vx_profile_timeline(char* buf, size_t cap);
 
 /* ---------------------------------------------------------------------------------------------------
  * JLC block — replaces JLC.forward, model/components/conv_blocks.py:41-75 (and autograd's backward of it).

@@ -190,7 +190,8 @@ def test_pwa_block(emu, size, C, mb, ms, heads, mdh, M, e, B):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("src,dst", [((3, 3, 3), (12, 12, 12)), ((2, 5, 4), (8, 10, 8)), ((6, 6, 6), (12, 12, 12)), ((1, 3, 2), (4, 6, 8))])
+@pytest.mark.parametrize("src,dst", [((3, 3, 3), (12, 12, 12)), ((2, 5, 4), (8, 10, 8)), ((6, 6, 6), (12, 12, 12)), ((1, 3, 2), (4, 6, 8)),
+                                     ((3, 4, 5), (32, 32, 32))])      # last: long rows -> the row-staged adjoint pass
 def test_resize_trilinear(emu, src, dst):
     import torch.nn.functional as F
     from veloxseg_b200 import ops

@@ -67,7 +67,7 @@ class LnpwDesc(C.Structure):
 # every symbol include/veloxseg_abi.h declares
 SYMBOLS = [
     "vx_version", "vx_last_error_string", "vx_launch_count", "vx_set_option", "vx_profile_enable", "vx_profile_reset",
-    "vx_profile_report",
+    "vx_profile_report", "vx_profile_timeline",
     "vx_jlc_workspace", "vx_jlc_fwd", "vx_jlc_bwd",
     "vx_mixer_workspace", "vx_mixer_fwd", "vx_mixer_bwd",
     "vx_inorm_fwd", "vx_inorm_bwd",
@@ -108,6 +108,8 @@ class VxLib:
         self.c.vx_launch_count.restype = C.c_uint64
         self.c.vx_profile_report.restype = C.c_size_t
         self.c.vx_profile_report.argtypes = [C.c_char_p, C.c_size_t]
+        self.c.vx_profile_timeline.restype = C.c_size_t
+        self.c.vx_profile_timeline.argtypes = [C.c_char_p, C.c_size_t]
         for name in ("vx_jlc_workspace", "vx_mixer_workspace", "vx_pwa_workspace", "vx_gram_workspace",
                      "vx_lnpw_workspace", "vx_resize_workspace", "vx_segloss_workspace"):
             getattr(self.c, name).restype = C.c_size_t
@@ -141,6 +143,17 @@ class VxLib:
         for line in buf.value.decode().splitlines():
             scope, kern, cnt, ms, nbytes = line.rsplit("|", 4)
             rows.append((scope, kern, int(cnt), float(ms), float(nbytes)))
+        return rows
+
+    def profile_timeline(self):
+        """[(scope, kernel, start_us, dur_us)] of every launch recorded since the last profile(True)."""
+        n = self.c.vx_profile_timeline(None, 0)
+        buf = C.create_string_buffer(int(n) + 16)
+        self.c.vx_profile_timeline(buf, len(buf))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            scope, kern, st, du = line.rsplit("|", 3)
+            rows.append((scope, kern, float(st), float(du)))
         return rows
 
     def set_option(self, option: int, value: int):

@@ -164,7 +164,28 @@ extern "C" size_t vx_profile_report(char* buf, size_t cap) {
   if (buf && cap > 0) { const size_t n = out.size() < cap - 1 ? out.size() : cap - 1; memcpy(buf, out.data(), n); buf[n] = 0; }
   return out.size() + 1;
 }
+// One line per recorded launch, "scope|kernel|start_us|dur_us", start relative to the first record (device timeline of the
+// profiled region across every stream the library launched on).
+extern "C" size_t vx_profile_timeline(char* buf, size_t cap) {
+  std::lock_guard<std::mutex> lk(vx::g_prof_mu);
+  std::string out;
+  char line[64];
+  if (!vx::g_prof.empty()) {
+    cudaEvent_t t0 = vx::g_prof[0].a;
+    for (auto& r : vx::g_prof) {
+      cudaEventSynchronize(r.b);
+      float st = 0.f, du = 0.f;
+      if (cudaEventElapsedTime(&st, t0, r.a) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (cudaEventElapsedTime(&du, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+      snprintf(line, sizeof(line), "|%.3f|%.3f\n", st * 1e3, du * 1e3);
+      out += r.key + line;
+    }
+  }
+  if (buf && cap > 0) { const size_t n = out.size() < cap - 1 ? out.size() : cap - 1; memcpy(buf, out.data(), n); buf[n] = 0; }
+  return out.size() + 1;
+}
 #else
+extern "C" size_t vx_profile_timeline(char*, size_t) { return 0; }
 namespace vx {
 void prof_bytes(double) {}
 cudaStream_t side_fork(cudaStream_t main) { return main; }

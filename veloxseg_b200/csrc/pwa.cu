@@ -81,19 +81,64 @@ VX_DEV void token_coords(const PwaGeo& G, int j, int Nloc, int t, int& z0, int& 
   x0 = wx * G.big[j][2] + c * G.small[j][2];
 }
 
+// Thread mode (small windows of < 32 voxels): a thread owns one token and walks its cper channels, tokens of a window are
+// consecutive threads.  Reads are then runs along x (the token's small window, next to its neighbour's) instead of one
+// sector per lane, and a token row (cper floats / indices) is written as 16-byte vectors.
+// Warp mode (>= 32 voxels per small window): a warp per (token, channel), lanes over the window.
 __global__ void __launch_bounds__(256) pwa_gather_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ GatherArgs A) {
   const int j = blockIdx.y;
   const int kind = blockIdx.z / G.M, m = blockIdx.z % G.M;
   const int cper = A.cper[kind], Ct = A.Ct[kind];
   const int Nj = G.Nw[j][0] * G.Nw[j][1] * G.Nw[j][2];
-  const long long total = (long long)G.B * G.heads * Nj * G.l * cper;
   const bool warp_mode = G.vol[j] >= 32;
   const int lane = threadIdx.x & 31;
-  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (warp_mode) e >>= 5;
-  const long long stride = warp_mode ? ((long long)gridDim.x * blockDim.x) >> 5 : (long long)gridDim.x * blockDim.x;
   const float* src = A.src[kind][m];
   const int s0 = G.small[j][0], s1 = G.small[j][1], s2 = G.small[j][2];
+  if (!warp_mode) {
+    const long long total = (long long)G.B * G.heads * Nj * G.l;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+      const int t = (int)(e % G.l);
+      const int Nloc = (int)((e / G.l) % Nj);
+      const int head = (int)((e / ((long long)G.l * Nj)) % G.heads);
+      const int b = (int)(e / ((long long)G.l * Nj * G.heads));
+      int z0, y0, x0;
+      token_coords(G, j, Nloc, t, z0, y0, x0);
+      const size_t o = ((((size_t)b * G.heads + head) * G.Ns + G.Noff[j] + Nloc) * G.L + (size_t)m * G.l + t) * cper;
+      const float* p0 = src + ((size_t)b * Ct + (size_t)(j * G.heads + head) * cper) * G.S;
+      const int idx0 = (z0 * G.H + y0) * G.W + x0;
+      for (int c4 = 0; c4 < cper; c4 += 4) {
+        float bv[4];
+        int bi[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float* p = p0 + (size_t)(c4 + cc) * G.S;
+          float best = -INFINITY;
+          int bidx = idx0;
+          for (int dz = 0; dz < s0; ++dz)
+            for (int dy = 0; dy < s1; ++dy)
+              for (int dx = 0; dx < s2; ++dx) {
+                const int idx = idx0 + (dz * G.H + dy) * G.W + dx;
+                const float v = __ldg(p + idx);
+                if (v > best) { best = v; bidx = idx; }
+              }
+          bv[cc] = best; bi[cc] = bidx;
+        }
+        if (c4 + 3 < cper) {
+          *reinterpret_cast<float4*>(A.tok[kind] + o + c4) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+          if (A.arg[kind]) *reinterpret_cast<int4*>(A.arg[kind] + o + c4) = make_int4(bi[0], bi[1], bi[2], bi[3]);
+        } else {
+          for (int cc = 0; cc < 4 && c4 + cc < cper; ++cc) {
+            A.tok[kind][o + c4 + cc] = bv[cc];
+            if (A.arg[kind]) A.arg[kind][o + c4 + cc] = bi[cc];
+          }
+        }
+      }
+    }
+    return;
+  }
+  const long long total = (long long)G.B * G.heads * Nj * G.l * cper;
+  long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
   for (; e < total; e += stride) {
     const int c = (int)(e % cper);
     const int t = (int)((e / cper) % G.l);
@@ -105,35 +150,23 @@ __global__ void __launch_bounds__(256) pwa_gather_kernel(const __grid_constant__
     const int ch = (j * G.heads + head) * cper + c;
     const float* p = src + ((size_t)b * Ct + ch) * G.S;
     float best = -INFINITY;
-    int bidx = (z0 * G.H + y0) * G.W + x0;
-    if (!warp_mode) {
-      for (int dz = 0; dz < s0; ++dz)
-        for (int dy = 0; dy < s1; ++dy)
-          for (int dx = 0; dx < s2; ++dx) {
-            const int idx = ((z0 + dz) * G.H + (y0 + dy)) * G.W + x0 + dx;
-            const float v = __ldg(p + idx);
-            if (v > best) { best = v; bidx = idx; }
-          }
-    } else {
-      int myidx = 0x7fffffff;
-      for (int q = lane; q < G.vol[j]; q += 32) {
-        const int dx = q % s2, dy = (q / s2) % s1, dz = q / (s2 * s1);
-        const int idx = ((z0 + dz) * G.H + (y0 + dy)) * G.W + x0 + dx;
-        const float v = __ldg(p + idx);
-        if (v > best) { best = v; myidx = idx; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, myidx, o);
-        if (ov > best || (ov == best && oi < myidx)) { best = ov; myidx = oi; }
-      }
-      bidx = myidx;
+    int myidx = 0x7fffffff;
+    for (int q = lane; q < G.vol[j]; q += 32) {
+      const int dx = q % s2, dy = (q / s2) % s1, dz = q / (s2 * s1);
+      const int idx = ((z0 + dz) * G.H + (y0 + dy)) * G.W + x0 + dx;
+      const float v = __ldg(p + idx);
+      if (v > best) { best = v; myidx = idx; }
     }
-    if (!warp_mode || lane == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, myidx, o);
+      if (ov > best || (ov == best && oi < myidx)) { best = ov; myidx = oi; }
+    }
+    if (lane == 0) {
       const size_t o = ((((size_t)b * G.heads + head) * G.Ns + G.Noff[j] + Nloc) * G.L + (size_t)m * G.l + t) * cper + c;
       A.tok[kind][o] = best;
-      if (A.arg[kind]) A.arg[kind][o] = bidx;
+      if (A.arg[kind]) A.arg[kind][o] = myidx;
     }
   }
 }
@@ -142,8 +175,8 @@ static int launch_gather(const PwaGeo& G, const GatherArgs& A, cudaStream_t st) 
   long long maxtotal = 0;
   for (int j = 0; j < G.nb; ++j)
     for (int k = 0; k < A.nkind; ++k) {
-      long long t = (long long)G.B * G.heads * G.Nw[j][0] * G.Nw[j][1] * G.Nw[j][2] * G.l * A.cper[k];
-      if (G.vol[j] >= 32) t *= 32;
+      long long t = (long long)G.B * G.heads * G.Nw[j][0] * G.Nw[j][1] * G.Nw[j][2] * G.l;     // thread mode: one per token
+      if (G.vol[j] >= 32) t *= 32LL * A.cper[k];                                                    // warp per (token, channel)
       maxtotal = t > maxtotal ? t : maxtotal;
     }
   int blocks = cdiv(maxtotal, 256);
@@ -161,24 +194,43 @@ struct GatherBwdArgs {
 };
 
 __global__ void __launch_bounds__(256) pwa_gather_bwd_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ GatherBwdArgs A) {
+  // thread = (batch, scale, head, voxel): one 16-byte read of the token's gradient row (and arg-max row) per 4 channels,
+  // channel planes written with the lanes along x
   const int kind = blockIdx.z / G.M, m = blockIdx.z % G.M;
   const int cper = A.cper[kind], Ct = A.Ct[kind];
-  const long long total = (long long)G.B * Ct * G.S;
+  const long long total = (long long)G.B * G.nb * G.heads * G.S;
   float* dst = A.dst[kind][m];
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int idx = (int)(e % G.S);
-    const int ch = (int)((e / G.S) % Ct);
-    const int b = (int)(e / ((long long)G.S * Ct));
-    const int c = ch % cper, head = (ch / cper) % G.heads, j = ch / (cper * G.heads);
+    const int head = (int)((e / G.S) % G.heads);
+    const int j = (int)((e / ((long long)G.S * G.heads)) % G.nb);
+    const int b = (int)(e / ((long long)G.S * G.heads * G.nb));
     const int x = idx % G.W, y = (idx / G.W) % G.H, z = idx / (G.W * G.H);
     const int wz = z / G.big[j][0], wy = y / G.big[j][1], wx = x / G.big[j][2];
     const int a = (z % G.big[j][0]) / G.small[j][0], bb = (y % G.big[j][1]) / G.small[j][1], cc = (x % G.big[j][2]) / G.small[j][2];
     const int Nloc = (wz * G.Nw[j][1] + wy) * G.Nw[j][2] + wx;
     const int t = (a * G.n[1] + bb) * G.n[2] + cc;
-    const size_t o = ((((size_t)b * G.heads + head) * G.Ns + G.Noff[j] + Nloc) * G.L + (size_t)m * G.l + t) * cper + c;
-    float g = 0.f;
-    if (G.vol[j] == 1 || A.arg[kind][o] == idx) g = A.dtok[kind][o];
-    dst[e] = g;
+    const size_t o = ((((size_t)b * G.heads + head) * G.Ns + G.Noff[j] + Nloc) * G.L + (size_t)m * G.l + t) * cper;
+    float* dp = dst + ((size_t)b * Ct + (size_t)(j * G.heads + head) * cper) * G.S + idx;
+    const bool all = G.vol[j] == 1;
+    for (int c4 = 0; c4 < cper; c4 += 4) {
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c4 + 3 < cper) {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(A.dtok[kind] + o + c4));
+        g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+        if (!all) {
+          const int4 av = __ldg(reinterpret_cast<const int4*>(A.arg[kind] + o + c4));
+          if (av.x != idx) g[0] = 0.f;
+          if (av.y != idx) g[1] = 0.f;
+          if (av.z != idx) g[2] = 0.f;
+          if (av.w != idx) g[3] = 0.f;
+        }
+      } else {
+        for (int q = 0; q < 4 && c4 + q < cper; ++q)
+          g[q] = (all || A.arg[kind][o + c4 + q] == idx) ? A.dtok[kind][o + c4 + q] : 0.f;
+      }
+      for (int q = 0; q < 4 && c4 + q < cper; ++q) dp[(size_t)(c4 + q) * G.S] = g[q];
+    }
   }
 }
 
@@ -194,12 +246,22 @@ __global__ void pwa_bias_kernel(const float* __restrict__ table, const long long
 }
 
 // dtable[index[tq][tk]][h] += dbias[h][tq][tk]     (the gradient buffer is query-major, unlike biasT)
-__global__ void pwa_bias_bwd_kernel(const float* __restrict__ dbias, const long long* __restrict__ index,
-                                    float* __restrict__ dtable, int heads, int l) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= heads * l * l) return;
-  const int tk = e % l, tq = (e / l) % l, h = e / (l * l);
-  atomicAdd(dtable + (size_t)index[(size_t)tq * l + tk] * heads + h, dbias[e]);
+// l*l contributions fold onto prod(2n-1) table rows (35 per row at level 2): a CTA histograms its share in shared memory
+// and flushes one atomic per row, instead of l*l contended global atomics.
+__global__ void __launch_bounds__(256) pwa_bias_bwd_kernel(const float* __restrict__ dbias, const long long* __restrict__ index,
+                                                           float* __restrict__ dtable, int heads, int l, int rows) {
+  VX_DYN_SMEM(float, hist);
+  const int h = blockIdx.y;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) hist[i] = 0.f;
+  __syncthreads();
+  const int n = l * l;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+    atomicAdd(hist + (int)index[e], dbias[(size_t)h * n + e]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    const float v = hist[i];
+    if (v != 0.f) atomicAdd(dtable + (size_t)i * heads + h, v);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -231,7 +293,15 @@ VX_DEV void attn_drop4(const AttnArgs& A, size_t row, int k4, float inv_keep, fl
   for (int i = 0; i < 4; ++i) ms[i] = ((float)(bits[i] >> 8) * (1.0f / 16777216.0f) < A.drop_p) ? 0.f : inv_keep;
 }
 
-VX_DEV void att_stage(float* dst, const float* src, int n, int tid, int nthr) {
+// K / V / Q / dO tiles in shared memory are [row][C] with 8 floats of padding after every 4 rows: the ATT_TS threads of a
+// query row walk keys 4 apart (one quad each), which without the skew is a 4-way bank conflict on every K / V read
+// (profiles/r1c_pwa_L2.digest.txt: 2.3e7 conflicts, L1 at 76 % of peak).  Row stride in floats: C, quad stride: 4 C + 8.
+VX_DEV int att_row(int k, int C) { return k * C + (k >> 2) * 8; }
+VX_DEV int att_rows_floats(int L, int C) { return L * C + ((L + 3) >> 2) * 8; }
+VX_DEV void att_stage(float* dst, const float* src, int L, int C, int tid, int nthr) {
+  for (int i = tid; i < L * C; i += nthr) { const int k = i / C; vx_cp_async4(dst + att_row(k, C) + (i - k * C), src + i, true); }
+}
+VX_DEV void att_stage_flat(float* dst, const float* src, int n, int tid, int nthr) {
   for (int i = tid; i < n; i += nthr) vx_cp_async4(dst + i, src + i, true);
 }
 
@@ -252,11 +322,11 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_fwd_kernel(const __g
   const int L = A.L, l = A.l;
   const int tid = threadIdx.x, nthr = blockDim.x;
   VX_DYN_SMEM(float, sm);
-  float* Ks = sm;            // [L][CQ]
-  float* Vs = sm + L * CQ;   // [L][CV]
+  float* Ks = sm;                            // [L][CQ] (padded, att_row)
+  float* Vs = sm + att_rows_floats(L, CQ);   // [L][CV]
   const size_t wbase = (size_t)bh * A.Ns + N;
-  att_stage(Ks, A.K + wbase * L * CQ, L * CQ, tid, nthr);
-  att_stage(Vs, A.V + wbase * L * CV, L * CV, tid, nthr);
+  att_stage(Ks, A.K + wbase * L * CQ, L, CQ, tid, nthr);
+  att_stage(Vs, A.V + wbase * L * CV, L, CV, tid, nthr);
   vx_cp_async_commit();
   const int rows = nthr / ATT_TS;
   const int i_raw = blockIdx.x * rows + tid / ATT_TS, t = tid % ATT_TS;
@@ -284,9 +354,11 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_fwd_kernel(const __g
     for (int kk = 0; kk < 4; ++kk) {
       const int k = k0 + kk;
       if (k >= L) break;
+      const float* kr = Ks + att_row(k, CQ);
+      const float* vr = Vs + att_row(k, CV);
       float s = __ldg(bT + (size_t)(k % l) * l);
 #pragma unroll
-      for (int c = 0; c < CQ; ++c) s = fmaf(q[c], Ks[k * CQ + c], s);
+      for (int c = 0; c < CQ; ++c) s = fmaf(q[c], kr[c], s);
       if (s > mx) {
         const float corr = expf(mx - s);
         ssum *= corr;
@@ -298,7 +370,7 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_fwd_kernel(const __g
       ssum += p;
       const float pm = p * ms[kk];
 #pragma unroll
-      for (int c = 0; c < CV; ++c) acc[c] = fmaf(pm, Vs[k * CV + c], acc[c]);
+      for (int c = 0; c < CV; ++c) acc[c] = fmaf(pm, vr[c], acc[c]);
     }
   }
   // merge the ATT_TS partial softmax states of the row
@@ -336,11 +408,12 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
   const int L = A.L, l = A.l;
   const int tid = threadIdx.x, nthr = blockDim.x;
   VX_DYN_SMEM(float, sm);
-  float* Ks = sm;                 // [L][CQ]
-  float* Vs = Ks + L * CQ;        // [L][CV]
-  float* Qs = Vs + L * CV;        // [L][CQ]  (pre-scaled)
-  float* dOs = Qs + L * CQ;       // [L][CV]
-  float* lses = dOs + L * CV;     // [L]
+  const int fq = att_rows_floats(L, CQ), fv = att_rows_floats(L, CV);
+  float* Ks = sm;                 // [L][CQ] (padded, att_row)
+  float* Vs = Ks + fq;            // [L][CV]
+  float* Qs = Vs + fv;            // [L][CQ]  (pre-scaled)
+  float* dOs = Qs + fq;           // [L][CV]
+  float* lses = dOs + fv;         // [L]
   float* Dv = lses + L;           // [L]
   float* sdb = A.smem_bias ? Dv + L : nullptr;    // [l][l]
   const bool drop = A.drop_p > 0.f;
@@ -360,11 +433,11 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
   for (int N = blockIdx.y * A.wpc; N < N1; ++N) {
     const size_t wbase = (size_t)bh * A.Ns + N;
     __syncthreads();
-    att_stage(Ks, A.K + wbase * L * CQ, L * CQ, tid, nthr);
-    att_stage(Qs, A.Q + wbase * L * CQ, L * CQ, tid, nthr);
-    att_stage(Vs, A.V + wbase * L * CV, L * CV, tid, nthr);
-    att_stage(dOs, A.dO + wbase * L * CV, L * CV, tid, nthr);
-    att_stage(lses, A.lse + wbase * L, L, tid, nthr);
+    att_stage(Ks, A.K + wbase * L * CQ, L, CQ, tid, nthr);
+    att_stage(Qs, A.Q + wbase * L * CQ, L, CQ, tid, nthr);
+    att_stage(Vs, A.V + wbase * L * CV, L, CV, tid, nthr);
+    att_stage(dOs, A.dO + wbase * L * CV, L, CV, tid, nthr);
+    att_stage_flat(lses, A.lse + wbase * L, L, tid, nthr);
     vx_cp_async_commit();
     for (int i = tid; i < L; i += nthr) {
       float d = 0.f;
@@ -373,30 +446,32 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
     }
     vx_cp_async_wait_all();
     __syncthreads();
-    for (int i = tid; i < L * CQ; i += nthr) Qs[i] *= A.scale;
+    for (int i = tid; i < fq; i += nthr) Qs[i] *= A.scale;      // (padding included: harmless)
     __syncthreads();
 
     // phase A: query row r -> dQ_r and the bias gradient of its row
     {
       float q[CQ], dq[CQ], dO[CV];
 #pragma unroll
-      for (int c = 0; c < CQ; ++c) { q[c] = Qs[r * CQ + c]; dq[c] = 0.f; }
+      for (int c = 0; c < CQ; ++c) { q[c] = Qs[att_row(r, CQ) + c]; dq[c] = 0.f; }
 #pragma unroll
-      for (int c = 0; c < CV; ++c) dO[c] = dOs[r * CV + c];
+      for (int c = 0; c < CV; ++c) dO[c] = dOs[att_row(r, CV) + c];
       const float lse = lses[r], Dr = Dv[r];
       const size_t row = wbase * L + r;
       // score gradient of key k (and its contribution to dq)
       auto key = [&](int k, int tk, float mscale) -> float {
+        const float* kr = Ks + att_row(k, CQ);
+        const float* vr = Vs + att_row(k, CV);
         float s = __ldg(bTh + (size_t)tk * l + tq);
 #pragma unroll
-        for (int c = 0; c < CQ; ++c) s = fmaf(q[c], Ks[k * CQ + c], s);
+        for (int c = 0; c < CQ; ++c) s = fmaf(q[c], kr[c], s);
         const float p = expf(s - lse);
         float dp = 0.f;
 #pragma unroll
-        for (int c = 0; c < CV; ++c) dp = fmaf(dO[c], Vs[k * CV + c], dp);
+        for (int c = 0; c < CV; ++c) dp = fmaf(dO[c], vr[c], dp);
         const float ds = p * (dp * mscale - Dr);
 #pragma unroll
-        for (int c = 0; c < CQ; ++c) dq[c] = fmaf(ds, Ks[k * CQ + c], dq[c]);
+        for (int c = 0; c < CQ; ++c) dq[c] = fmaf(ds, kr[c], dq[c]);
         return ds;
       };
       if (vec) {
@@ -440,14 +515,16 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
     {
       float kx[CQ], dk[CQ], v[CV], dv[CV];
 #pragma unroll
-      for (int c = 0; c < CQ; ++c) { kx[c] = Ks[r * CQ + c]; dk[c] = 0.f; }
+      for (int c = 0; c < CQ; ++c) { kx[c] = Ks[att_row(r, CQ) + c]; dk[c] = 0.f; }
 #pragma unroll
-      for (int c = 0; c < CV; ++c) { v[c] = Vs[r * CV + c]; dv[c] = 0.f; }
+      for (int c = 0; c < CV; ++c) { v[c] = Vs[att_row(r, CV) + c]; dv[c] = 0.f; }
       const int tk = r % l;
       for (int i = t; i < L; i += ATT_TS) {
+        const float* qr = Qs + att_row(i, CQ);
+        const float* gr = dOs + att_row(i, CV);
         float s = __ldg(bTh + (size_t)tk * l + (i % l));
 #pragma unroll
-        for (int c = 0; c < CQ; ++c) s = fmaf(Qs[i * CQ + c], kx[c], s);
+        for (int c = 0; c < CQ; ++c) s = fmaf(qr[c], kx[c], s);
         const float p = expf(s - lses[i]);
         float msk = 1.f;
         if (drop) {
@@ -457,13 +534,13 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
         }
         float dp = 0.f;
 #pragma unroll
-        for (int c = 0; c < CV; ++c) dp = fmaf(dOs[i * CV + c], v[c], dp);
+        for (int c = 0; c < CV; ++c) dp = fmaf(gr[c], v[c], dp);
         const float pm = p * msk;
 #pragma unroll
-        for (int c = 0; c < CV; ++c) dv[c] = fmaf(pm, dOs[i * CV + c], dv[c]);
+        for (int c = 0; c < CV; ++c) dv[c] = fmaf(pm, gr[c], dv[c]);
         const float ds = p * (dp * msk - Dv[i]);
 #pragma unroll
-        for (int c = 0; c < CQ; ++c) dk[c] = fmaf(ds, Qs[i * CQ + c], dk[c]);   // Qs carries the 1/sqrt(c) scale
+        for (int c = 0; c < CQ; ++c) dk[c] = fmaf(ds, qr[c], dk[c]);   // Qs carries the 1/sqrt(c) scale
       }
 #pragma unroll
       for (int o = 1; o < ATT_TS; o <<= 1) {
@@ -496,7 +573,8 @@ static int launch_attn(const AttnArgs& A, bool bwd, cudaStream_t st) {
   const int rows = threads / ATT_TS;
   dim3 grid(cdiv(A.L, rows), A.Ns, A.B * A.heads);
   if (!bwd) {
-    const size_t smem = sizeof(float) * (size_t)A.L * (CQ + CV);
+    const size_t pad = (size_t)((A.L + 3) / 4) * 8;
+    const size_t smem = sizeof(float) * ((size_t)A.L * (CQ + CV) + 2 * pad);
     VX_SET_SMEM((pwa_attn_fwd_kernel<CQ, CV>), smem);
     VX_LAUNCH((pwa_attn_fwd_kernel<CQ, CV>), grid, dim3(threads), smem, st, A);
     return check_launch("pwa_attn_fwd_kernel");
@@ -511,7 +589,8 @@ static int launch_attn(const AttnArgs& A, bool bwd, cudaStream_t st) {
     if (Ab.wpc > 8) Ab.wpc = 8;
     grid.y = cdiv(A.Ns, Ab.wpc);
   }
-  const size_t smem = sizeof(float) * ((size_t)A.L * (2 * CQ + 2 * CV + 2) + (Ab.smem_bias ? (size_t)A.l * A.l : 0));
+  const size_t smem = sizeof(float) * ((size_t)A.L * (2 * CQ + 2 * CV + 2) + 4 * (size_t)((A.L + 3) / 4) * 8 +
+                                       (Ab.smem_bias ? (size_t)A.l * A.l : 0));
   VX_SET_SMEM((pwa_attn_bwd_kernel<CQ, CV>), smem);
   VX_LAUNCH((pwa_attn_bwd_kernel<CQ, CV>), grid, dim3(threads), smem, st, Ab);
   return check_launch("pwa_attn_bwd_kernel");
@@ -1028,7 +1107,12 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
     A.B = B; A.heads = G.heads; A.Ns = G.Ns; A.L = G.L; A.l = G.l;
     A.scale = 1.0f / sqrtf((float)P.cq_h); A.drop_p = attn_p; A.seed = d->seed; A.seed_dev = get_seed_dev();
     VX_TRY(dispatch_attn(A, P.cq_h, P.cv_h, true, st));
-    VX_LAUNCH(pwa_bias_bwd_kernel, dim3(cdiv(nbias, 256)), dim3(256), 0, st, (const float*)dbiasT, index, dtable, G.heads, G.l);
+    const int trows = (2 * G.n[0] - 1) * (2 * G.n[1] - 1) * (2 * G.n[2] - 1);
+    int parts = cdiv((long long)G.l * G.l, 256 * 8);           // ~8 contributions per thread
+    if (parts > 32) parts = 32;
+    VX_SET_SMEM(pwa_bias_bwd_kernel, sizeof(float) * (size_t)trows);
+    VX_LAUNCH(pwa_bias_bwd_kernel, dim3(parts, G.heads), dim3(256), sizeof(float) * (size_t)trows, st, (const float*)dbiasT, index,
+              dtable, G.heads, G.l, trows);
     VX_TRY(check_launch("pwa_bias_bwd_kernel"));
   }
   // ---- gather adjoint -> full-resolution dq, dk, dv
@@ -1041,8 +1125,7 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
     A.arg[0] = (const int*)SV(SV_ARGQ); A.arg[1] = (const int*)SV(SV_ARGK); A.arg[2] = (const int*)SV(SV_ARGV);
     for (int m = 0; m < M; ++m) { A.dst[0][m] = dQf(m); A.dst[1][m] = dKf(m); A.dst[2][m] = dVf(m); }
     A.Ct[0] = A.Ct[1] = P.cqk; A.Ct[2] = P.cv; A.cper[0] = A.cper[1] = P.cq_h; A.cper[2] = P.cv_h;
-    const int cmax = P.cqk > P.cv ? P.cqk : P.cv;
-    int blocks = cdiv((long long)B * cmax * S, 256);
+    int blocks = cdiv((long long)B * G.nb * G.heads * S, 256);      // one thread per (batch, scale, head, voxel)
     if (blocks > kSMs * 16) blocks = kSMs * 16;
     VX_LAUNCH(pwa_gather_bwd_kernel, dim3(blocks, 1, 3 * M), dim3(256), 0, st, G, A);
     VX_TRY(check_launch("pwa_gather_bwd_kernel"));

@@ -45,6 +45,100 @@ __global__ void __launch_bounds__(256) resize_fwd_kernel(const __grid_constant__
   }
 }
 
+// Forward, W % 4 == 0: CTA = (8 output rows, Z, plane); the x-axis taps (index, weight) are tabulated once per CTA, a thread
+// produces 4 consecutive outputs of one row and stores them as one float4 -- the per-voxel kernel above spends ~150
+// instructions per output on index decoding and three float divisions; this one is bound by the 4-byte-per-voxel write.
+constexpr int RS_ROWS = 8;
+__global__ void __launch_bounds__(256) resize_fwd_rows_kernel(const __grid_constant__ ResizeArgs A) {
+  VX_DYN_SMEM(float, sm);
+  int* c0t = reinterpret_cast<int*>(sm);       // [W]
+  float* wct = sm + A.W;                       // [W]
+  for (int X = threadIdx.x; X < A.W; X += blockDim.x) {
+    int c0, c1; float wc;
+    lerp_ac(X, A.w, A.W, c0, c1, wc);
+    c0t[X] = c0 | (c1 << 16);
+    wct[X] = wc;
+  }
+  __syncthreads();
+  const int nq = A.W >> 2;
+  const int Z = blockIdx.y, pl = blockIdx.z;
+  int a0, a1; float wa;
+  lerp_ac(Z, A.d, A.D, a0, a1, wa);
+  const float* p = A.x + (size_t)pl * A.d * A.h * A.w;
+  for (int it = threadIdx.x; it < RS_ROWS * nq; it += blockDim.x) {
+    const int Y = blockIdx.x * RS_ROWS + it / nq, xq = it % nq;
+    if (Y >= A.H) continue;
+    int b0, b1; float wb;
+    lerp_ac(Y, A.h, A.H, b0, b1, wb);
+    const float* r00 = p + ((size_t)a0 * A.h + b0) * A.w;
+    const float* r01 = p + ((size_t)a0 * A.h + b1) * A.w;
+    const float* r10 = p + ((size_t)a1 * A.h + b0) * A.w;
+    const float* r11 = p + ((size_t)a1 * A.h + b1) * A.w;
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int X = xq * 4 + i;
+      const int cc = c0t[X], c0 = cc & 0xffff, c1 = cc >> 16;
+      const float wc = wct[X], uc = 1.f - wc;
+      // same association as the per-voxel kernel: x first, then y, then z
+      const float v00 = uc * __ldg(r00 + c0) + wc * __ldg(r00 + c1), v01 = uc * __ldg(r01 + c0) + wc * __ldg(r01 + c1);
+      const float v10 = uc * __ldg(r10 + c0) + wc * __ldg(r10 + c1), v11 = uc * __ldg(r11 + c0) + wc * __ldg(r11 + c1);
+      o[i] = (1.f - wa) * ((1.f - wb) * v00 + wb * v01) + wa * ((1.f - wb) * v10 + wb * v11);
+    }
+    *reinterpret_cast<float4*>(A.y + (((size_t)pl * A.D + Z) * A.H + Y) * A.W + xq * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// First adjoint pass (W -> w, inner == 1) for long rows: persistent CTAs; a block of 64 rows is staged in shared memory with
+// coalesced loads (row stride P + 1: conflict-free for threads that own different rows), the weight table is built once
+// per CTA, a thread owns one (row, j) output.  The generic kernel below reads a row per thread: 96-float strides.
+constexpr int RA_ROWS = 64;
+__global__ void __launch_bounds__(256) resize_adjoint_rows_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                  long long rows, int P, int n) {
+  VX_DYN_SMEM(float, sm);
+  float* wt = sm;                          // [n][P]
+  int* lohi = reinterpret_cast<int*>(sm + (size_t)n * P);      // [n] lo | hi << 16
+  float* tile = sm + (size_t)n * P + n;    // [RA_ROWS][P + 1]
+  for (int e = threadIdx.x; e < n * P; e += blockDim.x) {
+    const int j = e / P, p = e % P;
+    int i0, i1; float w1;
+    lerp_ac(p, n, P, i0, i1, w1);
+    float wgt = 0.f;
+    if (i0 == j) wgt += 1.f - w1;
+    if (i1 == j) wgt += w1;
+    wt[e] = wgt;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    int lo = P, hi = -1;
+    for (int p = 0; p < P; ++p) if (wt[j * P + p] != 0.f) { lo = p < lo ? p : lo; hi = p; }
+    lohi[j] = lo | (hi << 16);
+  }
+  __syncthreads();
+  const long long nblk = (rows + RA_ROWS - 1) / RA_ROWS;
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const long long r0 = blk * RA_ROWS;
+    const int nr = (int)((rows - r0) < RA_ROWS ? (rows - r0) : RA_ROWS);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nr * P; e += blockDim.x) {
+      const int r = e / P, p = e - r * P;
+      vx_cp_async4(tile + r * (P + 1) + p, in + (r0 + r) * P + p, true);
+    }
+    vx_cp_async_commit();
+    vx_cp_async_wait_all();
+    __syncthreads();
+    for (int e = threadIdx.x; e < nr * n; e += blockDim.x) {
+      const int r = e / n, j = e - r * n;
+      const int lh = lohi[j], lo = lh & 0xffff, hi = lh >> 16;
+      const float* row = tile + r * (P + 1);
+      const float* w = wt + j * P;
+      float acc = 0.f;
+      for (int p = lo; p <= hi; ++p) acc = fmaf(w[p], row[p], acc);
+      out[(r0 + r) * n + j] = acc;
+    }
+  }
+}
+
 // out[o, j, i] = sum_p weight(j <- p) * in[o, p, i]      in: (outer, P, inner)   out: (outer, n, inner)
 __global__ void __launch_bounds__(256) resize_adjoint1d_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                long long outer, int P, int n, int inner) {
@@ -75,6 +169,16 @@ __global__ void __launch_bounds__(256) resize_adjoint1d_kernel(const float* __re
 }
 
 static int launch_adjoint(const float* in, float* out, long long outer, int P, int n, int inner, cudaStream_t st) {
+  if (inner == 1 && P >= 32 && P <= 512 && n <= 64 && outer >= 4096) {
+    const size_t smem = sizeof(float) * ((size_t)n * P + n + (size_t)RA_ROWS * (P + 1));
+    if (smem <= 160 * 1024) {
+      VX_SET_SMEM(resize_adjoint_rows_kernel, smem);
+      long long nblk = (outer + RA_ROWS - 1) / RA_ROWS;
+      const int grid = (int)(nblk < kSMs * 4 ? nblk : kSMs * 4);
+      VX_LAUNCH(resize_adjoint_rows_kernel, dim3(grid), dim3(256), smem, st, in, out, outer, P, n);
+      return check_launch("resize_adjoint_rows_kernel");
+    }
+  }
   const long long total = outer * n * inner;
   int blocks = cdiv(total, 256);
   if (blocks > kSMs * 32) blocks = kSMs * 32;
@@ -108,6 +212,12 @@ extern "C" int vx_resize_trilinear_fwd(const vx_resize_desc* d, const void* cons
   prof_scope("resize_fwd P%d %dx%dx%d->%dx%dx%d", d->planes, d->d, d->h, d->w, d->D, d->H, d->W);
   ResizeArgs A{(const float*)in[0], (float*)out[0], d->planes, d->d, d->h, d->w, d->D, d->H, d->W};
   const long long total = (long long)d->planes * d->D * d->H * d->W;
+  prof_bytes(4.0 * ((double)total + (double)d->planes * d->d * d->h * d->w));
+  if ((d->W & 3) == 0 && d->W <= 4096 && d->w < 32768 && (((uintptr_t)out[0]) & 15) == 0 && d->D <= 65535 && d->planes <= 65535) {
+    const size_t smem = sizeof(float) * 2 * (size_t)d->W;
+    VX_LAUNCH(resize_fwd_rows_kernel, dim3(cdiv(d->H, RS_ROWS), d->D, d->planes), dim3(256), smem, (cudaStream_t)stream, A);
+    return check_launch("resize_fwd_rows_kernel");
+  }
   int blocks = cdiv(total, 256);
   if (blocks > kSMs * 32) blocks = kSMs * 32;
   VX_LAUNCH(resize_fwd_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, A);
