@@ -238,11 +238,13 @@ __global__ void __launch_bounds__(256) pwa_gather_bwd_kernel(const __grid_consta
 // relative-position bias:  biasT[h][tk][tq] = table[index[tq][tk]][h]      (attention_utils.py:120-125)
 // ---------------------------------------------------------------------------------------------------
 __global__ void pwa_bias_kernel(const float* __restrict__ table, const long long* __restrict__ index,
-                                float* __restrict__ biasT, int heads, int l) {
+                                float* __restrict__ biasT, float* __restrict__ biasN, int heads, int l) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= heads * l * l) return;
   const int tq = e % l, tk = (e / l) % l, h = e / (l * l);
-  biasT[e] = table[(size_t)index[(size_t)tq * l + tk] * heads + h];
+  const float v = table[(size_t)index[(size_t)tq * l + tk] * heads + h];
+  biasT[e] = v;
+  if (biasN) biasN[((size_t)h * l + tq) * l + tk] = v;      // query-major copy: coalesced for the key-row phase of the backward
 }
 
 // dtable[index[tq][tk]][h] += dbias[h][tq][tk]     (the gradient buffer is query-major, unlike biasT)
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(256) pwa_bias_bwd_kernel(const float* __restri
 // attention
 // ---------------------------------------------------------------------------------------------------
 struct AttnArgs {
-  const float* Q; const float* K; const float* V; const float* biasT;
+  const float* Q; const float* K; const float* V; const float* biasT; const float* biasN;
   float* O; float* lse;
   // backward
   const float* dO; float* dQ; float* dK; float* dV; float* dbiasT;
@@ -519,10 +521,11 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
 #pragma unroll
       for (int c = 0; c < CV; ++c) { v[c] = Vs[att_row(r, CV) + c]; dv[c] = 0.f; }
       const int tk = r % l;
+      const float* bN = A.biasN + (size_t)head * l * l + tk;       // [tq][tk]: the lanes of a warp are consecutive keys
       for (int i = t; i < L; i += ATT_TS) {
         const float* qr = Qs + att_row(i, CQ);
         const float* gr = dOs + att_row(i, CV);
-        float s = __ldg(bTh + (size_t)tk * l + (i % l));
+        float s = __ldg(bN + (size_t)(i % l) * l);
 #pragma unroll
         for (int c = 0; c < CQ; ++c) s = fmaf(qr[c], kx[c], s);
         const float p = expf(s - lses[i]);
@@ -758,7 +761,7 @@ struct PwaLayout {
   size_t saved[SV_COUNT];
   size_t tokq, tokv;                       // element counts
   // workspace offsets (bytes)
-  size_t off_qkv, off_biasT, off_dh, off_dln2, off_dy, off_dA, off_dOt, off_dQt, off_dKt, off_dVt, off_dqkv, off_dln1,
+  size_t off_qkv, off_biasT, off_biasN, off_dh, off_dln2, off_dy, off_dA, off_dOt, off_dQt, off_dKt, off_dVt, off_dqkv, off_dln1,
       off_dbiasT, total;
 };
 
@@ -783,6 +786,7 @@ static int pwa_layout(const vx_pwa_desc* d, PwaLayout& P) {
   const size_t cqkv = (size_t)2 * P.cqk + P.cv;
   P.off_qkv = off;    off += align256(4 * MB * cqkv * S);
   P.off_biasT = off;  off += align256(4 * (size_t)G.heads * G.l * G.l);
+  P.off_biasN = off;  off += align256(4 * (size_t)G.heads * G.l * G.l);
   P.off_dh = off;     off += align256(4 * MB * P.eC * S);
   P.off_dln2 = off;   off += align256(4 * MB * P.C * S);
   P.off_dy = off;     off += align256(4 * MB * P.C * S);
@@ -890,7 +894,7 @@ extern "C" int vx_pwa_block_fwd(const vx_pwa_desc* d, const void* const* in, voi
   // attention
   {
     const int nb = G.heads * G.l * G.l;
-    VX_LAUNCH(pwa_bias_kernel, dim3(cdiv(nb, 256)), dim3(256), 0, st, table, index, biasT, G.heads, G.l);
+    VX_LAUNCH(pwa_bias_kernel, dim3(cdiv(nb, 256)), dim3(256), 0, st, table, index, biasT, (float*)nullptr, G.heads, G.l);
     VX_TRY(check_launch("pwa_bias_kernel"));
     AttnArgs A{};
     A.Q = SV(SV_QT); A.K = SV(SV_KT); A.V = SV(SV_VT); A.biasT = biasT; A.O = SV(SV_OT); A.lse = SV(SV_LSE);
@@ -1005,7 +1009,8 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
     zl.add(dtable, rows * G.heads);
     VX_TRY(zero_many(zl, st));
   }
-  VX_LAUNCH(pwa_bias_kernel, dim3(cdiv(nbias, 256)), dim3(256), 0, st, table, index, biasT, G.heads, G.l);
+  float* biasN = (float*)(ws + P.off_biasN);
+  VX_LAUNCH(pwa_bias_kernel, dim3(cdiv(nbias, 256)), dim3(256), 0, st, table, index, biasT, biasN, G.heads, G.l);
   VX_TRY(check_launch("pwa_bias_kernel"));
 
   auto seedm = [&](int m) { return d->seed + 0x1000 * (uint64_t)(m + 1); };
@@ -1102,7 +1107,7 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
   // ---- attention backward
   {
     AttnArgs A{};
-    A.Q = SV(SV_QT); A.K = SV(SV_KT); A.V = SV(SV_VT); A.biasT = biasT; A.O = (float*)SV(SV_OT); A.lse = (float*)SV(SV_LSE);
+    A.Q = SV(SV_QT); A.K = SV(SV_KT); A.V = SV(SV_VT); A.biasT = biasT; A.biasN = biasN; A.O = (float*)SV(SV_OT); A.lse = (float*)SV(SV_LSE);
     A.dO = dOt; A.dQ = dQt; A.dK = dKt; A.dV = dVt; A.dbiasT = dbiasT;
     A.B = B; A.heads = G.heads; A.Ns = G.Ns; A.L = G.L; A.l = G.l;
     A.scale = 1.0f / sqrtf((float)P.cq_h); A.drop_p = attn_p; A.seed = d->seed; A.seed_dev = get_seed_dev();

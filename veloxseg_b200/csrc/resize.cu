@@ -168,6 +168,38 @@ __global__ void __launch_bounds__(256) resize_adjoint1d_kernel(const float* __re
   }
 }
 
+// The same reduction with a warp per output element (lanes stride the P axis): the later passes have only a few thousand
+// outputs (216 for the last pass of a 3^3 source), each a 96-term sum -- one thread per output is a long serial chain.
+__global__ void __launch_bounds__(256) resize_adjoint1d_warp_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                    long long outer, int P, int n, int inner) {
+  const long long total = outer * n * inner;
+  const int lane = threadIdx.x & 31;
+  for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int i = (int)(e % inner), j = (int)((e / inner) % n);
+    const long long o = e / ((long long)inner * n);
+    int lo = 0, hi = P - 1;
+    if (n > 1 && P > 1) {
+      const float inv = (float)(P - 1) / (float)(n - 1);
+      lo = (int)floorf((float)(j - 1) * inv) - 1;
+      hi = (int)ceilf((float)(j + 1) * inv) + 1;
+      if (lo < 0) lo = 0;
+      if (hi > P - 1) hi = P - 1;
+    }
+    const float* src = in + (o * P) * inner + i;
+    float acc = 0.f;
+    for (int p = lo + lane; p <= hi; p += 32) {
+      int i0, i1; float w1;
+      lerp_ac(p, n, P, i0, i1, w1);
+      float wgt = 0.f;
+      if (i0 == j) wgt += 1.f - w1;
+      if (i1 == j) wgt += w1;
+      if (wgt != 0.f) acc = fmaf(wgt, __ldg(src + (size_t)p * inner), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[e] = acc;
+  }
+}
+
 static int launch_adjoint(const float* in, float* out, long long outer, int P, int n, int inner, cudaStream_t st) {
   if (inner == 1 && P >= 32 && P <= 512 && n <= 64 && outer >= 4096) {
     const size_t smem = sizeof(float) * ((size_t)n * P + n + (size_t)RA_ROWS * (P + 1));
@@ -180,6 +212,12 @@ static int launch_adjoint(const float* in, float* out, long long outer, int P, i
     }
   }
   const long long total = outer * n * inner;
+  if (total <= (long long)kSMs * 64 * 8 && P >= 32) {      // few outputs, long sums: a warp each
+    int blocks = cdiv(total * 32, 256);
+    if (blocks < 1) blocks = 1;
+    VX_LAUNCH(resize_adjoint1d_warp_kernel, dim3(blocks), dim3(256), 0, st, in, out, outer, P, n, inner);
+    return check_launch("resize_adjoint1d_warp_kernel");
+  }
   int blocks = cdiv(total, 256);
   if (blocks > kSMs * 32) blocks = kSMs * 32;
   if (blocks < 1) blocks = 1;

@@ -35,11 +35,7 @@ __global__ void __launch_bounds__(SL_THREADS) segloss_partial_kernel(const __gri
   float ce = 0.f, I[C], P[C], T[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) { I[c] = 0.f; P[c] = 0.f; T[c] = 0.f; }
-  for (int v = blk * SL_THREADS + threadIdx.x; v < A.S; v += gridDim.x * SL_THREADS) {
-    float l[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) l[c] = __ldg(lg + (size_t)c * A.S + v);
-    const int y = (int)__ldg(lab + v);
+  auto voxel = [&](const float (&l)[C], int y) {
     float m = l[0];
 #pragma unroll
     for (int c = 1; c < C; ++c) m = fmaxf(m, l[c]);
@@ -52,6 +48,29 @@ __global__ void __launch_bounds__(SL_THREADS) segloss_partial_kernel(const __gri
     for (int c = 1; c < C; ++c) {
       const float p = e[c] * inv, t = (c == y) ? 1.f : 0.f;
       I[c] += p * t; P[c] += p; T[c] += t;
+    }
+  };
+  // 4 voxels per iteration (16-byte loads of every class plane, labels as two 16-byte loads): four independent
+  // exp / log chains in flight per thread instead of one
+  const bool vec = (A.S & 3) == 0 && (((uintptr_t)lg | (uintptr_t)lab) & 15) == 0;
+  if (vec) {
+    for (int v = (blk * SL_THREADS + threadIdx.x) * 4; v < A.S; v += gridDim.x * SL_THREADS * 4) {
+      float4 q[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) q[c] = __ldg(reinterpret_cast<const float4*>(lg + (size_t)c * A.S + v));
+      const longlong2 y01 = __ldg(reinterpret_cast<const longlong2*>(lab + v));
+      const longlong2 y23 = __ldg(reinterpret_cast<const longlong2*>(lab + v + 2));
+      float l0[C], l1[C], l2[C], l3[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) { l0[c] = q[c].x; l1[c] = q[c].y; l2[c] = q[c].z; l3[c] = q[c].w; }
+      voxel(l0, (int)y01.x); voxel(l1, (int)y01.y); voxel(l2, (int)y23.x); voxel(l3, (int)y23.y);
+    }
+  } else {
+    for (int v = blk * SL_THREADS + threadIdx.x; v < A.S; v += gridDim.x * SL_THREADS) {
+      float l[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) l[c] = __ldg(lg + (size_t)c * A.S + v);
+      voxel(l, (int)__ldg(lab + v));
     }
   }
   float* out = A.part + (((size_t)i * A.B + b) * A.nblk + blk) * (1 + 3 * C);
@@ -109,11 +128,7 @@ __global__ void __launch_bounds__(SL_THREADS) segloss_bwd_kernel(const __grid_co
     rden[c] = 1.0f / den;
     num[c] = (2.0f * s[1 + 3 * c] + 1e-5f) * rden[c] * rden[c];       // (2I + eps) / den^2
   }
-  for (int v = blockIdx.x * SL_THREADS + threadIdx.x; v < A.S; v += gridDim.x * SL_THREADS) {
-    float l[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) l[c] = __ldg(lg + (size_t)c * A.S + v);
-    const int y = (int)__ldg(lab + v);
+  auto voxel = [&](const float (&l)[C], int y, float (&d)[C]) {
     float m = l[0];
 #pragma unroll
     for (int c = 1; c < C; ++c) m = fmaxf(m, l[c]);
@@ -131,7 +146,32 @@ __global__ void __launch_bounds__(SL_THREADS) segloss_bwd_kernel(const __grid_co
       sg = fmaf(p[c], g[c], sg);
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) dl[(size_t)c * A.S + v] = kce * (p[c] - ((c == y) ? 1.f : 0.f)) + p[c] * (g[c] - sg);
+    for (int c = 0; c < C; ++c) d[c] = kce * (p[c] - ((c == y) ? 1.f : 0.f)) + p[c] * (g[c] - sg);
+  };
+  const bool vec = (A.S & 3) == 0 && (((uintptr_t)lg | (uintptr_t)lab | (uintptr_t)dl) & 15) == 0;
+  if (vec) {
+    for (int v = (blockIdx.x * SL_THREADS + threadIdx.x) * 4; v < A.S; v += gridDim.x * SL_THREADS * 4) {
+      float4 q[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) q[c] = __ldg(reinterpret_cast<const float4*>(lg + (size_t)c * A.S + v));
+      const longlong2 y01 = __ldg(reinterpret_cast<const longlong2*>(lab + v));
+      const longlong2 y23 = __ldg(reinterpret_cast<const longlong2*>(lab + v + 2));
+      float l0[C], l1[C], l2[C], l3[C], d0[C], d1[C], d2[C], d3[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) { l0[c] = q[c].x; l1[c] = q[c].y; l2[c] = q[c].z; l3[c] = q[c].w; }
+      voxel(l0, (int)y01.x, d0); voxel(l1, (int)y01.y, d1); voxel(l2, (int)y23.x, d2); voxel(l3, (int)y23.y, d3);
+#pragma unroll
+      for (int c = 0; c < C; ++c) *reinterpret_cast<float4*>(dl + (size_t)c * A.S + v) = make_float4(d0[c], d1[c], d2[c], d3[c]);
+    }
+  } else {
+    for (int v = blockIdx.x * SL_THREADS + threadIdx.x; v < A.S; v += gridDim.x * SL_THREADS) {
+      float l[C], d[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) l[c] = __ldg(lg + (size_t)c * A.S + v);
+      voxel(l, (int)__ldg(lab + v), d);
+#pragma unroll
+      for (int c = 0; c < C; ++c) dl[(size_t)c * A.S + v] = d[c];
+    }
   }
 }
 
