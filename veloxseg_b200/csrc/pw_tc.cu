@@ -248,26 +248,44 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
         obase = P.seg[0].out + ((size_t)b * Co + c0) * S + v;
       }
       const size_t lbase = ((size_t)b * Co + c0) * S + v;      // index in the logical (B, Co, S) tensor
+      // Optional epilogue streams: the pointer tests are CTA-uniform, so each stream is one predictable branch around 8
+      // independent loads (not 8 x 3 predicated selects); `nlive` = channels of this batch that exist for this voxel.
+      const int nlive = vok ? (Co - c0 < 8 ? Co - c0 : 8) : 0;
       float bias[8], mg[8], r1[8], r2[8];
-      bool live[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        live[j] = c0 + j < Co && vok;
-        bias[j] = (bptr && c0 + j < Co) ? __ldg(bptr + j) : 0.f;
-        mg[j] = (P.mulgrad && live[j]) ? __ldg(P.mulgrad + lbase + (size_t)j * S) : 0.f;
-        r1[j] = (P.res && live[j]) ? __ldg(P.res + lbase + (size_t)j * S) : 0.f;
-        r2[j] = (P.res2 && live[j]) ? __ldg(P.res2 + lbase + (size_t)j * S) : 0.f;
+      for (int j = 0; j < 8; ++j) { bias[j] = 0.f; mg[j] = 0.f; r1[j] = 0.f; r2[j] = 0.f; }
+      if (bptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (c0 + j < Co) bias[j] = __ldg(bptr + j);
+      }
+      if (P.mulgrad) {
+        const float* q = P.mulgrad + lbase;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < nlive) mg[j] = __ldg(q + (size_t)j * S);
+      }
+      if (P.res) {
+        const float* q = P.res + lbase;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < nlive) r1[j] = __ldg(q + (size_t)j * S);
+      }
+      if (P.res2) {
+        const float* q = P.res2 + lbase;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < nlive) r2[j] = __ldg(q + (size_t)j * S);
       }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float y[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (!live[j]) continue;
-        float y = __uint_as_float(r[j]) + bias[j];
-        if (heavy) y = pw_epi_heavy(y, P.act, P.mulgrad != nullptr, mg[j], P.drop_p, P.seed + soff, P.site, lbase + (size_t)j * S, dinv);
-        if (P.res) y = fmaf(P.res_scale, r1[j], y);
-        if (P.res2) y += r2[j];
-        obase[(size_t)j * S] = y;
+      for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[j]) + bias[j];
+      if (heavy) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < nlive) y[j] = pw_epi_heavy(y[j], P.act, P.mulgrad != nullptr, mg[j], P.drop_p, P.seed + soff, P.site, lbase + (size_t)j * S, dinv);
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = fmaf(P.res_scale, r1[j], y[j]) + r2[j];      // r1 / r2 are zero without their stream
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j < nlive) obase[(size_t)j * S] = y[j];
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

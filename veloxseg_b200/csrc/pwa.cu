@@ -300,6 +300,16 @@ VX_DEV void attn_drop4(const AttnArgs& A, size_t row, int k4, float inv_keep, fl
 // (profiles/r1c_pwa_L2.digest.txt: 2.3e7 conflicts, L1 at 76 % of peak).  Row stride in floats: C, quad stride: 4 C + 8.
 VX_DEV int att_row(int k, int C) { return k * C + (k >> 2) * 8; }
 VX_DEV int att_rows_floats(int L, int C) { return L * C + ((L + 3) >> 2) * 8; }
+// exp for the softmax terms: ex2.approx on the pre-scaled argument (relative error ~1e-6 for |x| < 20, far inside the
+// fp32 parity bar); the precise expf is ~15 instructions of a ~40-instruction inner loop.
+VX_DEV float att_exp(float x) {
+#ifdef VX_EMU
+  return expf(x);
+#else
+  return __expf(x);
+#endif
+}
+
 VX_DEV void att_stage(float* dst, const float* src, int L, int C, int tid, int nthr) {
   for (int i = tid; i < L * C; i += nthr) { const int k = i / C; vx_cp_async4(dst + att_row(k, C) + (i - k * C), src + i, true); }
 }
@@ -362,13 +372,13 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_fwd_kernel(const __g
 #pragma unroll
       for (int c = 0; c < CQ; ++c) s = fmaf(q[c], kr[c], s);
       if (s > mx) {
-        const float corr = expf(mx - s);
+        const float corr = att_exp(mx - s);
         ssum *= corr;
 #pragma unroll
         for (int c = 0; c < CV; ++c) acc[c] *= corr;
         mx = s;
       }
-      const float p = expf(s - mx);
+      const float p = att_exp(s - mx);
       ssum += p;
       const float pm = p * ms[kk];
 #pragma unroll
@@ -381,7 +391,7 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_fwd_kernel(const __g
     const float m2 = __shfl_xor_sync(0xffffffffu, mx, o);
     const float s2 = __shfl_xor_sync(0xffffffffu, ssum, o);
     const float mn = fmaxf(mx, m2);
-    const float c1 = mx == -INFINITY ? 0.f : expf(mx - mn), c2 = m2 == -INFINITY ? 0.f : expf(m2 - mn);
+    const float c1 = mx == -INFINITY ? 0.f : att_exp(mx - mn), c2 = m2 == -INFINITY ? 0.f : att_exp(m2 - mn);
     ssum = ssum * c1 + s2 * c2;
 #pragma unroll
     for (int c = 0; c < CV; ++c) {
@@ -467,7 +477,7 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
         float s = __ldg(bTh + (size_t)tk * l + tq);
 #pragma unroll
         for (int c = 0; c < CQ; ++c) s = fmaf(q[c], kr[c], s);
-        const float p = expf(s - lse);
+        const float p = att_exp(s - lse);
         float dp = 0.f;
 #pragma unroll
         for (int c = 0; c < CV; ++c) dp = fmaf(dO[c], vr[c], dp);
@@ -500,7 +510,7 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
             if (k >= L) break;
             const int tk = k % l;
             const float ds = key(k, tk, ms[kk]);
-            if (live) atomicAdd(sdb ? sdb + tq * l + tk : dbrow + tk, ds);
+            if (live) { if (sdb) atomicAdd(sdb + tq * l + tk, ds); else atomicAdd(dbrow + tk, ds); }
           }
         }
       }
@@ -528,7 +538,7 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
         float s = __ldg(bN + (size_t)(i % l) * l);
 #pragma unroll
         for (int c = 0; c < CQ; ++c) s = fmaf(qr[c], kx[c], s);
-        const float p = expf(s - lses[i]);
+        const float p = att_exp(s - lses[i]);
         float msk = 1.f;
         if (drop) {
           float ms[4];
@@ -587,9 +597,9 @@ static int launch_attn(const AttnArgs& A, bool bwd, cudaStream_t st) {
   Ab.wpc = 1;
   if (Ab.smem_bias) {
     const long long ctas = (long long)A.Ns * A.B * A.heads;
-    Ab.wpc = (int)(ctas / (2 * kSMs));
+    Ab.wpc = (int)((ctas + 2 * kSMs - 1) / (2 * kSMs));      // ceil: at most one wave of 2 CTAs per SM
     if (Ab.wpc < 1) Ab.wpc = 1;
-    if (Ab.wpc > 8) Ab.wpc = 8;
+    if (Ab.wpc > 16) Ab.wpc = 16;
     grid.y = cdiv(A.Ns, Ab.wpc);
   }
   const size_t smem = sizeof(float) * ((size_t)A.L * (2 * CQ + 2 * CV + 2) + 4 * (size_t)((A.L + 3) / 4) * 8 +
