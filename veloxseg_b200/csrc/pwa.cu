@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_fwd_kernel(const __g
   const int nk4 = (L + 3) >> 2;
   for (int qd = t; qd < nk4; qd += ATT_TS) {
     const int k0 = qd * 4;
+    const int tk0 = k0 % l;
     float ms[4] = {1.f, 1.f, 1.f, 1.f};
     if (drop) attn_drop4(A, row, qd, inv_keep, ms);
 #pragma unroll
@@ -368,7 +369,9 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_fwd_kernel(const __g
       if (k >= L) break;
       const float* kr = Ks + att_row(k, CQ);
       const float* vr = Vs + att_row(k, CV);
-      float s = __ldg(bT + (size_t)(k % l) * l);
+      int tk = tk0 + kk;
+      while (tk >= l) tk -= l;
+      float s = __ldg(bT + (size_t)tk * l);
 #pragma unroll
       for (int c = 0; c < CQ; ++c) s = fmaf(q[c], kr[c], s);
       if (s > mx) {
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
   float* dOs = Qs + fq;           // [L][CV]
   float* lses = dOs + fv;         // [L]
   float* Dv = lses + L;           // [L]
-  float* sdb = A.smem_bias ? Dv + L : nullptr;    // [l][l]
+  float* sdb = A.smem_bias ? Dv + L : nullptr;    // [L][L]: score gradients of the current window (small-table path)
   const bool drop = A.drop_p > 0.f;
   const float inv_keep = drop ? 1.0f / (1.0f - A.drop_p) : 1.f;
   const int rows = nthr / ATT_TS;
@@ -439,7 +442,10 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
   const bool vec = (l & 3) == 0 && !sdb;
   const int tq = r % l;
   float* dbrow = A.dbiasT + ((size_t)head * l + tq) * l;       // [head][tq][tk]
-  if (sdb) for (int i = tid; i < l * l; i += nthr) sdb[i] = 0.f;
+  constexpr int ATT_NE = 8;                       // bias-table entries owned by a thread on the small-table path
+  float accE[ATT_NE];
+#pragma unroll
+  for (int n = 0; n < ATT_NE; ++n) accE[n] = 0.f;
 
   const int N1 = min(A.Ns, (int)(blockIdx.y + 1) * A.wpc);
   for (int N = blockIdx.y * A.wpc; N < N1; ++N) {
@@ -502,15 +508,17 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
       } else {
         for (int qd = t; qd < nk4; qd += ATT_TS) {
           const int k0 = qd * 4;
+          const int tk0 = k0 % l;
           float ms[4] = {1.f, 1.f, 1.f, 1.f};
           if (drop) attn_drop4(A, row, qd, inv_keep, ms);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const int k = k0 + kk;
             if (k >= L) break;
-            const int tk = k % l;
+            int tk = tk0 + kk;
+            while (tk >= l) tk -= l;
             const float ds = key(k, tk, ms[kk]);
-            if (live) { if (sdb) atomicAdd(sdb + tq * l + tk, ds); else atomicAdd(dbrow + tk, ds); }
+            if (live) { if (sdb) sdb[r * L + k] = ds; else atomicAdd(dbrow + tk, ds); }
           }
         }
       }
@@ -523,6 +531,21 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
         for (int c = 0; c < CQ; ++c) A.dQ[row * CQ + c] = dq[c] * A.scale;
       }
     }
+    if (sdb) {      // fold the window's L x L score gradients onto the l x l entries this thread owns (no atomics)
+      __syncthreads();
+      const int M = L / l;
+#pragma unroll
+      for (int n = 0; n < ATT_NE; ++n) {
+        const int e = tid + n * nthr;
+        if (e < l * l) {
+          const int eq = e / l, ek = e - eq * l;
+          float a = 0.f;
+          for (int i = 0; i < M; ++i)
+            for (int j = 0; j < M; ++j) a += sdb[(i * l + eq) * L + j * l + ek];
+          accE[n] += a;
+        }
+      }
+    }
     // phase B: key row r -> dK_r, dV_r
     {
       float kx[CQ], dk[CQ], v[CV], dv[CV];
@@ -532,10 +555,14 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
       for (int c = 0; c < CV; ++c) { v[c] = Vs[att_row(r, CV) + c]; dv[c] = 0.f; }
       const int tk = r % l;
       const float* bN = A.biasN + (size_t)head * l * l + tk;       // [tq][tk]: the lanes of a warp are consecutive keys
+      int iq = t % l;                                              // i % l, kept incrementally
+#pragma unroll 2
       for (int i = t; i < L; i += ATT_TS) {
         const float* qr = Qs + att_row(i, CQ);
         const float* gr = dOs + att_row(i, CV);
-        float s = __ldg(bN + (size_t)(i % l) * l);
+        float s = __ldg(bN + (size_t)iq * l);
+        iq += ATT_TS;
+        while (iq >= l) iq -= l;
 #pragma unroll
         for (int c = 0; c < CQ; ++c) s = fmaf(qr[c], kx[c], s);
         const float p = att_exp(s - lses[i]);
@@ -572,9 +599,12 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
     }
   }
   if (sdb) {
-    __syncthreads();
     float* gdb = A.dbiasT + (size_t)head * l * l;
-    for (int i = tid; i < l * l; i += nthr) atomicAdd(gdb + i, sdb[i]);
+#pragma unroll
+    for (int n = 0; n < ATT_NE; ++n) {
+      const int e = tid + n * nthr;
+      if (e < l * l) atomicAdd(gdb + e, accE[n]);
+    }
   }
 }
 
@@ -593,7 +623,8 @@ static int launch_attn(const AttnArgs& A, bool bwd, cudaStream_t st) {
     return check_launch("pwa_attn_fwd_kernel");
   }
   AttnArgs Ab = A;
-  Ab.smem_bias = (A.l * A.l <= 2048 && grid.x == 1) ? 1 : 0;      // a row block must see whole windows
+  // small-table path: the CTA sees whole windows, a thread owns <= 8 table entries, the L x L buffer stays <= 64 KB
+  Ab.smem_bias = (A.l * A.l <= 2048 && grid.x == 1 && A.l * A.l <= 8 * threads && (size_t)A.L * A.L <= 16384) ? 1 : 0;
   Ab.wpc = 1;
   if (Ab.smem_bias) {
     const long long ctas = (long long)A.Ns * A.B * A.heads;
@@ -603,7 +634,7 @@ static int launch_attn(const AttnArgs& A, bool bwd, cudaStream_t st) {
     grid.y = cdiv(A.Ns, Ab.wpc);
   }
   const size_t smem = sizeof(float) * ((size_t)A.L * (2 * CQ + 2 * CV + 2) + 4 * (size_t)((A.L + 3) / 4) * 8 +
-                                       (Ab.smem_bias ? (size_t)A.l * A.l : 0));
+                                       (Ab.smem_bias ? (size_t)A.L * A.L : 0));
   VX_SET_SMEM((pwa_attn_bwd_kernel<CQ, CV>), smem);
   VX_LAUNCH((pwa_attn_bwd_kernel<CQ, CV>), grid, dim3(threads), smem, st, Ab);
   return check_launch("pwa_attn_bwd_kernel");
