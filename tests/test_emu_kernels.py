@@ -271,3 +271,36 @@ def test_lnpw_wide_channels(emu):
     got = ops.lnpw_bwd_raw(emu, 0, dy, xhat, rstd, lw, lb, W)
     for i, (g, r) in enumerate(zip(got, gr)):
         assert close(g, r, rtol=2e-4, atol=2e-5), (i, rel_err(g, r))
+
+
+@pytest.mark.parametrize("case", [0, 3])
+def test_pwa_dropout_backward_matches_forward_masks(emu, case):
+    """Train-mode dropout (attention weights + projections): with a fixed seed the block is a deterministic smooth
+    function, so the backward pass (which regenerates every mask) must agree with a central finite difference of the
+    forward pass.  A mask mismatch between the two directions shows up as an O(1) relative error."""
+    from tests._util import pwa_params
+    from veloxseg_b200 import ops
+    O = _oracle()
+    size, C, mb, ms, heads, mdh, M, e, B = PWA_CASES[case]
+    geo = O.pwa_geometry(size, C, mb, ms, 2, heads, mdh)
+    torch.manual_seed(11)
+    xs = [torch.randn(B, C, *size) for _ in range(M)]
+    flat, pd, table, index = pwa_params(M, C, geo, e, seed=4)
+    p_att, p_proj, seed = 0.3, 0.2, 77
+
+    def fwd(inp):
+        zs, saved = ops.pwa_block_fwd_raw(emu, 0, inp, flat, table, index, geo, e, p_att, p_proj, True, seed)
+        return zs, saved
+
+    zs, saved = fwd(xs)
+    zs2, _ = fwd(xs)
+    assert all(torch.equal(a, b) for a, b in zip(zs, zs2))
+    dzs = [torch.randn_like(z) for z in zs]
+    dxs, dps, dtable = ops.pwa_block_bwd_raw(emu, 0, dzs, xs, flat, table, index, saved, geo, e, p_att, p_proj, True, seed)
+    d = [torch.randn_like(x) for x in xs]
+    eps = 1e-2
+    zp, _ = fwd([x + eps * dd for x, dd in zip(xs, d)])
+    zm, _ = fwd([x - eps * dd for x, dd in zip(xs, d)])
+    fd = sum(float(((a - b) / (2 * eps) * g).double().sum()) for a, b, g in zip(zp, zm, dzs))
+    an = sum(float((gx * dd).double().sum()) for gx, dd in zip(dxs, d))
+    assert abs(fd - an) <= 3e-2 * max(abs(fd), abs(an), 1.0), (fd, an)

@@ -147,12 +147,13 @@ def test_jlc_levels(ops, lvl, B):
         assert float(gg[i].abs().max()) <= 1e-3 * float(gr[i - 1].abs().max()), (i, float(gg[i].abs().max()))
 
 
-def test_jlc_dropout_mask_consistency(ops):
+@pytest.mark.parametrize("shape", [(12, 12, 12), (24, 24, 24)])      # SIMT contraction kernels / tcgen05 kernels
+def test_jlc_dropout_mask_consistency(ops, shape):
     """train-mode dropout: same seed -> same mask in forward and backward; elements are either dropped or scaled 1/(1-p)."""
     from veloxseg_b200 import _lib
     torch.manual_seed(2)
     C, groups, e = 16, 4, 3
-    x = torch.randn(2, C, 12, 12, 12, device=DEV)
+    x = torch.randn(2, C, *shape, device=DEV)
     params = [p.to(DEV) for p in jlc_params(C, groups, e, seed=5)]
     lib, st = _lib.get_lib(), torch.cuda.current_stream().cuda_stream
     y0, z, o, hpre, stats = ops.jlc_fwd_raw(lib, st, x, params, groups, e, 0.0, False, 0)
@@ -229,6 +230,38 @@ def test_pwa_gather_bit_exact(ops, lvl):
                     assert torch.equal(torch.gather(flat[:, (j * heads + h) * cper + c], 1, a),
                                        ref[:, h, off:off + Nj, :, c].reshape(2, -1))
             off += Nj
+
+
+@pytest.mark.parametrize("lvl", ["autopet_L1", "autopet_L2", "autopet_L3", "hecktor_L1"])
+def test_pwa_dropout_backward_matches_forward_masks(ops, lvl):
+    """Train-mode dropout (attention weights + projections): with a fixed seed the block is a deterministic smooth function,
+    so the backward pass (which regenerates every mask, partly with Philox blocks shared between lanes) must agree with a
+    central finite difference of the forward pass; a mask mismatch is an O(1) relative error."""
+    from veloxseg_b200 import _lib
+    size, C, mb, heads, mdh, M, e = PWA_LEVELS[lvl]
+    geo = O.pwa_geometry(size, C, mb, [1, 1, 1], 2, heads, mdh)
+    torch.manual_seed(11)
+    lib, st = _lib.get_lib(), torch.cuda.current_stream().cuda_stream
+    xs = [torch.randn(1, C, *size, device=DEV) for _ in range(M)]
+    flat, pd, table, index = pwa_params(M, C, geo, e, seed=4)
+    flat, table, index = [p.to(DEV) for p in flat], table.to(DEV), index.to(DEV)
+    p_att, p_proj, seed = 0.3, 0.2, 77
+
+    def fwd(inp):
+        return ops.pwa_block_fwd_raw(lib, st, inp, flat, table, index, geo, e, p_att, p_proj, True, seed)
+
+    zs, saved = fwd(xs)
+    zs2, _ = fwd(xs)
+    assert all(torch.allclose(a, b, rtol=1e-5, atol=1e-6) for a, b in zip(zs, zs2))
+    dzs = [torch.randn_like(z) for z in zs]
+    dxs, dps, dtable = ops.pwa_block_bwd_raw(lib, st, dzs, xs, flat, table, index, saved, geo, e, p_att, p_proj, True, seed)
+    d = [torch.randn_like(x) for x in xs]
+    eps = 1e-2
+    zp, _ = fwd([x + eps * dd for x, dd in zip(xs, d)])
+    zm, _ = fwd([x - eps * dd for x, dd in zip(xs, d)])
+    fd = sum(float(((a - b).double() / (2 * eps) * g.double()).sum()) for a, b, g in zip(zp, zm, dzs))
+    an = sum(float((gx.double() * dd.double()).sum()) for gx, dd in zip(dxs, d))
+    assert abs(fd - an) <= 3e-2 * max(abs(fd), abs(an), 1.0), (fd, an)
 
 
 @pytest.mark.parametrize("lvl", list(PWA_LEVELS))

@@ -126,10 +126,17 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
 #pragma unroll
               for (int i = 0; i < 4; ++i) xx[i] = fmaf(xx[i], pa[u], pc[u]);
             } else if (P.pro != PRO_NONE) {
+              // the 4 voxels of a chunk are one Philox block (v % 4 == 0 and S % 4 == 0 on this path): one call, not four
+              if (P.pro == PRO_GELU || P.pro == PRO_GELU_DROPOUT) {
+                const float4 gq = gelu4_call(make_float4(xx[0], xx[1], xx[2], xx[3]));
+                xx[0] = gq.x; xx[1] = gq.y; xx[2] = gq.z; xx[3] = gq.w;
+              }
+              if (pro_drop) {
+                float ms[4];
+                dropout_scale4(P.pro_seed + soff, P.pro_site, ((uint64_t)b * Ci + ci) * (uint64_t)S + v, P.pro_drop_p, pinv, ms);
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                xx[i] = pw_pro_heavy(P.pro, xx[i], P.pro_seed + soff, P.pro_site, ((uint64_t)b * Ci + ci) * (uint64_t)S + v + i,
-                                     P.pro_drop_p, pinv);
+                for (int i = 0; i < 4; ++i) xx[i] *= ms[i];
+              }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) if (v + i >= S) xx[i] = 0.f;      // rows past the tensor stay zero
@@ -278,9 +285,46 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[j]) + bias[j];
       if (heavy) {
+        // dropout: lanes 4q..4q+3 hold 4 consecutive voxels = one Philox block per channel.  Lane (lane & 3) = i computes the
+        // blocks of channels i and i + 4 and the group exchanges the keep-scales by shuffle: 2 Philox calls per lane, not 8.
+        float keep[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < nlive) y[j] = pw_epi_heavy(y[j], P.act, P.mulgrad != nullptr, mg[j], P.drop_p, P.seed + soff, P.site, lbase + (size_t)j * S, dinv);
+        for (int j = 0; j < 8; ++j) keep[j] = 1.f;
+        if (P.drop_p > 0.f) {
+          const int li = lane & 3;
+          const size_t vb = lbase - (size_t)li;                      // index of the group's first voxel, channel c0
+          float mine[2][4];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2)
+            dropout_scale4(P.seed + soff, P.site, vb + (size_t)(li + 4 * h2) * S, P.drop_p, dinv, mine[h2]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // channel j's block lives in lane (j & 3) of the group, half j >> 2; this lane needs component li of it
+            float got = 1.f;
+#pragma unroll
+            for (int comp = 0; comp < 4; ++comp) {
+              const float cand = __shfl_sync(0xffffffffu, mine[j >> 2][comp], (lane & ~3) | (j & 3));
+              if (comp == li) got = cand;
+            }
+            keep[j] = got;
+          }
+        }
+        if (P.act == 1) {          // out-of-line 4-wide copies: the unrolled erff / expf would be ~10 KB of SASS
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 gq = gelu4_call(make_float4(y[4 * h2], y[4 * h2 + 1], y[4 * h2 + 2], y[4 * h2 + 3]));
+            y[4 * h2] = gq.x; y[4 * h2 + 1] = gq.y; y[4 * h2 + 2] = gq.z; y[4 * h2 + 3] = gq.w;
+          }
+        }
+        if (P.mulgrad) {
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 gq = gelu_grad4_call(make_float4(mg[4 * h2], mg[4 * h2 + 1], mg[4 * h2 + 2], mg[4 * h2 + 3]));
+            y[4 * h2] *= gq.x; y[4 * h2 + 1] *= gq.y; y[4 * h2 + 2] *= gq.z; y[4 * h2 + 3] *= gq.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] *= keep[j];
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = fmaf(P.res_scale, r1[j], y[j]) + r2[j];      // r1 / r2 are zero without their stream

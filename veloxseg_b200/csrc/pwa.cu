@@ -556,31 +556,49 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
       const int tk = r % l;
       const float* bN = A.biasN + (size_t)head * l * l + tk;       // [tq][tk]: the lanes of a warp are consecutive keys
       int iq = t % l;                                              // i % l, kept incrementally
-#pragma unroll 2
-      for (int i = t; i < L; i += ATT_TS) {
-        const float* qr = Qs + att_row(i, CQ);
-        const float* gr = dOs + att_row(i, CV);
-        float s = __ldg(bN + (size_t)iq * l);
-        iq += ATT_TS;
-        while (iq >= l) iq -= l;
-#pragma unroll
-        for (int c = 0; c < CQ; ++c) s = fmaf(qr[c], kx[c], s);
-        const float p = att_exp(s - lses[i]);
-        float msk = 1.f;
+      // Dropout: the 4 key rows of a quad (lanes 16g + 4u + t, u = 0..3) need the same Philox block (query i, key quad)
+      // and take one component each.  The lane of role u generates the block of the u-th of the next 4 queries and the
+      // group exchanges them by shuffle: one Philox call per 4 score elements instead of one per element.
+      const int lane = tid & 31, role = (lane >> 2) & 3;
+#pragma unroll 1
+      for (int i0 = t; i0 < L; i0 += 4 * ATT_TS) {
+        float mine[4] = {1.f, 1.f, 1.f, 1.f};
         if (drop) {
-          float ms[4];
-          attn_drop4(A, wbase * L + i, r >> 2, inv_keep, ms);
-          msk = ms[r & 3];
+          const int im = i0 + ATT_TS * role;
+          if (im < L) attn_drop4(A, wbase * L + im, r_raw >> 2, inv_keep, mine);
         }
-        float dp = 0.f;
 #pragma unroll
-        for (int c = 0; c < CV; ++c) dp = fmaf(gr[c], v[c], dp);
-        const float pm = p * msk;
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + ATT_TS * u;
+          float msk = 1.f;
+          if (drop) {
+            const int srcl = (lane & 16) | (u << 2) | t;
 #pragma unroll
-        for (int c = 0; c < CV; ++c) dv[c] = fmaf(pm, gr[c], dv[c]);
-        const float ds = p * (dp * msk - Dv[i]);
+            for (int comp = 0; comp < 4; ++comp) {
+              const float cand = __shfl_sync(0xffffffffu, mine[comp], srcl);
+              if (comp == role) msk = cand;
+            }
+          }
+          if (i < L) {
+            const float* qr = Qs + att_row(i, CQ);
+            const float* gr = dOs + att_row(i, CV);
+            float s = __ldg(bN + (size_t)iq * l);
 #pragma unroll
-        for (int c = 0; c < CQ; ++c) dk[c] = fmaf(ds, qr[c], dk[c]);   // Qs carries the 1/sqrt(c) scale
+            for (int c = 0; c < CQ; ++c) s = fmaf(qr[c], kx[c], s);
+            const float p = att_exp(s - lses[i]);
+            float dp = 0.f;
+#pragma unroll
+            for (int c = 0; c < CV; ++c) dp = fmaf(gr[c], v[c], dp);
+            const float pm = p * msk;
+#pragma unroll
+            for (int c = 0; c < CV; ++c) dv[c] = fmaf(pm, gr[c], dv[c]);
+            const float ds = p * (dp * msk - Dv[i]);
+#pragma unroll
+            for (int c = 0; c < CQ; ++c) dk[c] = fmaf(ds, qr[c], dk[c]);   // Qs carries the 1/sqrt(c) scale
+          }
+          iq += ATT_TS;
+          while (iq >= l) iq -= l;
+        }
       }
 #pragma unroll
       for (int o = 1; o < ATT_TS; o <<= 1) {
