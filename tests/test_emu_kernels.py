@@ -298,7 +298,7 @@ def test_pwa_dropout_backward_matches_forward_masks(emu, case):
     dzs = [torch.randn_like(z) for z in zs]
     dxs, dps, dtable = ops.pwa_block_bwd_raw(emu, 0, dzs, xs, flat, table, index, saved, geo, e, p_att, p_proj, True, seed)
     d = [torch.randn_like(x) for x in xs]
-    eps = 1e-2
+    eps = 1e-3      # small enough that max-pool kinks and curvature stay below the tolerance (2.6% at 1e-2, 0.3% at 1e-3)
     zp, _ = fwd([x + eps * dd for x, dd in zip(xs, d)])
     zm, _ = fwd([x - eps * dd for x, dd in zip(xs, d)])
     fd = sum(float(((a - b) / (2 * eps) * g).double().sum()) for a, b, g in zip(zp, zm, dzs))
