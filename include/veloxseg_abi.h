@@ -239,6 +239,33 @@ int vx_segloss_fwd(const vx_segloss_desc* d, const void* const* in, void* const*
                    size_t workspace_bytes, vx_stream_t stream);
 int vx_segloss_bwd(const vx_segloss_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Network-input stem -- monai PatchEmbed as used by model/Encoder.py:150-156 (Conv3d k = s = patch on one modality's
+ * channels of the input).  The input is addressed inside the full (B, C_in_total, D, H, W)
+ * tensor; there is no data gradient (it is the network input).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, C_in_total, c_in_off, C_in, C_out, patch, D, H, W;
+} vx_patch_embed_desc;
+/* fwd in: x (B,C_in_total,D,H,W), w (C_out,C_in,p,p,p), bias (C_out) or NULL    out: y (B,C_out,D/p,H/p,W/p)
+ * bwd in: dy, x                                                                 out: dw, db                  */
+int vx_patch_embed_fwd(const vx_patch_embed_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
+int vx_patch_embed_bwd(const vx_patch_embed_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * AdamW step over every parameter tensor in one launch (torch.optim.AdamW semantics: decoupled weight decay, bias
+ * correction; the reference's optimiser, utils/runtime.py).  SURVEY.md section 8f row 4.
+ *   in[0]  int64 table (n_tensors, 4): parameter pointer, gradient pointer (0 = no gradient: skipped), offset of the tensor
+ *          in the flat moment buffers, element count
+ *   in[1]  int32 (n_chunks, 2): tensor index, first element -- one CTA per 1024-element chunk
+ *   out[0], out[1]  flat exp_avg / exp_avg_sq (fp32);  out[2]  step counter (1 float, advanced by the call)
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_chunks;
+  float lr, beta1, beta2, eps, weight_decay;
+} vx_adamw_desc;
+int vx_adamw_step(const vx_adamw_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

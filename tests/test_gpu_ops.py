@@ -353,3 +353,48 @@ def test_segloss_levels(ops, C, shape, B):
     assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref)), (float(loss), float(ref))
     for a, b in zip(g, gr):
         assert close(a, b, rtol=1e-4, atol=1e-12), rel_err(a, b)
+
+
+@pytest.mark.parametrize("Ct,c_off,Ci,size,B", [(2, 0, 1, (96, 96, 96), 2), (2, 1, 1, (128, 128, 64), 1), (4, 0, 4, (96, 96, 96), 1)])
+def test_patch_embed_stem(ops, Ct, c_off, Ci, size, B):
+    """Network-input stem (PatchEmbed k = s = 4 on a channel range of the input) vs torch conv3d in fp32."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    x = torch.randn(B, Ct, *size, device=DEV)
+    w = (torch.randn(16, Ci, 4, 4, 4, device=DEV) * 0.2).requires_grad_(True)
+    b = (torch.randn(16, device=DEV) * 0.1).requires_grad_(True)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        yr = F.conv3d(x[:, c_off:c_off + Ci], w, b, stride=4)
+        dy = torch.randn_like(yr)
+        gw, gb = torch.autograd.grad(yr, [w, b], dy)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    wg, bg = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    y = ops.patch_embed(x, c_off, wg, bg)
+    assert rel_err(y, yr) < 1e-5
+    dw, db = torch.autograd.grad(y, [wg, bg], dy)
+    assert close(dw, gw, rtol=1e-3, atol=1e-4) and close(db, gb, rtol=1e-3, atol=1e-4), (rel_err(dw, gw), rel_err(db, gb))
+
+
+def test_adamw_one_launch_matches_torch(ops):
+    """veloxseg_b200.train.VxAdamW vs torch.optim.AdamW on the tiny model's parameter list, 3 steps."""
+    from veloxseg_b200.configs import MODEL_CONFIGS
+    from veloxseg_b200.nn import VeloxSeg
+    from veloxseg_b200.train import VxAdamW
+    torch.manual_seed(0)
+    m = VeloxSeg(**MODEL_CONFIGS["tiny"]).to(DEV)
+    ps = [p for p in m.parameters()]
+    ref = [p.detach().clone().requires_grad_(True) for p in ps]
+    opt_r = torch.optim.AdamW(ref, lr=2.5e-4, weight_decay=0.01)
+    opt = VxAdamW(ps, lr=2.5e-4, weight_decay=0.01)
+    for it in range(3):
+        for p, r in zip(ps, ref):
+            g = torch.randn_like(p) * 0.1
+            p.grad, r.grad = g, g.clone()
+        opt.step()
+        opt_r.step()
+    torch.cuda.synchronize()
+    worst = max(float((p.detach() - r.detach()).abs().max() / (r.detach().abs().max() + 1e-12)) for p, r in zip(ps, ref))
+    assert worst < 1e-5, worst

@@ -454,6 +454,15 @@ class Transformer_Encoder(nn.Module):
             size = [s // 2 for s in size]
 
     def embed(self, xs):
+        if xs.is_cuda and not xs.requires_grad and xs.dtype == torch.float32:
+            # read each modality's channels where they lie in the input (no slice copies, no layout conversion, and no data
+            # gradient: this is the network input)
+            out, off = [], 0
+            for m in range(self.num_modalities):
+                proj = self.patch_embeds[m].proj
+                out.append(self.pos_drop(ops.patch_embed(xs, off, proj.weight, proj.bias)))
+                off += proj.weight.shape[1]
+            return out
         xs = torch.chunk(xs, self.num_modalities, dim=1)
         xs = [self.pos_drop(self.patch_embeds[m](xs[m])) for m in range(self.num_modalities)]
         return [x.contiguous() for x in xs]

@@ -597,3 +597,51 @@ def pwa_block(xs: Sequence[Tensor], params: Sequence[Tensor], table: Tensor, ind
     seed = next_seed() if (training and (attn_drop > 0 or proj_drop > 0)) else 0
     cfg = (geo, int(ffn_expansion), float(attn_drop), float(proj_drop), bool(training), seed)
     return list(_PwaBlock.apply(cfg, table, index, len(xs), *[x.contiguous() for x in xs], *params))
+
+
+# ----------------------------------------------------------------------------------------------------
+# Network-input stem: PatchEmbed (Conv3d k = s = patch) on a channel range of the input, no data gradient
+# ----------------------------------------------------------------------------------------------------
+def patch_embed_fwd_raw(lib, stream, x: Tensor, c_off: int, weight: Tensor, bias: Optional[Tensor]):
+    from ._lib import PatchEmbedDesc
+    x, weight = _chk(x, "x"), _chk(weight, "weight")
+    B, Ct, D, H, W = x.shape
+    Co, Ci, p = weight.shape[0], weight.shape[1], weight.shape[2]
+    d = PatchEmbedDesc(B, Ct, int(c_off), Ci, Co, p, D, H, W)
+    y = torch.empty((B, Co, D // p, H // p, W // p), dtype=_f32, device=x.device)
+    lib.call("vx_patch_embed_fwd", d, [x, weight, _chk(bias, "bias") if bias is not None else None], [y], stream)
+    return y
+
+
+def patch_embed_bwd_raw(lib, stream, dy: Tensor, x: Tensor, c_off: int, weight_shape):
+    from ._lib import PatchEmbedDesc
+    B, Ct, D, H, W = x.shape
+    Co, Ci, p = weight_shape[0], weight_shape[1], weight_shape[2]
+    d = PatchEmbedDesc(B, Ct, int(c_off), Ci, Co, p, D, H, W)
+    dw = torch.empty(tuple(weight_shape), dtype=_f32, device=x.device)
+    db = torch.empty((Co,), dtype=_f32, device=x.device)
+    lib.call("vx_patch_embed_bwd", d, [_chk(dy, "dy"), x], [dw, db], stream)
+    return dw, db
+
+
+class _PatchEmbed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, c_off, weight, bias):
+        ctx.c_off, ctx.has_bias = int(c_off), bias is not None
+        ctx.save_for_backward(x, weight)
+        return patch_embed_fwd_raw(_lib.get_lib(), _stream(x), x, c_off, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dw, db = patch_embed_bwd_raw(_lib.get_lib(), _stream(x), dy.contiguous(), x, ctx.c_off, weight.shape)
+        return None, None, dw, (db if ctx.has_bias else None)
+
+
+def patch_embed(x: Tensor, c_off: int, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """Conv3d(weight, bias, stride = kernel = patch) applied to channels [c_off, c_off + weight.shape[1]) of the network
+    input `x` (B, C_total, D, H, W).  `x` must not require grad (it is the network input)."""
+    if x.requires_grad:
+        raise RuntimeError("veloxseg: patch_embed has no data gradient (network input); use the torch convolution")
+    return _PatchEmbed.apply(x.contiguous(), int(c_off), weight, bias)
+

@@ -82,6 +82,56 @@ class GradBuckets:
             self.buckets[bi].div_(self.world)
 
 
+class VxAdamW:
+    """torch.optim.AdamW (the reference's optimiser: decoupled weight decay, bias correction, betas (0.9, 0.999), eps
+    1e-8) as ONE launch of libveloxseg over every parameter tensor.  State = two flat fp32 moment buffers + a device step
+    counter, so a captured CUDA graph replays it unchanged; the (parameter, gradient) pointer table is refreshed from
+    pinned host memory on every call because autograd may hand out new gradient tensors (inside a captured graph the
+    copy node replays the addresses of the graph's own static gradient tensors)."""
+    CHUNK = 1024
+
+    def __init__(self, params, lr: float, weight_decay: float, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        self.lr, self.wd, self.betas, self.eps = float(lr), float(weight_decay), betas, float(eps)
+        total, offs, chunks = 0, [], []
+        for i, p in enumerate(self.params):
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise TypeError("VxAdamW: parameters must be contiguous float32")
+            offs.append(total)
+            chunks += [(i, s) for s in range(0, p.numel(), self.CHUNK)]
+            total += p.numel()
+        self.offsets = offs
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.step_t = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.chunks = torch.tensor(chunks, dtype=torch.int32).reshape(-1, 2).to(dev)
+        self.n_chunks = len(chunks)
+        self._tab_host = torch.zeros(len(self.params), 4, dtype=torch.int64).pin_memory()
+        self._tab_dev = torch.zeros(len(self.params), 4, dtype=torch.int64, device=dev)
+
+    def state_tensors(self):
+        return [self.exp_avg, self.exp_avg_sq, self.step_t]
+
+    def step(self):
+        from . import _lib
+        from ._lib import AdamwDesc
+        tab = self._tab_host
+        for i, p in enumerate(self.params):
+            g = p.grad
+            if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
+                raise TypeError("VxAdamW: gradients must be contiguous float32")
+            tab[i, 0] = p.data_ptr()
+            tab[i, 1] = g.data_ptr() if g is not None else 0
+            tab[i, 2] = self.offsets[i]
+            tab[i, 3] = p.numel()
+        self._tab_dev.copy_(tab, non_blocking=True)
+        lib = _lib.get_lib()
+        d = AdamwDesc(self.n_chunks, self.lr, self.betas[0], self.betas[1], self.eps, self.wd)
+        lib.call("vx_adamw_step", d, [self._tab_dev, self.chunks], [self.exp_avg, self.exp_avg_sq, self.step_t],
+                 torch.cuda.current_stream(self.step_t.device).cuda_stream)
+
+
 class TrainStep:
     """`step(inputs, labels)` = one optimisation step; accepts host (pinned) or device tensors and returns the loss
     as a Python float only when asked (`sync=True`), mirroring the reference's per-step `loss.item()`.
@@ -110,8 +160,13 @@ class TrainStep:
         self.params = [p for p in self.model.parameters() if p.requires_grad]
         # eager data-parallel path only: gradients accumulate straight into flat buckets, all-reduce from grad hooks
         self.buckets = GradBuckets(self.params, bucket_bytes) if not self.use_graph else None
-        self.opt = torch.optim.AdamW(self.model.parameters(), lr=lr, weight_decay=weight_decay, fused=cuda,
-                                     capturable=cuda and self.use_graph)
+        # libveloxseg's one-launch AdamW on CUDA (VX_TORCH_ADAMW=1 keeps torch's fused multi-tensor optimiser for A/B)
+        import os
+        if cuda and os.environ.get("VX_TORCH_ADAMW", "0") != "1":
+            self.opt = VxAdamW(self.model.parameters(), lr=lr, weight_decay=weight_decay)
+        else:
+            self.opt = torch.optim.AdamW(self.model.parameters(), lr=lr, weight_decay=weight_decay, fused=cuda,
+                                         capturable=cuda and self.use_graph)
         self._graph = None
         self._graph_b = None
         self.graph_launches = 0        # kernels of libveloxseg_sm100 recorded in the captured step
@@ -186,10 +241,14 @@ class TrainStep:
         with torch.no_grad():
             for p, q in zip(self.model.parameters(), snap_p):
                 p.copy_(q)
-            for st in self.opt.state.values():
-                for v in st.values():
-                    if torch.is_tensor(v):
-                        v.zero_()
+            if isinstance(self.opt, VxAdamW):
+                for v in self.opt.state_tensors():
+                    v.zero_()
+            else:
+                for st in self.opt.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
         torch.cuda.synchronize(self.device)
 
     # ---- host -> device staging: pinned host batches are copied on a side stream into a staging pair, so the copy of
