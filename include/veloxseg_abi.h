@@ -122,8 +122,11 @@ typedef struct {
   int32_t S;
   float eps;
   int32_t has_addend;
+  int32_t bias_channels;  /* bwd only, 0 = off: out[1] = db (bias_channels floats) = per-channel sums of dx -- the gradient of
+                             a per-channel bias added in front of the norm (conv bias of DownConv / UpConv: it cancels in
+                             the forward value, so the conv runs without it and its gradient comes from here)           */
 } vx_inorm_desc;
-/* fwd in: x, addend|NULL   out: y, stats (rows, 2)         bwd in: dy, x, stats   out: dx */
+/* fwd in: x, addend|NULL   out: y, stats (rows, 2)         bwd in: dy, x, stats   out: dx [, db] */
 int vx_inorm_fwd(const vx_inorm_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
 int vx_inorm_bwd(const vx_inorm_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
 

@@ -253,6 +253,15 @@ def test_inorm_register_cached(emu):
     assert rel_err(y, yr) < 1e-5
     dy = torch.randn_like(y)
     assert close(ops.inorm_bwd_raw(emu, 0, dy, x, stats), torch.autograd.grad(yr, xr, dy)[0], rtol=1e-4)
+    # bias-gradient output: per-channel sums of dx (analytically zero; must match the sum of what the kernel wrote)
+    dx, db = ops.inorm_bwd_raw(emu, 0, dy, x, stats, with_bias_grad=True)
+    assert close(dx, torch.autograd.grad(yr, xr, dy)[0], rtol=1e-4)
+    assert torch.allclose(db, dx.sum(dim=(0, 2, 3, 4)), atol=1e-4)
+    xs = torch.randn(2, 5, 3, 4, 5)
+    ys, sts = ops.inorm_fwd_raw(emu, 0, xs, None)
+    dys = torch.randn_like(ys)
+    dxs, dbs = ops.inorm_bwd_raw(emu, 0, dys, xs, sts, with_bias_grad=True)
+    assert torch.allclose(dbs, dxs.sum(dim=(0, 2, 3, 4)), atol=1e-4)
 
 
 def test_lnpw_wide_channels(emu):

@@ -27,7 +27,8 @@ class MixerDesc(C.Structure):
 
 
 class InormDesc(C.Structure):
-    _fields_ = [("rows", C.c_int32), ("S", C.c_int32), ("eps", C.c_float), ("has_addend", C.c_int32)]
+    _fields_ = [("rows", C.c_int32), ("S", C.c_int32), ("eps", C.c_float), ("has_addend", C.c_int32),
+                ("bias_channels", C.c_int32)]
 
 
 class PwaDesc(C.Structure):

@@ -207,8 +207,9 @@ extern "C" int vx_inorm_fwd(const vx_inorm_desc* d, const void* const* in, void*
 extern "C" int vx_inorm_bwd(const vx_inorm_desc* d, const void* const* in, void* const* out, vx_stream_t stream) {
   if (!d || d->rows <= 0 || d->S <= 0) { set_error("inorm: bad descriptor"); return VX_ERR_BAD_DESC; }
   prof_scope("inorm_bwd R%d S%d", d->rows, d->S);
+  if (d->bias_channels < 0 || (d->bias_channels > 0 && d->rows % d->bias_channels)) { set_error("inorm_bwd: bad bias_channels"); return VX_ERR_BAD_DESC; }
   return inorm_rows_bwd((const float*)in[0], (const float*)in[1], (const float*)in[2], nullptr, (float*)out[0], d->rows,
-                        d->S, (cudaStream_t)stream);
+                        d->S, (cudaStream_t)stream, d->bias_channels > 0 ? (float*)out[1] : nullptr, d->bias_channels);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -642,7 +642,7 @@ int inorm_rows_fwd(const float* x, const float* addend, float* y, float* stats, 
 __global__ void __launch_bounds__(256) inorm_rows_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                              const float* __restrict__ stats,
                                                              const float* __restrict__ dx_add, float* __restrict__ dx,
-                                                             int S) {
+                                                             int S, float* __restrict__ db, int C) {
   __shared__ float red[33];
   const size_t base = (size_t)blockIdx.x * S;
   const float mean = stats[2 * blockIdx.x], rstd = stats[2 * blockIdx.x + 1];
@@ -654,18 +654,24 @@ __global__ void __launch_bounds__(256) inorm_rows_bwd_kernel(const float* __rest
   }
   const float m1 = block_sum(s1, red) / (float)S;
   const float m2 = block_sum(s2, red) / (float)S;
+  float bs = 0.f;
   for (int i = threadIdx.x; i < S; i += blockDim.x) {
     const float xh = (x[base + i] - mean) * rstd;
     float v = rstd * (dy[base + i] - m1 - xh * m2);
+    bs += v;
     if (dx_add) v += dx_add[base + i];
     dx[base + i] = v;
+  }
+  if (db) {        // gradient of a per-channel bias in front of the norm: sum of this row's dx
+    bs = block_sum(bs, red);
+    if (threadIdx.x == 0) atomicAdd(db + blockIdx.x % C, bs);
   }
 }
 
 __global__ void __launch_bounds__(1024) inorm_rows_bwd_cached_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                     const float* __restrict__ stats,
                                                                     const float* __restrict__ dx_add, float* __restrict__ dx,
-                                                                    int S) {
+                                                                    int S, float* __restrict__ db, int C) {
   __shared__ float red[33];
   const size_t base = (size_t)blockIdx.x * S;
   const int nq = S >> 2;
@@ -690,27 +696,39 @@ __global__ void __launch_bounds__(1024) inorm_rows_bwd_cached_kernel(const float
   const float m2 = block_sum(s2, red) / (float)S;
   float4* o4 = reinterpret_cast<float4*>(dx + base);
   const float4* a4 = dx_add ? reinterpret_cast<const float4*>(dx_add + base) : nullptr;
+  float bs = 0.f;
 #pragma unroll
   for (int j = 0; j < IN_Q; ++j) {
     const int i = threadIdx.x + j * blockDim.x;
     if (i < nq) {
       float4 o = make_float4(rstd * (g[j].x - m1 - h[j].x * m2), rstd * (g[j].y - m1 - h[j].y * m2),
                              rstd * (g[j].z - m1 - h[j].z * m2), rstd * (g[j].w - m1 - h[j].w * m2));
+      bs += (o.x + o.y) + (o.z + o.w);
       if (a4) { const float4 a = __ldg(a4 + i); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
       o4[i] = o;
     }
   }
+  if (db) {
+    bs = block_sum(bs, red);
+    if (threadIdx.x == 0) atomicAdd(db + blockIdx.x % C, bs);
+  }
 }
 
 int inorm_rows_bwd(const float* dy, const float* x, const float* stats, const float* dx_add, float* dx, int rows,
-                   int S, cudaStream_t stream) {
+                   int S, cudaStream_t stream, float* db, int C) {
   if (rows <= 0) return VX_OK;
+  if (db) {
+    ZeroList zl;
+    zl.add(db, C);
+    const int rc = zero_many(zl, stream);
+    if (rc != VX_OK) return rc;
+  }
   prof_bytes(4.0 * rows * (double)S * (dx_add ? 4 : 3));
   if (const int t = inorm_cached_threads(dy, x, dx_add, dx, S)) {
-    VX_LAUNCH(inorm_rows_bwd_cached_kernel, dim3(rows), dim3(t), 0, stream, dy, x, stats, dx_add, dx, S);
+    VX_LAUNCH(inorm_rows_bwd_cached_kernel, dim3(rows), dim3(t), 0, stream, dy, x, stats, dx_add, dx, S, db, C);
     return check_launch("inorm_rows_bwd_cached_kernel");
   }
-  VX_LAUNCH(inorm_rows_bwd_kernel, dim3(rows), dim3(256), 0, stream, dy, x, stats, dx_add, dx, S);
+  VX_LAUNCH(inorm_rows_bwd_kernel, dim3(rows), dim3(256), 0, stream, dy, x, stats, dx_add, dx, S, db, C);
   return check_launch("inorm_rows_bwd_kernel");
 }
 

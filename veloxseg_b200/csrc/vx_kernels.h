@@ -162,8 +162,9 @@ int zero_many(const ZeroList& z, cudaStream_t stream);
 int inorm_rows_fwd(const float* x, const float* addend, float* y, float* stats, int rows, int S, float eps,
                    cudaStream_t stream);
 // dx = rstd*(dy - mean(dy) - xhat*mean(dy*xhat)) [+ dx_add]
+// db (optional, C floats): += per-channel sums of dx (row r belongs to channel r % C); zeroed by the call
 int inorm_rows_bwd(const float* dy, const float* x, const float* stats, const float* dx_add, float* dx, int rows,
-                   int S, cudaStream_t stream);
+                   int S, cudaStream_t stream, float* db = nullptr, int C = 0);
 // per-(b,c) affine (a = rstd, c = -mean*rstd) from (mean, rstd) stats
 int stats_to_affine(const float* stats, float* a, float* c, int rows, cudaStream_t stream);
 

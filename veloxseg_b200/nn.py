@@ -60,10 +60,16 @@ class DownConv(nn.Module):
         self.norm = nn.InstanceNorm3d(out_channels) if use_norm else nn.Identity()
 
     def forward(self, x, addend=None):
-        y = self.down(x)
         if isinstance(self.norm, nn.Identity):
+            y = self.down(x)
             return y if addend is None else y + addend
-        return ops.instance_norm(y, addend)
+        c = self.down
+        if c.bias is not None and x.is_cuda:
+            # the bias cancels inside the affine-less norm: run the library convolution without it (no bias-add kernel, no
+            # bias-gradient reduction over the conv output) and take its gradient from the norm's backward kernel
+            z = F.conv3d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups)
+            return ops.instance_norm_biased(z, c.bias, addend)
+        return ops.instance_norm(c(x), addend)
 
 
 class UpConv(nn.Module):
@@ -76,7 +82,11 @@ class UpConv(nn.Module):
         self.norm = nn.InstanceNorm3d(out_channels)
 
     def forward(self, x, addend=None):
-        return ops.instance_norm(self.up(x), addend)
+        c = self.up
+        if c.bias is not None and x.is_cuda:
+            z = F.conv_transpose3d(x, c.weight, None, c.stride, c.padding, c.output_padding, c.groups, c.dilation)
+            return ops.instance_norm_biased(z, c.bias, addend)
+        return ops.instance_norm(c(x), addend)
 
 
 class JLC(nn.Module):

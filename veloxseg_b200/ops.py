@@ -151,10 +151,15 @@ def inorm_fwd_raw(lib, stream, x, addend: Optional[Tensor]):
     return [y, stats]
 
 
-def inorm_bwd_raw(lib, stream, dy, x, stats):
+def inorm_bwd_raw(lib, stream, dy, x, stats, with_bias_grad: bool = False):
     dy = _chk(dy, "dy")
-    d = InormDesc(x.shape[0] * x.shape[1], x[0, 0].numel(), 1e-5, 0)
+    C_ = x.shape[1]
+    d = InormDesc(x.shape[0] * C_, x[0, 0].numel(), 1e-5, 0, C_ if with_bias_grad else 0)
     dx = torch.empty_like(x)
+    if with_bias_grad:
+        db = torch.empty((C_,), dtype=_f32, device=x.device)
+        lib.call("vx_inorm_bwd", d, [dy, x, stats], [dx, db], stream)
+        return dx, db
     lib.call("vx_inorm_bwd", d, [dy, x, stats], [dx], stream)
     return dx
 
@@ -471,6 +476,32 @@ class _INorm(torch.autograd.Function):
 
 def instance_norm(x: Tensor, addend: Optional[Tensor] = None) -> Tensor:
     return _INorm.apply(x.contiguous(), addend)
+
+
+class _INormBias(torch.autograd.Function):
+    """IN(z + bias[c]) [+ addend] where z is a bias-free convolution output: the per-channel bias cancels in the value of an
+    affine-less InstanceNorm, so it is not added; its gradient (sum over batch and voxels of dz, analytically zero --
+    SURVEY.md section 7.3) comes out of the norm's backward kernel instead of a separate reduction over dz."""
+
+    @staticmethod
+    def forward(ctx, z, bias, addend):
+        lib, st = _lib.get_lib(), _stream(z)
+        y, stats = inorm_fwd_raw(lib, st, z, addend)
+        ctx.save_for_backward(z, stats)
+        ctx.has_addend = addend is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, stats = ctx.saved_tensors
+        dy = dy.contiguous()
+        dz, db = inorm_bwd_raw(_lib.get_lib(), _stream(z), dy, z, stats, with_bias_grad=True)
+        return dz, db, (dy if ctx.has_addend else None)
+
+
+def instance_norm_biased(z: Tensor, bias: Tensor, addend: Optional[Tensor] = None) -> Tensor:
+    """InstanceNorm3d(affine=False)(z + bias[None, :, None, None, None]) [+ addend] for a bias-free conv output z."""
+    return _INormBias.apply(z.contiguous(), bias, addend)
 
 
 class _Gram(torch.autograd.Function):
