@@ -252,10 +252,11 @@ def test_inorm_register_cached(emu):
     yr = O.instance_norm(xr) + add
     assert rel_err(y, yr) < 1e-5
     dy = torch.randn_like(y)
-    assert close(ops.inorm_bwd_raw(emu, 0, dy, x, stats), torch.autograd.grad(yr, xr, dy)[0], rtol=1e-4)
+    gref = torch.autograd.grad(yr, xr, dy)[0]
+    assert close(ops.inorm_bwd_raw(emu, 0, dy, x, stats), gref, rtol=1e-4)
     # bias-gradient output: per-channel sums of dx (analytically zero; must match the sum of what the kernel wrote)
     dx, db = ops.inorm_bwd_raw(emu, 0, dy, x, stats, with_bias_grad=True)
-    assert close(dx, torch.autograd.grad(yr, xr, dy)[0], rtol=1e-4)
+    assert close(dx, gref, rtol=1e-4)
     assert torch.allclose(db, dx.sum(dim=(0, 2, 3, 4)), atol=1e-4)
     xs = torch.randn(2, 5, 3, 4, 5)
     ys, sts = ops.inorm_fwd_raw(emu, 0, xs, None)
