@@ -273,7 +273,7 @@ def run_ours(args, rank, world, local_rank):
                    "cache": "L2 flushed (256 MiB memset) between timed steps",
                    "launch": ("eager launches" if not used_graph else "whole step replayed as one CUDA graph" if world == 1 else
                               "CUDA graph (fwd+bwd) -> one NCCL all-reduce of the flat 9 MB gradient -> CUDA graph (AdamW)"),
-                   "pointwise": "tcgen05 3xTF32 (fp32-accurate) for S>=4096, fp32 SIMT below" if pw_tc else "fp32 SIMT",
+                   "pointwise": "tcgen05 3xTF32 (fp32-accurate) for S>=1024 (weight gradients S>=512), fp32 SIMT below" if pw_tc else "fp32 SIMT",
                    "library_convs_outside_path": args.library_convs},
         "e2e": {"value": round(total_patches / e2e_s, 3), "unit": "patches/s",
                 "h2d_bytes_per_step": int(xb[0].numel() * xb[0].element_size() + yb[0].numel() * yb[0].element_size()),

@@ -38,7 +38,8 @@ typedef enum {
 int vx_version(void);
 const char* vx_last_error_string(void);
 /* Process-wide switches (diagnostics / A-B measurements; defaults give the production path).
- *   VX_OPT_PW_TENSOR_CORES  1 (default): 1x1 contractions with >= 512 voxels run on the tcgen05 3xTF32 kernel;
+ *   VX_OPT_PW_TENSOR_CORES  1 (default): 1x1 contractions with >= 1024 voxels (weight gradients: >= 512) run on the tcgen05
+ *                           3xTF32 kernels;
  *                           0: every contraction uses the fp32 SIMT kernels.
  *   VX_OPT_PW_SMALL_MAX_S   voxel count below which the warp-per-(32 voxels x 4 channels) kernel is used (tuning probe).
  *   VX_OPT_PW_TC_MIN_S      voxel count from which the tensor-core kernel is used (tuning probe).

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(32 * PWS_MAX_KS) pw_small_kernel(const __grid_
   }
 }
 
-static int g_small_max_s = 512, g_tc_min_s = 4096;
+static int g_small_max_s = 512, g_tc_min_s = 1024;
 void pw_set_thresholds(int small_max_s, int tc_min_s) {
   if (small_max_s >= 0) g_small_max_s = small_max_s;
   if (tc_min_s >= 0) g_tc_min_s = tc_min_s;
@@ -351,7 +351,12 @@ int pw_forward(const PwBatch& batch, cudaStream_t stream) {
   }
   if (batch.nprob <= 0 || batch.B <= 0 || batch.S <= 0) return VX_OK;
 #ifndef VX_EMU
-  if (batch.S >= g_tc_min_s && batch.S >= g_small_max_s) {
+  // tcgen05 kernel from 1024 voxels per sample (measured at the level-2 shapes, B = 4: JLC 129 -> 115 us, PWA block
+  // 184 -> 157 us forward); concatenated multi-source inputs (the modal mixer: one problem, 56 tiles) stay on the SIMT
+  // kernel below 4096 voxels (27 vs 35 us).
+  bool multi_src = false;
+  for (int i = 0; i < batch.nprob; ++i) multi_src = multi_src || batch.p[i].nsrc > 1;
+  if (batch.S >= g_tc_min_s && batch.S >= g_small_max_s && !(multi_src && batch.S < 4096)) {
     prof_bytes(bytes);
     const int rc = pw_tc_forward(batch, stream);
     if (rc <= 0) return rc;
