@@ -366,3 +366,20 @@ def test_adamw_matches_torch(emu):
             if i != 2:
                 assert close(p, r.detach(), rtol=1e-5, atol=1e-6), (it, i, rel_err(p, r.detach()))
     assert float(step) == 3.0
+
+
+def test_lnpw_backward_multi_group_ctas(emu):
+    """Large B * S: the LayerNorm backward packs several 32-voxel groups per CTA and keeps dgamma / dbeta in registers."""
+    from veloxseg_b200 import ops
+    O = _oracle()
+    torch.manual_seed(5)
+    x = torch.randn(8, 8, 16, 16, 16)
+    lw, lb, W = torch.randn(8) * 0.3 + 1, torch.randn(8) * 0.2, torch.randn(6, 8) * 0.2
+    y, xhat, rstd = ops.lnpw_fwd_raw(emu, 0, x, lw, lb, W)
+    xr, lwr, lbr, Wr = [t.clone().requires_grad_(True) for t in (x, lw, lb, W)]
+    yr = O.pointwise(O.layer_norm_cf(xr, lwr, lbr), Wr, None)
+    dy = torch.randn_like(y)
+    gr = torch.autograd.grad(yr, [xr, lwr, lbr, Wr], dy)
+    got = ops.lnpw_bwd_raw(emu, 0, dy, xhat, rstd, lw, lb, W)
+    for i, (g, r) in enumerate(zip(got, gr)):
+        assert close(g, r, rtol=3e-4, atol=2e-5), (i, rel_err(g, r))

@@ -846,53 +846,87 @@ int ln_forward(const LnBatch& L, cudaStream_t stream) {
 // every global access is a coalesced run along the voxel axis, a channel is owned by exactly one warp of the CTA (its
 // dgamma / dbeta partial is one warp reduction + one global atomic), and the per-voxel means are combined through
 // shared memory.
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const __grid_constant__ LnBwdBatch L) {
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const __grid_constant__ LnBwdBatch L, int groups) {
+  // `groups` consecutive blocks of 32 voxels per CTA: the dgamma / dbeta partial sums of a warp's channels stay in registers
+  // across them (when a warp owns <= LN_NC channels), so the global atomics -- 2 per channel and CTA onto the same 2 C
+  // addresses from every CTA -- shrink by that factor.
+  constexpr int LN_NC = 8;
   const int t = blockIdx.z, b = blockIdx.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int v = blockIdx.x * 32 + lane;
   const int C = L.C, S = L.S;
-  const bool ok = v < S;
   __shared__ float red[2][8][32];
-  const size_t off = (size_t)b * C * S + (ok ? v : 0);
-  const float* dout = L.dout[t] + off;
-  const float* xh = L.xhat[t] + off;
   const float* gamma = L.gamma[t];
-  float m1 = 0.f, m2 = 0.f;
-  for (int c = w; c < C; c += 8) {
-    const float d = ok ? __ldg(dout + (size_t)c * S) : 0.f;
-    const float h = ok ? __ldg(xh + (size_t)c * S) : 0.f;
-    const float g = __ldg(gamma + c) * d;
-    m1 += g;
-    m2 = fmaf(g, h, m2);
-    const float sg = warp_sum(d * h), sb = warp_sum(d);
-    if (lane == 0) {
-      if (L.dgamma[t]) atomicAdd(L.dgamma[t] + c, sg);
-      if (L.dbeta[t]) atomicAdd(L.dbeta[t] + c, sb);
+  const bool keep = (C + 7) / 8 <= LN_NC;
+  float ag[LN_NC], ab[LN_NC];
+#pragma unroll
+  for (int i = 0; i < LN_NC; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+  for (int gi = 0; gi < groups; ++gi) {
+    const int v = (blockIdx.x * groups + gi) * 32 + lane;
+    if ((blockIdx.x * groups + gi) * 32 >= S) break;
+    const bool ok = v < S;
+    const size_t off = (size_t)b * C * S + (ok ? v : 0);
+    const float* dout = L.dout[t] + off;
+    const float* xh = L.xhat[t] + off;
+    float m1 = 0.f, m2 = 0.f;
+    int n = 0;
+    for (int c = w; c < C; c += 8, ++n) {
+      const float d = ok ? __ldg(dout + (size_t)c * S) : 0.f;
+      const float h = ok ? __ldg(xh + (size_t)c * S) : 0.f;
+      const float g = __ldg(gamma + c) * d;
+      m1 += g;
+      m2 = fmaf(g, h, m2);
+      if (keep) {
+#pragma unroll
+        for (int i = 0; i < LN_NC; ++i) if (i == n) { ag[i] = fmaf(d, h, ag[i]); ab[i] += d; }
+      } else {
+        const float sg = warp_sum(d * h), sb = warp_sum(d);
+        if (lane == 0) {
+          if (L.dgamma[t]) atomicAdd(L.dgamma[t] + c, sg);
+          if (L.dbeta[t]) atomicAdd(L.dbeta[t] + c, sb);
+        }
+      }
+    }
+    __syncthreads();                 // red[] of the previous group has been consumed
+    red[0][w][lane] = m1;
+    red[1][w][lane] = m2;
+    __syncthreads();
+    m1 = 0.f; m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { m1 += red[0][i][lane]; m2 += red[1][i][lane]; }
+    if (ok) {
+      m1 /= (float)C; m2 /= (float)C;
+      const float rstd = L.rstd[t][(size_t)b * S + v];
+      float* dx = L.dx[t] + off;
+      const float* add = L.dx_add[t] ? L.dx_add[t] + off : nullptr;
+      for (int c = w; c < C; c += 8) {
+        const float g = __ldg(gamma + c) * __ldg(dout + (size_t)c * S);
+        float r = rstd * (g - m1 - __ldg(xh + (size_t)c * S) * m2);
+        if (add) r = fmaf(L.dx_add_scale, __ldg(add + (size_t)c * S), r);
+        dx[(size_t)c * S] = r;
+      }
     }
   }
-  red[0][w][lane] = m1;
-  red[1][w][lane] = m2;
-  __syncthreads();
-  m1 = 0.f; m2 = 0.f;
+  if (keep) {
+    int n = 0;
+    for (int c = w; c < C; c += 8, ++n) {
+      float sg = 0.f, sb = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { m1 += red[0][i][lane]; m2 += red[1][i][lane]; }
-  if (!ok) return;
-  m1 /= (float)C; m2 /= (float)C;
-  const float rstd = L.rstd[t][(size_t)b * S + v];
-  float* dx = L.dx[t] + off;
-  const float* add = L.dx_add[t] ? L.dx_add[t] + off : nullptr;
-  for (int c = w; c < C; c += 8) {
-    const float g = __ldg(gamma + c) * __ldg(dout + (size_t)c * S);
-    float r = rstd * (g - m1 - __ldg(xh + (size_t)c * S) * m2);
-    if (add) r = fmaf(L.dx_add_scale, __ldg(add + (size_t)c * S), r);
-    dx[(size_t)c * S] = r;
+      for (int i = 0; i < LN_NC; ++i) if (i == n) { sg = ag[i]; sb = ab[i]; }
+      sg = warp_sum(sg); sb = warp_sum(sb);
+      if (lane == 0) {
+        if (L.dgamma[t]) atomicAdd(L.dgamma[t] + c, sg);
+        if (L.dbeta[t]) atomicAdd(L.dbeta[t] + c, sb);
+      }
+    }
   }
 }
 
 int ln_backward(const LnBwdBatch& L, cudaStream_t stream) {
   if (L.n <= 0) return VX_OK;
   prof_bytes(4.0 * L.n * L.B * (double)L.S * (3.0 * L.C + 1 + (L.dx_add[0] ? L.C : 0)));
-  VX_LAUNCH(ln_bwd_kernel, dim3(cdiv(L.S, 32), L.B, L.n), dim3(256), 0, stream, L);
+  int groups = 1;      // 32-voxel blocks per CTA: as many as leave >= ~2 CTAs per SM
+  while (groups < 8 && (long long)cdiv(L.S, 32 * groups * 2) * L.B * L.n >= 2 * kSMs) groups *= 2;
+  VX_LAUNCH(ln_bwd_kernel, dim3(cdiv(L.S, 32 * groups), L.B, L.n), dim3(256), 0, stream, L, groups);
   return check_launch("ln_bwd_kernel");
 }
 
