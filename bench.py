@@ -369,8 +369,10 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "patches/s", "n_gpus": world,
             "steps": steps, "warmup": 1, "ms_per_step": round(1e3 * patches / base["value"], 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "VeloxSeg AutoPET-II train step (models_config_autopetii + train_config_bs4), CPU path; "
-                                   "each step a bounded sample of 1 of the 4 patches", "parallelism": "host cores"},
+            "config": {"workload": "VeloxSeg AutoPET-II train step (models_config_autopetii + train_config_bs4): 4 patches "
+                                   "of 2x96^3 per GPU, CE+Dice x4 deep, 0.5 MSE recon, 2.0 SDKT, AdamW",
+                       "sample": "reference CPU path (oracle port); each timed step is a bounded sample of 1 of the 4 patches",
+                       "parallelism": "host cores"},
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "patches/s", "h2d_bytes_per_step": 0,
                                           "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
