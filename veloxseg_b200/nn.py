@@ -618,15 +618,47 @@ class Seg_Decoder(nn.Module):
             self.out_conv3 = nn.Conv3d(base_ch * 4, out_ch, 1, 1)
             self.out_conv4 = nn.Conv3d(base_ch * 8, out_ch, 1, 1)
 
-    def forward(self, enc1, enc2, enc3, enc4):
+    def forward(self, enc1, enc2, enc3, enc4, head_post=None):
+        """`head_post` (training, deep supervision, CUDA): callable applied to every head output (VeloxSeg passes its
+        `scale_prediction`).  The three low-resolution heads and their post-processing then run on a forked stream as soon
+        as their input exists, beside the rest of the decoder, instead of queueing behind `out_conv1` on the main stream
+        (~140 us of the step's critical path); under graph capture the fork is a parallel branch."""
+        side = None
+        if head_post is not None and self.training and self.deep_supervision and enc4.is_cuda and getattr(self, "fork_heads", True):
+            main = torch.cuda.current_stream(enc4.device)
+            if getattr(self, "_head_stream_dev", None) != enc4.device:
+                self._head_stream, self._head_stream_dev = torch.cuda.Stream(device=enc4.device), enc4.device
+            side = self._head_stream
+            heads = {}
+
+            def head(i, conv, feat):
+                side.wait_stream(main)                    # `feat` has just been produced on main
+                feat.record_stream(side)
+                with torch.cuda.stream(side):
+                    heads[i] = head_post(conv(feat))
+
+            head(4, self.out_conv4, enc4)
         up3 = self.layer3(self.layer_up3(enc4, addend=enc3))
+        if side is not None:
+            head(3, self.out_conv3, up3)
         up2 = self.layer2(self.layer_up2(up3, addend=enc2))
+        if side is not None:
+            head(2, self.out_conv2, up2)
         up1 = self.layer1(self.layer_up1(up2, addend=enc1))
         out = self.out_conv1(up1)
         if self.training:
+            pram = get_pram_matrix(up1)
+            if side is not None:
+                out = head_post(out)
+                main.wait_stream(side)
+                for t in heads.values():
+                    t.record_stream(main)
+                return [out, heads[2], heads[3], heads[4]], pram
             if self.deep_supervision:
-                return [out, self.out_conv2(up2), self.out_conv3(up3), self.out_conv4(enc4)], get_pram_matrix(up1)
-            return [out], get_pram_matrix(up1)
+                outs = [out, self.out_conv2(up2), self.out_conv3(up3), self.out_conv4(enc4)]
+            else:
+                outs = [out]
+            return ([head_post(o) for o in outs] if head_post is not None else outs), pram
         return out
 
 
@@ -702,8 +734,8 @@ class VeloxSeg(nn.Module):
                             a.record_stream(st)
                             e.record_stream(st)
                         rcs[m], rc_prams[m] = self.rc_decoders[m](*feats)
-            pred, dec_pram = self.decoder(*encs)
-            pred = [self.scale_prediction(p) for p in (pred if isinstance(pred, (list, tuple)) else [pred])]
+            self.decoder.fork_heads = fork
+            pred, dec_pram = self.decoder(*encs, head_post=self.scale_prediction)      # heads resized inside (forked stream)
             if fork:
                 for m, st in enumerate(streams):
                     main.wait_stream(st)
