@@ -257,6 +257,18 @@ int vx_patch_embed_fwd(const vx_patch_embed_desc* d, const void* const* in, void
 int vx_patch_embed_bwd(const vx_patch_embed_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Bias + 3-D PixelShuffle -- model/components/superpixel.py:15 behind `out_conv1` / the reconstruction `out_conv`
+ * (model/Decoder.py:73-76,150-153): y[b, c, d s + s1, h s + s2, w s + s3] = z[b, ((c s + s1) s + s2) s + s3, d, h, w] + bias.
+ * The convolution in front runs without its bias (the layout half).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, C, scale, d, h, w;    /* C = channels after the shuffle; z has C * scale^3 channels, extent (d, h, w) */
+} vx_pixel_shuffle_desc;
+/* fwd in: z, bias (C * scale^3) or NULL   out: y (B, C, d s, h s, w s)          bwd in: dy   out: dz, db or NULL */
+int vx_pixel_shuffle_fwd(const vx_pixel_shuffle_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
+int vx_pixel_shuffle_bwd(const vx_pixel_shuffle_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * AdamW step over every parameter tensor in one launch (torch.optim.AdamW semantics: decoupled weight decay, bias
  * correction; the reference's optimiser, utils/runtime.py).  SURVEY.md section 8f row 4.
  *   in[0]  int64 table (n_tensors, 4): parameter pointer, gradient pointer (0 = no gradient: skipped), offset of the tensor

@@ -383,3 +383,20 @@ def test_lnpw_backward_multi_group_ctas(emu):
     got = ops.lnpw_bwd_raw(emu, 0, dy, xhat, rstd, lw, lb, W)
     for i, (g, r) in enumerate(zip(got, gr)):
         assert close(g, r, rtol=3e-4, atol=2e-5), (i, rel_err(g, r))
+
+
+@pytest.mark.parametrize("B,C,s,size", [(2, 2, 4, (3, 4, 5)), (1, 3, 2, (4, 4, 6)), (2, 1, 4, (2, 3, 4))])
+def test_pixel_shuffle_bias(emu, B, C, s, size):
+    """bias + 3-D pixel shuffle vs the reference permutation (superpixel.py:15) and its autograd."""
+    from veloxseg_b200 import ops
+    from veloxseg_b200.nn import PixelShuffle
+    torch.manual_seed(0)
+    z = torch.randn(B, C * s ** 3, *size, requires_grad=True)
+    bias = torch.randn(C * s ** 3, requires_grad=True)
+    yr = PixelShuffle(s)(z + bias[None, :, None, None, None])
+    y = ops.pixel_shuffle_fwd_raw(emu, 0, z.detach(), bias.detach(), s)
+    assert torch.equal(y, yr.detach())
+    dy = torch.randn_like(yr)
+    gz, gb = torch.autograd.grad(yr, [z, bias], dy)
+    dz, db = ops.pixel_shuffle_bwd_raw(emu, 0, dy, s, True)
+    assert torch.equal(dz, gz) and close(db, gb, rtol=1e-5, atol=1e-5)

@@ -398,3 +398,20 @@ def test_adamw_one_launch_matches_torch(ops):
     torch.cuda.synchronize()
     worst = max(float((p.detach() - r.detach()).abs().max() / (r.detach().abs().max() + 1e-12)) for p, r in zip(ps, ref))
     assert worst < 1e-5, worst
+
+
+@pytest.mark.parametrize("B,C,s,size", [(4, 2, 4, (24, 24, 24)), (2, 1, 4, (32, 32, 16)), (1, 4, 4, (24, 24, 24))])
+def test_pixel_shuffle_bias(ops, B, C, s, size):
+    """bias + 3-D pixel shuffle (out_conv1 / reconstruction out_conv tail) vs the reference permutation and its autograd."""
+    from veloxseg_b200.nn import PixelShuffle
+    torch.manual_seed(0)
+    z = torch.randn(B, C * s ** 3, *size, device=DEV, requires_grad=True)
+    bias = torch.randn(C * s ** 3, device=DEV, requires_grad=True)
+    yr = PixelShuffle(s)(z + bias[None, :, None, None, None])
+    zg, bg = z.detach().clone().requires_grad_(True), bias.detach().clone().requires_grad_(True)
+    y = ops.pixel_shuffle_bias(zg, bg, s)
+    assert torch.equal(y, yr)
+    dy = torch.randn_like(yr)
+    gz, gb = torch.autograd.grad(yr, [z, bias], dy)
+    dz, db = torch.autograd.grad(y, [zg, bg], dy)
+    assert torch.equal(dz, gz) and close(db, gb, rtol=1e-4, atol=1e-3)

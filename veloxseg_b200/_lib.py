@@ -70,6 +70,10 @@ class PatchEmbedDesc(C.Structure):
                 ("C_out", C.c_int32), ("patch", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
 
 
+class PixelShuffleDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("C", C.c_int32), ("scale", C.c_int32), ("d", C.c_int32), ("h", C.c_int32), ("w", C.c_int32)]
+
+
 class AdamwDesc(C.Structure):
     _fields_ = [("n_chunks", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("weight_decay", C.c_float)]
@@ -88,7 +92,7 @@ SYMBOLS = [
     "vx_lnpw_workspace", "vx_lnpw_fwd", "vx_lnpw_bwd",
     "vx_resize_workspace", "vx_resize_trilinear_fwd", "vx_resize_trilinear_bwd",
     "vx_segloss_workspace", "vx_segloss_fwd", "vx_segloss_bwd",
-    "vx_patch_embed_fwd", "vx_patch_embed_bwd", "vx_adamw_step",
+    "vx_patch_embed_fwd", "vx_patch_embed_bwd", "vx_pixel_shuffle_fwd", "vx_pixel_shuffle_bwd", "vx_adamw_step",
 ]
 
 _WS_OPS = {"jlc", "mixer", "pwa_block", "gram_fwd", "lnpw", "segloss"}
@@ -133,7 +137,7 @@ class VxLib:
             f.restype = C.c_int
             f.argtypes = [vp, vp, vp, vp, sz, vp]
         for name in ("vx_inorm_fwd", "vx_inorm_bwd", "vx_gram_bwd", "vx_sdkt_loss_fwd", "vx_sdkt_loss_bwd",
-                     "vx_resize_trilinear_fwd", "vx_segloss_bwd", "vx_patch_embed_fwd", "vx_patch_embed_bwd", "vx_adamw_step"):
+                     "vx_resize_trilinear_fwd", "vx_segloss_bwd", "vx_patch_embed_fwd", "vx_patch_embed_bwd", "vx_pixel_shuffle_fwd", "vx_pixel_shuffle_bwd", "vx_adamw_step"):
             f = getattr(self.c, name)
             f.restype = C.c_int
             f.argtypes = [vp, vp, vp, vp]

@@ -147,6 +147,75 @@ __global__ void __launch_bounds__(256) patch_embed_wgrad_kernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------------
+// bias + 3-D pixel shuffle: y[b, c, d s + s1, h s + s2, w s + s3] = z[b, ((c s + s1) s + s2) s + s3, d, h, w] + bias[channel]
+// (superpixel.py:15 behind out_conv1 / the reconstruction out_conv, Decoder.py:73-76,150-153).  The library convolution runs
+// without its bias; this one pass replaces its 28 MB bias-add pass and the 28 MB permuted copy.  Thread = (b, c, s1, s2, d,
+// h, w): s channel planes are read with the lanes along w, the s outputs are contiguous (one 16-byte store for s = 4).
+// Backward: the inverse permutation plus the bias gradient (block-reduced, one atomic per channel and CTA).
+// ---------------------------------------------------------------------------------------------------
+struct PsArgs { const float* src; const float* bias; float* dst; float* db; int B, C, s, d, h, w; };
+constexpr int PS_MAX_S = 4;
+
+__global__ void __launch_bounds__(256) pixel_shuffle_fwd_kernel(const __grid_constant__ PsArgs A) {
+  const int s = A.s, s2n = s * s, dhw = A.d * A.h * A.w;
+  const int cs = blockIdx.y;                         // (c, s1, s2)
+  const int c = cs / s2n, s1 = (cs / s) % s, s2 = cs % s;
+  const long long total = (long long)A.B * dhw;
+  const int H = A.h * s, W = A.w * s, D = A.d * s;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(e % dhw), b = (int)(e / dhw);
+    const int x = v % A.w, y = (v / A.w) % A.h, z = v / (A.w * A.h);
+    const int ch0 = cs * s;
+    float o[PS_MAX_S];
+#pragma unroll
+    for (int s3 = 0; s3 < PS_MAX_S; ++s3)
+      if (s3 < s) o[s3] = __ldg(A.src + ((size_t)b * A.C * s2n * s + ch0 + s3) * dhw + v) + (A.bias ? __ldg(A.bias + ch0 + s3) : 0.f);
+    float* q = A.dst + ((((size_t)b * A.C + c) * D + z * s + s1) * H + y * s + s2) * W + (size_t)x * s;
+    if (s == 4 && (((uintptr_t)q) & 15) == 0) {
+      *reinterpret_cast<float4*>(q) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int s3 = 0; s3 < PS_MAX_S; ++s3) if (s3 < s) q[s3] = o[s3];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pixel_shuffle_bwd_kernel(const __grid_constant__ PsArgs A) {
+  __shared__ float red[33];
+  const int s = A.s, s2n = s * s, dhw = A.d * A.h * A.w;
+  const int cs = blockIdx.y;
+  const int c = cs / s2n, s1 = (cs / s) % s, s2 = cs % s;
+  const long long total = (long long)A.B * dhw;
+  const int H = A.h * s, W = A.w * s, D = A.d * s;
+  float acc[PS_MAX_S];
+#pragma unroll
+  for (int s3 = 0; s3 < PS_MAX_S; ++s3) acc[s3] = 0.f;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(e % dhw), b = (int)(e / dhw);
+    const int x = v % A.w, y = (v / A.w) % A.h, z = v / (A.w * A.h);
+    const float* q = A.src + ((((size_t)b * A.C + c) * D + z * s + s1) * H + y * s + s2) * W + (size_t)x * s;
+    float g[PS_MAX_S];
+    if (s == 4 && (((uintptr_t)q) & 15) == 0) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(q));
+      g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+    } else {
+#pragma unroll
+      for (int s3 = 0; s3 < PS_MAX_S; ++s3) g[s3] = s3 < s ? __ldg(q + s3) : 0.f;
+    }
+#pragma unroll
+    for (int s3 = 0; s3 < PS_MAX_S; ++s3)
+      if (s3 < s) { A.dst[((size_t)b * A.C * s2n * s + cs * s + s3) * dhw + v] = g[s3]; acc[s3] += g[s3]; }
+  }
+  if (A.db) {
+#pragma unroll
+    for (int s3 = 0; s3 < PS_MAX_S; ++s3) {
+      const float t = block_sum(acc[s3], red);
+      if (threadIdx.x == 0 && s3 < s) atomicAdd(A.db + cs * s + s3, t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // AdamW
 // ---------------------------------------------------------------------------------------------------
 struct AdamArgs {
@@ -241,6 +310,51 @@ extern "C" int vx_patch_embed_bwd(const vx_patch_embed_desc* d, const void* cons
   VX_SET_SMEM(patch_embed_wgrad_kernel, smem);
   VX_LAUNCH(patch_embed_wgrad_kernel, dim3(A.B * cdiv(s, PE_VC)), dim3(256), smem, st, A);
   return check_launch("patch_embed_wgrad_kernel");
+}
+
+static int ps_args(const vx_pixel_shuffle_desc* d, PsArgs& A) {
+  if (!d || d->B <= 0 || d->C <= 0 || d->scale <= 0 || d->scale > PS_MAX_S || d->d <= 0 || d->h <= 0 || d->w <= 0) {
+    set_error("pixel_shuffle: bad descriptor (scale <= %d)", PS_MAX_S); return VX_ERR_BAD_DESC;
+  }
+  A.B = d->B; A.C = d->C; A.s = d->scale; A.d = d->d; A.h = d->h; A.w = d->w;
+  return VX_OK;
+}
+
+static dim3 ps_grid(const PsArgs& A) {
+  const long long total = (long long)A.B * A.d * A.h * A.w;
+  int gx = cdiv(total, 256 * 2);
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  return dim3(gx, A.C * A.s * A.s);
+}
+
+extern "C" int vx_pixel_shuffle_fwd(const vx_pixel_shuffle_desc* d, const void* const* in, void* const* out, vx_stream_t stream) {
+  PsArgs A{};
+  int rc = ps_args(d, A);
+  if (rc != VX_OK) return rc;
+  prof_scope("pixel_shuffle_fwd B%d C%d s%d %dx%dx%d", d->B, d->C, d->scale, d->d, d->h, d->w);
+  A.src = (const float*)in[0]; A.bias = (const float*)in[1]; A.dst = (float*)out[0];
+  prof_bytes(8.0 * d->B * d->C * (double)d->scale * d->scale * d->scale * d->d * d->h * d->w);
+  VX_LAUNCH(pixel_shuffle_fwd_kernel, ps_grid(A), dim3(256), 0, (cudaStream_t)stream, A);
+  return check_launch("pixel_shuffle_fwd_kernel");
+}
+
+extern "C" int vx_pixel_shuffle_bwd(const vx_pixel_shuffle_desc* d, const void* const* in, void* const* out, vx_stream_t stream) {
+  PsArgs A{};
+  int rc = ps_args(d, A);
+  if (rc != VX_OK) return rc;
+  prof_scope("pixel_shuffle_bwd B%d C%d s%d %dx%dx%d", d->B, d->C, d->scale, d->d, d->h, d->w);
+  A.src = (const float*)in[0]; A.dst = (float*)out[0]; A.db = (float*)out[1];
+  cudaStream_t st = (cudaStream_t)stream;
+  if (A.db) {
+    ZeroList zl;
+    zl.add(A.db, (size_t)d->C * d->scale * d->scale * d->scale);
+    rc = zero_many(zl, st);
+    if (rc != VX_OK) return rc;
+  }
+  prof_bytes(8.0 * d->B * d->C * (double)d->scale * d->scale * d->scale * d->d * d->h * d->w);
+  VX_LAUNCH(pixel_shuffle_bwd_kernel, ps_grid(A), dim3(256), 0, st, A);
+  return check_launch("pixel_shuffle_bwd_kernel");
 }
 
 extern "C" int vx_adamw_step(const vx_adamw_desc* d, const void* const* in, void* const* out, vx_stream_t stream) {

@@ -365,6 +365,16 @@ class PixelShuffle(nn.Module):
         return x.view(B, c, s, s, s, D, H, W).permute(0, 1, 5, 2, 6, 3, 7, 4).reshape(B, c, D * s, H * s, W * s)
 
 
+def conv_shuffle(seq: nn.Sequential, x):
+    """`Sequential(Conv3d, PixelShuffle)` (out_conv1 / reconstruction out_conv): on CUDA the library convolution runs without
+    its bias and the bias add + shuffle are one kernel; parameters and state_dict keys are those of the Sequential."""
+    conv, ps = seq[0], seq[1]
+    if x.is_cuda and isinstance(ps, PixelShuffle) and ps.scale <= 4 and x.dtype == torch.float32:
+        z = F.conv3d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        return ops.pixel_shuffle_bias(z, conv.bias, ps.scale)
+    return seq(x)
+
+
 class ModalMixer(nn.Sequential):
     """`nn.Sequential(Conv3d 1x1, InstanceNorm3d)` of Encoder.py:334-337 / Decoder.py:54-57 with a fused forward:
     keeps the Sequential's state_dict keys (`0.weight`, `0.bias`); accepts either the concatenated tensor (the
@@ -591,8 +601,8 @@ class RC_Decoder(nn.Module):
         up2 = self.layer2(self.layer_up2(up3, addend=e2))
         up1 = self.layer1(self.layer_up1(up2, addend=e1))
         if self.training:
-            return self.out_conv(up1), get_pram_matrix(up1)
-        return self.out_conv(up1)
+            return conv_shuffle(self.out_conv, up1), get_pram_matrix(up1)
+        return conv_shuffle(self.out_conv, up1)
 
 
 class Seg_Decoder(nn.Module):
@@ -645,7 +655,7 @@ class Seg_Decoder(nn.Module):
         if side is not None:
             head(2, self.out_conv2, up2)
         up1 = self.layer1(self.layer_up1(up2, addend=enc1))
-        out = self.out_conv1(up1)
+        out = conv_shuffle(self.out_conv1, up1)
         if self.training:
             pram = get_pram_matrix(up1)
             if side is not None:

@@ -676,3 +676,45 @@ def patch_embed(x: Tensor, c_off: int, weight: Tensor, bias: Optional[Tensor]) -
         raise RuntimeError("veloxseg: patch_embed has no data gradient (network input); use the torch convolution")
     return _PatchEmbed.apply(x.contiguous(), int(c_off), weight, bias)
 
+
+# ----------------------------------------------------------------------------------------------------
+# bias + 3-D pixel shuffle behind a bias-free convolution (out_conv1 / reconstruction out_conv)
+# ----------------------------------------------------------------------------------------------------
+def pixel_shuffle_fwd_raw(lib, stream, z: Tensor, bias: Optional[Tensor], scale: int):
+    from ._lib import PixelShuffleDesc
+    z = _chk(z, "z")
+    B, Cs, d, h, w = z.shape
+    C_ = Cs // scale ** 3
+    desc = PixelShuffleDesc(B, C_, scale, d, h, w)
+    y = torch.empty((B, C_, d * scale, h * scale, w * scale), dtype=_f32, device=z.device)
+    lib.call("vx_pixel_shuffle_fwd", desc, [z, _chk(bias, "bias") if bias is not None else None], [y], stream)
+    return y
+
+
+def pixel_shuffle_bwd_raw(lib, stream, dy: Tensor, scale: int, with_bias: bool):
+    from ._lib import PixelShuffleDesc
+    dy = _chk(dy, "dy")
+    B, C_, D, H, W = dy.shape
+    desc = PixelShuffleDesc(B, C_, scale, D // scale, H // scale, W // scale)
+    dz = torch.empty((B, C_ * scale ** 3, D // scale, H // scale, W // scale), dtype=_f32, device=dy.device)
+    db = torch.empty((C_ * scale ** 3,), dtype=_f32, device=dy.device) if with_bias else None
+    lib.call("vx_pixel_shuffle_bwd", desc, [dy], [dz, db], stream)
+    return dz, db
+
+
+class _PixelShuffleBias(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, bias, scale):
+        ctx.scale, ctx.has_bias = int(scale), bias is not None
+        return pixel_shuffle_fwd_raw(_lib.get_lib(), _stream(z), z, bias, int(scale))
+
+    @staticmethod
+    def backward(ctx, dy):
+        dz, db = pixel_shuffle_bwd_raw(_lib.get_lib(), _stream(dy), dy.contiguous(), ctx.scale, ctx.has_bias)
+        return dz, db, None
+
+
+def pixel_shuffle_bias(z: Tensor, bias: Optional[Tensor], scale: int) -> Tensor:
+    """PixelShuffle3d(scale)(z + bias[None, :, None, None, None]) in one pass (z: output of a bias-free convolution)."""
+    return _PixelShuffleBias.apply(z.contiguous(), bias, int(scale))
+
