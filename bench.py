@@ -26,8 +26,17 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-CFG_NAME = "autopetii"
+CFG_NAME = "autopetii"      # --workload: autopetii = BASELINE configs[1] (default, the headline), brats2021 = configs[2]
 PATCHES = 4
+CFG_TITLE = {"autopetii": "AutoPET-II", "brats2021": "BraTS2021", "hecktor2022": "Hecktor2022"}
+
+
+def workload_name(cfg_name):
+    from veloxseg_b200.configs import MODEL_CONFIGS
+    cfg = MODEL_CONFIGS[cfg_name]
+    return ("VeloxSeg %s train step (models_config_%s + train_config_bs4): %d patches of %dx%s per GPU, CE+Dice x4 deep, "
+            "0.5 MSE recon, 2.0 SDKT, AdamW" % (CFG_TITLE[cfg_name], cfg_name, PATCHES, sum(cfg["in_ch"]),
+                                                 "96^3" if cfg["input_size"] == [96, 96, 96] else "x".join(map(str, cfg["input_size"]))))
 METRIC = "train patches/s"
 L2_FLUSH_BYTES = 256 << 20
 
@@ -108,7 +117,7 @@ def run_ours(args, rank, world, local_rank):
     torch.backends.cudnn.allow_tf32 = args.library_convs == "tf32"
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = os.environ.get("VX_CUDNN_BENCHMARK", "1") == "1"
-    cfg = MODEL_CONFIGS[CFG_NAME]
+    cfg = MODEL_CONFIGS[args.workload]
     torch.manual_seed(12345)
     model = VeloxSeg(**cfg)
     ts = TrainStep(model, len(cfg["in_ch"]), dev, lr=TRAIN["lr"], weight_decay=TRAIN["weight_decay"],
@@ -267,8 +276,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": round(total_patches / (ms_total * 1e-3), 3), "unit": "patches/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "VeloxSeg AutoPET-II train step (models_config_autopetii + train_config_bs4): 4 patches "
-                               "of 2x96^3 per GPU, CE+Dice x4 deep, 0.5 MSE recon, 2.0 SDKT, AdamW",
+        "config": {"workload": workload_name(args.workload),
                    "patches_per_gpu": PATCHES, "global_patches": PATCHES * world, "parallelism": f"dp{world}",
                    "cache": "L2 flushed (256 MiB memset) between timed steps",
                    "launch": ("eager launches" if not used_graph else "whole step replayed as one CUDA graph" if world == 1 else
@@ -286,7 +294,7 @@ def run_ours(args, rank, world, local_rank):
     if infer is not None:
         line["infer"] = infer
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_port(steps=1, patches=1, threads=None)
+        line["cpu_baseline"] = cpu_port(steps=1, patches=1, threads=None, cfg_name=args.workload)
     print(json.dumps(line), flush=True)
 
 
@@ -327,14 +335,14 @@ def run_infer(rank, world, dev, reps=3):
                        "fg_voxels": int(seg.sum())}}
 
 
-def cpu_port(steps, patches, threads):
+def cpu_port(steps, patches, threads, cfg_name=CFG_NAME):
     """The oracle's restatement of the reference CPU path: train step (fwd + full loss + bwd + AdamW) on host cores."""
     from oracle import veloxseg_oracle as O
     from veloxseg_b200.configs import MODEL_CONFIGS, TRAIN
     from veloxseg_b200.nn import VeloxSeg
     cores = threads or (os.cpu_count() or 1)
     torch.set_num_threads(cores)
-    cfg = MODEL_CONFIGS[CFG_NAME]
+    cfg = MODEL_CONFIGS[cfg_name]
     torch.manual_seed(12345)
     m = VeloxSeg(**cfg)
     p = {k: (v.detach().clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in m.state_dict().items()}
@@ -349,14 +357,14 @@ def cpu_port(steps, patches, threads):
         loss = O.total_loss(outs, y, x, spec.M, TRAIN["deep_Loss_weight"], TRAIN["RC_Loss_weight"], TRAIN["Feature_Loss_weight"])
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
     step()      # warm-up (allocator, thread pool)
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
     return {"value": round(steps * patches / dt, 4), "unit": "patches/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} train step(s) of {patches} patch(es) (2x96^3, fp32, dropout off) after 1 warm-up step, "
+            "sample": f"{steps} train step(s) of {patches} patch(es) ({sum(cfg['in_ch'])}x{'x'.join(map(str, cfg['input_size']))}, fp32, dropout off) after 1 warm-up step, "
                       f"torch CPU with {cores} threads"}
 
 
@@ -365,12 +373,11 @@ def run_reference(args, rank, world):
         return
     patches = 1
     steps = max(1, min(args.steps, 5))
-    base = cpu_port(steps=steps, patches=patches, threads=None)
+    base = cpu_port(steps=steps, patches=patches, threads=None, cfg_name=args.workload)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "patches/s", "n_gpus": world,
             "steps": steps, "warmup": 1, "ms_per_step": round(1e3 * patches / base["value"], 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "VeloxSeg AutoPET-II train step (models_config_autopetii + train_config_bs4): 4 patches "
-                                   "of 2x96^3 per GPU, CE+Dice x4 deep, 0.5 MSE recon, 2.0 SDKT, AdamW",
+            "config": {"workload": workload_name(args.workload),
                        "sample": "reference CPU path (oracle port); each timed step is a bounded sample of 1 of the 4 patches",
                        "parallelism": "host cores"},
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "patches/s", "h2d_bytes_per_step": 0,
@@ -384,6 +391,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=CFG_NAME, choices=sorted(CFG_TITLE),
+                    help="model config of the train step: autopetii = BASELINE configs[1] (the headline metric), brats2021 = configs[2]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the secondary all-fp32 timing")
     ap.add_argument("--no-infer", action="store_true", help="skip the sliding-window inference measurement")
