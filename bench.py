@@ -302,7 +302,7 @@ def run_infer(rank, world, dev, reps=3):
     """BASELINE.json configs[3]: Hecktor2022 sliding-window inference on one synthetic PET/CT volume (1,2,320,320,256),
     roi (128,128,64), overlap 0.25 -> 45 windows, sharded round-robin over ranks, partial sums all-reduced."""
     from veloxseg_b200.configs import MODEL_CONFIGS, TRAIN
-    from veloxseg_b200.inference import GraphedPredictor, sliding_window_predict, window_starts
+    from veloxseg_b200.inference import GraphedPredictor, sliding_window_labels, sliding_window_predict, window_starts
     from veloxseg_b200.nn import VeloxSeg
     cfg = MODEL_CONFIGS["hecktor2022"]
     torch.manual_seed(12345)
@@ -312,15 +312,21 @@ def run_infer(rank, world, dev, reps=3):
     roi, sw = cfg["input_size"], 4
     pred = GraphedPredictor(model, sw, vol_shape[1], roi, dev)
     nwin = len(window_starts(vol_shape[2:], roi, TRAIN["sw_overlap"]))
+    sharded_io = os.environ.get("VX_INFER_IO", "replicated") == "sharded"
+    seg_h = torch.zeros(vol_shape[2:], dtype=torch.uint8).pin_memory()
     times = []
     for i in range(reps + 1):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        vol = vol_h.to(dev, non_blocking=True)                      # host volume in, host label map out
-        out = sliding_window_predict(vol, pred, roi, sw_batch_size=sw, overlap=TRAIN["sw_overlap"])
-        seg = out.argmax(1).to(torch.uint8).cpu()
+        if sharded_io:                                              # opt-in (VX_INFER_IO=sharded), see sliding_window_labels
+            seg = sliding_window_labels(vol_h, pred, roi, dev, sw_batch_size=sw, overlap=TRAIN["sw_overlap"], out_host=seg_h)
+            seg = seg_h if seg is None else seg                     # ranks other than 0 hold no result
+        else:
+            vol = vol_h.to(dev, non_blocking=True)                  # host volume in, host label map out
+            out = sliding_window_predict(vol, pred, roi, sw_batch_size=sw, overlap=TRAIN["sw_overlap"])
+            seg = out.argmax(1).to(torch.uint8).cpu()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if i:
@@ -331,7 +337,10 @@ def run_infer(rank, world, dev, reps=3):
     return {"metric": "sliding-window infer ms/volume", "value": round(float(t.item()) * 1e3, 2), "unit": "ms/volume",
             "higher_is_better": False, "scaling": "strong", "n_gpus": world,
             "config": {"workload": "VeloxSeg Hecktor2022 eval, volume 2x320x320x256, roi 128x128x64, overlap 0.25",
-                       "windows": nwin, "sw_batch": sw, "timed": "H2D volume + windows + all-reduce + argmax + D2H labels, best of %d" % reps,
+                       "windows": nwin, "sw_batch": sw,
+                       "io": ("1/world of the host volume per rank + all-gather; reduce-scatter, arg-max per slab, label gather"
+                              if sharded_io else "every rank copies the whole host volume; all-reduce of the logit sums"),
+                       "timed": "H2D volume + windows + all-reduce + argmax + D2H labels, best of %d" % reps,
                        "fg_voxels": int(seg.sum())}}
 
 

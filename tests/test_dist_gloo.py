@@ -6,6 +6,9 @@
   partial logit sums equals the single-process result on every rank (ragged volume that needs padding, a volume with
   fewer windows than ranks, batch > 1).
 
+* sliding_window_labels: the sharded-IO variant (1/world of the host volume per rank + all-gather, reduce-scatter of the
+  partial sums in slabs, arg-max per slab, label gather) gives rank 0 the arg-max of the single-process blend.
+
 The predictor here is a plain torch function: the product model needs the sm_100a library and is covered by -m gpu.
 """
 import os
@@ -120,3 +123,38 @@ def test_sharded_sliding_window_matches_single_process(tmp_path):
         for r in range(WORLD):
             got = torch.load(out + f".{r}")[ci]
             assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6), (ci, r, float((got - ref).abs().max()))
+
+
+LABEL_CASES = CASES[:2] + [((1, 2, 21, 16, 12), (8, 8, 4))]      # odd first axis: slab padding plane; 3 x 3 x 4 windows
+
+
+def _labels_worker(rank, port, out):
+    from veloxseg_b200.inference import sliding_window_labels
+    _init(rank, port)
+    try:
+        pred = _predictor()
+        res = []
+        for shape, roi in LABEL_CASES:
+            x = torch.randn(*shape, generator=torch.Generator().manual_seed(5))
+            res.append(sliding_window_labels(x, pred, roi, "cpu", sw_batch_size=2, overlap=0.25))
+        torch.save(res, out + f".{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_io_labels_match_single_process_argmax(tmp_path):
+    from veloxseg_b200.inference import sliding_window_labels, sliding_window_predict
+    out = str(tmp_path / "lab.pt")
+    mp.spawn(_labels_worker, args=(_free_port(), out), nprocs=WORLD, join=True)
+    pred = _predictor()
+    got0, got1 = torch.load(out + ".0"), torch.load(out + ".1")
+    for ci, (shape, roi) in enumerate(LABEL_CASES):
+        x = torch.randn(*shape, generator=torch.Generator().manual_seed(5))
+        ref = sliding_window_predict(x, pred, roi, sw_batch_size=2, overlap=0.25, shard=False)[0]
+        single = sliding_window_labels(x, pred, roi, "cpu", sw_batch_size=2, overlap=0.25)     # no process group here
+        assert single.dtype == torch.uint8 and torch.equal(single, ref.argmax(0).to(torch.uint8))    # same sum order: bit-exact
+        assert got1[ci] is None and got0[ci].shape == tuple(shape[2:])
+        top2 = ref.topk(2, dim=0).values
+        decided = (top2[0] - top2[1]) > 1e-5             # the sharded sum folds windows in another order: near-ties may flip
+        assert torch.equal(got0[ci][decided], single[decided]), ci
+        assert float((got0[ci] != single).float().mean()) < 1e-3

@@ -20,14 +20,20 @@ def scan_interval(image: Sequence[int], roi: Sequence[int], overlap: float) -> L
     return [int(r) if r == i else max(int(r * (1 - overlap)), 1) for i, r in zip(image, roi)]
 
 
-def window_starts(image: Sequence[int], roi: Sequence[int], overlap: float) -> List[Tuple[int, int, int]]:
-    """dense_patch_slices: per axis ceil(image/interval) candidates up to the first that reaches the border, the last
-    one clamped back to fit; enumeration with the first spatial axis slowest."""
+def axis_starts(image: Sequence[int], roi: Sequence[int], overlap: float) -> List[List[int]]:
+    """dense_patch_slices, one axis at a time: ceil(image/interval) candidates up to the first that reaches the border,
+    the last one clamped back to fit."""
     per_axis = []
     for i, r, s in zip(image, roi, scan_interval(image, roi, overlap)):
         num = int(math.ceil(i / s))
         n = next((d + 1 for d in range(num) if d * s + r >= i), 1)
         per_axis.append([d * s - max(d * s + r - i, 0) for d in range(n)])
+    return per_axis
+
+
+def window_starts(image: Sequence[int], roi: Sequence[int], overlap: float) -> List[Tuple[int, int, int]]:
+    """The window list is the Cartesian product of the per-axis starts, first spatial axis slowest."""
+    per_axis = axis_starts(image, roi, overlap)
     return [(a, b, c) for a in per_axis[0] for b in per_axis[1] for c in per_axis[2]]
 
 
@@ -36,6 +42,19 @@ def count_map(image: Sequence[int], roi: Sequence[int], starts, device, dtype=to
     for a, b, c in starts:
         cnt[:, :, a:a + roi[0], b:b + roi[1], c:c + roi[2]] += 1
     return cnt
+
+
+def axis_counts(image: Sequence[int], roi: Sequence[int], per_axis, device, dtype=torch.float32) -> List[torch.Tensor]:
+    """count_map factorised: the windows are a Cartesian product, so count(x, y, z) = cx[x] * cy[y] * cz[z] (small
+    integers, exact in fp32) -- three 1-D tables instead of one slice-add over the volume per window."""
+    out = []
+    for n, r, st in zip(image, roi, per_axis):
+        c = [0] * n
+        for s0 in st:
+            for j in range(s0, s0 + r):
+                c[j] += 1
+        out.append(torch.tensor(c, dtype=dtype, device=device))
+    return out
 
 
 def _logits(y):
@@ -79,6 +98,90 @@ def sliding_window_predict(inputs: torch.Tensor, predictor: Callable, roi_size: 
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
     out = out / count_map(image, roi_size, starts, out.device, out.dtype)
     return out[:, :, lo[0]:lo[0] + size[0], lo[1]:lo[1] + size[1], lo[2]:lo[2] + size[2]]
+
+
+@torch.no_grad()
+def sliding_window_labels(volume_host: torch.Tensor, predictor: Callable, roi_size: Sequence[int], device,
+                          sw_batch_size: int = 2, overlap: float = 0.25, group=None, dst: int = 0,
+                          out_host: torch.Tensor | None = None):
+    """Host volume (1, C, X, Y, Z) in -> host uint8 label map (X, Y, Z) = argmax of the blended logits, on rank `dst`
+    (None on the other ranks).  Same arithmetic as `sliding_window_predict(...).argmax(1)` (utils/inference_petct.py:214-233
+    takes the arg-max of the sliding-window logits); what changes is where the bytes travel when windows are sharded:
+
+    * in:  rank r copies 1/world of the (contiguous) host volume over its own PCIe link and the ranks all-gather the
+           pieces over NVLink, instead of every rank pulling the whole volume from host memory at once;
+    * out: the partial sums are reduce-scattered in slabs of the first spatial axis, each rank divides by the count map
+           and takes the arg-max of its slab only, and the 1-byte labels (not the n_cls fp32 logits) are gathered;
+    * the count map is the outer product of three per-axis tables (`axis_counts`).
+
+    Every rank calls this with the same host volume (as the reference's per-rank data loader would supply it).
+    """
+    assert volume_host.dim() == 5 and volume_host.shape[0] == 1, "one volume per call (the reference infers batch 1)"
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    device = torch.device(device)
+    C = volume_host.shape[1]
+    size = list(volume_host.shape[2:])
+    host_flat = volume_host.contiguous().view(-1)
+    n = host_flat.numel()
+    chunk = -(-n // world)
+    lo_e, hi_e = min(rank * chunk, n), min((rank + 1) * chunk, n)
+    if world > 1:
+        piece = torch.empty(chunk, dtype=volume_host.dtype, device=device)
+        piece[:hi_e - lo_e].copy_(host_flat[lo_e:hi_e], non_blocking=True)
+        flat = torch.empty(world * chunk, dtype=volume_host.dtype, device=device)
+        dist.all_gather_into_tensor(flat, piece, group=group)
+    else:
+        flat = host_flat.to(device, non_blocking=True)
+    inputs = flat[:n].view(1, C, *size)
+    pads = [max(r - s, 0) for r, s in zip(roi_size, size)]
+    lo = [p // 2 for p in pads]
+    if any(pads):
+        inputs = F.pad(inputs, [lo[2], pads[2] - lo[2], lo[1], pads[1] - lo[1], lo[0], pads[0] - lo[0]])
+    image = list(inputs.shape[2:])
+    per_axis = axis_starts(image, roi_size, overlap)
+    starts = [(a, b, c) for a in per_axis[0] for b in per_axis[1] for c in per_axis[2]]
+    xs = -(-image[0] // world)                      # slab thickness; the accumulator is padded to world * xs planes
+    mine = [i for i in range(len(starts)) if i % world == rank]
+    acc = None
+    for g in range(0, len(mine), sw_batch_size):
+        ids = mine[g:g + sw_batch_size]
+        win = torch.cat([inputs[:, :, a:a + roi_size[0], b:b + roi_size[1], c:c + roi_size[2]]
+                         for a, b, c in (starts[i] for i in ids)])
+        y = _logits(predictor(win))
+        if acc is None:
+            acc = torch.zeros((y.shape[1], world * xs, image[1], image[2]), dtype=y.dtype, device=y.device)
+        for k, i in enumerate(ids):
+            a, b, c = starts[i]
+            acc[:, a:a + roi_size[0], b:b + roi_size[1], c:c + roi_size[2]] += y[k]
+    if acc is None:         # more ranks than windows
+        n_cls = _logits(predictor(inputs[:, :, :roi_size[0], :roi_size[1], :roi_size[2]])).shape[1]
+        acc = torch.zeros((n_cls, world * xs, image[1], image[2]), dtype=inputs.dtype, device=device)
+    n_cls = acc.shape[0]
+    if world > 1:
+        send = acc.view(n_cls, world, xs, image[1], image[2]).permute(1, 0, 2, 3, 4).contiguous()
+        slab = torch.empty((n_cls, xs, image[1], image[2]), dtype=acc.dtype, device=acc.device)
+        dist.reduce_scatter_tensor(slab.view(-1), send.view(-1), op=dist.ReduceOp.SUM, group=group)
+    else:
+        slab = acc
+    cx, cy, cz = axis_counts(image, roi_size, per_axis, slab.device, slab.dtype)
+    cx = torch.cat([cx, cx.new_ones(world * xs - image[0])])[rank * xs:(rank + 1) * xs]     # padding planes: count 1
+    slab = slab / (cx[:, None, None] * cy[None, :, None] * cz[None, None, :])
+    lab = slab.argmax(0).to(torch.uint8)
+    if world > 1:
+        full = torch.empty((world * xs, image[1], image[2]), dtype=torch.uint8, device=lab.device)
+        dist.all_gather_into_tensor(full.view(-1), lab.contiguous().view(-1), group=group)
+        if rank != dst:
+            return None
+    else:
+        full = lab
+    full = full[lo[0]:lo[0] + size[0], lo[1]:lo[1] + size[1], lo[2]:lo[2] + size[2]]
+    if out_host is None:
+        return full.cpu()
+    out_host.copy_(full, non_blocking=True)
+    if full.is_cuda:
+        torch.cuda.current_stream(full.device).synchronize()
+    return out_host
 
 
 class GraphedPredictor:
