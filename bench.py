@@ -294,7 +294,7 @@ def run_ours(args, rank, world, local_rank):
     if infer is not None:
         line["infer"] = infer
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_port(steps=1, patches=1, threads=None, cfg_name=args.workload)
+        line["cpu_baseline"] = cpu_port(steps=3, patches=1, threads=None, cfg_name=args.workload, min_seconds=10.0)   # ~10 s of CPU work
     print(json.dumps(line), flush=True)
 
 
@@ -344,7 +344,7 @@ def run_infer(rank, world, dev, reps=3):
                        "fg_voxels": int(seg.sum())}}
 
 
-def cpu_port(steps, patches, threads, cfg_name=CFG_NAME):
+def cpu_port(steps, patches, threads, cfg_name=CFG_NAME, min_seconds=0.0, warmup=1):
     """The oracle's restatement of the reference CPU path: train step (fwd + full loss + bwd + AdamW) on host cores."""
     from oracle import veloxseg_oracle as O
     from veloxseg_b200.configs import MODEL_CONFIGS, TRAIN
@@ -367,13 +367,17 @@ def cpu_port(steps, patches, threads, cfg_name=CFG_NAME):
         loss.backward()
         opt.step()
         return float(loss.detach())
-    step()      # warm-up (allocator, thread pool)
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(max(1, warmup)):      # warm-up (allocator, thread pool)
         step()
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps or (min_seconds and time.perf_counter() - t0 < min_seconds and done < 200):
+        step()
+        done += 1
+    steps = done
     dt = time.perf_counter() - t0
     return {"value": round(steps * patches / dt, 4), "unit": "patches/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} train step(s) of {patches} patch(es) ({sum(cfg['in_ch'])}x{'x'.join(map(str, cfg['input_size']))}, fp32, dropout off) after 1 warm-up step, "
+            "sample": f"{steps} train step(s) of {patches} patch(es) ({sum(cfg['in_ch'])}x{'x'.join(map(str, cfg['input_size']))}, fp32, dropout off) after {max(1, warmup)} warm-up step(s), "
                       f"torch CPU with {cores} threads"}
 
 
@@ -381,10 +385,11 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     patches = 1
-    steps = max(1, min(args.steps, 5))
-    base = cpu_port(steps=steps, patches=patches, threads=None, cfg_name=args.workload)
+    steps = max(1, min(args.steps, 100))      # one patch per step, ~0.3-0.6 s each on the box's cores: bounded at about a minute
+    warm = max(1, min(args.warmup, 5))
+    base = cpu_port(steps=steps, patches=patches, threads=None, cfg_name=args.workload, warmup=warm)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "patches/s", "n_gpus": world,
-            "steps": steps, "warmup": 1, "ms_per_step": round(1e3 * patches / base["value"], 1), "higher_is_better": True,
+            "steps": steps, "warmup": warm, "ms_per_step": round(1e3 * patches / base["value"], 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.workload),
                        "sample": "reference CPU path (oracle port); each timed step is a bounded sample of 1 of the 4 patches",
