@@ -56,3 +56,17 @@ def test_sliding_window_slices():
     assert len(O.sw_slices((320, 320, 256), (128, 128, 64), 0.25)) == 45      # 3 x 3 x 5
     assert len(O.sw_slices((512, 512, 384), (128, 128, 64), 0.25)) == 200
     assert O.sw_scan_interval((320, 320, 256), (128, 128, 64), 0.25) == [96, 96, 48]
+
+
+def test_count_map_factorises_into_axis_tables():
+    # the window list is a Cartesian product of per-axis starts, so the overlap count is an outer product (integer-exact)
+    from veloxseg_b200.inference import axis_counts, axis_starts, count_map, window_starts
+    for image, roi in [((320, 320, 256), (128, 128, 64)), ((100, 130, 70), (96, 96, 96)), ((97, 96, 200), (96, 96, 96)),
+                       ((20, 17, 9), (8, 8, 8))]:
+        img = [max(i, r) for i, r in zip(image, roi)]
+        per_axis = axis_starts(img, roi, 0.25)
+        starts = window_starts(img, roi, 0.25)
+        assert starts == O.sw_slices(img, roi, 0.25)
+        cx, cy, cz = axis_counts(img, roi, per_axis, "cpu")
+        assert torch.equal(cx[:, None, None] * cy[None, :, None] * cz[None, None, :], count_map(img, roi, starts, "cpu")[0, 0])
+        assert int(cx.min()) >= 1 and int(cy.min()) >= 1 and int(cz.min()) >= 1
