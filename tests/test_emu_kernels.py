@@ -400,3 +400,37 @@ def test_pixel_shuffle_bias(emu, B, C, s, size):
     gz, gb = torch.autograd.grad(yr, [z, bias], dy)
     dz, db = ops.pixel_shuffle_bwd_raw(emu, 0, dy, s, True)
     assert torch.equal(dz, gz) and close(db, gb, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("C,groups,shape,B", [(8, 2, (5, 6, 8), 2), (16, 4, (9, 7, 12), 1), (8, 2, (3, 13, 5), 1)])
+def test_jlc_conv_tensor_core(emu, C, groups, shape, B):
+    """jlc_tc.cu (candidate, off by default) with its MMAs replaced by the software model on the same shared-memory layout:
+    brick staging with halo and guards, tap -> shifted-descriptor arithmetic (two taps per k-step), weight rows of the three
+    branches, TMEM read-back, masked stores and the per-tile InstanceNorm statistics -- against the SIMT conv path
+    (branch outputs z, statistics) and the oracle (block output, all gradients through the unchanged backward)."""
+    from veloxseg_b200 import ops
+    O = _oracle()
+    e = 2
+    torch.manual_seed(4)
+    x = torch.randn(B, C, *shape)
+    params = jlc_params(C, groups, e, seed=6)
+    emu.set_option(8, 0)          # VX_OPT_JLC_SMALL_MAX_S = 0: the small-volume kernels would take these shapes
+    try:
+        y0, z0, o0, h0, st0 = ops.jlc_fwd_raw(emu, 0, x, params, groups, e)
+        emu.set_option(11, 1)     # VX_OPT_JLC_CONV_TC
+        y1, z1, o1, h1, st1 = ops.jlc_fwd_raw(emu, 0, x, params, groups, e)
+        assert rel_err(z1, z0) < 2e-6, rel_err(z1, z0)
+        assert not torch.equal(z1, z0)          # the 3-term split drops lo*lo: bit-identical output would mean the SIMT path ran
+        assert rel_err(st1, st0) < 2e-5 and rel_err(y1, y0) < 2e-5
+        xr = x.clone().requires_grad_(True)
+        pr = [p.clone().requires_grad_(True) for p in params]
+        yr = O.jlc(xr, jlc_param_dict(pr), "", groups)
+        assert rel_err(y1, yr) < 2e-5, rel_err(y1, yr)
+        dy = torch.randn_like(y1)
+        grads = torch.autograd.grad(yr, [xr] + pr, dy)
+        got = ops.jlc_bwd_raw(emu, 0, dy, x, z1, o1, h1, st1, params, groups, e)
+        for i, (g, r) in enumerate(zip(got, grads)):
+            assert close(g, r, rtol=2e-4, atol=2e-5), (i, rel_err(g, r))
+    finally:
+        emu.set_option(11, 0)
+        emu.set_option(8, 512)
