@@ -406,8 +406,9 @@ def test_pixel_shuffle_bias(emu, B, C, s, size):
 def test_jlc_conv_tensor_core(emu, C, groups, shape, B):
     """jlc_tc.cu (candidate, off by default) with its MMAs replaced by the software model on the same shared-memory layout:
     brick staging with halo and guards, tap -> shifted-descriptor arithmetic (two taps per k-step), weight rows of the three
-    branches, TMEM read-back, masked stores and the per-tile InstanceNorm statistics -- against the SIMT conv path
-    (branch outputs z, statistics) and the oracle (block output, all gradients through the unchanged backward)."""
+    branches, TMEM read-back, masked stores and the per-tile InstanceNorm statistics, and the 3-pass data gradient (mirrored
+    taps, per-branch k-step lists, accumulation across passes) -- against the SIMT conv path (branch outputs z, statistics,
+    dx) and the oracle (block output, all gradients)."""
     from veloxseg_b200 import ops
     O = _oracle()
     e = 2
@@ -428,9 +429,12 @@ def test_jlc_conv_tensor_core(emu, C, groups, shape, B):
         assert rel_err(y1, yr) < 2e-5, rel_err(y1, yr)
         dy = torch.randn_like(y1)
         grads = torch.autograd.grad(yr, [xr] + pr, dy)
-        got = ops.jlc_bwd_raw(emu, 0, dy, x, z1, o1, h1, st1, params, groups, e)
+        got = ops.jlc_bwd_raw(emu, 0, dy, x, z1, o1, h1, st1, params, groups, e)       # data gradient on the 3-pass kernel
         for i, (g, r) in enumerate(zip(got, grads)):
             assert close(g, r, rtol=2e-4, atol=2e-5), (i, rel_err(g, r))
+        emu.set_option(11, 0)
+        simt = ops.jlc_bwd_raw(emu, 0, dy, x, z1, o1, h1, st1, params, groups, e)
+        assert rel_err(got[0], simt[0]) < 2e-6 and not torch.equal(got[0], simt[0])
     finally:
         emu.set_option(11, 0)
         emu.set_option(8, 512)

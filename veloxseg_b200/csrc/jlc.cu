@@ -1175,7 +1175,12 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
   G.gz = gz; G.dO = dO; G.w1 = w1; G.w3 = w3; G.w5 = w5; G.dx = dx;
   G.B = d->B; G.C = C; G.D = d->D; G.H = d->H; G.W = d->W; G.t = L.tf;
   prof_bytes(5.0 * sizeof(float) * (double)L.BCS);       // gz(3), dO in, dx out
-  if (L.small) {
+  if (L.tc) {
+    JlcTcArgs T = L.tcgeo;
+    T.w1 = w1; T.w3 = w3; T.w5 = w5; T.gz = gz; T.dO = dO; T.dx = dx;
+    T.B = d->B; T.C = C; T.D = d->D; T.H = d->H; T.W = d->W;
+    VX_TRY(jlc_conv_tc_dgrad(T, d->groups, st));
+  } else if (L.small) {
     if (CG == 4) VX_TRY(launch_conv_small_dgrad<4>(G, d->groups, st));
     else if (CG == 8) VX_TRY(launch_conv_small_dgrad<8>(G, d->groups, st));
     else VX_TRY(launch_conv_small_dgrad<16>(G, d->groups, st));

@@ -190,11 +190,13 @@ struct JlcTcArgs {
   const float* x; const float* w1; const float* b1; const float* w3; const float* b3; const float* w5; const float* b5;
   float* z;        // (3, B, C, S): branch k = 1, 3, 5
   float* part;     // (3, B*C, ntz*nty, 2)
+  const float* gz; const float* dO; float* dx;      // data gradient: (3, B, C, S) branch gradients, (B, C, S) addend, output
   int B, C, D, H, W;
   int ZR, TY, ntz, nty, nblk, tmem_cols;
 };
 void jlc_tc_set(int enabled);
 int jlc_tc_geo(int B, int groups, int CG, int D, int H, int W, JlcTcArgs& geo);    // stats partials per row, 0 = not applicable
 int jlc_conv_tc_fwd(const JlcTcArgs& A, int groups, cudaStream_t stream);
+int jlc_conv_tc_dgrad(const JlcTcArgs& A, int groups, cudaStream_t stream);
 
 }  // namespace vx
