@@ -127,6 +127,9 @@ def run_ours(args, rank, world, local_rank):
     lib = _lib.get_lib()
     pw_tc = os.environ.get("VX_PW_TC", "1") == "1"
     lib.set_option(1, int(pw_tc))        # VX_OPT_PW_TENSOR_CORES (A/B switch; default on)
+    jlc_tc = os.environ.get("VX_JLC_CONV_TC", "0") == "1"
+    if jlc_tc:
+        lib.set_option(11, 1)            # VX_OPT_JLC_CONV_TC: candidate tcgen05 JLC conv kernels (A/B switch; default off)
     x_h, y_h = synth_batch(cfg, PATCHES, 1000 + rank)
     x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
     x_d, y_d = x_h.to(dev), y_h.to(dev)
@@ -282,7 +285,8 @@ def run_ours(args, rank, world, local_rank):
                    "launch": ("eager launches" if not used_graph else "whole step replayed as one CUDA graph" if world == 1 else
                               "CUDA graph (fwd+bwd) -> one NCCL all-reduce of the flat 9 MB gradient -> CUDA graph (AdamW)"),
                    "pointwise": "tcgen05 3xTF32 (fp32-accurate) for S>=1024 (weight gradients S>=512), fp32 SIMT below" if pw_tc else "fp32 SIMT",
-                   "library_convs_outside_path": args.library_convs},
+                   "library_convs_outside_path": args.library_convs,
+                   **({"jlc_conv": "tcgen05 implicit-GEMM candidate (VX_JLC_CONV_TC=1)"} if jlc_tc else {})},
         "e2e": {"value": round(total_patches / e2e_s, 3), "unit": "patches/s",
                 "h2d_bytes_per_step": int(xb[0].numel() * xb[0].element_size() + yb[0].numel() * yb[0].element_size()),
                 "d2h_bytes_per_step": 4},
