@@ -269,7 +269,7 @@ def run_ours(args, rank, world, local_rank):
     used_graph = ts.use_graph
     del ts, model
     torch.cuda.empty_cache()
-    infer = None if args.no_infer else run_infer(rank, world, dev)
+    infer = None if args.no_infer else run_infer(rank, world, dev, volume=tuple(int(v) for v in args.infer_volume.split("x")))
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -302,7 +302,7 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
-def run_infer(rank, world, dev, reps=3):
+def run_infer(rank, world, dev, reps=3, volume=(320, 320, 256)):
     """BASELINE.json configs[3]: Hecktor2022 sliding-window inference on one synthetic PET/CT volume (1,2,320,320,256),
     roi (128,128,64), overlap 0.25 -> 45 windows, sharded round-robin over ranks, partial sums all-reduced."""
     from veloxseg_b200.configs import MODEL_CONFIGS, TRAIN
@@ -311,7 +311,7 @@ def run_infer(rank, world, dev, reps=3):
     cfg = MODEL_CONFIGS["hecktor2022"]
     torch.manual_seed(12345)
     model = VeloxSeg(**cfg).to(dev).eval()
-    vol_shape = (1, sum(cfg["in_ch"]), 320, 320, 256)
+    vol_shape = (1, sum(cfg["in_ch"])) + tuple(volume)
     vol_h = torch.randn(vol_shape, generator=torch.Generator().manual_seed(5)).pin_memory()
     roi, sw = cfg["input_size"], 4
     pred = GraphedPredictor(model, sw, vol_shape[1], roi, dev)
@@ -340,7 +340,7 @@ def run_infer(rank, world, dev, reps=3):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return {"metric": "sliding-window infer ms/volume", "value": round(float(t.item()) * 1e3, 2), "unit": "ms/volume",
             "higher_is_better": False, "scaling": "strong", "n_gpus": world,
-            "config": {"workload": "VeloxSeg Hecktor2022 eval, volume 2x320x320x256, roi 128x128x64, overlap 0.25",
+            "config": {"workload": "VeloxSeg Hecktor2022 eval, volume 2x%s, roi 128x128x64, overlap 0.25" % "x".join(map(str, volume)),
                        "windows": nwin, "sw_batch": sw,
                        "io": ("1/world of the host volume per rank + all-gather; reduce-scatter, arg-max per slab, label gather"
                               if sharded_io else "every rank copies the whole host volume; all-reduce of the logit sums"),
@@ -414,6 +414,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the secondary all-fp32 timing")
     ap.add_argument("--no-infer", action="store_true", help="skip the sliding-window inference measurement")
+    ap.add_argument("--infer-volume", default="320x320x256",
+                    help="synthetic Hecktor volume of the sliding-window leg: 320x320x256 (45 windows, default) or 512x512x384 (200 windows)")
     ap.add_argument("--library-convs", default="tf32", choices=["tf32", "fp32"],
                     help="precision of the cuDNN convolutions outside the hot path (out_conv1, Down/Up convs, patch-embed)")
     args = ap.parse_args()
