@@ -249,7 +249,10 @@ __global__ void __launch_bounds__(JT_THREADS) jlc_conv_tc_kernel(const __grid_co
   float bias[3][4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    bias[0][c] = __ldg(A.b1 + g * 4 + c); bias[1][c] = __ldg(A.b3 + g * 4 + c); bias[2][c] = __ldg(A.b5 + g * 4 + c);
+    bias[0][c] = bias[1][c] = bias[2][c] = 0.f;
+    if (MODE == 0) {      // the data-gradient launch carries no bias pointers
+      bias[0][c] = __ldg(A.b1 + g * 4 + c); bias[1][c] = __ldg(A.b3 + g * 4 + c); bias[2][c] = __ldg(A.b5 + g * 4 + c);
+    }
   }
   float ssum[3][4], ssq[3][4];
 #pragma unroll
