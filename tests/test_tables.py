@@ -70,3 +70,23 @@ def test_count_map_factorises_into_axis_tables():
         cx, cy, cz = axis_counts(img, roi, per_axis, "cpu")
         assert torch.equal(cx[:, None, None] * cy[None, :, None] * cz[None, None, :], count_map(img, roi, starts, "cpu")[0, 0])
         assert int(cx.min()) >= 1 and int(cy.min()) >= 1 and int(cz.min()) >= 1
+
+
+def test_sliding_window_blend_properties():
+    # size-independent properties of the restated MONAI blend (constant importance map): an identity predictor gives the
+    # volume back (every voxel is the mean of identical copies), also through the symmetric padding of a volume smaller
+    # than the roi; a predictor that returns the window index map reproduces it, so every window lands where it was cut.
+    from veloxseg_b200.inference import sliding_window_labels, sliding_window_predict
+    g = torch.Generator().manual_seed(3)
+    for shape, roi in [((1, 2, 20, 17, 9), (8, 8, 8)), ((1, 2, 6, 10, 8), (8, 8, 8)), ((2, 2, 12, 8, 10), (8, 8, 4))]:
+        x = torch.randn(*shape, generator=g)
+        y = sliding_window_predict(x, lambda w: w, roi, sw_batch_size=3, overlap=0.25, shard=False)
+        assert y.shape == x.shape and torch.allclose(y, x, rtol=1e-6, atol=1e-7)
+        y2 = sliding_window_predict(x, lambda w: [w * 2.0, w], roi, sw_batch_size=2, overlap=0.25, shard=False)   # list output
+        assert torch.allclose(y2, 2.0 * x, rtol=1e-6, atol=1e-7)
+    ramp = torch.arange(20 * 17 * 9, dtype=torch.float32).view(1, 1, 20, 17, 9)
+    two = torch.cat([ramp, -ramp], 1)                       # class 0 wins where ramp > 0: labels are 0 except at voxel 0 (tie)
+    lab = sliding_window_labels(two, lambda w: w, (8, 8, 8), "cpu", sw_batch_size=2, overlap=0.25)
+    assert lab.shape == (20, 17, 9) and int(lab.sum()) == 0
+    lab = sliding_window_labels(-two, lambda w: w, (8, 8, 8), "cpu", sw_batch_size=2, overlap=0.25)
+    assert int(lab.sum()) == 20 * 17 * 9 - 1                # class 1 everywhere but the tie at voxel 0 (first index wins)
