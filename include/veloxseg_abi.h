@@ -49,7 +49,7 @@ const char* vx_last_error_string(void);
  *                           (default 512; VX_OPT_PW_TENSOR_CORES = 0 switches it off together with the forward kernel).
  *   VX_OPT_SIDE_WGRAD       1 (default): inside a backward op the weight-gradient kernels run on a library-owned side
  *                           stream that forks from and joins back into the caller's stream before the op returns.
- *   VX_OPT_JLC_CONV_TC      0 (default).  1: the forward and data-gradient JLC grouped convolutions with 4 channels per group run on the
+ *   VX_OPT_JLC_CONV_TC      0 (default).  1: the forward and data-gradient JLC grouped convolutions with 4 or 8 channels per group (levels 1-2) run on the
  *                           tcgen05 implicit-GEMM candidate kernel (jlc_tc.cu) -- checked on the CPU shim only, not yet
  *                           run or measured on hardware; for A/B measurement. */
 enum { VX_OPT_PW_TENSOR_CORES = 1, VX_OPT_PW_SMALL_MAX_S = 2, VX_OPT_PW_TC_MIN_S = 3, VX_OPT_JLC_TILE_FWD = 4,

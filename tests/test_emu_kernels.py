@@ -402,7 +402,8 @@ def test_pixel_shuffle_bias(emu, B, C, s, size):
     assert torch.equal(dz, gz) and close(db, gb, rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("C,groups,shape,B", [(8, 2, (5, 6, 8), 2), (16, 4, (9, 7, 12), 1), (8, 2, (3, 13, 5), 1)])
+@pytest.mark.parametrize("C,groups,shape,B", [(8, 2, (5, 6, 8), 2), (16, 4, (9, 7, 12), 1), (8, 2, (3, 13, 5), 1),
+                                              (16, 2, (5, 6, 8), 1), (8, 1, (7, 9, 4), 2)])      # the last two: 8 channels per group
 def test_jlc_conv_tensor_core(emu, C, groups, shape, B):
     """jlc_tc.cu (candidate, off by default) with its MMAs replaced by the software model on the same shared-memory layout:
     brick staging with halo and guards, tap -> shifted-descriptor arithmetic (two taps per k-step), weight rows of the three

@@ -12,17 +12,18 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("VX_CANDIDATES"
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("shape,B", [((24, 24, 24), 1), ((24, 24, 24), 4), ((32, 32, 16), 2), ((9, 7, 12), 1)])
-def test_jlc_conv_tensor_core_vs_simt_and_oracle(shape, B):
+@pytest.mark.parametrize("C,shape,B", [(16, (24, 24, 24), 1), (16, (24, 24, 24), 4), (16, (32, 32, 16), 2), (16, (9, 7, 12), 1),
+                                       (32, (12, 12, 12), 4), (32, (16, 16, 8), 1), (32, (5, 6, 8), 2)])     # C = 32: 8 channels per group
+def test_jlc_conv_tensor_core_vs_simt_and_oracle(C, shape, B):
     from oracle import veloxseg_oracle as O
     from veloxseg_b200 import _lib, ops
     lib, st = _lib.get_lib(), torch.cuda.current_stream().cuda_stream
-    C, groups, e = 16, 4, 3
+    groups, e = 4, 3
     torch.manual_seed(4)
     x = torch.randn(B, C, *shape)
     params = jlc_params(C, groups, e, seed=6)
     xd, pd = x.to(DEV), [p.to(DEV) for p in params]
-    lib.set_option(8, 0)              # never the small-volume kernels (the 9x7x12 case)
+    lib.set_option(8, 0)              # never the small-volume kernels (the small cases)
     try:
         y0, z0, o0, h0, s0 = ops.jlc_fwd_raw(lib, st, xd, pd, groups, e)
         lib.set_option(11, 1)

@@ -1,4 +1,4 @@
-// JLC grouped convolutions (k = 1, 3, 5, c_g = 4 channels per group) as ONE implicit GEMM on the 5th-generation tensor
+// JLC grouped convolutions (k = 1, 3, 5; c_g = 4 or 8 channels per group) as ONE implicit GEMM on the 5th-generation tensor
 // cores -- tcgen05.mma kind::tf32, accumulators in tensor memory, fp32-accurate through the 3-term split of vx_tc.cuh.
 //
 // STATUS: candidate, OFF by default (vx_set_option(VX_OPT_JLC_CONV_TC, 1)).  Written after the round's GPU budget was
@@ -35,11 +35,8 @@
 namespace vx {
 
 constexpr int JT_THREADS = 256;
-constexpr int JT_KSTEPS = 65;      // 13 (dz, dy) pairs x 5 dx
-constexpr int JT_N = 16;           // z5 | z3 | z1 | zero
 constexpr int JT_G0 = 8;           // guard positions before the brick (the first block reads 2 positions in front of it)
-constexpr int JT_G1 = 144;         // guard positions behind it: 2 + 127 padding rows of the last block + 8 (second k-half of the single tap)
-constexpr int JT_BSTEP = 128;      // floats of one k-step of the weight operand: [2 n-groups][2 k-halves][8 n][4 k]
+constexpr int JT_G1 = 144;         // guard positions behind it: 2 + 127 padding rows of the last block + 8 (second k-half of a single tap)
 constexpr int JT_MAX_BLK = 32;     // 512 TMEM columns / 16
 
 #ifdef VX_EMU
@@ -51,28 +48,58 @@ static inline void jt_split(float x, float& hi, float& lo) {
 VX_DEV void jt_split(float x, float& hi, float& lo) { split_tf32(x, hi, lo); }
 #endif
 
-// k-step s of a pass over a k x k x k kernel -> column offset dx (0..4) and the two (dz, dy) indices (0..24, -1 = absent).
-// kind 5: 13 pairs x 5 dx; kind 3: the 9 inner (dz, dy) in ascending order, 5 pairs x 3 dx; kind 1: the centre.
-VX_DEV int jt_nsteps(int kind) { return kind == 5 ? JT_KSTEPS : kind == 3 ? 15 : 1; }
-VX_DEV void jt_step(int kind, int s, int& dxi, int& ja, int& jb) {
-  if (kind == 5) {
+// TMEM columns per M-block = N of the MMA, and the most k-steps any pass stages
+__host__ __device__ constexpr int jt_ncol(int mode, int cg) { return mode == 0 && cg == 8 ? 32 : 16; }
+__host__ __device__ constexpr int jt_maxsteps(int cg) { return cg == 4 ? 65 : 27; }
+
+// Pass p of a launch -> kernel size walked (5 / 3 / 1), dz slab (-1 = every dz) and whether the brick is restaged.
+//   forward:        c_g 4: one pass over all taps;            c_g 8: five dz slabs of the 5^3 kernel over one brick
+//   data gradient:  c_g 4: k = 5, 3, 1 (a brick each);        c_g 8: five slabs of k = 5, then k = 3, then k = 1
+__host__ __device__ constexpr int jt_npass(int mode, int cg) { return mode == 0 ? (cg == 4 ? 1 : 5) : (cg == 4 ? 3 : 7); }
+VX_DEV void jt_pass(int mode, int cg, int p, int& kind, int& slab, bool& restage) {
+  if (cg == 4) { kind = mode == 0 ? 5 : (p == 0 ? 5 : p == 1 ? 3 : 1); slab = -1; restage = true; return; }
+  if (mode == 0 || p < 5) { kind = 5; slab = p; restage = p == 0; return; }
+  kind = p == 5 ? 3 : 1; slab = -1; restage = true;
+}
+VX_DEV int jt_nsteps(int cg, int kind, int slab) {
+  if (cg == 4) return kind == 5 ? 65 : kind == 3 ? 15 : 1;
+  return kind == 5 ? (slab >= 0 ? 25 : 125) : kind == 3 ? 27 : 1;
+}
+// k-step s -> column offset dx (0..4) and the (dz, dy) indices (0..24) of its taps (jb = -1: no second tap).
+//   c_g 4: two taps per k-step.  kind 5: 13 (dz, dy) pairs x 5 dx; kind 3: the 9 inner (dz, dy) ascending, 5 pairs x 3 dx.
+//   c_g 8: one tap per k-step.
+VX_DEV void jt_step(int cg, int kind, int slab, int s, int& dxi, int& ja, int& jb) {
+  jb = -1;
+  if (kind == 1) { dxi = 2; ja = 12; return; }
+  if (cg == 4) {
+    if (kind == 5) {
+      dxi = s % 5;
+      const int j = s / 5;
+      ja = 2 * j;
+      jb = 2 * j + 1 < 25 ? 2 * j + 1 : -1;
+    } else {
+      dxi = 1 + s % 3;
+      const int q = s / 3, i0 = 2 * q, i1 = 2 * q + 1;         // inner list index i -> j = (1 + i / 3) * 5 + 1 + i % 3
+      ja = (1 + i0 / 3) * 5 + 1 + i0 % 3;
+      jb = i1 < 9 ? (1 + i1 / 3) * 5 + 1 + i1 % 3 : -1;
+    }
+  } else if (kind == 5) {
     dxi = s % 5;
-    const int j = s / 5;
-    ja = 2 * j;
-    jb = 2 * j + 1 < 25 ? 2 * j + 1 : -1;
-  } else if (kind == 3) {
-    dxi = 1 + s % 3;
-    const int q = s / 3, i0 = 2 * q, i1 = 2 * q + 1;           // inner list index i -> j = (1 + i / 3) * 5 + 1 + i % 3
-    ja = (1 + i0 / 3) * 5 + 1 + i0 % 3;
-    jb = i1 < 9 ? (1 + i1 / 3) * 5 + 1 + i1 % 3 : -1;
+    ja = slab >= 0 ? slab * 5 + s / 5 : s / 5;
   } else {
-    dxi = 2; ja = 12; jb = -1;
+    dxi = 1 + s % 3;
+    ja = (1 + s / 9) * 5 + 1 + (s / 3) % 3;
   }
 }
 VX_DEV int jt_shift(int j, int dxi, int PY, int PX) { return ((j / 5 - 2) * PY + (j % 5 - 2)) * PX + (dxi - 2); }
 
-template <int MODE>      // 0: forward (x -> z1, z3, z5 + statistics), 1: data gradient (gz1, gz3, gz5, dO -> dx)
+template <int MODE, int CG>      // MODE 0: forward (x -> z1, z3, z5 + statistics), 1: data gradient (gz1, gz3, gz5, dO -> dx)
 __global__ void __launch_bounds__(JT_THREADS) jlc_conv_tc_kernel(const __grid_constant__ JlcTcArgs A) {
+  constexpr int NCH = CG / 4;                       // [position][4 channels] arrays of the brick
+  constexpr int NCOL = jt_ncol(MODE, CG);
+  constexpr int BSTEP = NCOL * 8;                   // floats of one k-step of the weight operand: [n-groups][2 k-halves][8 n][4 k]
+  constexpr int MAXSTEPS = jt_maxsteps(CG);
+  constexpr int NPASS = jt_npass(MODE, CG);
   const int g = blockIdx.y, b = blockIdx.z, tile = blockIdx.x;
   const int ty_i = tile % A.nty, tz_i = tile / A.nty;
   const int z0 = tz_i * A.ZR, y0 = ty_i * A.TY;
@@ -82,15 +109,16 @@ __global__ void __launch_bounds__(JT_THREADS) jlc_conv_tc_kernel(const __grid_co
   const int p_first = (2 * PY + 2) * PX;              // first output row of the first output plane, column 0
   const int nblk = A.nblk;
   const size_t S = (size_t)D * H * W;
+  const size_t BCS = (size_t)A.B * C * S;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   VX_DYN_SMEM(float, sm);
   const int NALL = JT_G0 + NPOS + JT_G1;
-  float* Xhi = sm;                                    // [NALL][4]
-  float* Xlo = Xhi + (size_t)NALL * 4;
-  float* Bhi = Xlo + (size_t)NALL * 4;                // [65][128]
-  float* Blo = Bhi + JT_KSTEPS * JT_BSTEP;
-  float* sst = Blo + JT_KSTEPS * JT_BSTEP;            // [3 branches][4 co][2]
+  float* Xhi = sm;                                    // [NCH][NALL][4]
+  float* Xlo = Xhi + (size_t)NCH * NALL * 4;
+  float* Bhi = Xlo + (size_t)NCH * NALL * 4;          // [MAXSTEPS][BSTEP]
+  float* Blo = Bhi + MAXSTEPS * BSTEP;
+  float* sst = Blo + MAXSTEPS * BSTEP;                // [3 branches][CG co][2]
 
 #ifndef VX_EMU
   __shared__ __align__(8) uint64_t mbar[JT_MAX_BLK + 1];      // one per M-block + the pass barrier
@@ -106,25 +134,25 @@ __global__ void __launch_bounds__(JT_THREADS) jlc_conv_tc_kernel(const __grid_co
     mbar_init(smem_u32(&mbar[JT_MAX_BLK]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  uint32_t tmem = 0;
 #endif
-  if (tid < 24) sst[tid] = 0.f;
+  if (tid < 3 * CG * 2) sst[tid] = 0.f;
 
-  // ---- the brick: [position][4 channels], hi / lo; zero outside the volume and in the guards
+  // ---- guards: zero, written once (the brick is [position][4 channels] per chunk, hi / lo; zero outside the volume)
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = tid; i < JT_G0 + JT_G1; i += JT_THREADS) {
-    const int pos = i < JT_G0 ? i : NPOS + i;
+  for (int i = tid; i < NCH * (JT_G0 + JT_G1); i += JT_THREADS) {
+    const int ch = i / (JT_G0 + JT_G1), r = i % (JT_G0 + JT_G1);
+    const int pos = ch * NALL + (r < JT_G0 ? r : NPOS + r);
     reinterpret_cast<float4*>(Xhi)[pos] = zero4;
     reinterpret_cast<float4*>(Xlo)[pos] = zero4;
   }
-  constexpr int NPASS = MODE == 0 ? 1 : 3;
-  const size_t BCS = (size_t)A.B * C * S;
-#ifndef VX_EMU
-  uint32_t tmem = 0;
-#endif
+
 #pragma unroll 1
   for (int pass = 0; pass < NPASS; ++pass) {
-    const int kind = MODE == 0 ? 5 : (pass == 0 ? 5 : pass == 1 ? 3 : 1);
-    const int nsteps = jt_nsteps(kind);
+    int kind, slab;
+    bool restage;
+    jt_pass(MODE, CG, pass, kind, slab, restage);
+    const int nsteps = jt_nsteps(CG, kind, slab);
     if (pass > 0) {      // the previous pass's MMAs have read the brick and the weights
 #ifndef VX_EMU
       mbar_wait(smem_u32(&mbar[JT_MAX_BLK]), (uint32_t)((pass - 1) & 1));
@@ -134,50 +162,54 @@ __global__ void __launch_bounds__(JT_THREADS) jlc_conv_tc_kernel(const __grid_co
 #endif
     }
     // ---- the brick of this pass
-    const float* xg = MODE == 0 ? A.x + ((size_t)b * C + g * 4) * S
-                                : A.gz + (size_t)(kind == 5 ? 2 : kind == 3 ? 1 : 0) * BCS + ((size_t)b * C + g * 4) * S;
-    for (int idx = tid; idx < NPOS; idx += JT_THREADS) {
-      const int px = idx % PX, py = (idx / PX) % PY, pz = idx / (PX * PY);
-      const int gz = z0 + pz - 2, gy = y0 + py - 2, gx = px - 2;
-      float4 hi = zero4, lo = zero4;
-      if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        const size_t o = ((size_t)gz * H + gy) * W + gx;
-        jt_split(__ldg(xg + o), hi.x, lo.x);
-        jt_split(__ldg(xg + S + o), hi.y, lo.y);
-        jt_split(__ldg(xg + 2 * S + o), hi.z, lo.z);
-        jt_split(__ldg(xg + 3 * S + o), hi.w, lo.w);
+    if (restage) {
+      const float* xg = MODE == 0 ? A.x + ((size_t)b * C + g * CG) * S
+                                  : A.gz + (size_t)(kind == 5 ? 2 : kind == 3 ? 1 : 0) * BCS + ((size_t)b * C + g * CG) * S;
+      for (int it = tid; it < NCH * NPOS; it += JT_THREADS) {
+        const int ch = it / NPOS, idx = it % NPOS;
+        const int px = idx % PX, py = (idx / PX) % PY, pz = idx / (PX * PY);
+        const int gz = z0 + pz - 2, gy = y0 + py - 2, gx = px - 2;
+        float4 hi = zero4, lo = zero4;
+        if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+          const float* xc = xg + (size_t)(ch * 4) * S + ((size_t)gz * H + gy) * W + gx;
+          jt_split(__ldg(xc), hi.x, lo.x);
+          jt_split(__ldg(xc + S), hi.y, lo.y);
+          jt_split(__ldg(xc + 2 * S), hi.z, lo.z);
+          jt_split(__ldg(xc + 3 * S), hi.w, lo.w);
+        }
+        reinterpret_cast<float4*>(Xhi)[ch * NALL + JT_G0 + idx] = hi;
+        reinterpret_cast<float4*>(Xlo)[ch * NALL + JT_G0 + idx] = lo;
       }
-      reinterpret_cast<float4*>(Xhi)[JT_G0 + idx] = hi;
-      reinterpret_cast<float4*>(Xlo)[JT_G0 + idx] = lo;
     }
-    // ---- the weights: element (n, k) of k-step s at s*128 + (n/8)*64 + (k/4)*32 + (n%8)*4 + k%4  (LBO 128 B, SBO 256 B)
-    for (int e = tid; e < nsteps * JT_BSTEP; e += JT_THREADS) {
-      const int s = e >> 7, r = e & 127, n = r >> 3, k = r & 7;
+    // ---- the weights: element (n, k) of k-step s at s*BSTEP + (n/8)*64 + (k/4)*32 + (n%8)*4 + k%4  (LBO 128 B, SBO 256 B)
+    for (int e = tid; e < nsteps * BSTEP; e += JT_THREADS) {
+      const int s = e / BSTEP, r = e % BSTEP, n = r >> 3, k = r & 7;
       int dxi, ja, jb;
-      jt_step(kind, s, dxi, ja, jb);
-      const int j = (k >> 2) ? jb : ja, kc = k & 3;
+      jt_step(CG, kind, slab, s, dxi, ja, jb);
+      const int j = CG == 4 ? ((k >> 2) ? jb : ja) : ja;      // c_g 4: the k-half picks the tap; c_g 8: k is the channel
+      const int kc = CG == 4 ? (k & 3) : k;
       float w = 0.f;
       if (MODE == 0) {       // columns z5 | z3 | z1, k = input channel
-        if (j >= 0 && n < 12) {
-          const int dzi = j / 5, dyi = j % 5, br = n >> 2, co = g * 4 + (n & 3);
+        if (j >= 0 && n < 3 * CG) {
+          const int dzi = j / 5, dyi = j % 5, br = n / CG, co = g * CG + n % CG;
           if (br == 0) {
-            w = __ldg(A.w5 + ((size_t)co * 4 + kc) * 125 + (dzi * 5 + dyi) * 5 + dxi);
+            w = __ldg(A.w5 + ((size_t)co * CG + kc) * 125 + (dzi * 5 + dyi) * 5 + dxi);
           } else if (br == 1) {
             if (dzi >= 1 && dzi <= 3 && dyi >= 1 && dyi <= 3 && dxi >= 1 && dxi <= 3)
-              w = __ldg(A.w3 + ((size_t)co * 4 + kc) * 27 + ((dzi - 1) * 3 + (dyi - 1)) * 3 + (dxi - 1));
+              w = __ldg(A.w3 + ((size_t)co * CG + kc) * 27 + ((dzi - 1) * 3 + (dyi - 1)) * 3 + (dxi - 1));
           } else if (dzi == 2 && dyi == 2 && dxi == 2) {
-            w = __ldg(A.w1 + (size_t)co * 4 + kc);
+            w = __ldg(A.w1 + (size_t)co * CG + kc);
           }
         }
-      } else if (j >= 0 && n < 4) {      // columns = input channel n, k = output channel; taps mirrored about the centre
+      } else if (j >= 0 && n < CG) {      // columns = input channel n, k = output channel; taps mirrored about the centre
         const int P = kind >> 1;
         const int tz = P - (j / 5 - 2), ty = P - (j % 5 - 2), tx = P - (dxi - 2);      // inside [0, kind) by construction
         const float* wk = kind == 5 ? A.w5 : kind == 3 ? A.w3 : A.w1;
-        w = __ldg(wk + ((size_t)(g * 4 + kc) * 4 + n) * (kind * kind * kind) + (tz * kind + ty) * kind + tx);
+        w = __ldg(wk + ((size_t)(g * CG + kc) * CG + n) * (kind * kind * kind) + (tz * kind + ty) * kind + tx);
       }
       float hi, lo;
       jt_split(w, hi, lo);
-      const int o = s * JT_BSTEP + (n >> 3) * 64 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
+      const int o = s * BSTEP + (n >> 3) * 64 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
       Bhi[o] = hi; Blo[o] = lo;
     }
 
@@ -188,7 +220,7 @@ __global__ void __launch_bounds__(JT_THREADS) jlc_conv_tc_kernel(const __grid_co
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     tmem = tmem_slot;
     if (tid == 0) {
-      const uint32_t idesc = umma_idesc_tf32(JT_N);
+      const uint32_t idesc = umma_idesc_tf32(NCOL);
       const uint32_t x_hi = smem_u32(Xhi), x_lo = smem_u32(Xlo), b_hi = smem_u32(Bhi), b_lo = smem_u32(Blo);
 #pragma unroll 1
       for (int blk = 0; blk < nblk; ++blk) {
@@ -196,13 +228,15 @@ __global__ void __launch_bounds__(JT_THREADS) jlc_conv_tc_kernel(const __grid_co
 #pragma unroll 1
         for (int s = 0; s < nsteps; ++s) {
           int dxi, ja, jb;
-          jt_step(kind, s, dxi, ja, jb);
+          jt_step(CG, kind, slab, s, dxi, ja, jb);
           const int sa = jt_shift(ja, dxi, PY, PX);
-          const uint32_t lbo = jb >= 0 ? (uint32_t)(jt_shift(jb, dxi, PY, PX) - sa) * 16u : 128u;
-          const uint32_t ao = (uint32_t)(p0 + sa) * 16u, bo = (uint32_t)s * (JT_BSTEP * 4);
+          // distance between the k-halves: c_g 4: the second tap (8 positions when it is absent and meets zero weights);
+          // c_g 8: the next [position][4 channels] array
+          const uint32_t lbo = CG == 8 ? (uint32_t)NALL * 16u : jb >= 0 ? (uint32_t)(jt_shift(jb, dxi, PY, PX) - sa) * 16u : 128u;
+          const uint32_t ao = (uint32_t)(p0 + sa) * 16u, bo = (uint32_t)s * (BSTEP * 4);
           const uint64_t dah = umma_desc(x_hi + ao, lbo, 128u), dal = umma_desc(x_lo + ao, lbo, 128u);
           const uint64_t dbh = umma_desc(b_hi + bo, 128u, 256u), dbl = umma_desc(b_lo + bo, 128u, 256u);
-          const uint32_t d = tmem + (uint32_t)(blk * JT_N);
+          const uint32_t d = tmem + (uint32_t)(blk * NCOL);
           umma_tf32(d, dal, dbh, idesc, (pass > 0 || s > 0) ? 1u : 0u);
           umma_tf32(d, dah, dbl, idesc, 1u);
           umma_tf32(d, dah, dbh, idesc, 1u);
@@ -223,20 +257,20 @@ __global__ void __launch_bounds__(JT_THREADS) jlc_conv_tc_kernel(const __grid_co
       for (int blk = 0; blk < nblk; ++blk) {
         const int p0 = JT_G0 + p_first + blk * 128;
         for (int m = 0; m < 128; ++m)
-          for (int n = 0; n < JT_N; ++n) {
-            float acc = pass > 0 ? g_emu_tmem_jt[m][blk * JT_N + n] : 0.f;
+          for (int n = 0; n < NCOL; ++n) {
+            float acc = pass > 0 ? g_emu_tmem_jt[m][blk * NCOL + n] : 0.f;
             for (int s = 0; s < nsteps; ++s) {
               int dxi, ja, jb;
-              jt_step(kind, s, dxi, ja, jb);
+              jt_step(CG, kind, slab, s, dxi, ja, jb);
               const int sa = jt_shift(ja, dxi, PY, PX);
-              const int lbo_pos = jb >= 0 ? jt_shift(jb, dxi, PY, PX) - sa : 8;
+              const int lbo_pos = CG == 8 ? NALL : jb >= 0 ? jt_shift(jb, dxi, PY, PX) - sa : 8;
               for (int k = 0; k < 8; ++k) {
                 const int ao = (p0 + sa + m + (k >> 2) * lbo_pos) * 4 + (k & 3);
-                const int bo = s * JT_BSTEP + (n >> 3) * 64 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
+                const int bo = s * BSTEP + (n >> 3) * 64 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
                 acc += Xlo[ao] * Bhi[bo] + Xhi[ao] * Blo[bo] + Xhi[ao] * Bhi[bo];
               }
             }
-            g_emu_tmem_jt[m][blk * JT_N + n] = acc;
+            g_emu_tmem_jt[m][blk * NCOL + n] = acc;
           }
       }
     }
@@ -246,51 +280,54 @@ __global__ void __launch_bounds__(JT_THREADS) jlc_conv_tc_kernel(const __grid_co
 
   // ---- drain: warp = (TMEM lane quadrant, parity of the blocks it takes); thread = one position of the block
   const int wq = warp & 3, wp = warp >> 2;
-  float bias[3][4];
+  float bias[3][CG];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < CG; ++c) {
     bias[0][c] = bias[1][c] = bias[2][c] = 0.f;
     if (MODE == 0) {      // the data-gradient launch carries no bias pointers
-      bias[0][c] = __ldg(A.b1 + g * 4 + c); bias[1][c] = __ldg(A.b3 + g * 4 + c); bias[2][c] = __ldg(A.b5 + g * 4 + c);
+      bias[0][c] = __ldg(A.b1 + g * CG + c); bias[1][c] = __ldg(A.b3 + g * CG + c); bias[2][c] = __ldg(A.b5 + g * CG + c);
     }
   }
-  float ssum[3][4], ssq[3][4];
+  float ssum[3][CG], ssq[3][CG];
 #pragma unroll
   for (int k = 0; k < 3; ++k)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { ssum[k][c] = 0.f; ssq[k][c] = 0.f; }
+    for (int c = 0; c < CG; ++c) { ssum[k][c] = 0.f; ssq[k][c] = 0.f; }
 #pragma unroll 1
   for (int blk = wp; blk < nblk; blk += 2) {
-    float r[JT_N];
+    float r[NCOL];
 #ifndef VX_EMU
     mbar_wait(smem_u32(&mbar[blk]), 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint32_t q[JT_N];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
-          "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
-        : "r"(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(blk * JT_N))
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int j = 0; j < JT_N; ++j) r[j] = __uint_as_float(q[j]);
+    for (int c0 = 0; c0 < NCOL; c0 += 16) {
+      uint32_t q[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+            "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+          : "r"(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(blk * NCOL + c0))
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[c0 + j] = __uint_as_float(q[j]);
+    }
 #else
-    for (int j = 0; j < JT_N; ++j) r[j] = g_emu_tmem_jt[wq * 32 + lane][blk * JT_N + j];
+    for (int j = 0; j < NCOL; ++j) r[j] = g_emu_tmem_jt[wq * 32 + lane][blk * NCOL + j];
 #endif
     const int p = p_first + blk * 128 + wq * 32 + lane;
     const int px = p % PX, py = (p / PX) % PY, pz = p / (PX * PY);
     const int gz = z0 + pz - 2, gy = y0 + py - 2, gx = px - 2;
     const bool ok = px >= 2 && px < 2 + W && py >= 2 && py < 2 + A.TY && pz >= 2 && pz < 2 + A.ZR && gz < D && gy < H;
     if (ok && MODE == 1) {
-      const size_t o = ((size_t)b * C + g * 4) * S + ((size_t)gz * H + gy) * W + gx;
+      const size_t o = ((size_t)b * C + g * CG) * S + ((size_t)gz * H + gy) * W + gx;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) A.dx[o + c * S] = r[c] + __ldg(A.dO + o + c * S);
+      for (int c = 0; c < CG; ++c) A.dx[o + c * S] = r[c] + __ldg(A.dO + o + c * S);
     } else if (ok) {
-      const size_t o = ((size_t)b * C + g * 4) * S + ((size_t)gz * H + gy) * W + gx;
+      const size_t o = ((size_t)b * C + g * CG) * S + ((size_t)gz * H + gy) * W + gx;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float r1 = r[8 + c] + bias[0][c], r3 = r[4 + c] + bias[1][c], r5 = r[c] + bias[2][c];
+      for (int c = 0; c < CG; ++c) {
+        const float r1 = r[2 * CG + c] + bias[0][c], r3 = r[CG + c] + bias[1][c], r5 = r[c] + bias[2][c];
         A.z[o + c * S] = r1; A.z[BCS + o + c * S] = r3; A.z[2 * BCS + o + c * S] = r5;
         ssum[0][c] += r1; ssq[0][c] = fmaf(r1, r1, ssq[0][c]);
         ssum[1][c] += r3; ssq[1][c] = fmaf(r3, r3, ssq[1][c]);
@@ -302,9 +339,9 @@ __global__ void __launch_bounds__(JT_THREADS) jlc_conv_tc_kernel(const __grid_co
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < CG; ++c) {
         const float s1 = warp_sum(ssum[k][c]), s2 = warp_sum(ssq[k][c]);
-        if (lane == 0) { atomicAdd(sst + (k * 4 + c) * 2, s1); atomicAdd(sst + (k * 4 + c) * 2 + 1, s2); }
+        if (lane == 0) { atomicAdd(sst + (k * CG + c) * 2, s1); atomicAdd(sst + (k * CG + c) * 2 + 1, s2); }
       }
   }
 #ifndef VX_EMU
@@ -312,9 +349,9 @@ __global__ void __launch_bounds__(JT_THREADS) jlc_conv_tc_kernel(const __grid_co
 #endif
   __syncthreads();
   const int ntiles = gridDim.x;
-  if (MODE == 0 && tid < 12) {
-    const int k = tid >> 2, c = tid & 3;
-    const size_t row = (size_t)k * A.B * C + (size_t)b * C + g * 4 + c;
+  if (MODE == 0 && tid < 3 * CG) {
+    const int k = tid / CG, c = tid % CG;
+    const size_t row = (size_t)k * A.B * C + (size_t)b * C + g * CG + c;
     float* pp = A.part + (row * ntiles + tile) * 2;
     pp[0] = sst[tid * 2]; pp[1] = sst[tid * 2 + 1];
   }
@@ -328,15 +365,18 @@ __global__ void __launch_bounds__(JT_THREADS) jlc_conv_tc_kernel(const __grid_co
 static int g_jt_enabled = 0;
 void jlc_tc_set(int enabled) { g_jt_enabled = enabled ? 1 : 0; }
 
-static size_t jt_smem_bytes(int ZR, int TY, int W) {
-  const size_t npos = (size_t)(ZR + 4) * (TY + 4) * (W + 4);
-  return sizeof(float) * (2 * 4 * (JT_G0 + npos + JT_G1) + 2 * JT_KSTEPS * JT_BSTEP + 24);
+static size_t jt_smem_bytes(int CG, int ZR, int TY, int W) {
+  const size_t nall = JT_G0 + (size_t)(ZR + 4) * (TY + 4) * (W + 4) + JT_G1;
+  // the forward launch has the wider weight tile; both launches of an op share the geometry
+  return sizeof(float) * (2 * (CG / 4) * nall * 4 + 2 * (size_t)jt_maxsteps(CG) * jt_ncol(0, CG) * 8 + 3 * CG * 2);
 }
 
-// Picks the brick (ZR planes x TY rows x full width) of the tensor-core forward conv; returns 0 when the path is off or
-// the shape does not qualify (c_g != 4, rows wider than one M-block).
+// Picks the brick (ZR planes x TY rows x full width) of the tensor-core conv kernels; returns the number of bricks per
+// (batch, group) = statistics partials per row, or 0 when the path is off or the shape does not qualify.
 int jlc_tc_geo(int B, int groups, int CG, int D, int H, int W, JlcTcArgs& A) {
-  if (!g_jt_enabled || CG != 4 || W + 4 > 128) return 0;
+  if (!g_jt_enabled || (CG != 4 && CG != 8) || W + 4 > 128) return 0;
+  const int ncol = jt_ncol(0, CG);
+  const double mma_cycles = CG == 4 ? 195.0 * 16.0 : 375.0 * 20.0;      // per M-block (guess until measured)
   double best = -1.0;
   const int zr_c[] = {1, 2, 3, 4, 6, 8};
   for (int div = 1; div <= 4; ++div) {
@@ -344,36 +384,41 @@ int jlc_tc_geo(int B, int groups, int CG, int D, int H, int W, JlcTcArgs& A) {
     for (int ZR : zr_c) {
       if (ZR > D && ZR != 1) continue;
       const int PX = W + 4, PY = TY + 4;
-      if (jt_smem_bytes(ZR, TY, W) > 227 * 1024) continue;
+      const long long nall = JT_G0 + (long long)(ZR + 4) * PY * PX + JT_G1;
+      if (jt_smem_bytes(CG, ZR, TY, W) > 227 * 1024) continue;
       const int nblk = cdiv((long long)((ZR - 1) * PY + TY) * PX, 128);
-      if (nblk > JT_MAX_BLK) continue;
-      if ((PY - 4) * PX > 16383) continue;                           // LBO field: 14 bits of 16-byte units
+      if (nblk > JT_MAX_BLK || nblk * ncol > 512) continue;
+      if ((PY - 4) * PX > 16383 || nall > 16383) continue;          // LBO field: 14 bits of 16-byte units
       const int ntz = cdiv(D, ZR), nty = cdiv(H, TY);
       const long long ncta = (long long)ntz * nty * groups * B;
-      const double cost = (double)cdiv(ncta, kSMs) * ((double)nblk * 3200.0 + (double)(ZR + 4) * PY * PX * 6.0);
+      const double cost = (double)cdiv(ncta, kSMs) * ((double)nblk * mma_cycles + (double)(CG / 4) * (ZR + 4) * PY * PX * 6.0);
       if (best < 0.0 || cost < best) {
         best = cost;
         A.ZR = ZR; A.TY = TY; A.ntz = ntz; A.nty = nty; A.nblk = nblk;
         A.tmem_cols = 32;
-        while (A.tmem_cols < nblk * JT_N) A.tmem_cols <<= 1;
+        while (A.tmem_cols < nblk * ncol) A.tmem_cols <<= 1;
       }
     }
   }
   return best >= 0.0 ? A.ntz * A.nty : 0;
 }
 
-int jlc_conv_tc_fwd(const JlcTcArgs& A, int groups, cudaStream_t st) {
-  const size_t smem = jt_smem_bytes(A.ZR, A.TY, A.W);
-  VX_SET_SMEM(jlc_conv_tc_kernel<0>, smem);
-  VX_LAUNCH(jlc_conv_tc_kernel<0>, dim3(A.ntz * A.nty, groups, A.B), dim3(JT_THREADS), smem, st, A);
-  return check_launch("jlc_conv_tc_kernel<0>");
+template <int MODE>
+static int jt_launch(const JlcTcArgs& A, int groups, cudaStream_t st, const char* what) {
+  const int CG = A.C / groups;
+  const size_t smem = jt_smem_bytes(CG, A.ZR, A.TY, A.W);
+  const dim3 grid(A.ntz * A.nty, groups, A.B);
+  if (CG == 4) {
+    VX_SET_SMEM((jlc_conv_tc_kernel<MODE, 4>), smem);
+    VX_LAUNCH((jlc_conv_tc_kernel<MODE, 4>), grid, dim3(JT_THREADS), smem, st, A);
+  } else {
+    VX_SET_SMEM((jlc_conv_tc_kernel<MODE, 8>), smem);
+    VX_LAUNCH((jlc_conv_tc_kernel<MODE, 8>), grid, dim3(JT_THREADS), smem, st, A);
+  }
+  return check_launch(what);
 }
 
-int jlc_conv_tc_dgrad(const JlcTcArgs& A, int groups, cudaStream_t st) {
-  const size_t smem = jt_smem_bytes(A.ZR, A.TY, A.W);
-  VX_SET_SMEM(jlc_conv_tc_kernel<1>, smem);
-  VX_LAUNCH(jlc_conv_tc_kernel<1>, dim3(A.ntz * A.nty, groups, A.B), dim3(JT_THREADS), smem, st, A);
-  return check_launch("jlc_conv_tc_kernel<1>");
-}
+int jlc_conv_tc_fwd(const JlcTcArgs& A, int groups, cudaStream_t st) { return jt_launch<0>(A, groups, st, "jlc_conv_tc_kernel<0>"); }
+int jlc_conv_tc_dgrad(const JlcTcArgs& A, int groups, cudaStream_t st) { return jt_launch<1>(A, groups, st, "jlc_conv_tc_kernel<1>"); }
 
 }  // namespace vx
