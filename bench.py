@@ -286,7 +286,9 @@ def run_ours(args, rank, world, local_rank):
                               "CUDA graph (fwd+bwd) -> one NCCL all-reduce of the flat 9 MB gradient -> CUDA graph (AdamW)"),
                    "pointwise": "tcgen05 3xTF32 (fp32-accurate) for S>=1024 (weight gradients S>=512), fp32 SIMT below" if pw_tc else "fp32 SIMT",
                    "library_convs_outside_path": args.library_convs,
-                   **({"jlc_conv": "tcgen05 implicit-GEMM candidate (VX_JLC_CONV_TC=1)"} if jlc_tc else {})},
+                   **({"jlc_conv": "tcgen05 implicit-GEMM candidate (VX_JLC_CONV_TC=1)"} if jlc_tc else {}),
+                   **({"out_conv": "tcgen05 tf32 implicit-GEMM candidate, forward (VX_DENSE_CONV_TC=1)"}
+                      if os.environ.get("VX_DENSE_CONV_TC", "0") == "1" and args.library_convs == "tf32" else {})},
         "e2e": {"value": round(total_patches / e2e_s, 3), "unit": "patches/s",
                 "h2d_bytes_per_step": int(xb[0].numel() * xb[0].element_size() + yb[0].numel() * yb[0].element_size()),
                 "d2h_bytes_per_step": 4},

@@ -51,10 +51,11 @@ const char* vx_last_error_string(void);
  *                           stream that forks from and joins back into the caller's stream before the op returns.
  *   VX_OPT_JLC_CONV_TC      0 (default).  1: the forward and data-gradient JLC grouped convolutions with 4 or 8 channels per group (levels 1-2) run on the
  *                           tcgen05 implicit-GEMM candidate kernel (jlc_tc.cu) -- checked on the CPU shim only, not yet
- *                           run or measured on hardware; for A/B measurement. */
+ *                           run or measured on hardware; for A/B measurement.
+ *   VX_OPT_DENSE_CONV_TC    0 (default).  1: enables vx_dense_conv_fwd (candidate, same status). */
 enum { VX_OPT_PW_TENSOR_CORES = 1, VX_OPT_PW_SMALL_MAX_S = 2, VX_OPT_PW_TC_MIN_S = 3, VX_OPT_JLC_TILE_FWD = 4,
        VX_OPT_JLC_TILE_WGRAD = 5, VX_OPT_JLC_SMALL_MAX_S = 8, VX_OPT_WGRAD_TC_MIN_S = 9, VX_OPT_SIDE_WGRAD = 10,
-       VX_OPT_JLC_CONV_TC = 11 };
+       VX_OPT_JLC_CONV_TC = 11, VX_OPT_DENSE_CONV_TC = 12 };
 int vx_set_option(int option, int value);
 /* number of kernels this library has enqueued since it was loaded (all threads, all streams) */
 uint64_t vx_launch_count(void);
@@ -271,6 +272,18 @@ typedef struct {
 /* fwd in: z, bias (C * scale^3) or NULL   out: y (B, C, d s, h s, w s)          bwd in: dy   out: dz, db or NULL */
 int vx_pixel_shuffle_fwd(const vx_pixel_shuffle_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
 int vx_pixel_shuffle_bwd(const vx_pixel_shuffle_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * CANDIDATE (off unless VX_OPT_DENSE_CONV_TC is set; not yet run on hardware): dense 3x3x3 convolution, stride 1,
+ * padding 1, 16 input channels, no bias -- the convolution of decoder.out_conv1 / the reconstruction out_conv
+ * (model/Decoder.py:73-76,150-153) on the tcgen05 tensor cores in tf32 (the precision class of
+ * the library convolution under torch.backends.cudnn.allow_tf32).  Forward only.
+ *   in[0] x (B, 16, D, H, W)   in[1] w (C_out, 16, 3, 3, 3)        out[0] z (B, C_out, D, H, W)
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, C_in, C_out, D, H, W;
+} vx_dense_conv_desc;
+int vx_dense_conv_fwd(const vx_dense_conv_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * AdamW step over every parameter tensor in one launch (torch.optim.AdamW semantics: decoupled weight decay, bias

@@ -439,3 +439,31 @@ def test_jlc_conv_tensor_core(emu, C, groups, shape, B):
     finally:
         emu.set_option(11, 0)
         emu.set_option(8, 512)
+
+
+@pytest.mark.parametrize("Cout,shape,B", [(64, (5, 6, 8), 2), (128, (3, 9, 7), 1), (16, (4, 4, 5), 1), (160, (2, 5, 6), 1)])
+def test_dense_conv_tensor_core(emu, Cout, shape, B):
+    """conv_dense_tc.cu (candidate, off by default) with its MMAs replaced by the software model on the same shared-memory
+    layout: halo-1 brick as four [position][4 channels] arrays, tap -> shifted descriptor, channel pairs through LBO, dz-slab
+    weight passes, output-channel tiles (160 = two tiles, the second partly empty), TMEM read-back and masked stores --
+    against conv3d on tf32-rounded operands (exact up to summation order) and on the fp32 operands (tf32 tolerance)."""
+    from veloxseg_b200 import ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(B, 16, *shape, generator=g)
+    w = torch.randn(Cout, 16, 3, 3, 3, generator=g) * 0.05
+
+    def tf32(t):
+        return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    with pytest.raises(RuntimeError):
+        ops.dense_conv_fwd_raw(emu, 0, x, w)            # off by default: the entry point refuses
+    emu.set_option(12, 1)                               # VX_OPT_DENSE_CONV_TC
+    try:
+        z = ops.dense_conv_fwd_raw(emu, 0, x, w)
+    finally:
+        emu.set_option(12, 0)
+    ref_t = F.conv3d(tf32(x).double(), tf32(w).double(), None, 1, 1).float()
+    ref = F.conv3d(x.double(), w.double(), None, 1, 1).float()
+    assert z.shape == ref.shape
+    assert rel_err(z, ref_t) < 1e-6, rel_err(z, ref_t)
+    assert rel_err(z, ref) < 2e-3, rel_err(z, ref)

@@ -44,3 +44,34 @@ def test_jlc_conv_tensor_core_vs_simt_and_oracle(C, shape, B):
     finally:
         lib.set_option(11, 0)
         lib.set_option(8, 512)
+
+
+@pytest.mark.parametrize("Cout,shape,B", [(128, (24, 24, 24), 4), (64, (24, 24, 24), 2), (256, (24, 24, 24), 1), (128, (32, 32, 16), 1),
+                                          (64, (5, 6, 8), 2)])
+def test_dense_conv_tensor_core_vs_library(Cout, shape, B):
+    """conv_dense_tc.cu (out_conv1 / reconstruction out_conv on tcgen05, tf32) against conv3d in fp64 on tf32-rounded
+    operands (tight) and on the fp32 operands (tf32 tolerance), forward; backward goes through the library either way."""
+    import torch.nn.functional as F
+    from veloxseg_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(B, 16, *shape, generator=g).to(DEV)
+    w = (torch.randn(Cout, 16, 3, 3, 3, generator=g) * 0.05).to(DEV)
+
+    def tf32(t):
+        return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    ops.dense_conv_tc_enable(True)
+    try:
+        xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        z = ops.dense_conv3(xr, wr)
+        torch.cuda.synchronize()
+        ref_t = F.conv3d(tf32(x).double(), tf32(w).double(), None, 1, 1)
+        ref = F.conv3d(x.double(), w.double(), None, 1, 1)
+        assert rel_err(z, ref_t) < 1e-5, rel_err(z, ref_t)
+        assert rel_err(z, ref) < 2e-3, rel_err(z, ref)
+        dz = torch.randn_like(z)
+        z.backward(dz)
+        x2, w2 = x.double().requires_grad_(True), w.double().requires_grad_(True)
+        F.conv3d(x2, w2, None, 1, 1).backward(dz.double())
+        assert rel_err(xr.grad, x2.grad) < 3e-3 and rel_err(wr.grad, w2.grad) < 3e-3
+    finally:
+        ops.dense_conv_tc_enable(False)

@@ -74,6 +74,10 @@ class PixelShuffleDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("C", C.c_int32), ("scale", C.c_int32), ("d", C.c_int32), ("h", C.c_int32), ("w", C.c_int32)]
 
 
+class DenseConvDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("C_in", C.c_int32), ("C_out", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+
+
 class AdamwDesc(C.Structure):
     _fields_ = [("n_chunks", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("weight_decay", C.c_float)]
@@ -93,6 +97,7 @@ SYMBOLS = [
     "vx_resize_workspace", "vx_resize_trilinear_fwd", "vx_resize_trilinear_bwd",
     "vx_segloss_workspace", "vx_segloss_fwd", "vx_segloss_bwd",
     "vx_patch_embed_fwd", "vx_patch_embed_bwd", "vx_pixel_shuffle_fwd", "vx_pixel_shuffle_bwd", "vx_adamw_step",
+    "vx_dense_conv_fwd",
 ]
 
 _WS_OPS = {"jlc", "mixer", "pwa_block", "gram_fwd", "lnpw", "segloss"}
@@ -137,7 +142,8 @@ class VxLib:
             f.restype = C.c_int
             f.argtypes = [vp, vp, vp, vp, sz, vp]
         for name in ("vx_inorm_fwd", "vx_inorm_bwd", "vx_gram_bwd", "vx_sdkt_loss_fwd", "vx_sdkt_loss_bwd",
-                     "vx_resize_trilinear_fwd", "vx_segloss_bwd", "vx_patch_embed_fwd", "vx_patch_embed_bwd", "vx_pixel_shuffle_fwd", "vx_pixel_shuffle_bwd", "vx_adamw_step"):
+                     "vx_resize_trilinear_fwd", "vx_segloss_bwd", "vx_patch_embed_fwd", "vx_patch_embed_bwd", "vx_pixel_shuffle_fwd", "vx_pixel_shuffle_bwd", "vx_adamw_step",
+                     "vx_dense_conv_fwd"):
             f = getattr(self.c, name)
             f.restype = C.c_int
             f.argtypes = [vp, vp, vp, vp]

@@ -199,4 +199,13 @@ int jlc_tc_geo(int B, int groups, int CG, int D, int H, int W, JlcTcArgs& geo); 
 int jlc_conv_tc_fwd(const JlcTcArgs& A, int groups, cudaStream_t stream);
 int jlc_conv_tc_dgrad(const JlcTcArgs& A, int groups, cudaStream_t stream);
 
+// Dense 3x3x3 convolution, 16 input channels, on the tensor cores (conv_dense_tc.cu; candidate, off by default)
+struct DenseConvArgs {
+  const float* x; const float* w; float* z;
+  int B, Cout, D, H, W;
+  int NT, ZR, TY, ntz, nty, nblk, tmem_cols;      // output-channel tile, brick, M-blocks per CTA
+};
+void dense_conv_tc_set(int enabled);
+int dense_conv_tc_fwd(const vx_dense_conv_desc* d, const float* x, const float* w, float* z, cudaStream_t stream);
+
 }  // namespace vx

@@ -370,7 +370,10 @@ def conv_shuffle(seq: nn.Sequential, x):
     its bias and the bias add + shuffle are one kernel; parameters and state_dict keys are those of the Sequential."""
     conv, ps = seq[0], seq[1]
     if x.is_cuda and isinstance(ps, PixelShuffle) and ps.scale <= 4 and x.dtype == torch.float32:
-        z = F.conv3d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        if ops.dense_conv_tc_enabled() and ops.dense_conv_qualifies(conv, x):      # candidate kernel, off by default
+            z = ops.dense_conv3(x, conv.weight)
+        else:
+            z = F.conv3d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
         return ops.pixel_shuffle_bias(z, conv.bias, ps.scale)
     return seq(x)
 

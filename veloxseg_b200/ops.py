@@ -718,3 +718,62 @@ def pixel_shuffle_bias(z: Tensor, bias: Optional[Tensor], scale: int) -> Tensor:
     """PixelShuffle3d(scale)(z + bias[None, :, None, None, None]) in one pass (z: output of a bias-free convolution)."""
     return _PixelShuffleBias.apply(z.contiguous(), bias, int(scale))
 
+
+# ----------------------------------------------------------------------------------------------------
+# CANDIDATE (off by default, not yet run on hardware): dense 3x3x3 convolution with 16 input channels on the tensor cores
+# (csrc/conv_dense_tc.cu) for decoder.out_conv1 / the reconstruction out_conv.  Forward on the candidate kernel, backward
+# through the library convolution.  Enabled by VX_DENSE_CONV_TC=1 (read once) or dense_conv_tc_enable(True).
+# ----------------------------------------------------------------------------------------------------
+_dense_conv_tc = None
+
+
+def dense_conv_tc_enable(on: bool):
+    global _dense_conv_tc
+    _dense_conv_tc = bool(on)
+    _lib.get_lib().set_option(12, int(_dense_conv_tc))          # VX_OPT_DENSE_CONV_TC
+
+
+def dense_conv_tc_enabled() -> bool:
+    global _dense_conv_tc
+    if _dense_conv_tc is None:
+        import os
+        if os.environ.get("VX_DENSE_CONV_TC", "0") == "1":
+            dense_conv_tc_enable(True)
+        else:
+            _dense_conv_tc = False          # the default path never touches the library switch
+    return _dense_conv_tc
+
+
+def dense_conv_qualifies(conv: "torch.nn.Conv3d", x: Tensor) -> bool:
+    return (x.is_cuda and conv.in_channels == 16 and conv.out_channels % 16 == 0 and conv.kernel_size == (3, 3, 3)
+            and conv.stride == (1, 1, 1) and conv.padding == (1, 1, 1) and conv.dilation == (1, 1, 1) and conv.groups == 1
+            and x.shape[-1] + 2 <= 128 and torch.backends.cudnn.allow_tf32)
+
+
+def dense_conv_fwd_raw(lib, stream, x: Tensor, w: Tensor) -> Tensor:
+    from ._lib import DenseConvDesc
+    x, w = _chk(x, "x"), _chk(w, "w")
+    B, Ci, D, H, W = x.shape
+    desc = DenseConvDesc(B, Ci, w.shape[0], D, H, W)
+    z = torch.empty((B, w.shape[0], D, H, W), dtype=_f32, device=x.device)
+    lib.call("vx_dense_conv_fwd", desc, [x, w], [z], stream)
+    return z
+
+
+class _DenseConv3(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return dense_conv_fwd_raw(_lib.get_lib(), _stream(x), x, w)
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, w = ctx.saved_tensors
+        dx, dw, _ = torch.ops.aten.convolution_backward(dz.contiguous(), x, w, None, [1, 1, 1], [1, 1, 1], [1, 1, 1], False,
+                                                        [0, 0, 0], 1, [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        return dx, dw
+
+
+def dense_conv3(x: Tensor, w: Tensor) -> Tensor:
+    """conv3d(x, w, bias=None, stride 1, padding 1) for 16 input channels, tf32 on the tensor cores (candidate)."""
+    return _DenseConv3.apply(x.contiguous(), w.contiguous())
