@@ -275,13 +275,16 @@ int vx_pixel_shuffle_bwd(const vx_pixel_shuffle_desc* d, const void* const* in, 
 
 /* ---------------------------------------------------------------------------------------------------
  * CANDIDATE (off unless VX_OPT_DENSE_CONV_TC is set; not yet run on hardware): dense 3x3x3 convolution, stride 1,
- * padding 1, 16 input channels, no bias -- the convolution of decoder.out_conv1 / the reconstruction out_conv
+ * padding 1, 16 input channels -- the convolution of decoder.out_conv1 / the reconstruction out_conv
  * (model/Decoder.py:73-76,150-153) on the tcgen05 tensor cores in tf32 (the precision class of
  * the library convolution under torch.backends.cudnn.allow_tf32).  Forward only.
- *   in[0] x (B, 16, D, H, W)   in[1] w (C_out, 16, 3, 3, 3)        out[0] z (B, C_out, D, H, W)
+ *   in[0] x (B, 16, D, H, W)   in[1] w (C_out, 16, 3, 3, 3)   in[2] bias (C_out) or NULL
+ *   out[0] z (B, C_out, D, H, W), or with shuffle = 4 the PixelShuffle(4) of it (superpixel.py:15):
+ *          (B, C_out / 64, 4 D, 4 H, 4 W), written directly from the accumulators
  * ------------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t B, C_in, C_out, D, H, W;
+  int32_t shuffle;                 /* 0, or 4 = store through PixelShuffle(4) (C_out % 64 == 0) */
 } vx_dense_conv_desc;
 int vx_dense_conv_fwd(const vx_dense_conv_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
 

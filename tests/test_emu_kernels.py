@@ -467,3 +467,18 @@ def test_dense_conv_tensor_core(emu, Cout, shape, B):
     assert z.shape == ref.shape
     assert rel_err(z, ref_t) < 1e-6, rel_err(z, ref_t)
     assert rel_err(z, ref) < 2e-3, rel_err(z, ref)
+    # bias, and the PixelShuffle(4) store (superpixel.py:15) straight from the accumulators
+    from veloxseg_b200.nn import PixelShuffle
+    bias = torch.randn(Cout, generator=g)
+    emu.set_option(12, 1)
+    try:
+        zb = ops.dense_conv_fwd_raw(emu, 0, x, w, bias)
+        zs = ops.dense_conv_fwd_raw(emu, 0, x, w, bias, 4) if Cout % 64 == 0 else None
+        if Cout % 64:
+            with pytest.raises(RuntimeError):
+                ops.dense_conv_fwd_raw(emu, 0, x, w, bias, 4)
+    finally:
+        emu.set_option(12, 0)
+    assert torch.equal(zb, z + bias.view(1, -1, 1, 1, 1))
+    if zs is not None:
+        assert torch.equal(zs, PixelShuffle(4, 3)(zb))

@@ -73,5 +73,17 @@ def test_dense_conv_tensor_core_vs_library(Cout, shape, B):
         x2, w2 = x.double().requires_grad_(True), w.double().requires_grad_(True)
         F.conv3d(x2, w2, None, 1, 1).backward(dz.double())
         assert rel_err(xr.grad, x2.grad) < 3e-3 and rel_err(wr.grad, w2.grad) < 3e-3
+        if Cout % 64 == 0:      # conv + bias + PixelShuffle(4) in one kernel, backward through the inverse shuffle + library conv
+            from veloxseg_b200.nn import PixelShuffle
+            bias = torch.randn(Cout, generator=g).to(DEV)
+            xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+            y = ops.dense_conv3(xr, wr, br, 4)
+            yref = PixelShuffle(4, 3)(z.detach() + bias.view(1, -1, 1, 1, 1))
+            assert y.shape == yref.shape and torch.equal(y, yref)
+            dy = torch.randn_like(y)
+            y.backward(dy)
+            x2, w2, b2 = x.double().requires_grad_(True), w.double().requires_grad_(True), bias.double().requires_grad_(True)
+            PixelShuffle(4, 3)(F.conv3d(x2, w2, b2, 1, 1)).backward(dy.double())
+            assert rel_err(xr.grad, x2.grad) < 3e-3 and rel_err(wr.grad, w2.grad) < 3e-3 and rel_err(br.grad, b2.grad) < 1e-4
     finally:
         ops.dense_conv_tc_enable(False)

@@ -75,7 +75,8 @@ class PixelShuffleDesc(C.Structure):
 
 
 class DenseConvDesc(C.Structure):
-    _fields_ = [("B", C.c_int32), ("C_in", C.c_int32), ("C_out", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+    _fields_ = [("B", C.c_int32), ("C_in", C.c_int32), ("C_out", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("shuffle", C.c_int32)]
 
 
 class AdamwDesc(C.Structure):

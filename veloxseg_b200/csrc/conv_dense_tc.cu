@@ -8,7 +8,8 @@
 // (tests/test_emu_kernels.py::test_dense_conv_tensor_core); it has NOT run on a B200 yet.  Same open hardware questions as
 // jlc_tc.cu (operand descriptors with 16-byte-aligned start addresses).  Forward only: the backward stays the library's.
 //
-//   z[b, co, p] = sum over taps t in 3^3 and ci in 0..15 of  w[co, ci, t] * x[b, ci, p + t - 1]          (no bias)
+//   z[b, co, p] = sum over taps t in 3^3 and ci in 0..15 of  w[co, ci, t] * x[b, ci, p + t - 1]  (+ bias[co])
+// optionally stored through PixelShuffle(4) (superpixel.py:15): the (B, C_out, D, H, W) intermediate never reaches memory.
 //
 // GEMM view per CTA = (batch b, tile of <= 128 output channels, brick of ZR planes x TY rows x full width):
 //   D[m = flat padded position][n = co]  with the shifted-descriptor addressing of jlc_tc.cu: the halo brick (halo 1)
@@ -202,11 +203,25 @@ __global__ void __launch_bounds__(DC_THREADS) conv_dense_tc_kernel(const __grid_
 #else
       for (int j = 0; j < 16; ++j) r[j] = g_emu_tmem_dc[wq * 32 + lane][blk * NT + c0 + j];
 #endif
-      if (ok) {
+      const int co0 = nt_i * NT + c0;
+      if (ok && co0 < A.Cout) {
+        if (A.bias) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int co = nt_i * NT + c0 + j;
-          if (co < A.Cout) A.z[o + (size_t)co * S] = r[j];
+          for (int j = 0; j < 16; ++j) r[j] += __ldg(A.bias + co0 + j);
+        }
+        if (A.shuffle == 4) {
+          // PixelShuffle(4): channel ((cls * 4 + i) * 4 + j) * 4 + k -> voxel (4 gz + i, 4 gy + j, 4 gx + k) of class cls.
+          // The 16 channels of a chunk share (cls, i); each j is four consecutive output voxels = one 16-byte store, and
+          // the lanes of a warp (consecutive gx) write one contiguous row segment.
+          const int cls = co0 >> 6, i = (co0 & 63) >> 4;
+          const size_t W4 = (size_t)4 * W, H4 = (size_t)4 * H;
+          float* orow = A.z + ((((size_t)b * (A.Cout >> 6) + cls) * (4 * D) + (4 * gz + i)) * H4 + 4 * gy) * W4 + 4 * gx;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(orow + j * W4) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) A.z[o + (size_t)(co0 + j) * S] = r[j];
         }
       }
     }
@@ -228,14 +243,19 @@ static size_t dc_smem_bytes(int NT, int ZR, int TY, int W) {
   return sizeof(float) * (4 * nall * 4 + (size_t)DC_STEPS * NT * 8);
 }
 
-int dense_conv_tc_fwd(const vx_dense_conv_desc* d, const float* x, const float* w, float* z, cudaStream_t st) {
+int dense_conv_tc_fwd(const vx_dense_conv_desc* d, const float* x, const float* w, const float* bias, float* z, cudaStream_t st) {
   if (!g_dc_enabled) { set_error("dense_conv: the candidate kernel is off (VX_OPT_DENSE_CONV_TC)"); return VX_ERR_UNSUPPORTED; }
   if (!d || d->B <= 0 || d->C_in != 16 || d->C_out <= 0 || d->C_out % 16 || d->D <= 0 || d->H <= 0 || d->W <= 0 || d->W + 2 > 128) {
     set_error("dense_conv: needs 16 input channels, output channels in multiples of 16, width <= 126");
     return VX_ERR_UNSUPPORTED;
   }
+  if (d->shuffle != 0 && (d->shuffle != 4 || d->C_out % 64)) {
+    set_error("dense_conv: fused pixel shuffle needs scale 4 and output channels in multiples of 64");
+    return VX_ERR_UNSUPPORTED;
+  }
+  if (((uintptr_t)z & 15) != 0) { set_error("dense_conv: output not 16-byte aligned"); return VX_ERR_BAD_DESC; }
   DenseConvArgs A{};
-  A.x = x; A.w = w; A.z = z; A.B = d->B; A.Cout = d->C_out; A.D = d->D; A.H = d->H; A.W = d->W;
+  A.x = x; A.w = w; A.bias = bias; A.shuffle = d->shuffle; A.z = z; A.B = d->B; A.Cout = d->C_out; A.D = d->D; A.H = d->H; A.W = d->W;
   A.NT = d->C_out <= 128 ? (d->C_out + 31) / 32 * 32 : 128;
   const int ntile = cdiv(d->C_out, A.NT), max_blk = 512 / A.NT < DC_MAX_BLK ? 512 / A.NT : DC_MAX_BLK;
   double best = -1.0;
@@ -269,5 +289,5 @@ using namespace vx;
 
 extern "C" int vx_dense_conv_fwd(const vx_dense_conv_desc* d, const void* const* in, void* const* out, vx_stream_t stream) {
   if (!in || !out || !in[0] || !in[1] || !out[0]) { set_error("dense_conv_fwd: null pointer"); return VX_ERR_BAD_DESC; }
-  return dense_conv_tc_fwd(d, (const float*)in[0], (const float*)in[1], (float*)out[0], (cudaStream_t)stream);
+  return dense_conv_tc_fwd(d, (const float*)in[0], (const float*)in[1], (const float*)in[2], (float*)out[0], (cudaStream_t)stream);
 }

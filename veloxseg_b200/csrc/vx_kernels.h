@@ -201,11 +201,11 @@ int jlc_conv_tc_dgrad(const JlcTcArgs& A, int groups, cudaStream_t stream);
 
 // Dense 3x3x3 convolution, 16 input channels, on the tensor cores (conv_dense_tc.cu; candidate, off by default)
 struct DenseConvArgs {
-  const float* x; const float* w; float* z;
-  int B, Cout, D, H, W;
+  const float* x; const float* w; const float* bias; float* z;
+  int B, Cout, D, H, W, shuffle;
   int NT, ZR, TY, ntz, nty, nblk, tmem_cols;      // output-channel tile, brick, M-blocks per CTA
 };
 void dense_conv_tc_set(int enabled);
-int dense_conv_tc_fwd(const vx_dense_conv_desc* d, const float* x, const float* w, float* z, cudaStream_t stream);
+int dense_conv_tc_fwd(const vx_dense_conv_desc* d, const float* x, const float* w, const float* bias, float* z, cudaStream_t stream);
 
 }  // namespace vx

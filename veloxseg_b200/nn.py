@@ -371,6 +371,8 @@ def conv_shuffle(seq: nn.Sequential, x):
     conv, ps = seq[0], seq[1]
     if x.is_cuda and isinstance(ps, PixelShuffle) and ps.scale <= 4 and x.dtype == torch.float32:
         if ops.dense_conv_tc_enabled() and ops.dense_conv_qualifies(conv, x):      # candidate kernel, off by default
+            if ps.scale == 4 and conv.out_channels % 64 == 0:                      # conv + bias + shuffle in one kernel
+                return ops.dense_conv3(x, conv.weight, conv.bias, 4)
             z = ops.dense_conv3(x, conv.weight)
         else:
             z = F.conv3d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)

@@ -750,30 +750,41 @@ def dense_conv_qualifies(conv: "torch.nn.Conv3d", x: Tensor) -> bool:
             and x.shape[-1] + 2 <= 128 and torch.backends.cudnn.allow_tf32)
 
 
-def dense_conv_fwd_raw(lib, stream, x: Tensor, w: Tensor) -> Tensor:
+def dense_conv_fwd_raw(lib, stream, x: Tensor, w: Tensor, bias: Optional[Tensor] = None, shuffle: int = 0) -> Tensor:
     from ._lib import DenseConvDesc
     x, w = _chk(x, "x"), _chk(w, "w")
     B, Ci, D, H, W = x.shape
-    desc = DenseConvDesc(B, Ci, w.shape[0], D, H, W)
-    z = torch.empty((B, w.shape[0], D, H, W), dtype=_f32, device=x.device)
-    lib.call("vx_dense_conv_fwd", desc, [x, w], [z], stream)
+    Co = w.shape[0]
+    desc = DenseConvDesc(B, Ci, Co, D, H, W, int(shuffle))
+    shape = (B, Co // shuffle ** 3, D * shuffle, H * shuffle, W * shuffle) if shuffle else (B, Co, D, H, W)
+    z = torch.empty(shape, dtype=_f32, device=x.device)
+    lib.call("vx_dense_conv_fwd", desc, [x, w, _chk(bias, "bias") if bias is not None else None], [z], stream)
     return z
 
 
 class _DenseConv3(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w):
+    def forward(ctx, x, w, bias, shuffle):
         ctx.save_for_backward(x, w)
-        return dense_conv_fwd_raw(_lib.get_lib(), _stream(x), x, w)
+        ctx.shuffle, ctx.has_bias = int(shuffle), bias is not None
+        return dense_conv_fwd_raw(_lib.get_lib(), _stream(x), x, w, bias, int(shuffle))
 
     @staticmethod
-    def backward(ctx, dz):
+    def backward(ctx, dy):
         x, w = ctx.saved_tensors
-        dx, dw, _ = torch.ops.aten.convolution_backward(dz.contiguous(), x, w, None, [1, 1, 1], [1, 1, 1], [1, 1, 1], False,
-                                                        [0, 0, 0], 1, [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
-        return dx, dw
+        db = None
+        if ctx.shuffle:         # inverse shuffle of the output gradient (+ the bias gradient in the same pass)
+            dz, db = pixel_shuffle_bwd_raw(_lib.get_lib(), _stream(dy), dy.contiguous(), ctx.shuffle, ctx.has_bias)
+        else:
+            dz = dy.contiguous()
+            if ctx.has_bias:
+                db = dz.sum(dim=(0, 2, 3, 4))
+        dx, dw, _ = torch.ops.aten.convolution_backward(dz, x, w, None, [1, 1, 1], [1, 1, 1], [1, 1, 1], False, [0, 0, 0], 1,
+                                                        [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        return dx, dw, db, None
 
 
-def dense_conv3(x: Tensor, w: Tensor) -> Tensor:
-    """conv3d(x, w, bias=None, stride 1, padding 1) for 16 input channels, tf32 on the tensor cores (candidate)."""
-    return _DenseConv3.apply(x.contiguous(), w.contiguous())
+def dense_conv3(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, shuffle: int = 0) -> Tensor:
+    """conv3d(x, w, bias, stride 1, padding 1) for 16 input channels, tf32 on the tensor cores (candidate); with
+    shuffle = 4 the result is PixelShuffle(4) of it, stored straight from the accumulators."""
+    return _DenseConv3.apply(x.contiguous(), w.contiguous(), bias, int(shuffle))
