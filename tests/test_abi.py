@@ -54,3 +54,19 @@ def test_sass_is_sm100(lib_path):
     import subprocess
     out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", lib_path], capture_output=True, text=True).stdout
     assert "sm_100a" in out, out
+
+
+def test_candidate_kernels_are_off_by_default(lib_path):
+    """The tcgen05 candidates written without GPU access must not be reachable unless switched on: the dense-conv entry point
+    refuses before it looks at its buffers, and the Python layer routes out_conv1 to the library convolution."""
+    import os
+    from veloxseg_b200 import _lib, ops
+    lib = _lib.VxLib(lib_path)
+    d = _lib.DenseConvDesc(1, 16, 64, 4, 4, 4, 0)
+    dummy = (ctypes.c_float * 4)()
+    ptrs = (ctypes.c_void_p * 3)(ctypes.addressof(dummy), ctypes.addressof(dummy), None)
+    outs = (ctypes.c_void_p * 1)(ctypes.addressof(dummy))
+    rc = lib.c.vx_dense_conv_fwd(ctypes.byref(d), ptrs, outs, None)
+    assert rc < 0 and "off" in lib.last_error()
+    if os.environ.get("VX_DENSE_CONV_TC", "0") != "1":
+        assert ops.dense_conv_tc_enabled() is False
