@@ -5,7 +5,9 @@
 // spent: the indexing / operand layouts are checked on the CPU shim (tests/test_emu_kernels.py::test_jlc_conv_tensor_core,
 // software model of the MMA on the same shared-memory layout); it has NOT run on a B200 yet.  Hardware questions to
 // settle first: operand descriptors whose start address is 16-byte (not 128-byte) aligned, and LBO values that are not a
-// multiple of 128 B.  The SIMT kernels in jlc.cu remain the product path until this one is parity-green and measured.
+// multiple of 128 B.  On paper both are inside the canonical K-major no-swizzle form, in 16-byte units
+// ((8, n), 2) : ((1, SBO), LBO) with free SBO / LBO (CuTe's mma_traits_sm100.hpp, "UmmaDescriptor Major-K", INTERLEAVE):
+// here ((8, 16), 2) : ((1, 8), LBO).  The SIMT kernels in jlc.cu remain the product path until this one is parity-green and measured.
 //
 // GEMM view per CTA = (batch b, group g, brick of ZR planes x TY rows x full width):
 //   D[m = flat padded position (128 per M-block)][n = z5 co 0..3 | z3 co 0..3 | z1 co 0..3 | 4 zero columns]
