@@ -270,6 +270,11 @@ def run_ours(args, rank, world, local_rank):
     del ts, model
     torch.cuda.empty_cache()
     infer = None if args.no_infer else run_infer(rank, world, dev, volume=tuple(int(v) for v in args.infer_volume.split("x")))
+    eager = evalf = None
+    if world == 1 and not args.no_eager:
+        torch.cuda.empty_cache()
+        eager = gpu_eager_port(dev, args.workload, PATCHES)
+        evalf = eval_forward_legs(dev, args.workload)
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -299,6 +304,9 @@ def run_ours(args, rank, world, local_rank):
                             "note": "same step with the cuDNN convolutions outside the hot path in fp32 too"}
     if infer is not None:
         line["infer"] = infer
+    if eager is not None:
+        line["gpu_eager_baseline"] = eager
+        line["eval_forward"] = evalf
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_port(steps=3, patches=1, threads=None, cfg_name=args.workload, min_seconds=10.0)   # ~10 s of CPU work
     print(json.dumps(line), flush=True)
@@ -348,6 +356,114 @@ def run_infer(rank, world, dev, reps=3, volume=(320, 320, 256)):
                               if sharded_io else "every rank copies the whole host volume; all-reduce of the logit sums"),
                        "timed": "H2D volume + windows + all-reduce + argmax + D2H labels, best of %d" % reps,
                        "fg_voxels": int(seg.sum())}}
+
+
+def gpu_eager_port(dev, cfg_name, patches, steps=10, warmup=3):
+    """The GPU bar: the same reference math (the oracle's plain-torch
+    restatement: F.conv3d / instance_norm / einsum / softmax leaf ops, autograd backward, torch AdamW) under PyTorch eager on
+    this B200 -- fp32 (TF32 off) and torch.autocast(bfloat16).  Baseline only; nothing of libveloxseg runs here."""
+    from oracle import veloxseg_oracle as O
+    from veloxseg_b200.configs import MODEL_CONFIGS, TRAIN
+    from veloxseg_b200.nn import VeloxSeg
+    cfg = MODEL_CONFIGS[cfg_name]
+    spec = O.ModelSpec(cfg)
+    x, y = synth_batch(cfg, patches, 1000)
+    x, y = x.to(dev), y.to(dev)
+    out = {}
+    for mode in ("fp32", "autocast_bf16"):
+        torch.manual_seed(12345)
+        m = VeloxSeg(**cfg)
+        p = {k: (v.detach().clone().to(dev).requires_grad_(True) if v.dtype.is_floating_point else v.to(dev)) for k, v in m.state_dict().items()}
+        leaves = [v for v in p.values() if v.dtype.is_floating_point]
+        opt = torch.optim.AdamW(leaves, lr=TRAIN["lr"], weight_decay=TRAIN["weight_decay"], fused=True)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "autocast_bf16"):
+                outs = O.forward(x, p, spec, training=True)
+            loss = O.total_loss([o.float() for o in outs], y, x, spec.M, TRAIN["deep_Loss_weight"], TRAIN["RC_Loss_weight"], TRAIN["Feature_Loss_weight"])
+            loss.backward()
+            opt.step()
+            return loss
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            loss = step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        out[mode] = {"ms_per_step": round(ms, 3), "value": round(patches / (ms * 1e-3), 2), "unit": "patches/s", "loss": float(loss)}
+        del opt, p, leaves
+        torch.cuda.empty_cache()
+    out["what"] = ("oracle restatement of the reference (plain torch leaf ops + autograd + fused torch AdamW) under PyTorch eager on this GPU, "
+                   "%d patches/step, %d timed steps, cudnn.benchmark on, TF32 off" % (patches, steps))
+    return out
+
+
+def eval_forward_legs(dev, cfg_name, seconds=3.0):
+    """BASELINE configs[0] / the reference's only published numbers (README: 599.06 patches/s GPU, 6.67 patches/s CPU):
+    speed_test.py's protocol -- eval(), grad off, randn input; GPU: largest power-of-two batch <= 16, synchronize per
+    iteration; CPU: batch 1, ONE thread (speed_test.py:27,64-70,102-134).  Time-boxed to `seconds` per leg instead of 60 s."""
+    from oracle import veloxseg_oracle as O
+    from veloxseg_b200.configs import MODEL_CONFIGS
+    from veloxseg_b200.nn import VeloxSeg
+    cfg = MODEL_CONFIGS[cfg_name]
+    spec = O.ModelSpec(cfg)
+    torch.manual_seed(12345)
+    model = VeloxSeg(**cfg)
+    p_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    p_gpu = {k: v.to(dev) for k, v in p_cpu.items()}
+    model = model.to(dev).eval()
+    res = {}
+
+    def timed(fn, bs, sync):
+        fn()
+        fn()
+        sync()
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < seconds:
+            fn()
+            sync()
+            n += 1
+        return round(n * bs / (time.perf_counter() - t0), 2)
+    with torch.no_grad():
+        for bs in (1, 16):
+            xg = torch.randn(bs, sum(cfg["in_ch"]), *cfg["input_size"], device=dev)
+            res["ours_fp32_bs%d" % bs] = timed(lambda: model(xg), bs, torch.cuda.synchronize)
+            g = torch.cuda.CUDAGraph()
+            s_ = torch.cuda.Stream(device=dev)
+            s_.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s_):
+                model(xg)
+            torch.cuda.current_stream(dev).wait_stream(s_)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                yg = model(xg)
+            res["ours_fp32_graph_bs%d" % bs] = timed(g.replay, bs, torch.cuda.synchronize)
+            del g, yg
+            torch.backends.cudnn.allow_tf32 = False
+            res["eager_fp32_bs%d" % bs] = timed(lambda: O.forward(xg, p_gpu, spec, training=False), bs, torch.cuda.synchronize)
+
+            def amp():
+                with torch.autocast("cuda", dtype=torch.float16):
+                    O.forward(xg, p_gpu, spec, training=False)
+            res["eager_autocast_fp16_bs%d" % bs] = timed(amp, bs, torch.cuda.synchronize)
+        nthr = torch.get_num_threads()
+        torch.set_num_threads(1)
+        xc = torch.randn(1, sum(cfg["in_ch"]), *cfg["input_size"])
+        res["cpu_1thread_fp32_bs1"] = timed(lambda: O.forward(xc, p_cpu, spec, training=False), 1, lambda: None)
+        torch.set_num_threads(nthr)
+    res["unit"] = "patches/s"
+    res["protocol"] = ("speed_test.py: eval forward, grad off, randn %s input, synchronize per iteration, %.0f s per leg; 'ours' = "
+                       "veloxseg_b200.nn.VeloxSeg (eager launches / one CUDA graph), 'eager' = oracle restatement of the reference under "
+                       "PyTorch eager on this GPU, cpu = the same on ONE host thread (reference README: 599.06 GPU fp16 on its hardware, "
+                       "6.67 CPU)" % (cfg_name, seconds))
+    return res
 
 
 def cpu_port(steps, patches, threads, cfg_name=CFG_NAME, min_seconds=0.0, warmup=1):
@@ -408,7 +524,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=CFG_NAME, choices=sorted(CFG_TITLE),
@@ -416,10 +532,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the secondary all-fp32 timing")
     ap.add_argument("--no-infer", action="store_true", help="skip the sliding-window inference measurement")
+    ap.add_argument("--only-infer", action="store_true", help="run only the sliding-window inference leg and print its object")
     ap.add_argument("--infer-volume", default="320x320x256",
                     help="synthetic Hecktor volume of the sliding-window leg: 320x320x256 (45 windows, default) or 512x512x384 (200 windows)")
-    ap.add_argument("--library-convs", default="tf32", choices=["tf32", "fp32"],
-                    help="precision of the cuDNN convolutions outside the hot path (out_conv1, Down/Up convs, patch-embed)")
+    ap.add_argument("--library-convs", default="fp32", choices=["tf32", "fp32"],
+                    help="precision of any remaining library (cuDNN) convolution: fp32 = the reference's precision (default, the "
+                         "headline); tf32 is an A/B switch only")
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager GPU baseline and the eval-forward legs")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -431,6 +550,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
+        if args.only_infer:
+            torch.cuda.set_device(local_rank)
+            res = run_infer(rank, world, torch.device("cuda", local_rank), volume=tuple(int(v) for v in args.infer_volume.split("x")))
+            if rank == 0:
+                print(json.dumps(res), flush=True)
+            return
         run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:

@@ -147,13 +147,13 @@ def gather_tokens(x: Tensor, heads: int, bws, sws) -> Tuple[Tensor, List[List[in
     return torch.cat(outs, dim=2), Ns, n_ref
 
 
-def _lerp_matrix(n: int, s: int, dtype) -> Tensor:
+def _lerp_matrix(n: int, s: int, dtype, device=None) -> Tensor:
     """(n*s, n) matrix of 1-D linear interpolation with align_corners=True
     (src = dst * (n-1)/(n*s-1)); identity when s == 1.  Matches F.interpolate, PWA.py:190."""
     m = torch.zeros(n * s, n, dtype=dtype)
     if n * s == 1:
         m[0, 0] = 1
-        return m
+        return m.to(device) if device is not None else m
     scale = (n - 1) / (n * s - 1) if n * s > 1 else 0.0
     for d in range(n * s):
         src = d * scale
@@ -162,7 +162,7 @@ def _lerp_matrix(n: int, s: int, dtype) -> Tensor:
         w1 = src - i0
         m[d, i0] += 1.0 - w1
         m[d, i1] += w1
-    return m
+    return m.to(device) if device is not None else m
 
 
 def scatter_tokens(tok: Tensor, heads: int, bws, sws, Ns, n) -> Tensor:
@@ -177,8 +177,8 @@ def scatter_tokens(tok: Tensor, heads: int, bws, sws, Ns, n) -> Tensor:
         N = Nh * Nw * Nd
         sh, sw_, sd = sws[j]
         t = tok[:, :, idx:idx + N].reshape(B, h, Nh, Nw, Nd, nh, nw, nd, c)
-        Mh, Mw, Md = (_lerp_matrix(nh, sh, tok.dtype), _lerp_matrix(nw, sw_, tok.dtype),
-                      _lerp_matrix(nd, sd, tok.dtype))
+        Mh, Mw, Md = (_lerp_matrix(nh, sh, tok.dtype, tok.device), _lerp_matrix(nw, sw_, tok.dtype, tok.device),
+                      _lerp_matrix(nd, sd, tok.dtype, tok.device))
         t = torch.einsum("bhxyzijkc,pi,qj,rk->bhcxpyqzr", t, Mh, Mw, Md)
         outs.append(t.reshape(B, h * c, Nh * nh * sh, Nw * nw * sw_, Nd * nd * sd))
         idx += N
