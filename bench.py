@@ -110,11 +110,9 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    # Library (cuDNN) convolutions OUTSIDE the section-8 path (out_conv1, Down/Up convs, patch-embed): tf32 tensor cores by
-    # default -- BASELINE.json names bf16 for this config, tf32 is above that, and the whole-model parity tests bound this
-    # mode at 3e-3 against the reference (measured ~1e-3).  Every libveloxseg kernel computes in fp32 (the
-    # tcgen05 contraction is 3xTF32 = fp32-accurate) in both modes.  --library-convs fp32 gives the all-fp32 number.
-    torch.backends.cudnn.allow_tf32 = args.library_convs == "tf32"
+    # No library (cuDNN / cuBLAS) kernel is on the model path any more: every convolution is libveloxseg's, fp32-accurate
+    # (fp32 SIMT or tcgen05 3xTF32).  TF32 is switched off for whatever torch op remains around the step.
+    torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = os.environ.get("VX_CUDNN_BENCHMARK", "1") == "1"
     cfg = MODEL_CONFIGS[args.workload]
@@ -127,9 +125,6 @@ def run_ours(args, rank, world, local_rank):
     lib = _lib.get_lib()
     pw_tc = os.environ.get("VX_PW_TC", "1") == "1"
     lib.set_option(1, int(pw_tc))        # VX_OPT_PW_TENSOR_CORES (A/B switch; default on)
-    jlc_tc = os.environ.get("VX_JLC_CONV_TC", "0") == "1"
-    if jlc_tc:
-        lib.set_option(11, 1)            # VX_OPT_JLC_CONV_TC: candidate tcgen05 JLC conv kernels (A/B switch; default off)
     x_h, y_h = synth_batch(cfg, PATCHES, 1000 + rank)
     x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
     x_d, y_d = x_h.to(dev), y_h.to(dev)
@@ -241,30 +236,6 @@ def run_ours(args, rank, world, local_rank):
                             "no host gaps); kernels of the forked streams overlap in the graph-replayed step, so the summed "
                             "kernel time exceeds ms_per_step; working sets are L2-resident at 4 patches (DESIGN.md section 3)"}
             break
-    # ---- the same device-resident measurement with the library convolutions in fp32 as well (reported beside the headline)
-    alt_ms = None
-    if args.library_convs == "tf32" and not args.no_alt:
-        torch.backends.cudnn.allow_tf32 = False
-        torch.manual_seed(12345)
-        ts2 = TrainStep(VeloxSeg(**cfg), len(cfg["in_ch"]), dev, lr=TRAIN["lr"], weight_decay=TRAIN["weight_decay"],
-                        deep_weights=TRAIN["deep_Loss_weight"], rc_weight=TRAIN["RC_Loss_weight"],
-                        feature_weight=TRAIN["Feature_Loss_weight"])
-        for _ in range(3):
-            ts2.step(x_d, y_d)
-        barrier()
-        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 5))]
-        for a, b in ev2:
-            flush.zero_()
-            a.record()
-            ts2.step(x_d, y_d)
-            b.record()
-        barrier()
-        t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2) / len(ev2)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        alt_ms = float(t2.item())
-        del ts2
-        torch.backends.cudnn.allow_tf32 = True
     # ---- second headline metric: sliding-window inference (all ranks take part)
     used_graph = ts.use_graph
     del ts, model
@@ -290,18 +261,14 @@ def run_ours(args, rank, world, local_rank):
                    "launch": ("eager launches" if not used_graph else "whole step replayed as one CUDA graph" if world == 1 else
                               "CUDA graph (fwd+bwd) -> one NCCL all-reduce of the flat 9 MB gradient -> CUDA graph (AdamW)"),
                    "pointwise": "tcgen05 3xTF32 (fp32-accurate) for S>=1024 (weight gradients S>=512), fp32 SIMT below" if pw_tc else "fp32 SIMT",
-                   "library_convs_outside_path": args.library_convs,
-                   **({"jlc_conv": "tcgen05 implicit-GEMM candidate (VX_JLC_CONV_TC=1)"} if jlc_tc else {}),
-                   **({"out_conv": "tcgen05 tf32 implicit-GEMM candidate, forward (VX_DENSE_CONV_TC=1)"}
-                      if os.environ.get("VX_DENSE_CONV_TC", "0") == "1" and args.library_convs == "tf32" else {})},
+                   "convolutions": "all libveloxseg: out_conv1 / RC out_conv tcgen05 3xTF32 implicit GEMM with fused bias + PixelShuffle, "
+                                   "DownConv / UpConv / heads / stems fp32 SIMT; no cuDNN or cuBLAS kernel in the step",
+                   },
         "e2e": {"value": round(total_patches / e2e_s, 3), "unit": "patches/s",
                 "h2d_bytes_per_step": int(xb[0].numel() * xb[0].element_size() + yb[0].numel() * yb[0].element_size()),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "host_enqueue_ms_per_step": round(enqueue_ms, 2), "clocks": clk.summary(), "roofline": roof, "loss": last_loss, "top_kernels": table,
     }
-    if alt_ms is not None:
-        line["all_fp32"] = {"ms_per_step": round(alt_ms, 3), "value": round(PATCHES * world / (alt_ms * 1e-3), 3), "unit": "patches/s",
-                            "note": "same step with the cuDNN convolutions outside the hot path in fp32 too"}
     if infer is not None:
         line["infer"] = infer
     if eager is not None:
@@ -530,14 +497,11 @@ def main():
     ap.add_argument("--workload", default=CFG_NAME, choices=sorted(CFG_TITLE),
                     help="model config of the train step: autopetii = BASELINE configs[1] (the headline metric), brats2021 = configs[2]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-alt", action="store_true", help="skip the secondary all-fp32 timing")
+    ap.add_argument("--no-alt", action="store_true", help="(accepted for old scripts; there is no alternate precision leg any more)")
     ap.add_argument("--no-infer", action="store_true", help="skip the sliding-window inference measurement")
     ap.add_argument("--only-infer", action="store_true", help="run only the sliding-window inference leg and print its object")
     ap.add_argument("--infer-volume", default="320x320x256",
                     help="synthetic Hecktor volume of the sliding-window leg: 320x320x256 (45 windows, default) or 512x512x384 (200 windows)")
-    ap.add_argument("--library-convs", default="fp32", choices=["tf32", "fp32"],
-                    help="precision of any remaining library (cuDNN) convolution: fp32 = the reference's precision (default, the "
-                         "headline); tf32 is an A/B switch only")
     ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager GPU baseline and the eval-forward legs")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -48,14 +48,9 @@ const char* vx_last_error_string(void);
  *   VX_OPT_WGRAD_TC_MIN_S   voxel count from which weight gradients of the 1x1 contractions run on the tcgen05 kernel
  *                           (default 512; VX_OPT_PW_TENSOR_CORES = 0 switches it off together with the forward kernel).
  *   VX_OPT_SIDE_WGRAD       1 (default): inside a backward op the weight-gradient kernels run on a library-owned side
- *                           stream that forks from and joins back into the caller's stream before the op returns.
- *   VX_OPT_JLC_CONV_TC      0 (default).  1: the forward and data-gradient JLC grouped convolutions with 4 or 8 channels per group (levels 1-2) run on the
- *                           tcgen05 implicit-GEMM candidate kernel (jlc_tc.cu) -- checked on the CPU shim only, not yet
- *                           run or measured on hardware; for A/B measurement.
- *   VX_OPT_DENSE_CONV_TC    0 (default).  1: enables vx_dense_conv_fwd (candidate, same status). */
+ *                           stream that forks from and joins back into the caller's stream before the op returns. */
 enum { VX_OPT_PW_TENSOR_CORES = 1, VX_OPT_PW_SMALL_MAX_S = 2, VX_OPT_PW_TC_MIN_S = 3, VX_OPT_JLC_TILE_FWD = 4,
-       VX_OPT_JLC_TILE_WGRAD = 5, VX_OPT_JLC_SMALL_MAX_S = 8, VX_OPT_WGRAD_TC_MIN_S = 9, VX_OPT_SIDE_WGRAD = 10,
-       VX_OPT_JLC_CONV_TC = 11, VX_OPT_DENSE_CONV_TC = 12 };
+       VX_OPT_JLC_TILE_WGRAD = 5, VX_OPT_JLC_SMALL_MAX_S = 8, VX_OPT_WGRAD_TC_MIN_S = 9, VX_OPT_SIDE_WGRAD = 10 };
 int vx_set_option(int option, int value);
 /* number of kernels this library has enqueued since it was loaded (all threads, all streams) */
 uint64_t vx_launch_count(void);
@@ -274,19 +269,29 @@ int vx_pixel_shuffle_fwd(const vx_pixel_shuffle_desc* d, const void* const* in, 
 int vx_pixel_shuffle_bwd(const vx_pixel_shuffle_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
- * CANDIDATE (off unless VX_OPT_DENSE_CONV_TC is set; not yet run on hardware): dense 3x3x3 convolution, stride 1,
- * padding 1, 16 input channels -- the convolution of decoder.out_conv1 / the reconstruction out_conv
- * (model/Decoder.py:73-76,150-153) on the tcgen05 tensor cores in tf32 (the precision class of
- * the library convolution under torch.backends.cudnn.allow_tf32).  Forward only.
- *   in[0] x (B, 16, D, H, W)   in[1] w (C_out, 16, 3, 3, 3)   in[2] bias (C_out) or NULL
- *   out[0] z (B, C_out, D, H, W), or with shuffle = 4 the PixelShuffle(4) of it (superpixel.py:15):
- *          (B, C_out / 64, 4 D, 4 H, 4 W), written directly from the accumulators
+ * Convolutions of the glue layers around the hot path, all in fp32 accuracy:
+ *   kernel 3, stride 1, pad 1, C_in 16   decoder.out_conv1 / reconstruction out_conv, model/Decoder.py:73-76,150-153
+ *                                        -> tcgen05 implicit GEMMs (3xTF32 = fp32-accurate), csrc/conv3_tc.cu; with
+ *                                        shuffle = 4 the PixelShuffle(4) of components/superpixel.py:15 and the bias are part
+ *                                        of the kernel (y is (B, C_out/64, 4D, 4H, 4W); dy of that shape in backward)
+ *   kernel 2p-1, stride p, pad p-1       DownConv.down, model/components/conv_blocks.py:10-17 (p = 4: k7 s4, p = 2: k3 s2)
+ *   transposed, kernel = stride = 2      UpConv.up (ConvTranspose3d), model/components/conv_blocks.py:31-35
+ * (D, H, W) is the INPUT extent.  Weights in torch layout: (C_out, C_in, k, k, k), transposed: (C_in, C_out, k, k, k).
+ *   fwd  in[0] x   in[1] w   in[2] bias or NULL                     out[0] y
+ *   bwd  in[0] dy  in[1] x   in[2] w      out[0] dx or NULL (no data gradient wanted)  out[1] dw  out[2] db or NULL
+ * Any other geometry returns VX_ERR_UNSUPPORTED (there is no library fallback behind this ABI).
  * ------------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t B, C_in, C_out, D, H, W;
-  int32_t shuffle;                 /* 0, or 4 = store through PixelShuffle(4) (C_out % 64 == 0) */
-} vx_dense_conv_desc;
-int vx_dense_conv_fwd(const vx_dense_conv_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
+  int32_t kernel, stride, pad;
+  int32_t transposed;              /* 1: ConvTranspose3d with kernel == stride, pad 0 */
+  int32_t shuffle;                 /* dense k3 only: 0, or 4 = PixelShuffle(4) fused (C_out % 64 == 0) */
+} vx_conv_desc;
+size_t vx_conv_workspace(const vx_conv_desc* d);
+int vx_conv_fwd(const vx_conv_desc* d, const void* const* in, void* const* out, void* workspace, size_t workspace_bytes,
+                vx_stream_t stream);
+int vx_conv_bwd(const vx_conv_desc* d, const void* const* in, void* const* out, void* workspace, size_t workspace_bytes,
+                vx_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * AdamW step over every parameter tensor in one launch (torch.optim.AdamW semantics: decoupled weight decay, bias

@@ -56,17 +56,23 @@ def test_sass_is_sm100(lib_path):
     assert "sm_100a" in out, out
 
 
-def test_candidate_kernels_are_off_by_default(lib_path):
-    """The tcgen05 candidates written without GPU access must not be reachable unless switched on: the dense-conv entry point
-    refuses before it looks at its buffers, and the Python layer routes out_conv1 to the library convolution."""
-    import os
-    from veloxseg_b200 import _lib, ops
+def test_conv_entry_point_reports_unsupported_geometry(lib_path):
+    """vx_conv_* has no library fallback: a geometry outside the VeloxSeg layers is refused with a message, before any
+    buffer is touched; the workspace query of the tcgen05 convolution is non-zero and of the others zero."""
+    from veloxseg_b200 import _lib
     lib = _lib.VxLib(lib_path)
-    d = _lib.DenseConvDesc(1, 16, 64, 4, 4, 4, 0)
+    d = _lib.ConvDesc(1, 16, 64, 4, 4, 4, 2, 2, 0, 1, 4)          # transposed conv with a pixel shuffle: not a VeloxSeg layer
     dummy = (ctypes.c_float * 4)()
     ptrs = (ctypes.c_void_p * 3)(ctypes.addressof(dummy), ctypes.addressof(dummy), None)
-    outs = (ctypes.c_void_p * 1)(ctypes.addressof(dummy))
-    rc = lib.c.vx_dense_conv_fwd(ctypes.byref(d), ptrs, outs, None)
-    assert rc < 0 and "off" in lib.last_error()
-    if os.environ.get("VX_DENSE_CONV_TC", "0") != "1":
-        assert ops.dense_conv_tc_enabled() is False
+    outs = (ctypes.c_void_p * 3)(ctypes.addressof(dummy), ctypes.addressof(dummy), None)
+    rc = lib.c.vx_conv_fwd(ctypes.byref(d), ptrs, outs, None, 0, None)
+    assert rc == -4 and "unsupported" in lib.last_error()
+    assert lib.workspace("conv", _lib.ConvDesc(4, 16, 128, 24, 24, 24, 3, 1, 1, 0, 4)) > 0
+    assert lib.workspace("conv", _lib.ConvDesc(4, 2, 16, 96, 96, 96, 7, 4, 3, 0, 0)) == 0
+
+
+def test_model_path_has_no_library_convolution():
+    """nn.py calls no torch / cuDNN convolution (everything goes through ops.conv3d)."""
+    src = open(os.path.join(ROOT, "veloxseg_b200", "nn.py")).read()
+    for needle in ("F.conv3d", "F.conv_transpose3d", "torch.nn.functional", "self.proj(", "self.down(", "self.up(", "seq(x)"):
+        assert needle not in src, needle

@@ -402,83 +402,56 @@ def test_pixel_shuffle_bias(emu, B, C, s, size):
     assert torch.equal(dz, gz) and close(db, gb, rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("C,groups,shape,B", [(8, 2, (5, 6, 8), 2), (16, 4, (9, 7, 12), 1), (8, 2, (3, 13, 5), 1),
-                                              (16, 2, (5, 6, 8), 1), (8, 1, (7, 9, 4), 2)])      # the last two: 8 channels per group
-def test_jlc_conv_tensor_core(emu, C, groups, shape, B):
-    """jlc_tc.cu (candidate, off by default) with its MMAs replaced by the software model on the same shared-memory layout:
-    brick staging with halo and guards, tap -> shifted-descriptor arithmetic (two taps per k-step), weight rows of the three
-    branches, TMEM read-back, masked stores and the per-tile InstanceNorm statistics, and the 3-pass data gradient (mirrored
-    taps, per-branch k-step lists, accumulation across passes) -- against the SIMT conv path (branch outputs z, statistics,
-    dx) and the oracle (block output, all gradients)."""
-    from veloxseg_b200 import ops
-    O = _oracle()
-    e = 2
-    torch.manual_seed(4)
-    x = torch.randn(B, C, *shape)
-    params = jlc_params(C, groups, e, seed=6)
-    emu.set_option(8, 0)          # VX_OPT_JLC_SMALL_MAX_S = 0: the small-volume kernels would take these shapes
-    try:
-        y0, z0, o0, h0, st0 = ops.jlc_fwd_raw(emu, 0, x, params, groups, e)
-        emu.set_option(11, 1)     # VX_OPT_JLC_CONV_TC
-        y1, z1, o1, h1, st1 = ops.jlc_fwd_raw(emu, 0, x, params, groups, e)
-        assert rel_err(z1, z0) < 2e-6, rel_err(z1, z0)
-        assert not torch.equal(z1, z0)          # the 3-term split drops lo*lo: bit-identical output would mean the SIMT path ran
-        assert rel_err(st1, st0) < 2e-5 and rel_err(y1, y0) < 2e-5
-        xr = x.clone().requires_grad_(True)
-        pr = [p.clone().requires_grad_(True) for p in params]
-        yr = O.jlc(xr, jlc_param_dict(pr), "", groups)
-        assert rel_err(y1, yr) < 2e-5, rel_err(y1, yr)
-        dy = torch.randn_like(y1)
-        grads = torch.autograd.grad(yr, [xr] + pr, dy)
-        got = ops.jlc_bwd_raw(emu, 0, dy, x, z1, o1, h1, st1, params, groups, e)       # data gradient on the 3-pass kernel
-        for i, (g, r) in enumerate(zip(got, grads)):
-            assert close(g, r, rtol=2e-4, atol=2e-5), (i, rel_err(g, r))
-        emu.set_option(11, 0)
-        simt = ops.jlc_bwd_raw(emu, 0, dy, x, z1, o1, h1, st1, params, groups, e)
-        assert rel_err(got[0], simt[0]) < 2e-6 and not torch.equal(got[0], simt[0])
-    finally:
-        emu.set_option(11, 0)
-        emu.set_option(8, 512)
-
-
-@pytest.mark.parametrize("Cout,shape,B", [(64, (5, 6, 8), 2), (128, (3, 9, 7), 1), (16, (4, 4, 5), 1), (160, (2, 5, 6), 1)])
-def test_dense_conv_tensor_core(emu, Cout, shape, B):
-    """conv_dense_tc.cu (candidate, off by default) with its MMAs replaced by the software model on the same shared-memory
-    layout: halo-1 brick as four [position][4 channels] arrays, tap -> shifted descriptor, channel pairs through LBO, dz-slab
-    weight passes, output-channel tiles (160 = two tiles, the second partly empty), TMEM read-back and masked stores --
-    against conv3d on tf32-rounded operands (exact up to summation order) and on the fp32 operands (tf32 tolerance)."""
-    from veloxseg_b200 import ops
+def _conv_ref(x, w, b, kernel, stride, pad, transposed, shuffle):
     import torch.nn.functional as F
+    from veloxseg_b200.nn import PixelShuffle
+    if transposed:
+        y = F.conv_transpose3d(x, w, b, stride=stride)
+    else:
+        y = F.conv3d(x, w, b, stride=stride, padding=pad)
+    return PixelShuffle(shuffle, 3)(y) if shuffle else y
+
+
+@pytest.mark.parametrize("Cout,shape,B,shuffle", [(64, (3, 5, 8), 1, 4), (128, (4, 9, 8), 1, 4), (32, (2, 3, 12), 2, 0), (64, (5, 4, 8), 1, 0)])
+def test_conv3_tensor_core(emu, Cout, shape, B, shuffle):
+    """conv3_tc.cu with the tcgen05 / mbarrier / bulk-copy calls replaced by the descriptor-level software model of
+    vx_tc2.cuh: brick staging, tap -> shifted-descriptor arithmetic, weight images and their ring, TMEM column bookkeeping,
+    fused bias + PixelShuffle store; the im2col weight gradient (inverse shuffle as register transpose, partial tiles, fixed-
+    order fold, bias column) and the plane-wise col2im data gradient -- against conv3d in fp64."""
+    from veloxseg_b200 import ops
     g = torch.Generator().manual_seed(8)
     x = torch.randn(B, 16, *shape, generator=g)
     w = torch.randn(Cout, 16, 3, 3, 3, generator=g) * 0.05
+    b = torch.randn(Cout, generator=g)
+    y = ops.conv_fwd_raw(emu, 0, x, w, b, 3, 1, 1, False, shuffle)
+    x2, w2, b2 = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = _conv_ref(x2, w2, b2, 3, 1, 1, False, shuffle)
+    assert y.shape == yr.shape and rel_err(y, yr) < 5e-6, rel_err(y, yr)
+    dy = torch.randn(y.shape, generator=g)
+    yr.backward(dy.double())
+    dx, dw, db = ops.conv_bwd_raw(emu, 0, dy, x, w, 3, 1, 1, False, shuffle)
+    assert rel_err(dw, w2.grad) < 5e-6, rel_err(dw, w2.grad)
+    assert rel_err(db, b2.grad) < 5e-6, rel_err(db, b2.grad)
+    assert rel_err(dx, x2.grad) < 5e-6, rel_err(dx, x2.grad)
 
-    def tf32(t):
-        return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
-    with pytest.raises(RuntimeError):
-        ops.dense_conv_fwd_raw(emu, 0, x, w)            # off by default: the entry point refuses
-    emu.set_option(12, 1)                               # VX_OPT_DENSE_CONV_TC
-    try:
-        z = ops.dense_conv_fwd_raw(emu, 0, x, w)
-    finally:
-        emu.set_option(12, 0)
-    ref_t = F.conv3d(tf32(x).double(), tf32(w).double(), None, 1, 1).float()
-    ref = F.conv3d(x.double(), w.double(), None, 1, 1).float()
-    assert z.shape == ref.shape
-    assert rel_err(z, ref_t) < 1e-6, rel_err(z, ref_t)
-    assert rel_err(z, ref) < 2e-3, rel_err(z, ref)
-    # bias, and the PixelShuffle(4) store (superpixel.py:15) straight from the accumulators
-    from veloxseg_b200.nn import PixelShuffle
-    bias = torch.randn(Cout, generator=g)
-    emu.set_option(12, 1)
-    try:
-        zb = ops.dense_conv_fwd_raw(emu, 0, x, w, bias)
-        zs = ops.dense_conv_fwd_raw(emu, 0, x, w, bias, 4) if Cout % 64 == 0 else None
-        if Cout % 64:
-            with pytest.raises(RuntimeError):
-                ops.dense_conv_fwd_raw(emu, 0, x, w, bias, 4)
-    finally:
-        emu.set_option(12, 0)
-    assert torch.equal(zb, z + bias.view(1, -1, 1, 1, 1))
-    if zs is not None:
-        assert torch.equal(zs, PixelShuffle(4, 3)(zb))
+
+@pytest.mark.parametrize("Ci,Co,k,s,p,tr,shape,B", [(2, 16, 7, 4, 3, False, (8, 12, 16), 2), (8, 16, 3, 2, 1, False, (6, 4, 8), 1),
+                                                    (16, 8, 2, 2, 0, True, (3, 2, 5), 2), (12, 20, 3, 2, 1, False, (5, 7, 3), 1),
+                                                    (20, 12, 2, 2, 0, True, (1, 3, 3), 1)])
+def test_conv_strided_transposed(emu, Ci, Co, k, s, p, tr, shape, B):
+    """conv_simt.cu: DownConv / UpConv convolutions (strided, scatter and weight-gradient kernels) against torch in fp64."""
+    from veloxseg_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, Ci, *shape, generator=g)
+    w = torch.randn(*((Ci, Co) if tr else (Co, Ci)), k, k, k, generator=g) * 0.1
+    b = torch.randn(Co, generator=g)
+    y = ops.conv_fwd_raw(emu, 0, x, w, b, k, s, p, tr)
+    x2, w2, b2 = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = _conv_ref(x2, w2, b2, k, s, p, tr, 0)
+    assert y.shape == yr.shape and rel_err(y, yr) < 2e-6, rel_err(y, yr)
+    dy = torch.randn(y.shape, generator=g)
+    yr.backward(dy.double())
+    dx, dw, db = ops.conv_bwd_raw(emu, 0, dy, x, w, k, s, p, tr)
+    assert rel_err(dx, x2.grad) < 2e-6 and rel_err(dw, w2.grad) < 2e-6 and rel_err(db, b2.grad) < 2e-6
+    _, dw1, _ = ops.conv_bwd_raw(emu, 0, dy, x, w, k, s, p, tr, need_dx=False, need_db=False)
+    assert rel_err(dw1, w2.grad) < 2e-6

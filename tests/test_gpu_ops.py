@@ -415,3 +415,69 @@ def test_pixel_shuffle_bias(ops, B, C, s, size):
     gz, gb = torch.autograd.grad(yr, [z, bias], dy)
     dz, db = torch.autograd.grad(y, [zg, bg], dy)
     assert torch.equal(dz, gz) and close(db, gb, rtol=1e-4, atol=1e-3)
+
+
+# ----------------------------------------------------------------------------------------------------
+# convolutions of the glue layers: vx_conv_fwd / vx_conv_bwd
+# ----------------------------------------------------------------------------------------------------
+def _conv_ref(x, w, b, kernel, stride, pad, transposed, shuffle):
+    import torch.nn.functional as F
+    from veloxseg_b200.nn import PixelShuffle
+    y = F.conv_transpose3d(x, w, b, stride=stride) if transposed else F.conv3d(x, w, b, stride=stride, padding=pad)
+    return PixelShuffle(shuffle, 3)(y) if shuffle else y
+
+
+@pytest.mark.parametrize("Cout,shape,B,shuffle", [(128, (24, 24, 24), 4, 4), (64, (24, 24, 24), 2, 4), (256, (24, 24, 24), 1, 4),
+                                                  (128, (32, 32, 16), 1, 4), (64, (5, 6, 8), 2, 4), (32, (7, 9, 12), 1, 0),
+                                                  (128, (6, 10, 20), 1, 0)])
+def test_conv3_tensor_core(ops, Cout, shape, B, shuffle):
+    """decoder.out_conv1 / reconstruction out_conv (Decoder.py:73-76,150-153) on the tcgen05 kernels of conv3_tc.cu against
+    conv3d (+ PixelShuffle, superpixel.py:15) in fp64: forward, data gradient, weight and bias gradients at 1e-5 (3xTF32 is
+    fp32-accurate; single-pass TF32 would sit at ~1e-3)."""
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(B, 16, *shape, generator=g).to(DEV)
+    w = (torch.randn(Cout, 16, 3, 3, 3, generator=g) * 0.05).to(DEV)
+    b = torch.randn(Cout, generator=g).to(DEV)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = ops.conv3d(xr, wr, br, 3, 1, 1, shuffle=shuffle)
+    x2, w2, b2 = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = _conv_ref(x2, w2, b2, 3, 1, 1, False, shuffle)
+    assert y.shape == yr.shape and rel_err(y, yr) < 1e-5, rel_err(y, yr)
+    dy = torch.randn(y.shape, generator=g).to(DEV)
+    y.backward(dy)
+    yr.backward(dy.double())
+    torch.cuda.synchronize()
+    assert rel_err(xr.grad, x2.grad) < 1e-5, rel_err(xr.grad, x2.grad)
+    assert rel_err(wr.grad, w2.grad) < 1e-5, rel_err(wr.grad, w2.grad)
+    assert rel_err(br.grad, b2.grad) < 1e-5, rel_err(br.grad, b2.grad)
+    y2 = ops.conv3d(x, w, b, 3, 1, 1, shuffle=shuffle)          # bit-reproducible (fixed fold order everywhere)
+    assert torch.equal(y2, y.detach())
+
+
+@pytest.mark.parametrize("Ci,Co,k,s,p,tr,shape,B", [
+    (2, 16, 7, 4, 3, False, (96, 96, 96), 4), (4, 16, 7, 4, 3, False, (96, 96, 96), 1), (2, 16, 7, 4, 3, False, (128, 128, 64), 1),
+    (16, 32, 3, 2, 1, False, (24, 24, 24), 4), (32, 64, 3, 2, 1, False, (12, 12, 12), 4), (64, 128, 3, 2, 1, False, (6, 6, 6), 4),
+    (64, 128, 3, 2, 1, False, (8, 8, 4), 1),
+    (128, 64, 2, 2, 0, True, (3, 3, 3), 4), (64, 32, 2, 2, 0, True, (6, 6, 6), 4), (32, 16, 2, 2, 0, True, (12, 12, 12), 4),
+    (32, 16, 2, 2, 0, True, (16, 16, 8), 1),
+    (32, 2, 1, 1, 0, False, (12, 12, 12), 4), (128, 4, 1, 1, 0, False, (3, 3, 3), 2), (1, 16, 4, 4, 0, False, (32, 32, 32), 1),
+    (5, 7, 3, 2, 1, False, (5, 7, 9), 2)])
+def test_conv_strided_transposed(ops, Ci, Co, k, s, p, tr, shape, B):
+    """DownConv.down / UpConv.up (conv_blocks.py:10-17,31-35), the 1x1 deep-supervision heads (Decoder.py:155-158) and a
+    PatchEmbed-shaped stem at the shapes of the three configs, against torch in fp64."""
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, Ci, *shape, generator=g).to(DEV)
+    w = (torch.randn(*((Ci, Co) if tr else (Co, Ci)), k, k, k, generator=g) * 0.1).to(DEV)
+    b = torch.randn(Co, generator=g).to(DEV)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = ops.conv3d(xr, wr, br, k, s, p, transposed=tr)
+    x2, w2, b2 = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = _conv_ref(x2, w2, b2, k, s, p, tr, 0)
+    assert y.shape == yr.shape and rel_err(y, yr) < 2e-6, rel_err(y, yr)
+    dy = torch.randn(y.shape, generator=g).to(DEV)
+    y.backward(dy)
+    yr.backward(dy.double())
+    torch.cuda.synchronize()
+    assert rel_err(xr.grad, x2.grad) < 2e-6, rel_err(xr.grad, x2.grad)
+    assert rel_err(wr.grad, w2.grad) < 1e-5, rel_err(wr.grad, w2.grad)
+    assert rel_err(br.grad, b2.grad) < 1e-5, rel_err(br.grad, b2.grad)

@@ -55,8 +55,6 @@ def main():
         lib.set_option(8, int(os.environ["VX_JLC_SMALL_MAX_S"]))
     if "VX_PW_TC_MIN_S" in os.environ:
         lib.set_option(3, int(os.environ["VX_PW_TC_MIN_S"]))
-    if "VX_JLC_CONV_TC" in os.environ:          # candidate tcgen05 JLC conv kernels (jlc_tc.cu), off by default
-        lib.set_option(11, int(os.environ["VX_JLC_CONV_TC"]))
     B, res = args.B, []
     torch.manual_seed(0)
 

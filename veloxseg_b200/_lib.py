@@ -74,9 +74,9 @@ class PixelShuffleDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("C", C.c_int32), ("scale", C.c_int32), ("d", C.c_int32), ("h", C.c_int32), ("w", C.c_int32)]
 
 
-class DenseConvDesc(C.Structure):
+class ConvDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("C_in", C.c_int32), ("C_out", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("shuffle", C.c_int32)]
+                ("kernel", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("transposed", C.c_int32), ("shuffle", C.c_int32)]
 
 
 class AdamwDesc(C.Structure):
@@ -98,7 +98,7 @@ SYMBOLS = [
     "vx_resize_workspace", "vx_resize_trilinear_fwd", "vx_resize_trilinear_bwd",
     "vx_segloss_workspace", "vx_segloss_fwd", "vx_segloss_bwd",
     "vx_patch_embed_fwd", "vx_patch_embed_bwd", "vx_pixel_shuffle_fwd", "vx_pixel_shuffle_bwd", "vx_adamw_step",
-    "vx_dense_conv_fwd",
+    "vx_conv_workspace", "vx_conv_fwd", "vx_conv_bwd",
 ]
 
 _WS_OPS = {"jlc", "mixer", "pwa_block", "gram_fwd", "lnpw", "segloss"}
@@ -133,18 +133,17 @@ class VxLib:
         self.c.vx_profile_timeline.restype = C.c_size_t
         self.c.vx_profile_timeline.argtypes = [C.c_char_p, C.c_size_t]
         for name in ("vx_jlc_workspace", "vx_mixer_workspace", "vx_pwa_workspace", "vx_gram_workspace",
-                     "vx_lnpw_workspace", "vx_resize_workspace", "vx_segloss_workspace"):
+                     "vx_lnpw_workspace", "vx_resize_workspace", "vx_segloss_workspace", "vx_conv_workspace"):
             getattr(self.c, name).restype = C.c_size_t
             getattr(self.c, name).argtypes = [C.c_void_p]
         vp, sz = C.c_void_p, C.c_size_t
         for name in ("vx_jlc_fwd", "vx_jlc_bwd", "vx_mixer_fwd", "vx_mixer_bwd", "vx_pwa_block_fwd", "vx_pwa_block_bwd",
-                     "vx_gram_fwd", "vx_lnpw_fwd", "vx_lnpw_bwd", "vx_resize_trilinear_bwd", "vx_segloss_fwd"):
+                     "vx_gram_fwd", "vx_lnpw_fwd", "vx_lnpw_bwd", "vx_resize_trilinear_bwd", "vx_segloss_fwd", "vx_conv_fwd", "vx_conv_bwd"):
             f = getattr(self.c, name)
             f.restype = C.c_int
             f.argtypes = [vp, vp, vp, vp, sz, vp]
         for name in ("vx_inorm_fwd", "vx_inorm_bwd", "vx_gram_bwd", "vx_sdkt_loss_fwd", "vx_sdkt_loss_bwd",
-                     "vx_resize_trilinear_fwd", "vx_segloss_bwd", "vx_patch_embed_fwd", "vx_patch_embed_bwd", "vx_pixel_shuffle_fwd", "vx_pixel_shuffle_bwd", "vx_adamw_step",
-                     "vx_dense_conv_fwd"):
+                     "vx_resize_trilinear_fwd", "vx_segloss_bwd", "vx_patch_embed_fwd", "vx_patch_embed_bwd", "vx_pixel_shuffle_fwd", "vx_pixel_shuffle_bwd", "vx_adamw_step"):
             f = getattr(self.c, name)
             f.restype = C.c_int
             f.argtypes = [vp, vp, vp, vp]

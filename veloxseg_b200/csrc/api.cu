@@ -201,8 +201,6 @@ extern "C" int vx_set_option(int option, int value) {
   if (option == VX_OPT_WGRAD_TC_MIN_S) { vx::pw_wgrad_tc_set(-1, value); return VX_OK; }
   if (option == VX_OPT_JLC_SMALL_MAX_S) { vx::jlc_set_small_max(value); return VX_OK; }
   if (option == VX_OPT_SIDE_WGRAD) { vx::side_set(value ? 1 : 0); return VX_OK; }
-  if (option == VX_OPT_JLC_CONV_TC) { vx::jlc_tc_set(value); return VX_OK; }
-  if (option == VX_OPT_DENSE_CONV_TC) { vx::dense_conv_tc_set(value); return VX_OK; }
 #ifndef VX_EMU
   if (option == VX_OPT_PW_TENSOR_CORES) { vx::pw_tc_set(value ? 1 : 0); vx::pw_wgrad_tc_set(value ? 1 : 0, -1); return VX_OK; }
   if (option == VX_OPT_PW_SMALL_MAX_S) { vx::pw_set_thresholds(value, -1); return VX_OK; }

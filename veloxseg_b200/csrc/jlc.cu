@@ -873,7 +873,6 @@ struct JlcLayout {
   size_t S, BCS, rows;
   ConvTile tf, tw;
   int small, ntiles_f;      // small-volume conv kernels; stats partials per row of the forward conv
-  int tc; JlcTcArgs tcgeo;  // forward conv on the tensor-core candidate kernel (jlc_tc.cu), off by default
   int nchunk, chunk;
   size_t off_part_z, off_part_o, off_a, off_c;                       // forward scratch
   size_t off_dh, off_dohat, off_dO, off_gz, off_acc, off_acc2;      // backward scratch
@@ -896,12 +895,6 @@ static int jlc_layout(const vx_jlc_desc* d, JlcLayout& L) {
   L.small = jlc_use_small(d->D, d->H, d->W) &&
             sizeof(float) * ((size_t)3 * CG * (d->D + 4) * (d->H + 4) * (d->W + 4) + (size_t)CG * 153 * 4 + 4096) <= 200 * 1024;
   L.ntiles_f = L.small ? small_geo(CG, d->D, d->H, d->W).nsplit : L.tf.ntz * L.tf.nty * L.tf.ntx;
-  L.tcgeo = JlcTcArgs{};
-  L.tc = 0;
-  if (!L.small) {
-    const int nt = jlc_tc_geo(d->B, d->groups, CG, d->D, d->H, d->W, L.tcgeo);
-    if (nt > 0) { L.tc = 1; L.ntiles_f = nt; }
-  }
   const int ntiles = L.ntiles_f;
   size_t off = 0;
   L.off_part_z = off; off += align256(sizeof(float) * 3 * L.rows * ntiles * 2);
@@ -1022,12 +1015,7 @@ extern "C" int vx_jlc_fwd(const vx_jlc_desc* d, const void* const* in, void* con
   const int npos = L.tf.TZ * L.tf.TY * (L.tf.TX / L.tf.VX);
   A.uniform_warps = (npos % 32 == 0) ? 1 : 0;
   prof_bytes(4.0 * sizeof(float) * (double)L.BCS);       // x in, z1 z3 z5 out
-  if (L.tc) {
-    JlcTcArgs T = L.tcgeo;
-    T.x = A.x; T.w1 = A.w1; T.b1 = A.b1; T.w3 = A.w3; T.b3 = A.b3; T.w5 = A.w5; T.b5 = A.b5; T.z = z; T.part = part_z;
-    T.B = d->B; T.C = d->C; T.D = d->D; T.H = d->H; T.W = d->W;
-    VX_TRY(jlc_conv_tc_fwd(T, d->groups, st));
-  } else if (L.small) {
+  if (L.small) {
     if (CG == 4) VX_TRY(launch_conv_small_fwd<4>(A, d->groups, st));
     else if (CG == 8) VX_TRY(launch_conv_small_fwd<8>(A, d->groups, st));
     else VX_TRY(launch_conv_small_fwd<16>(A, d->groups, st));
@@ -1175,12 +1163,7 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
   G.gz = gz; G.dO = dO; G.w1 = w1; G.w3 = w3; G.w5 = w5; G.dx = dx;
   G.B = d->B; G.C = C; G.D = d->D; G.H = d->H; G.W = d->W; G.t = L.tf;
   prof_bytes(5.0 * sizeof(float) * (double)L.BCS);       // gz(3), dO in, dx out
-  if (L.tc) {
-    JlcTcArgs T = L.tcgeo;
-    T.w1 = w1; T.w3 = w3; T.w5 = w5; T.gz = gz; T.dO = dO; T.dx = dx;
-    T.B = d->B; T.C = C; T.D = d->D; T.H = d->H; T.W = d->W;
-    VX_TRY(jlc_conv_tc_dgrad(T, d->groups, st));
-  } else if (L.small) {
+  if (L.small) {
     if (CG == 4) VX_TRY(launch_conv_small_dgrad<4>(G, d->groups, st));
     else if (CG == 8) VX_TRY(launch_conv_small_dgrad<8>(G, d->groups, st));
     else VX_TRY(launch_conv_small_dgrad<16>(G, d->groups, st));

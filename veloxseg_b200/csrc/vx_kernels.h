@@ -183,29 +183,8 @@ struct LnBwdBatch {
 };
 int ln_backward(const LnBwdBatch& b, cudaStream_t stream);
 
-// ---------------------------------------------------------------------------------------------------
-// JLC grouped convolutions on the tensor cores (jlc_tc.cu; candidate path, off unless VX_OPT_JLC_CONV_TC is set)
-// ---------------------------------------------------------------------------------------------------
-struct JlcTcArgs {
-  const float* x; const float* w1; const float* b1; const float* w3; const float* b3; const float* w5; const float* b5;
-  float* z;        // (3, B, C, S): branch k = 1, 3, 5
-  float* part;     // (3, B*C, ntz*nty, 2)
-  const float* gz; const float* dO; float* dx;      // data gradient: (3, B, C, S) branch gradients, (B, C, S) addend, output
-  int B, C, D, H, W;
-  int ZR, TY, ntz, nty, nblk, tmem_cols;
-};
-void jlc_tc_set(int enabled);
-int jlc_tc_geo(int B, int groups, int CG, int D, int H, int W, JlcTcArgs& geo);    // stats partials per row, 0 = not applicable
-int jlc_conv_tc_fwd(const JlcTcArgs& A, int groups, cudaStream_t stream);
-int jlc_conv_tc_dgrad(const JlcTcArgs& A, int groups, cudaStream_t stream);
-
-// Dense 3x3x3 convolution, 16 input channels, on the tensor cores (conv_dense_tc.cu; candidate, off by default)
-struct DenseConvArgs {
-  const float* x; const float* w; const float* bias; float* z;
-  int B, Cout, D, H, W, shuffle;
-  int NT, ZR, TY, ntz, nty, nblk, tmem_cols;      // output-channel tile, brick, M-blocks per CTA
-};
-void dense_conv_tc_set(int enabled);
-int dense_conv_tc_fwd(const vx_dense_conv_desc* d, const float* x, const float* w, const float* bias, float* z, cudaStream_t stream);
+// Convolutions of the glue layers: conv3_tc.cu (dense 3x3x3, tcgen05) and conv_simt.cu (strided / transposed); C ABI vx_conv_*.
+bool conv3_tc_supported(const vx_conv_desc* d);
+size_t conv3_tc_workspace(const vx_conv_desc* d);
 
 }  // namespace vx

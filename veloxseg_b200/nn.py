@@ -14,8 +14,8 @@ Reference files (path:line into the reference repository):
   get_pram_matrix                          model/components/common_function.py:8-14
   PixelShuffle                             model/components/superpixel.py:4-17
   Encoder / Seg_Decoder / RC_Decoder / VeloxSeg   model/Encoder.py, model/Decoder.py, model/VeloxSeg.py
-What stays on library kernels (SURVEY.md section 8f "next" rows): the strided DownConv / ConvTranspose UpConv /
-PatchEmbed stems and the dense 3x3x3 output convs.
+Nothing on the model path is a library (cuDNN / cuBLAS) call: the SURVEY.md section 8f "next" rows -- strided DownConv,
+ConvTranspose UpConv, PatchEmbed stems, dense 3x3x3 output convs, 1x1 heads -- run on libveloxseg kernels too (ops.conv3d).
 """
 from __future__ import annotations
 
@@ -24,7 +24,6 @@ from typing import List, Sequence
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import ops
 
@@ -60,16 +59,17 @@ class DownConv(nn.Module):
         self.norm = nn.InstanceNorm3d(out_channels) if use_norm else nn.Identity()
 
     def forward(self, x, addend=None):
-        if isinstance(self.norm, nn.Identity):
-            y = self.down(x)
-            return y if addend is None else y + addend
         c = self.down
-        if c.bias is not None and x.is_cuda:
-            # the bias cancels inside the affine-less norm: run the library convolution without it (no bias-add kernel, no
-            # bias-gradient reduction over the conv output) and take its gradient from the norm's backward kernel
-            z = F.conv3d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups)
-            return ops.instance_norm_biased(z, c.bias, addend)
-        return ops.instance_norm(c(x), addend)
+        if c.groups != 1:
+            raise NotImplementedError("veloxseg_b200.DownConv: groups = 1 (every VeloxSeg config)")
+        k, s, p = c.kernel_size[0], c.stride[0], c.padding[0]
+        if isinstance(self.norm, nn.Identity):
+            y = ops.conv3d(x, c.weight, c.bias, k, s, p)
+            return y if addend is None else y + addend
+        # the bias cancels inside the affine-less norm: the convolution runs without it (no bias add, no bias-gradient
+        # reduction over the conv output) and its (analytically zero) gradient comes from the norm's backward kernel
+        z = ops.conv3d(x, c.weight, None, k, s, p)
+        return ops.instance_norm_biased(z, c.bias, addend) if c.bias is not None else ops.instance_norm(z, addend)
 
 
 class UpConv(nn.Module):
@@ -83,10 +83,10 @@ class UpConv(nn.Module):
 
     def forward(self, x, addend=None):
         c = self.up
-        if c.bias is not None and x.is_cuda:
-            z = F.conv_transpose3d(x, c.weight, None, c.stride, c.padding, c.output_padding, c.groups, c.dilation)
-            return ops.instance_norm_biased(z, c.bias, addend)
-        return ops.instance_norm(c(x), addend)
+        if c.groups != 1 or c.kernel_size != c.stride or any(c.padding) or any(c.output_padding):
+            raise NotImplementedError("veloxseg_b200.UpConv: kernel = stride, no padding, groups = 1 (every VeloxSeg config)")
+        z = ops.conv3d(x, c.weight, None, c.kernel_size[0], c.stride[0], 0, transposed=True)
+        return ops.instance_norm_biased(z, c.bias, addend) if c.bias is not None else ops.instance_norm(z, addend)
 
 
 class JLC(nn.Module):
@@ -366,18 +366,21 @@ class PixelShuffle(nn.Module):
 
 
 def conv_shuffle(seq: nn.Sequential, x):
-    """`Sequential(Conv3d, PixelShuffle)` (out_conv1 / reconstruction out_conv): on CUDA the library convolution runs without
-    its bias and the bias add + shuffle are one kernel; parameters and state_dict keys are those of the Sequential."""
+    """`Sequential(Conv3d k3 p1, PixelShuffle)` (decoder.out_conv1 / reconstruction out_conv, Decoder.py:73-76,150-153).
+    16 input channels, scale 4 (every VeloxSeg config): ONE tcgen05 kernel -- convolution, bias and shuffle store; the
+    (B, 64 n, D, H, W) intermediate is never written.  Other shapes: convolution kernel + fused bias/shuffle kernel.
+    Parameters and state_dict keys are those of the Sequential."""
     conv, ps = seq[0], seq[1]
-    if x.is_cuda and isinstance(ps, PixelShuffle) and ps.scale <= 4 and x.dtype == torch.float32:
-        if ops.dense_conv_tc_enabled() and ops.dense_conv_qualifies(conv, x):      # candidate kernel, off by default
-            if ps.scale == 4 and conv.out_channels % 64 == 0:                      # conv + bias + shuffle in one kernel
-                return ops.dense_conv3(x, conv.weight, conv.bias, 4)
-            z = ops.dense_conv3(x, conv.weight)
-        else:
-            z = F.conv3d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
-        return ops.pixel_shuffle_bias(z, conv.bias, ps.scale)
-    return seq(x)
+    if conv.kernel_size != (3, 3, 3) or conv.stride != (1, 1, 1) or conv.padding != (1, 1, 1) or conv.groups != 1:
+        raise NotImplementedError("veloxseg_b200.conv_shuffle: Conv3d k3 s1 p1 (Decoder.py:73-76,150-153)")
+    if conv.in_channels == 16 and ps.scale == 4 and conv.out_channels % 64 == 0 and (conv.out_channels <= 128 or conv.out_channels % 128 == 0):
+        return ops.conv3d(x, conv.weight, conv.bias, 3, 1, 1, shuffle=4)
+    return ops.pixel_shuffle_bias(ops.conv3d(x, conv.weight, None, 3, 1, 1), conv.bias, ps.scale)
+
+
+def conv1x1(conv: nn.Conv3d, x):
+    """Deep-supervision heads `out_conv2..4` (Conv3d 1x1 with bias, Decoder.py:155-158)."""
+    return ops.conv3d(x, conv.weight, conv.bias, 1, 1, 0)
 
 
 class ModalMixer(nn.Sequential):
@@ -404,7 +407,8 @@ class PatchEmbed(nn.Module):
         self.proj = nn.Conv3d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
 
     def forward(self, x):
-        return self.proj(x)
+        p = self.proj
+        return ops.conv3d(x, p.weight, p.bias, p.kernel_size[0], p.stride[0], 0)
 
 
 class InitWeights_He:
@@ -479,7 +483,7 @@ class Transformer_Encoder(nn.Module):
             size = [s // 2 for s in size]
 
     def embed(self, xs):
-        if xs.is_cuda and not xs.requires_grad and xs.dtype == torch.float32:
+        if not xs.requires_grad:
             # read each modality's channels where they lie in the input (no slice copies, no layout conversion, and no data
             # gradient: this is the network input)
             out, off = [], 0
@@ -650,7 +654,7 @@ class Seg_Decoder(nn.Module):
                 side.wait_stream(main)                    # `feat` has just been produced on main
                 feat.record_stream(side)
                 with torch.cuda.stream(side):
-                    heads[i] = head_post(conv(feat))
+                    heads[i] = head_post(conv1x1(conv, feat))
 
             head(4, self.out_conv4, enc4)
         up3 = self.layer3(self.layer_up3(enc4, addend=enc3))
@@ -670,7 +674,7 @@ class Seg_Decoder(nn.Module):
                     t.record_stream(main)
                 return [out, heads[2], heads[3], heads[4]], pram
             if self.deep_supervision:
-                outs = [out, self.out_conv2(up2), self.out_conv3(up3), self.out_conv4(enc4)]
+                outs = [out, conv1x1(self.out_conv2, up2), conv1x1(self.out_conv3, up3), conv1x1(self.out_conv4, enc4)]
             else:
                 outs = [out]
             return ([head_post(o) for o in outs] if head_post is not None else outs), pram

@@ -720,71 +720,68 @@ def pixel_shuffle_bias(z: Tensor, bias: Optional[Tensor], scale: int) -> Tensor:
 
 
 # ----------------------------------------------------------------------------------------------------
-# CANDIDATE (off by default, not yet run on hardware): dense 3x3x3 convolution with 16 input channels on the tensor cores
-# (csrc/conv_dense_tc.cu) for decoder.out_conv1 / the reconstruction out_conv.  Forward on the candidate kernel, backward
-# through the library convolution.  Enabled by VX_DENSE_CONV_TC=1 (read once) or dense_conv_tc_enable(True).
+# Convolutions of the glue layers through vx_conv_fwd / vx_conv_bwd:
+#   dense 3x3x3, 16 input channels (+ fused bias / PixelShuffle(4))   Decoder.py:73-76,150-153   tcgen05 3xTF32 (fp32-accurate)
+#   strided k = 2p-1 / transposed k = s = 2                           conv_blocks.py:10-17,31-35  fp32 SIMT
 # ----------------------------------------------------------------------------------------------------
-_dense_conv_tc = None
+def conv_desc(x_shape, c_out: int, kernel: int, stride: int, pad: int, transposed: bool, shuffle: int = 0):
+    from ._lib import ConvDesc
+    B, Ci, D, H, W = x_shape
+    return ConvDesc(B, Ci, int(c_out), D, H, W, int(kernel), int(stride), int(pad), int(bool(transposed)), int(shuffle))
 
 
-def dense_conv_tc_enable(on: bool):
-    global _dense_conv_tc
-    _dense_conv_tc = bool(on)
-    _lib.get_lib().set_option(12, int(_dense_conv_tc))          # VX_OPT_DENSE_CONV_TC
+def conv_out_shape(d) -> tuple:
+    if d.transposed:
+        return (d.B, d.C_out, d.D * d.stride, d.H * d.stride, d.W * d.stride)
+    o = [(n + 2 * d.pad - d.kernel) // d.stride + 1 for n in (d.D, d.H, d.W)]
+    if d.shuffle:
+        return (d.B, d.C_out // d.shuffle ** 3, o[0] * d.shuffle, o[1] * d.shuffle, o[2] * d.shuffle)
+    return (d.B, d.C_out, o[0], o[1], o[2])
 
 
-def dense_conv_tc_enabled() -> bool:
-    global _dense_conv_tc
-    if _dense_conv_tc is None:
-        import os
-        if os.environ.get("VX_DENSE_CONV_TC", "0") == "1":
-            dense_conv_tc_enable(True)
-        else:
-            _dense_conv_tc = False          # the default path never touches the library switch
-    return _dense_conv_tc
-
-
-def dense_conv_qualifies(conv: "torch.nn.Conv3d", x: Tensor) -> bool:
-    return (x.is_cuda and conv.in_channels == 16 and conv.out_channels % 16 == 0 and conv.kernel_size == (3, 3, 3)
-            and conv.stride == (1, 1, 1) and conv.padding == (1, 1, 1) and conv.dilation == (1, 1, 1) and conv.groups == 1
-            and x.shape[-1] + 2 <= 128 and torch.backends.cudnn.allow_tf32)
-
-
-def dense_conv_fwd_raw(lib, stream, x: Tensor, w: Tensor, bias: Optional[Tensor] = None, shuffle: int = 0) -> Tensor:
-    from ._lib import DenseConvDesc
+def conv_fwd_raw(lib, stream, x: Tensor, w: Tensor, bias: Optional[Tensor], kernel: int, stride: int, pad: int, transposed: bool = False,
+                 shuffle: int = 0) -> Tensor:
     x, w = _chk(x, "x"), _chk(w, "w")
-    B, Ci, D, H, W = x.shape
-    Co = w.shape[0]
-    desc = DenseConvDesc(B, Ci, Co, D, H, W, int(shuffle))
-    shape = (B, Co // shuffle ** 3, D * shuffle, H * shuffle, W * shuffle) if shuffle else (B, Co, D, H, W)
-    z = torch.empty(shape, dtype=_f32, device=x.device)
-    lib.call("vx_dense_conv_fwd", desc, [x, w, _chk(bias, "bias") if bias is not None else None], [z], stream)
-    return z
+    c_out = w.shape[1] if transposed else w.shape[0]
+    d = conv_desc(x.shape, c_out, kernel, stride, pad, transposed, shuffle)
+    y = torch.empty(conv_out_shape(d), dtype=_f32, device=x.device)
+    ws = _ws(lib, "conv", d, x)
+    lib.call_ws("vx_conv_fwd", d, [x, w, _chk(bias, "bias") if bias is not None else None], [y], ws, stream)
+    return y
 
 
-class _DenseConv3(torch.autograd.Function):
+def conv_bwd_raw(lib, stream, dy: Tensor, x: Tensor, w: Tensor, kernel: int, stride: int, pad: int, transposed: bool = False,
+                 shuffle: int = 0, need_dx: bool = True, need_db: bool = True):
+    """Returns (dx or None, dw, db or None)."""
+    dy, x, w = _chk(dy, "dy"), _chk(x, "x"), _chk(w, "w")
+    c_out = w.shape[1] if transposed else w.shape[0]
+    d = conv_desc(x.shape, c_out, kernel, stride, pad, transposed, shuffle)
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty_like(w)
+    db = torch.empty((c_out,), dtype=_f32, device=x.device) if need_db else None
+    ws = _ws(lib, "conv", d, x)
+    lib.call_ws("vx_conv_bwd", d, [dy, x, w], [dx, dw, db], ws, stream)
+    return dx, dw, db
+
+
+class _Conv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, bias, shuffle):
+    def forward(ctx, x, w, bias, cfg):
         ctx.save_for_backward(x, w)
-        ctx.shuffle, ctx.has_bias = int(shuffle), bias is not None
-        return dense_conv_fwd_raw(_lib.get_lib(), _stream(x), x, w, bias, int(shuffle))
+        ctx.cfg, ctx.has_bias = cfg, bias is not None
+        return conv_fwd_raw(_lib.get_lib(), _stream(x), x, w, bias, *cfg)
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
-        db = None
-        if ctx.shuffle:         # inverse shuffle of the output gradient (+ the bias gradient in the same pass)
-            dz, db = pixel_shuffle_bwd_raw(_lib.get_lib(), _stream(dy), dy.contiguous(), ctx.shuffle, ctx.has_bias)
-        else:
-            dz = dy.contiguous()
-            if ctx.has_bias:
-                db = dz.sum(dim=(0, 2, 3, 4))
-        dx, dw, _ = torch.ops.aten.convolution_backward(dz, x, w, None, [1, 1, 1], [1, 1, 1], [1, 1, 1], False, [0, 0, 0], 1,
-                                                        [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        dx, dw, db = conv_bwd_raw(_lib.get_lib(), _stream(x), dy.contiguous(), x, w, *ctx.cfg, need_dx=ctx.needs_input_grad[0],
+                                  need_db=ctx.has_bias)
         return dx, dw, db, None
 
 
-def dense_conv3(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, shuffle: int = 0) -> Tensor:
-    """conv3d(x, w, bias, stride 1, padding 1) for 16 input channels, tf32 on the tensor cores (candidate); with
-    shuffle = 4 the result is PixelShuffle(4) of it, stored straight from the accumulators."""
-    return _DenseConv3.apply(x.contiguous(), w.contiguous(), bias, int(shuffle))
+def conv3d(x: Tensor, w: Tensor, bias: Optional[Tensor], kernel: int, stride: int, pad: int, transposed: bool = False,
+           shuffle: int = 0) -> Tensor:
+    """Conv3d / ConvTranspose3d of the VeloxSeg glue layers on libveloxseg kernels (cubic kernel; see vx_conv_desc)."""
+    if not x.is_cuda:
+        raise NotImplementedError("veloxseg::conv3d has no CPU implementation")
+    return _Conv.apply(x.contiguous(), w.contiguous(), bias, (int(kernel), int(stride), int(pad), bool(transposed), int(shuffle)))
