@@ -48,10 +48,14 @@ const char* vx_last_error_string(void);
  *   VX_OPT_WGRAD_TC_MIN_S   voxel count from which weight gradients of the 1x1 contractions run on the tcgen05 kernel
  *                           (default 512; VX_OPT_PW_TENSOR_CORES = 0 switches it off together with the forward kernel).
  *   VX_OPT_SIDE_WGRAD       1 (default): inside a backward op the weight-gradient kernels run on a library-owned side
- *                           stream that forks from and joins back into the caller's stream before the op returns. */
+ *                           stream that forks from and joins back into the caller's stream before the op returns.
+ *   VX_OPT_CONV3_TRACE      0 (default).  1: CTA 0 of the dense-convolution forward kernel records clock64() at its phase
+ *                           boundaries; vx_conv3_trace() copies the 64 stamps out (developer diagnostics, tools/conv3_phases.py). */
 enum { VX_OPT_PW_TENSOR_CORES = 1, VX_OPT_PW_SMALL_MAX_S = 2, VX_OPT_PW_TC_MIN_S = 3, VX_OPT_JLC_TILE_FWD = 4,
-       VX_OPT_JLC_TILE_WGRAD = 5, VX_OPT_JLC_SMALL_MAX_S = 8, VX_OPT_WGRAD_TC_MIN_S = 9, VX_OPT_SIDE_WGRAD = 10 };
+       VX_OPT_JLC_TILE_WGRAD = 5, VX_OPT_JLC_SMALL_MAX_S = 8, VX_OPT_WGRAD_TC_MIN_S = 9, VX_OPT_SIDE_WGRAD = 10,
+       VX_OPT_CONV3_TRACE = 13 };
 int vx_set_option(int option, int value);
+int vx_conv3_trace(long long* out64, int n);
 /* number of kernels this library has enqueued since it was loaded (all threads, all streams) */
 uint64_t vx_launch_count(void);
 /* Per-kernel timing with CUDA events on the launching stream (diagnostics for bench.py; off by default).

@@ -437,7 +437,9 @@ def test_conv3_tensor_core(emu, Cout, shape, B, shuffle):
 
 @pytest.mark.parametrize("Ci,Co,k,s,p,tr,shape,B", [(2, 16, 7, 4, 3, False, (8, 12, 16), 2), (8, 16, 3, 2, 1, False, (6, 4, 8), 1),
                                                     (16, 8, 2, 2, 0, True, (3, 2, 5), 2), (12, 20, 3, 2, 1, False, (5, 7, 3), 1),
-                                                    (20, 12, 2, 2, 0, True, (1, 3, 3), 1)])
+                                                    (20, 12, 2, 2, 0, True, (1, 3, 3), 1), (24, 3, 1, 1, 0, False, (3, 4, 5), 2),
+                                                    (3, 8, 4, 4, 0, False, (8, 8, 12), 1), (40, 24, 3, 2, 1, False, (4, 4, 4), 1),
+                                                    (8, 12, 3, 1, 1, False, (4, 5, 6), 2)])
 def test_conv_strided_transposed(emu, Ci, Co, k, s, p, tr, shape, B):
     """conv_simt.cu: DownConv / UpConv convolutions (strided, scatter and weight-gradient kernels) against torch in fp64."""
     from veloxseg_b200 import ops
@@ -455,3 +457,6 @@ def test_conv_strided_transposed(emu, Ci, Co, k, s, p, tr, shape, B):
     assert rel_err(dx, x2.grad) < 2e-6 and rel_err(dw, w2.grad) < 2e-6 and rel_err(db, b2.grad) < 2e-6
     _, dw1, _ = ops.conv_bwd_raw(emu, 0, dy, x, w, k, s, p, tr, need_dx=False, need_db=False)
     assert rel_err(dw1, w2.grad) < 2e-6
+    if tr:      # without a bias the transposed convolution runs as a channel contraction + depth-to-space pass
+        y0 = ops.conv_fwd_raw(emu, 0, x, w, None, k, s, p, tr)
+        assert rel_err(y0, _conv_ref(x.double(), w.double(), None, k, s, p, tr, 0)) < 2e-6

@@ -461,7 +461,7 @@ def test_conv3_tensor_core(ops, Cout, shape, B, shuffle):
     (128, 64, 2, 2, 0, True, (3, 3, 3), 4), (64, 32, 2, 2, 0, True, (6, 6, 6), 4), (32, 16, 2, 2, 0, True, (12, 12, 12), 4),
     (32, 16, 2, 2, 0, True, (16, 16, 8), 1),
     (32, 2, 1, 1, 0, False, (12, 12, 12), 4), (128, 4, 1, 1, 0, False, (3, 3, 3), 2), (1, 16, 4, 4, 0, False, (32, 32, 32), 1),
-    (5, 7, 3, 2, 1, False, (5, 7, 9), 2)])
+    (5, 7, 3, 2, 1, False, (5, 7, 9), 2), (8, 128, 3, 1, 1, False, (16, 16, 16), 2)])
 def test_conv_strided_transposed(ops, Ci, Co, k, s, p, tr, shape, B):
     """DownConv.down / UpConv.up (conv_blocks.py:10-17,31-35), the 1x1 deep-supervision heads (Decoder.py:155-158) and a
     PatchEmbed-shaped stem at the shapes of the three configs, against torch in fp64."""

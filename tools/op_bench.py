@@ -100,6 +100,22 @@ def main():
         dzs = [torch.randn_like(zz) for zz in zs]
         run(f"pwa_L{li + 1}", lambda: ops.pwa_block_fwd_raw(lib, st, xs, flat, table, index, geo, e, args.drop, args.drop, tr, 5),
             lambda: ops.pwa_block_bwd_raw(lib, st, dzs, xs, flat, table, index, saved, geo, e, args.drop, args.drop, tr, 5))
+    # convolutions of the glue layers (AutoPET-II shapes): (name, C_in, C_out, k, s, p, transposed, shuffle, input extent)
+    CONVS = [("conv3_out1", 16, 128, 3, 1, 1, False, 4, (24, 24, 24)), ("conv3_rc", 16, 64, 3, 1, 1, False, 4, (24, 24, 24)),
+             ("down1", 2, 16, 7, 4, 3, False, 0, (96, 96, 96)), ("down2", 16, 32, 3, 2, 1, False, 0, (24, 24, 24)),
+             ("down3", 32, 64, 3, 2, 1, False, 0, (12, 12, 12)), ("down4", 64, 128, 3, 2, 1, False, 0, (6, 6, 6)),
+             ("up3", 128, 64, 2, 2, 0, True, 0, (3, 3, 3)), ("up2", 64, 32, 2, 2, 0, True, 0, (6, 6, 6)), ("up1", 32, 16, 2, 2, 0, True, 0, (12, 12, 12)),
+             ("head2", 32, 2, 1, 1, 0, False, 0, (12, 12, 12)), ("head3", 64, 2, 1, 1, 0, False, 0, (6, 6, 6)), ("head4", 128, 2, 1, 1, 0, False, 0, (3, 3, 3))]
+    for name, ci, co, k, s_, p_, tr, sh, ext in CONVS:
+        if args.only and args.only not in "conv_" + name:
+            continue
+        xc = torch.randn(B, ci, *ext, device=DEV)
+        wc = torch.randn(*((ci, co) if tr else (co, ci)), k, k, k, device=DEV) * 0.05
+        yc = ops.conv_fwd_raw(lib, st, xc, wc, None, k, s_, p_, tr, sh)
+        dyc = torch.randn_like(yc)
+        need_dx = name != "down1"
+        run("conv_" + name, lambda: ops.conv_fwd_raw(lib, st, xc, wc, None, k, s_, p_, tr, sh),
+            lambda: ops.conv_bwd_raw(lib, st, dyc, xc, wc, k, s_, p_, tr, sh, need_dx=need_dx, need_db=False))
     f = torch.randn(B, 16, 24, 24, 24, device=DEV)
     dG = torch.randn(B, 16, 16, device=DEV)
     run("gram", lambda: ops.gram_fwd_raw(lib, st, f), lambda: ops.gram_bwd_raw(lib, st, dG, f))

@@ -98,7 +98,7 @@ SYMBOLS = [
     "vx_resize_workspace", "vx_resize_trilinear_fwd", "vx_resize_trilinear_bwd",
     "vx_segloss_workspace", "vx_segloss_fwd", "vx_segloss_bwd",
     "vx_patch_embed_fwd", "vx_patch_embed_bwd", "vx_pixel_shuffle_fwd", "vx_pixel_shuffle_bwd", "vx_adamw_step",
-    "vx_conv_workspace", "vx_conv_fwd", "vx_conv_bwd",
+    "vx_conv_workspace", "vx_conv_fwd", "vx_conv_bwd", "vx_conv3_trace",
 ]
 
 _WS_OPS = {"jlc", "mixer", "pwa_block", "gram_fwd", "lnpw", "segloss"}

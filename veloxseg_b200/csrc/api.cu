@@ -200,6 +200,7 @@ extern "C" size_t vx_profile_report(char*, size_t) { return 0; }
 extern "C" int vx_set_option(int option, int value) {
   if (option == VX_OPT_WGRAD_TC_MIN_S) { vx::pw_wgrad_tc_set(-1, value); return VX_OK; }
   if (option == VX_OPT_JLC_SMALL_MAX_S) { vx::jlc_set_small_max(value); return VX_OK; }
+  if (option == VX_OPT_CONV3_TRACE) { vx::conv3_trace_set(value); return VX_OK; }
   if (option == VX_OPT_SIDE_WGRAD) { vx::side_set(value ? 1 : 0); return VX_OK; }
 #ifndef VX_EMU
   if (option == VX_OPT_PW_TENSOR_CORES) { vx::pw_tc_set(value ? 1 : 0); vx::pw_wgrad_tc_set(value ? 1 : 0, -1); return VX_OK; }
@@ -216,3 +217,5 @@ extern "C" int vx_set_option(int option, int value) {
 extern "C" int vx_version(void) { return 101; }
 extern "C" uint64_t vx_launch_count(void) { return __atomic_load_n(&vx::g_launches, __ATOMIC_RELAXED); }
 extern "C" const char* vx_last_error_string(void) { return vx::g_err; }
+
+extern "C" int vx_conv3_trace(long long* out64, int n) { return vx::conv3_trace_read(out64, n); }

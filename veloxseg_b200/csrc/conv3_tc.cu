@@ -34,6 +34,27 @@ constexpr int C3_G0 = 8;             // guard positions in front of a brick (fir
 constexpr int C3_G1 = 136;           // behind it: 1 + the 127 padding rows of the last M-block, rounded up
 constexpr int C3_MAXBLK = 4;
 
+// Phase timestamps of CTA 0 (developer diagnostics, tools/conv3_phases.py): set through vx_set_option(VX_OPT_CONV3_TRACE, 1).
+#ifndef VX_EMU
+__device__ long long g_c3_trace[64];
+static int g_c3_trace_on = 0;
+#define C3_STAMP(on, slot) do { if ((on) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) g_c3_trace[slot] = clock64(); } while (0)
+#else
+#define C3_STAMP(on, slot) do { } while (0)
+#endif
+void conv3_trace_set(int on) {
+#ifndef VX_EMU
+  g_c3_trace_on = on;
+#endif
+}
+int conv3_trace_read(long long* out, int n) {
+#ifndef VX_EMU
+  return cudaMemcpyFromSymbol(out, g_c3_trace, sizeof(long long) * (n < 64 ? n : 64)) == cudaSuccess ? 0 : -1;
+#else
+  return -1;
+#endif
+}
+
 VX_DEV float4 c3_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 VX_DEV void c3_split4(const float4 v, float4& hi, float4& lo) {
   tc::split(v.x, hi.x, lo.x); tc::split(v.y, hi.y, lo.y); tc::split(v.z, hi.z, lo.z); tc::split(v.w, hi.w, lo.w);
@@ -79,7 +100,7 @@ __global__ void conv3_prep_dgrad_kernel(const float* __restrict__ w, float* __re
 struct Conv3FwdArgs {
   const float* x; const float* wimg; const float* bias; float* y;
   int B, Cout, D, H, W, shuffle;
-  int NT, ZR, TY, ntz, nty, nblk, tmem_cols;
+  int NT, ZR, TY, ntz, nty, nblk, tmem_cols, trace;
 };
 
 __global__ void __launch_bounds__(C3_THREADS) conv3_fwd_tc_kernel(const __grid_constant__ Conv3FwdArgs A) {
@@ -103,6 +124,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_fwd_tc_kernel(const __grid_c
   VX_TC_SHARED_SLOT(tmem_slot);
   uint64_t* full = bars; uint64_t* empty = bars + 2; uint64_t* done = bars + 4;
 
+  C3_STAMP(A.trace, 0);
   if (warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)A.tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < 4 + C3_MAXBLK; ++i) tc::mbar_init(&bars[i], 1);
@@ -125,24 +147,44 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_fwd_tc_kernel(const __grid_c
     reinterpret_cast<float4*>(Xhi)[pos] = zero4;
     reinterpret_cast<float4*>(Xlo)[pos] = zero4;
   }
+  C3_STAMP(A.trace, 1);
   const float* xg = A.x + (size_t)b * 16 * S;
-  for (int it = tid; it < 4 * NPOS; it += C3_THREADS) {
-    const int ch = it / NPOS, idx = it % NPOS;
-    const int px = idx % PX, py = (idx / PX) % PY, pz = idx / (PX * PY);
-    const int gz = z0 + pz - 1, gy = y0 + py - 1, gx = px - 1;
-    float4 hi = zero4, lo = zero4;
-    if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      const float* xc = xg + (size_t)(ch * 4) * S + ((size_t)gz * H + gy) * W + gx;
-      c3_split4(make_float4(__ldg(xc), __ldg(xc + S), __ldg(xc + 2 * S), __ldg(xc + 3 * S)), hi, lo);
+  constexpr int FU = 4;                                // items in flight per thread: 16 independent loads before the first use
+#pragma unroll 1
+  for (int base = tid; base < 4 * NPOS; base += FU * C3_THREADS) {
+    float4 v[FU];
+#pragma unroll
+    for (int u = 0; u < FU; ++u) {
+      const int it = base + u * C3_THREADS;
+      v[u] = zero4;
+      if (it < 4 * NPOS) {
+        const int ch = it / NPOS, idx = it % NPOS;
+        const int px = idx % PX, py = (idx / PX) % PY, pz = idx / (PX * PY);
+        const int gz = z0 + pz - 1, gy = y0 + py - 1, gx = px - 1;
+        if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+          const float* xc = xg + (size_t)(ch * 4) * S + ((size_t)gz * H + gy) * W + gx;
+          v[u] = make_float4(__ldg(xc), __ldg(xc + S), __ldg(xc + 2 * S), __ldg(xc + 3 * S));
+        }
+      }
     }
-    reinterpret_cast<float4*>(Xhi)[ch * NALL + C3_G0 + idx] = hi;
-    reinterpret_cast<float4*>(Xlo)[ch * NALL + C3_G0 + idx] = lo;
+#pragma unroll
+    for (int u = 0; u < FU; ++u) {
+      const int it = base + u * C3_THREADS;
+      if (it < 4 * NPOS) {
+        const int ch = it / NPOS, idx = it % NPOS;
+        float4 hi, lo;
+        c3_split4(v[u], hi, lo);
+        reinterpret_cast<float4*>(Xhi)[ch * NALL + C3_G0 + idx] = hi;
+        reinterpret_cast<float4*>(Xlo)[ch * NALL + C3_G0 + idx] = lo;
+      }
+    }
   }
   tc::fence_async_smem();
   tc::fence_before();
   __syncthreads();
   tc::fence_after();
   const uint32_t tmem = tmem_slot;
+  C3_STAMP(A.trace, 2);
 
   if (tid == 0) {
     // ---- MMA issue: 9 weight groups x nblk M-blocks x 6 k-steps x 3 terms
@@ -154,6 +196,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_fwd_tc_kernel(const __grid_c
       const int buf = g & 1;
       tc::mbar_wait(&full[buf], (uint32_t)((g >> 1) & 1));
       tc::fence_after();
+      C3_STAMP(A.trace, 8 + 2 * g);
       const int dzs = g / 3 - 1, dys = g % 3 - 1;
       const uint32_t wg = wb + (uint32_t)buf * (uint32_t)GF * 4u;
 #pragma unroll 1
@@ -174,6 +217,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_fwd_tc_kernel(const __grid_c
         if (g == 8) tc::commit(&done[blk]);
       }
       if (g < 7) tc::commit(&empty[buf]);
+      C3_STAMP(A.trace, 9 + 2 * g);
     }
   } else if (tid == 32) {
     // ---- weight producer: group g reuses the buffer of group g-2 once that group's MMAs have completed
@@ -187,6 +231,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_fwd_tc_kernel(const __grid_c
     }
   }
   __syncwarp();
+  C3_STAMP(A.trace, 3);
 
   // ---- drain: warp = (TMEM lane quadrant, half of the channels); thread = one position of the block
   const int wq = warp & 3, wp = warp >> 2;
@@ -195,6 +240,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_fwd_tc_kernel(const __grid_c
   for (int blk = 0; blk < nblk; ++blk) {
     tc::mbar_wait(&done[blk], 0u);
     tc::fence_after();
+    C3_STAMP(A.trace, 4 + (blk > 0));
     const int p = p_first + blk * 128 + wq * 32 + lane;
     const int px = p % PX, py = (p / PX) % PY, pz = p / (PX * PY);
     const int gz = z0 + pz - 1, gy = y0 + py - 1, gx = px - 1;
@@ -228,6 +274,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_fwd_tc_kernel(const __grid_c
   }
   tc::fence_before();
   __syncthreads();
+  C3_STAMP(A.trace, 6);
   if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)A.tmem_cols);
 }
 
@@ -271,16 +318,21 @@ struct Conv3WgradArgs {
   int nyg, units;                                     // y groups per plane, units = B * D * nyg
 };
 
+// raw x brick: [16 ci][3 planes][RY+2 rows][W+2], the per-channel pitch padded to an odd number of words so that the 16
+// channels of an im2col row group land in 16 different banks
+VX_DEV int c3w_cpitch(int W) { return (3 * (C3W_RY + 2) * (W + 2)) | 1; }
+
 __global__ void __launch_bounds__(C3_THREADS) conv3_wgrad_tc_kernel(const __grid_constant__ Conv3WgradArgs A) {
   const int D = A.D, H = A.H, W = A.W, Cout = A.Cout;
   const int PXW = W + 2, RYP = C3W_RY + 2;
+  const int CP = c3w_cpitch(W);
   const size_t S = (size_t)D * H * W;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nks_row = (W + 7) / 8;
 
   VX_DYN_SMEM(float, sm);
-  float* xs = sm;                                     // raw x brick [16 ci][3 planes][RYP rows][PXW], zero outside the volume
-  const int XS = 16 * 3 * RYP * PXW;
+  float* xs = sm;
+  const int XS = 16 * CP;
   float* stg = xs + ((XS + 3) & ~3);                  // stages: A hi [2][128][4] | A lo | B hi [2][448][4] | B lo
   constexpr int SA = 2 * 128 * 4, SB = 2 * C3W_N * 4, STG = 2 * SA + 2 * SB;
   VX_TC_SHARED_BARS(bars, C3W_STAGES + 1);            // empty[stage], done
@@ -307,23 +359,67 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_wgrad_tc_kernel(const __grid
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc = tc::idesc_tf32(C3W_N / 2, 0, 0);
 
+  // A item of this thread: one 16-byte load per k-step.  shuffle: (q = (cls,i,j), h, p) -> 4 channels of position x0+4h+p;
+  // plain: (co, h) -> 4 positions of channel co.  Loaded one k-step ahead.
+  const bool a_live = A.shuffle == 4 ? tid < (Cout >> 2) * 8 : tid < Cout * 2;
+  auto load_a = [&](int b, int z, int gy, int x0) -> float4 {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!a_live) return v;
+    if (A.shuffle == 4) {
+      const int p = tid & 3, h = (tid >> 2) & 1, q = tid >> 3;
+      const int cls = q >> 4, ii = (q >> 2) & 3, jj = q & 3;
+      const int xx = x0 + 4 * h + p;
+      if (xx < W)
+        v = c3_ld4(A.dy + ((((size_t)b * (A.Ctot >> 6) + (A.co0 >> 6) + cls) * (4 * D) + (4 * z + ii)) * (4 * H) + 4 * gy + jj) * (size_t)(4 * W) + 4 * xx);
+    } else {
+      const int h = tid / Cout, co = tid % Cout;
+      const int xb = x0 + 4 * h;
+      const float* src = A.dy + ((size_t)b * A.Ctot + A.co0 + co) * S + ((size_t)z * H + gy) * W + xb;
+      v.x = xb < W ? __ldg(src) : 0.f; v.y = xb + 1 < W ? __ldg(src + 1) : 0.f;
+      v.z = xb + 2 < W ? __ldg(src + 2) : 0.f; v.w = xb + 3 < W ? __ldg(src + 3) : 0.f;
+    }
+    return v;
+  };
+
   int t = 0;                                          // k-steps issued by this CTA
 #pragma unroll 1
   for (int unit = blockIdx.x; unit < A.units; unit += gridDim.x) {
     const int yg = unit % A.nyg, z = (unit / A.nyg) % D, b = unit / (A.nyg * D);
     const int y0 = yg * C3W_RY;
     const int ny = min(C3W_RY, H - y0);
+    float4 av = load_a(b, z, y0, 0);                  // first k-step of the unit
     __syncthreads();                                  // every thread has finished reading the previous unit's brick
-    for (int i = tid; i < XS; i += C3_THREADS) {
-      const int px = i % PXW, py = (i / PXW) % RYP, pz = (i / (PXW * RYP)) % 3, ci = i / (PXW * RYP * 3);
-      const int gz = z + pz - 1, gy = y0 + py - 1, gx = px - 1;
-      float v = 0.f;
-      if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(A.x + ((size_t)b * 16 + ci) * S + ((size_t)gz * H + gy) * W + gx);
-      xs[i] = v;
+    // ---- raw brick of the unit, zero outside the volume: items = (ci, plane, row), a row's W floats in batches
+    {
+      const int nrow = 16 * 3 * RYP;
+      constexpr int XU = 4;
+#pragma unroll 1
+      for (int rb = tid; rb < nrow * PXW; rb += XU * C3_THREADS) {
+        float v[XU];
+#pragma unroll
+        for (int u = 0; u < XU; ++u) {
+          const int i = rb + u * C3_THREADS;
+          v[u] = 0.f;
+          if (i < nrow * PXW) {
+            const int px = i % PXW, r = i / PXW, py = r % RYP, pz = (r / RYP) % 3, ci = r / (RYP * 3);
+            const int gz = z + pz - 1, gy = y0 + py - 1, gx = px - 1;
+            if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W) v[u] = __ldg(A.x + ((size_t)b * 16 + ci) * S + ((size_t)gz * H + gy) * W + gx);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < XU; ++u) {
+          const int i = rb + u * C3_THREADS;
+          if (i < nrow * PXW) {
+            const int px = i % PXW, r = i / PXW, ci = r / (RYP * 3), rr = r % (RYP * 3);
+            xs[ci * CP + rr * PXW + px] = v[u];
+          }
+        }
+      }
     }
     __syncthreads();
+    const int nks = ny * nks_row;
 #pragma unroll 1
-    for (int ks = 0; ks < ny * nks_row; ++ks, ++t) {
+    for (int ks = 0; ks < nks; ++ks, ++t) {
       const int yl = ks / nks_row, x0 = (ks % nks_row) * 8;
       const int buf = t % C3W_STAGES;
       if (t >= C3W_STAGES) {                          // the MMAs that read this stage have completed
@@ -331,46 +427,29 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_wgrad_tc_kernel(const __grid
         tc::fence_after();
       }
       float* Ahi = stg + (size_t)buf * STG; float* Alo = Ahi + SA; float* Bhi = Alo + SA; float* Blo = Bhi + SB;
-      // ---- A: dz[co][8 positions] (K-major rows of 4 positions)
-      const int gy = y0 + yl;
-      if (A.shuffle == 4) {
-        for (int it = tid; it < (Cout >> 2) * 2; it += C3_THREADS) {
-          const int h = it & 1, q = it >> 1;          // q = (cls, i, j): the four k-channels 4q .. 4q+3
-          const int cls = q >> 4, ii = (q >> 2) & 3, jj = q & 3;
-          const int xb = x0 + 4 * h;
-          const float* src = A.dy + ((((size_t)b * (A.Ctot >> 6) + (A.co0 >> 6) + cls) * (4 * D) + (4 * z + ii)) * (4 * H) + 4 * gy + jj) * (size_t)(4 * W) + 4 * xb;
-          float4 v[4];
-#pragma unroll
-          for (int p = 0; p < 4; ++p) v[p] = (xb + p < W) ? c3_ld4(src + 4 * p) : make_float4(0.f, 0.f, 0.f, 0.f);
+      // ---- A: dz[co][8 positions] (K-major rows of 4 positions), from the value loaded one step ahead
+      if (a_live) {
+        if (A.shuffle == 4) {
+          const int p = tid & 3, h = (tid >> 2) & 1, q = tid >> 3;
           float4 hi, lo;
-          c3_split4(make_float4(v[0].x, v[1].x, v[2].x, v[3].x), hi, lo);
-          reinterpret_cast<float4*>(Ahi)[h * 128 + 4 * q] = hi; reinterpret_cast<float4*>(Alo)[h * 128 + 4 * q] = lo;
-          c3_split4(make_float4(v[0].y, v[1].y, v[2].y, v[3].y), hi, lo);
-          reinterpret_cast<float4*>(Ahi)[h * 128 + 4 * q + 1] = hi; reinterpret_cast<float4*>(Alo)[h * 128 + 4 * q + 1] = lo;
-          c3_split4(make_float4(v[0].z, v[1].z, v[2].z, v[3].z), hi, lo);
-          reinterpret_cast<float4*>(Ahi)[h * 128 + 4 * q + 2] = hi; reinterpret_cast<float4*>(Alo)[h * 128 + 4 * q + 2] = lo;
-          c3_split4(make_float4(v[0].w, v[1].w, v[2].w, v[3].w), hi, lo);
-          reinterpret_cast<float4*>(Ahi)[h * 128 + 4 * q + 3] = hi; reinterpret_cast<float4*>(Alo)[h * 128 + 4 * q + 3] = lo;
-        }
-      } else {
-        for (int it = tid; it < Cout * 2; it += C3_THREADS) {
-          const int h = it / Cout, co = it % Cout;
-          const int xb = x0 + 4 * h;
-          const float* src = A.dy + ((size_t)b * A.Ctot + A.co0 + co) * S + ((size_t)z * H + gy) * W + xb;
-          float4 v;
-          v.x = xb < W ? __ldg(src) : 0.f; v.y = xb + 1 < W ? __ldg(src + 1) : 0.f;
-          v.z = xb + 2 < W ? __ldg(src + 2) : 0.f; v.w = xb + 3 < W ? __ldg(src + 3) : 0.f;
+          c3_split4(av, hi, lo);
+          float* ah = Ahi + (h * 128 + 4 * q) * 4 + p; float* al = Alo + (h * 128 + 4 * q) * 4 + p;
+          ah[0] = hi.x; ah[4] = hi.y; ah[8] = hi.z; ah[12] = hi.w;
+          al[0] = lo.x; al[4] = lo.y; al[8] = lo.z; al[12] = lo.w;
+        } else {
+          const int h = tid / Cout, co = tid % Cout;
           float4 hi, lo;
-          c3_split4(v, hi, lo);
+          c3_split4(av, hi, lo);
           reinterpret_cast<float4*>(Ahi)[h * 128 + co] = hi; reinterpret_cast<float4*>(Alo)[h * 128 + co] = lo;
         }
       }
+      if (ks + 1 < nks) av = load_a(b, z, y0 + (ks + 1) / nks_row, ((ks + 1) % nks_row) * 8);
       // ---- B: im2col rows n = tap*16 + ci of the same 8 positions, from the raw brick
       for (int it = tid; it < 2 * 432; it += C3_THREADS) {
         const int h = it / 432, n = it % 432;
         const int tap = n >> 4, ci = n & 15;
         const int tz = tap / 9, tyy = (tap / 3) % 3, tx = tap % 3;
-        const float* s0 = xs + ((ci * 3 + tz) * RYP + (yl + tyy)) * PXW + x0 + 4 * h + tx;
+        const float* s0 = xs + ci * CP + (tz * RYP + (yl + tyy)) * PXW + x0 + 4 * h + tx;
         const int xb = x0 + 4 * h;                       // ragged last k-step of a row: positions >= W are zero on both operands
         float4 v;
         v.x = xb < W ? s0[0] : 0.f; v.y = xb + 1 < W ? s0[1] : 0.f; v.z = xb + 2 < W ? s0[2] : 0.f; v.w = xb + 3 < W ? s0[3] : 0.f;
@@ -434,20 +513,23 @@ __global__ void conv3_wgrad_reduce_kernel(const float* __restrict__ part, int np
   if (i >= Cout * 433) return;
   const int co = i / 433, n = i % 433;
   const float* p = part + (size_t)co * C3W_N + n;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const size_t st = (size_t)Cout * C3W_N;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
   int k = 0;
-  for (; k + 3 < nparts; k += 4) {
-    s0 += p[(size_t)k * Cout * C3W_N]; s1 += p[(size_t)(k + 1) * Cout * C3W_N];
-    s2 += p[(size_t)(k + 2) * Cout * C3W_N]; s3 += p[(size_t)(k + 3) * Cout * C3W_N];
+  for (; k + 7 < nparts; k += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += p[(size_t)(k + j) * st];
   }
-  for (; k < nparts; ++k) s0 += p[(size_t)k * Cout * C3W_N];
-  const float s = (s0 + s1) + (s2 + s3);
+  for (; k < nparts; ++k) a[0] += p[(size_t)k * st];
+  const float s = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   if (n < 432) dw[((size_t)co * 16 + (n & 15)) * 27 + (n >> 4)] = s;
   else if (db) db[co] = s;
 }
 
 static size_t c3_wgrad_smem(int W) {
-  const int XS = 16 * 3 * (C3W_RY + 2) * (W + 2);
+  const int XS = 16 * ((3 * (C3W_RY + 2) * (W + 2)) | 1);
   return sizeof(float) * (((XS + 3) & ~3) + (size_t)C3W_STAGES * (2 * 2 * 128 * 4 + 2 * 2 * C3W_N * 4)) + 16;
 }
 
@@ -495,6 +577,33 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_dgrad_tc_kernel(const __grid
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc = tc::idesc_tf32(C3D_N, 0, 0);
 
+  // The brick of pass c (dz channels 8c .. 8c+7 at the 3 x PY x PX padded positions, [chunk][position][4 channels]) is loaded
+  // into registers one pass AHEAD: the loads of pass c+1 are in flight while pass c is fenced, synchronised and issued.
+  constexpr int DU = 8;                               // items per thread (2 * NPOS <= 8 * 256, checked by the launcher)
+  float4 v[DU];
+  auto load_pass = [&](int c) {
+#pragma unroll
+    for (int u = 0; u < DU; ++u) {
+      const int it = tid + u * C3_THREADS;
+      v[u] = zero4;
+      if (it < 2 * NPOS) {
+        const int ch = it / NPOS, idx = it % NPOS;
+        const int px = idx % PX, py = (idx / PX) % PY, pz = idx / P2;
+        const int gz = z + pz - 1, gy = y0 + py - 1, gx = px - 1;
+        if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+          const int co = 8 * c + 4 * ch;
+          if (A.shuffle == 4) {
+            const int cls = co >> 6, ii = (co >> 4) & 3, jj = (co >> 2) & 3;
+            v[u] = c3_ld4(A.dy + ((((size_t)b * (Cout >> 6) + cls) * (4 * D) + (4 * gz + ii)) * (4 * H) + 4 * gy + jj) * (size_t)(4 * W) + 4 * gx);
+          } else {
+            const float* s0 = A.dy + ((size_t)b * Cout + co) * S + ((size_t)gz * H + gy) * W + gx;
+            v[u] = make_float4(__ldg(s0), __ldg(s0 + S), __ldg(s0 + 2 * S), __ldg(s0 + 3 * S));
+          }
+        }
+      }
+    }
+  };
+  load_pass(0);
 #pragma unroll 1
   for (int c = 0; c < npass; ++c) {
     const int buf = c & 1;
@@ -506,28 +615,19 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_dgrad_tc_kernel(const __grid
       tc::mbar_expect_tx(&full[buf], (uint32_t)C3D_WF * 4u);
       tc::bulk_g2s(Wb + (size_t)buf * C3D_WF, A.wimg + (size_t)c * C3D_WF, (uint32_t)C3D_WF * 4u, &full[buf]);
     }
-    // ---- brick of pass c: dz channels 8c .. 8c+7 at the 3 x PY x PX padded positions, [chunk][position][4 channels]
     float* Bh = brick + (size_t)buf * BR; float* Bl = Bh + BR / 2;
-    for (int it = tid; it < 2 * NPOS; it += C3_THREADS) {
-      const int ch = it / NPOS, idx = it % NPOS;
-      const int px = idx % PX, py = (idx / PX) % PY, pz = idx / P2;
-      const int gz = z + pz - 1, gy = y0 + py - 1, gx = px - 1;
-      float4 hi = zero4, lo = zero4;
-      if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        float4 v;
-        const int co = 8 * c + 4 * ch;
-        if (A.shuffle == 4) {
-          const int cls = co >> 6, ii = (co >> 4) & 3, jj = (co >> 2) & 3;
-          v = c3_ld4(A.dy + ((((size_t)b * (Cout >> 6) + cls) * (4 * D) + (4 * gz + ii)) * (4 * H) + 4 * gy + jj) * (size_t)(4 * W) + 4 * gx);
-        } else {
-          const float* s0 = A.dy + ((size_t)b * Cout + co) * S + ((size_t)gz * H + gy) * W + gx;
-          v = make_float4(__ldg(s0), __ldg(s0 + S), __ldg(s0 + 2 * S), __ldg(s0 + 3 * S));
-        }
-        c3_split4(v, hi, lo);
+#pragma unroll
+    for (int u = 0; u < DU; ++u) {
+      const int it = tid + u * C3_THREADS;
+      if (it < 2 * NPOS) {
+        const int ch = it / NPOS, idx = it % NPOS;
+        float4 hi, lo;
+        c3_split4(v[u], hi, lo);
+        reinterpret_cast<float4*>(Bh)[ch * NALL + C3_G0 + idx] = hi;
+        reinterpret_cast<float4*>(Bl)[ch * NALL + C3_G0 + idx] = lo;
       }
-      reinterpret_cast<float4*>(Bh)[ch * NALL + C3_G0 + idx] = hi;
-      reinterpret_cast<float4*>(Bl)[ch * NALL + C3_G0 + idx] = lo;
     }
+    if (c + 1 < npass) load_pass(c + 1);
     tc::fence_async_smem();
     tc::fence_before();
     __syncthreads();
@@ -609,7 +709,7 @@ static int c3_dgrad_geo(const vx_conv_desc* d, Conv3DgradArgs& A) {
     const int P2 = (TY + 2) * (d->W + 2);
     const int nblk = cdiv(P2, 128);
     const long long nall = C3_G0 + 3LL * P2 + C3_G1;
-    if (nblk * C3D_N > 512 || nall > 16383 || c3_dgrad_smem(TY, d->W) > 227 * 1024) continue;
+    if (nblk * C3D_N > 512 || nall > 16383 || c3_dgrad_smem(TY, d->W) > 227 * 1024 || 2 * 3 * P2 > 8 * C3_THREADS) continue;
     if ((size_t)nblk * 128 * 9 * 16 > sizeof(float) * 2 * (size_t)2 * 2 * nall * 4) continue;      // exchange tile inside the brick buffers
     const int nty = cdiv(d->H, TY);
     const long long ncta = (long long)nty * d->D * d->B;
@@ -654,6 +754,9 @@ int conv3_tc_fwd(const vx_conv_desc* d, const float* x, const float* w, const fl
   if (((uintptr_t)y & 15) || ((uintptr_t)ws & 15)) { set_error("conv3_fwd: output / workspace not 16-byte aligned"); return VX_ERR_BAD_DESC; }
   Conv3FwdArgs A{};
   A.x = x; A.wimg = (const float*)ws; A.bias = bias; A.y = y; A.B = d->B; A.Cout = d->C_out; A.D = d->D; A.H = d->H; A.W = d->W; A.shuffle = d->shuffle;
+#ifndef VX_EMU
+  A.trace = g_c3_trace_on;
+#endif
   const int ntile = c3_fwd_geo(d, A);
   if (!ntile) { set_error("conv3_fwd: no brick fits"); return VX_ERR_UNSUPPORTED; }
   prof_scope("conv3_fwd B%d Co%d %dx%dx%d", d->B, d->C_out, d->D, d->H, d->W);

@@ -28,7 +28,8 @@
   extern __shared__ __align__(16) unsigned char vx_dsm_[];                                \
   type* name = reinterpret_cast<type*>(vx_dsm_)
 #define VX_SET_SMEM(kern, bytes)                                                          \
-  do { auto _k = kern; static size_t _have = 48 * 1024;   /* one static per call site = per kernel instantiation */ \
+  do { auto _k = kern; static size_t _have = 32 * 1024;   /* one static per call site = per kernel instantiation; the default \
+       48 KB limit counts static shared memory too, so the opt-in starts well below it */ \
        if ((size_t)(bytes) > _have) {                                                     \
          cudaFuncSetAttribute(_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); _have = (bytes); } } while (0)
 #endif

@@ -184,6 +184,8 @@ struct LnBwdBatch {
 int ln_backward(const LnBwdBatch& b, cudaStream_t stream);
 
 // Convolutions of the glue layers: conv3_tc.cu (dense 3x3x3, tcgen05) and conv_simt.cu (strided / transposed); C ABI vx_conv_*.
+void conv3_trace_set(int on);
+int conv3_trace_read(long long* out, int n);
 bool conv3_tc_supported(const vx_conv_desc* d);
 size_t conv3_tc_workspace(const vx_conv_desc* d);
 
