@@ -184,7 +184,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = float(t.item())
     # ---- per-kernel profile of one step (separate pass, not the timed one)
     # every rank runs the same steps (they contain the gradient all-reduces); only rank 0 switches the profiler on
-    roof, table = None, []
+    roof, table, fp32_tflops, hbm, tensor_peak, how = None, [], 0.0, 0.0, 0.0, ""
     nprof = 3
     if rank == 0:
         lib.profile(True)
@@ -195,46 +195,86 @@ def run_ours(args, rank, world, local_rank):
         ts._step_eager(x_d, y_d)       # eager: the event profiler brackets individual launches
         torch.cuda.synchronize()
     if rank == 0:
-        rows = lib.profile_report()          # (scope, kernel, launches, total_ms, algorithmic_bytes)
+        rows = lib.profile_report()          # (scope, kernel, launches, total_ms, algorithmic_bytes, algorithmic_flops)
         tl = lib.profile_timeline()
+        # ---- calibration of the instrument: an event pair around an EMPTY kernel enqueued behind the same kind of spin gate
+        # measures what the profiler adds to every launch (event records + the launch itself); it is subtracted below
+        lib.profile(True)
+        torch.cuda._sleep(50_000_000)
+        st_ = torch.cuda.current_stream().cuda_stream
+        for _ in range(200):
+            lib.c.vx_microbench(1, 0, None, st_)
+        torch.cuda.synchronize()
+        null_rows = [r for r in lib.profile_report() if "null_kernel" in r[1]]
+        ev_overhead_us = 1e3 * sum(r[3] for r in null_rows) / max(1, sum(r[2] for r in null_rows))
         lib.profile(False)
+        # ---- fp32 FMA peak of this device (SURVEY.md section 8d "derive/measure on the box")
+        scratch = torch.zeros(4, device=dev)
+        fma_flops = 2.0 * 8 * 32 * 2000 * 148 * 8 * 256
+        best = 1e9
+        for i in range(6):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            lib.c.vx_microbench(0, 2000, scratch.data_ptr(), st_)
+            b_.record()
+            torch.cuda.synchronize()
+            if i:
+                best = min(best, a_.elapsed_time(b_))
+        fp32_tflops = fma_flops / (best * 1e-3) / 1e12
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "timeline.json"), "w") as f:      # tools/timeline_digest.py reads it
             json.dump(tl, f)
         rows.sort(key=lambda r: -r[3])
         ours_ms = sum(r[3] for r in rows) / nprof
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        n_launch = sum(r[2] for r in rows) / nprof
         with open(os.path.join(ROOT, "gpurun_out", "kernel_table.json"), "w") as f:
-            json.dump({"steps": nprof, "own_kernel_ms_per_step": ours_ms,
-                       "rows": [dict(scope=r[0], kernel=r[1], launches=r[2], ms=r[3], alg_bytes=r[4]) for r in rows]}, f, indent=1)
-        # the dominant kernel = largest summed device time over all its launches in the step
+            json.dump({"steps": nprof, "own_kernel_ms_per_step": ours_ms, "event_overhead_us_per_launch": ev_overhead_us,
+                       "fp32_fma_tflops_measured": fp32_tflops,
+                       "rows": [dict(scope=r[0], kernel=r[1], launches=r[2], ms=r[3], alg_bytes=r[4], alg_flops=r[5]) for r in rows]}, f, indent=1)
+        hbm, tensor_peak, how = peaks()
+        tf32_peak = tensor_peak / 2.0          # dense tf32 = half the measured bf16 rate (nominal 1.1 vs 2.25 PFLOP/s)
+        # the dominant kernel = largest summed device time over all its launches in the step (instrument overhead removed)
         by_kernel = {}
         for r in rows:
-            k = by_kernel.setdefault(r[1].strip("()"), [0, 0.0, 0.0, 0])
-            k[0] += r[2]; k[1] += r[3]; k[2] += r[4]; k[3] += r[2] if r[4] > 0 else 0
+            k = by_kernel.setdefault(r[1].strip("()"), [0, 0.0, 0.0, 0, 0.0])
+            k[0] += r[2]; k[1] += max(r[3] - r[2] * ev_overhead_us * 1e-3, 0.05 * r[3]); k[2] += r[4]; k[3] += r[2] if r[4] > 0 else 0; k[4] += r[5]
         ranked = sorted(by_kernel.items(), key=lambda kv: -kv[1][1])
         table = [dict(kernel=k, launches_per_step=v[0] / nprof, ms_per_step=round(v[1] / nprof, 4),
-                      alg_gbs=round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] > 0 and v[3] == v[0] else None) for k, v in ranked[:12]]
-        hbm, _, how = peaks()
+                      alg_gbs=round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] > 0 and v[3] == v[0] else None,
+                      alg_tflops=round(v[4] / (v[1] * 1e-3) / 1e12, 2) if v[1] > 0 and v[4] > 0 else None) for k, v in ranked[:14]]
         traffic = {}
-        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")      # dram bytes per launch from the committed ncu --set full captures
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")      # dram bytes per launch from the committed ncu --set full captures
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("kernels", {})
+        TENSOR_KERNELS = ("pw_tc_kernel", "pw_wgrad_tc_kernel", "conv3_fwd_tc_kernel", "conv3_wgrad_tc_kernel", "conv3_dgrad_tc_kernel")
         for top_name, top in ranked:
             if not (top[3] == top[0] and top[1] > 0):
                 continue                    # kernels without an algorithmic-byte model (attention: flop-bound) are skipped
-            ach = top[2] / (top[1] * 1e-3) / 1e9
+            sec = top[1] * 1e-3
+            ach_b = top[2] / sec / 1e9
+            is_tc = top_name.split("<")[0] in TENSOR_KERNELS
+            # 3xTF32 issues three tensor-core products per algorithmic one: the pipe peak for ALGORITHMIC flops is tf32 / 3
+            pipe_peak = (tf32_peak / 3.0) if is_tc else fp32_tflops
+            ach_f = top[4] / sec / 1e12
+            t_hbm, t_pipe = top[2] / (hbm * 1e9), top[4] / (pipe_peak * 1e12)
+            binds = "hbm" if t_hbm >= t_pipe else ("tensor" if is_tc else "fp32_fma")
             tr = traffic.get(top_name.split("<")[0])
-            roof = {"bound": "hbm", "kernel": top_name, "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
-                    "frac": round(ach / hbm, 4), "traffic": tr["dram_bytes_per_launch"] if tr else None,
+            roof = {"bound": "hbm", "kernel": top_name, "achieved": round(ach_b, 1), "peak": hbm, "unit": "GB/s",
+                    "frac": round(ach_b / hbm, 4), "traffic": tr["dram_bytes_per_launch"] if tr else None,
                     "traffic_source": tr["source"] if tr else None, "peak_source": how,
+                    "binding_bound": binds, "frac_of_binding_bound": round(max(t_hbm, t_pipe) / sec, 4),
+                    "flops": {"achieved_tflops": round(ach_f, 3), "pipe": "tcgen05 tf32 (3 products per algorithmic product)" if is_tc else "fp32 FMA",
+                              "pipe_peak_tflops": round(pipe_peak, 1), "frac": round(ach_f / pipe_peak, 4)},
                     "launches_per_step": top[0] / nprof, "alg_bytes_per_launch": round(top[2] / top[0]),
                     "kernel_us_avg": round(1e3 * top[1] / top[0], 2),
-                    "share_of_own_kernel_time": round(top[1] / nprof / ours_ms, 4),
-                    "own_kernel_ms_per_step": round(ours_ms, 3),
+                    "event_overhead_us_subtracted": round(ev_overhead_us, 2),
+                    "share_of_own_kernel_time": round(top[1] / sum(v[1] for v in by_kernel.values()), 4),
+                    "own_kernel_ms_per_step": round(sum(v[1] for v in by_kernel.values()) / nprof, 3),
+                    "own_launches_per_step": n_launch,
                     "note": "event-timed launch by launch in an eager step enqueued behind a spin kernel (device back-to-back, "
-                            "no host gaps); kernels of the forked streams overlap in the graph-replayed step, so the summed "
-                            "kernel time exceeds ms_per_step; working sets are L2-resident at 4 patches (DESIGN.md section 3)"}
+                            "no host gaps), minus the profiler's own per-launch overhead measured on an empty kernel; kernels of "
+                            "the forked streams overlap in the graph-replayed step, so the summed kernel time exceeds "
+                            "ms_per_step; working sets are L2-resident at 4 patches (DESIGN.md section 3)"}
             break
     # ---- second headline metric: sliding-window inference (all ranks take part)
     used_graph = ts.use_graph
@@ -268,6 +308,8 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_bytes_per_step": int(xb[0].numel() * xb[0].element_size() + yb[0].numel() * yb[0].element_size()),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "host_enqueue_ms_per_step": round(enqueue_ms, 2), "clocks": clk.summary(), "roofline": roof, "loss": last_loss, "top_kernels": table,
+        "peaks": {"hbm_gbs": hbm, "bf16_tflops": tensor_peak, "source": how, "fp32_fma_tflops_measured": round(fp32_tflops, 1),
+                  "fp32_fma_how": "vx_microbench: 8 independent FMA chains per thread, 148 x 8 CTAs of 256 threads, best of 5"},
     }
     if infer is not None:
         line["infer"] = infer

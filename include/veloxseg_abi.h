@@ -49,18 +49,26 @@ const char* vx_last_error_string(void);
  *                           (default 512; VX_OPT_PW_TENSOR_CORES = 0 switches it off together with the forward kernel).
  *   VX_OPT_SIDE_WGRAD       1 (default): inside a backward op the weight-gradient kernels run on a library-owned side
  *                           stream that forks from and joins back into the caller's stream before the op returns.
+ *   VX_OPT_PRECISION        0 (default): fp32 mode -- every kernel fp32-accurate (tensor-core contractions 3xTF32);
+ *                           1: bf16 mode (north_star's second precision mode) -- the tensor-core contractions (1x1 convs of
+ *                           levels 1-2 and their weight gradients, dense 3x3x3 convs forward / data / weight gradient) round
+ *                           both operands to bfloat16 (RNE), issue ONE product with fp32 accumulation and round the stored
+ *                           activation to bfloat16; statistics, norms, softmax, losses, optimiser stay fp32.  Storage stays fp32.
  *   VX_OPT_CONV3_TRACE      0 (default).  1: CTA 0 of the dense-convolution forward kernel records clock64() at its phase
  *                           boundaries; vx_conv3_trace() copies the 64 stamps out (developer diagnostics, tools/conv3_phases.py). */
 enum { VX_OPT_PW_TENSOR_CORES = 1, VX_OPT_PW_SMALL_MAX_S = 2, VX_OPT_PW_TC_MIN_S = 3, VX_OPT_JLC_TILE_FWD = 4,
        VX_OPT_JLC_TILE_WGRAD = 5, VX_OPT_JLC_SMALL_MAX_S = 8, VX_OPT_WGRAD_TC_MIN_S = 9, VX_OPT_SIDE_WGRAD = 10,
-       VX_OPT_CONV3_TRACE = 13 };
+       VX_OPT_CONV3_TRACE = 13, VX_OPT_PRECISION = 14 };
 int vx_set_option(int option, int value);
 int vx_conv3_trace(long long* out64, int n);
+/* Measurement helpers (bench.py): kind 0 = fp32 FMA throughput probe (2 * 8 * 32 * iters * 148 * 8 * 256 flops per launch,
+ * `scratch` = one device float), kind 1 = one empty kernel (calibrates the per-launch overhead of the event profiler). */
+int vx_microbench(int kind, int iters, void* scratch, vx_stream_t stream);
 /* number of kernels this library has enqueued since it was loaded (all threads, all streams) */
 uint64_t vx_launch_count(void);
 /* Per-kernel timing with CUDA events on the launching stream (diagnostics for bench.py; off by default).
  * vx_profile_enable(1) brackets every subsequent launch with an event pair; vx_profile_report() synchronises those
- * events and writes one line per (scope, kernel): "scope|kernel|launches|total_ms|algorithmic_bytes\n"; returns the bytes needed. */
+ * events and writes one line per (scope, kernel): "scope|kernel|launches|total_ms|algorithmic_bytes|algorithmic_flops\n"; returns the bytes needed. */
 int vx_profile_enable(int on);
 void vx_profile_reset(void);
 size_t vx_profile_report(char* buf, size_t cap);

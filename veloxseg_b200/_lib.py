@@ -98,7 +98,7 @@ SYMBOLS = [
     "vx_resize_workspace", "vx_resize_trilinear_fwd", "vx_resize_trilinear_bwd",
     "vx_segloss_workspace", "vx_segloss_fwd", "vx_segloss_bwd",
     "vx_patch_embed_fwd", "vx_patch_embed_bwd", "vx_pixel_shuffle_fwd", "vx_pixel_shuffle_bwd", "vx_adamw_step",
-    "vx_conv_workspace", "vx_conv_fwd", "vx_conv_bwd", "vx_conv3_trace",
+    "vx_conv_workspace", "vx_conv_fwd", "vx_conv_bwd", "vx_conv3_trace", "vx_microbench",
 ]
 
 _WS_OPS = {"jlc", "mixer", "pwa_block", "gram_fwd", "lnpw", "segloss"}
@@ -147,6 +147,10 @@ class VxLib:
             f = getattr(self.c, name)
             f.restype = C.c_int
             f.argtypes = [vp, vp, vp, vp]
+        self.c.vx_microbench.restype = C.c_int
+        self.c.vx_microbench.argtypes = [C.c_int, C.c_int, vp, vp]
+        self.c.vx_conv3_trace.restype = C.c_int
+        self.c.vx_conv3_trace.argtypes = [vp, C.c_int]
         self.c.vx_pwa_saved_layout.restype = C.c_int
         self.c.vx_pwa_saved_layout.argtypes = [vp, vp]
         self.c.vx_pwa_gather.restype = C.c_int
@@ -157,14 +161,14 @@ class VxLib:
         self.c.vx_profile_enable(int(on))
 
     def profile_report(self):
-        """[(scope, kernel, launches, total_ms, algorithmic_bytes)] since the last profile(True)."""
+        """[(scope, kernel, launches, total_ms, algorithmic_bytes, algorithmic_flops)] since the last profile(True)."""
         n = self.c.vx_profile_report(None, 0)
         buf = C.create_string_buffer(int(n) + 16)
         self.c.vx_profile_report(buf, len(buf))
         rows = []
         for line in buf.value.decode().splitlines():
-            scope, kern, cnt, ms, nbytes = line.rsplit("|", 4)
-            rows.append((scope, kern, int(cnt), float(ms), float(nbytes)))
+            scope, kern, cnt, ms, nbytes, nflops = line.rsplit("|", 5)
+            rows.append((scope, kern, int(cnt), float(ms), float(nbytes), float(nflops)))
         return rows
 
     def profile_timeline(self):

@@ -15,6 +15,10 @@ static thread_local char g_err[512] = "";
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
+static int g_precision = 0;
+int precision_mode() { return g_precision; }
+void precision_set(int m) { g_precision = m ? 1 : 0; }
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -89,8 +93,8 @@ void side_join(cudaStream_t main) {
   c->forked = false;
 }
 
-struct ProfRec { std::string key; cudaEvent_t a, b; double bytes; };
-static thread_local double g_next_bytes = 0.0;
+struct ProfRec { std::string key; cudaEvent_t a, b; double bytes, flops; };
+static thread_local double g_next_bytes = 0.0, g_next_flops = 0.0;
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 static int g_prof_on = 0;
@@ -112,13 +116,16 @@ int prof_begin(const char* kernel, cudaStream_t st) {
   r.a = pool_get();
   r.b = pool_get();
   r.bytes = g_next_bytes;
+  r.flops = g_next_flops;
   g_next_bytes = 0.0;
+  g_next_flops = 0.0;
   cudaEventRecord(r.a, st);
   g_prof.push_back(r);
   return (int)g_prof.size() - 1;
 }
 
 void prof_bytes(double b) { g_next_bytes = b; }
+void prof_flops(double f) { g_next_flops = f; }
 
 void prof_end(int slot, cudaStream_t st) {
   if (slot < 0) return;
@@ -146,19 +153,19 @@ extern "C" void vx_profile_reset(void) {
 }
 extern "C" size_t vx_profile_report(char* buf, size_t cap) {
   std::lock_guard<std::mutex> lk(vx::g_prof_mu);
-  struct Agg { int n = 0; double ms = 0.0, bytes = 0.0; };
+  struct Agg { int n = 0; double ms = 0.0, bytes = 0.0, flops = 0.0; };
   std::map<std::string, Agg> agg;
   for (auto& r : vx::g_prof) {
     cudaEventSynchronize(r.b);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
     auto& e = agg[r.key];
-    e.n += 1; e.ms += ms; e.bytes += r.bytes;
+    e.n += 1; e.ms += ms; e.bytes += r.bytes; e.flops += r.flops;
   }
   std::string out;
-  char line[96];
+  char line[128];
   for (auto& kv : agg) {
-    snprintf(line, sizeof(line), "|%d|%.6f|%.0f\n", kv.second.n, kv.second.ms, kv.second.bytes);
+    snprintf(line, sizeof(line), "|%d|%.6f|%.0f|%.0f\n", kv.second.n, kv.second.ms, kv.second.bytes, kv.second.flops);
     out += kv.first + line;
   }
   if (buf && cap > 0) { const size_t n = out.size() < cap - 1 ? out.size() : cap - 1; memcpy(buf, out.data(), n); buf[n] = 0; }
@@ -188,6 +195,7 @@ extern "C" size_t vx_profile_timeline(char* buf, size_t cap) {
 extern "C" size_t vx_profile_timeline(char*, size_t) { return 0; }
 namespace vx {
 void prof_bytes(double) {}
+void prof_flops(double) {}
 cudaStream_t side_fork(cudaStream_t main) { return main; }
 void side_join(cudaStream_t) {}
 void side_set(int) {}
@@ -201,6 +209,7 @@ extern "C" int vx_set_option(int option, int value) {
   if (option == VX_OPT_WGRAD_TC_MIN_S) { vx::pw_wgrad_tc_set(-1, value); return VX_OK; }
   if (option == VX_OPT_JLC_SMALL_MAX_S) { vx::jlc_set_small_max(value); return VX_OK; }
   if (option == VX_OPT_CONV3_TRACE) { vx::conv3_trace_set(value); return VX_OK; }
+  if (option == VX_OPT_PRECISION) { vx::precision_set(value); return VX_OK; }
   if (option == VX_OPT_SIDE_WGRAD) { vx::side_set(value ? 1 : 0); return VX_OK; }
 #ifndef VX_EMU
   if (option == VX_OPT_PW_TENSOR_CORES) { vx::pw_tc_set(value ? 1 : 0); vx::pw_wgrad_tc_set(value ? 1 : 0, -1); return VX_OK; }

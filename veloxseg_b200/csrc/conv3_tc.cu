@@ -59,13 +59,18 @@ VX_DEV float4 c3_ld4(const float* p) { return *reinterpret_cast<const float4*>(p
 VX_DEV void c3_split4(const float4 v, float4& hi, float4& lo) {
   tc::split(v.x, hi.x, lo.x); tc::split(v.y, hi.y, lo.y); tc::split(v.z, hi.z, lo.z); tc::split(v.w, hi.w, lo.w);
 }
+// prec 0: fp32-accurate hi / lo split; prec 1 (bf16 numerics): hi = bf16(v), lo unused
+VX_DEV void c3_split4p(int prec, const float4 v, float4& hi, float4& lo) {
+  if (prec) { hi = make_float4(bf16_round(v.x), bf16_round(v.y), bf16_round(v.z), bf16_round(v.w)); lo = make_float4(0.f, 0.f, 0.f, 0.f); }
+  else c3_split4(v, hi, lo);
+}
 
 // =====================================================================================================================
 // weight images (one launch per forward / backward: the weights change every optimiser step)
 // =====================================================================================================================
 // forward image  [co tile][group g = dz*3+dy][hi|lo][step s = dx*2 + ci octet][NT*8]: element (n, k) of a step at
 //   (n/8)*64 + (k/4)*32 + (n%8)*4 + k%4  (K-major B operand: LBO 128 B between the k halves, SBO 256 B between 8-row groups)
-__global__ void conv3_prep_fwd_kernel(const float* __restrict__ w, float* __restrict__ img, int Cout, int NT, int ntile) {
+__global__ void conv3_prep_fwd_kernel(const float* __restrict__ w, float* __restrict__ img, int Cout, int NT, int ntile, int prec) {
   const int per_tile = 9 * 6 * NT * 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ntile * per_tile) return;
@@ -73,21 +78,25 @@ __global__ void conv3_prep_fwd_kernel(const float* __restrict__ w, float* __rest
   const int g = r / (6 * NT * 8), r2 = r % (6 * NT * 8), s = r2 / (NT * 8), e = r2 % (NT * 8), n = e >> 3, k = e & 7;
   const int co = t * NT + n, ci = (s & 1) * 8 + k, tap = g * 3 + (s >> 1);
   float hi = 0.f, lo = 0.f;
-  if (co < Cout) tc::split(__ldg(w + ((size_t)co * 16 + ci) * 27 + tap), hi, lo);
+  if (co < Cout) {
+    const float wv = __ldg(w + ((size_t)co * 16 + ci) * 27 + tap);
+    if (prec) hi = bf16_round(wv); else tc::split(wv, hi, lo);
+  }
   const size_t base = ((size_t)(t * 9 + g) * 2) * (6 * NT * 8);
   const int o = s * NT * 8 + (n >> 3) * 64 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
   img[base + o] = hi;
   img[base + 6 * NT * 8 + o] = lo;
 }
 // data-gradient image  [pass c = co octet][tz][hi|lo][144 x 8]: row n = (ty*3+tx)*16 + ci, k = co - 8c
-__global__ void conv3_prep_dgrad_kernel(const float* __restrict__ w, float* __restrict__ img, int Cout) {
+__global__ void conv3_prep_dgrad_kernel(const float* __restrict__ w, float* __restrict__ img, int Cout, int prec) {
   const int npass = Cout / 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npass * 3 * 144 * 8) return;
   const int c = i / (3 * 144 * 8), r = i % (3 * 144 * 8), tz = r / (144 * 8), e = r % (144 * 8), n = e >> 3, k = e & 7;
   const int tyx = n >> 4, ci = n & 15, co = c * 8 + k;
-  float hi, lo;
-  tc::split(__ldg(w + ((size_t)co * 16 + ci) * 27 + tz * 9 + tyx), hi, lo);
+  float hi, lo = 0.f;
+  const float wv = __ldg(w + ((size_t)co * 16 + ci) * 27 + tz * 9 + tyx);
+  if (prec) hi = bf16_round(wv); else tc::split(wv, hi, lo);
   const size_t base = ((size_t)(c * 3 + tz) * 2) * (144 * 8);
   const int o = (n >> 3) * 64 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
   img[base + o] = hi;
@@ -100,7 +109,7 @@ __global__ void conv3_prep_dgrad_kernel(const float* __restrict__ w, float* __re
 struct Conv3FwdArgs {
   const float* x; const float* wimg; const float* bias; float* y;
   int B, Cout, D, H, W, shuffle;
-  int NT, ZR, TY, ntz, nty, nblk, tmem_cols, trace;
+  int NT, ZR, TY, ntz, nty, nblk, tmem_cols, trace, prec;
 };
 
 __global__ void __launch_bounds__(C3_THREADS) conv3_fwd_tc_kernel(const __grid_constant__ Conv3FwdArgs A) {
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_fwd_tc_kernel(const __grid_c
       if (it < 4 * NPOS) {
         const int ch = it / NPOS, idx = it % NPOS;
         float4 hi, lo;
-        c3_split4(v[u], hi, lo);
+        c3_split4p(A.prec, v[u], hi, lo);
         reinterpret_cast<float4*>(Xhi)[ch * NALL + C3_G0 + idx] = hi;
         reinterpret_cast<float4*>(Xlo)[ch * NALL + C3_G0 + idx] = lo;
       }
@@ -210,9 +219,13 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_fwd_tc_kernel(const __grid_c
           const uint64_t bh = tc::desc(wg + (uint32_t)s * (uint32_t)NT * 32u, 128u, 256u);
           const uint64_t bl = tc::desc(wg + (uint32_t)(6 + s) * (uint32_t)NT * 32u, 128u, 256u);
           const uint32_t d = tmem + (uint32_t)(blk * NT);
-          tc::mma_tf32(d, al, bh, idesc, (g > 0 || s > 0) ? 1u : 0u);
-          tc::mma_tf32(d, ah, bl, idesc, 1u);
-          tc::mma_tf32(d, ah, bh, idesc, 1u);
+          if (A.prec) {                                // bf16 numerics: one product
+            tc::mma_tf32(d, ah, bh, idesc, (g > 0 || s > 0) ? 1u : 0u);
+          } else {
+            tc::mma_tf32(d, al, bh, idesc, (g > 0 || s > 0) ? 1u : 0u);
+            tc::mma_tf32(d, ah, bl, idesc, 1u);
+            tc::mma_tf32(d, ah, bh, idesc, 1u);
+          }
         }
         if (g == 8) tc::commit(&done[blk]);
       }
@@ -255,6 +268,10 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_fwd_tc_kernel(const __grid_c
         if (A.bias) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) r[j] += __ldg(A.bias + co0 + j);
+        }
+        if (A.prec) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = bf16_round(r[j]);
         }
         if (A.shuffle == 4) {
           // PixelShuffle(4): channel ((cls*4 + i)*4 + j)*4 + k -> voxel (4gz + i, 4gy + j, 4gx + k) of class cls.  The 16
@@ -314,7 +331,7 @@ constexpr int C3W_RY = 8;            // rows of one unit
 
 struct Conv3WgradArgs {
   const float* dy; const float* x; float* part;       // part [grid][Cout][448]
-  int B, Cout, Ctot, co0, D, H, W, shuffle;           // this launch: output channels co0 .. co0 + Cout (<= 128) of Ctot
+  int B, Cout, Ctot, co0, D, H, W, shuffle, prec;     // this launch: output channels co0 .. co0 + Cout (<= 128) of Ctot
   int nyg, units;                                     // y groups per plane, units = B * D * nyg
 };
 
@@ -432,14 +449,14 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_wgrad_tc_kernel(const __grid
         if (A.shuffle == 4) {
           const int p = tid & 3, h = (tid >> 2) & 1, q = tid >> 3;
           float4 hi, lo;
-          c3_split4(av, hi, lo);
+          c3_split4p(A.prec, av, hi, lo);
           float* ah = Ahi + (h * 128 + 4 * q) * 4 + p; float* al = Alo + (h * 128 + 4 * q) * 4 + p;
           ah[0] = hi.x; ah[4] = hi.y; ah[8] = hi.z; ah[12] = hi.w;
           al[0] = lo.x; al[4] = lo.y; al[8] = lo.z; al[12] = lo.w;
         } else {
           const int h = tid / Cout, co = tid % Cout;
           float4 hi, lo;
-          c3_split4(av, hi, lo);
+          c3_split4p(A.prec, av, hi, lo);
           reinterpret_cast<float4*>(Ahi)[h * 128 + co] = hi; reinterpret_cast<float4*>(Alo)[h * 128 + co] = lo;
         }
       }
@@ -454,7 +471,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_wgrad_tc_kernel(const __grid
         float4 v;
         v.x = xb < W ? s0[0] : 0.f; v.y = xb + 1 < W ? s0[1] : 0.f; v.z = xb + 2 < W ? s0[2] : 0.f; v.w = xb + 3 < W ? s0[3] : 0.f;
         float4 hi, lo;
-        c3_split4(v, hi, lo);
+        c3_split4p(A.prec, v, hi, lo);
         reinterpret_cast<float4*>(Bhi)[h * C3W_N + n] = hi; reinterpret_cast<float4*>(Blo)[h * C3W_N + n] = lo;
       }
       tc::fence_async_smem();
@@ -469,9 +486,13 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_wgrad_tc_kernel(const __grid
           const uint32_t bo = (uint32_t)half * (C3W_N / 2) * 16u;
           const uint64_t dbh = tc::desc(bh + bo, (uint32_t)C3W_N * 16u, 128u), dbl = tc::desc(bl + bo, (uint32_t)C3W_N * 16u, 128u);
           const uint32_t d = tmem + (uint32_t)half * (C3W_N / 2);
-          tc::mma_tf32(d, dal, dbh, idesc, t > 0 ? 1u : 0u);
-          tc::mma_tf32(d, dah, dbl, idesc, 1u);
-          tc::mma_tf32(d, dah, dbh, idesc, 1u);
+          if (A.prec) {
+            tc::mma_tf32(d, dah, dbh, idesc, t > 0 ? 1u : 0u);
+          } else {
+            tc::mma_tf32(d, dal, dbh, idesc, t > 0 ? 1u : 0u);
+            tc::mma_tf32(d, dah, dbl, idesc, 1u);
+            tc::mma_tf32(d, dah, dbh, idesc, 1u);
+          }
         }
         tc::commit(&bars[buf]);
       }
@@ -538,7 +559,7 @@ static size_t c3_wgrad_smem(int W) {
 // =====================================================================================================================
 struct Conv3DgradArgs {
   const float* dy; const float* wimg; float* dx;
-  int B, Cout, D, H, W, shuffle;
+  int B, Cout, D, H, W, shuffle, prec;
   int TY, nty, nblk;
 };
 constexpr int C3D_N = 144;
@@ -622,7 +643,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_dgrad_tc_kernel(const __grid
       if (it < 2 * NPOS) {
         const int ch = it / NPOS, idx = it % NPOS;
         float4 hi, lo;
-        c3_split4(v[u], hi, lo);
+        c3_split4p(A.prec, v[u], hi, lo);
         reinterpret_cast<float4*>(Bh)[ch * NALL + C3_G0 + idx] = hi;
         reinterpret_cast<float4*>(Bl)[ch * NALL + C3_G0 + idx] = lo;
       }
@@ -647,9 +668,13 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_dgrad_tc_kernel(const __grid
           const uint64_t bh = tc::desc(wb + (uint32_t)(tz * 2) * (C3D_N * 32u), 128u, 256u);
           const uint64_t bl = tc::desc(wb + (uint32_t)(tz * 2 + 1) * (C3D_N * 32u), 128u, 256u);
           const uint32_t d = tmem + (uint32_t)(blk * C3D_N);
-          tc::mma_tf32(d, al, bh, idesc, (c > 0 || tz > 0) ? 1u : 0u);
-          tc::mma_tf32(d, ah, bl, idesc, 1u);
-          tc::mma_tf32(d, ah, bh, idesc, 1u);
+          if (A.prec) {
+            tc::mma_tf32(d, ah, bh, idesc, (c > 0 || tz > 0) ? 1u : 0u);
+          } else {
+            tc::mma_tf32(d, al, bh, idesc, (c > 0 || tz > 0) ? 1u : 0u);
+            tc::mma_tf32(d, ah, bl, idesc, 1u);
+            tc::mma_tf32(d, ah, bh, idesc, 1u);
+          }
         }
       }
       tc::commit(c == npass - 1 ? done : &empty[buf]);
@@ -689,6 +714,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_dgrad_tc_kernel(const __grid
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
       float* dst = A.dx + ((size_t)b * 16 + qd * 4) * S + ((size_t)z * H + gy) * W + xx;
+      if (A.prec) acc = make_float4(bf16_round(acc.x), bf16_round(acc.y), bf16_round(acc.z), bf16_round(acc.w));
       dst[0] = acc.x; dst[S] = acc.y; dst[2 * S] = acc.z; dst[3 * S] = acc.w;
     }
     __syncthreads();
@@ -757,13 +783,15 @@ int conv3_tc_fwd(const vx_conv_desc* d, const float* x, const float* w, const fl
 #ifndef VX_EMU
   A.trace = g_c3_trace_on;
 #endif
+  A.prec = precision_mode();
   const int ntile = c3_fwd_geo(d, A);
   if (!ntile) { set_error("conv3_fwd: no brick fits"); return VX_ERR_UNSUPPORTED; }
   prof_scope("conv3_fwd B%d Co%d %dx%dx%d", d->B, d->C_out, d->D, d->H, d->W);
   const int nimg = ntile * 9 * 6 * A.NT * 8;
-  VX_LAUNCH(conv3_prep_fwd_kernel, dim3(cdiv(nimg, 256)), dim3(256), 0, st, w, (float*)ws, d->C_out, A.NT, ntile);
+  VX_LAUNCH(conv3_prep_fwd_kernel, dim3(cdiv(nimg, 256)), dim3(256), 0, st, w, (float*)ws, d->C_out, A.NT, ntile, A.prec);
   const size_t smem = c3_fwd_smem(A.NT, A.ZR, A.TY, A.W);
   prof_bytes(4.0 * d->B * (16.0 + d->C_out) * d->D * d->H * d->W + 4.0 * 27 * 16 * d->C_out);
+  prof_flops(2.0 * 27 * 16 * (double)d->C_out * d->B * d->D * d->H * d->W);
   VX_SET_SMEM(conv3_fwd_tc_kernel, smem);
   VX_LAUNCH(conv3_fwd_tc_kernel, dim3(A.ntz * A.nty, ntile, A.B), dim3(C3_THREADS), smem, st, A);
   return check_launch("conv3_fwd_tc_kernel");
@@ -787,11 +815,13 @@ int conv3_tc_bwd(const vx_conv_desc* d, const float* dy, const float* x, const f
       const int co0 = t * 128, cn = d->C_out - co0 < 128 ? d->C_out - co0 : 128;
       A.dy = dy; A.x = x; A.part = (float*)(wsb + c3_img_dgrad_bytes(d));       // the tiles run back to back on one stream: one partial buffer
       A.B = d->B; A.Cout = cn; A.Ctot = d->C_out; A.co0 = co0; A.D = d->D; A.H = d->H; A.W = d->W; A.shuffle = d->shuffle;
+      A.prec = precision_mode();
       A.nyg = cdiv(d->H, C3W_RY); A.units = d->B * d->D * A.nyg;
       const int grid = c3_wgrad_grid(d);
       const size_t smem = c3_wgrad_smem(d->W);
       if (smem > 227 * 1024) { set_error("conv3_bwd: row too wide for the weight-gradient brick"); return VX_ERR_UNSUPPORTED; }
       prof_bytes(act_bytes);
+      prof_flops(2.0 * 27 * 16 * (double)cn * d->B * d->D * d->H * d->W);
       VX_SET_SMEM(conv3_wgrad_tc_kernel, smem);
       VX_LAUNCH(conv3_wgrad_tc_kernel, dim3(grid), dim3(C3_THREADS), smem, sw, A);
       VX_LAUNCH(conv3_wgrad_reduce_kernel, dim3(cdiv(cn * 433, 256)), dim3(256), 0, sw, A.part, grid, cn, dw + (size_t)co0 * 16 * 27, db ? db + co0 : nullptr);
@@ -802,11 +832,13 @@ int conv3_tc_bwd(const vx_conv_desc* d, const float* dy, const float* x, const f
   if (dx) {
     Conv3DgradArgs A{};
     A.dy = dy; A.wimg = (const float*)wsb; A.dx = dx; A.B = d->B; A.Cout = d->C_out; A.D = d->D; A.H = d->H; A.W = d->W; A.shuffle = d->shuffle;
+    A.prec = precision_mode();
     if (!c3_dgrad_geo(d, A)) { set_error("conv3_bwd: no data-gradient brick fits"); return VX_ERR_UNSUPPORTED; }
     const int nimg = (d->C_out / 8) * 3 * 144 * 8;
-    VX_LAUNCH(conv3_prep_dgrad_kernel, dim3(cdiv(nimg, 256)), dim3(256), 0, st, w, (float*)wsb, d->C_out);
+    VX_LAUNCH(conv3_prep_dgrad_kernel, dim3(cdiv(nimg, 256)), dim3(256), 0, st, w, (float*)wsb, d->C_out, A.prec);
     const size_t smem = c3_dgrad_smem(A.TY, A.W);
     prof_bytes(act_bytes);
+    prof_flops(2.0 * 27 * 16 * (double)d->C_out * d->B * d->D * d->H * d->W);
     VX_SET_SMEM(conv3_dgrad_tc_kernel, smem);
     VX_LAUNCH(conv3_dgrad_tc_kernel, dim3(A.nty * d->D, d->B), dim3(C3_THREADS), smem, st, A);
     const int rc = check_launch("conv3_dgrad_tc_kernel");

@@ -317,6 +317,7 @@ int conv_strided(const ConvGeo& G, const float* X, const float* Wt, const float*
   if (smem < fold) smem = fold;
   const dim3 grid(cdiv(nvox, 32 * vw), cdiv(G.Co, ct)), block(32, ks, vw);
   prof_bytes(4.0 * ((double)G.B * G.Ci * G.D * G.H * G.W + (double)nvox * G.Co + (double)G.Co * R * G.k));
+  prof_flops(2.0 * (double)nvox * G.Co * R * G.k);
   if (G.k == 7) launch_strided<7>(ct, grid, block, smem, st, G, X, Wt, bias, Y, rchunk);
   else if (G.k == 3) launch_strided<3>(ct, grid, block, smem, st, G, X, Wt, bias, Y, rchunk);
   else if (G.k == 2) launch_strided<2>(ct, grid, block, smem, st, G, X, Wt, bias, Y, rchunk);
@@ -340,6 +341,7 @@ int conv_scatter(const ConvGeo& G, const float* X, const float* Wt, const float*
   if (smem < fold) smem = fold;
   const dim3 grid(cdiv(nfine, 32 * vw), cdiv(G.Ci, ct)), block(32, ks, vw);
   prof_bytes(4.0 * ((double)nfine * G.Ci + (double)G.B * G.Co * G.d * G.h * G.w + (double)G.Co * G.Ci * k3));
+  prof_flops(2.0 * (double)G.B * G.d * G.h * G.w * G.Co * G.Ci * k3);
   if (ct == 16) { VX_SET_SMEM(conv_scatter_kernel<16>, smem); VX_LAUNCH(conv_scatter_kernel<16>, grid, block, smem, st, G, X, Wt, bias, Y, ochunk); }
   else if (ct == 8) { VX_SET_SMEM(conv_scatter_kernel<8>, smem); VX_LAUNCH(conv_scatter_kernel<8>, grid, block, smem, st, G, X, Wt, bias, Y, ochunk); }
   else { VX_SET_SMEM(conv_scatter_kernel<4>, smem); VX_LAUNCH(conv_scatter_kernel<4>, grid, block, smem, st, G, X, Wt, bias, Y, ochunk); }
@@ -361,6 +363,7 @@ int conv_wgrad(const ConvGeo& G, const float* Gc, const float* F, float* dW, flo
   const int gz = cdiv(nvox, vchunk);
   const size_t smem = sizeof(float) * (size_t)vchunk * CW_CT + sizeof(int) * 4 * (size_t)vchunk;
   prof_bytes(4.0 * ((double)G.B * G.Ci * G.D * G.H * G.W + (double)nvox * G.Co + (double)G.Co * npair));
+  prof_flops(2.0 * (double)nvox * G.Co * npair);
   VX_LAUNCH(conv_wgrad_kernel, dim3(gx, gy, gz), dim3(128), smem, st, G, Gc, F, dW, db, (int)vchunk);
   return check_launch("conv_wgrad_kernel");
 }

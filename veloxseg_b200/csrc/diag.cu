@@ -1,0 +1,46 @@
+// Measurement helpers of libveloxseg_sm100 (no model arithmetic): the fp32 FMA peak of the device the library runs on, and an
+// empty kernel for calibrating the per-launch overhead of the event profiler.  bench.py reports both next to MEASURED_PEAKS.json.
+#include "vx_kernels.h"
+
+namespace vx {
+
+// 8 independent FMA chains per thread, `iters` x 32 FMAs each chain step: 2 * 8 * 32 * iters flops per thread
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float* __restrict__ out) {
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 1.0f + 1e-3f * (float)(threadIdx.x + j);
+  const float m = 1.0000001f, c = 1e-7f;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], m, c);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += a[j];
+  if (s == 123.456f) out[0] = s;                       // never true: keeps the chains alive
+}
+
+__global__ void null_kernel(int) {}
+
+}  // namespace vx
+
+using namespace vx;
+
+// kind 0: fp32 FMA throughput probe -- launches 148 x 8 CTAs of 256 threads, `iters` outer iterations; flops = 2 * 8 * 32 *
+//         iters * 148 * 8 * 256.  kind 1: one empty kernel through the same launch / profiler path as every other kernel.
+extern "C" int vx_microbench(int kind, int iters, void* scratch, vx_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (kind == 0) {
+    if (!scratch || iters <= 0) { set_error("microbench: scratch / iters"); return VX_ERR_BAD_DESC; }
+    prof_scope("microbench fma");
+    VX_LAUNCH(fma_peak_kernel, dim3(kSMs * 8), dim3(256), 0, st, iters, (float*)scratch);
+    return check_launch("fma_peak_kernel");
+  }
+  prof_scope("microbench null");
+  VX_LAUNCH(null_kernel, dim3(1), dim3(32), 0, st, 0);
+  return check_launch("null_kernel");
+}

@@ -1015,6 +1015,7 @@ extern "C" int vx_jlc_fwd(const vx_jlc_desc* d, const void* const* in, void* con
   const int npos = L.tf.TZ * L.tf.TY * (L.tf.TX / L.tf.VX);
   A.uniform_warps = (npos % 32 == 0) ? 1 : 0;
   prof_bytes(4.0 * sizeof(float) * (double)L.BCS);       // x in, z1 z3 z5 out
+  prof_flops(2.0 * 153.0 * CG * (double)L.BCS);
   if (L.small) {
     if (CG == 4) VX_TRY(launch_conv_small_fwd<4>(A, d->groups, st));
     else if (CG == 8) VX_TRY(launch_conv_small_fwd<8>(A, d->groups, st));
@@ -1155,6 +1156,7 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
   Wg.x = x; Wg.gz = gz; Wg.dw1 = dw1; Wg.db1 = db1; Wg.dw3 = dw3; Wg.db3 = db3; Wg.dw5 = dw5; Wg.db5 = db5;
   Wg.B = d->B; Wg.C = C; Wg.D = d->D; Wg.H = d->H; Wg.W = d->W; Wg.t = L.tw;
   prof_bytes(4.0 * sizeof(float) * (double)L.BCS);       // x, gz(3) in (weight gradients are KBs)
+  prof_flops(2.0 * 153.0 * (C / d->groups) * (double)L.BCS);
   if (CG == 4) VX_TRY(launch_conv_wgrad<4>(Wg, d->groups, st_w));
   else if (CG == 8) VX_TRY(launch_conv_wgrad<8>(Wg, d->groups, st_w));
   else VX_TRY(launch_conv_wgrad<16>(Wg, d->groups, st_w));
@@ -1163,6 +1165,7 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
   G.gz = gz; G.dO = dO; G.w1 = w1; G.w3 = w3; G.w5 = w5; G.dx = dx;
   G.B = d->B; G.C = C; G.D = d->D; G.H = d->H; G.W = d->W; G.t = L.tf;
   prof_bytes(5.0 * sizeof(float) * (double)L.BCS);       // gz(3), dO in, dx out
+  prof_flops(2.0 * 153.0 * (C / d->groups) * (double)L.BCS);
   if (L.small) {
     if (CG == 4) VX_TRY(launch_conv_small_dgrad<4>(G, d->groups, st));
     else if (CG == 8) VX_TRY(launch_conv_small_dgrad<8>(G, d->groups, st));

@@ -335,7 +335,7 @@ void pw_set_thresholds(int small_max_s, int tc_min_s) {
 
 int pw_forward(const PwBatch& batch, cudaStream_t stream) {
   int maxCo = 0;
-  double bytes = 0.0;
+  double bytes = 0.0, flops = 0.0;
   for (int i = 0; i < batch.nprob; ++i) {
     const PwProblem& P = batch.p[i];
     maxCo = P.Co > maxCo ? P.Co : maxCo;
@@ -348,6 +348,7 @@ int pw_forward(const PwBatch& batch, cudaStream_t stream) {
     // algorithmic bytes: X in, Y out, epilogue tensors in, weights
     bytes += 4.0 * batch.B * batch.S * (P.Ci + P.Co * (1.0 + (P.res ? 1 : 0) + (P.res2 ? 1 : 0) + (P.mulgrad ? 1 : 0))) +
              4.0 * P.Ci * P.Co;
+    flops += 2.0 * batch.B * batch.S * P.Ci * P.Co;
   }
   if (batch.nprob <= 0 || batch.B <= 0 || batch.S <= 0) return VX_OK;
 #ifndef VX_EMU
@@ -358,6 +359,7 @@ int pw_forward(const PwBatch& batch, cudaStream_t stream) {
   for (int i = 0; i < batch.nprob; ++i) multi_src = multi_src || batch.p[i].nsrc > 1;
   if (batch.S >= g_tc_min_s && batch.S >= g_small_max_s && !(multi_src && batch.S < 4096)) {
     prof_bytes(bytes);
+    prof_flops(flops);
     const int rc = pw_tc_forward(batch, stream);
     if (rc <= 0) return rc;
   }
@@ -365,6 +367,7 @@ int pw_forward(const PwBatch& batch, cudaStream_t stream) {
   PwBatch launch = batch;
   launch.seed_dev = get_seed_dev();
   prof_bytes(bytes);
+  prof_flops(flops);
   if (batch.S < g_small_max_s) {
     int maxCi = 0;
     for (int i = 0; i < batch.nprob; ++i) maxCi = batch.p[i].Ci > maxCi ? batch.p[i].Ci : maxCi;
@@ -548,10 +551,13 @@ int pw_wgrad(const WgBatch& batch, cudaStream_t main_stream) {
   WgBatch launch = batch;
   launch.seed_dev = get_seed_dev();
   {
-    double bytes = 0.0;
-    for (int i = 0; i < batch.nprob; ++i)
+    double bytes = 0.0, flops = 0.0;
+    for (int i = 0; i < batch.nprob; ++i) {
       bytes += 4.0 * batch.B * batch.S * (batch.p[i].Ci + batch.p[i].Co) + 4.0 * batch.p[i].Ci * batch.p[i].Co;
+      flops += 2.0 * batch.B * batch.S * batch.p[i].Ci * batch.p[i].Co;
+    }
     prof_bytes(bytes);
+    prof_flops(flops);
   }
   VX_LAUNCH(pw_wgrad_kernel, grid, dim3(WG_THREADS), smem, stream, launch, TV, nK);
   return check_launch("pw_wgrad_kernel");

@@ -147,10 +147,14 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
           for (int j = 0; j < 4; ++j) {
             const int e = (j + r) & 3;
             const float xe = e == 0 ? xx[0] : e == 1 ? xx[1] : e == 2 ? xx[2] : xx[3];
-            float h, l;
-            split_tf32(xe, h, l);
-            A_hi[base + e * 4] = h;
-            A_lo[base + e * 4] = l;
+            if (batch.prec) {
+              A_hi[base + e * 4] = bf16_round(xe);
+            } else {
+              float h, l;
+              split_tf32(xe, h, l);
+              A_hi[base + e * 4] = h;
+              A_lo[base + e * 4] = l;
+            }
           }
         }
       }
@@ -186,7 +190,9 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
         const float ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
         float h[4], l[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split_tf32(ww[i], h[i], l[i]);
+        for (int i = 0; i < 4; ++i) {
+          if (batch.prec) { h[i] = bf16_round(ww[i]); l[i] = 0.f; } else split_tf32(ww[i], h[i], l[i]);
+        }
         if (!P.transposed) {        // (n = row, k = q4..q4+3): four consecutive floats of one core-matrix row
           const int n = row[u], kk = q4[u];
           const int off = (kk >> 3) * (Npad * 8) + (n >> 3) * 64 + ((kk & 7) >> 2) * 32 + (n & 7) * 4;
@@ -217,9 +223,13 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
       const uint32_t ao = (uint32_t)g8 * (TC_M * 8 * 4), bo = (uint32_t)g8 * (uint32_t)(Npad * 8 * 4);
       const uint64_t dah = umma_desc(a_hi + ao, a_lbo, a_sbo), dal = umma_desc(a_lo + ao, a_lbo, a_sbo);
       const uint64_t dbh = umma_desc(b_hi + bo, b_lbo, b_sbo), dbl = umma_desc(b_lo + bo, b_lbo, b_sbo);
-      umma_tf32(tmem, dal, dbh, idesc, g8 > 0 ? 1u : 0u);
-      umma_tf32(tmem, dah, dbl, idesc, 1u);
-      umma_tf32(tmem, dah, dbh, idesc, 1u);
+      if (batch.prec) {                               // bf16 numerics: operands are exact in tf32, one product
+        umma_tf32(tmem, dah, dbh, idesc, g8 > 0 ? 1u : 0u);
+      } else {
+        umma_tf32(tmem, dal, dbh, idesc, g8 > 0 ? 1u : 0u);
+        umma_tf32(tmem, dah, dbl, idesc, 1u);
+        umma_tf32(tmem, dah, dbh, idesc, 1u);
+      }
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar))
                  : "memory");
@@ -328,6 +338,10 @@ __global__ void __launch_bounds__(TC_THREADS) pw_tc_kernel(const __grid_constant
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = fmaf(P.res_scale, r1[j], y[j]) + r2[j];      // r1 / r2 are zero without their stream
+      if (batch.prec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = bf16_round(y[j]);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) if (j < nlive) obase[(size_t)j * S] = y[j];
     }
@@ -376,6 +390,7 @@ int pw_tc_forward(const PwBatch& batch, cudaStream_t stream) {
   VX_SET_SMEM(pw_tc_kernel, smem);
   PwBatch launch = batch;
   launch.seed_dev = get_seed_dev();
+  launch.prec = precision_mode();
   dim3 grid(cdiv(S, TC_M), 1, batch.nprob * batch.B);
   VX_LAUNCH(pw_tc_kernel, grid, dim3(TC_THREADS), smem, stream, launch, shp);
   return check_launch("pw_tc_kernel");

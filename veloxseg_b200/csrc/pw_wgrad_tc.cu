@@ -158,9 +158,11 @@ __global__ void __launch_bounds__(WT_THREADS) pw_wgrad_tc_kernel(const __grid_co
       }
       float h[4], l[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) split_tf32(x[e], h[e], l[e]);
+      for (int e = 0; e < 4; ++e) {
+        if (batch.prec) { h[e] = bf16_round(x[e]); l[e] = 0.f; } else split_tf32(x[e], h[e], l[e]);
+      }
       *reinterpret_cast<float4*>((isB ? B_hi : A_hi) + off) = make_float4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<float4*>((isB ? B_lo : A_lo) + off) = make_float4(l[0], l[1], l[2], l[3]);
+      if (!batch.prec) *reinterpret_cast<float4*>((isB ? B_lo : A_lo) + off) = make_float4(l[0], l[1], l[2], l[3]);
     }
   };
 
@@ -196,9 +198,13 @@ __global__ void __launch_bounds__(WT_THREADS) pw_wgrad_tc_kernel(const __grid_co
         const uint32_t ao = (uint32_t)(g8 * BLKA * 4), bo = (uint32_t)(g8 * BLKB * 4);
         const uint64_t dah = umma_desc(a_hi + ao, 128u, 256u), dal = umma_desc(a_lo + ao, 128u, 256u);
         const uint64_t dbh = umma_desc(b_hi + bo, 128u, 256u), dbl = umma_desc(b_lo + bo, 128u, 256u);
-        umma_tf32(tmem, dal, dbh, idesc, (it > 0 || g8 > 0) ? 1u : 0u);
-        umma_tf32(tmem, dah, dbl, idesc, 1u);
-        umma_tf32(tmem, dah, dbh, idesc, 1u);
+        if (batch.prec) {
+          umma_tf32(tmem, dah, dbh, idesc, (it > 0 || g8 > 0) ? 1u : 0u);
+        } else {
+          umma_tf32(tmem, dal, dbh, idesc, (it > 0 || g8 > 0) ? 1u : 0u);
+          umma_tf32(tmem, dah, dbl, idesc, 1u);
+          umma_tf32(tmem, dah, dbh, idesc, 1u);
+        }
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar))
                    : "memory");
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(WT_THREADS) pw_wgrad_tc_kernel(const __grid_co
             for (int k = 0; k < 8; ++k) {
               const int ao = g8 * BLKA + (m >> 3) * 64 + (k >> 2) * 32 + (m & 7) * 4 + (k & 3);
               const int bo = g8 * BLKB + (n >> 3) * 64 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
-              acc += A_lo[ao] * B_hi[bo] + A_hi[ao] * B_lo[bo] + A_hi[ao] * B_hi[bo];
+              acc += batch.prec ? A_hi[ao] * B_hi[bo] : A_lo[ao] * B_hi[bo] + A_hi[ao] * B_lo[bo] + A_hi[ao] * B_hi[bo];
             }
           g_emu_tmem[m][n] = acc;
         }
@@ -285,7 +291,7 @@ int pw_wgrad_tc(const WgBatch& batch, cudaStream_t stream) {
   const int S = batch.S;
   if (S < g_wt_min_s || (S & 3)) return 1;
   int maxCo = 0, maxNB = 0;
-  double bytes = 0.0;
+  double bytes = 0.0, flops = 0.0;
   for (int i = 0; i < batch.nprob; ++i) {
     const WgProblem& P = batch.p[i];
     int cs = 0;
@@ -300,6 +306,7 @@ int pw_wgrad_tc(const WgBatch& batch, cudaStream_t stream) {
     const int nb = P.Ci + (P.db ? 1 : 0);
     maxNB = nb > maxNB ? nb : maxNB;
     bytes += 4.0 * batch.B * S * (P.Ci + P.Co) + 4.0 * P.Ci * P.Co;
+    flops += 2.0 * batch.B * S * P.Ci * P.Co;
   }
   if (maxCo > 128) return 1;
   WgTcShape shp{};
@@ -324,7 +331,9 @@ int pw_wgrad_tc(const WgBatch& batch, cudaStream_t stream) {
   VX_SET_SMEM(pw_wgrad_tc_kernel, smem);
   WgBatch launch = batch;
   launch.seed_dev = get_seed_dev();
+  launch.prec = precision_mode();
   prof_bytes(bytes);
+  prof_flops(flops);
   VX_LAUNCH(pw_wgrad_tc_kernel, dim3(nsplit, batch.nprob), dim3(WT_THREADS), smem, stream, launch, shp);
   return check_launch("pw_wgrad_tc_kernel");
 }

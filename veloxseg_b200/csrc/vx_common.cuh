@@ -62,8 +62,22 @@ int prof_begin(const char* kernel, cudaStream_t st);   // -1 when profiling is o
 void prof_end(int slot, cudaStream_t st);
 #endif
 void prof_bytes(double bytes);                         // algorithmic bytes of the NEXT launch (profiler only)
+void prof_flops(double flops);                         // algorithmic flops of the NEXT launch (profiler only)
 void prof_scope(const char* fmt, ...);                 // names the op whose kernels follow (thread-local)
 int check_launch(const char* what);   // cudaGetLastError -> vx_status
+
+// round-to-nearest-even to bfloat16, kept in an fp32 container (bf16 numerics mode; finite inputs)
+VX_DEV float bf16_round(float x) {
+#ifdef VX_EMU
+  uint32_t u; memcpy(&u, &x, 4); u += 0x7FFFu + ((u >> 16) & 1u); u &= 0xFFFF0000u; float r; memcpy(&r, &u, 4); return r;
+#else
+  uint32_t u = __float_as_uint(x);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return __uint_as_float(u & 0xFFFF0000u);
+#endif
+}
+// 0: fp32-accurate (3xTF32 on the tensor cores), 1: bf16 numerics (tensor-core operands and outputs rounded to bf16, one product)
+int precision_mode();
 
 VX_DEV float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 // d/dx GELU(x) = Phi(x) + x * phi(x)

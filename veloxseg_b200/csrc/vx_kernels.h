@@ -30,7 +30,7 @@ struct PwProblem {
   const float* res2;                                         // out += res2[b,co,s]
 };
 
-struct PwBatch { PwProblem p[VX_MAX_MODAL]; int nprob; int B; int S; const unsigned long long* seed_dev; };
+struct PwBatch { PwProblem p[VX_MAX_MODAL]; int nprob; int B; int S; const unsigned long long* seed_dev; int prec; };
 
 int pw_forward(const PwBatch& batch, cudaStream_t stream);
 
@@ -115,7 +115,7 @@ struct WgProblem {
   float* dW; int ld;                                          // accumulated with atomics: caller zeroes
   float* db;                                                  // may be null
 };
-struct WgBatch { WgProblem p[VX_MAX_MODAL * 3]; int nprob; int B; int S; const unsigned long long* seed_dev; };
+struct WgBatch { WgProblem p[VX_MAX_MODAL * 3]; int nprob; int B; int S; const unsigned long long* seed_dev; int prec; };
 
 // Device pointer whose value the dropout kernels add to their seeds (graph-replay-safe masks).  Thread-local: set by the
 // op entry point, picked up by pw_forward / pw_wgrad.

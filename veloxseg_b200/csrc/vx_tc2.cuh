@@ -1,15 +1,16 @@
 // Portable wrappers around the sm_100a tensor-core / async-copy instructions used by the implicit-GEMM convolution kernels
-// (conv3_tc.cu): tcgen05.mma kind::tf32 (cta_group::1, M = 128, SWIZZLE_NONE operands, K-major or MN-major), tensor memory
-// alloc / ld, mbarriers, tcgen05.commit and cp.async.bulk (global -> shared, mbarrier-tracked).
+// (conv3_tc.cu): tcgen05.mma kind::tf32 (cta_group::1, M = 128, SWIZZLE_NONE K-major operands), tensor memory alloc / ld,
+// mbarriers, tcgen05.commit and cp.async.bulk (global -> shared, mbarrier-tracked).
 //
 // Under VX_EMU (tools/emu, developer tooling only) the same calls run a DESCRIPTOR-LEVEL software model: an MMA decodes
 // its shared-memory descriptors (start, LBO, SBO, major bits) and reads the emulated shared memory exactly where the
 // hardware would, so operand layouts, shifted start addresses and TMEM column bookkeeping are checked by the CPU tests with
-// the kernel source unchanged.  Layout rules modelled (CUTLASS cute/atom/mma_traits_sm100.hpp "INTERLEAVE", confirmed on
-// a B200 with tools/bringup/tc_probe2.cu):
-//   K-major  operand, element (r, k):  start + (r/8)*SBO + (r%8)*16 + (k/4)*LBO + (k%4)*4      (k < 8 per MMA)
-//   MN-major operand, element (r, k):  start + (r/4)*SBO + (r%4)*4  + (k%8)*16                 (LBO: next 8 k, unused)
+// the kernel source unchanged.  Layout rule modelled (CUTLASS cute/atom/mma_traits_sm100.hpp "INTERLEAVE", confirmed on a
+// B200 with tools/bringup/tc_probe2.cu incl. start addresses that are only 16-byte aligned):
+//   K-major operand, element (r, k):  start + (r/8)*SBO + (r%8)*16 + (k/4)*LBO + (k%4)*4      (k < 8 per MMA)
 //   D (M = 128):  row m -> TMEM lane m, column = d_col + n.
+// MN-major operands (idesc bits 15 / 16) are NOT usable with kind::tf32: on the hardware every such MMA returned zeros
+// whatever the descriptor fields (tools/bringup/tc_probe2.cu / tc_probe3.cu, profiles/r2a_tc_probe2.txt); the model aborts on them.
 #pragma once
 #include "vx_common.cuh"
 
@@ -152,6 +153,7 @@ inline float emu_operand(uint64_t d, int mn_major, int r, int k) {
 }
 inline void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   const int N = (int)((idesc >> 17) & 0x3Fu) << 3, a_mn = (idesc >> 15) & 1, b_mn = (idesc >> 16) & 1;
+  if (a_mn || b_mn) { fprintf(stderr, "vx_emu: MN-major operands do not work with kind::tf32 on the hardware\n"); abort(); }
   const int col = (int)(tmem_d & 0xFFFFu);
   if (col + N > 512) { fprintf(stderr, "vx_emu: MMA writes past TMEM column 512\n"); abort(); }
   float a[128][8];
