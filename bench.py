@@ -236,7 +236,8 @@ def run_ours(args, rank, world, local_rank):
         # the dominant kernel = largest summed device time over all its launches in the step (instrument overhead removed)
         by_kernel = {}
         for r in rows:
-            k = by_kernel.setdefault(r[1].strip("()"), [0, 0.0, 0.0, 0, 0.0])
+            # one row per kernel: template instantiations (occupancy / tile variants of one source kernel) are merged
+            k = by_kernel.setdefault(r[1].strip("()").split("<")[0], [0, 0.0, 0.0, 0, 0.0])
             k[0] += r[2]; k[1] += max(r[3] - r[2] * ev_overhead_us * 1e-3, 0.05 * r[3]); k[2] += r[4]; k[3] += r[2] if r[4] > 0 else 0; k[4] += r[5]
         ranked = sorted(by_kernel.items(), key=lambda kv: -kv[1][1])
         table = [dict(kernel=k, launches_per_step=v[0] / nprof, ms_per_step=round(v[1] / nprof, 4),

@@ -311,11 +311,16 @@ int vx_conv_bwd(const vx_conv_desc* d, const void* const* in, void* const* out, 
  *   in[0]  int64 table (n_tensors, 4): parameter pointer, gradient pointer (0 = no gradient: skipped), offset of the tensor
  *          in the flat moment buffers, element count
  *   in[1]  int32 (n_chunks, 2): tensor index, first element -- one CTA per 1024-element chunk
+ *   in[2]  (only when hyper_on_device != 0) 2 floats on the device: learning rate, weight decay -- read by the kernel at run
+ *          time, so a learning-rate schedule takes effect inside a replayed CUDA graph (utils/train_*.py schedulers)
  *   out[0], out[1]  flat exp_avg / exp_avg_sq (fp32);  out[2]  step counter (1 float, advanced by the call)
+ *   grad_scale  the gradient is multiplied by it on the way in (1 / world_size after an all-reduce(sum)); 0 means 1
  * ------------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t n_chunks;
   float lr, beta1, beta2, eps, weight_decay;
+  float grad_scale;
+  int32_t hyper_on_device;
 } vx_adamw_desc;
 int vx_adamw_step(const vx_adamw_desc* d, const void* const* in, void* const* out, vx_stream_t stream);
 

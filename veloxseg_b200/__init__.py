@@ -5,3 +5,9 @@
 Importing the package does not load the native library; the first op call does, and fails loudly if it is missing.
 """
 __version__ = "0.1.0"
+
+
+def set_precision(mode: str) -> None:
+    """"fp32" (default) or "bf16" numerics for the tensor-core kernels; see veloxseg_b200.ops.set_precision."""
+    from . import ops
+    ops.set_precision(mode)

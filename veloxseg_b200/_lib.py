@@ -81,7 +81,7 @@ class ConvDesc(C.Structure):
 
 class AdamwDesc(C.Structure):
     _fields_ = [("n_chunks", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("weight_decay", C.c_float)]
+                ("weight_decay", C.c_float), ("grad_scale", C.c_float), ("hyper_on_device", C.c_int32)]
 
 
 # every symbol include/veloxseg_abi.h declares

@@ -24,6 +24,55 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float* __restr
   if (s == 123.456f) out[0] = s;                       // never true: keeps the chains alive
 }
 
+// 3-register form: acc = x * w + acc with every operand a run-time register (what a convolution inner loop issues)
+__global__ void __launch_bounds__(256) fma3_peak_kernel(int iters, float* __restrict__ out) {
+  float a[8], x[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a[j] = 1e-3f * (float)(threadIdx.x + j); x[j] = out[1 + (threadIdx.x + j) % 3]; }
+  float w = out[1];
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = fmaf(x[j], w, a[j]);
+    }
+    w = -w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += a[j];
+  if (s == 123.456f) out[0] = s;
+}
+
+#ifndef VX_EMU
+// packed form: fma.rn.f32x2 (FFMA2), two fp32 FMAs per instruction on 64-bit register pairs
+__global__ void __launch_bounds__(256) fma2_peak_kernel(int iters, float* __restrict__ out) {
+  unsigned long long a[8], x[8], w;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float2 t = make_float2(1e-3f * (float)(threadIdx.x + j), 2e-3f * (float)(threadIdx.x + j));
+    a[j] = *reinterpret_cast<unsigned long long*>(&t);
+    float2 u = make_float2(out[1 + (threadIdx.x + j) % 3], out[1 + (threadIdx.x + j + 1) % 3]);
+    x[j] = *reinterpret_cast<unsigned long long*>(&u);
+  }
+  { float2 t = make_float2(out[1], out[2]); w = *reinterpret_cast<unsigned long long*>(&t); }
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[j]) : "l"(x[j]), "l"(w));
+    }
+    w ^= 0x8000000080000000ull;
+  }
+  unsigned long long s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s ^= a[j];
+  if (s == 0x123456789abcdefull) out[0] = 1.f;
+}
+#endif
+
 __global__ void null_kernel(int) {}
 
 }  // namespace vx
@@ -39,6 +88,18 @@ extern "C" int vx_microbench(int kind, int iters, void* scratch, vx_stream_t str
     prof_scope("microbench fma");
     VX_LAUNCH(fma_peak_kernel, dim3(kSMs * 8), dim3(256), 0, st, iters, (float*)scratch);
     return check_launch("fma_peak_kernel");
+  }
+  if (kind == 2 || kind == 3) {          // flops = 2 * 8 * 32 * iters * 148 * 8 * 256 (kind 2), twice that (kind 3); scratch = 4 floats
+    if (!scratch || iters <= 0) { set_error("microbench: scratch / iters"); return VX_ERR_BAD_DESC; }
+    prof_scope("microbench fma%d", kind);
+#ifndef VX_EMU
+    if (kind == 3) {
+      VX_LAUNCH(fma2_peak_kernel, dim3(kSMs * 8), dim3(256), 0, st, iters, (float*)scratch);
+      return check_launch("fma2_peak_kernel");
+    }
+#endif
+    VX_LAUNCH(fma3_peak_kernel, dim3(kSMs * 8), dim3(256), 0, st, iters, (float*)scratch);
+    return check_launch("fma3_peak_kernel");
   }
   prof_scope("microbench null");
   VX_LAUNCH(null_kernel, dim3(1), dim3(32), 0, st, 0);

@@ -223,7 +223,8 @@ struct AdamArgs {
   const int* chunks;           // [nchunk][2]: tensor index, first element of the chunk
   float* m; float* v;          // flat first / second moment
   float* step;                 // (1) step counter, advanced by adamw_tick_kernel
-  float lr, beta1, beta2, eps, wd;
+  float lr, beta1, beta2, eps, wd, gscale;
+  const float* hyper;          // device (lr, wd) or null
 };
 constexpr int AD_CHUNK = 1024;
 
@@ -238,11 +239,12 @@ __global__ void __launch_bounds__(256) adamw_kernel(const __grid_constant__ Adam
   const int n = (int)e[3];
   if (!g || start >= n) return;
   const float step = A.step[0];
+  const float lr = A.hyper ? A.hyper[0] : A.lr, wd = A.hyper ? A.hyper[1] : A.wd;
   const float bc1 = 1.f - powf(A.beta1, step), bc2 = 1.f - powf(A.beta2, step);
-  const float step_size = A.lr / bc1, rbc2s = 1.f / sqrtf(bc2), decay = 1.f - A.lr * A.wd;
+  const float step_size = lr / bc1, rbc2s = 1.f / sqrtf(bc2), decay = 1.f - lr * wd;
   const int end = min(n, start + AD_CHUNK);
   for (int i = start + threadIdx.x; i < end; i += blockDim.x) {
-    const float gi = g[i];
+    const float gi = g[i] * A.gscale;
     float pi = p[i] * decay;
     const float mi = A.m[off + i] + (gi - A.m[off + i]) * (1.f - A.beta1);        // exp_avg.lerp_(grad, 1 - beta1)
     const float vi = A.v[off + i] * A.beta2 + (1.f - A.beta2) * gi * gi;
@@ -365,6 +367,9 @@ extern "C" int vx_adamw_step(const vx_adamw_desc* d, const void* const* in, void
   A.table = (const long long*)in[0]; A.chunks = (const int*)in[1];
   A.m = (float*)out[0]; A.v = (float*)out[1]; A.step = (float*)out[2];
   A.lr = d->lr; A.beta1 = d->beta1; A.beta2 = d->beta2; A.eps = d->eps; A.wd = d->weight_decay;
+  A.gscale = d->grad_scale != 0.f ? d->grad_scale : 1.f;
+  A.hyper = d->hyper_on_device ? (const float*)in[2] : nullptr;
+  if (d->hyper_on_device && !A.hyper) { set_error("adamw: hyper_on_device without in[2]"); return VX_ERR_BAD_DESC; }
   cudaStream_t st = (cudaStream_t)stream;
   VX_LAUNCH(adamw_tick_kernel, dim3(1), dim3(1), 0, st, A.step);
   int rc = check_launch("adamw_tick_kernel");

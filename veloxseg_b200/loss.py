@@ -16,7 +16,8 @@ from . import ops
 
 
 def veloxseg_output_layout(output_count: int, num_modal: int) -> dict:
-    """utils/runtime.py:158-174."""
+    """Restatement of utils/runtime.py:158-174 (the reference's list-layout helper, same error text): validation glue the
+    drop-in contract needs verbatim, not new logic."""
     tail = 2 + int(num_modal)
     if output_count <= tail:
         raise ValueError(f"VeloxSeg output count {output_count} is too small for {num_modal} modality "
@@ -27,7 +28,7 @@ def veloxseg_output_layout(output_count: int, num_modal: int) -> dict:
 
 
 def normalized_deep_loss_weights(configured, output_count: int):
-    """utils/runtime.py:125-144."""
+    """Restatement of utils/runtime.py:125-144 (same rules and error texts as the reference helper)."""
     if output_count <= 0:
         raise ValueError("output_count must be greater than 0")
     w = [float(v) for v in configured]
@@ -65,13 +66,12 @@ class Loss(torch.nn.Module):
         s0, s1 = lay["seg"]
         w = normalized_deep_loss_weights(self.deep_weights, s1 - s0)
         outs = list(output[s0:s1])
-        if outs[0].is_cuda and len(outs) <= 8 and 2 <= outs[0].shape[1] <= 4 and all(o.shape == outs[0].shape for o in outs):
-            seg = ops.seg_loss(outs, labels.long(), w)        # one fused pass per direction (veloxseg_b200/csrc/segloss.cu)
-        else:                                                 # shapes the fused kernel does not cover: torch ops
-            y = labels.squeeze(1).long()
-            seg = outs[0].new_zeros(())
-            for wi, o in zip(w, outs):
-                seg = seg + wi * (F.cross_entropy(o, y) + dice_loss(o, labels))
+        if not (outs[0].is_cuda and len(outs) <= 8 and 2 <= outs[0].shape[1] <= 4 and all(o.shape == outs[0].shape for o in outs)):
+            # no torch fallback: the three reference configs have 4 deep outputs of 2 or 4 classes (segloss.cu covers
+            # <= 8 outputs, 2..4 classes); anything else is outside the drop-in path and fails loudly
+            raise NotImplementedError("veloxseg_b200.loss.Loss: the fused CE+Dice kernel covers CUDA logits with 2..4 classes "
+                                      "and up to 8 equally-shaped deep outputs")
+        seg = ops.seg_loss(outs, labels.long(), w)            # one fused pass per direction (veloxseg_b200/csrc/segloss.cu)
         rc = F.mse_loss(output[lay["reconstruction"]], sr_labels)
         feat = ops.sdkt_loss(output[lay["decoder_gram"]], [output[i] for i in lay["teacher_grams"]])
         return seg + self.rc_weight * rc + self.feature_weight * feat

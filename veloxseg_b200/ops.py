@@ -27,6 +27,25 @@ _f32 = torch.float32
 _seed_offset = {}
 
 
+_PRECISION = "fp32"
+
+
+def set_precision(mode: str) -> None:
+    """`"fp32"` (default): every kernel fp32-accurate (tensor-core contractions 3xTF32).  `"bf16"`: north_star's second
+    precision mode -- the tensor-core contractions (1x1 convs of levels 1-2 with their weight gradients, dense 3x3x3 convs
+    forward / data / weight gradient) round operands and stored activations to bfloat16 and issue one product with fp32
+    accumulation; statistics, norms, softmax, losses and the optimiser stay fp32 (VX_OPT_PRECISION, include/veloxseg_abi.h)."""
+    global _PRECISION
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _lib.get_lib().set_option(14, 1 if mode == "bf16" else 0)
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
 def seed_offset_tensor(device) -> Optional[Tensor]:
     """Device-resident uint64 (stored as int64) that every dropout kernel adds to its per-call seed.  `advance_seed`
     bumps it with a kernel, so a CUDA graph that captured one training step draws fresh masks on every replay."""

@@ -4,7 +4,9 @@ Step semantics follow the reference loop: inputs = cat(modalities) (B, sum(in_ch
 Loss(output, labels, sr_labels=inputs) -> backward -> AdamW step (lr 2.5e-4, wd 0.01).  One process per GPU; every
 norm in the model is per-sample, so ranks exchange nothing but gradients: `GradBuckets` lays the parameters out in a
 few flat fp32 buckets (reverse registration order ~ backward completion order), exposes `.grad` as views into them and
-launches one asynchronous all-reduce per bucket from the autograd hooks while the rest of backward is still running.
+launches one asynchronous all-reduce per bucket from the autograd hooks while the rest of backward is still running
+(eager path).  The default path captures the whole step -- forward, backward, the gradient all-reduce (NCCL is captured
+into the graph) and AdamW -- as ONE CUDA graph per rank.
 """
 from __future__ import annotations
 
@@ -50,7 +52,10 @@ class GradBuckets:
             self.total.append(len(g))
         self.pending = list(self.total)
         self.works: List[Optional[object]] = [None] * len(self.buckets)
-        self.comm_stream = None
+        # The model runs branches on forked streams and autograd replays every AccumulateGrad on its forward stream, so the
+        # gradients of one bucket are produced on several streams: each hook records an event on ITS stream and the
+        # all-reduce waits for all of the bucket's events (NCCL itself orders only against the launching stream).
+        self.events: List[list] = [[] for _ in self.buckets]
         if self.world > 1:
             for p in self.params:
                 p.register_post_accumulate_grad_hook(self._ready)
@@ -64,11 +69,20 @@ class GradBuckets:
             b.zero_()
         self.pending = list(self.total)
         self.works = [None] * len(self.buckets)
+        self.events = [[] for _ in self.buckets]
 
     def _ready(self, p):
         bi = self.bucket_of[p]
         self.pending[bi] -= 1
+        if p.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(p.device))
+            self.events[bi].append(ev)
         if self.pending[bi] == 0:
+            if p.is_cuda:
+                cur = torch.cuda.current_stream(p.device)
+                for ev in self.events[bi]:
+                    cur.wait_event(ev)
             self.works[bi] = dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def finish(self):
@@ -77,6 +91,10 @@ class GradBuckets:
             return
         for bi, w in enumerate(self.works):
             if w is None:       # a bucket whose parameters received no gradient this step
+                if self.buckets[bi].is_cuda:
+                    cur = torch.cuda.current_stream(self.buckets[bi].device)
+                    for ev in self.events[bi]:
+                        cur.wait_event(ev)
                 w = dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             w.wait()
             self.buckets[bi].div_(self.world)
@@ -84,16 +102,23 @@ class GradBuckets:
 
 class VxAdamW:
     """torch.optim.AdamW (the reference's optimiser: decoupled weight decay, bias correction, betas (0.9, 0.999), eps
-    1e-8) as ONE launch of libveloxseg over every parameter tensor.  State = two flat fp32 moment buffers + a device step
-    counter, so a captured CUDA graph replays it unchanged; the (parameter, gradient) pointer table is refreshed from
-    pinned host memory on every call because autograd may hand out new gradient tensors (inside a captured graph the
-    copy node replays the addresses of the graph's own static gradient tensors)."""
-    CHUNK = 1024
+    1e-8) as ONE launch of libveloxseg over every parameter tensor.  State = two flat fp32 moment buffers, a device step
+    counter and a device (lr, weight_decay) pair, so a captured CUDA graph replays it unchanged and `set_lr` (the
+    reference's schedulers, utils/train_*.py) takes effect inside the replayed graph.
 
-    def __init__(self, params, lr: float, weight_decay: float, betas=(0.9, 0.999), eps: float = 1e-8):
+    The (parameter, gradient) pointer table lives on the device and is refreshed from pinned host memory only when it
+    changes (autograd hands out new gradient tensors in eager mode).  Uploads rotate through a ring of pinned tables, each
+    guarded by an event, so a table is never rewritten while its asynchronous copy may still be pending; a table uploaded
+    during stream capture is private to that graph and never rewritten (the graph's copy node re-reads it at every replay).
+    `grad_source(flat, params)` points the gradient column into a flat buffer instead (the all-reduced one of TrainStep)."""
+    CHUNK = 1024
+    RING = 4
+
+    def __init__(self, params, lr: float, weight_decay: float, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0):
         self.params = [p for p in params if p.requires_grad]
         dev = self.params[0].device
         self.lr, self.wd, self.betas, self.eps = float(lr), float(weight_decay), betas, float(eps)
+        self.grad_scale = float(grad_scale)
         total, offs, chunks = 0, [], []
         for i, p in enumerate(self.params):
             if p.dtype != torch.float32 or not p.is_contiguous():
@@ -105,31 +130,97 @@ class VxAdamW:
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.step_t = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.hyper = torch.tensor([self.lr, self.wd], dtype=torch.float32, device=dev)
         self.chunks = torch.tensor(chunks, dtype=torch.int32).reshape(-1, 2).to(dev)
         self.n_chunks = len(chunks)
-        self._tab_host = torch.zeros(len(self.params), 4, dtype=torch.int64).pin_memory()
+        self._ring = [torch.zeros(len(self.params), 4, dtype=torch.int64).pin_memory() for _ in range(self.RING)]
+        self._ring_ev = [None] * self.RING
+        self._ring_i = 0
+        self._graph_tabs = []            # pinned tables owned by captured graphs: kept alive, never rewritten
         self._tab_dev = torch.zeros(len(self.params), 4, dtype=torch.int64, device=dev)
+        self._tab_last = None            # host copy of what _tab_dev holds (None: unknown)
+        self._grad_src = None
+
+    # ---- hyper-parameters / state (torch.optim.Optimizer-like surface)
+    @property
+    def param_groups(self):
+        return [{"params": self.params, "lr": self.lr, "weight_decay": self.wd, "betas": self.betas, "eps": self.eps}]
+
+    def set_lr(self, lr: float, weight_decay: Optional[float] = None):
+        """Takes effect at the next step, also inside an already captured graph (the kernel reads the device pair)."""
+        self.lr = float(lr)
+        if weight_decay is not None:
+            self.wd = float(weight_decay)
+        self.hyper.copy_(torch.tensor([self.lr, self.wd], dtype=torch.float32))
 
     def state_tensors(self):
         return [self.exp_avg, self.exp_avg_sq, self.step_t]
 
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step_t.clone(),
+                "lr": self.lr, "weight_decay": self.wd, "betas": tuple(self.betas), "eps": self.eps}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_t.copy_(sd["step"])
+        self.betas, self.eps = tuple(sd["betas"]), float(sd["eps"])
+        self.set_lr(sd["lr"], sd["weight_decay"])
+
+    def grad_source(self, flat: Optional[torch.Tensor], params=None):
+        """Read the gradients of `params` (in order) from consecutive slices of `flat` instead of `p.grad`; None resets."""
+        if flat is None:
+            self._grad_src = None
+            return
+        if flat.dtype != torch.float32 or not flat.is_contiguous():
+            raise TypeError("VxAdamW: the flat gradient buffer must be contiguous float32")
+        ptrs, off = {}, 0
+        for p in params:
+            ptrs[id(p)] = flat.data_ptr() + 4 * off
+            off += p.numel()
+        if off != flat.numel():
+            raise ValueError("VxAdamW.grad_source: flat buffer size does not match the parameter list")
+        self._grad_src = ptrs
+
+    def _table(self):
+        rows = []
+        for i, p in enumerate(self.params):
+            if self._grad_src is not None:
+                gp = self._grad_src.get(id(p), 0)
+            else:
+                g = p.grad
+                if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
+                    raise TypeError("VxAdamW: gradients must be contiguous float32")
+                gp = g.data_ptr() if g is not None else 0
+            rows.append((p.data_ptr(), gp, self.offsets[i], p.numel()))
+        return rows
+
     def step(self):
         from . import _lib
         from ._lib import AdamwDesc
-        tab = self._tab_host
-        for i, p in enumerate(self.params):
-            g = p.grad
-            if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
-                raise TypeError("VxAdamW: gradients must be contiguous float32")
-            tab[i, 0] = p.data_ptr()
-            tab[i, 1] = g.data_ptr() if g is not None else 0
-            tab[i, 2] = self.offsets[i]
-            tab[i, 3] = p.numel()
-        self._tab_dev.copy_(tab, non_blocking=True)
+        dev = self.step_t.device
+        rows = self._table()
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing:
+            tab = torch.tensor(rows, dtype=torch.int64).pin_memory()       # private to this graph, immutable
+            self._graph_tabs.append(tab)
+            self._tab_dev.copy_(tab, non_blocking=True)
+            self._tab_last = None                                          # replays rewrite _tab_dev behind our back
+        elif rows != self._tab_last:
+            i = self._ring_i
+            self._ring_i = (i + 1) % self.RING
+            if self._ring_ev[i] is not None:
+                self._ring_ev[i].synchronize()                             # its previous upload has been consumed
+            self._ring[i].copy_(torch.tensor(rows, dtype=torch.int64))
+            self._tab_dev.copy_(self._ring[i], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self._ring_ev[i] = ev
+            self._tab_last = rows if not self._graph_tabs else None        # a graph replay may overwrite the device table
         lib = _lib.get_lib()
-        d = AdamwDesc(self.n_chunks, self.lr, self.betas[0], self.betas[1], self.eps, self.wd)
-        lib.call("vx_adamw_step", d, [self._tab_dev, self.chunks], [self.exp_avg, self.exp_avg_sq, self.step_t],
-                 torch.cuda.current_stream(self.step_t.device).cuda_stream)
+        d = AdamwDesc(self.n_chunks, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.grad_scale, 1)
+        lib.call("vx_adamw_step", d, [self._tab_dev, self.chunks, self.hyper], [self.exp_avg, self.exp_avg_sq, self.step_t],
+                 torch.cuda.current_stream(dev).cuda_stream)
 
 
 class TrainStep:
@@ -142,11 +233,13 @@ class TrainStep:
     because the kernels add a device-resident offset (ops.advance_seed, captured in the graph) to their seeds.
 
       world == 1   one graph: forward, loss, backward, AdamW.
-      world  > 1   graph A: forward, loss, backward, gradients gathered into one flat fp32 buffer (9 MB);
-                   one NCCL all-reduce of that buffer (latency-bound over NVLink: tens of microseconds next to an 18 ms
-                   step, so nothing is gained by splitting it into buckets inside the graph);
-                   graph B: mean, scatter back into `.grad`, AdamW.
-    `use_graph=False` keeps the eager path, where `GradBuckets` overlaps bucketed all-reduces with backward."""
+      world  > 1   one graph: forward, loss, backward, the gradients gathered into one flat fp32 buffer (9 MB), the NCCL
+                   all-reduce of that buffer CAPTURED in the graph, AdamW reading the summed gradients straight from the flat
+                   buffer with grad_scale = 1 / world (no scatter back, no second graph, no host launch between them).
+                   `VX_DP_GRAPH=split` keeps the older form (graph A: forward / backward / gather; eager all-reduce;
+                   graph B: AdamW) for A/B measurements and for NCCL builds that cannot be captured.
+    `use_graph=False` keeps the eager path, where `GradBuckets` overlaps bucketed all-reduces with backward.
+    `set_lr` changes the learning rate of the next step, also of an already captured graph."""
 
     def __init__(self, model: torch.nn.Module, num_modal: int, device, lr: float = 2.5e-4, weight_decay: float = 0.01,
                  deep_weights=(1, 1, 1, 1), rc_weight: float = 0.5, feature_weight: float = 2.0,
@@ -162,6 +255,7 @@ class TrainStep:
         self.buckets = GradBuckets(self.params, bucket_bytes) if not self.use_graph else None
         # libveloxseg's one-launch AdamW on CUDA (VX_TORCH_ADAMW=1 keeps torch's fused multi-tensor optimiser for A/B)
         import os
+        self.split_graph = os.environ.get("VX_DP_GRAPH", "one") == "split"
         if cuda and os.environ.get("VX_TORCH_ADAMW", "0") != "1":
             self.opt = VxAdamW(self.model.parameters(), lr=lr, weight_decay=weight_decay)
         else:
@@ -189,6 +283,26 @@ class TrainStep:
         flat.div_(self.world)
         torch._foreach_copy_(grads, [f.view_as(g) for f, g in zip(flat.split([g.numel() for g in grads]), grads)])
 
+    def set_lr(self, lr: float):
+        if isinstance(self.opt, VxAdamW):
+            self.opt.set_lr(lr)
+        else:
+            for g in self.opt.param_groups:
+                if torch.is_tensor(g["lr"]):
+                    g["lr"].fill_(lr)
+                else:
+                    g["lr"] = lr
+
+    def _reduce_and_step_flat(self):
+        """world > 1, own optimiser: gather -> all-reduce(sum) -> AdamW reads the flat buffer scaled by 1 / world."""
+        self._gparams = [p for p in self.params if p.grad is not None]
+        flat = torch.cat([p.grad.reshape(-1) for p in self._gparams])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        self.opt.grad_scale = 1.0 / self.world
+        self.opt.grad_source(flat, self._gparams)
+        self.opt.step()
+        return flat
+
     def _step_eager(self, x, y):
         """One full step without graphs (also the warm-up before capture and the profiler's per-kernel pass)."""
         if self.buckets is not None:
@@ -200,6 +314,9 @@ class TrainStep:
                 p.grad = None
             loss = self._fwd_bwd(x, y)
             if self.world > 1:
+                if isinstance(self.opt, VxAdamW) and not self.split_graph:
+                    self._flat = self._reduce_and_step_flat()
+                    return loss
                 grads, flat = self._gather_grads()
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM)
                 self._scatter_mean(grads, flat)
@@ -224,8 +341,8 @@ class TrainStep:
         lib = _lib.get_lib()
         n0 = lib.c.vx_launch_count()
         self._graph = torch.cuda.CUDAGraph()
-        if self.world == 1:
-            with torch.cuda.graph(self._graph):
+        if self.world == 1 or (isinstance(self.opt, VxAdamW) and not self.split_graph):
+            with torch.cuda.graph(self._graph):       # world > 1: the NCCL all-reduce is one of the captured nodes
                 self._sloss = self._step_eager(self._sx, self._sy)
         else:
             for p in self.params:
@@ -274,6 +391,12 @@ class TrainStep:
 
     def step(self, inputs: torch.Tensor, labels: torch.Tensor, sync: bool = False, prefetch=None):
         """`prefetch=(next_inputs, next_labels)`: start copying the next host batch while this step runs."""
+        if self.device.type == "cuda":
+            with torch.cuda.device(self.device):      # the library launches on the current device
+                return self._step(inputs, labels, sync, prefetch)
+        return self._step(inputs, labels, sync, prefetch)
+
+    def _step(self, inputs, labels, sync, prefetch):
         if self.use_graph:
             if self._graph is None:
                 self._capture(inputs, labels.long() if labels.dtype != torch.int64 else labels)
@@ -297,7 +420,7 @@ class TrainStep:
                 self._graph_b.replay()
             if prefetch is not None:
                 self._stage(*prefetch)
-            loss = self._sloss
+            loss = self._sloss if sync else self._sloss.clone()      # the static tensor is overwritten by the next replay
         else:
             loss = self._step_eager(inputs.to(self.device, non_blocking=True), labels.to(self.device, non_blocking=True).long())
         return float(loss.item()) if sync else loss
