@@ -27,7 +27,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 CFG_NAME = "autopetii"      # --workload: autopetii = BASELINE configs[1] (default, the headline), brats2021 = configs[2]
-PATCHES = 4
+PATCHES = int(os.environ.get("VX_PATCHES", "4"))      # 4 = the reference's train_config_bs4 step; other values are scaling probes only
 CFG_TITLE = {"autopetii": "AutoPET-II", "brats2021": "BraTS2021", "hecktor2022": "Hecktor2022"}
 
 

@@ -23,7 +23,7 @@ def _oracle():
 
 
 @pytest.mark.parametrize("C,groups,e,shape,B", [(8, 2, 3, (5, 6, 8), 2), (16, 2, 2, (3, 4, 7), 1), (32, 2, 2, (3, 3, 3), 2),
-                                                  (8, 2, 3, (9, 7, 12), 1)])
+                                                  (8, 2, 3, (9, 7, 12), 1), (16, 2, 2, (9, 8, 12), 1), (8, 2, 2, (9, 9, 7), 1)])
 def test_jlc(emu, C, groups, e, shape, B):
     from veloxseg_b200 import ops
     O = _oracle()

@@ -53,6 +53,8 @@ def main():
         lib.set_option(6, int(os.environ["VX_JLC_VX"]))
     if "VX_JLC_SMALL_MAX_S" in os.environ:
         lib.set_option(8, int(os.environ["VX_JLC_SMALL_MAX_S"]))
+    if "VX_JLC_KS" in os.environ:
+        lib.set_option(15, int(os.environ["VX_JLC_KS"]))
     if "VX_PW_TC_MIN_S" in os.environ:
         lib.set_option(3, int(os.environ["VX_PW_TC_MIN_S"]))
     B, res = args.B, []

@@ -37,11 +37,11 @@ for r in rows[2:]:
     for k in ("noinst", "long", "short", "barrier", "wait", "issue", "warps"):
         a[k] += num(r, k) * t            # time-weighted
 tot = sum(a["t"] for a in agg.values())
-print("%d kernels, %d launches, %.2f ms summed" % (len(agg), sum(a["n"] for a in agg.values()), tot / 1e6))
+print("%d kernels, %d launches, %.2f ms summed" % (len(agg), sum(a["n"] for a in agg.values()), tot / 1e3))
 print("%-44s %4s %8s %6s %7s | stalled warps per issue: %6s %6s %6s %6s %6s | %6s %6s" %
       ("kernel", "n", "us", "avg", "inst/w", "noinst", "long", "short", "barr", "wait", "issue%", "warps%"))
 for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["t"])[: int(sys.argv[2]) if len(sys.argv) > 2 else 40]:
     t = a["t"] or 1.0
     print("%-44s %4d %8.1f %6.1f %7.0f | %30.1f %6.1f %6.1f %6.1f %6.1f | %6.1f %6.1f" %
-          (name[:44], a["n"], a["t"] / 1e3, a["t"] / 1e3 / a["n"], a["ipw"] / a["n"], a["noinst"] / t, a["long"] / t, a["short"] / t,
+          (name[:44], a["n"], a["t"], a["t"] / a["n"], a["ipw"] / a["n"], a["noinst"] / t, a["long"] / t, a["short"] / t,
            a["barrier"] / t, a["wait"] / t, a["issue"] / t, a["warps"] / t))

@@ -208,6 +208,7 @@ extern "C" size_t vx_profile_report(char*, size_t) { return 0; }
 extern "C" int vx_set_option(int option, int value) {
   if (option == VX_OPT_WGRAD_TC_MIN_S) { vx::pw_wgrad_tc_set(-1, value); return VX_OK; }
   if (option == VX_OPT_JLC_SMALL_MAX_S) { vx::jlc_set_small_max(value); return VX_OK; }
+  if (option == VX_OPT_JLC_KS) { vx::jlc_set_ks(value); return VX_OK; }
   if (option == VX_OPT_CONV3_TRACE) { vx::conv3_trace_set(value); return VX_OK; }
   if (option == VX_OPT_PRECISION) { vx::precision_set(value); return VX_OK; }
   if (option == VX_OPT_SIDE_WGRAD) { vx::side_set(value ? 1 : 0); return VX_OK; }

@@ -66,7 +66,9 @@ static ConvTile pick_tile(int B, int groups, int CG, int D, int H, int W, int ma
       const int waste = (ntz * tz - D) * H + (nty * ty - H) * D;        // padded rows: tie-break towards exact tilings
       long long key;
       if (smem_kind == 0) {
-        const int enough_threads = threads >= 32, whole_warps = npos % 32 == 0, enough_ctas = ncta >= 96;
+        // >= 132 CTAs (0.9 x 148 SMs): the reduction-split kernels multiply the threads of a CTA by KS afterwards, so what the
+        // tile has to provide is one CTA per SM (level 2, 12^3: 4 x 4 x 12 -> 144 CTAs of 96 x KS threads, no padded rows)
+        const int enough_threads = threads >= 32, whole_warps = npos % 32 == 0, enough_ctas = ncta >= 132;
         key = ((((long long)enough_threads * 2 + whole_warps) * 2 + enough_ctas) << 40) +
               ((long long)(enough_ctas ? threads : (ncta < 4096 ? ncta : 4096)) << 20) + (1 << 19) - waste * 64 + tz;
       } else {
@@ -78,6 +80,43 @@ static ConvTile pick_tile(int B, int groups, int CG, int D, int H, int W, int ma
     }
   }
   return best;
+}
+
+// Stages `nch` channels of a zero-padded halo tile, layout [ch][HZ][HY][TXP], from NCDHW rows: tile origin (z0, y0, x0), halo
+// PZ in z / y and XH (0 or 2) in x (TXP even).  16 lanes walk one row in 8-byte chunks, the (thread / 16) groups walk the
+// (channel, z, y) rows with incremental indices: no per-element integer division -- the flat-index decoding this replaces
+// was 14 % of the forward kernel's instructions at level 1 (profiles/r2o_jlc_conv_L1.source.txt).  Rows that are not
+// 8-byte aligned in global memory (odd W or odd x0) take 4-byte copies.
+VX_DEV void stage_halo_rows(float* xs, const float* __restrict__ src, size_t ch_stride, int nch, int z0, int y0, int x0, int PZ,
+                            int HZ, int HY, int TXP, int D, int H, int W, int XH = 2) {
+  const int l = threadIdx.x & 15, sub = threadIdx.x >> 4, nsub = blockDim.x >> 4;
+  if (sub >= nsub) return;
+  const int R = HZ * HY;
+  const bool wide = ((W | x0 | TXP) & 1) == 0 && (((uintptr_t)src | (ch_stride * sizeof(float))) & 7) == 0;
+  int hz = sub / HY, hy = sub - hz * HY;             // one division per thread, not per element
+  for (int r = sub; r < nch * R; r += nsub) {
+    int ch = 0, rz = hz;
+    while (rz >= HZ) { rz -= HZ; ++ch; }             // nch <= 16 iterations at most, usually 0-1 per step
+    const int gz = z0 + rz - PZ, gy = y0 + hy - PZ;
+    const bool rowok = gz >= 0 && gz < D && gy >= 0 && gy < H;
+    const float* grow = src + (size_t)ch * ch_stride + ((size_t)(rowok ? gz : 0) * H + (rowok ? gy : 0)) * W;
+    float* srow = xs + (size_t)r * TXP;
+    if (wide) {
+      for (int c = l; 2 * c < TXP; c += 16) {
+        const int gx = x0 + 2 * c - XH;
+        const bool ok = rowok && gx >= 0 && gx < W;       // W and gx even: the pair is inside or outside together
+        vx_cp_async8(srow + 2 * c, ok ? grow + gx : src, ok);
+      }
+    } else {
+      for (int c = l; c < TXP; c += 16) {
+        const int gx = x0 + c - XH;
+        const bool ok = rowok && gx >= 0 && gx < W;
+        vx_cp_async4(srow + c, ok ? grow + gx : src, ok);
+      }
+    }
+    hy += nsub;
+    while (hy >= HY) { hy -= HY; ++hz; }
+  }
 }
 
 struct ConvFwdArgs {
@@ -126,12 +165,7 @@ __global__ void __launch_bounds__(256) jlc_conv_fwd_kernel(const __grid_constant
     if (chunk > 0) __syncthreads();
     // stage 4 input channels of the group with a 2-voxel zero halo
     const int cin0 = g * CG + chunk * 4;
-    for (int idx = tid; idx < 4 * HZ * HY * TXP; idx += nthr) {
-      const int hx = idx % TXP, hy = (idx / TXP) % HY, hz = (idx / (TXP * HY)) % HZ, ci = idx / (TXP * HY * HZ);
-      const int gz = z0 + hz - 2, gy = y0 + hy - 2, gx = x0 + hx - 2;
-      const bool ok = gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W;
-      vx_cp_async4(xs + idx, ok ? A.x + ((size_t)b * C + cin0 + ci) * S + ((size_t)gz * H + gy) * W + gx : A.x, ok);
-    }
+    stage_halo_rows(xs, A.x + ((size_t)b * C + cin0) * S, S, 4, z0, y0, x0, 2, HZ, HY, TXP, D, H, W);
     // weights of this ci-chunk, transposed to [ci][tap][co]
     for (int idx = tid; idx < CG * 4 * 125; idx += nthr) {
       const int tap = idx % 125, ci = (idx / 125) % 4, co = idx / 500;
@@ -254,6 +288,202 @@ __global__ void __launch_bounds__(256) jlc_conv_fwd_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Reduction-split variant of the tiled forward kernel (levels 1-2).  The tiled kernel above has exactly one thread per
+// (4 voxels x 4 output channels): 1 728 warps at level 1 and 432 at level 2 for B = 4 -- 12 and 3 warps per SM walking a
+// serial (ci, dz, dy) chain (ncu: 17 % / 9 % warps active, 56 % / 46 % issue-active, profiles/r2o_jlc_conv_L*.digest.txt).
+// Here the whole group (all CG input channels and their weights) is staged once and the CG input channels are dealt to KS
+// thread slices: KS times the warps, a chain KS times shorter, no re-staging per 4-channel chunk; the slices' 48
+// accumulators meet in shared memory (fixed order: slice 0 adds slices 1 .. KS-1) before the unchanged epilogue.
+// ---------------------------------------------------------------------------------------------------
+// CTA size limit / CTAs per SM the register budget is cut for: c_g = 4 (level 1, 288 CTAs at B = 4) wants two CTAs of 384
+// threads per SM (24 warps), c_g = 8 (level 2, 96 CTAs) one CTA of up to 576 threads.
+template <int CG> struct JlcKs { static constexpr int MAXT = CG == 4 ? 384 : 576, MINB = CG == 4 ? 2 : 1; };
+
+template <int CG, int VX>
+__global__ void __launch_bounds__(JlcKs<CG>::MAXT, JlcKs<CG>::MINB) jlc_conv_fwd_ks_kernel(const __grid_constant__ ConvFwdArgs A, int KS) {
+  constexpr int NCB = CG / 4;
+  const int g = blockIdx.y, b = blockIdx.z;
+  const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;
+  const int tile = blockIdx.x;
+  const int tx_i = tile % A.t.ntx, ty_i = (tile / A.t.ntx) % A.t.nty, tz_i = tile / (A.t.ntx * A.t.nty);
+  const int z0 = tz_i * TZ, y0 = ty_i * TY, x0 = tx_i * TX;
+  const int HZ = TZ + 4, HY = TY + 4, TXP = (TX + 4 + 3) & ~3;
+  const int D = A.D, H = A.H, W = A.W, C = A.C;
+  const size_t S = (size_t)D * H * W;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int NXQ = TX / VX;
+  const int NPOS = TZ * TY * NXQ, NT = NPOS * NCB;
+  const int kz = tid / NT, t2 = tid % NT;               // reduction slice, thread inside the slice
+  const int pos = t2 % NPOS, cb = t2 / NPOS;
+  const int xq = pos % NXQ, ty = (pos / NXQ) % TY, tz = pos / (NXQ * TY);
+  const int XV = HZ * HY * TXP;                          // one staged channel
+
+  VX_DYN_SMEM(float, sm);
+  float* xs = sm;                                   // [CG][HZ][HY][TXP]
+  float* ws5 = xs + (size_t)CG * XV;                // [CG ci][125][CG co]
+  float* ws3 = ws5 + CG * 125 * CG;                 // [CG][27][CG]
+  float* ws1 = ws3 + CG * 27 * CG;                  // [CG][CG]
+  const size_t stage_fl = (size_t)CG * XV + (size_t)CG * 153 * CG, red_fl = (size_t)(KS - 1) * 12 * VX * NT;
+  float* sst = sm + (stage_fl > red_fl ? stage_fl : red_fl);      // [3][CG][2]
+  float* red = sm;                                  // [(KS - 1)][12 VX][NT]: reuses the staging area after the compute phase
+
+  for (int i = tid; i < 3 * CG * 2; i += nthr) sst[i] = 0.f;
+  stage_halo_rows(xs, A.x + ((size_t)b * C + g * CG) * S, S, CG, z0, y0, x0, 2, HZ, HY, TXP, D, H, W);
+  for (int idx = tid; idx < CG * CG * 125; idx += nthr) {      // weights transposed to [ci][tap][co]
+    const int tap = idx % 125, ci = (idx / 125) % CG, co = idx / (125 * CG);
+    vx_cp_async4(ws5 + ((ci * 125 + tap) * CG + co), A.w5 + ((size_t)(g * CG + co) * CG + ci) * 125 + tap, true);
+  }
+  for (int idx = tid; idx < CG * CG * 27; idx += nthr) {
+    const int tap = idx % 27, ci = (idx / 27) % CG, co = idx / (27 * CG);
+    vx_cp_async4(ws3 + ((ci * 27 + tap) * CG + co), A.w3 + ((size_t)(g * CG + co) * CG + ci) * 27 + tap, true);
+  }
+  for (int idx = tid; idx < CG * CG; idx += nthr) {
+    const int ci = idx % CG, co = idx / CG;
+    vx_cp_async4(ws1 + (ci * CG + co), A.w1 + (size_t)(g * CG + co) * CG + ci, true);
+  }
+  vx_cp_async_commit();
+  vx_cp_async_wait_all();
+  __syncthreads();
+
+  float a5[VX][4], a3[VX][4], a1[VX][4];
+#pragma unroll
+  for (int v = 0; v < VX; ++v)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { a5[v][c] = 0.f; a3[v][c] = 0.f; a1[v][c] = 0.f; }
+
+  if (kz < KS) {
+    const int per = CG / KS;
+    // (ci, dz, dy) stay rolled: the unrolled (dx, v) body must stay instruction-cache resident
+#pragma unroll 1
+    for (int ci = kz * per; ci < (kz + 1) * per; ++ci) {
+#pragma unroll 1
+      for (int dz = 0; dz < 5; ++dz) {
+        const float* xrow = xs + ((size_t)(ci * HZ + tz + dz) * HY + ty) * TXP + xq * VX;
+        const bool mid_z = dz >= 1 && dz <= 3;
+#pragma unroll 1
+        for (int dy = 0; dy < 5; ++dy) {
+          float xr[VX + 4];
+#pragma unroll
+          for (int q = 0; q < (VX + 4) / 4; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(xrow + dy * TXP + 4 * q);
+            xr[4 * q] = t4.x; xr[4 * q + 1] = t4.y; xr[4 * q + 2] = t4.z; xr[4 * q + 3] = t4.w;
+          }
+          const float* w5p = ws5 + (size_t)(ci * 125 + (dz * 5 + dy) * 5) * CG + cb * 4;
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx) {
+            const float4 w = *reinterpret_cast<const float4*>(w5p + dx * CG);
+#pragma unroll
+            for (int v = 0; v < VX; ++v) {
+              a5[v][0] = fmaf(w.x, xr[v + dx], a5[v][0]); a5[v][1] = fmaf(w.y, xr[v + dx], a5[v][1]);
+              a5[v][2] = fmaf(w.z, xr[v + dx], a5[v][2]); a5[v][3] = fmaf(w.w, xr[v + dx], a5[v][3]);
+            }
+          }
+          if (dy >= 1 && dy <= 3) {
+            if (mid_z) {
+              const float* w3p = ws3 + (size_t)(ci * 27 + ((dz - 1) * 3 + (dy - 1)) * 3) * CG + cb * 4;
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const float4 w = *reinterpret_cast<const float4*>(w3p + dx * CG);
+#pragma unroll
+                for (int v = 0; v < VX; ++v) {
+                  a3[v][0] = fmaf(w.x, xr[v + 1 + dx], a3[v][0]); a3[v][1] = fmaf(w.y, xr[v + 1 + dx], a3[v][1]);
+                  a3[v][2] = fmaf(w.z, xr[v + 1 + dx], a3[v][2]); a3[v][3] = fmaf(w.w, xr[v + 1 + dx], a3[v][3]);
+                }
+              }
+            }
+            if (dy == 2 && dz == 2) {
+              const float4 w = *reinterpret_cast<const float4*>(ws1 + ci * CG + cb * 4);
+#pragma unroll
+              for (int v = 0; v < VX; ++v) {
+                a1[v][0] = fmaf(w.x, xr[v + 2], a1[v][0]); a1[v][1] = fmaf(w.y, xr[v + 2], a1[v][1]);
+                a1[v][2] = fmaf(w.z, xr[v + 2], a1[v][2]); a1[v][3] = fmaf(w.w, xr[v + 2], a1[v][3]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---- the slices meet: slice r > 0 parks its accumulators, slice 0 adds them in slice order
+  __syncthreads();                                  // the staged tile and weights are dead from here on
+  if (kz > 0 && kz < KS) {
+    float* r = red + (size_t)(kz - 1) * 12 * VX * NT + t2;
+#pragma unroll
+    for (int v = 0; v < VX; ++v)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        r[(size_t)((0 * VX + v) * 4 + c) * NT] = a1[v][c];
+        r[(size_t)((1 * VX + v) * 4 + c) * NT] = a3[v][c];
+        r[(size_t)((2 * VX + v) * 4 + c) * NT] = a5[v][c];
+      }
+  }
+  __syncthreads();
+  const bool lead = kz == 0;
+  if (lead) {
+    for (int s2 = 1; s2 < KS; ++s2) {
+      const float* r = red + (size_t)(s2 - 1) * 12 * VX * NT + t2;
+#pragma unroll
+      for (int v = 0; v < VX; ++v)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          a1[v][c] += r[(size_t)((0 * VX + v) * 4 + c) * NT];
+          a3[v][c] += r[(size_t)((1 * VX + v) * 4 + c) * NT];
+          a5[v][c] += r[(size_t)((2 * VX + v) * 4 + c) * NT];
+        }
+    }
+  }
+
+  // epilogue (slice 0): bias, store, stats
+  const int gz = z0 + tz, gy = y0 + ty, gx0 = x0 + xq * VX;
+  const bool row_ok = lead && gz < D && gy < H;
+  const size_t BCS = (size_t)A.B * C * S;
+  const int lane = tid & 31;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int co = g * CG + cb * 4 + c;
+    const float bias[3] = {__ldg(A.b1 + co), __ldg(A.b3 + co), __ldg(A.b5 + co)};
+    float s[3] = {0.f, 0.f, 0.f}, q[3] = {0.f, 0.f, 0.f};
+    if (row_ok) {
+      const size_t o = ((size_t)b * C + co) * S + ((size_t)gz * H + gy) * W + gx0;
+#pragma unroll
+      for (int v = 0; v < VX; ++v) {
+        if (gx0 + v < W) {
+          const float r1 = a1[v][c] + bias[0], r3 = a3[v][c] + bias[1], r5 = a5[v][c] + bias[2];
+          A.z[o + v] = r1; A.z[BCS + o + v] = r3; A.z[2 * BCS + o + v] = r5;
+          s[0] += r1; q[0] = fmaf(r1, r1, q[0]);
+          s[1] += r3; q[1] = fmaf(r3, r3, q[1]);
+          s[2] += r5; q[2] = fmaf(r5, r5, q[2]);
+        }
+      }
+    }
+    if (A.uniform_warps) {                          // NPOS % 32 == 0: a warp is uniform in (slice, channel block)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float ss = warp_sum(s[k]), qq = warp_sum(q[k]);
+        if (lane == 0 && lead) {
+          atomicAdd(sst + ((k * CG) + cb * 4 + c) * 2, ss);
+          atomicAdd(sst + ((k * CG) + cb * 4 + c) * 2 + 1, qq);
+        }
+      }
+    } else if (row_ok) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        atomicAdd(sst + ((k * CG) + cb * 4 + c) * 2, s[k]);
+        atomicAdd(sst + ((k * CG) + cb * 4 + c) * 2 + 1, q[k]);
+      }
+    }
+  }
+  __syncthreads();
+  const int ntiles = gridDim.x;
+  for (int i = tid; i < 3 * CG; i += nthr) {
+    const int k = i / CG, c = i % CG;
+    const size_t row = (size_t)k * A.B * C + (size_t)b * C + g * CG + c;
+    float* p = A.part + (row * ntiles + tile) * 2;
+    p[0] = sst[i * 2]; p[1] = sst[i * 2 + 1];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Small-volume variants (levels 3-4: S = 216 / 27, Hecktor 256 / 32).  The tiled kernels above leave 32-128 CTAs of
 // 36-64 threads walking a serial (ci, tap) loop -- 75-250 us of pure latency for a few MFLOP.  Here the whole padded
 // volume of a group lives in shared memory and the work is split three ways: CTA = (batch, group, 4 output channels,
@@ -291,12 +521,7 @@ __global__ void __launch_bounds__(256) jlc_conv_small_fwd_kernel(const __grid_co
   __shared__ float sst[12 * 4 * 2];             // (sum, sumsq) per (branch * 4 + c, warp of the voxel slab): fixed-order fold
   const int tid = threadIdx.x, nthr = blockDim.x;
 
-  for (int idx = tid; idx < CG * PV; idx += nthr) {
-    const int px = idx % Wp, py = (idx / Wp) % Hp, pz = (idx / (Wp * Hp)) % G.Dp, ci = idx / PV;
-    const int gz = pz - 2, gy = py - 2, gx = px - 2;
-    const bool ok = gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W;
-    vx_cp_async4(xs + idx, ok ? A.x + ((size_t)b * C + g * CG + ci) * S + ((size_t)gz * H + gy) * W + gx : A.x, ok);
-  }
+  stage_halo_rows(xs, A.x + ((size_t)b * C + g * CG) * S, (size_t)S, CG, 0, 0, 0, 2, G.Dp, Hp, Wp, D, H, W);
   const int co0 = g * CG + q * 4;
   for (int idx = tid; idx < 4 * CG * 125; idx += nthr) {
     const int tap = idx % 125, ci = (idx / 125) % CG, c = idx / (125 * CG);
@@ -545,12 +770,7 @@ VX_DEV void dgrad_branch(const ConvDgradArgs& A, const float* __restrict__ gzk, 
   for (int chunk = 0; chunk < NCB; ++chunk) {
     __syncthreads();
     const int c0 = g * CG + chunk * 4;     // 4 "input" channels of this correlation = conv output channels
-    for (int idx = tid; idx < 4 * HZ * HY * TXP; idx += nthr) {
-      const int hx = idx % TXP, hy = (idx / TXP) % HY, hz = (idx / (TXP * HY)) % HZ, ci = idx / (TXP * HY * HZ);
-      const int gz_ = z0 + hz - P, gy = y0 + hy - P, gx = x0 + hx - 2;
-      const bool ok = gz_ >= 0 && gz_ < D && gy >= 0 && gy < H && gx >= 0 && gx < W;
-      vx_cp_async4(xs + idx, ok ? gzk + ((size_t)b * C + c0 + ci) * S + ((size_t)gz_ * H + gy) * W + gx : gzk, ok);
-    }
+    stage_halo_rows(xs, gzk + ((size_t)b * C + c0) * S, S, 4, z0, y0, x0, P, HZ, HY, TXP, D, H, W);
     // ws[co_local(4)][tap'][ci_out(CG)] = w[co][ci][K3-1-tap']
     for (int idx = tid; idx < 4 * CG * K3; idx += nthr) {
       const int tap = idx % K3, cio = (idx / K3) % CG, col = idx / (K3 * CG);
@@ -633,6 +853,123 @@ __global__ void __launch_bounds__(256) jlc_conv_dgrad_kernel(const __grid_consta
   }
 }
 
+// Reduction-split data gradient (same idea as jlc_conv_fwd_ks_kernel): per branch the gradients of ALL CG output channels
+// of the group and the flipped weights are staged once (three staging phases instead of 3 * CG / 4) and the CG reduction
+// channels are dealt to KS thread slices; the 4 VX accumulators of the slices meet in shared memory.
+template <int CG, int VX, int K>
+VX_DEV void dgrad_branch_ks(const ConvDgradArgs& A, const float* __restrict__ gzk, const float* __restrict__ wk, float* xs,
+                            float* ws, float (&acc)[VX][4], int g, int b, int z0, int y0, int x0, int tz, int ty, int xq,
+                            int cb, int kz, int KS) {
+  constexpr int P = K / 2, K3 = K * K * K;
+  const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;
+  const int HZ = TZ + 2 * P, HY = TY + 2 * P, TXP = (TX + 4 + 3) & ~3;   // x keeps the 2-voxel halo for alignment
+  const int D = A.D, H = A.H, W = A.W, C = A.C;
+  const size_t S = (size_t)D * H * W;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int XV = HZ * HY * TXP;
+  __syncthreads();                                   // the previous branch has been consumed
+  stage_halo_rows(xs, gzk + ((size_t)b * C + g * CG) * S, S, CG, z0, y0, x0, P, HZ, HY, TXP, D, H, W);
+  // ws[co][tap'][ci] = w[co][ci][K3 - 1 - tap']
+  for (int idx = tid; idx < CG * CG * K3; idx += nthr) {
+    const int tap = idx % K3, cio = (idx / K3) % CG, col = idx / (K3 * CG);
+    vx_cp_async4(ws + ((col * K3 + (K3 - 1 - tap)) * CG + cio), wk + ((size_t)(g * CG + col) * CG + cio) * K3 + tap, true);
+  }
+  vx_cp_async_commit();
+  vx_cp_async_wait_all();
+  __syncthreads();
+  if (kz < KS) {
+    const int per = CG / KS;
+#pragma unroll 1
+    for (int co = kz * per; co < (kz + 1) * per; ++co) {
+#pragma unroll 1
+      for (int dz = 0; dz < K; ++dz) {
+        const float* xrow = xs + ((size_t)(co * HZ + tz + dz) * HY + ty) * TXP + xq * VX;
+#pragma unroll 1
+        for (int dy = 0; dy < K; ++dy) {
+          float xr[VX + 4];
+#pragma unroll
+          for (int q = 0; q < (VX + 4) / 4; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(xrow + dy * TXP + 4 * q);
+            xr[4 * q] = t4.x; xr[4 * q + 1] = t4.y; xr[4 * q + 2] = t4.z; xr[4 * q + 3] = t4.w;
+          }
+          const float* wp = ws + (size_t)(co * K3 + (dz * K + dy) * K) * CG + cb * 4;
+#pragma unroll
+          for (int dx = 0; dx < K; ++dx) {
+            const float4 w = *reinterpret_cast<const float4*>(wp + dx * CG);
+#pragma unroll
+            for (int v = 0; v < VX; ++v) {
+              const float xv = xr[v + dx + 2 - P];
+              acc[v][0] = fmaf(w.x, xv, acc[v][0]); acc[v][1] = fmaf(w.y, xv, acc[v][1]);
+              acc[v][2] = fmaf(w.z, xv, acc[v][2]); acc[v][3] = fmaf(w.w, xv, acc[v][3]);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int CG, int VX>
+__global__ void __launch_bounds__(JlcKs<CG>::MAXT, JlcKs<CG>::MINB) jlc_conv_dgrad_ks_kernel(const __grid_constant__ ConvDgradArgs A, int KS) {
+  constexpr int NCB = CG / 4;
+  const int g = blockIdx.y, b = blockIdx.z;
+  const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;
+  const int tile = blockIdx.x;
+  const int tx_i = tile % A.t.ntx, ty_i = (tile / A.t.ntx) % A.t.nty, tz_i = tile / (A.t.ntx * A.t.nty);
+  const int z0 = tz_i * TZ, y0 = ty_i * TY, x0 = tx_i * TX;
+  const int TXP = (TX + 4 + 3) & ~3;
+  VX_DYN_SMEM(float, sm);
+  float* xs = sm;                                            // [CG][TZ + 4][TY + 4][TXP] (largest branch)
+  float* ws = sm + (size_t)CG * (TZ + 4) * (TY + 4) * TXP;   // [CG][125][CG]
+  const int tid = threadIdx.x;
+  const int NXQ = TX / VX, NPOS = TZ * TY * NXQ, NT = NPOS * NCB;
+  const int kz = tid / NT, t2 = tid % NT;
+  const int pos = t2 % NPOS, cb = t2 / NPOS;
+  const int xq = pos % NXQ, ty = (pos / NXQ) % TY, tz = pos / (NXQ * TY);
+  const size_t S = (size_t)A.D * A.H * A.W;
+  const size_t BCS = (size_t)A.B * A.C * S;
+
+  float acc[VX][4];
+#pragma unroll
+  for (int v = 0; v < VX; ++v)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[v][c] = 0.f;
+
+  dgrad_branch_ks<CG, VX, 5>(A, A.gz + 2 * BCS, A.w5, xs, ws, acc, g, b, z0, y0, x0, tz, ty, xq, cb, kz, KS);
+  dgrad_branch_ks<CG, VX, 3>(A, A.gz + BCS, A.w3, xs, ws, acc, g, b, z0, y0, x0, tz, ty, xq, cb, kz, KS);
+  dgrad_branch_ks<CG, VX, 1>(A, A.gz, A.w1, xs, ws, acc, g, b, z0, y0, x0, tz, ty, xq, cb, kz, KS);
+
+  __syncthreads();
+  float* red = sm;                                           // [(KS - 1)][4 VX][NT]
+  if (kz > 0 && kz < KS) {
+    float* r = red + (size_t)(kz - 1) * 4 * VX * NT + t2;
+#pragma unroll
+    for (int v = 0; v < VX; ++v)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) r[(size_t)(v * 4 + c) * NT] = acc[v][c];
+  }
+  __syncthreads();
+  if (kz != 0) return;
+  for (int s2 = 1; s2 < KS; ++s2) {
+    const float* r = red + (size_t)(s2 - 1) * 4 * VX * NT + t2;
+#pragma unroll
+    for (int v = 0; v < VX; ++v)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[v][c] += r[(size_t)(v * 4 + c) * NT];
+  }
+  const int gz = z0 + tz, gy = y0 + ty, gx0 = x0 + xq * VX;
+  if (gz < A.D && gy < A.H) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int ci = g * CG + cb * 4 + c;
+      const size_t o = ((size_t)b * A.C + ci) * S + ((size_t)gz * A.H + gy) * A.W + gx0;
+#pragma unroll
+      for (int v = 0; v < VX; ++v)
+        if (gx0 + v < A.W) A.dx[o + v] = acc[v][c] + A.dO[o + v];
+    }
+  }
+}
+
 // Small-volume dgrad (same decomposition as jlc_conv_small_fwd_kernel): CTA = (batch, group, 4 input channels, voxel
 // slab), thread = (voxel, slice of the group's output channels); the three branch gradients sit in shared memory as
 // padded volumes (k=5 and k=3 share the halo-2 layout, k=1 is read at the centre), weights are staged flipped so the
@@ -652,12 +989,9 @@ __global__ void __launch_bounds__(256) jlc_conv_small_dgrad_kernel(const __grid_
   float* red = ws + (size_t)CG * 153 * 4;       // [KS][4][VP]
   const int tid = threadIdx.x, nthr = blockDim.x;
 
-  for (int idx = tid; idx < 3 * CG * PV; idx += nthr) {
-    const int px = idx % Wp, py = (idx / Wp) % Hp, pz = (idx / (Wp * Hp)) % G.Dp, co = (idx / PV) % CG, k = idx / (PV * CG);
-    const int gz = pz - 2, gy = py - 2, gx = px - 2;
-    const bool ok = gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W;
-    vx_cp_async4(gs + idx, ok ? A.gz + (size_t)k * BCS + ((size_t)b * C + g * CG + co) * S + ((size_t)gz * H + gy) * W + gx : A.gz, ok);
-  }
+  for (int k = 0; k < 3; ++k)
+    stage_halo_rows(gs + (size_t)k * CG * PV, A.gz + (size_t)k * BCS + ((size_t)b * C + g * CG) * S, (size_t)S, CG, 0, 0, 0, 2, G.Dp, Hp, Wp,
+                    D, H, W);
   const int ci0 = q * 4;                         // input channels (within the group) this CTA produces
   for (int idx = tid; idx < CG * 4 * 125; idx += nthr) {
     const int tap = idx % 125, c = (idx / 125) % 4, co = idx / 500;
@@ -820,12 +1154,8 @@ __global__ void __launch_bounds__(JW_THREADS) jlc_conv_wgrad_kernel(const __grid
   const int tvol = TZ * TY * TX;
 
   if (tid < 3 * 16) sdb[tid] = 0.f;
-  for (int idx = tid; idx < 3 * CG * tvol; idx += nthr) {
-    const int x = idx % TX, y = (idx / TX) % TY, z = (idx / (TX * TY)) % TZ, co = (idx / tvol) % CG, k = idx / (tvol * CG);
-    const int gz_ = z0 + z, gy = y0 + y, gx = x0 + x;
-    const bool ok = gz_ < D && gy < H && gx < W;
-    vx_cp_async4(gs + idx, ok ? A.gz + k * BCS + ((size_t)b * C + g * CG + co) * S + ((size_t)gz_ * H + gy) * W + gx : A.gz, ok);
-  }
+  for (int k = 0; k < 3; ++k)                      // [k][co][TZ][TY][TX], no halo
+    stage_halo_rows(gs + (size_t)k * CG * tvol, A.gz + k * BCS + ((size_t)b * C + g * CG) * S, S, CG, z0, y0, x0, 0, TZ, TY, TX, D, H, W, 0);
   vx_cp_async_commit();
   vx_cp_async_wait_all();
   __syncthreads();
@@ -840,12 +1170,7 @@ __global__ void __launch_bounds__(JW_THREADS) jlc_conv_wgrad_kernel(const __grid
   for (int chunk = 0; chunk < NCB; ++chunk) {
     __syncthreads();
     const int cin0 = g * CG + chunk * 4;
-    for (int idx = tid; idx < 4 * HZ * HY * TXP; idx += nthr) {
-      const int hx = idx % TXP, hy = (idx / TXP) % HY, hz = (idx / (TXP * HY)) % HZ, ci = idx / (TXP * HY * HZ);
-      const int gz_ = z0 + hz - 2, gy = y0 + hy - 2, gx = x0 + hx - 2;
-      const bool ok = gz_ >= 0 && gz_ < D && gy >= 0 && gy < H && gx >= 0 && gx < W;
-      vx_cp_async4(xs + idx, ok ? A.x + ((size_t)b * C + cin0 + ci) * S + ((size_t)gz_ * H + gy) * W + gx : A.x, ok);
-    }
+    stage_halo_rows(xs, A.x + ((size_t)b * C + cin0) * S, S, 4, z0, y0, x0, 2, HZ, HY, TXP, D, H, W);
     vx_cp_async_commit();
     vx_cp_async_wait_all();
     __syncthreads();
@@ -911,12 +1236,35 @@ static int jlc_layout(const vx_jlc_desc* d, JlcLayout& L) {
   return VX_OK;
 }
 
+// reduction slices of the K-split kernels: the largest divisor of CG in {8, 4, 2} that keeps the CTA within JLC_KS_THREADS
+static int g_jlc_ks = -1;           // -1: automatic, 0 / 1: K-split kernels off, 2 / 4 / 8: forced (vx_set_option probe)
+void jlc_set_ks(int ks) { g_jlc_ks = ks; }
+static int pick_ks(int CG, int nt, int max_threads) {
+  if (g_jlc_ks == 0 || g_jlc_ks == 1) return 1;
+  const int cand[] = {8, 4, 2};
+  for (int k : cand) {
+    if (g_jlc_ks > 1 && k != g_jlc_ks) continue;
+    if (CG % k == 0 && nt * k <= max_threads) return k;
+  }
+  return 1;
+}
+
 template <int CG>
 static int launch_conv_fwd(const ConvFwdArgs& A, int groups, cudaStream_t st) {
   const ConvTile& t = A.t;
   const int TXP = (t.TX + 4 + 3) & ~3;
-  const size_t smem = sizeof(float) * ((size_t)4 * (t.TZ + 4) * (t.TY + 4) * TXP + 4 * 153 * CG + 3 * CG * 2);
   dim3 grid(t.ntz * t.nty * t.ntx, groups, A.B);
+  if (t.VX == 4) {
+    const int KS = pick_ks(CG, t.threads, JlcKs<CG>::MAXT);
+    const size_t stage = (size_t)CG * (t.TZ + 4) * (t.TY + 4) * TXP + (size_t)CG * 153 * CG, red = (size_t)(KS - 1) * 48 * t.threads;
+    const size_t smem_ks = sizeof(float) * ((stage > red ? stage : red) + 3 * CG * 2);
+    if (KS > 1 && smem_ks <= 200 * 1024) {
+      VX_SET_SMEM((jlc_conv_fwd_ks_kernel<CG, 4>), smem_ks);
+      VX_LAUNCH((jlc_conv_fwd_ks_kernel<CG, 4>), grid, dim3(t.threads * KS), smem_ks, st, A, KS);
+      return check_launch("jlc_conv_fwd_ks_kernel");
+    }
+  }
+  const size_t smem = sizeof(float) * ((size_t)4 * (t.TZ + 4) * (t.TY + 4) * TXP + 4 * 153 * CG + 3 * CG * 2);
   if (t.VX == 8) {
     VX_SET_SMEM((jlc_conv_fwd_kernel<CG, 8>), smem);
     VX_LAUNCH((jlc_conv_fwd_kernel<CG, 8>), grid, dim3(t.threads), smem, st, A);
@@ -931,8 +1279,18 @@ template <int CG>
 static int launch_conv_dgrad(const ConvDgradArgs& A, int groups, cudaStream_t st) {
   const ConvTile& t = A.t;
   const int TXP = (t.TX + 4 + 3) & ~3;
-  const size_t smem = sizeof(float) * ((size_t)4 * (t.TZ + 4) * (t.TY + 4) * TXP + 4 * 125 * CG);
   dim3 grid(t.ntz * t.nty * t.ntx, groups, A.B);
+  if (t.VX == 4) {
+    const int KS = pick_ks(CG, t.threads, JlcKs<CG>::MAXT);
+    const size_t stage = (size_t)CG * (t.TZ + 4) * (t.TY + 4) * TXP + (size_t)CG * 125 * CG, red = (size_t)(KS - 1) * 16 * t.threads;
+    const size_t smem_ks = sizeof(float) * (stage > red ? stage : red);
+    if (KS > 1 && smem_ks <= 200 * 1024) {
+      VX_SET_SMEM((jlc_conv_dgrad_ks_kernel<CG, 4>), smem_ks);
+      VX_LAUNCH((jlc_conv_dgrad_ks_kernel<CG, 4>), grid, dim3(t.threads * KS), smem_ks, st, A, KS);
+      return check_launch("jlc_conv_dgrad_ks_kernel");
+    }
+  }
+  const size_t smem = sizeof(float) * ((size_t)4 * (t.TZ + 4) * (t.TY + 4) * TXP + 4 * 125 * CG);
   if (t.VX == 8) {
     VX_SET_SMEM((jlc_conv_dgrad_kernel<CG, 8>), smem);
     VX_LAUNCH((jlc_conv_dgrad_kernel<CG, 8>), grid, dim3(t.threads), smem, st, A);

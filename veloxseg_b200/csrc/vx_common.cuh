@@ -39,9 +39,16 @@
 // 4-byte asynchronous global -> shared copy (LDGSTS); `ok == false` zero-fills.
 #ifdef VX_EMU
 static inline void vx_cp_async4(float* dst, const float* src, bool ok) { *dst = ok ? *src : 0.f; }
+static inline void vx_cp_async8(float* dst, const float* src, bool ok) { dst[0] = ok ? src[0] : 0.f; dst[1] = ok ? src[1] : 0.f; }
 static inline void vx_cp_async_commit() {}
 static inline void vx_cp_async_wait_all() {}
 #else
+// 8-byte variant: both addresses 8-byte aligned
+VX_DEV void vx_cp_async8(float* dst, const float* src, bool ok) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int n = ok ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
 VX_DEV void vx_cp_async4(float* dst, const float* src, bool ok) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
   const int n = ok ? 4 : 0;
@@ -79,12 +86,35 @@ VX_DEV float bf16_round(float x) {
 // 0: fp32-accurate (3xTF32 on the tensor cores), 1: bf16 numerics (tensor-core operands and outputs rounded to bf16, one product)
 int precision_mode();
 
-VX_DEV float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf(u) and exp(-u^2) together: Abramowitz & Stegun 7.1.26, erf(u) = sign(u) (1 - (a1 t + ... + a5 t^5) exp(-u^2)),
+// t = 1 / (1 + p |u|), absolute error <= 1.5e-7 (fp32 resolution near 1) -- 14 instructions instead of the 27 (erff) / 39 (erff +
+// expf) per value of the library calls, which dominated the issue slots of the element-wise and epilogue code (profiles/
+// r2m_pw_tc_L2.source.txt: 30 % of the samples).  The exponential is shared with the Gaussian density of GELU'.
+VX_DEV float erf_exp(float u, float& e) {
+  const float a = fabsf(u);
+#ifdef VX_EMU
+  const float t = 1.0f / fmaf(0.3275911f, a, 1.0f);
+  e = expf(-a * a);
+#else
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));
+  e = __expf(-a * a);
+#endif
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = fmaf(-p * t, e, 1.0f);
+  return copysignf(r, u);
+}
+VX_DEV float gelu_f(float x) {
+  float e;
+  return 0.5f * x * (1.0f + erf_exp(x * 0.70710678118654752440f, e));
+}
 // d/dx GELU(x) = Phi(x) + x * phi(x)
 VX_DEV float gelu_grad_f(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e;
+  const float cdf = 0.5f * (1.0f + erf_exp(x * 0.70710678118654752440f, e));
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
 VX_DEV float warp_sum(float v) {
