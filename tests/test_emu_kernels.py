@@ -23,7 +23,8 @@ def _oracle():
 
 
 @pytest.mark.parametrize("C,groups,e,shape,B", [(8, 2, 3, (5, 6, 8), 2), (16, 2, 2, (3, 4, 7), 1), (32, 2, 2, (3, 3, 3), 2),
-                                                  (8, 2, 3, (9, 7, 12), 1), (16, 2, 2, (9, 8, 12), 1), (8, 2, 2, (9, 9, 7), 1)])
+                                                  (8, 2, 3, (9, 7, 12), 1), (16, 2, 2, (9, 8, 12), 1), (8, 2, 2, (9, 9, 7), 1),
+                                                  (8, 2, 2, (12, 14, 14), 1)])      # last: two combine chunks per row (S > 2048)
 def test_jlc(emu, C, groups, e, shape, B):
     from veloxseg_b200 import ops
     O = _oracle()
@@ -38,8 +39,11 @@ def test_jlc(emu, C, groups, e, shape, B):
     dy = torch.randn_like(y)
     grads = torch.autograd.grad(yr, [xr] + pr, dy)
     got = ops.jlc_bwd_raw(emu, 0, dy, x, z, o, hpre, stats, params, groups, e)
+    # the conv-bias gradients are structurally zero (the bias cancels inside the InstanceNorm): pure accumulation noise, which
+    # grows with the voxel count -- the absolute tolerance admits it
+    atol = 2e-5 if x[0, 0].numel() <= 1024 else 6e-5
     for i, (g, r) in enumerate(zip(got, grads)):
-        assert close(g, r, rtol=2e-4, atol=2e-5), (i, rel_err(g, r), float(r.norm()))
+        assert close(g, r, rtol=2e-4, atol=atol), (i, rel_err(g, r), float(r.norm()))
 
 
 def test_jlc_dropout_consistency(emu):
@@ -308,12 +312,17 @@ def test_pwa_dropout_backward_matches_forward_masks(emu, case):
     dzs = [torch.randn_like(z) for z in zs]
     dxs, dps, dtable = ops.pwa_block_bwd_raw(emu, 0, dzs, xs, flat, table, index, saved, geo, e, p_att, p_proj, True, seed)
     d = [torch.randn_like(x) for x in xs]
-    eps = 1e-3      # small enough that max-pool kinks and curvature stay below the tolerance (2.6% at 1e-2, 0.3% at 1e-3)
-    zp, _ = fwd([x + eps * dd for x, dd in zip(xs, d)])
-    zm, _ = fwd([x - eps * dd for x, dd in zip(xs, d)])
-    fd = sum(float(((a - b) / (2 * eps) * g).double().sum()) for a, b, g in zip(zp, zm, dzs))
-    an = sum(float((gx * dd).double().sum()) for gx, dd in zip(dxs, d))
-    assert abs(fd - an) <= 3e-2 * max(abs(fd), abs(an), 1.0), (fd, an)
+    an = sum(float((gx.double() * dd.double()).sum()) for gx, dd in zip(dxs, d))
+    # Max-pool kinks and curvature make the finite difference itself O(eps)-inexact and the size of that error depends on the
+    # mask realisation (measured on a B200, tools/dbg_pwa_drop.py: 0.2-1.3 % at 1e-3, 0.04-0.7 % at 3e-4, 4 % on an unlucky
+    # draw), whereas a mask mismatch is O(1) at every step size: the best of two step sizes must be inside the tolerance.
+    gaps = []
+    for eps in (1e-3, 3e-4):
+        zp, _ = fwd([x + eps * dd for x, dd in zip(xs, d)])
+        zm, _ = fwd([x - eps * dd for x, dd in zip(xs, d)])
+        fd = sum(float(((a - b).double() / (2 * eps) * g.double()).sum()) for a, b, g in zip(zp, zm, dzs))
+        gaps.append(abs(fd - an) / max(abs(fd), abs(an), 1.0))
+    assert min(gaps) <= 3e-2, (gaps, an)
 
 
 

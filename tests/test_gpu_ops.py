@@ -235,7 +235,7 @@ def test_pwa_gather_bit_exact(ops, lvl):
 @pytest.mark.parametrize("lvl", ["autopet_L1", "autopet_L2", "autopet_L3", "hecktor_L1"])
 def test_pwa_dropout_backward_matches_forward_masks(ops, lvl):
     """Train-mode dropout (attention weights + projections): with a fixed seed the block is a deterministic smooth function,
-    so the backward pass (which regenerates every mask, partly with Philox blocks shared between lanes) must agree with a
+    so the backward pass (which regenerates every mask, with the same hashed words per element) must agree with a
     central finite difference of the forward pass; a mask mismatch is an O(1) relative error."""
     from veloxseg_b200 import _lib
     size, C, mb, heads, mdh, M, e = PWA_LEVELS[lvl]
@@ -256,12 +256,17 @@ def test_pwa_dropout_backward_matches_forward_masks(ops, lvl):
     dzs = [torch.randn_like(z) for z in zs]
     dxs, dps, dtable = ops.pwa_block_bwd_raw(lib, st, dzs, xs, flat, table, index, saved, geo, e, p_att, p_proj, True, seed)
     d = [torch.randn_like(x) for x in xs]
-    eps = 1e-3      # small enough that max-pool kinks and curvature stay below the tolerance (2.6% at 1e-2, 0.3% at 1e-3)
-    zp, _ = fwd([x + eps * dd for x, dd in zip(xs, d)])
-    zm, _ = fwd([x - eps * dd for x, dd in zip(xs, d)])
-    fd = sum(float(((a - b).double() / (2 * eps) * g.double()).sum()) for a, b, g in zip(zp, zm, dzs))
     an = sum(float((gx.double() * dd.double()).sum()) for gx, dd in zip(dxs, d))
-    assert abs(fd - an) <= 3e-2 * max(abs(fd), abs(an), 1.0), (fd, an)
+    # Max-pool kinks and curvature make the finite difference itself O(eps)-inexact and the size of that error depends on the
+    # mask realisation (measured on a B200, tools/dbg_pwa_drop.py: 0.2-1.3 % at 1e-3, 0.04-0.7 % at 3e-4, 4 % on an unlucky
+    # draw), whereas a mask mismatch is O(1) at every step size: the best of two step sizes must be inside the tolerance.
+    gaps = []
+    for eps in (1e-3, 3e-4):
+        zp, _ = fwd([x + eps * dd for x, dd in zip(xs, d)])
+        zm, _ = fwd([x - eps * dd for x, dd in zip(xs, d)])
+        fd = sum(float(((a - b).double() / (2 * eps) * g.double()).sum()) for a, b, g in zip(zp, zm, dzs))
+        gaps.append(abs(fd - an) / max(abs(fd), abs(an), 1.0))
+    assert min(gaps) <= 3e-2, (gaps, an)
 
 
 @pytest.mark.parametrize("lvl", list(PWA_LEVELS))

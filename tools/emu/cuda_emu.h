@@ -75,6 +75,7 @@ void launch(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... a
 
 static inline void __syncthreads() { vx_emu::cta_barrier(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline float __shfl_xor_sync(unsigned, float v, int m) {
   uint32_t b; memcpy(&b, &v, 4); b = vx_emu::shfl(b, (vx_emu::t_lane_slot & 31) ^ m); float r; memcpy(&r, &b, 4); return r;
 }

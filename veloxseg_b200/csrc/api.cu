@@ -49,7 +49,7 @@ void prof_scope(const char* fmt, ...) {
 
 #ifndef VX_EMU
 // ---- weight-gradient side streams: one per (device, caller stream), created on first use
-struct SideCtx { cudaStream_t side; cudaEvent_t fork, join; bool forked; };
+struct SideCtx { cudaStream_t side; cudaEvent_t fork, join, mid; bool forked; };
 static std::mutex g_side_mu;
 static std::map<std::pair<int, cudaStream_t>, SideCtx> g_side;
 static int g_side_on = 1;
@@ -66,6 +66,7 @@ static SideCtx* side_ctx(cudaStream_t main) {
     if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c.mid, cudaEventDisableTiming);
     c.forked = false;
     it = g_side.emplace(key, c).first;
   }
@@ -82,6 +83,15 @@ cudaStream_t side_fork(cudaStream_t main) {
   }
   c->forked = true;
   return c->side;
+}
+
+// main waits for everything enqueued on the side stream so far (the side stream stays forked)
+void side_wait(cudaStream_t main) {
+  if (!g_side_on) return;
+  SideCtx* c = side_ctx(main);
+  if (!c || !c->forked) return;
+  cudaEventRecord(c->mid, c->side);
+  cudaStreamWaitEvent(main, c->mid, 0);
 }
 
 void side_join(cudaStream_t main) {
@@ -197,6 +207,7 @@ namespace vx {
 void prof_bytes(double) {}
 void prof_flops(double) {}
 cudaStream_t side_fork(cudaStream_t main) { return main; }
+void side_wait(cudaStream_t) {}
 void side_join(cudaStream_t) {}
 void side_set(int) {}
 }

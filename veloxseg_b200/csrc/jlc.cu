@@ -41,7 +41,7 @@ static bool jlc_use_small(int D, int H, int W) { return g_small_max_s > 0 && D *
 //  * wgrad (fixed 256 threads, tile-size-independent register use): it wants CTAs: the largest tile that still gives
 //    >= 256 of them, never smaller than 4 (z, y) positions.
 static ConvTile pick_tile(int B, int groups, int CG, int D, int H, int W, int max_threads, size_t max_smem_floats,
-                          int smem_kind) {
+                          int smem_kind, int min_ctas = 96) {
   // smem_kind 0: fwd/dgrad (4 * halo tile), 1: wgrad (4 * halo tile + 3 * CG * tile)
   ConvTile best{};
   long long best_key = -1;
@@ -66,9 +66,11 @@ static ConvTile pick_tile(int B, int groups, int CG, int D, int H, int W, int ma
       const int waste = (ntz * tz - D) * H + (nty * ty - H) * D;        // padded rows: tie-break towards exact tilings
       long long key;
       if (smem_kind == 0) {
-        // >= 132 CTAs (0.9 x 148 SMs): the reduction-split kernels multiply the threads of a CTA by KS afterwards, so what the
-        // tile has to provide is one CTA per SM (level 2, 12^3: 4 x 4 x 12 -> 144 CTAs of 96 x KS threads, no padded rows)
-        const int enough_threads = threads >= 32, whole_warps = npos % 32 == 0, enough_ctas = ncta >= 132;
+        // min_ctas: 96 for the forward kernel (48 accumulators per thread: it wants the larger tile), 132 = 0.9 x 148 SMs for
+        // the data gradient (16 accumulators: one CTA per SM, the reduction slices supply the threads) -- measured with
+        // tools/gpu_r2_call17.sh (profiles/r2s_jlc_ks_sweep.txt): level 2 forward 64 us at 8x4 / KS 2 vs 76 us at 4x4 / KS 4,
+        // data gradient 42 us at 4x4 / KS 4 vs 60 us at 8x4 / KS 2.
+        const int enough_threads = threads >= 32, whole_warps = npos % 32 == 0, enough_ctas = ncta >= min_ctas;
         key = ((((long long)enough_threads * 2 + whole_warps) * 2 + enough_ctas) << 40) +
               ((long long)(enough_ctas ? threads : (ncta < 4096 ? ncta : 4096)) << 20) + (1 << 19) - waste * 64 + tz;
       } else {
@@ -123,6 +125,7 @@ struct ConvFwdArgs {
   const float* x; const float* w1; const float* b1; const float* w3; const float* b3; const float* w5; const float* b5;
   float* z;      // (3, B, C, S): branch k=1, 3, 5
   float* part;   // (3, B*C, ntiles, 2)
+  int* cnt;      // (B*C) arrival counters of jlc_combine_kernel's chunks: zeroed here, by the first tile of every (b, group)
   int B, C, D, H, W;
   ConvTile t;
   int uniform_warps;
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(256) jlc_conv_fwd_kernel(const __grid_constant
     for (int c = 0; c < 4; ++c) { a5[v][c] = 0.f; a3[v][c] = 0.f; a1[v][c] = 0.f; }
 
   for (int i = tid; i < 3 * CG * 2; i += nthr) sst[i] = 0.f;
+  if (tile == 0 && tid < CG && A.cnt) A.cnt[b * C + g * CG + tid] = 0;
 
   for (int chunk = 0; chunk < NCB; ++chunk) {
     if (chunk > 0) __syncthreads();
@@ -328,6 +332,7 @@ __global__ void __launch_bounds__(JlcKs<CG>::MAXT, JlcKs<CG>::MINB) jlc_conv_fwd
   float* red = sm;                                  // [(KS - 1)][12 VX][NT]: reuses the staging area after the compute phase
 
   for (int i = tid; i < 3 * CG * 2; i += nthr) sst[i] = 0.f;
+  if (tile == 0 && tid < CG && A.cnt) A.cnt[b * C + g * CG + tid] = 0;
   stage_halo_rows(xs, A.x + ((size_t)b * C + g * CG) * S, S, CG, z0, y0, x0, 2, HZ, HY, TXP, D, H, W);
   for (int idx = tid; idx < CG * CG * 125; idx += nthr) {      // weights transposed to [ci][tap][co]
     const int tap = idx % 125, ci = (idx / 125) % CG, co = idx / (125 * CG);
@@ -523,6 +528,7 @@ __global__ void __launch_bounds__(256) jlc_conv_small_fwd_kernel(const __grid_co
 
   stage_halo_rows(xs, A.x + ((size_t)b * C + g * CG) * S, (size_t)S, CG, 0, 0, 0, 2, G.Dp, Hp, Wp, D, H, W);
   const int co0 = g * CG + q * 4;
+  if (split == 0 && tid < 4 && A.cnt) A.cnt[b * C + co0 + tid] = 0;
   for (int idx = tid; idx < 4 * CG * 125; idx += nthr) {
     const int tap = idx % 125, ci = (idx / 125) % CG, c = idx / (125 * CG);
     vx_cp_async4(ws + ((ci * 153 + tap) * 4 + c), A.w5 + ((size_t)(co0 + c) * CG + ci) * 125 + tap, true);
@@ -621,27 +627,30 @@ __global__ void __launch_bounds__(256) jlc_conv_small_fwd_kernel(const __grid_co
   }
 }
 
-// stats[row] = (mean, rstd) from tile partials; optionally the (a, c) affine used as a contraction prologue
-__global__ void jlc_finalize_kernel(const float* __restrict__ part, int rows, int npart, float n, float eps,
-                                    float* __restrict__ stats, float* __restrict__ a, float* __restrict__ c) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  float mean, rstd;
-  finalize_stats(part, r, npart, n, eps, mean, rstd);
-  stats[2 * r] = mean; stats[2 * r + 1] = rstd;
-  if (a) { a[r] = rstd; c[r] = -mean * rstd; }
-}
-
-// o = x + sum_k GELU((z_k - mean_k) * rstd_k);  partial (sum, sumsq) of o per (row, chunk)
+// o = x + sum_k GELU((z_k - mean_k) * rstd_k) with both InstanceNorm statistics passes folded in (no finalize launches):
+//  * every CTA (row, chunk) folds the convolution's per-tile (sum, sumsq) partials of its row into (mean, rstd) itself
+//    (ntiles <= a few dozen numbers, fixed order); chunk 0 records them in `stats` for the backward pass;
+//  * the CTA that arrives last at the row's counter (zeroed by the convolution kernel) folds the chunks' partials of o, again
+//    in fixed order, into stats[3 rows + row] and the (a, c) affine the FFN's first contraction applies as its prologue.
 __global__ void __launch_bounds__(256) jlc_combine_kernel(const float* __restrict__ x, const float* __restrict__ z,
-                                                          const float* __restrict__ stats, float* __restrict__ o,
-                                                          float* __restrict__ part_o, int rows, int S, int chunk) {
+                                                          const float* __restrict__ part_z, int ntiles, float* __restrict__ stats,
+                                                          float* __restrict__ o, float* __restrict__ part_o, int* __restrict__ cnt,
+                                                          float* __restrict__ aff_a, float* __restrict__ aff_c, int rows, int S,
+                                                          int chunk, float eps) {
   __shared__ float red[33];
-  const int row = blockIdx.y, ck = blockIdx.x;
+  __shared__ float mr[6];
+  const int row = blockIdx.y, ck = blockIdx.x, nchunk = gridDim.x;
   const size_t RS = (size_t)rows * S;
+  if (threadIdx.x < 3) {
+    float mean, rstd;
+    finalize_stats(part_z, threadIdx.x * rows + row, ntiles, (float)S, eps, mean, rstd);
+    mr[2 * threadIdx.x] = mean; mr[2 * threadIdx.x + 1] = rstd;
+    if (ck == 0) { stats[2 * (threadIdx.x * rows + row)] = mean; stats[2 * (threadIdx.x * rows + row) + 1] = rstd; }
+  }
+  __syncthreads();
   float m[3], r[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { m[k] = stats[2 * (k * rows + row)]; r[k] = stats[2 * (k * rows + row) + 1]; }
+  for (int k = 0; k < 3; ++k) { m[k] = mr[2 * k]; r[k] = mr[2 * k + 1]; }
   const size_t base = (size_t)row * S;
   const int lo = ck * chunk, hi = min(S, lo + chunk);
   float s = 0.f, q = 0.f;
@@ -655,8 +664,20 @@ __global__ void __launch_bounds__(256) jlc_combine_kernel(const float* __restric
   s = block_sum(s, red);
   q = block_sum(q, red);
   if (threadIdx.x == 0) {
-    float* p = part_o + ((size_t)row * gridDim.x + ck) * 2;
+    float* p = part_o + ((size_t)row * nchunk + ck) * 2;
     p[0] = s; p[1] = q;
+    bool last = true;
+    if (nchunk > 1) {
+      __threadfence();                                   // the partial is visible before the arrival is
+      last = atomicAdd(cnt + row, 1) == nchunk - 1;
+      if (last) __threadfence();
+    }
+    if (last) {
+      float mean, rstd;
+      finalize_stats(part_o, row, nchunk, (float)S, eps, mean, rstd);
+      stats[2 * (3 * rows + row)] = mean; stats[2 * (3 * rows + row) + 1] = rstd;
+      aff_a[row] = rstd; aff_c[row] = -mean * rstd;
+    }
   }
 }
 
@@ -1196,10 +1217,10 @@ static inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 struct JlcLayout {
   size_t S, BCS, rows;
-  ConvTile tf, tw;
+  ConvTile tf, td, tw;      // forward, data gradient, weight gradient
   int small, ntiles_f;      // small-volume conv kernels; stats partials per row of the forward conv
   int nchunk, chunk;
-  size_t off_part_z, off_part_o, off_a, off_c;                       // forward scratch
+  size_t off_part_z, off_part_o, off_a, off_c, off_cnt;              // forward scratch
   size_t off_dh, off_dohat, off_dO, off_gz, off_acc, off_acc2;      // backward scratch
   size_t total;
 };
@@ -1213,6 +1234,7 @@ static int jlc_layout(const vx_jlc_desc* d, JlcLayout& L) {
   L.rows = (size_t)d->B * d->C;
   L.BCS = L.rows * L.S;
   L.tf = pick_tile(d->B, d->groups, CG, d->D, d->H, d->W, 256, 40 * 1024, 0);
+  L.td = pick_tile(d->B, d->groups, CG, d->D, d->H, d->W, 256, 40 * 1024, 0, 132);
   L.tw = pick_tile(d->B, d->groups, CG, d->D, d->H, d->W, 256, 44 * 1024, 1);
   if (L.tf.threads == 0 || L.tw.TZ == 0) { set_error("jlc: no tile fits"); return VX_ERR_UNSUPPORTED; }
   L.chunk = 2048;
@@ -1226,6 +1248,7 @@ static int jlc_layout(const vx_jlc_desc* d, JlcLayout& L) {
   L.off_part_o = off; off += align256(sizeof(float) * L.rows * L.nchunk * 2);
   L.off_a = off; off += align256(sizeof(float) * L.rows);
   L.off_c = off; off += align256(sizeof(float) * L.rows);
+  L.off_cnt = off; off += align256(sizeof(int) * L.rows);
   L.off_dh = off; off += align256(sizeof(float) * (size_t)d->B * d->expansion * d->C * L.S);
   L.off_dohat = off; off += align256(sizeof(float) * L.BCS);
   L.off_dO = off; off += align256(sizeof(float) * L.BCS);
@@ -1369,7 +1392,7 @@ extern "C" int vx_jlc_fwd(const vx_jlc_desc* d, const void* const* in, void* con
   ConvFwdArgs A{};
   A.x = x; A.w1 = (const float*)in[1]; A.b1 = (const float*)in[2]; A.w3 = (const float*)in[3]; A.b3 = (const float*)in[4];
   A.w5 = (const float*)in[5]; A.b5 = (const float*)in[6];
-  A.z = z; A.part = part_z; A.B = d->B; A.C = d->C; A.D = d->D; A.H = d->H; A.W = d->W; A.t = L.tf;
+  A.z = z; A.part = part_z; A.cnt = (int*)(ws + L.off_cnt); A.B = d->B; A.C = d->C; A.D = d->D; A.H = d->H; A.W = d->W; A.t = L.tf;
   const int npos = L.tf.TZ * L.tf.TY * (L.tf.TX / L.tf.VX);
   A.uniform_warps = (npos % 32 == 0) ? 1 : 0;
   prof_bytes(4.0 * sizeof(float) * (double)L.BCS);       // x in, z1 z3 z5 out
@@ -1383,16 +1406,10 @@ extern "C" int vx_jlc_fwd(const vx_jlc_desc* d, const void* const* in, void* con
   else VX_TRY(launch_conv_fwd<16>(A, d->groups, st));
 
   const int ntiles = L.ntiles_f;
-  VX_LAUNCH(jlc_finalize_kernel, dim3(cdiv(3 * rows, 128)), dim3(128), 0, st, (const float*)part_z, 3 * rows, ntiles,
-            (float)S, d->eps, stats, (float*)nullptr, (float*)nullptr);
-  VX_TRY(check_launch("jlc_finalize_kernel"));
   prof_bytes(5.0 * sizeof(float) * (double)L.BCS);       // x, z1 z3 z5 in, o out
-  VX_LAUNCH(jlc_combine_kernel, dim3(L.nchunk, rows), dim3(256), 0, st, x, (const float*)z, (const float*)stats, o,
-            part_o, rows, S, L.chunk);
+  VX_LAUNCH(jlc_combine_kernel, dim3(L.nchunk, rows), dim3(256), 0, st, x, (const float*)z, (const float*)part_z, ntiles, stats, o,
+            part_o, (int*)(ws + L.off_cnt), aff_a, aff_c, rows, S, L.chunk, d->eps);
   VX_TRY(check_launch("jlc_combine_kernel"));
-  VX_LAUNCH(jlc_finalize_kernel, dim3(cdiv(rows, 128)), dim3(128), 0, st, (const float*)part_o, rows, L.nchunk,
-            (float)S, d->eps, stats + (size_t)2 * 3 * rows, aff_a, aff_c);
-  VX_TRY(check_launch("jlc_finalize_kernel"));
 
   // hpre = W1 IN(o) + b1
   PwBatch pb{};
@@ -1455,15 +1472,20 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
   const float* stats_o = stats + (size_t)2 * 3 * rows;
   const bool drop = d->training && d->drop_p > 0.f;
 
+  // The zeroing of every atomically accumulated buffer and the (a, c) affine of IN(o) run on the side stream from the start
+  // of the op: their consumers are the weight-gradient kernels (side stream) and the statistics kernels four launches down
+  // the main stream (side_wait below), so the data-gradient chain starts with the first contraction instead of two
+  // latency-bound helper launches.
   {
+    cudaStream_t sz = side_fork(st);
     ZeroList zl;
     zl.add(acc, (size_t)rows * 2); zl.add(acc2, (size_t)3 * rows * 2);
     zl.add(dw1, (size_t)C * CG); zl.add(dw3, (size_t)C * CG * 27); zl.add(dw5, (size_t)C * CG * 125);
     zl.add(db1, C); zl.add(db3, C); zl.add(db5, C);
     zl.add(dfw1, (size_t)eC * C); zl.add(dfb1, eC); zl.add(dfw2, (size_t)eC * C); zl.add(dfb2, C);
-    VX_TRY(zero_many(zl, st));
+    VX_TRY(zero_many(zl, sz));
+    VX_TRY(stats_to_affine(stats_o, aff_a, aff_c, rows, sz));
   }
-  VX_TRY(stats_to_affine(stats_o, aff_a, aff_c, rows, st));
 
   // dh = (W2^T (dy * mask)) * GELU'(hpre)
   {
@@ -1496,6 +1518,7 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
     p.seg[0] = PwSeg{fw1, nullptr, C, eC, dohat}; p.nseg = 1; p.Co = C; p.transposed = 1;
     VX_TRY(pw_forward(pb, st));
   }
+  side_wait(st);                                         // acc / acc2 are zero (the side stream finished that long ago)
   prof_bytes(2.0 * sizeof(float) * (double)L.BCS);
   VX_LAUNCH(jlc_bwd_a_kernel, dim3(L.nchunk, rows), dim3(256), 0, st, (const float*)dohat, o, stats_o, acc, S, L.chunk);
   VX_TRY(check_launch("jlc_bwd_a_kernel"));
@@ -1521,7 +1544,7 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
 
   ConvDgradArgs G{};
   G.gz = gz; G.dO = dO; G.w1 = w1; G.w3 = w3; G.w5 = w5; G.dx = dx;
-  G.B = d->B; G.C = C; G.D = d->D; G.H = d->H; G.W = d->W; G.t = L.tf;
+  G.B = d->B; G.C = C; G.D = d->D; G.H = d->H; G.W = d->W; G.t = L.td;
   prof_bytes(5.0 * sizeof(float) * (double)L.BCS);       // gz(3), dO in, dx out
   prof_flops(2.0 * 153.0 * (C / d->groups) * (double)L.BCS);
   if (L.small) {

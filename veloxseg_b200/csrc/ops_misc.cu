@@ -175,8 +175,9 @@ extern "C" int vx_mixer_bwd(const vx_mixer_desc* d, const void* const* in, void*
   float* dW = (float*)out[M];
   float* db = (float*)out[M + 1];
   float* dt = (float*)workspace;
+  // dW / db are accumulated by the weight-gradient kernel on the side stream only: they are zeroed there
+  { ZeroList zl; zl.add(dW, (size_t)Co * K); zl.add(db, Co); VX_TRY(zero_many(zl, side_fork(st))); }
   VX_TRY(inorm_rows_bwd(dy, t, stats, nullptr, dt, d->B * Co, d->S, st));
-  { ZeroList zl; zl.add(dW, (size_t)Co * K); zl.add(db, Co); VX_TRY(zero_many(zl, st)); }
   WgBatch wb{}; wb.nprob = 1; wb.B = d->B; wb.S = d->S;
   WgProblem& w = wb.p[0];
   w.dY = dt; w.Co = Co;
@@ -328,7 +329,8 @@ extern "C" int vx_lnpw_bwd(const vx_lnpw_desc* d, const void* const* in, void* c
   float* dbeta = (float*)out[2];
   float* dW = (float*)out[3];
   float* dln = (float*)workspace;
-  { ZeroList zl; zl.add(dgamma, d->C_in); zl.add(dbeta, d->C_in); zl.add(dW, (size_t)d->C_in * d->C_out); VX_TRY(zero_many(zl, st)); }
+  // zeroed on the side stream (dW is accumulated there; dgamma / dbeta by ln_backward on the main stream after side_wait)
+  { ZeroList zl; zl.add(dgamma, d->C_in); zl.add(dbeta, d->C_in); zl.add(dW, (size_t)d->C_in * d->C_out); VX_TRY(zero_many(zl, side_fork(st))); }
   PwBatch pb{}; pb.nprob = 1; pb.B = d->B; pb.S = d->S;
   PwProblem& p = pb.p[0];
   p.src[0] = PwSrc{dy, d->C_out}; p.nsrc = 1; p.Ci = d->C_out;
@@ -344,5 +346,6 @@ extern "C" int vx_lnpw_bwd(const vx_lnpw_desc* d, const void* const* in, void* c
   LnBwdBatch B{}; B.n = 1; B.B = d->B; B.C = d->C_in; B.S = d->S;
   B.dout[0] = dln; B.xhat[0] = xhat; B.rstd[0] = rstd; B.gamma[0] = gamma; B.dx[0] = dx;
   B.dgamma[0] = dgamma; B.dbeta[0] = dbeta; B.dx_add_scale = 0.f;
+  side_wait(st);
   return ln_backward(B, st);
 }

@@ -36,26 +36,12 @@ constexpr int TC_THREADS = 256;      // two warps per TMEM lane quadrant: they a
 struct PwTcShape { int Kpad, Npad, tmem_cols; };
 
 // keep-scales (0 or 1 / (1 - p)) of the 8 channels c0 .. c0 + 7 at this thread's voxel.  `idx` = element index of (c0, voxel),
-// channels S elements apart.  Lanes 4q .. 4q + 3 hold 4 consecutive voxels = one Philox block per channel: lane (lane & 3) = i
-// computes the blocks of channels c0 + i and c0 + i + 4 and the group exchanges the scales by shuffle -- 2 Philox calls per
-// lane, not 8.  Warp-collective: every lane of the warp must call it.
+// channels S elements apart.
 VX_DEV void drop_keep8(uint64_t seed, uint32_t site, size_t idx, size_t S, int lane, float p, float inv_keep, float (&keep)[8]) {
-  const int li = lane & 3;
-  const size_t vb = idx - (size_t)li;                      // index of the group's first voxel, channel c0
-  float mine[2][4];
+  (void)lane;
+  const uint32_t key = rng_key(seed, site);
 #pragma unroll
-  for (int h2 = 0; h2 < 2; ++h2) dropout_scale4(seed, site, vb + (size_t)(li + 4 * h2) * S, p, inv_keep, mine[h2]);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    // channel j's block lives in lane (j & 3) of the group, half j >> 2; this lane needs component li of it
-    float got = 1.f;
-#pragma unroll
-    for (int comp = 0; comp < 4; ++comp) {
-      const float cand = __shfl_sync(0xffffffffu, mine[j >> 2][comp], (lane & ~3) | (j & 3));
-      if (comp == li) got = cand;
-    }
-    keep[j] = got;
-  }
+  for (int j = 0; j < 8; ++j) keep[j] = keep_from_bits(rng_word(key, idx + (size_t)j * S), p, inv_keep);
 }
 
 // The kernel body runs ONCE per thread (one 128-voxel tile per CTA), so its cost is first of all the number of distinct

@@ -285,14 +285,20 @@ constexpr int ATT_TS = 4;            // threads per attention row (the key / que
 constexpr int ATT_MAX_THREADS = 512;
 constexpr uint32_t ATT_SITE = 7;
 
-// keep-scales of 4 consecutive keys of one (window,row): one Philox call per 4 score elements
+// keep-scales of 4 consecutive keys of one (window,row)
 VX_DEV void attn_drop4(const AttnArgs& A, size_t row, int k4, float inv_keep, float (&ms)[4]) {
   const int nk4 = (A.L + 3) >> 2;
   const uint64_t soff = A.seed_dev ? (uint64_t)__ldg(A.seed_dev) : 0;
-  const uint4 r = philox4x32_call(A.seed + soff, (uint64_t)row * nk4 + k4, ATT_SITE);
+  const uint4 r = rng4(A.seed + soff, (uint64_t)row * nk4 + k4, ATT_SITE);
   const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) ms[i] = ((float)(bits[i] >> 8) * (1.0f / 16777216.0f) < A.drop_p) ? 0.f : inv_keep;
+}
+
+// keep-scale of key k of one (window,row): the same word attn_drop4 hands out for it
+VX_DEV float attn_drop1(const AttnArgs& A, uint32_t key, size_t row, int k, float inv_keep) {
+  const int nk4 = (A.L + 3) >> 2;
+  return keep_from_bits(rng_word(key, ((uint64_t)row * nk4 + (k >> 2)) * 4 + (k & 3)), A.drop_p, inv_keep);
 }
 
 // K / V / Q / dO tiles in shared memory are [row][C] with 8 floats of padding after every 4 rows: the ATT_TS threads of a
@@ -556,29 +562,14 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __g
       const int tk = r % l;
       const float* bN = A.biasN + (size_t)head * l * l + tk;       // [tq][tk]: the lanes of a warp are consecutive keys
       int iq = t % l;                                              // i % l, kept incrementally
-      // Dropout: the 4 key rows of a quad (lanes 16g + 4u + t, u = 0..3) need the same Philox block (query i, key quad)
-      // and take one component each.  The lane of role u generates the block of the u-th of the next 4 queries and the
-      // group exchanges them by shuffle: one Philox call per 4 score elements instead of one per element.
-      const int lane = tid & 31, role = (lane >> 2) & 3;
+      // Dropout: one hashed word per (query i, key r) element -- cheaper than generating quads and exchanging them by shuffle
+      const uint32_t dkey = drop ? rng_key(A.seed + (A.seed_dev ? (uint64_t)__ldg(A.seed_dev) : 0), ATT_SITE) : 0u;
 #pragma unroll 1
       for (int i0 = t; i0 < L; i0 += 4 * ATT_TS) {
-        float mine[4] = {1.f, 1.f, 1.f, 1.f};
-        if (drop) {
-          const int im = i0 + ATT_TS * role;
-          if (im < L) attn_drop4(A, wbase * L + im, r_raw >> 2, inv_keep, mine);
-        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int i = i0 + ATT_TS * u;
-          float msk = 1.f;
-          if (drop) {
-            const int srcl = (lane & 16) | (u << 2) | t;
-#pragma unroll
-            for (int comp = 0; comp < 4; ++comp) {
-              const float cand = __shfl_sync(0xffffffffu, mine[comp], srcl);
-              if (comp == role) msk = cand;
-            }
-          }
+          const float msk = (drop && i < L) ? attn_drop1(A, dkey, wbase * L + i, r_raw, inv_keep) : 1.f;
           if (i < L) {
             const float* qr = Qs + att_row(i, CQ);
             const float* gr = dOs + att_row(i, CV);
@@ -1066,7 +1057,7 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
     // table rows = prod(2n-1)
     const size_t rows = (size_t)(2 * G.n[0] - 1) * (2 * G.n[1] - 1) * (2 * G.n[2] - 1);
     zl.add(dtable, rows * G.heads);
-    VX_TRY(zero_many(zl, st));
+    VX_TRY(zero_many(zl, side_fork(st)));      // side stream: the main stream catches up with it after its first contraction
   }
   float* biasN = (float*)(ws + P.off_biasN);
   VX_LAUNCH(pwa_bias_kernel, dim3(cdiv(nbias, 256)), dim3(256), 0, st, table, index, biasT, biasN, G.heads, G.l);
@@ -1089,6 +1080,7 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
     }
     VX_TRY(pw_forward(pb, st));
   }
+  side_wait(st);       // every gradient buffer is zero from here on (nothing above touches one)
   {
     PwBatch pb{}; pb.nprob = M; pb.B = B; pb.S = S;     // dln2 = W1^T dh
     for (int m = 0; m < M; ++m) {

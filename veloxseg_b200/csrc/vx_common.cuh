@@ -141,31 +141,37 @@ VX_DEV float block_sum(float v, float* red) {
   return red[32];
 }
 
-// Counter-based RNG for dropout masks (Philox-4x32-10).  Keyed by (seed, element index): forward and backward
-// regenerate the same keep/drop decision without storing a mask.
-VX_DEV uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
-VX_DEV uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint32_t ctr_hi) {
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = ctr_hi, c3 = 0x5eed5eedu;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  uint4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3; return o;
+// Counter-based RNG for dropout masks: 32 random bits per (seed, site, element index) from an integer hash (two rounds of
+// the "lowbias32" xorshift-multiply finaliser over the element index, keyed by a hash of seed and site).  Forward and backward
+// regenerate the same keep / drop decision without storing a mask.  Round 1 used Philox-4x32-10 (145 instructions per 4
+// elements, one full call per ELEMENT in the per-element paths): the mask generation was the largest single block of issue
+// slots in the contraction kernels of levels 3-4 (profiles/r2n_step_stalls.txt: 2 500-3 600 instructions per warp for <= 20
+// MFLOP).  A dropout mask needs independence across elements and sites, not cryptographic strength: ~10 instructions per element.
+VX_DEV uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+VX_DEV uint32_t rng_key(uint64_t seed, uint32_t site) {
+  return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + site * 0x9E3779B9u + 0x85EBCA6Bu));
+}
+VX_DEV uint32_t rng_word(uint32_t key, uint64_t idx) {
+  const uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);
+  return mix32((lo * 0x9E3779B1u) ^ key ^ (hi * 0xC2B2AE35u));
 }
 #ifdef VX_EMU
 #define VX_NOINLINE
 #else
 #define VX_NOINLINE __noinline__
 #endif
-// Out-of-line copies for kernels whose code size matters (a kernel runs once per thread: unrolled call sites of the
-// 10-round Philox or of erff/expf multiply the SASS far beyond the 32 KB instruction cache and the kernel becomes
-// instruction-fetch bound -- measured: 68 % of pw_kernel's stall samples were `no_instructions` at 200 KB of SASS).
-static __device__ VX_NOINLINE uint4 philox4x32_call(uint64_t seed, uint64_t ctr_lo, uint32_t ctr_hi) {
-  return philox4x32(seed, ctr_lo, ctr_hi);
+// Out-of-line copies for kernels whose code size matters (a kernel runs once per thread: unrolled call sites of erff / expf
+// style helpers multiply the SASS beyond the 32 KB instruction cache and the kernel becomes instruction-fetch bound --
+// measured: 68 % of pw_kernel's stall samples were `no_instructions` at 200 KB of SASS).
+// the four words of elements 4 ctr .. 4 ctr + 3 (same values as rng_word element by element)
+VX_DEV uint4 rng4(uint64_t seed, uint64_t ctr, uint32_t site) {
+  const uint32_t key = rng_key(seed, site);
+  uint4 o;
+  o.x = rng_word(key, 4 * ctr); o.y = rng_word(key, 4 * ctr + 1); o.z = rng_word(key, 4 * ctr + 2); o.w = rng_word(key, 4 * ctr + 3);
+  return o;
 }
 static __device__ VX_NOINLINE float4 gelu_grad4_call(float4 x) {
   return make_float4(gelu_grad_f(x.x), gelu_grad_f(x.y), gelu_grad_f(x.z), gelu_grad_f(x.w));
@@ -176,35 +182,15 @@ static __device__ VX_NOINLINE float4 gelu4_call(float4 x) {
 VX_DEV float keep_from_bits(uint32_t bits, float p, float inv_keep) {
   return ((float)(bits >> 8) * (1.0f / 16777216.0f) < p) ? 0.f : inv_keep;
 }
-// keep-scales of the 4 consecutive elements idx .. idx+3 (same values as dropout_scale element by element): one Philox
-// block when idx is a multiple of 4, two otherwise.
-VX_DEV void dropout_scale4(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep, float (&ms)[4]) {
-  const uint4 r0 = philox4x32_call(seed, idx >> 2, site);
-  const uint32_t b0[4] = {r0.x, r0.y, r0.z, r0.w};
-  const int sh = (int)(idx & 3);
-  if (sh == 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) ms[i] = keep_from_bits(b0[i], p, inv_keep);
-  } else {
-    const uint4 r1 = philox4x32_call(seed, (idx >> 2) + 1, site);
-    const uint32_t b1[4] = {r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int q = sh + i;
-      uint32_t bits = 0;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) { if (q == t) bits = b0[t]; if (q == t + 4) bits = b1[t]; }
-      ms[i] = keep_from_bits(bits, p, inv_keep);
-    }
-  }
-}
 // keep-scale for element `idx` of dropout site `site`: 0 (dropped) or 1/(1-p).
 VX_DEV float dropout_scale(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep) {
-  const uint4 r = philox4x32_call(seed, idx >> 2, site);
-  const uint32_t sel = (uint32_t)(idx & 3);
-  const uint32_t bits = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
-  const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);      // [0,1)
-  return u < p ? 0.f : inv_keep;
+  return keep_from_bits(rng_word(rng_key(seed, site), idx), p, inv_keep);
+}
+// keep-scales of the 4 consecutive elements idx .. idx+3 (same values as dropout_scale element by element)
+VX_DEV void dropout_scale4(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep, float (&ms)[4]) {
+  const uint32_t key = rng_key(seed, site);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ms[i] = keep_from_bits(rng_word(key, idx + i), p, inv_keep);
 }
 
 // mean / rstd from partial sums laid out [row][npart][2] (sum, sumsq); n = element count behind the full row.

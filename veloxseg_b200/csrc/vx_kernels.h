@@ -59,7 +59,7 @@ VX_DEV const float* pw_w_ptr(const PwProblem& P, int co, int ci) {
 #endif
 
 #if defined(__CUDACC__) || defined(VX_EMU)
-// Out-of-line pieces of the contraction prologue / epilogue.  GELU (erff), GELU' (erff + expf) and the Philox dropout mask
+// Out-of-line pieces of the contraction prologue / epilogue.  GELU, GELU' and the dropout mask
 // are tens to hundreds of instructions each; inlined at every unrolled use they push a kernel far beyond the instruction
 // caches and it becomes fetch-bound (measured: pw_tc_kernel at 94 KB of SASS stalled 3-5 warps per issue on
 // `no_instruction`).  One shared copy per kernel instead.
@@ -135,6 +135,7 @@ void pw_wgrad_tc_set(int enabled, int min_s);             // -1 keeps a value
 // see ordinary single-stream semantics; under CUDA-graph capture the fork/join become parallel graph branches.
 // ---------------------------------------------------------------------------------------------------
 cudaStream_t side_fork(cudaStream_t main);
+void side_wait(cudaStream_t main);      // main waits for what the side stream has been given so far (stays forked)
 void side_join(cudaStream_t main);
 void side_set(int enabled);
 struct SideJoin {
