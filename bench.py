@@ -279,6 +279,7 @@ def run_ours(args, rank, world, local_rank):
             break
     # ---- second headline metric: sliding-window inference (all ranks take part)
     used_graph = ts.use_graph
+    ts.close()                   # the step graph owns the captured NCCL all-reduce: released before anything else touches the group
     del ts, model
     torch.cuda.empty_cache()
     infer = None if args.no_infer else run_infer(rank, world, dev, volume=tuple(int(v) for v in args.infer_volume.split("x")))
@@ -336,7 +337,10 @@ def run_infer(rank, world, dev, reps=3, volume=(320, 320, 256)):
     roi, sw = cfg["input_size"], 4
     pred = GraphedPredictor(model, sw, vol_shape[1], roi, dev)
     nwin = len(window_starts(vol_shape[2:], roi, TRAIN["sw_overlap"]))
-    sharded_io = os.environ.get("VX_INFER_IO", "replicated") == "sharded"
+    # default: sharded IO (1/world of the host volume per rank + NVLink all-gather, reduce-scatter of the partial sums, label
+    # gather) -- measured 13.5 vs 26.8 ms/volume at 2 GPUs (profiles/r2v_*_2gpu.log); VX_INFER_IO=replicated keeps the
+    # round-1 path (every rank copies the whole volume, all-reduce of the logit sums) for A/B runs
+    sharded_io = os.environ.get("VX_INFER_IO", "sharded") == "sharded"
     seg_h = torch.zeros(vol_shape[2:], dtype=torch.uint8).pin_memory()
     times = []
     for i in range(reps + 1):
@@ -344,7 +348,7 @@ def run_infer(rank, world, dev, reps=3, volume=(320, 320, 256)):
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        if sharded_io:                                              # opt-in (VX_INFER_IO=sharded), see sliding_window_labels
+        if sharded_io:                                              # see inference.sliding_window_labels
             seg = sliding_window_labels(vol_h, pred, roi, dev, sw_batch_size=sw, overlap=TRAIN["sw_overlap"], out_host=seg_h)
             seg = seg_h if seg is None else seg                     # ranks other than 0 hold no result
         else:

@@ -283,6 +283,19 @@ class TrainStep:
         flat.div_(self.world)
         torch._foreach_copy_(grads, [f.view_as(g) for f, g in zip(flat.split([g.numel() for g in grads]), grads)])
 
+    def close(self):
+        """Releases the captured graphs.  With world > 1 the step graph holds the captured NCCL all-reduce: release it (or drop
+        the TrainStep) BEFORE `dist.destroy_process_group()`, which otherwise waits on the communicator the graph still owns
+        (observed as a hang at interpreter exit in tests/dp_worker.py on 2 GPUs)."""
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        for name in ("_graph", "_graph_b"):
+            g = getattr(self, name, None)
+            if g is not None:
+                g.reset()
+            setattr(self, name, None)
+        self._staged = None
+
     def set_lr(self, lr: float):
         if isinstance(self.opt, VxAdamW):
             self.opt.set_lr(lr)
