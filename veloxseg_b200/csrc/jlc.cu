@@ -13,7 +13,7 @@
 //   jlc_conv_dgrad_kernel transposed (flipped-weight) correlation of the three branch gradients into dx.
 //   jlc_conv_wgrad_kernel per-tile weight-gradient partials, thread = (ci, dz, dy) x 4 output channels with the
 //                         5 (or 3, 1) dx taps in registers; folded with fp32 atomics.
-//   jlc_bwd_{a,b,c}       element-wise InstanceNorm / GELU backward with block-level partial reductions.
+//   jlc_bwd_abc_kernel    element-wise InstanceNorm / GELU backward: one CTA per (b, channel) row, three block reductions.
 // The channel_conv FFN runs on the generic channel-contraction kernels in pointwise.cu.
 #include "vx_kernels.h"
 
@@ -684,43 +684,59 @@ __global__ void __launch_bounds__(256) jlc_combine_kernel(const float* __restric
 // ---------------------------------------------------------------------------------------------------
 // backward element-wise stages
 // ---------------------------------------------------------------------------------------------------
-// a: acc[row] += (sum dohat, sum dohat * ohat)
-__global__ void __launch_bounds__(256) jlc_bwd_a_kernel(const float* __restrict__ dohat, const float* __restrict__ o,
-                                                        const float* __restrict__ stats_o, float* __restrict__ acc,
-                                                        int S, int chunk) {
-  __shared__ float red[33];
-  const int row = blockIdx.y;
-  const float mean = stats_o[2 * row], rstd = stats_o[2 * row + 1];
-  const size_t base = (size_t)row * S;
-  const int lo = blockIdx.x * chunk, hi = min(S, lo + chunk);
-  float s1 = 0.f, s2 = 0.f;
-  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const float g = dohat[base + i];
-    s1 += g; s2 = fmaf(g, (o[base + i] - mean) * rstd, s2);
+// a + b + c in one launch (round 2): a CTA owns one whole (b, channel) row, so the three dependent row reductions
+// (sum dohat / dohat ohat -> dO and the six branch sums -> gz) are block reductions in a fixed order instead of three launches
+// with global atomics in between.  The row is re-read from L1 / L2 between the phases (the element-wise work is a few hundred
+// KB per CTA); the sums no longer depend on the arrival order of atomics, i.e. the backward is run-to-run deterministic here.
+template <int N>
+VX_DEV void block_sum_n(float (&v)[N], float* red /* [N][33] */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) red[k * 33 + w] = v[k];
   }
-  s1 = block_sum(s1, red);
-  s2 = block_sum(s2, red);
-  if (threadIdx.x == 0) { atomicAdd(acc + 2 * row, s1); atomicAdd(acc + 2 * row + 1, s2); }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      float t = lane < nw ? red[k * 33 + lane] : 0.f;
+      t = warp_sum(t);
+      if (lane == 0) red[k * 33 + 32] = t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) v[k] = red[k * 33 + 32];
 }
 
-// b: dO = dy + rstd_o (dohat - m1 - ohat m2);  acc2[k][row] += (sum g_k, sum g_k zhat_k), g_k = dO * GELU'(zhat_k)
-__global__ void __launch_bounds__(256) jlc_bwd_b_kernel(const float* __restrict__ dy, const float* __restrict__ dohat,
-                                                        const float* __restrict__ o, const float* __restrict__ z,
-                                                        const float* __restrict__ stats, const float* __restrict__ acc,
-                                                        float* __restrict__ dO, float* __restrict__ acc2, int rows,
-                                                        int S, int chunk) {
-  __shared__ float red[33];
-  const int row = blockIdx.y;
-  const size_t RS = (size_t)rows * S;
+__global__ void __launch_bounds__(1024) jlc_bwd_abc_kernel(const float* __restrict__ dy, const float* __restrict__ dohat,
+                                                           const float* __restrict__ o, const float* __restrict__ z,
+                                                           const float* __restrict__ stats, float* __restrict__ dO,
+                                                           float* __restrict__ gz, int rows, int S) {
+  __shared__ float red[6 * 33];
+  const int row = blockIdx.x;
+  const size_t RS = (size_t)rows * S, base = (size_t)row * S;
   const float mo = stats[2 * (3 * rows + row)], ro = stats[2 * (3 * rows + row) + 1];
-  const float m1 = acc[2 * row] / (float)S, m2 = acc[2 * row + 1] / (float)S;
   float m[3], r[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) { m[k] = stats[2 * (k * rows + row)]; r[k] = stats[2 * (k * rows + row) + 1]; }
-  const size_t base = (size_t)row * S;
-  const int lo = blockIdx.x * chunk, hi = min(S, lo + chunk);
-  float s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f};
-  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+  const float invS = 1.0f / (float)S;
+  // a: (sum dohat, sum dohat * ohat)
+  float a[2] = {0.f, 0.f};
+#pragma unroll 4
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    const float g = dohat[base + i];
+    a[0] += g; a[1] = fmaf(g, (o[base + i] - mo) * ro, a[1]);
+  }
+  block_sum_n<2>(a, red);
+  const float m1 = a[0] * invS, m2 = a[1] * invS;
+  // b: dO = dy + rstd_o (dohat - m1 - ohat m2);  (sum g_k, sum g_k zhat_k), g_k = dO * GELU'(zhat_k)
+  float sb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
     const float oh = (o[base + i] - mo) * ro;
     const float d = dy[base + i] + ro * (dohat[base + i] - m1 - oh * m2);
     dO[base + i] = d;
@@ -728,39 +744,19 @@ __global__ void __launch_bounds__(256) jlc_bwd_b_kernel(const float* __restrict_
     for (int k = 0; k < 3; ++k) {
       const float zh = (z[k * RS + base + i] - m[k]) * r[k];
       const float g = d * gelu_grad_f(zh);
-      s1[k] += g; s2[k] = fmaf(g, zh, s2[k]);
+      sb[2 * k] += g; sb[2 * k + 1] = fmaf(g, zh, sb[2 * k + 1]);
     }
   }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const float t1 = block_sum(s1[k], red), t2 = block_sum(s2[k], red);
-    if (threadIdx.x == 0) {
-      atomicAdd(acc2 + 2 * ((size_t)k * rows + row), t1);
-      atomicAdd(acc2 + 2 * ((size_t)k * rows + row) + 1, t2);
-    }
-  }
-}
-
-// c: gz_k = rstd_k (g_k - mean(g_k) - zhat_k mean(g_k zhat_k))
-__global__ void __launch_bounds__(256) jlc_bwd_c_kernel(const float* __restrict__ dO, const float* __restrict__ z,
-                                                        const float* __restrict__ stats, const float* __restrict__ acc2,
-                                                        float* __restrict__ gz, int rows, int S) {
-  const int row = blockIdx.y;
-  const size_t RS = (size_t)rows * S;
-  float m[3], r[3], m1[3], m2[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    m[k] = stats[2 * (k * rows + row)]; r[k] = stats[2 * (k * rows + row) + 1];
-    m1[k] = acc2[2 * ((size_t)k * rows + row)] / (float)S; m2[k] = acc2[2 * ((size_t)k * rows + row) + 1] / (float)S;
-  }
-  const size_t base = (size_t)row * S;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
+  block_sum_n<6>(sb, red);
+  // c: gz_k = rstd_k (g_k - mean(g_k) - zhat_k mean(g_k zhat_k)); every thread re-reads the dO values it wrote itself
+#pragma unroll 2
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
     const float d = dO[base + i];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const float zh = (z[k * RS + base + i] - m[k]) * r[k];
       const float g = d * gelu_grad_f(zh);
-      gz[k * RS + base + i] = r[k] * (g - m1[k] - zh * m2[k]);
+      gz[k * RS + base + i] = r[k] * (g - sb[2 * k] * invS - zh * sb[2 * k + 1] * invS);
     }
   }
 }
@@ -1467,19 +1463,16 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
   float* dohat = (float*)(ws + L.off_dohat);
   float* dO = (float*)(ws + L.off_dO);
   float* gz = (float*)(ws + L.off_gz);
-  float* acc = (float*)(ws + L.off_acc);
-  float* acc2 = (float*)(ws + L.off_acc2);
   const float* stats_o = stats + (size_t)2 * 3 * rows;
   const bool drop = d->training && d->drop_p > 0.f;
 
   // The zeroing of every atomically accumulated buffer and the (a, c) affine of IN(o) run on the side stream from the start
   // of the op: their consumers are the weight-gradient kernels (side stream) and the statistics kernels four launches down
   // the main stream (side_wait below), so the data-gradient chain starts with the first contraction instead of two
-  // latency-bound helper launches.
+  // latency-bound helper launches.  (Every consumer of these buffers runs on the side stream.)
   {
     cudaStream_t sz = side_fork(st);
     ZeroList zl;
-    zl.add(acc, (size_t)rows * 2); zl.add(acc2, (size_t)3 * rows * 2);
     zl.add(dw1, (size_t)C * CG); zl.add(dw3, (size_t)C * CG * 27); zl.add(dw5, (size_t)C * CG * 125);
     zl.add(db1, C); zl.add(db3, C); zl.add(db5, C);
     zl.add(dfw1, (size_t)eC * C); zl.add(dfb1, eC); zl.add(dfw2, (size_t)eC * C); zl.add(dfb2, C);
@@ -1518,18 +1511,14 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
     p.seg[0] = PwSeg{fw1, nullptr, C, eC, dohat}; p.nseg = 1; p.Co = C; p.transposed = 1;
     VX_TRY(pw_forward(pb, st));
   }
-  side_wait(st);                                         // acc / acc2 are zero (the side stream finished that long ago)
-  prof_bytes(2.0 * sizeof(float) * (double)L.BCS);
-  VX_LAUNCH(jlc_bwd_a_kernel, dim3(L.nchunk, rows), dim3(256), 0, st, (const float*)dohat, o, stats_o, acc, S, L.chunk);
-  VX_TRY(check_launch("jlc_bwd_a_kernel"));
-  prof_bytes(7.0 * sizeof(float) * (double)L.BCS);       // dy, dohat, o, z(3) in, dO out
-  VX_LAUNCH(jlc_bwd_b_kernel, dim3(L.nchunk, rows), dim3(256), 0, st, dy, (const float*)dohat, o, z, stats,
-            (const float*)acc, dO, acc2, rows, S, L.chunk);
-  VX_TRY(check_launch("jlc_bwd_b_kernel"));
-  prof_bytes(7.0 * sizeof(float) * (double)L.BCS);       // dO, z(3) in, gz(3) out
-  VX_LAUNCH(jlc_bwd_c_kernel, dim3(cdiv(S, 1024), rows), dim3(256), 0, st, (const float*)dO, z, stats,
-            (const float*)acc2, gz, rows, S);
-  VX_TRY(check_launch("jlc_bwd_c_kernel"));
+  {
+    // one CTA per row: 32 threads per ~4 elements, at most 1024
+    int T = ((S + 3) / 4 + 31) & ~31;
+    T = T < 32 ? 32 : (T > 1024 ? 1024 : T);
+    prof_bytes(10.0 * sizeof(float) * (double)L.BCS);    // dy, dohat, o, z(3) in, dO + gz(3) out
+    VX_LAUNCH(jlc_bwd_abc_kernel, dim3(rows), dim3(T), 0, st, dy, (const float*)dohat, o, z, stats, dO, gz, rows, S);
+    VX_TRY(check_launch("jlc_bwd_abc_kernel"));
+  }
 
   // weight gradients first, on the side stream (forked here, after gz is complete): dgrad then runs beside them
   cudaStream_t st_w = side_fork(st);

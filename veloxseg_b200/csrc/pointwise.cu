@@ -5,6 +5,7 @@
 //                load/store is a 128-byte-coalesced run along the voxel axis.
 // pw_wgrad     : split-K over voxel chunks; chunk tiles are transposed through shared memory and reduced as
 //                4x4 register outer products, partial results are folded with fp32 atomics.
+#include <cstdlib>
 #include "vx_kernels.h"
 
 #ifdef VX_EMU
@@ -927,9 +928,90 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __grid_constant__ LnB
   }
 }
 
+// Narrow-channel variant (C = 8 / 16: level 1 of every configuration, where S is largest).  The wide kernel above spreads the
+// channels of a voxel over 8 warps and meets in shared memory: two barriers and two dependent load rounds per 32-voxel
+// block, walked serially -- ncu: 11 warps per issue stalled on the long scoreboard, 16 % issue-active, 28 us per launch
+// (profiles/r2n_step_stalls.txt).  Here a thread owns ALL channels of its voxel: 2 C independent coalesced loads in flight,
+// the per-voxel means are plain register sums (no shared memory, no barrier), dgamma / dbeta partials stay in registers over
+// the warp's voxel blocks and leave through one warp reduction per channel at the end.
+template <int C>
+__global__ void __launch_bounds__(256) ln_bwd_narrow_kernel(const __grid_constant__ LnBwdBatch L, int bpw) {
+  const int t = blockIdx.z, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int S = L.S;
+  __shared__ float sg[8][2 * C];
+  __shared__ float gam[C];
+  if (threadIdx.x < C) gam[threadIdx.x] = __ldg(L.gamma[t] + threadIdx.x);
+  __syncthreads();
+  float ag[C], ab[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) { ag[c] = 0.f; ab[c] = 0.f; }
+  const int nblk = (S + 31) >> 5;
+  const int blk0 = (blockIdx.x * 8 + w) * bpw;
+#pragma unroll 1
+  for (int j = 0; j < bpw; ++j) {
+    const int blk = blk0 + j;
+    if (blk >= nblk) break;                                   // warp-uniform
+    const int v = blk * 32 + lane;
+    const bool ok = v < S;
+    const size_t off = (size_t)b * C * S + (ok ? v : 0);
+    const float* dout = L.dout[t] + off;
+    const float* xh = L.xhat[t] + off;
+    float d[C], h[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { d[c] = ok ? __ldg(dout + (size_t)c * S) : 0.f; h[c] = ok ? __ldg(xh + (size_t)c * S) : 0.f; }
+    const float rstd = ok ? L.rstd[t][(size_t)b * S + v] : 0.f;
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float g = gam[c] * d[c];
+      m1 += g; m2 = fmaf(g, h[c], m2);
+      ag[c] = fmaf(d[c], h[c], ag[c]); ab[c] += d[c];
+    }
+    m1 *= 1.0f / (float)C; m2 *= 1.0f / (float)C;
+    if (ok) {
+      float* dx = L.dx[t] + off;
+      const float* add = L.dx_add[t] ? L.dx_add[t] + off : nullptr;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float r = rstd * (gam[c] * d[c] - m1 - h[c] * m2);
+        if (add) r = fmaf(L.dx_add_scale, __ldg(add + (size_t)c * S), r);
+        dx[(size_t)c * S] = r;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float a = warp_sum(ag[c]), bb = warp_sum(ab[c]);
+    if (lane == 0) { sg[w][c] = a; sg[w][C + c] = bb; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * C) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += sg[k][threadIdx.x];
+    float* dst = threadIdx.x < C ? L.dgamma[t] : L.dbeta[t];
+    if (dst) atomicAdd(dst + (threadIdx.x < C ? threadIdx.x : threadIdx.x - C), sum);
+  }
+}
+
 int ln_backward(const LnBwdBatch& L, cudaStream_t stream) {
   if (L.n <= 0) return VX_OK;
   prof_bytes(4.0 * L.n * L.B * (double)L.S * (3.0 * L.C + 1 + (L.dx_add[0] ? L.C : 0)));
+  static const bool narrow_on = !(getenv("VX_LN_NARROW") && atoi(getenv("VX_LN_NARROW")) == 0);      // A/B probe
+  if (narrow_on && (L.C == 8 || L.C == 16) && L.S >= 1024) {
+    const int nblk = cdiv(L.S, 32);
+    // 32-voxel blocks per warp: as many as leave >= one CTA per SM (VX_LN_BPW overrides for probes; the block count makes no
+    // measurable difference between 112 and 432 CTAs -- isolated: 13.3 us against 30.4 us for the wide kernel at level 1,
+    // profiles/r2z_ln_narrow.digest.txt / r2z_ln_wide.digest.txt)
+    int bpw = 1;
+    while (bpw < 8 && (long long)cdiv(nblk, 8 * bpw * 2) * L.B * L.n >= kSMs) bpw *= 2;
+    if (const char* e = getenv("VX_LN_BPW")) bpw = atoi(e) > 0 ? atoi(e) : bpw;
+    const dim3 grid(cdiv(nblk, 8 * bpw), L.B, L.n);
+    if (L.C == 16) VX_LAUNCH(ln_bwd_narrow_kernel<16>, grid, dim3(256), 0, stream, L, bpw);
+    else VX_LAUNCH(ln_bwd_narrow_kernel<8>, grid, dim3(256), 0, stream, L, bpw);
+    return check_launch("ln_bwd_narrow_kernel");
+  }
   int groups = 1;      // 32-voxel blocks per CTA: as many as leave >= ~2 CTAs per SM
   while (groups < 8 && (long long)cdiv(L.S, 32 * groups * 2) * L.B * L.n >= 2 * kSMs) groups *= 2;
   VX_LAUNCH(ln_bwd_kernel, dim3(cdiv(L.S, 32 * groups), L.B, L.n), dim3(256), 0, stream, L, groups);

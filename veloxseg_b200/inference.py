@@ -190,20 +190,23 @@ class GraphedPredictor:
 
     def __init__(self, model: torch.nn.Module, batch: int, channels: int, roi_size: Sequence[int], device):
         self.model = model.eval()
-        self.x = torch.zeros((batch, channels) + tuple(roi_size), device=device)
-        side = torch.cuda.Stream(device=device)
-        side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side), torch.no_grad():
-            for _ in range(2):
-                self.model(self.x)
-        torch.cuda.current_stream(device).wait_stream(side)
-        torch.cuda.synchronize(device)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph), torch.no_grad():
-            self.y = _logits(self.model(self.x))
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):             # the library launches on the current device
+            self.x = torch.zeros((batch, channels) + tuple(roi_size), device=device)
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(2):
+                    self.model(self.x)
+            torch.cuda.current_stream(device).wait_stream(side)
+            torch.cuda.synchronize(device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph), torch.no_grad():
+                self.y = _logits(self.model(self.x))
 
     def __call__(self, win: torch.Tensor) -> torch.Tensor:
         k = win.shape[0]
-        self.x[:k].copy_(win)
-        self.graph.replay()
+        with torch.cuda.device(self.device):
+            self.x[:k].copy_(win)
+            self.graph.replay()
         return self.y[:k]

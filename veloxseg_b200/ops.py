@@ -71,6 +71,12 @@ def advance_seed(device):
 
 
 def _stream(t: Tensor) -> int:
+    """Current stream of the tensor's device.  The library launches on the CURRENT CUDA device, so the tensor's device has to
+    be the current one: a mismatch is reported here instead of surfacing as an invalid-resource-handle launch error."""
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"veloxseg_b200: tensors live on {t.device} but the current CUDA device is "
+                           f"cuda:{torch.cuda.current_device()} -- wrap the call in `with torch.cuda.device({t.device.index}):` "
+                           "(TrainStep.step and GraphedPredictor do this themselves)")
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
@@ -404,6 +410,9 @@ _L.define("lnpw_bwd(Tensor dy, Tensor xhat, Tensor rstd, Tensor ln_w, Tensor ln_
 def _cuda(fn):
     def run(*a, **k):
         first = a[0][0] if isinstance(a[0], (list, tuple)) else a[0]
+        if first.device.index != torch.cuda.current_device():       # device guard (the library launches on the current device)
+            with torch.cuda.device(first.device):
+                return fn(_lib.get_lib(), _stream(first), *a, **k)
         return fn(_lib.get_lib(), _stream(first), *a, **k)
     return run
 
