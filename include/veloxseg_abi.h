@@ -56,11 +56,15 @@ const char* vx_last_error_string(void);
  *                           activation to bfloat16; statistics, norms, softmax, losses, optimiser stay fp32.  Storage stays fp32.
  *   VX_OPT_JLC_KS           reduction slices of the level-1/2 JLC convolution kernels: -1 (default) automatic, 0 / 1 off (one
  *                           thread per 4 voxels x 4 channels, 4-channel staging chunks), 2 / 4 / 8 forced (A/B probe).
+ *   VX_OPT_PDL              0 (default): plain stream-ordered launches.  1: every kernel is launched with programmatic dependent
+ *                           launch allowed (cudaLaunchAttributeProgrammaticStreamSerialization; every kernel starts with
+ *                           griddepcontrol.wait + griddepcontrol.launch_dependents), also as programmatic edges inside a captured
+ *                           CUDA graph.  Measured 3-5 % SLOWER on the train step (profiles/r3a_pdl_ab.txt): A/B switch only.
  *   VX_OPT_CONV3_TRACE      0 (default).  1: CTA 0 of the dense-convolution forward kernel records clock64() at its phase
  *                           boundaries; vx_conv3_trace() copies the 64 stamps out (developer diagnostics, tools/conv3_phases.py). */
 enum { VX_OPT_PW_TENSOR_CORES = 1, VX_OPT_PW_SMALL_MAX_S = 2, VX_OPT_PW_TC_MIN_S = 3, VX_OPT_JLC_TILE_FWD = 4,
        VX_OPT_JLC_TILE_WGRAD = 5, VX_OPT_JLC_SMALL_MAX_S = 8, VX_OPT_WGRAD_TC_MIN_S = 9, VX_OPT_SIDE_WGRAD = 10,
-       VX_OPT_CONV3_TRACE = 13, VX_OPT_PRECISION = 14, VX_OPT_JLC_KS = 15 };
+       VX_OPT_CONV3_TRACE = 13, VX_OPT_PRECISION = 14, VX_OPT_JLC_KS = 15, VX_OPT_PDL = 16 };
 int vx_set_option(int option, int value);
 int vx_conv3_trace(long long* out64, int n);
 /* Measurement helpers (bench.py): kind 0 = fp32 FMA throughput probe (2 * 8 * 32 * iters * 148 * 8 * 256 flops per launch,

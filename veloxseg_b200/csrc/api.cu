@@ -15,6 +15,10 @@ static thread_local char g_err[512] = "";
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
+static int g_pdl = 0;      // measured slower when on (see vx_common.cuh): opt-in
+int pdl_enabled() { return g_pdl; }
+void pdl_set(int on) { g_pdl = on ? 1 : 0; }
+
 static int g_precision = 0;
 int precision_mode() { return g_precision; }
 void precision_set(int m) { g_precision = m ? 1 : 0; }
@@ -222,6 +226,11 @@ extern "C" int vx_set_option(int option, int value) {
   if (option == VX_OPT_JLC_KS) { vx::jlc_set_ks(value); return VX_OK; }
   if (option == VX_OPT_CONV3_TRACE) { vx::conv3_trace_set(value); return VX_OK; }
   if (option == VX_OPT_PRECISION) { vx::precision_set(value); return VX_OK; }
+#ifndef VX_EMU
+  if (option == VX_OPT_PDL) { vx::pdl_set(value); return VX_OK; }
+#else
+  if (option == VX_OPT_PDL) return VX_OK;
+#endif
   if (option == VX_OPT_SIDE_WGRAD) { vx::side_set(value ? 1 : 0); return VX_OK; }
 #ifndef VX_EMU
   if (option == VX_OPT_PW_TENSOR_CORES) { vx::pw_tc_set(value ? 1 : 0); vx::pw_wgrad_tc_set(value ? 1 : 0, -1); return VX_OK; }

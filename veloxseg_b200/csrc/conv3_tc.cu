@@ -71,6 +71,7 @@ VX_DEV void c3_split4p(int prec, const float4 v, float4& hi, float4& lo) {
 // forward image  [co tile][group g = dz*3+dy][hi|lo][step s = dx*2 + ci octet][NT*8]: element (n, k) of a step at
 //   (n/8)*64 + (k/4)*32 + (n%8)*4 + k%4  (K-major B operand: LBO 128 B between the k halves, SBO 256 B between 8-row groups)
 __global__ void conv3_prep_fwd_kernel(const float* __restrict__ w, float* __restrict__ img, int Cout, int NT, int ntile, int prec) {
+  VX_PDL_ENTRY();
   const int per_tile = 9 * 6 * NT * 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ntile * per_tile) return;
@@ -89,6 +90,7 @@ __global__ void conv3_prep_fwd_kernel(const float* __restrict__ w, float* __rest
 }
 // data-gradient image  [pass c = co octet][tz][hi|lo][144 x 8]: row n = (ty*3+tx)*16 + ci, k = co - 8c
 __global__ void conv3_prep_dgrad_kernel(const float* __restrict__ w, float* __restrict__ img, int Cout, int prec) {
+  VX_PDL_ENTRY();
   const int npass = Cout / 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npass * 3 * 144 * 8) return;
@@ -113,6 +115,7 @@ struct Conv3FwdArgs {
 };
 
 __global__ void __launch_bounds__(C3_THREADS) conv3_fwd_tc_kernel(const __grid_constant__ Conv3FwdArgs A) {
+  VX_PDL_ENTRY();
   const int tile = blockIdx.x, nt_i = blockIdx.y, b = blockIdx.z;
   const int ty_i = tile % A.nty, tz_i = tile / A.nty;
   const int z0 = tz_i * A.ZR, y0 = ty_i * A.TY;
@@ -340,6 +343,7 @@ struct Conv3WgradArgs {
 VX_DEV int c3w_cpitch(int W) { return (3 * (C3W_RY + 2) * (W + 2)) | 1; }
 
 __global__ void __launch_bounds__(C3_THREADS) conv3_wgrad_tc_kernel(const __grid_constant__ Conv3WgradArgs A) {
+  VX_PDL_ENTRY();
   const int D = A.D, H = A.H, W = A.W, Cout = A.Cout;
   const int PXW = W + 2, RYP = C3W_RY + 2;
   const int CP = c3w_cpitch(W);
@@ -530,6 +534,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_wgrad_tc_kernel(const __grid
 
 // dW[co][ci][tap] = sum over partial tiles, in tile order (deterministic); db[co] from column 432
 __global__ void conv3_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int Cout, float* __restrict__ dw, float* __restrict__ db) {
+  VX_PDL_ENTRY();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Cout * 433) return;
   const int co = i / 433, n = i % 433;
@@ -566,6 +571,7 @@ constexpr int C3D_N = 144;
 constexpr int C3D_WF = 3 * 2 * C3D_N * 8;             // floats of one pass of the weight image: [tz][hi|lo][144 x 8]
 
 __global__ void __launch_bounds__(C3_THREADS) conv3_dgrad_tc_kernel(const __grid_constant__ Conv3DgradArgs A) {
+  VX_PDL_ENTRY();
   const int ty_i = blockIdx.x % A.nty, z = blockIdx.x / A.nty, b = blockIdx.y;
   const int y0 = ty_i * A.TY;
   const int D = A.D, H = A.H, W = A.W, Cout = A.Cout;

@@ -34,6 +34,7 @@ struct ConvGeo {
 template <int CT, int KW>      // KW = kernel width known at compile time, 0 = runtime
 __global__ void __launch_bounds__(256) conv_strided_kernel(ConvGeo G, const float* __restrict__ X, const float* __restrict__ Wt,
                                                            const float* __restrict__ bias, float* __restrict__ Y, int rchunk) {
+  VX_PDL_ENTRY();
   VX_DYN_SMEM(float, ws);                              // [rchunk][k][CT], reused as [KS][32][CT] for the final fold
   const int k = KW ? KW : G.k, k2 = k * k, k3 = k2 * k;
   const int lane = threadIdx.x, ks = threadIdx.y, KS = blockDim.y, vw = threadIdx.z, VW = blockDim.z;
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(256) conv_strided_kernel(ConvGeo G, const floa
 template <int CT>
 __global__ void __launch_bounds__(256) conv_scatter_kernel(ConvGeo G, const float* __restrict__ X, const float* __restrict__ Wt,
                                                            const float* __restrict__ bias, float* __restrict__ Y, int ochunk) {
+  VX_PDL_ENTRY();
   VX_DYN_SMEM(float, ws);                              // [ochunk][k3][CT], reused for the final fold
   const int k = G.k, k2 = k * k, k3 = k2 * k, s = G.s;
   const int lane = threadIdx.x, ks = threadIdx.y, KS = blockDim.y, vw = threadIdx.z, VW = blockDim.z;
@@ -205,6 +207,7 @@ __global__ void __launch_bounds__(256) conv_scatter_kernel(ConvGeo G, const floa
 constexpr int CW_CT = 16;
 __global__ void __launch_bounds__(128) conv_wgrad_kernel(ConvGeo G, const float* __restrict__ Gc, const float* __restrict__ F,
                                                          float* __restrict__ dW, float* __restrict__ db, int vchunk) {
+  VX_PDL_ENTRY();
   VX_DYN_SMEM(float, gs);                              // [vchunk][16] gradients, then [vchunk] int4 (batch offset, z, y, x origins)
   int4* vo = reinterpret_cast<int4*>(gs + (size_t)vchunk * CW_CT);
   const int k = G.k, k2 = k * k, k3 = k2 * k;
@@ -273,6 +276,7 @@ __global__ void __launch_bounds__(128) conv_wgrad_kernel(ConvGeo G, const float*
 
 // out[c] = sum over (b, s) of X[b, c, s]  (bias gradient of a transposed convolution): one CTA per channel, fixed fold order
 __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ X, float* __restrict__ out, int B, int C, int S) {
+  VX_PDL_ENTRY();
   __shared__ float red[33];
   const int c = blockIdx.x;
   float acc = 0.f;
@@ -454,7 +458,8 @@ static int pw_conv_bwd(const vx_conv_desc* d, const float* dy, const float* x, c
     if (rc != VX_OK) return rc;
     g = (const float*)ws; Cg = 8 * d->C_out;
   }
-  { ZeroList zl; zl.add(dw, (size_t)d->C_in * Cg); if (db && !d->transposed) zl.add(db, d->C_out); const int rc = zero_many(zl, st); if (rc != VX_OK) return rc; }
+  // accumulated by the weight-gradient kernel on the side stream only: zeroed there
+  { ZeroList zl; zl.add(dw, (size_t)d->C_in * Cg); if (db && !d->transposed) zl.add(db, d->C_out); const int rc = zero_many(zl, side_fork(st)); if (rc != VX_OK) return rc; }
   WgBatch wb{}; wb.nprob = 1; wb.B = d->B; wb.S = S;
   WgProblem& q = wb.p[0];
   if (!d->transposed) {      // dW (C_out, C_in) = dy x^T, db = sum dy

@@ -6,6 +6,7 @@ namespace vx {
 
 // 8 independent FMA chains per thread, `iters` x 32 FMAs each chain step: 2 * 8 * 32 * iters flops per thread
 __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float* __restrict__ out) {
+  VX_PDL_ENTRY();
   float a[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = 1.0f + 1e-3f * (float)(threadIdx.x + j);
@@ -26,6 +27,7 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float* __restr
 
 // 3-register form: acc = x * w + acc with every operand a run-time register (what a convolution inner loop issues)
 __global__ void __launch_bounds__(256) fma3_peak_kernel(int iters, float* __restrict__ out) {
+  VX_PDL_ENTRY();
   float a[8], x[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = 1e-3f * (float)(threadIdx.x + j); x[j] = out[1 + (threadIdx.x + j) % 3]; }
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(256) fma3_peak_kernel(int iters, float* __rest
 #ifndef VX_EMU
 // packed form: fma.rn.f32x2 (FFMA2), two fp32 FMAs per instruction on 64-bit register pairs
 __global__ void __launch_bounds__(256) fma2_peak_kernel(int iters, float* __restrict__ out) {
+  VX_PDL_ENTRY();
   unsigned long long a[8], x[8], w;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -73,7 +76,8 @@ __global__ void __launch_bounds__(256) fma2_peak_kernel(int iters, float* __rest
 }
 #endif
 
-__global__ void null_kernel(int) {}
+__global__ void null_kernel(int) {
+  VX_PDL_ENTRY();}
 
 }  // namespace vx
 

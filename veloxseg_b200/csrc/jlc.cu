@@ -133,6 +133,7 @@ struct ConvFwdArgs {
 
 template <int CG, int VX>
 __global__ void __launch_bounds__(256) jlc_conv_fwd_kernel(const __grid_constant__ ConvFwdArgs A) {
+  VX_PDL_ENTRY();
   constexpr int NCB = CG / 4;
   const int g = blockIdx.y, b = blockIdx.z;
   const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;
@@ -305,6 +306,7 @@ template <int CG> struct JlcKs { static constexpr int MAXT = CG == 4 ? 384 : 576
 
 template <int CG, int VX>
 __global__ void __launch_bounds__(JlcKs<CG>::MAXT, JlcKs<CG>::MINB) jlc_conv_fwd_ks_kernel(const __grid_constant__ ConvFwdArgs A, int KS) {
+  VX_PDL_ENTRY();
   constexpr int NCB = CG / 4;
   const int g = blockIdx.y, b = blockIdx.z;
   const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;
@@ -514,6 +516,7 @@ static SmallGeo small_geo(int CG, int D, int H, int W) {
 template <int CG>
 __global__ void __launch_bounds__(256) jlc_conv_small_fwd_kernel(const __grid_constant__ ConvFwdArgs A,
                                                                  const __grid_constant__ SmallGeo G) {
+  VX_PDL_ENTRY();
   constexpr int NQ = CG / 4;
   const int split = blockIdx.x, g = blockIdx.y / NQ, q = blockIdx.y % NQ, b = blockIdx.z;
   const int D = A.D, H = A.H, W = A.W, C = A.C;
@@ -637,6 +640,7 @@ __global__ void __launch_bounds__(256) jlc_combine_kernel(const float* __restric
                                                           float* __restrict__ o, float* __restrict__ part_o, int* __restrict__ cnt,
                                                           float* __restrict__ aff_a, float* __restrict__ aff_c, int rows, int S,
                                                           int chunk, float eps) {
+  VX_PDL_ENTRY();
   __shared__ float red[33];
   __shared__ float mr[6];
   const int row = blockIdx.y, ck = blockIdx.x, nchunk = gridDim.x;
@@ -716,6 +720,7 @@ __global__ void __launch_bounds__(1024) jlc_bwd_abc_kernel(const float* __restri
                                                            const float* __restrict__ o, const float* __restrict__ z,
                                                            const float* __restrict__ stats, float* __restrict__ dO,
                                                            float* __restrict__ gz, int rows, int S) {
+  VX_PDL_ENTRY();
   __shared__ float red[6 * 33];
   const int row = blockIdx.x;
   const size_t RS = (size_t)rows * S, base = (size_t)row * S;
@@ -830,6 +835,7 @@ VX_DEV void dgrad_branch(const ConvDgradArgs& A, const float* __restrict__ gzk, 
 
 template <int CG, int VX>
 __global__ void __launch_bounds__(256) jlc_conv_dgrad_kernel(const __grid_constant__ ConvDgradArgs A) {
+  VX_PDL_ENTRY();
   constexpr int NCB = CG / 4;
   const int g = blockIdx.y, b = blockIdx.z;
   const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;
@@ -928,6 +934,7 @@ VX_DEV void dgrad_branch_ks(const ConvDgradArgs& A, const float* __restrict__ gz
 
 template <int CG, int VX>
 __global__ void __launch_bounds__(JlcKs<CG>::MAXT, JlcKs<CG>::MINB) jlc_conv_dgrad_ks_kernel(const __grid_constant__ ConvDgradArgs A, int KS) {
+  VX_PDL_ENTRY();
   constexpr int NCB = CG / 4;
   const int g = blockIdx.y, b = blockIdx.z;
   const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;
@@ -994,6 +1001,7 @@ __global__ void __launch_bounds__(JlcKs<CG>::MAXT, JlcKs<CG>::MINB) jlc_conv_dgr
 template <int CG>
 __global__ void __launch_bounds__(256) jlc_conv_small_dgrad_kernel(const __grid_constant__ ConvDgradArgs A,
                                                                    const __grid_constant__ SmallGeo G) {
+  VX_PDL_ENTRY();
   constexpr int NQ = CG / 4;
   const int split = blockIdx.x, g = blockIdx.y / NQ, q = blockIdx.y % NQ, b = blockIdx.z;
   const int D = A.D, H = A.H, W = A.W, C = A.C;
@@ -1153,6 +1161,7 @@ constexpr int JW_THREADS = 320;      // 280 (item, z-split) tasks per ci-chunk f
 
 template <int CG>
 __global__ void __launch_bounds__(JW_THREADS) jlc_conv_wgrad_kernel(const __grid_constant__ ConvWgradArgs A) {
+  VX_PDL_ENTRY();
   constexpr int NCB = CG / 4;
   const int g = blockIdx.y, b = blockIdx.z;
   const int TZ = A.t.TZ, TY = A.t.TY, TX = A.t.TX;

@@ -17,6 +17,7 @@ constexpr int GRAM_TV = 512;
 
 __global__ void __launch_bounds__(256) gram_partial_kernel(const float* __restrict__ x, float* __restrict__ part, int C,
                                                            int S) {
+  VX_PDL_ENTRY();
   VX_DYN_SMEM(float, sx);   // [GRAM_TV][C+1]
   const int b = blockIdx.y, ck = blockIdx.x, CP = C + 1;
   const int v0 = ck * GRAM_TV;
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(256) gram_partial_kernel(const float* __restri
 
 __global__ void gram_reduce_kernel(const float* __restrict__ part, float* __restrict__ G, int CC, int nchunk,
                                    float scale) {
+  VX_PDL_ENTRY();
   const int b = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= CC) return;
@@ -47,6 +49,7 @@ __global__ void gram_reduce_kernel(const float* __restrict__ part, float* __rest
 template <int CT>
 __global__ void __launch_bounds__(128) gram_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ x,
                                                        float* __restrict__ dx, int C, int S, float scale) {
+  VX_PDL_ENTRY();
   VX_DYN_SMEM(float, w);   // [C][C] symmetrised
   const int b = blockIdx.y;
   for (int p = threadIdx.x; p < C * C; p += blockDim.x) {
@@ -84,6 +87,7 @@ __global__ void __launch_bounds__(128) gram_bwd_kernel(const float* __restrict__
 struct SdktArgs { const float* gs; const float* gt[VX_MAX_MODAL]; float* dgt[VX_MAX_MODAL]; float* dgs; const float* dloss; float* loss; int n; int T; };
 
 __global__ void __launch_bounds__(256) sdkt_loss_fwd_kernel(const __grid_constant__ SdktArgs A) {
+  VX_PDL_ENTRY();
   __shared__ float red[33];
   float s = 0.f;
   for (int i = threadIdx.x; i < A.n; i += blockDim.x) {
@@ -95,6 +99,7 @@ __global__ void __launch_bounds__(256) sdkt_loss_fwd_kernel(const __grid_constan
 }
 
 __global__ void __launch_bounds__(256) sdkt_loss_bwd_kernel(const __grid_constant__ SdktArgs A) {
+  VX_PDL_ENTRY();
   const float k = 2.0f * A.dloss[0] / ((float)A.n * (float)A.T);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) {
     const float g = A.gs[i];

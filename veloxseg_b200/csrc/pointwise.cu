@@ -36,6 +36,7 @@ VX_DEV float pw_prologue(const PwProblem& P, float x, int b, int cg, int v, int 
 // cache is fetch-bound): staging and epilogue are ROLLED loops with a single copy of the address / prologue /
 // epilogue logic, and the epilogue reads the accumulator tile back from shared memory.
 __global__ void __launch_bounds__(PW_THREADS) pw_kernel(const __grid_constant__ PwBatch batch) {
+  VX_PDL_ENTRY();
   const int pi = blockIdx.z / batch.B, b = blockIdx.z % batch.B;
   const PwProblem& P = batch.p[pi];
   const int S = batch.S, Ci = P.Ci, Co = P.Co;
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(PW_THREADS) pw_kernel(const __grid_constant__ 
 constexpr int PWS_MAX_KS = 8;
 
 __global__ void __launch_bounds__(32 * PWS_MAX_KS) pw_small_kernel(const __grid_constant__ PwBatch batch) {
+  VX_PDL_ENTRY();
   const PwProblem& P = batch.p[blockIdx.z];
   const int S = batch.S, Co = P.Co;
   const int lane = threadIdx.x, ks = threadIdx.y, KS = blockDim.y;
@@ -396,6 +398,7 @@ constexpr int WG_THREADS = 256;
 // consecutive channels are conflict-free); when the tile block has fewer tiles than threads the voxels of a chunk are
 // split between thread groups and folded through shared memory at the end.
 __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_kernel(const __grid_constant__ WgBatch batch, int TV, int nK) {
+  VX_PDL_ENTRY();
   const WgProblem& P = batch.p[blockIdx.z];
   const int S = batch.S, B = batch.B;
   const int Co = P.Co, Ci = P.Ci;
@@ -570,6 +573,7 @@ int pw_wgrad(const WgBatch& batch, cudaStream_t main_stream) {
 __global__ void __launch_bounds__(256) inorm_rows_fwd_kernel(const float* __restrict__ x, const float* __restrict__ addend,
                                                              float* __restrict__ y, float* __restrict__ stats, int S,
                                                              float eps) {
+  VX_PDL_ENTRY();
   __shared__ float red[33];
   const size_t base = (size_t)blockIdx.x * S;
   float s = 0.f;
@@ -594,6 +598,7 @@ constexpr int IN_Q = 4;
 __global__ void __launch_bounds__(1024) inorm_rows_fwd_cached_kernel(const float* __restrict__ x, const float* __restrict__ addend,
                                                                     float* __restrict__ y, float* __restrict__ stats, int S,
                                                                     float eps) {
+  VX_PDL_ENTRY();
   __shared__ float red[33];
   const size_t base = (size_t)blockIdx.x * S;
   const int nq = S >> 2;
@@ -655,6 +660,7 @@ __global__ void __launch_bounds__(256) inorm_rows_bwd_kernel(const float* __rest
                                                              const float* __restrict__ stats,
                                                              const float* __restrict__ dx_add, float* __restrict__ dx,
                                                              int S, float* __restrict__ db, int C) {
+  VX_PDL_ENTRY();
   __shared__ float red[33];
   const size_t base = (size_t)blockIdx.x * S;
   const float mean = stats[2 * blockIdx.x], rstd = stats[2 * blockIdx.x + 1];
@@ -684,6 +690,7 @@ __global__ void __launch_bounds__(1024) inorm_rows_bwd_cached_kernel(const float
                                                                     const float* __restrict__ stats,
                                                                     const float* __restrict__ dx_add, float* __restrict__ dx,
                                                                     int S, float* __restrict__ db, int C) {
+  VX_PDL_ENTRY();
   __shared__ float red[33];
   const size_t base = (size_t)blockIdx.x * S;
   const int nq = S >> 2;
@@ -746,6 +753,7 @@ int inorm_rows_bwd(const float* dy, const float* x, const float* stats, const fl
 
 __global__ void stats_to_affine_kernel(const float* __restrict__ stats, float* __restrict__ a, float* __restrict__ c,
                                        int rows) {
+  VX_PDL_ENTRY();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows) { const float m = stats[2 * i], r = stats[2 * i + 1]; a[i] = r; c[i] = -m * r; }
 }
@@ -759,6 +767,7 @@ int stats_to_affine(const float* stats, float* a, float* c, int rows, cudaStream
 // zero_many: blockIdx.y = buffer, blockIdx.x strides its elements (16-byte stores where the buffer allows)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) zero_many_kernel(const __grid_constant__ ZeroList Z) {
+  VX_PDL_ENTRY();
   float* p = Z.ptr[blockIdx.y];
   const unsigned n = Z.n[blockIdx.y];
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
@@ -788,6 +797,7 @@ int zero_many(const ZeroList& z, cudaStream_t stream) {
 // channel-first LayerNorm (thread per voxel, channel loop strides by S so every warp access is coalesced)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) ln_fwd_kernel(const __grid_constant__ LnBatch L) {
+  VX_PDL_ENTRY();
   const int t = blockIdx.z, b = blockIdx.y;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= L.S) return;
@@ -808,6 +818,7 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const __grid_constant__ LnB
 // is 4-8 CTAs walking 3 x C strided loads each.  Here a CTA is 32 voxels (lanes) x 8 warps that split the channel axis and
 // meet in shared memory; same two-pass arithmetic.
 __global__ void __launch_bounds__(256) ln_fwd_wide_kernel(const __grid_constant__ LnBatch L) {
+  VX_PDL_ENTRY();
   const int t = blockIdx.z, b = blockIdx.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int v = blockIdx.x * 32 + lane;
@@ -854,6 +865,7 @@ int ln_forward(const LnBatch& L, cudaStream_t stream) {
 // dgamma / dbeta partial is one warp reduction + one global atomic), and the per-voxel means are combined through
 // shared memory.
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const __grid_constant__ LnBwdBatch L, int groups) {
+  VX_PDL_ENTRY();
   // `groups` consecutive blocks of 32 voxels per CTA: the dgamma / dbeta partial sums of a warp's channels stay in registers
   // across them (when a warp owns <= LN_NC channels), so the global atomics -- 2 per channel and CTA onto the same 2 C
   // addresses from every CTA -- shrink by that factor.
@@ -936,6 +948,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __grid_constant__ LnB
 // the warp's voxel blocks and leave through one warp reduction per channel at the end.
 template <int C>
 __global__ void __launch_bounds__(256) ln_bwd_narrow_kernel(const __grid_constant__ LnBwdBatch L, int bpw) {
+  VX_PDL_ENTRY();
   const int t = blockIdx.z, b = blockIdx.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int S = L.S;

@@ -52,6 +52,7 @@ VX_DEV void drop_keep8(uint64_t seed, uint32_t site, size_t idx, size_t S, int l
 // (two register sets, rotated) plus the other CTAs of the SM, not by unrolling.
 __global__ void __launch_bounds__(TC_THREADS, 3) pw_tc_kernel(const __grid_constant__ PwBatch batch,
                                                               const __grid_constant__ PwTcShape shp) {
+  VX_PDL_ENTRY();
   const int pi = blockIdx.z / batch.B, b = blockIdx.z % batch.B;
   const PwProblem& P = batch.p[pi];
   const int S = batch.S, Ci = P.Ci, Co = P.Co;

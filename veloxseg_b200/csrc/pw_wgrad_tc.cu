@@ -42,6 +42,7 @@ static inline void split_tf32(float x, float& hi, float& lo) {
 
 __global__ void __launch_bounds__(WT_THREADS) pw_wgrad_tc_kernel(const __grid_constant__ WgBatch batch,
                                                                 const __grid_constant__ WgTcShape shp) {
+  VX_PDL_ENTRY();
   const WgProblem& P = batch.p[blockIdx.y];
   const int S = batch.S, B = batch.B;
   const int Co = P.Co, Ci = P.Ci;

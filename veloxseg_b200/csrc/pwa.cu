@@ -86,6 +86,7 @@ VX_DEV void token_coords(const PwaGeo& G, int j, int Nloc, int t, int& z0, int& 
 // sector per lane, and a token row (cper floats / indices) is written as 16-byte vectors.
 // Warp mode (>= 32 voxels per small window): a warp per (token, channel), lanes over the window.
 __global__ void __launch_bounds__(256) pwa_gather_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ GatherArgs A) {
+  VX_PDL_ENTRY();
   const int j = blockIdx.y;
   const int kind = blockIdx.z / G.M, m = blockIdx.z % G.M;
   const int cper = A.cper[kind], Ct = A.Ct[kind];
@@ -194,6 +195,7 @@ struct GatherBwdArgs {
 };
 
 __global__ void __launch_bounds__(256) pwa_gather_bwd_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ GatherBwdArgs A) {
+  VX_PDL_ENTRY();
   // thread = (batch, scale, head, voxel): one 16-byte read of the token's gradient row (and arg-max row) per 4 channels,
   // channel planes written with the lanes along x
   const int kind = blockIdx.z / G.M, m = blockIdx.z % G.M;
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(256) pwa_gather_bwd_kernel(const __grid_consta
 // ---------------------------------------------------------------------------------------------------
 __global__ void pwa_bias_kernel(const float* __restrict__ table, const long long* __restrict__ index,
                                 float* __restrict__ biasT, float* __restrict__ biasN, int heads, int l) {
+  VX_PDL_ENTRY();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= heads * l * l) return;
   const int tq = e % l, tk = (e / l) % l, h = e / (l * l);
@@ -252,6 +255,7 @@ __global__ void pwa_bias_kernel(const float* __restrict__ table, const long long
 // and flushes one atomic per row, instead of l*l contended global atomics.
 __global__ void __launch_bounds__(256) pwa_bias_bwd_kernel(const float* __restrict__ dbias, const long long* __restrict__ index,
                                                            float* __restrict__ dtable, int heads, int l, int rows) {
+  VX_PDL_ENTRY();
   VX_DYN_SMEM(float, hist);
   const int h = blockIdx.y;
   for (int i = threadIdx.x; i < rows; i += blockDim.x) hist[i] = 0.f;
@@ -336,6 +340,7 @@ VX_DEV void att_red4(float* p, const float (&v)[4]) {
 // row (each takes every ATT_TS-th quad of keys with its own online-softmax state, merged with two shuffle rounds).
 template <int CQ, int CV>
 __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_fwd_kernel(const __grid_constant__ AttnArgs A) {
+  VX_PDL_ENTRY();
   const int N = blockIdx.y, bh = blockIdx.z, head = bh % A.heads;
   const int L = A.L, l = A.l;
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -425,6 +430,7 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_fwd_kernel(const __g
 //    and flushes l*l coalesced atomics once -- 8-30x fewer L2 atomics than one per score element.
 template <int CQ, int CV>
 __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_bwd_kernel(const __grid_constant__ AttnArgs A) {
+  VX_PDL_ENTRY();
   const int bh = blockIdx.z, head = bh % A.heads;
   const int L = A.L, l = A.l;
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -678,6 +684,7 @@ struct ScatterArgs {
 };
 
 __global__ void __launch_bounds__(256) pwa_scatter_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ ScatterArgs A) {
+  VX_PDL_ENTRY();
   const int m = blockIdx.z;
   const int cper = A.cper, Ct = A.Ct;
   const long long total = (long long)G.B * Ct * G.S;
@@ -735,6 +742,7 @@ VX_DEV float lerp_weight(int p, int n, int out, int a) {
 // then y, then z with per-axis weight tables (the trilinear adjoint is separable inside a big window), so every voxel is
 // read once and the work per token no longer grows with the window volume.
 __global__ void __launch_bounds__(256) pwa_scatter_bwd_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ ScatterBwdArgs A) {
+  VX_PDL_ENTRY();
   const int ch = blockIdx.x, b = blockIdx.y, m = blockIdx.z;
   const int cper = A.cper, Ct = A.Ct;
   const int c = ch % cper, head = (ch / cper) % G.heads, j = ch / (cper * G.heads);
@@ -1060,8 +1068,13 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
     VX_TRY(zero_many(zl, side_fork(st)));      // side stream: the main stream catches up with it after its first contraction
   }
   float* biasN = (float*)(ws + P.off_biasN);
-  VX_LAUNCH(pwa_bias_kernel, dim3(cdiv(nbias, 256)), dim3(256), 0, st, table, index, biasT, biasN, G.heads, G.l);
-  VX_TRY(check_launch("pwa_bias_kernel"));
+  {
+    // the dense bias is first needed by the attention backward, a dozen launches down the main stream: built on the side
+    // stream, behind the zeroing (the main stream joins both at side_wait below)
+    cudaStream_t sb = side_fork(st);
+    VX_LAUNCH(pwa_bias_kernel, dim3(cdiv(nbias, 256)), dim3(256), 0, sb, table, index, biasT, biasN, G.heads, G.l);
+    VX_TRY(check_launch("pwa_bias_kernel"));
+  }
 
   auto seedm = [&](int m) { return d->seed + 0x1000 * (uint64_t)(m + 1); };
 

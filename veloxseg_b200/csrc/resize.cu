@@ -27,6 +27,7 @@ VX_DEV void lerp_ac(int p, int n, int out, int& i0, int& i1, float& w1) {
 struct ResizeArgs { const float* x; float* y; int planes, d, h, w, D, H, W; };
 
 __global__ void __launch_bounds__(256) resize_fwd_kernel(const __grid_constant__ ResizeArgs A) {
+  VX_PDL_ENTRY();
   const long long total = (long long)A.planes * A.D * A.H * A.W;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int X = (int)(e % A.W), Y = (int)((e / A.W) % A.H), Z = (int)((e / ((long long)A.W * A.H)) % A.D);
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256) resize_fwd_kernel(const __grid_constant__
 // instructions per output on index decoding and three float divisions; this one is bound by the 4-byte-per-voxel write.
 constexpr int RS_ROWS = 8;
 __global__ void __launch_bounds__(256) resize_fwd_rows_kernel(const __grid_constant__ ResizeArgs A) {
+  VX_PDL_ENTRY();
   VX_DYN_SMEM(float, sm);
   int* c0t = reinterpret_cast<int*>(sm);       // [W]
   float* wct = sm + A.W;                       // [W]
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(256) resize_fwd_rows_kernel(const __grid_const
 constexpr int RA_ROWS = 64;
 __global__ void __launch_bounds__(256) resize_adjoint_rows_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                   long long rows, int P, int n) {
+  VX_PDL_ENTRY();
   VX_DYN_SMEM(float, sm);
   float* wt = sm;                          // [n][P]
   int* lohi = reinterpret_cast<int*>(sm + (size_t)n * P);      // [n] lo | hi << 16
@@ -142,6 +145,7 @@ __global__ void __launch_bounds__(256) resize_adjoint_rows_kernel(const float* _
 // out[o, j, i] = sum_p weight(j <- p) * in[o, p, i]      in: (outer, P, inner)   out: (outer, n, inner)
 __global__ void __launch_bounds__(256) resize_adjoint1d_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                long long outer, int P, int n, int inner) {
+  VX_PDL_ENTRY();
   const long long total = outer * n * inner;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(e % inner), j = (int)((e / inner) % n);
@@ -172,6 +176,7 @@ __global__ void __launch_bounds__(256) resize_adjoint1d_kernel(const float* __re
 // outputs (216 for the last pass of a 3^3 source), each a 96-term sum -- one thread per output is a long serial chain.
 __global__ void __launch_bounds__(256) resize_adjoint1d_warp_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                     long long outer, int P, int n, int inner) {
+  VX_PDL_ENTRY();
   const long long total = outer * n * inner;
   const int lane = threadIdx.x & 31;
   for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += ((long long)gridDim.x * blockDim.x) >> 5) {

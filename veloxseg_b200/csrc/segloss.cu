@@ -28,6 +28,7 @@ struct SegLossArgs {
 
 template <int C>
 __global__ void __launch_bounds__(SL_THREADS) segloss_partial_kernel(const __grid_constant__ SegLossArgs A) {
+  VX_PDL_ENTRY();
   __shared__ float red[33];
   const int i = blockIdx.z, b = blockIdx.y, blk = blockIdx.x;
   const float* lg = A.logits[i] + (size_t)b * C * A.S;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(SL_THREADS) segloss_partial_kernel(const __gri
 
 // one CTA: fixed-order reduction of the partials, then the scalar loss
 __global__ void __launch_bounds__(SL_THREADS) segloss_finalize_kernel(const __grid_constant__ SegLossArgs A) {
+  VX_PDL_ENTRY();
   __shared__ float sloss[SL_THREADS];
   const int C = A.C, W = 1 + 3 * C;
   float acc = 0.f;
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(SL_THREADS) segloss_finalize_kernel(const __gr
 // dlogit_k = w_i dL [ (p_k - t_k) / (B S) + p_k (g_k - sum_c p_c g_c) ],  g_c = -(2 t_c den_c - (2 I_c + eps)) / den_c^2 / (B (C-1))
 template <int C>
 __global__ void __launch_bounds__(SL_THREADS) segloss_bwd_kernel(const __grid_constant__ SegLossArgs A) {
+  VX_PDL_ENTRY();
   const int i = blockIdx.z, b = blockIdx.y;
   const float* lg = A.logits[i] + (size_t)b * C * A.S;
   float* dl = A.dlogits[i] + (size_t)b * C * A.S;

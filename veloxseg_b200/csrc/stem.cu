@@ -30,6 +30,7 @@ struct PeArgs {
 
 template <int CO>
 __global__ void __launch_bounds__(256) patch_embed_fwd_kernel(const __grid_constant__ PeArgs A) {
+  VX_PDL_ENTRY();
   VX_DYN_SMEM(float, ws);                         // [Ci * p^3][CO] (channels past Co are zero)
   const int p = A.p, p3 = p * p * p, K = A.Ci * p3, Co = A.Co;
   for (int i = threadIdx.x; i < K * CO; i += blockDim.x) {
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(256) patch_embed_fwd_kernel(const __grid_const
 constexpr int PE_VC = 128;
 
 __global__ void __launch_bounds__(256) patch_embed_wgrad_kernel(const __grid_constant__ PeArgs A) {
+  VX_PDL_ENTRY();
   VX_DYN_SMEM(float, sm);
   const int p = A.p, p3 = p * p * p, Co = A.Co, Co4 = (Co + 3) & ~3;
   float* dys = sm;                               // [PE_VC][Co4]
@@ -157,6 +159,7 @@ struct PsArgs { const float* src; const float* bias; float* dst; float* db; int 
 constexpr int PS_MAX_S = 4;
 
 __global__ void __launch_bounds__(256) pixel_shuffle_fwd_kernel(const __grid_constant__ PsArgs A) {
+  VX_PDL_ENTRY();
   const int s = A.s, s2n = s * s, dhw = A.d * A.h * A.w;
   const int cs = blockIdx.y;                         // (c, s1, s2)
   const int c = cs / s2n, s1 = (cs / s) % s, s2 = cs % s;
@@ -181,6 +184,7 @@ __global__ void __launch_bounds__(256) pixel_shuffle_fwd_kernel(const __grid_con
 }
 
 __global__ void __launch_bounds__(256) pixel_shuffle_bwd_kernel(const __grid_constant__ PsArgs A) {
+  VX_PDL_ENTRY();
   __shared__ float red[33];
   const int s = A.s, s2n = s * s, dhw = A.d * A.h * A.w;
   const int cs = blockIdx.y;
@@ -228,9 +232,11 @@ struct AdamArgs {
 };
 constexpr int AD_CHUNK = 1024;
 
-__global__ void adamw_tick_kernel(float* step) { step[0] += 1.f; }
+__global__ void adamw_tick_kernel(float* step) {
+  VX_PDL_ENTRY(); step[0] += 1.f; }
 
 __global__ void __launch_bounds__(256) adamw_kernel(const __grid_constant__ AdamArgs A) {
+  VX_PDL_ENTRY();
   const int t = A.chunks[2 * blockIdx.x], start = A.chunks[2 * blockIdx.x + 1];
   const long long* e = A.table + 4 * (size_t)t;
   float* p = reinterpret_cast<float*>(e[0]);

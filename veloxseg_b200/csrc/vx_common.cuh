@@ -21,9 +21,19 @@
 #define VX_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(vx_emu::dyn_smem())
 #define VX_SET_SMEM(kern, bytes) do { } while (0)
 #else
+// Programmatic dependent launch (VX_OPT_PDL, default OFF): with the option on, every kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization; a kernel starts with griddepcontrol.wait (returns once the PREVIOUS kernel
+// of the stream has completed and flushed) + griddepcontrol.launch_dependents (the NEXT kernel is dispatched and becomes resident
+// while this one runs) -- VX_PDL_ENTRY, the first statement of every __global__ function of this library; with the option off
+// both instructions are no-ops.  The idea was to pay the dispatch latency of the ~400 serial sub-wave launches of a step once
+// instead of per edge.  Measured on a B200 (profiles/r3a_pdl_ab.txt, same tree, 100 steps each): 6.94 ms/step with
+// launch_dependents before wait, 6.86 ms with it after, against 6.63-6.66 ms without PDL (sliding window 26.5-28.0 vs 24.3 ms):
+// the early-resident CTAs of the next kernel take SM slots from the kernels the forked streams run concurrently.  Kept as an
+// A/B switch, results bit-identical either way.
 #define VX_LAUNCH(kern, grid, block, smem, stream, ...)                                   \
   do { auto _k = kern; const int _pi = vx::prof_begin(#kern, (stream));                  \
-       _k<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); vx::count_launch(); vx::prof_end(_pi, (stream)); } while (0)
+       vx::launch_pdl(_k, dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__); vx::count_launch();              \
+       vx::prof_end(_pi, (stream)); } while (0)
 #define VX_DYN_SMEM(type, name)                                                           \
   extern __shared__ __align__(16) unsigned char vx_dsm_[];                                \
   type* name = reinterpret_cast<type*>(vx_dsm_)
@@ -35,6 +45,12 @@
 #endif
 
 #define VX_DEV __device__ __forceinline__
+
+#ifdef VX_EMU
+#define VX_PDL_ENTRY() do { } while (0)
+#else
+#define VX_PDL_ENTRY() do { asm volatile("griddepcontrol.wait;" ::: "memory"); asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); } while (0)
+#endif
 
 // 4-byte asynchronous global -> shared copy (LDGSTS); `ok == false` zero-fills.
 #ifdef VX_EMU
@@ -61,6 +77,21 @@ VX_DEV void vx_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" :::
 namespace vx {
 
 constexpr int kSMs = 148;
+
+#ifndef VX_EMU
+int pdl_enabled();                                     // VX_OPT_PDL
+void pdl_set(int on);
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k, static_cast<KArgs>(args)...);
+}
+#endif
 
 void set_error(const char* fmt, ...);
 void count_launch();
