@@ -59,6 +59,9 @@ static int make_geo(const vx_pwa_desc* d, PwaGeo& G) {
   G.l = G.n[0] * G.n[1] * G.n[2];
   G.L = G.l * G.M;
   if (d->c_qk % (G.nb * G.heads) || d->c_v % (G.nb * G.heads)) { set_error("pwa: channels do not split into scales x heads"); return VX_ERR_BAD_DESC; }
+  // the gather / scatter kernels decode flat indices in 32-bit arithmetic
+  const long long cmax = d->c_qk > d->c_v ? d->c_qk : d->c_v;
+  if ((long long)G.B * G.S * cmax * (G.nb > 1 ? G.nb : 1) >= (1LL << 31)) { set_error("pwa: more than 2^31 elements per tensor"); return VX_ERR_UNSUPPORTED; }
   return VX_OK;
 }
 
@@ -96,12 +99,16 @@ __global__ void __launch_bounds__(256) pwa_gather_kernel(const __grid_constant__
   const float* src = A.src[kind][m];
   const int s0 = G.small[j][0], s1 = G.small[j][1], s2 = G.small[j][2];
   if (!warp_mode) {
-    const long long total = (long long)G.B * G.heads * Nj * G.l;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-      const int t = (int)(e % G.l);
-      const int Nloc = (int)((e / G.l) % Nj);
-      const int head = (int)((e / ((long long)G.l * Nj)) % G.heads);
-      const int b = (int)(e / ((long long)G.l * Nj * G.heads));
+    // 32-bit index arithmetic throughout (the launcher refuses problems with more than 2^31 elements): the 64-bit divisions of
+    // the flat-index decoding cost ~100 instructions each, several per token
+    const unsigned total = (unsigned)G.B * G.heads * Nj * G.l;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+      const unsigned q1 = e / (unsigned)G.l;
+      const int t = (int)(e - q1 * (unsigned)G.l);
+      const unsigned q2 = q1 / (unsigned)Nj;
+      const int Nloc = (int)(q1 - q2 * (unsigned)Nj);
+      const int b = (int)(q2 / (unsigned)G.heads);
+      const int head = (int)(q2 - (unsigned)b * (unsigned)G.heads);
       int z0, y0, x0;
       token_coords(G, j, Nloc, t, z0, y0, x0);
       const size_t o = ((((size_t)b * G.heads + head) * G.Ns + G.Noff[j] + Nloc) * G.L + (size_t)m * G.l + t) * cper;
@@ -137,15 +144,18 @@ __global__ void __launch_bounds__(256) pwa_gather_kernel(const __grid_constant__
     }
     return;
   }
-  const long long total = (long long)G.B * G.heads * Nj * G.l * cper;
-  long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
+  const unsigned total = (unsigned)G.B * G.heads * Nj * G.l * cper;
+  unsigned e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned stride = (gridDim.x * blockDim.x) >> 5;
   for (; e < total; e += stride) {
-    const int c = (int)(e % cper);
-    const int t = (int)((e / cper) % G.l);
-    const int Nloc = (int)((e / ((long long)cper * G.l)) % Nj);
-    const int head = (int)((e / ((long long)cper * G.l * Nj)) % G.heads);
-    const int b = (int)(e / ((long long)cper * G.l * Nj * G.heads));
+    const unsigned q0 = e / (unsigned)cper;
+    const int c = (int)(e - q0 * (unsigned)cper);
+    const unsigned q1 = q0 / (unsigned)G.l;
+    const int t = (int)(q0 - q1 * (unsigned)G.l);
+    const unsigned q2 = q1 / (unsigned)Nj;
+    const int Nloc = (int)(q1 - q2 * (unsigned)Nj);
+    const int b = (int)(q2 / (unsigned)G.heads);
+    const int head = (int)(q2 - (unsigned)b * (unsigned)G.heads);
     int z0, y0, x0;
     token_coords(G, j, Nloc, t, z0, y0, x0);
     const int ch = (j * G.heads + head) * cper + c;
@@ -180,6 +190,7 @@ static int launch_gather(const PwaGeo& G, const GatherArgs& A, cudaStream_t st) 
       if (G.vol[j] >= 32) t *= 32LL * A.cper[k];                                                    // warp per (token, channel)
       maxtotal = t > maxtotal ? t : maxtotal;
     }
+  if (maxtotal >= (1LL << 31)) { set_error("pwa gather: more than 2^31 elements"); return VX_ERR_UNSUPPORTED; }
   int blocks = cdiv(maxtotal, 256);
   if (blocks > kSMs * 16) blocks = kSMs * 16;
   if (blocks < 1) blocks = 1;
@@ -187,6 +198,7 @@ static int launch_gather(const PwaGeo& G, const GatherArgs& A, cudaStream_t st) 
   return check_launch("pwa_gather_kernel");
 }
 
+constexpr int GB_MAX_AXIS = 3 * 160;       // D + H + W entries of the per-axis tables
 // backward of the gather: full-resolution gradient; a voxel receives its token's gradient iff it was the arg-max.
 struct GatherBwdArgs {
   const float* dtok[3]; const int* arg[3];
@@ -196,22 +208,31 @@ struct GatherBwdArgs {
 
 __global__ void __launch_bounds__(256) pwa_gather_bwd_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ GatherBwdArgs A) {
   VX_PDL_ENTRY();
-  // thread = (batch, scale, head, voxel): one 16-byte read of the token's gradient row (and arg-max row) per 4 channels,
-  // channel planes written with the lanes along x
+  // CTA = one (batch, scale, head) x a slab of voxels; thread = voxel: one 16-byte read of the token's gradient row (and
+  // arg-max row) per 4 channels, channel planes written with the lanes along x.  Window index and token coordinate of every
+  // position along each axis are tabulated in shared memory once per CTA (two divisions per voxel instead of ~15).
   const int kind = blockIdx.z / G.M, m = blockIdx.z % G.M;
   const int cper = A.cper[kind], Ct = A.Ct[kind];
-  const long long total = (long long)G.B * G.nb * G.heads * G.S;
+  const int head = blockIdx.y % G.heads, j = (blockIdx.y / G.heads) % G.nb, b = blockIdx.y / (G.heads * G.nb);
+  __shared__ int t_w[GB_MAX_AXIS], t_t[GB_MAX_AXIS];
+  const int aoff[3] = {0, G.D, G.D + G.H};
+  for (int i = threadIdx.x; i < G.D + G.H + G.W; i += blockDim.x) {
+    const int ax = i < G.D ? 0 : (i < G.D + G.H ? 1 : 2);
+    const int p = i - aoff[ax];
+    const int big = G.big[j][ax];
+    const int w = p / big;
+    t_w[i] = w; t_t[i] = (p - w * big) / G.small[j][ax];
+  }
+  __syncthreads();
   float* dst = A.dst[kind][m];
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int idx = (int)(e % G.S);
-    const int head = (int)((e / G.S) % G.heads);
-    const int j = (int)((e / ((long long)G.S * G.heads)) % G.nb);
-    const int b = (int)(e / ((long long)G.S * G.heads * G.nb));
-    const int x = idx % G.W, y = (idx / G.W) % G.H, z = idx / (G.W * G.H);
-    const int wz = z / G.big[j][0], wy = y / G.big[j][1], wx = x / G.big[j][2];
-    const int a = (z % G.big[j][0]) / G.small[j][0], bb = (y % G.big[j][1]) / G.small[j][1], cc = (x % G.big[j][2]) / G.small[j][2];
-    const int Nloc = (wz * G.Nw[j][1] + wy) * G.Nw[j][2] + wx;
-    const int t = (a * G.n[1] + bb) * G.n[2] + cc;
+  const unsigned HW = (unsigned)(G.H * G.W);
+  for (unsigned uidx = blockIdx.x * blockDim.x + threadIdx.x; uidx < (unsigned)G.S; uidx += gridDim.x * blockDim.x) {
+    const int idx = (int)uidx;
+    const unsigned z = uidx / HW, rem = uidx - z * HW;
+    const unsigned y = rem / (unsigned)G.W, x = rem - y * (unsigned)G.W;
+    const int iz = (int)z, iy = G.D + (int)y, ix = G.D + G.H + (int)x;
+    const int Nloc = (t_w[iz] * G.Nw[j][1] + t_w[iy]) * G.Nw[j][2] + t_w[ix];
+    const int t = (t_t[iz] * G.n[1] + t_t[iy]) * G.n[2] + t_t[ix];
     const size_t o = ((((size_t)b * G.heads + head) * G.Ns + G.Noff[j] + Nloc) * G.L + (size_t)m * G.l + t) * cper;
     float* dp = dst + ((size_t)b * Ct + (size_t)(j * G.heads + head) * cper) * G.S + idx;
     const bool all = G.vol[j] == 1;
@@ -683,32 +704,52 @@ struct ScatterArgs {
   int Ct, cper;
 };
 
+// CTA = one (b, channel) plane x a slab of voxels; blockIdx.z = modality.  The scale j, head and per-head channel are uniform
+// per CTA, and everything that depends on one coordinate only -- window index, token index inside the window, the two
+// interpolation taps and their weight (align_corners=True inside each big window) -- is tabulated per axis in shared memory
+// once per CTA: a voxel then costs two divisions (flat index -> z, y, x) instead of ~25 (profiles/r2n_step_stalls.txt:
+// pwa_scatter_kernel was issue-bound at 72 % issue-active).
+constexpr int SC_MAX_AXIS = 3 * 160;       // D + H + W table entries (the launcher falls back to one entry per voxel axis beyond)
 __global__ void __launch_bounds__(256) pwa_scatter_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ ScatterArgs A) {
   VX_PDL_ENTRY();
   const int m = blockIdx.z;
   const int cper = A.cper, Ct = A.Ct;
-  const long long total = (long long)G.B * Ct * G.S;
-  float* dst = A.dst[m];
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int idx = (int)(e % G.S);
-    const int ch = (int)((e / G.S) % Ct);
-    const int b = (int)(e / ((long long)G.S * Ct));
-    const int c = ch % cper, head = (ch / cper) % G.heads, j = ch / (cper * G.heads);
-    const int x = idx % G.W, y = (idx / G.W) % G.H, z = idx / (G.W * G.H);
-    const int wz = z / G.big[j][0], wy = y / G.big[j][1], wx = x / G.big[j][2];
-    const int Nloc = (wz * G.Nw[j][1] + wy) * G.Nw[j][2] + wx;
-    const float* tp = A.tok + ((((size_t)b * G.heads + head) * G.Ns + G.Noff[j] + Nloc) * G.L + (size_t)m * G.l) * cper + c;
+  const int b = blockIdx.y / Ct, ch = blockIdx.y % Ct;
+  const int c = ch % cper, head = (ch / cper) % G.heads, j = ch / (cper * G.heads);
+  __shared__ int t_w[SC_MAX_AXIS], t_i0[SC_MAX_AXIS], t_i1[SC_MAX_AXIS];
+  __shared__ float t_w1[SC_MAX_AXIS];
+  const int ext[3] = {G.D, G.H, G.W};
+  const int aoff[3] = {0, G.D, G.D + G.H};
+  const bool nearest = G.vol[j] == 1;
+  for (int i = threadIdx.x; i < G.D + G.H + G.W; i += blockDim.x) {
+    const int ax = i < G.D ? 0 : (i < G.D + G.H ? 1 : 2);
+    const int p = i - aoff[ax];
+    const int big = G.big[j][ax];
+    const int w = p / big, r = p - w * big;
+    t_w[i] = w;
+    if (nearest) { t_i0[i] = r; t_i1[i] = r; t_w1[i] = 0.f; }
+    else { int i0, i1; float w1; lerp_coef(r, G.n[ax], big, i0, i1, w1); t_i0[i] = i0; t_i1[i] = i1; t_w1[i] = w1; }
+  }
+  (void)ext;
+  __syncthreads();
+  float* dst = A.dst[m] + ((size_t)b * Ct + ch) * G.S;
+  const float* tok0 = A.tok + (((size_t)b * G.heads + head) * G.Ns + G.Noff[j]) * (size_t)G.L * cper + (size_t)m * G.l * cper + c;
+  const int n1 = G.n[1], n2 = G.n[2], Nw1 = G.Nw[j][1], Nw2 = G.Nw[j][2];
+  const size_t wstride = (size_t)G.L * cper;                     // tokens of one window
+  const unsigned HW = (unsigned)(G.H * G.W);
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < (unsigned)G.S; idx += gridDim.x * blockDim.x) {
+    const unsigned z = idx / HW, rem = idx - z * HW;
+    const unsigned y = rem / (unsigned)G.W, x = rem - y * (unsigned)G.W;
+    const int iz = (int)z, iy = G.D + (int)y, ix = G.D + G.H + (int)x;
+    const int Nloc = (t_w[iz] * Nw1 + t_w[iy]) * Nw2 + t_w[ix];
+    const float* tp = tok0 + (size_t)Nloc * wstride;
     float val;
-    if (G.vol[j] == 1) {
-      const int t = ((z % G.big[j][0]) * G.n[1] + (y % G.big[j][1])) * G.n[2] + (x % G.big[j][2]);
+    if (nearest) {
+      const int t = (t_i0[iz] * n1 + t_i0[iy]) * n2 + t_i0[ix];
       val = __ldg(tp + (size_t)t * cper);
     } else {
-      int a0, a1, b0, b1, c0, c1;
-      float wa, wb, wc;
-      lerp_coef(z % G.big[j][0], G.n[0], G.big[j][0], a0, a1, wa);
-      lerp_coef(y % G.big[j][1], G.n[1], G.big[j][1], b0, b1, wb);
-      lerp_coef(x % G.big[j][2], G.n[2], G.big[j][2], c0, c1, wc);
-      const int n1 = G.n[1], n2 = G.n[2];
+      const int a0 = t_i0[iz], a1 = t_i1[iz], b0 = t_i0[iy], b1 = t_i1[iy], c0 = t_i0[ix], c1 = t_i1[ix];
+      const float wa = t_w1[iz], wb = t_w1[iy], wc = t_w1[ix];
 #define VX_T(a, bq, cq_) __ldg(tp + (size_t)(((a) * n1 + (bq)) * n2 + (cq_)) * cper)
       const float v000 = VX_T(a0, b0, c0), v001 = VX_T(a0, b0, c1), v010 = VX_T(a0, b1, c0), v011 = VX_T(a0, b1, c1);
       const float v100 = VX_T(a1, b0, c0), v101 = VX_T(a1, b0, c1), v110 = VX_T(a1, b1, c0), v111 = VX_T(a1, b1, c1);
@@ -717,7 +758,7 @@ __global__ void __launch_bounds__(256) pwa_scatter_kernel(const __grid_constant_
       val = ua * (ub * (uc * v000 + wc * v001) + wb * (uc * v010 + wc * v011)) +
             wa * (ub * (uc * v100 + wc * v101) + wb * (uc * v110 + wc * v111));
     }
-    dst[e] = val;
+    dst[idx] = val;
   }
 }
 
@@ -964,9 +1005,10 @@ extern "C" int vx_pwa_block_fwd(const vx_pwa_desc* d, const void* const* in, voi
   {
     ScatterArgs A{}; A.tok = SV(SV_OT); A.Ct = P.cv; A.cper = P.cv_h;
     for (int m = 0; m < M; ++m) A.dst[m] = SV(SV_A) + (size_t)m * P.cv * BS;
-    int blocks = cdiv((long long)B * P.cv * S, 256);
-    if (blocks > kSMs * 16) blocks = kSMs * 16;
-    VX_LAUNCH(pwa_scatter_kernel, dim3(blocks, 1, M), dim3(256), 0, st, G, A);
+    if (G.D + G.H + G.W > SC_MAX_AXIS || (long long)B * P.cv > 65535) { set_error("pwa scatter: extent / plane count beyond the kernel's tables"); return VX_ERR_UNSUPPORTED; }
+    int blocks = cdiv(S, 256 * 2);                     // plane slabs: ~2 voxels per thread, at least ~2 CTAs per SM overall
+    while (blocks > 1 && (long long)blocks * B * P.cv * M > 8LL * kSMs) blocks = (blocks + 1) / 2;
+    VX_LAUNCH(pwa_scatter_kernel, dim3(blocks, B * P.cv, M), dim3(256), 0, st, G, A);
     VX_TRY(check_launch("pwa_scatter_kernel"));
   }
   // y = 2x + Drop(Wmix a + b)
@@ -1194,9 +1236,10 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
     A.arg[0] = (const int*)SV(SV_ARGQ); A.arg[1] = (const int*)SV(SV_ARGK); A.arg[2] = (const int*)SV(SV_ARGV);
     for (int m = 0; m < M; ++m) { A.dst[0][m] = dQf(m); A.dst[1][m] = dKf(m); A.dst[2][m] = dVf(m); }
     A.Ct[0] = A.Ct[1] = P.cqk; A.Ct[2] = P.cv; A.cper[0] = A.cper[1] = P.cq_h; A.cper[2] = P.cv_h;
-    int blocks = cdiv((long long)B * G.nb * G.heads * S, 256);      // one thread per (batch, scale, head, voxel)
-    if (blocks > kSMs * 16) blocks = kSMs * 16;
-    VX_LAUNCH(pwa_gather_bwd_kernel, dim3(blocks, 1, 3 * M), dim3(256), 0, st, G, A);
+    if (G.D + G.H + G.W > GB_MAX_AXIS) { set_error("pwa gather bwd: extent beyond the kernel's tables"); return VX_ERR_UNSUPPORTED; }
+    int blocks = cdiv(S, 256);                          // one thread per voxel of a (batch, scale, head) plane
+    while (blocks > 1 && (long long)blocks * B * G.nb * G.heads * 3 * M > 16LL * kSMs) blocks = (blocks + 1) / 2;
+    VX_LAUNCH(pwa_gather_bwd_kernel, dim3(blocks, B * G.nb * G.heads, 3 * M), dim3(256), 0, st, G, A);
     VX_TRY(check_launch("pwa_gather_bwd_kernel"));
   }
   // ---- projection backward

@@ -163,10 +163,10 @@ __global__ void __launch_bounds__(256) pixel_shuffle_fwd_kernel(const __grid_con
   const int s = A.s, s2n = s * s, dhw = A.d * A.h * A.w;
   const int cs = blockIdx.y;                         // (c, s1, s2)
   const int c = cs / s2n, s1 = (cs / s) % s, s2 = cs % s;
-  const long long total = (long long)A.B * dhw;
+  const unsigned total = (unsigned)A.B * (unsigned)dhw;      // 32-bit index arithmetic (64-bit divisions are ~100 instructions each)
   const int H = A.h * s, W = A.w * s, D = A.d * s;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(e % dhw), b = (int)(e / dhw);
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int b = (int)(e / (unsigned)dhw), v = (int)(e - (unsigned)b * (unsigned)dhw);
     const int x = v % A.w, y = (v / A.w) % A.h, z = v / (A.w * A.h);
     const int ch0 = cs * s;
     float o[PS_MAX_S];
@@ -189,13 +189,13 @@ __global__ void __launch_bounds__(256) pixel_shuffle_bwd_kernel(const __grid_con
   const int s = A.s, s2n = s * s, dhw = A.d * A.h * A.w;
   const int cs = blockIdx.y;
   const int c = cs / s2n, s1 = (cs / s) % s, s2 = cs % s;
-  const long long total = (long long)A.B * dhw;
+  const unsigned total = (unsigned)A.B * (unsigned)dhw;      // 32-bit index arithmetic (64-bit divisions are ~100 instructions each)
   const int H = A.h * s, W = A.w * s, D = A.d * s;
   float acc[PS_MAX_S];
 #pragma unroll
   for (int s3 = 0; s3 < PS_MAX_S; ++s3) acc[s3] = 0.f;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(e % dhw), b = (int)(e / dhw);
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int b = (int)(e / (unsigned)dhw), v = (int)(e - (unsigned)b * (unsigned)dhw);
     const int x = v % A.w, y = (v / A.w) % A.h, z = v / (A.w * A.h);
     const float* q = A.src + ((((size_t)b * A.C + c) * D + z * s + s1) * H + y * s + s2) * W + (size_t)x * s;
     float g[PS_MAX_S];
@@ -325,6 +325,7 @@ static int ps_args(const vx_pixel_shuffle_desc* d, PsArgs& A) {
     set_error("pixel_shuffle: bad descriptor (scale <= %d)", PS_MAX_S); return VX_ERR_BAD_DESC;
   }
   A.B = d->B; A.C = d->C; A.s = d->scale; A.d = d->d; A.h = d->h; A.w = d->w;
+  if ((long long)d->B * d->d * d->h * d->w >= (1LL << 31)) { set_error("pixel_shuffle: more than 2^31 voxels"); return VX_ERR_UNSUPPORTED; }
   return VX_OK;
 }
 
