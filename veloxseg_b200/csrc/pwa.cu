@@ -76,44 +76,55 @@ struct GatherArgs {
   int nkind;
 };
 
-VX_DEV void token_coords(const PwaGeo& G, int j, int Nloc, int t, int& z0, int& y0, int& x0) {
-  const int wx = Nloc % G.Nw[j][2], wy = (Nloc / G.Nw[j][2]) % G.Nw[j][1], wz = Nloc / (G.Nw[j][2] * G.Nw[j][1]);
-  const int c = t % G.n[2], b = (t / G.n[2]) % G.n[1], a = t / (G.n[2] * G.n[1]);
-  z0 = wz * G.big[j][0] + a * G.small[j][0];
-  y0 = wy * G.big[j][1] + b * G.small[j][1];
-  x0 = wx * G.big[j][2] + c * G.small[j][2];
-}
 
-// Thread mode (small windows of < 32 voxels): a thread owns one token and walks its cper channels, tokens of a window are
-// consecutive threads.  Reads are then runs along x (the token's small window, next to its neighbour's) instead of one
-// sector per lane, and a token row (cper floats / indices) is written as 16-byte vectors.
-// Warp mode (>= 32 voxels per small window): a warp per (token, channel), lanes over the window.
-__global__ void __launch_bounds__(256) pwa_gather_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ GatherArgs A) {
+// Tokens are enumerated by their position (tz, ty, tx) in the token grid of the scale (extent / small window per axis): the
+// window index and the token coordinate inside the window of every grid position are tabulated per axis in shared memory
+// once per CTA, so a token costs two divisions (flat index -> tz, ty, tx) instead of ~10 (round 1 decoded a 64-bit flat index
+// with a handful of 64-bit divisions per token, and the warp mode three more per VOXEL).
+// Thread mode (small windows of < 32 voxels): a thread owns one token and walks its cper channels; reads are runs along x
+// (the token's small window, next to its neighbour's), a token row (cper floats / indices) is written as 16-byte vectors.
+// Warp mode (>= 32 voxels per small window): a warp per token, lanes over the window, channels in turn.
+// grid: x = (b, head) planes x token chunks, y = scale, z = kind * M + modality.
+constexpr int GA_MAX_AXIS = 3 * 160;
+__global__ void __launch_bounds__(256) pwa_gather_kernel(const __grid_constant__ PwaGeo G, const __grid_constant__ GatherArgs A,
+                                                         int chunks) {
   VX_PDL_ENTRY();
   const int j = blockIdx.y;
   const int kind = blockIdx.z / G.M, m = blockIdx.z % G.M;
   const int cper = A.cper[kind], Ct = A.Ct[kind];
-  const int Nj = G.Nw[j][0] * G.Nw[j][1] * G.Nw[j][2];
+  const int plane = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int b = plane / G.heads, head = plane % G.heads;
   const bool warp_mode = G.vol[j] >= 32;
   const int lane = threadIdx.x & 31;
-  const float* src = A.src[kind][m];
   const int s0 = G.small[j][0], s1 = G.small[j][1], s2 = G.small[j][2];
+  const int T0 = G.D / s0, T1 = G.H / s1, T2 = G.W / s2;            // token grid of this scale
+  __shared__ int t_w[GA_MAX_AXIS], t_a[GA_MAX_AXIS];
+  {
+    const int toff[3] = {0, T0, T0 + T1};
+    for (int i = threadIdx.x; i < T0 + T1 + T2; i += blockDim.x) {
+      const int ax = i < T0 ? 0 : (i < T0 + T1 ? 1 : 2);
+      const int p = i - toff[ax];
+      const int w = p / G.n[ax];
+      t_w[i] = w; t_a[i] = p - w * G.n[ax];
+    }
+  }
+  __syncthreads();
+  const unsigned ntok = (unsigned)(T0 * T1 * T2), T12 = (unsigned)(T1 * T2);
+  const float* p0 = A.src[kind][m] + ((size_t)b * Ct + (size_t)(j * G.heads + head) * cper) * G.S;
+  const size_t obase = ((size_t)b * G.heads + head) * G.Ns + G.Noff[j];
+  auto token_out = [&](unsigned u, int& idx0) -> size_t {
+    const unsigned tz = u / T12, rem = u - tz * T12;
+    const unsigned ty = rem / (unsigned)T2, tx = rem - ty * (unsigned)T2;
+    const int iz = (int)tz, iy = T0 + (int)ty, ix = T0 + T1 + (int)tx;
+    const int Nloc = (t_w[iz] * G.Nw[j][1] + t_w[iy]) * G.Nw[j][2] + t_w[ix];
+    const int t = (t_a[iz] * G.n[1] + t_a[iy]) * G.n[2] + t_a[ix];
+    idx0 = ((int)tz * s0 * G.H + (int)ty * s1) * G.W + (int)tx * s2;
+    return ((obase + Nloc) * G.L + (size_t)m * G.l + t) * cper;
+  };
   if (!warp_mode) {
-    // 32-bit index arithmetic throughout (the launcher refuses problems with more than 2^31 elements): the 64-bit divisions of
-    // the flat-index decoding cost ~100 instructions each, several per token
-    const unsigned total = (unsigned)G.B * G.heads * Nj * G.l;
-    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-      const unsigned q1 = e / (unsigned)G.l;
-      const int t = (int)(e - q1 * (unsigned)G.l);
-      const unsigned q2 = q1 / (unsigned)Nj;
-      const int Nloc = (int)(q1 - q2 * (unsigned)Nj);
-      const int b = (int)(q2 / (unsigned)G.heads);
-      const int head = (int)(q2 - (unsigned)b * (unsigned)G.heads);
-      int z0, y0, x0;
-      token_coords(G, j, Nloc, t, z0, y0, x0);
-      const size_t o = ((((size_t)b * G.heads + head) * G.Ns + G.Noff[j] + Nloc) * G.L + (size_t)m * G.l + t) * cper;
-      const float* p0 = src + ((size_t)b * Ct + (size_t)(j * G.heads + head) * cper) * G.S;
-      const int idx0 = (z0 * G.H + y0) * G.W + x0;
+    for (unsigned u = chunk * blockDim.x + threadIdx.x; u < ntok; u += chunks * blockDim.x) {
+      int idx0;
+      const size_t o = token_out(u, idx0);
       for (int c4 = 0; c4 < cper; c4 += 4) {
         float bv[4];
         int bi[4];
@@ -122,13 +133,15 @@ __global__ void __launch_bounds__(256) pwa_gather_kernel(const __grid_constant__
           const float* p = p0 + (size_t)(c4 + cc) * G.S;
           float best = -INFINITY;
           int bidx = idx0;
-          for (int dz = 0; dz < s0; ++dz)
-            for (int dy = 0; dy < s1; ++dy)
-              for (int dx = 0; dx < s2; ++dx) {
-                const int idx = idx0 + (dz * G.H + dy) * G.W + dx;
-                const float v = __ldg(p + idx);
-                if (v > best) { best = v; bidx = idx; }
-              }
+          if (c4 + cc < cper) {
+            for (int dz = 0; dz < s0; ++dz)
+              for (int dy = 0; dy < s1; ++dy)
+                for (int dx = 0; dx < s2; ++dx) {
+                  const int idx = idx0 + (dz * G.H + dy) * G.W + dx;
+                  const float v = __ldg(p + idx);
+                  if (v > best) { best = v; bidx = idx; }
+                }
+          }
           bv[cc] = best; bi[cc] = bidx;
         }
         if (c4 + 3 < cper) {
@@ -144,57 +157,58 @@ __global__ void __launch_bounds__(256) pwa_gather_kernel(const __grid_constant__
     }
     return;
   }
-  const unsigned total = (unsigned)G.B * G.heads * Nj * G.l * cper;
-  unsigned e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned stride = (gridDim.x * blockDim.x) >> 5;
-  for (; e < total; e += stride) {
-    const unsigned q0 = e / (unsigned)cper;
-    const int c = (int)(e - q0 * (unsigned)cper);
-    const unsigned q1 = q0 / (unsigned)G.l;
-    const int t = (int)(q0 - q1 * (unsigned)G.l);
-    const unsigned q2 = q1 / (unsigned)Nj;
-    const int Nloc = (int)(q1 - q2 * (unsigned)Nj);
-    const int b = (int)(q2 / (unsigned)G.heads);
-    const int head = (int)(q2 - (unsigned)b * (unsigned)G.heads);
-    int z0, y0, x0;
-    token_coords(G, j, Nloc, t, z0, y0, x0);
-    const int ch = (j * G.heads + head) * cper + c;
-    const float* p = src + ((size_t)b * Ct + ch) * G.S;
+  // warp mode: lane q of the window -> (dz, dy, dx); shifts when the small window is a power of two per axis (the usual case)
+  const bool pow2 = !(s1 & (s1 - 1)) && !(s2 & (s2 - 1));
+  const int l2 = 31 - __clz(s2 > 0 ? s2 : 1), l1 = 31 - __clz(s1 > 0 ? s1 : 1);
+  const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5;
+  // a warp per (token, channel): the window walk of one channel is the serial chain, so channels go to different warps
+  for (unsigned uc = chunk * warps + wid; uc < ntok * (unsigned)cper; uc += chunks * warps) {
+    const unsigned u = uc / (unsigned)cper;
+    const int c = (int)(uc - u * (unsigned)cper);
+    int idx0;
+    const size_t o = token_out(u, idx0);
+    const float* p = p0 + (size_t)c * G.S;
     float best = -INFINITY;
     int myidx = 0x7fffffff;
     for (int q = lane; q < G.vol[j]; q += 32) {
-      const int dx = q % s2, dy = (q / s2) % s1, dz = q / (s2 * s1);
-      const int idx = ((z0 + dz) * G.H + (y0 + dy)) * G.W + x0 + dx;
+      int dx, dy, dz;
+      if (pow2) { dx = q & (s2 - 1); dy = (q >> l2) & (s1 - 1); dz = q >> (l2 + l1); }
+      else { dx = q % s2; dy = (q / s2) % s1; dz = q / (s2 * s1); }
+      const int idx = idx0 + (dz * G.H + dy) * G.W + dx;
       const float v = __ldg(p + idx);
       if (v > best) { best = v; myidx = idx; }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, myidx, o);
+    for (int sft = 16; sft > 0; sft >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, sft);
+      const int oi = __shfl_xor_sync(0xffffffffu, myidx, sft);
       if (ov > best || (ov == best && oi < myidx)) { best = ov; myidx = oi; }
     }
     if (lane == 0) {
-      const size_t o = ((((size_t)b * G.heads + head) * G.Ns + G.Noff[j] + Nloc) * G.L + (size_t)m * G.l + t) * cper + c;
-      A.tok[kind][o] = best;
-      if (A.arg[kind]) A.arg[kind][o] = myidx;
+      A.tok[kind][o + c] = best;
+      if (A.arg[kind]) A.arg[kind][o + c] = myidx;
     }
   }
 }
 
 static int launch_gather(const PwaGeo& G, const GatherArgs& A, cudaStream_t st) {
-  long long maxtotal = 0;
-  for (int j = 0; j < G.nb; ++j)
-    for (int k = 0; k < A.nkind; ++k) {
-      long long t = (long long)G.B * G.heads * G.Nw[j][0] * G.Nw[j][1] * G.Nw[j][2] * G.l;     // thread mode: one per token
-      if (G.vol[j] >= 32) t *= 32LL * A.cper[k];                                                    // warp per (token, channel)
-      maxtotal = t > maxtotal ? t : maxtotal;
-    }
-  if (maxtotal >= (1LL << 31)) { set_error("pwa gather: more than 2^31 elements"); return VX_ERR_UNSUPPORTED; }
-  int blocks = cdiv(maxtotal, 256);
-  if (blocks > kSMs * 16) blocks = kSMs * 16;
-  if (blocks < 1) blocks = 1;
-  VX_LAUNCH(pwa_gather_kernel, dim3(blocks, G.nb, A.nkind * G.M), dim3(256), 0, st, G, A);
+  // chunks of the token list per (b, head) plane: sized for the busiest scale (thread mode: a thread per token, warp mode: a
+  // warp per token), capped so that the whole grid stays around 16 CTAs per SM
+  long long maxwork = 1;
+  for (int j = 0; j < G.nb; ++j) {
+    const long long ntok = (long long)(G.D / G.small[j][0]) * (G.H / G.small[j][1]) * (G.W / G.small[j][2]);
+    if ((G.D / G.small[j][0]) + (G.H / G.small[j][1]) + (G.W / G.small[j][2]) > GA_MAX_AXIS) { set_error("pwa gather: extent beyond the kernel's tables"); return VX_ERR_UNSUPPORTED; }
+    long long cmax = 1;
+    for (int k = 0; k < A.nkind; ++k) cmax = A.cper[k] > cmax ? A.cper[k] : cmax;
+    const long long work = G.vol[j] >= 32 ? ntok * cmax * 32 : ntok;      // warp mode: a warp per (token, channel)
+    maxwork = work > maxwork ? work : maxwork;
+  }
+  const int planes = G.B * G.heads;
+  int chunks = cdiv(maxwork, 256);
+  const long long cap = (16LL * kSMs) / ((long long)planes * G.nb * A.nkind * G.M);
+  if (chunks > cap) chunks = (int)(cap > 1 ? cap : 1);
+  if (chunks < 1) chunks = 1;
+  VX_LAUNCH(pwa_gather_kernel, dim3(chunks * planes, G.nb, A.nkind * G.M), dim3(256), 0, st, G, A, chunks);
   return check_launch("pwa_gather_kernel");
 }
 
