@@ -186,6 +186,13 @@ def run_ours(args, rank, world, local_rank):
     # every rank runs the same steps (they contain the gradient all-reduces); only rank 0 switches the profiler on
     roof, table, fp32_tflops, hbm, tensor_peak, how = None, [], 0.0, 0.0, 0.0, ""
     nprof = 3
+    # The per-kernel pass runs the step SERIALISED on one stream (no forked branches in the model, weight gradients on the main
+    # stream): an event pair then brackets exactly one kernel with the device to itself.  With the forked streams of the timed
+    # step the intervals also contain the time a kernel waits for SMs held by the other streams' kernels (the pw_tc_kernel
+    # average read 25.6 us there against 15.1 us in the ncu launch list, profiles/r3f_*).
+    model.parallel_branches = False
+    model.encoder.pipeline_branches = False
+    lib.set_option(10, 0)               # VX_OPT_SIDE_WGRAD off
     if rank == 0:
         lib.profile(True)
     for _ in range(nprof):
@@ -194,6 +201,9 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda._sleep(200_000_000)
         ts._step_eager(x_d, y_d)       # eager: the event profiler brackets individual launches
         torch.cuda.synchronize()
+    lib.set_option(10, 1)
+    model.parallel_branches = True
+    model.encoder.pipeline_branches = True
     if rank == 0:
         rows = lib.profile_report()          # (scope, kernel, launches, total_ms, algorithmic_bytes, algorithmic_flops)
         tl = lib.profile_timeline()
@@ -272,9 +282,10 @@ def run_ours(args, rank, world, local_rank):
                     "share_of_own_kernel_time": round(top[1] / sum(v[1] for v in by_kernel.values()), 4),
                     "own_kernel_ms_per_step": round(sum(v[1] for v in by_kernel.values()) / nprof, 3),
                     "own_launches_per_step": n_launch,
-                    "note": "event-timed launch by launch in an eager step enqueued behind a spin kernel (device back-to-back, "
-                            "no host gaps), minus the profiler's own per-launch overhead measured on an empty kernel; kernels of "
-                            "the forked streams overlap in the graph-replayed step, so the summed kernel time exceeds "
+                    "note": "event-timed launch by launch in an eager step that is serialised on one stream (no forked branches, "
+                            "weight gradients on the main stream) and enqueued behind a spin kernel (device back-to-back, no host "
+                            "gaps), minus the profiler's own per-launch overhead measured on an empty kernel; in the timed "
+                            "graph-replayed step the forked streams overlap these kernels, so the summed kernel time exceeds "
                             "ms_per_step; working sets are L2-resident at 4 patches (DESIGN.md section 3)"}
             break
     # ---- second headline metric: sliding-window inference (all ranks take part)

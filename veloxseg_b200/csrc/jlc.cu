@@ -91,33 +91,36 @@ static ConvTile pick_tile(int B, int groups, int CG, int D, int H, int W, int ma
 // 8-byte aligned in global memory (odd W or odd x0) take 4-byte copies.
 VX_DEV void stage_halo_rows(float* xs, const float* __restrict__ src, size_t ch_stride, int nch, int z0, int y0, int x0, int PZ,
                             int HZ, int HY, int TXP, int D, int H, int W, int XH = 2) {
-  const int l = threadIdx.x & 15, sub = threadIdx.x >> 4, nsub = blockDim.x >> 4;
-  if (sub >= nsub) return;
-  const int R = HZ * HY;
   const bool wide = ((W | x0 | TXP) & 1) == 0 && (((uintptr_t)src | (ch_stride * sizeof(float))) & 7) == 0;
-  int hz = sub / HY, hy = sub - hz * HY;             // one division per thread, not per element
-  for (int r = sub; r < nch * R; r += nsub) {
-    int ch = 0, rz = hz;
-    while (rz >= HZ) { rz -= HZ; ++ch; }             // nch <= 16 iterations at most, usually 0-1 per step
+  // lanes per row: the smallest power of two that covers a row's copies (16 for the 24-wide level-1 tiles, 8 for the 10-wide
+  // padded rows of the small-volume kernels: with 16 there, 11 of 16 lanes idled and the kernels lost 15-40 %)
+  const int ncopy = wide ? TXP >> 1 : TXP;
+  int lpr = 32;
+  while (lpr > 1 && (lpr >> 1) >= ncopy) lpr >>= 1;
+  const int l = threadIdx.x % lpr, sub = threadIdx.x / lpr, nsub = blockDim.x / lpr;
+  if (sub >= nsub) return;
+  int hy = sub % HY, rz = (sub / HY) % HZ, ch = sub / (HY * HZ);      // three divisions per thread, none per element
+  for (int r = sub; r < nch * HZ * HY; r += nsub) {
     const int gz = z0 + rz - PZ, gy = y0 + hy - PZ;
     const bool rowok = gz >= 0 && gz < D && gy >= 0 && gy < H;
     const float* grow = src + (size_t)ch * ch_stride + ((size_t)(rowok ? gz : 0) * H + (rowok ? gy : 0)) * W;
     float* srow = xs + (size_t)r * TXP;
     if (wide) {
-      for (int c = l; 2 * c < TXP; c += 16) {
+      for (int c = l; 2 * c < TXP; c += lpr) {
         const int gx = x0 + 2 * c - XH;
         const bool ok = rowok && gx >= 0 && gx < W;       // W and gx even: the pair is inside or outside together
         vx_cp_async8(srow + 2 * c, ok ? grow + gx : src, ok);
       }
     } else {
-      for (int c = l; c < TXP; c += 16) {
+      for (int c = l; c < TXP; c += lpr) {
         const int gx = x0 + c - XH;
         const bool ok = rowok && gx >= 0 && gx < W;
         vx_cp_async4(srow + c, ok ? grow + gx : src, ok);
       }
     }
     hy += nsub;
-    while (hy >= HY) { hy -= HY; ++hz; }
+    while (hy >= HY) { hy -= HY; ++rz; }
+    while (rz >= HZ) { rz -= HZ; ++ch; }
   }
 }
 

@@ -213,77 +213,96 @@ __global__ void __launch_bounds__(32 * PWS_MAX_KS) pw_small_kernel(const __grid_
   }
 
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int cg = 0;                                             // channel index in the concatenated input
-  int step = 0;                                           // work-item counter for the round-robin K split
+  int cg0 = 0;                                            // channel index of the source's first channel in the concatenated input
+  // One 8-channel block = 8 coalesced X loads + 8 warp-uniform 16-byte weight loads, then 32 FMAs.  The kernel is a latency
+  // chain (one or two warps per scheduler), so a warp takes its blocks (ks, ks + KS, ...) two at a time: the 32 loads of both
+  // are in flight before the first FMA -- half as many dependent memory round trips as one block per iteration (the K = 256-512
+  // contractions of level 4 were 8 round trips per warp, 15-22 us per launch for 7-14 MFLOP; profiles/r3g kernel table).
+  auto load_block = [&](const float* xp, int c, int cg, const float* w0, int ld, float (&x)[8], float4 (&w)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = ok ? __ldg(xp + (size_t)(c + i) * S) : 0.f;
+    if (!P.transposed) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {      // w[2j], w[2j+1] = row j, k 0..3 and 4..7
+        w[2 * j] = __ldg(reinterpret_cast<const float4*>(rp[j] + cg));
+        w[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(rp[j] + cg + 4));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(w0 + (size_t)i * ld));   // row k = i
+    }
+  };
+  auto fma_block = [&](int cg, float (&x)[8], const float4 (&w)[8]) {
+    if (P.pro == PRO_AFFINE) {
+      const int q = b * P.pro_bstride + cg;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], __ldg(P.pro_a + q + i), __ldg(P.pro_c + q + i));
+    } else if (P.pro != PRO_NONE) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        x[i] = pw_pro_heavy(P.pro, x[i], P.pro_seed + soff, P.pro_site, ((uint64_t)b * P.Ci + cg + i) * (uint64_t)S + v,
+                            P.pro_drop_p, pinv);
+    }
+    if (!P.transposed) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 a = w[2 * j], q = w[2 * j + 1];
+        acc[j] = fmaf(a.x, x[0], acc[j]); acc[j] = fmaf(a.y, x[1], acc[j]); acc[j] = fmaf(a.z, x[2], acc[j]);
+        acc[j] = fmaf(a.w, x[3], acc[j]); acc[j] = fmaf(q.x, x[4], acc[j]); acc[j] = fmaf(q.y, x[5], acc[j]);
+        acc[j] = fmaf(q.z, x[6], acc[j]); acc[j] = fmaf(q.w, x[7], acc[j]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[0] = fmaf(w[i].x, x[i], acc[0]); acc[1] = fmaf(w[i].y, x[i], acc[1]);
+        acc[2] = fmaf(w[i].z, x[i], acc[2]); acc[3] = fmaf(w[i].w, x[i], acc[3]);
+      }
+    }
+  };
+  // weight rows of block `blk` of the current source are vector-loadable (uniform over the CTA)
+  auto block_vec = [&](int cg, const float*& w0, int& ld) -> bool {
+    if (!P.transposed) { w0 = nullptr; ld = 0; return rows_vec && (cg & 3) == 0; }
+    int ld7;
+    w0 = pw_w_row(P, co0, cg, ld);
+    return quad && (((uintptr_t)w0 & 15) == 0) && ((ld & 3) == 0) && pw_w_row(P, co0, cg + 7, ld7) == w0 + (size_t)7 * ld;
+  };
 #pragma unroll 1
   for (int s = 0; s < P.nsrc; ++s) {
     const int Cs = P.src[s].C;
     const float* xp = P.src[s].ptr + (size_t)b * Cs * S + v;
-    int c = 0;
-    // 8 input channels per step: every load of the step is issued before the first FMA (the kernel is latency-bound:
-    // one or two warps per scheduler), 8 coalesced X loads + 8 warp-uniform 16-byte weight loads in flight
-#pragma unroll 1
-    for (; c + 8 <= Cs; c += 8, cg += 8) {
-      const float* w0 = nullptr;
-      int ld = 0;
-      bool vec;
-      if (!P.transposed) {
-        vec = rows_vec && (cg & 3) == 0;
-      } else {
-        int ld7;
-        w0 = pw_w_row(P, co0, cg, ld);
-        vec = quad && (((uintptr_t)w0 & 15) == 0) && ((ld & 3) == 0) && pw_w_row(P, co0, cg + 7, ld7) == w0 + (size_t)7 * ld;
-      }
-      if (!vec) break;                                   // odd shapes: the scalar loop below finishes this source
-      if ((step++) % KS != ks) continue;
-      float x[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = ok ? __ldg(xp + (size_t)(c + i) * S) : 0.f;
-      float4 w[8];
-      if (!P.transposed) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {      // w[2j], w[2j+1] = row j, k 0..3 and 4..7
-          w[2 * j] = __ldg(reinterpret_cast<const float4*>(rp[j] + cg));
-          w[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(rp[j] + cg + 4));
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(w0 + (size_t)i * ld));   // row k = i
-      }
-      if (P.pro == PRO_AFFINE) {
-        const int q = b * P.pro_bstride + cg;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], __ldg(P.pro_a + q + i), __ldg(P.pro_c + q + i));
-      } else if (P.pro != PRO_NONE) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          x[i] = pw_pro_heavy(P.pro, x[i], P.pro_seed + soff, P.pro_site, ((uint64_t)b * P.Ci + cg + i) * (uint64_t)S + v,
-                              P.pro_drop_p, pinv);
-      }
-      if (!P.transposed) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 a = w[2 * j], q = w[2 * j + 1];
-          acc[j] = fmaf(a.x, x[0], acc[j]); acc[j] = fmaf(a.y, x[1], acc[j]); acc[j] = fmaf(a.z, x[2], acc[j]);
-          acc[j] = fmaf(a.w, x[3], acc[j]); acc[j] = fmaf(q.x, x[4], acc[j]); acc[j] = fmaf(q.y, x[5], acc[j]);
-          acc[j] = fmaf(q.z, x[6], acc[j]); acc[j] = fmaf(q.w, x[7], acc[j]);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc[0] = fmaf(w[i].x, x[i], acc[0]); acc[1] = fmaf(w[i].y, x[i], acc[1]);
-          acc[2] = fmaf(w[i].z, x[i], acc[2]); acc[3] = fmaf(w[i].w, x[i], acc[3]);
-        }
-      }
+    // vector part: leading 8-channel blocks whose weights are vector-loadable (the first block that is not ends it for everyone)
+    int nvec = 0;
+    {
+      const float* w0; int ld;
+      while ((nvec + 1) * 8 <= Cs && block_vec(cg0 + nvec * 8, w0, ld)) ++nvec;
     }
 #pragma unroll 1
-    for (; c < Cs; ++c, ++cg) {
-      if ((step++) % KS != ks) continue;
+    for (int blk = ks; blk < nvec; blk += 2 * KS) {
+      const int blk2 = blk + KS;
+      const bool two = blk2 < nvec;
+      float xa[8], xb[8];
+      float4 wa[8], wb[8];
+      const float* w0a; const float* w0b = nullptr;
+      int lda, ldb = 0;
+      block_vec(cg0 + blk * 8, w0a, lda);
+      load_block(xp, blk * 8, cg0 + blk * 8, w0a, lda, xa, wa);
+      if (two) {
+        block_vec(cg0 + blk2 * 8, w0b, ldb);
+        load_block(xp, blk2 * 8, cg0 + blk2 * 8, w0b, ldb, xb, wb);
+      }
+      fma_block(cg0 + blk * 8, xa, wa);
+      if (two) fma_block(cg0 + blk2 * 8, xb, wb);
+    }
+    // scalar remainder of this source, dealt to the warps channel by channel
+#pragma unroll 1
+    for (int c = nvec * 8 + ks; c < Cs; c += KS) {
+      const int cg = cg0 + c;
       float x = ok ? __ldg(xp + (size_t)c * S) : 0.f;
       if (P.pro != PRO_NONE) x = pw_prologue(P, x, b, cg, v, S, pinv, soff);
 #pragma unroll
       for (int j = 0; j < 4; ++j) if (co0 + j < Co) acc[j] = fmaf(__ldg(pw_w_ptr(P, co0 + j, cg)), x, acc[j]);
     }
+    cg0 += Cs;
   }
   if (KS > 1) {
 #pragma unroll
