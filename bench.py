@@ -4,7 +4,7 @@
 Workload (BASELINE.json configs[1]): VeloxSeg AutoPET-II training step, 4 patches (2 x 96^3) per GPU per step
 (train_config_bs4.json: batch_size 2 x num_samples 2), full loss (CE + Dice over 4 deep outputs, 0.5 MSE
 reconstruction, 2.0 SDKT), backward, AdamW.  Synthetic inputs, seeded He-init weights.  One rank per GPU; weak
-scaling (every rank steps its own 4 patches, gradients all-reduced in buckets during backward).
+scaling (every rank steps its own 4 patches; the flat 9 MB gradient is all-reduced by NCCL inside the captured step graph).
 
 value   patches/s with the batch resident in HBM (CUDA events per step, L2 flushed between steps, max over ranks)
 e2e     the same step through veloxseg_b200.train.TrainStep.step with pinned HOST batches: H2D copy of inputs and
@@ -312,7 +312,8 @@ def run_ours(args, rank, world, local_rank):
                    "patches_per_gpu": PATCHES, "global_patches": PATCHES * world, "parallelism": f"dp{world}",
                    "cache": "L2 flushed (256 MiB memset) between timed steps",
                    "launch": ("eager launches" if not used_graph else "whole step replayed as one CUDA graph" if world == 1 else
-                              "CUDA graph (fwd+bwd) -> one NCCL all-reduce of the flat 9 MB gradient -> CUDA graph (AdamW)"),
+                              ("one CUDA graph per rank: fwd + bwd + NCCL all-reduce of the flat 9 MB gradient (captured) + AdamW" if os.environ.get("VX_DP_GRAPH", "one") != "split"
+                               else "CUDA graph (fwd+bwd) -> eager NCCL all-reduce of the flat 9 MB gradient -> CUDA graph (AdamW)")),
                    "pointwise": "tcgen05 3xTF32 (fp32-accurate) for S>=1024 (weight gradients S>=512), fp32 SIMT below" if pw_tc else "fp32 SIMT",
                    "convolutions": "all libveloxseg: out_conv1 / RC out_conv tcgen05 3xTF32 implicit GEMM with fused bias + PixelShuffle, "
                                    "DownConv / UpConv / heads / stems fp32 SIMT; no cuDNN or cuBLAS kernel in the step",
@@ -321,6 +322,13 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_bytes_per_step": int(xb[0].numel() * xb[0].element_size() + yb[0].numel() * yb[0].element_size()),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "host_enqueue_ms_per_step": round(enqueue_ms, 2), "clocks": clk.summary(), "roofline": roof, "loss": last_loss, "top_kernels": table,
+        # whole step against the pipes: algorithmic flops / bytes of every launch that carries a model
+        # (contractions, convolutions; the attention and element-wise kernels carry bytes only or nothing) over the timed step
+        "step_rates": (lambda fl, by: {"alg_gflop_per_step": round(fl / 1e9, 2), "alg_tflops": round(fl / (ms_total / args.steps * 1e-3) / 1e12, 2),
+                                       "frac_of_fp32_fma_peak": round(fl / (ms_total / args.steps * 1e-3) / 1e12 / fp32_tflops, 4) if fp32_tflops else None,
+                                       "alg_gbytes_per_step": round(by / 1e9, 3),
+                                       "alg_gbs": round(by / (ms_total / args.steps * 1e-3) / 1e9, 1)})(
+            sum(r[5] for r in rows) / nprof, sum(r[4] for r in rows) / nprof) if rank == 0 and rows else None,
         "peaks": {"hbm_gbs": hbm, "bf16_tflops": tensor_peak, "source": how, "fp32_fma_tflops_measured": round(fp32_tflops, 1),
                   "fp32_fma_how": "vx_microbench: 8 independent FMA chains per thread, 148 x 8 CTAs of 256 threads, best of 5"},
     }

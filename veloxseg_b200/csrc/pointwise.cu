@@ -202,12 +202,13 @@ __global__ void __launch_bounds__(32 * PWS_MAX_KS) pw_small_kernel(const __grid_
 
   // forward orientation: the four weight rows of this warp (a row never crosses an output segment)
   const float* rp[4] = {nullptr, nullptr, nullptr, nullptr};
-  bool rows_vec = quad && !P.transposed;
+  // fewer than 4 live rows (the 2-class heads): the missing rows alias the last live one, their accumulators are never stored
+  bool rows_vec = !P.transposed;
   if (!P.transposed) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int ld;
-      rp[j] = pw_w_row(P, quad ? co0 + j : co0, 0, ld);
+      rp[j] = pw_w_row(P, co0 + j < Co ? co0 + j : Co - 1, 0, ld);
       rows_vec = rows_vec && (((uintptr_t)rp[j] & 15) == 0) && ((ld & 3) == 0);
     }
   }
