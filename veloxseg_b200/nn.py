@@ -740,6 +740,14 @@ class VeloxSeg(nn.Module):
     def forward(self, x):
         if self.training:
             attns, encs = self.encoder(x)
+            # encoder / decoder boundary for a two-phase backward (train.TrainStep, data-parallel overlap): with `split_boundary`
+            # the decoders consume detached aliases of the encoder outputs (same storage, new autograd leaves), so phase 1
+            # differentiates the loss down to `_boundary` only and phase 2 feeds those gradients into `_boundary_src`
+            if getattr(self, "split_boundary", False):
+                self._boundary_src = [a for lvl in attns for a in lvl] + list(encs)
+                attns = [[a.detach().requires_grad_(True) for a in lvl] for lvl in attns]
+                encs = [e.detach().requires_grad_(True) for e in encs]
+                self._boundary = [a for lvl in attns for a in lvl] + list(encs)
             fork = self.parallel_branches and x.is_cuda
             rcs, rc_prams = [None] * self.num_modalities, [None] * self.num_modalities
             if fork:

@@ -167,8 +167,9 @@ class VxAdamW:
         self.betas, self.eps = tuple(sd["betas"]), float(sd["eps"])
         self.set_lr(sd["lr"], sd["weight_decay"])
 
-    def grad_source(self, flat: Optional[torch.Tensor], params=None):
-        """Read the gradients of `params` (in order) from consecutive slices of `flat` instead of `p.grad`; None resets."""
+    def grad_source(self, flat: Optional[torch.Tensor], params=None, append: bool = False):
+        """Read the gradients of `params` (in order) from consecutive slices of `flat` instead of `p.grad`; None resets;
+        `append=True` adds a second flat buffer (parameters not named by any buffer are skipped by the step)."""
         if flat is None:
             self._grad_src = None
             return
@@ -180,7 +181,10 @@ class VxAdamW:
             off += p.numel()
         if off != flat.numel():
             raise ValueError("VxAdamW.grad_source: flat buffer size does not match the parameter list")
-        self._grad_src = ptrs
+        if append and self._grad_src is not None:
+            self._grad_src.update(ptrs)
+        else:
+            self._grad_src = ptrs
 
     def _table(self):
         rows = []
@@ -256,6 +260,11 @@ class TrainStep:
         # libveloxseg's one-launch AdamW on CUDA (VX_TORCH_ADAMW=1 keeps torch's fused multi-tensor optimiser for A/B)
         import os
         self.split_graph = os.environ.get("VX_DP_GRAPH", "one") == "split"
+        # VX_DP_OVERLAP=1: two-phase backward with the decoder-side all-reduce under the encoder backward (world > 1, one-graph
+        # form).  Measured SLOWER on 2 x B200 (6.93 vs 6.59 ms/step, profiles/r3j_dp_overlap_2gpu.txt): phase 1 has to join every
+        # forked decoder stream before the encoder backward may start, which costs more than the ~0.15 ms of exposed all-reduce
+        # it hides.  Off by default; kept as an A/B switch (parity: tests/test_gpu_dp.py passes with it on).
+        self.overlap = os.environ.get("VX_DP_OVERLAP", "0") == "1" and hasattr(self.model, "encoder")
         if cuda and os.environ.get("VX_TORCH_ADAMW", "0") != "1":
             self.opt = VxAdamW(self.model.parameters(), lr=lr, weight_decay=weight_decay)
         else:
@@ -306,6 +315,43 @@ class TrainStep:
                 else:
                     g["lr"] = lr
 
+    def _fwd_bwd_overlapped(self, x, y):
+        """world > 1: backward in two phases at the encoder / decoder boundary.  Phase 1 differentiates the loss with respect
+        to the decoder-side parameters (segmentation decoder, reconstruction teachers, heads) and the boundary tensors; the
+        all-reduce of those gradients (about half of the 9 MB) is then in flight on a communication stream while phase 2
+        runs the encoder backward.  Returns (loss, [(flat, params), ...]) with both all-reduces issued."""
+        from . import ops
+        ops.advance_seed(self.device)
+        self.model.split_boundary = True
+        try:
+            out = self.model(x)
+        finally:
+            self.model.split_boundary = False
+        loss = self.loss_fn(out, y, x)
+        enc_ids = {id(p) for p in self.model.encoder.parameters()}
+        dec_params = [p for p in self.params if id(p) not in enc_ids]
+        enc_params = [p for p in self.params if id(p) in enc_ids]
+        boundary, boundary_src = self.model._boundary, self.model._boundary_src
+        g = torch.autograd.grad(loss, dec_params + boundary, allow_unused=True)
+        gd, gb = g[:len(dec_params)], g[len(dec_params):]
+        live = [(p, gi) for p, gi in zip(dec_params, gd) if gi is not None]
+        flat_a = torch.cat([gi.reshape(-1) for _, gi in live])
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        comm = self._comm_stream
+        comm.wait_stream(cur)
+        flat_a.record_stream(comm)
+        with torch.cuda.stream(comm):
+            dist.all_reduce(flat_a, op=dist.ReduceOp.SUM)
+        bt = [(t, gt) for t, gt in zip(boundary_src, gb) if gt is not None and t.requires_grad]
+        torch.autograd.backward([t for t, _ in bt], [gt for _, gt in bt])
+        enc_live = [p for p in enc_params if p.grad is not None]
+        flat_b = torch.cat([p.grad.reshape(-1) for p in enc_live])
+        dist.all_reduce(flat_b, op=dist.ReduceOp.SUM)
+        cur.wait_stream(comm)
+        return loss.detach(), [(flat_a, [p for p, _ in live]), (flat_b, enc_live)]
+
     def _reduce_and_step_flat(self):
         """world > 1, own optimiser: gather -> all-reduce(sum) -> AdamW reads the flat buffer scaled by 1 / world."""
         self._gparams = [p for p in self.params if p.grad is not None]
@@ -325,6 +371,14 @@ class TrainStep:
         else:
             for p in self.params:
                 p.grad = None
+            if self.world > 1 and isinstance(self.opt, VxAdamW) and not self.split_graph and self.overlap:
+                loss, parts = self._fwd_bwd_overlapped(x, y)
+                self.opt.grad_scale = 1.0 / self.world
+                for i, (flat, ps) in enumerate(parts):
+                    self.opt.grad_source(flat, ps, append=i > 0)
+                self.opt.step()
+                self._flat = parts
+                return loss
             loss = self._fwd_bwd(x, y)
             if self.world > 1:
                 if isinstance(self.opt, VxAdamW) and not self.split_graph:
