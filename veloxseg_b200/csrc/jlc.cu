@@ -1419,6 +1419,19 @@ extern "C" int vx_jlc_fwd(const vx_jlc_desc* d, const void* const* in, void* con
             part_o, (int*)(ws + L.off_cnt), aff_a, aff_c, rows, S, L.chunk, d->eps);
   VX_TRY(check_launch("jlc_combine_kernel"));
 
+  // small levels: both contractions in one launch (the hidden activation stays in shared memory)
+  {
+    FfnBatch fb{};
+    fb.nprob = 1; fb.B = d->B; fb.S = S;
+    FfnProblem& f = fb.p[0];
+    f.x = o; f.C = d->C; f.pro_a = aff_a; f.pro_c = aff_c; f.pro_bstride = d->C;
+    f.W1 = (const float*)in[7]; f.b1 = (const float*)in[8]; f.eC = eC; f.hpre = hpre;
+    f.W2 = (const float*)in[9]; f.b2 = (const float*)in[10];
+    if (d->training && d->drop_p > 0.f) { f.drop_p = d->drop_p; f.seed = d->seed; f.site = 1; }
+    f.res = o; f.res_scale = 1.f; f.y = y;
+    const int rc = pw_ffn_small(fb, st);
+    if (rc <= 0) return rc;
+  }
   // hpre = W1 IN(o) + b1
   PwBatch pb{};
   pb.nprob = 1; pb.B = d->B; pb.S = S;
@@ -1492,8 +1505,18 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
     VX_TRY(stats_to_affine(stats_o, aff_a, aff_c, rows, sz));
   }
 
-  // dh = (W2^T (dy * mask)) * GELU'(hpre)
+  // dh = (W2^T (dy * mask)) * GELU'(hpre);  dohat = W1^T dh  -- one launch on the small levels
+  int ffn_fused = 0;
   {
+    FfnBwdBatch fb{}; fb.nprob = 1; fb.B = d->B; fb.S = S;
+    FfnBwdProblem& f = fb.p[0];
+    f.dy = dy; f.C = C; f.W2 = fw2; f.eC = eC; f.hpre = hpre; f.dh = dh; f.W1 = fw1; f.dx = dohat;
+    if (drop) { f.out_drop_p = d->drop_p; f.out_seed = d->seed; f.out_site = 1; }
+    const int rc = pw_ffn_small_bwd(fb, st);
+    if (rc != VX_OK && rc != 1) return rc;
+    ffn_fused = rc == VX_OK;
+  }
+  if (!ffn_fused) {
     PwBatch pb{}; pb.nprob = 1; pb.B = d->B; pb.S = S;
     PwProblem& p = pb.p[0];
     p.src[0] = PwSrc{dy, C}; p.nsrc = 1; p.Ci = C;
@@ -1516,7 +1539,7 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
     VX_TRY(pw_wgrad(wb, st));
   }
   // dohat = W1^T dh
-  {
+  if (!ffn_fused) {
     PwBatch pb{}; pb.nprob = 1; pb.B = d->B; pb.S = S;
     PwProblem& p = pb.p[0];
     p.src[0] = PwSrc{dh, eC}; p.nsrc = 1; p.Ci = eC;

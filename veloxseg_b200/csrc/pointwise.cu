@@ -406,6 +406,350 @@ int pw_forward(const PwBatch& batch, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Fused two-layer MLP of the small levels (S < 512: levels 3-4).  CTA = FF_VT consecutive flattened voxels (f = b S + v) x
+// every channel; 256 threads.  Phase 1 stages the prologued input tile [C][FF_VT]; phase 2: thread = hidden channel (x a
+// share of the tile's voxels when eC < 256), whole K loop in registers, weights as 16-byte loads along the row; hpre goes to
+// global memory, GELU(hpre) (x mask) to shared memory; phase 3: thread = (output channel, slice of the hidden channels), the
+// slices meet in shared memory; epilogue: bias, dropout, residual.  One launch and no global round trip for the hidden
+// activation instead of two latency-bound pw_small_kernel launches (12-16 us each for 7-28 MFLOP).
+// ---------------------------------------------------------------------------------------------------
+constexpr int FF_VT = 8, FF_THREADS = 256, FF_MAX_C = 128, FF_MAX_E = 256;
+
+__global__ void __launch_bounds__(FF_THREADS) pw_ffn_small_kernel(const __grid_constant__ FfnBatch batch) {
+  VX_PDL_ENTRY();
+  const FfnProblem& P = batch.p[blockIdx.y];
+  const int S = batch.S, C = P.C, eC = P.eC, tid = threadIdx.x;
+  const int f0 = blockIdx.x * FF_VT, total = batch.B * S;
+  __align__(16) __shared__ float xs[FF_MAX_C][FF_VT];
+  __align__(16) __shared__ float hs[FF_MAX_E][FF_VT];
+  __align__(16) __shared__ float red[FF_THREADS][FF_VT];
+  __shared__ int vb[FF_VT], vv[FF_VT];
+  const uint64_t soff = batch.seed_dev ? (uint64_t)__ldg(batch.seed_dev) : 0;
+  if (tid < FF_VT) {
+    const int f = f0 + tid;
+    vb[tid] = f < total ? f / S : -1;
+    vv[tid] = f < total ? f % S : 0;
+  }
+  __syncthreads();
+  // ---- phase 1: xs[c][i] = a x + c
+  for (int e = tid; e < C * FF_VT; e += FF_THREADS) {
+    const int c = e / FF_VT, i = e % FF_VT;
+    float v = 0.f;
+    if (vb[i] >= 0) {
+      v = __ldg(P.x + ((size_t)vb[i] * C + c) * S + vv[i]);
+      if (P.pro_a) { const int q = vb[i] * P.pro_bstride + c; v = fmaf(v, __ldg(P.pro_a + q), __ldg(P.pro_c + q)); }
+    }
+    xs[c][i] = v;
+  }
+  __syncthreads();
+  // ---- phase 2: hidden channel j, voxel share [i0, i0 + nv)
+  {
+    const int nsp = eC <= 64 ? 4 : (eC <= 128 ? 2 : 1);       // threads per hidden channel
+    const int j = tid / nsp, nv = FF_VT / nsp, i0 = (tid % nsp) * nv;
+    if (j < eC) {
+      float acc[FF_VT];
+#pragma unroll
+      for (int i = 0; i < FF_VT; ++i) acc[i] = 0.f;
+      const float* wrow = P.W1 + (size_t)j * C;
+      // 8 weight loads (32 input channels) in flight per thread: the row walk is the latency chain of this phase
+#pragma unroll 1
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        float4 w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = c0 + 4 * u < C ? __ldg(reinterpret_cast<const float4*>(wrow + c0 + 4 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c = c0 + 4 * u;
+          if (c >= C) break;
+          const float ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int i = 0; i < FF_VT; ++i)
+              if (i < nv) acc[i] = fmaf(ww[k], xs[c + k][i0 + i], acc[i]);
+        }
+      }
+      const float bj = P.b1 ? __ldg(P.b1 + j) : 0.f;
+      const float minv = P.mid_drop_p > 0.f ? 1.0f / (1.0f - P.mid_drop_p) : 1.f;
+      const uint32_t mkey = P.mid_drop_p > 0.f ? rng_key(P.mid_seed + soff, P.mid_site) : 0u;
+#pragma unroll
+      for (int i = 0; i < FF_VT; ++i) {
+        if (i < nv) {
+          const int ii = i0 + i;
+          float h = 0.f;
+          if (vb[ii] >= 0) {
+            const float pre = acc[i] + bj;
+            const size_t idx = ((size_t)vb[ii] * eC + j) * S + vv[ii];
+            P.hpre[idx] = pre;
+            h = gelu_f(pre);
+            if (P.mid_drop_p > 0.f) h *= keep_from_bits(rng_word(mkey, idx), P.mid_drop_p, minv);
+          }
+          hs[j][ii] = h;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 3: output channel c, hidden slice `part`
+  {
+    const int parts = FF_THREADS / C;                       // C is a power of two <= 128 on this path: 2, 4, 8, ...
+    const int c = tid % C, part = tid / C;
+    const int per = ((eC + parts - 1) / parts + 3) & ~3;    // slices start on 16-byte boundaries of the weight row; late ones may be empty
+    const int j0 = part * per < eC ? part * per : eC, j1 = j0 + per < eC ? j0 + per : eC;
+    float acc[FF_VT];
+#pragma unroll
+    for (int i = 0; i < FF_VT; ++i) acc[i] = 0.f;
+    const float* wrow = P.W2 + (size_t)c * eC;
+    int j = j0;
+#pragma unroll 1
+    for (; j + 32 <= j1; j += 32) {                         // 8 weight loads in flight
+      float4 w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(wrow + j + 4 * u));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 ha = *reinterpret_cast<const float4*>(&hs[j + 4 * u + k][0]), hb = *reinterpret_cast<const float4*>(&hs[j + 4 * u + k][4]);
+          acc[0] = fmaf(ww[k], ha.x, acc[0]); acc[1] = fmaf(ww[k], ha.y, acc[1]); acc[2] = fmaf(ww[k], ha.z, acc[2]); acc[3] = fmaf(ww[k], ha.w, acc[3]);
+          acc[4] = fmaf(ww[k], hb.x, acc[4]); acc[5] = fmaf(ww[k], hb.y, acc[5]); acc[6] = fmaf(ww[k], hb.z, acc[6]); acc[7] = fmaf(ww[k], hb.w, acc[7]);
+        }
+      }
+    }
+#pragma unroll 1
+    for (; j + 4 <= j1; j += 4) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + j));
+      const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 ha = *reinterpret_cast<const float4*>(&hs[j + k][0]), hb = *reinterpret_cast<const float4*>(&hs[j + k][4]);
+        acc[0] = fmaf(ww[k], ha.x, acc[0]); acc[1] = fmaf(ww[k], ha.y, acc[1]); acc[2] = fmaf(ww[k], ha.z, acc[2]); acc[3] = fmaf(ww[k], ha.w, acc[3]);
+        acc[4] = fmaf(ww[k], hb.x, acc[4]); acc[5] = fmaf(ww[k], hb.y, acc[5]); acc[6] = fmaf(ww[k], hb.z, acc[6]); acc[7] = fmaf(ww[k], hb.w, acc[7]);
+      }
+    }
+    for (; j < j1; ++j) {
+      const float w = __ldg(wrow + j);
+#pragma unroll
+      for (int i = 0; i < FF_VT; ++i) acc[i] = fmaf(w, hs[j][i], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < FF_VT; ++i) red[tid][i] = acc[i];
+    __syncthreads();
+    // epilogue: item = (c, voxel); the slices fold in fixed order
+    const float dinv = P.drop_p > 0.f ? 1.0f / (1.0f - P.drop_p) : 1.f;
+    const uint32_t okey = P.drop_p > 0.f ? rng_key(P.seed + soff, P.site) : 0u;
+    for (int e = tid; e < C * FF_VT; e += FF_THREADS) {
+      const int cc = e / FF_VT, i = e % FF_VT;
+      if (vb[i] < 0) continue;
+      float y = P.b2 ? __ldg(P.b2 + cc) : 0.f;
+      for (int pp = 0; pp < parts; ++pp) y += red[pp * C + cc][i];
+      const size_t idx = ((size_t)vb[i] * C + cc) * S + vv[i];
+      if (P.drop_p > 0.f) y *= keep_from_bits(rng_word(okey, idx), P.drop_p, dinv);
+      if (P.res) y = fmaf(P.res_scale, __ldg(P.res + idx), y);
+      P.y[idx] = y;
+    }
+  }
+}
+
+static int g_ffn_fused = 1;
+void pw_ffn_set(int on) { g_ffn_fused = on; }
+
+int pw_ffn_small(const FfnBatch& batch, cudaStream_t stream) {
+  if (!g_ffn_fused || batch.nprob <= 0 || batch.S >= g_small_max_s) return 1;
+  double bytes = 0.0, flops = 0.0;
+  for (int i = 0; i < batch.nprob; ++i) {
+    const FfnProblem& P = batch.p[i];
+    // C a power of two in [8, 128] (phase 3 deals 256 threads to C channels), eC <= 256, 16-byte weight rows
+    if (P.C < 8 || P.C > FF_MAX_C || (P.C & (P.C - 1)) || P.eC > FF_MAX_E || (P.eC & 3) || ((uintptr_t)P.W1 & 15) || ((uintptr_t)P.W2 & 15)) return 1;
+    bytes += 4.0 * batch.B * batch.S * (2.0 * P.C + P.eC + (P.res ? P.C : 0)) + 8.0 * P.C * P.eC;
+    flops += 4.0 * batch.B * batch.S * P.C * P.eC;
+  }
+  FfnBatch launch = batch;
+  launch.seed_dev = get_seed_dev();
+  prof_bytes(bytes);
+  prof_flops(flops);
+  VX_LAUNCH(pw_ffn_small_kernel, dim3(cdiv((long long)batch.B * batch.S, FF_VT), batch.nprob), dim3(FF_THREADS), 0, stream, launch);
+  return check_launch("pw_ffn_small_kernel");
+}
+
+// Data gradient of the fused MLP (same tiling).  Both contractions use the weights TRANSPOSED, so a thread walks a COLUMN of
+// the stored matrix: threads own 4 adjacent columns (one 16-byte load per row, adjacent threads adjacent quads -- fully
+// coalesced) and the rows of the reduction are split over thread groups that meet in shared memory.
+//   phase 2: dh[j][i] = (sum_c W2[c][j] dym[c][i]) GELU'(hpre[j][i]) mask1       thread = (j quad, share of the tile's voxels)
+//   phase 3: dx[c][i] = sum_j W1[j][c] dh[j][i]                                  thread = (c quad, slice of the hidden rows)
+__global__ void __launch_bounds__(FF_THREADS) pw_ffn_small_bwd_kernel(const __grid_constant__ FfnBwdBatch batch) {
+  VX_PDL_ENTRY();
+  const FfnBwdProblem& P = batch.p[blockIdx.y];
+  const int S = batch.S, C = P.C, eC = P.eC, tid = threadIdx.x;
+  const int f0 = blockIdx.x * FF_VT, total = batch.B * S;
+  __align__(16) __shared__ float ds[FF_MAX_C][FF_VT];           // dy * mask2
+  __align__(16) __shared__ float hs[FF_MAX_E][FF_VT];           // dh
+  __align__(16) __shared__ float red[8 * FF_MAX_C][FF_VT];      // phase-3 slices: [part][c][voxel], parts * C <= 1024
+  __shared__ int vb[FF_VT], vv[FF_VT];
+  const uint64_t soff = batch.seed_dev ? (uint64_t)__ldg(batch.seed_dev) : 0;
+  if (tid < FF_VT) {
+    const int f = f0 + tid;
+    vb[tid] = f < total ? f / S : -1;
+    vv[tid] = f < total ? f % S : 0;
+  }
+  __syncthreads();
+  {
+    const float oinv = P.out_drop_p > 0.f ? 1.0f / (1.0f - P.out_drop_p) : 1.f;
+    const uint32_t okey = P.out_drop_p > 0.f ? rng_key(P.out_seed + soff, P.out_site) : 0u;
+    for (int e = tid; e < C * FF_VT; e += FF_THREADS) {
+      const int c = e / FF_VT, i = e % FF_VT;
+      float v = 0.f;
+      if (vb[i] >= 0) {
+        const size_t idx = ((size_t)vb[i] * C + c) * S + vv[i];
+        v = __ldg(P.dy + idx);
+        if (P.out_drop_p > 0.f) v *= keep_from_bits(rng_word(okey, idx), P.out_drop_p, oinv);
+      }
+      ds[c][i] = v;
+    }
+  }
+  __syncthreads();
+  // ---- phase 2
+  {
+    const int Q = eC >> 2;                                  // column quads of W2 (<= 64)
+    const int nsp = FF_THREADS / Q < FF_VT ? FF_THREADS / Q : FF_VT;      // voxel shares
+    const int nv = FF_VT / nsp;
+    const int jq = tid % Q, vs = tid / Q;
+    if (vs < nsp) {
+      const int i0 = vs * nv;
+      float acc[4][FF_VT];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < FF_VT; ++i) acc[k][i] = 0.f;
+      const float* wcol = P.W2 + 4 * jq;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C; c0 += 8) {                   // 8 rows in flight
+        float4 w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(wcol + (size_t)(c0 + u) * eC));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+          for (int i = 0; i < FF_VT; ++i) {
+            if (i < nv) {
+              const float dv = ds[c0 + u][i0 + i];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) acc[k][i] = fmaf(ww[k], dv, acc[k][i]);
+            }
+          }
+        }
+      }
+      const float minv = P.mid_drop_p > 0.f ? 1.0f / (1.0f - P.mid_drop_p) : 1.f;
+      const uint32_t mkey = P.mid_drop_p > 0.f ? rng_key(P.mid_seed + soff, P.mid_site) : 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = 4 * jq + k;
+#pragma unroll
+        for (int i = 0; i < FF_VT; ++i) {
+          if (i < nv) {
+            const int ii = i0 + i;
+            float g = 0.f;
+            if (vb[ii] >= 0) {
+              const size_t idx = ((size_t)vb[ii] * eC + j) * S + vv[ii];
+              g = acc[k][i] * gelu_grad_f(__ldg(P.hpre + idx));
+              if (P.mid_drop_p > 0.f) g *= keep_from_bits(rng_word(mkey, idx), P.mid_drop_p, minv);
+              P.dh[idx] = g;
+            }
+            hs[j][ii] = g;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 3
+  {
+    const int Q = C >> 2;                                   // column quads of W1 (2 ... 32)
+    const int parts = 8;                                    // slices of the hidden rows; parts * C <= 1024 rows of `red`
+    const int nsp = FF_THREADS / (Q * parts) < FF_VT ? FF_THREADS / (Q * parts) : FF_VT;      // voxel shares (1 ... 8)
+    const int nv = FF_VT / nsp;
+    const int cq = tid % Q, part = (tid / Q) % parts, vs = tid / (Q * parts);
+    if (vs < nsp) {
+      const int i0 = vs * nv;
+      const int per = (eC + parts - 1) / parts;
+      const int j0 = part * per < eC ? part * per : eC, j1 = j0 + per < eC ? j0 + per : eC;
+      float acc[4][FF_VT];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < FF_VT; ++i) acc[k][i] = 0.f;
+      const float* wcol = P.W1 + 4 * cq;
+      int j = j0;
+#pragma unroll 1
+      for (; j + 8 <= j1; j += 8) {
+        float4 w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(wcol + (size_t)(j + u) * C));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+          for (int i = 0; i < FF_VT; ++i) {
+            if (i < nv) {
+              const float hv = hs[j + u][i0 + i];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) acc[k][i] = fmaf(ww[k], hv, acc[k][i]);
+            }
+          }
+        }
+      }
+      for (; j < j1; ++j) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wcol + (size_t)j * C));
+        const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < FF_VT; ++i) {
+          if (i < nv) {
+            const float hv = hs[j][i0 + i];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k][i] = fmaf(ww[k], hv, acc[k][i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < FF_VT; ++i)
+          if (i < nv) red[part * C + 4 * cq + k][i0 + i] = acc[k][i];
+    }
+    __syncthreads();
+    for (int e = tid; e < C * FF_VT; e += FF_THREADS) {
+      const int cc = e / FF_VT, i = e % FF_VT;
+      if (vb[i] < 0) continue;
+      float y = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < parts; ++pp) y += red[pp * C + cc][i];
+      P.dx[((size_t)vb[i] * C + cc) * S + vv[i]] = y;
+    }
+  }
+}
+
+int pw_ffn_small_bwd(const FfnBwdBatch& batch, cudaStream_t stream) {
+  if (!g_ffn_fused || batch.nprob <= 0 || batch.S >= g_small_max_s) return 1;
+  double bytes = 0.0, flops = 0.0;
+  for (int i = 0; i < batch.nprob; ++i) {
+    const FfnBwdProblem& P = batch.p[i];
+    // C a power of two in [8, 128] (rows of 8 in flight), eC <= 256 and a multiple of 4, eC / 4 a divisor of 256, 16-byte rows
+    if (P.C < 8 || P.C > FF_MAX_C || (P.C & (P.C - 1)) || P.eC > FF_MAX_E || (P.eC & 3) || (FF_THREADS % (P.eC >> 2)) ||
+        ((uintptr_t)P.W1 & 15) || ((uintptr_t)P.W2 & 15)) return 1;
+    bytes += 4.0 * batch.B * batch.S * (2.0 * P.C + 2.0 * P.eC) + 8.0 * P.C * P.eC;
+    flops += 4.0 * batch.B * batch.S * P.C * P.eC;
+  }
+  FfnBwdBatch launch = batch;
+  launch.seed_dev = get_seed_dev();
+  prof_bytes(bytes);
+  prof_flops(flops);
+  VX_LAUNCH(pw_ffn_small_bwd_kernel, dim3(cdiv((long long)batch.B * batch.S, FF_VT), batch.nprob), dim3(FF_THREADS), 0, stream, launch);
+  return check_launch("pw_ffn_small_bwd_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // weight gradient
 // ---------------------------------------------------------------------------------------------------
 constexpr int WG_THREADS = 256;

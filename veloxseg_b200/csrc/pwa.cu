@@ -1042,6 +1042,24 @@ extern "C" int vx_pwa_block_fwd(const vx_pwa_desc* d, const void* const* in, voi
   for (int m = 0; m < M; ++m) { L2.x[m] = SV(SV_Y) + (size_t)m * C * BS; L2.xhat[m] = SV(SV_XHAT2) + (size_t)m * C * BS; L2.rstd[m] = SV(SV_RSTD2) + (size_t)m * BS; }
   VX_TRY(ln_forward(L2, st));
   {
+    // small levels: W1 -> GELU -> dropout -> W2 -> dropout -> residual in one launch
+    FfnBatch fb{}; fb.nprob = M; fb.B = B; fb.S = S;
+    for (int m = 0; m < M; ++m) {
+      FfnProblem& f = fb.p[m];
+      f.x = L2.xhat[m]; f.C = C; f.pro_a = PRM(m, PP_LN2W); f.pro_c = PRM(m, PP_LN2B); f.pro_bstride = 0;
+      f.W1 = PRM(m, PP_W1); f.b1 = PRM(m, PP_B1); f.eC = P.eC; f.hpre = SV(SV_HPRE) + (size_t)m * P.eC * BS;
+      f.W2 = PRM(m, PP_W2); f.b2 = PRM(m, PP_B2);
+      if (proj_p > 0.f) {
+        f.mid_drop_p = proj_p; f.mid_seed = d->seed + 0x1000 * (m + 1); f.mid_site = SITE_FFN1;
+        f.drop_p = proj_p; f.seed = d->seed + 0x1000 * (m + 1); f.site = SITE_FFN2;
+      }
+      f.res = SV(SV_Y) + (size_t)m * C * BS; f.res_scale = 1.f; f.y = Z(m);
+    }
+    const int rc = pw_ffn_small(fb, st);
+    if (rc < 0) return rc;
+    if (rc == 0) return VX_OK;
+  }
+  {
     PwBatch pb{}; pb.nprob = M; pb.B = B; pb.S = S;
     for (int m = 0; m < M; ++m) {
       PwProblem& p = pb.p[m];
@@ -1135,7 +1153,24 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
   auto seedm = [&](int m) { return d->seed + 0x1000 * (uint64_t)(m + 1); };
 
   // ---- FFN backward
+  int ffn_fused = 0;
   {
+    // dh = (W2^T (dz*m2)) * GELU'(hpre) * m1 and dln2 = W1^T dh in one launch on the small levels (it writes no zeroed buffer)
+    FfnBwdBatch fb{}; fb.nprob = M; fb.B = B; fb.S = S;
+    for (int m = 0; m < M; ++m) {
+      FfnBwdProblem& f = fb.p[m];
+      f.dy = DZ(m); f.C = C; f.W2 = PRM(m, PP_W2); f.eC = P.eC; f.hpre = SV(SV_HPRE) + (size_t)m * P.eC * BS;
+      f.dh = dh + (size_t)m * P.eC * BS; f.W1 = PRM(m, PP_W1); f.dx = dln2 + (size_t)m * C * BS;
+      if (proj_p > 0.f) {
+        f.out_drop_p = proj_p; f.out_seed = seedm(m); f.out_site = SITE_FFN2;
+        f.mid_drop_p = proj_p; f.mid_seed = seedm(m); f.mid_site = SITE_FFN1;
+      }
+    }
+    const int rc = pw_ffn_small_bwd(fb, st);
+    if (rc != VX_OK && rc != 1) return rc;
+    ffn_fused = rc == VX_OK;
+  }
+  if (!ffn_fused) {
     PwBatch pb{}; pb.nprob = M; pb.B = B; pb.S = S;     // dh = (W2^T (dz*m2)) * GELU'(hpre) * m1
     for (int m = 0; m < M; ++m) {
       PwProblem& p = pb.p[m];
@@ -1150,7 +1185,7 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
     VX_TRY(pw_forward(pb, st));
   }
   side_wait(st);       // every gradient buffer is zero from here on (nothing above touches one)
-  {
+  if (!ffn_fused) {
     PwBatch pb{}; pb.nprob = M; pb.B = B; pb.S = S;     // dln2 = W1^T dh
     for (int m = 0; m < M; ++m) {
       PwProblem& p = pb.p[m];

@@ -34,6 +34,40 @@ struct PwBatch { PwProblem p[VX_MAX_MODAL]; int nprob; int B; int S; const unsig
 
 int pw_forward(const PwBatch& batch, cudaStream_t stream);
 
+// ---------------------------------------------------------------------------------------------------
+// Two-layer channel MLP of the small levels in one launch (JLC channel_conv, conv_blocks.py:62-69; PWA FFN,
+// attention_utils.py:45-71):   hpre = W1 (a x + c) + b1;   y = res_scale * res + Drop2( W2 Drop1(GELU(hpre)) + b2 )
+// hpre is written out (the backward pass needs it), the hidden activation never leaves shared memory.
+// ---------------------------------------------------------------------------------------------------
+struct FfnProblem {
+  const float* x; int C;                                         // (B, C, S)
+  const float* pro_a; const float* pro_c; int pro_bstride;       // prologue affine per (b * bstride + c); null = identity
+  const float* W1; const float* b1; int eC;                      // (eC, C), (eC)
+  float* hpre;                                                   // (B, eC, S)
+  const float* W2; const float* b2;                              // (C, eC), (C)
+  float mid_drop_p; uint64_t mid_seed; uint32_t mid_site;        // dropout on GELU(hpre), mask indexed like hpre
+  float drop_p; uint64_t seed; uint32_t site;                    // dropout on the output, mask indexed like y
+  const float* res; float res_scale;                             // y += res_scale * res
+  float* y;                                                      // (B, C, S)
+};
+struct FfnBatch { FfnProblem p[VX_MAX_MODAL]; int nprob; int B; int S; const unsigned long long* seed_dev; };
+// VX_OK when launched, 1 when the shape is outside the kernel's range (the caller runs the two contractions instead)
+int pw_ffn_small(const FfnBatch& batch, cudaStream_t stream);
+// Data gradient of the same MLP in one launch:  dh = (W2^T (dy * mask2)) * GELU'(hpre) * mask1  (written out: the weight
+// gradients read it);  dx = W1^T dh  (the gradient at the prologue's output: the caller owns the norm backward).
+struct FfnBwdProblem {
+  const float* dy; int C;                                        // (B, C, S)
+  float out_drop_p; uint64_t out_seed; uint32_t out_site;        // mask of the output dropout, indexed like dy
+  const float* W2; int eC;                                       // (C, eC)
+  const float* hpre;                                             // (B, eC, S)
+  float mid_drop_p; uint64_t mid_seed; uint32_t mid_site;        // mask on GELU(hpre), indexed like hpre
+  float* dh;                                                     // (B, eC, S)
+  const float* W1;                                               // (eC, C)
+  float* dx;                                                     // (B, C, S)
+};
+struct FfnBwdBatch { FfnBwdProblem p[VX_MAX_MODAL]; int nprob; int B; int S; const unsigned long long* seed_dev; };
+int pw_ffn_small_bwd(const FfnBwdBatch& batch, cudaStream_t stream);
+
 #if defined(__CUDACC__) || defined(VX_EMU)
 // Address of one input element of the (possibly multi-source) X operand.
 VX_DEV const float* pw_x_ptr(const PwProblem& P, int b, int cg, int v, int S) {
