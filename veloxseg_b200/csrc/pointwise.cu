@@ -415,7 +415,67 @@ int pw_forward(const PwBatch& batch, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------------
 constexpr int FF_VT = 8, FF_THREADS = 256, FF_MAX_C = 128, FF_MAX_E = 256;
 
-__global__ void __launch_bounds__(FF_THREADS) pw_ffn_small_kernel(const __grid_constant__ FfnBatch batch) {
+// Row walk of the forward phases: acc[i] += W[row][c] * v[c][i0 + i] over c in [c0, c1) (c0 a multiple of 4), 8 16-byte weight
+// loads (32 columns) in flight.  NV (voxels per thread) is a template parameter so that no accumulator slot is predicated.
+template <int NV>
+VX_DEV void ffn_row_walk(const float* __restrict__ wrow, int c0, int c1, const float (*v)[FF_VT], int i0, float (&acc)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  int c = c0;
+#pragma unroll 1
+  for (; c + 32 <= c1; c += 32) {
+    float4 w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(wrow + c + 4 * u));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = fmaf(ww[k], v[c + 4 * u + k][i0 + i], acc[i]);
+    }
+  }
+#pragma unroll 1
+  for (; c + 4 <= c1; c += 4) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + c));
+    const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] = fmaf(ww[k], v[c + k][i0 + i], acc[i]);
+  }
+  for (; c < c1; ++c) {
+    const float w = __ldg(wrow + c);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = fmaf(w, v[c][i0 + i], acc[i]);
+  }
+}
+
+template <int NV>
+VX_DEV void ffn_fwd_hidden(const FfnProblem& P, int S, uint64_t soff, const float (*xs)[FF_VT], float (*hs)[FF_VT], const int* vb,
+                           const int* vv, int j, int i0) {
+  float acc[NV];
+  ffn_row_walk<NV>(P.W1 + (size_t)j * P.C, 0, P.C, xs, i0, acc);
+  const float bj = P.b1 ? __ldg(P.b1 + j) : 0.f;
+  const float minv = P.mid_drop_p > 0.f ? 1.0f / (1.0f - P.mid_drop_p) : 1.f;
+  const uint32_t mkey = P.mid_drop_p > 0.f ? rng_key(P.mid_seed + soff, P.mid_site) : 0u;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int ii = i0 + i;
+    float h = 0.f;
+    if (vb[ii] >= 0) {
+      const float pre = acc[i] + bj;
+      const size_t idx = ((size_t)vb[ii] * P.eC + j) * S + vv[ii];
+      P.hpre[idx] = pre;
+      h = gelu_f(pre);
+      if (P.mid_drop_p > 0.f) h *= keep_from_bits(rng_word(mkey, idx), P.mid_drop_p, minv);
+    }
+    hs[j][ii] = h;
+  }
+}
+
+__global__ void __launch_bounds__(FF_THREADS, 2) pw_ffn_small_kernel(const __grid_constant__ FfnBatch batch) {
   VX_PDL_ENTRY();
   const FfnProblem& P = batch.p[blockIdx.y];
   const int S = batch.S, C = P.C, eC = P.eC, tid = threadIdx.x;
@@ -445,47 +505,12 @@ __global__ void __launch_bounds__(FF_THREADS) pw_ffn_small_kernel(const __grid_c
   // ---- phase 2: hidden channel j, voxel share [i0, i0 + nv)
   {
     const int nsp = eC <= 64 ? 4 : (eC <= 128 ? 2 : 1);       // threads per hidden channel
-    const int j = tid / nsp, nv = FF_VT / nsp, i0 = (tid % nsp) * nv;
+    const int j = tid / nsp, sh = tid % nsp;
     if (j < eC) {
-      float acc[FF_VT];
-#pragma unroll
-      for (int i = 0; i < FF_VT; ++i) acc[i] = 0.f;
-      const float* wrow = P.W1 + (size_t)j * C;
-      // 8 weight loads (32 input channels) in flight per thread: the row walk is the latency chain of this phase
-#pragma unroll 1
-      for (int c0 = 0; c0 < C; c0 += 32) {
-        float4 w[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) w[u] = c0 + 4 * u < C ? __ldg(reinterpret_cast<const float4*>(wrow + c0 + 4 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int c = c0 + 4 * u;
-          if (c >= C) break;
-          const float ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int i = 0; i < FF_VT; ++i)
-              if (i < nv) acc[i] = fmaf(ww[k], xs[c + k][i0 + i], acc[i]);
-        }
-      }
-      const float bj = P.b1 ? __ldg(P.b1 + j) : 0.f;
-      const float minv = P.mid_drop_p > 0.f ? 1.0f / (1.0f - P.mid_drop_p) : 1.f;
-      const uint32_t mkey = P.mid_drop_p > 0.f ? rng_key(P.mid_seed + soff, P.mid_site) : 0u;
-#pragma unroll
-      for (int i = 0; i < FF_VT; ++i) {
-        if (i < nv) {
-          const int ii = i0 + i;
-          float h = 0.f;
-          if (vb[ii] >= 0) {
-            const float pre = acc[i] + bj;
-            const size_t idx = ((size_t)vb[ii] * eC + j) * S + vv[ii];
-            P.hpre[idx] = pre;
-            h = gelu_f(pre);
-            if (P.mid_drop_p > 0.f) h *= keep_from_bits(rng_word(mkey, idx), P.mid_drop_p, minv);
-          }
-          hs[j][ii] = h;
-        }
+      switch (nsp) {
+        case 4: ffn_fwd_hidden<2>(P, S, soff, xs, hs, vb, vv, j, sh * 2); break;
+        case 2: ffn_fwd_hidden<4>(P, S, soff, xs, hs, vb, vv, j, sh * 4); break;
+        default: ffn_fwd_hidden<8>(P, S, soff, xs, hs, vb, vv, j, 0); break;
       }
     }
   }
@@ -497,42 +522,7 @@ __global__ void __launch_bounds__(FF_THREADS) pw_ffn_small_kernel(const __grid_c
     const int per = ((eC + parts - 1) / parts + 3) & ~3;    // slices start on 16-byte boundaries of the weight row; late ones may be empty
     const int j0 = part * per < eC ? part * per : eC, j1 = j0 + per < eC ? j0 + per : eC;
     float acc[FF_VT];
-#pragma unroll
-    for (int i = 0; i < FF_VT; ++i) acc[i] = 0.f;
-    const float* wrow = P.W2 + (size_t)c * eC;
-    int j = j0;
-#pragma unroll 1
-    for (; j + 32 <= j1; j += 32) {                         // 8 weight loads in flight
-      float4 w[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(wrow + j + 4 * u));
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float4 ha = *reinterpret_cast<const float4*>(&hs[j + 4 * u + k][0]), hb = *reinterpret_cast<const float4*>(&hs[j + 4 * u + k][4]);
-          acc[0] = fmaf(ww[k], ha.x, acc[0]); acc[1] = fmaf(ww[k], ha.y, acc[1]); acc[2] = fmaf(ww[k], ha.z, acc[2]); acc[3] = fmaf(ww[k], ha.w, acc[3]);
-          acc[4] = fmaf(ww[k], hb.x, acc[4]); acc[5] = fmaf(ww[k], hb.y, acc[5]); acc[6] = fmaf(ww[k], hb.z, acc[6]); acc[7] = fmaf(ww[k], hb.w, acc[7]);
-        }
-      }
-    }
-#pragma unroll 1
-    for (; j + 4 <= j1; j += 4) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + j));
-      const float ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 ha = *reinterpret_cast<const float4*>(&hs[j + k][0]), hb = *reinterpret_cast<const float4*>(&hs[j + k][4]);
-        acc[0] = fmaf(ww[k], ha.x, acc[0]); acc[1] = fmaf(ww[k], ha.y, acc[1]); acc[2] = fmaf(ww[k], ha.z, acc[2]); acc[3] = fmaf(ww[k], ha.w, acc[3]);
-        acc[4] = fmaf(ww[k], hb.x, acc[4]); acc[5] = fmaf(ww[k], hb.y, acc[5]); acc[6] = fmaf(ww[k], hb.z, acc[6]); acc[7] = fmaf(ww[k], hb.w, acc[7]);
-      }
-    }
-    for (; j < j1; ++j) {
-      const float w = __ldg(wrow + j);
-#pragma unroll
-      for (int i = 0; i < FF_VT; ++i) acc[i] = fmaf(w, hs[j][i], acc[i]);
-    }
+    ffn_row_walk<FF_VT>(P.W2 + (size_t)c * eC, j0, j1, hs, 0, acc);
 #pragma unroll
     for (int i = 0; i < FF_VT; ++i) red[tid][i] = acc[i];
     __syncthreads();
@@ -578,7 +568,86 @@ int pw_ffn_small(const FfnBatch& batch, cudaStream_t stream) {
 // coalesced) and the rows of the reduction are split over thread groups that meet in shared memory.
 //   phase 2: dh[j][i] = (sum_c W2[c][j] dym[c][i]) GELU'(hpre[j][i]) mask1       thread = (j quad, share of the tile's voxels)
 //   phase 3: dx[c][i] = sum_j W1[j][c] dh[j][i]                                  thread = (c quad, slice of the hidden rows)
-__global__ void __launch_bounds__(FF_THREADS) pw_ffn_small_bwd_kernel(const __grid_constant__ FfnBwdBatch batch) {
+// Column-quad walk shared by both phases: acc[k][i] += W[r][col0 + k] * v[r][i0 + i] over rows [r0, r1), 8 rows of weights in
+// flight.  NV (voxels per thread) is a template parameter: the accumulators are 4 NV registers and no slot is predicated.
+template <int NV>
+VX_DEV void ffn_col_walk(const float* __restrict__ wcol, int ld, int r0, int r1, const float (*v)[FF_VT], int i0, float (&acc)[4][NV]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[k][i] = 0.f;
+  int r = r0;
+#pragma unroll 1
+  for (; r + 8 <= r1; r += 8) {
+    float4 w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(wcol + (size_t)(r + u) * ld));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float x = v[r + u][i0 + i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k][i] = fmaf(ww[k], x, acc[k][i]);
+      }
+    }
+  }
+  for (; r < r1; ++r) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(wcol + (size_t)r * ld));
+    const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float x = v[r][i0 + i];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k][i] = fmaf(ww[k], x, acc[k][i]);
+    }
+  }
+}
+
+template <int NV>
+VX_DEV void ffn_bwd_hidden(const FfnBwdProblem& P, int S, uint64_t soff, const float (*ds)[FF_VT], float (*hs)[FF_VT], const int* vb,
+                           const int* vv, int jq, int i0) {
+  float acc[4][NV];
+  ffn_col_walk<NV>(P.W2 + 4 * jq, P.eC, 0, P.C, ds, i0, acc);
+  const float minv = P.mid_drop_p > 0.f ? 1.0f / (1.0f - P.mid_drop_p) : 1.f;
+  const uint32_t mkey = P.mid_drop_p > 0.f ? rng_key(P.mid_seed + soff, P.mid_site) : 0u;
+  // every hpre load first (dead voxels read element 0), then the arithmetic: one round trip instead of 4 NV
+  float hp[4][NV];
+  size_t idx[4][NV];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int ii = i0 + i;
+      idx[k][i] = vb[ii] >= 0 ? ((size_t)vb[ii] * P.eC + 4 * jq + k) * S + vv[ii] : 0;
+      hp[k][i] = __ldg(P.hpre + idx[k][i]);
+    }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int ii = i0 + i;
+      float g = acc[k][i] * gelu_grad_f(hp[k][i]);
+      if (P.mid_drop_p > 0.f) g *= keep_from_bits(rng_word(mkey, idx[k][i]), P.mid_drop_p, minv);
+      if (vb[ii] >= 0) P.dh[idx[k][i]] = g; else g = 0.f;
+      hs[4 * jq + k][ii] = g;
+    }
+}
+
+template <int NV>
+VX_DEV void ffn_bwd_input(const FfnBwdProblem& P, const float (*hs)[FF_VT], float (*red)[FF_VT], int cq, int part, int parts, int i0) {
+  const int per = (P.eC + parts - 1) / parts;
+  const int j0 = part * per < P.eC ? part * per : P.eC, j1 = j0 + per < P.eC ? j0 + per : P.eC;
+  float acc[4][NV];
+  ffn_col_walk<NV>(P.W1 + 4 * cq, P.C, j0, j1, hs, i0, acc);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[part * P.C + 4 * cq + k][i0 + i] = acc[k][i];
+}
+
+__global__ void __launch_bounds__(FF_THREADS, 2) pw_ffn_small_bwd_kernel(const __grid_constant__ FfnBwdBatch batch) {
   VX_PDL_ENTRY();
   const FfnBwdProblem& P = batch.p[blockIdx.y];
   const int S = batch.S, C = P.C, eC = P.eC, tid = threadIdx.x;
@@ -611,122 +680,41 @@ __global__ void __launch_bounds__(FF_THREADS) pw_ffn_small_bwd_kernel(const __gr
   __syncthreads();
   // ---- phase 2
   {
-    const int Q = eC >> 2;                                  // column quads of W2 (<= 64)
+    const int Q = eC >> 2;                                  // column quads of W2 (<= 64, a power of two)
     const int nsp = FF_THREADS / Q < FF_VT ? FF_THREADS / Q : FF_VT;      // voxel shares
-    const int nv = FF_VT / nsp;
     const int jq = tid % Q, vs = tid / Q;
     if (vs < nsp) {
-      const int i0 = vs * nv;
-      float acc[4][FF_VT];
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int i = 0; i < FF_VT; ++i) acc[k][i] = 0.f;
-      const float* wcol = P.W2 + 4 * jq;
-#pragma unroll 1
-      for (int c0 = 0; c0 < C; c0 += 8) {                   // 8 rows in flight
-        float4 w[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(wcol + (size_t)(c0 + u) * eC));
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
-#pragma unroll
-          for (int i = 0; i < FF_VT; ++i) {
-            if (i < nv) {
-              const float dv = ds[c0 + u][i0 + i];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) acc[k][i] = fmaf(ww[k], dv, acc[k][i]);
-            }
-          }
-        }
-      }
-      const float minv = P.mid_drop_p > 0.f ? 1.0f / (1.0f - P.mid_drop_p) : 1.f;
-      const uint32_t mkey = P.mid_drop_p > 0.f ? rng_key(P.mid_seed + soff, P.mid_site) : 0u;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int j = 4 * jq + k;
-#pragma unroll
-        for (int i = 0; i < FF_VT; ++i) {
-          if (i < nv) {
-            const int ii = i0 + i;
-            float g = 0.f;
-            if (vb[ii] >= 0) {
-              const size_t idx = ((size_t)vb[ii] * eC + j) * S + vv[ii];
-              g = acc[k][i] * gelu_grad_f(__ldg(P.hpre + idx));
-              if (P.mid_drop_p > 0.f) g *= keep_from_bits(rng_word(mkey, idx), P.mid_drop_p, minv);
-              P.dh[idx] = g;
-            }
-            hs[j][ii] = g;
-          }
-        }
+      switch (nsp) {
+        case 8: ffn_bwd_hidden<1>(P, S, soff, ds, hs, vb, vv, jq, vs); break;
+        case 4: ffn_bwd_hidden<2>(P, S, soff, ds, hs, vb, vv, jq, vs * 2); break;
+        default: ffn_bwd_hidden<4>(P, S, soff, ds, hs, vb, vv, jq, vs * 4); break;      // eC = 512 would land here; FF_MAX_E is 256
       }
     }
   }
   __syncthreads();
   // ---- phase 3
+  const int parts = 8;                                      // slices of the hidden rows; parts * C <= 1024 rows of `red`
   {
     const int Q = C >> 2;                                   // column quads of W1 (2 ... 32)
-    const int parts = 8;                                    // slices of the hidden rows; parts * C <= 1024 rows of `red`
     const int nsp = FF_THREADS / (Q * parts) < FF_VT ? FF_THREADS / (Q * parts) : FF_VT;      // voxel shares (1 ... 8)
-    const int nv = FF_VT / nsp;
     const int cq = tid % Q, part = (tid / Q) % parts, vs = tid / (Q * parts);
     if (vs < nsp) {
-      const int i0 = vs * nv;
-      const int per = (eC + parts - 1) / parts;
-      const int j0 = part * per < eC ? part * per : eC, j1 = j0 + per < eC ? j0 + per : eC;
-      float acc[4][FF_VT];
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int i = 0; i < FF_VT; ++i) acc[k][i] = 0.f;
-      const float* wcol = P.W1 + 4 * cq;
-      int j = j0;
-#pragma unroll 1
-      for (; j + 8 <= j1; j += 8) {
-        float4 w[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(wcol + (size_t)(j + u) * C));
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
-#pragma unroll
-          for (int i = 0; i < FF_VT; ++i) {
-            if (i < nv) {
-              const float hv = hs[j + u][i0 + i];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) acc[k][i] = fmaf(ww[k], hv, acc[k][i]);
-            }
-          }
-        }
+      switch (nsp) {
+        case 8: ffn_bwd_input<1>(P, hs, red, cq, part, parts, vs); break;
+        case 4: ffn_bwd_input<2>(P, hs, red, cq, part, parts, vs * 2); break;
+        case 2: ffn_bwd_input<4>(P, hs, red, cq, part, parts, vs * 4); break;
+        default: ffn_bwd_input<8>(P, hs, red, cq, part, parts, 0); break;
       }
-      for (; j < j1; ++j) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(wcol + (size_t)j * C));
-        const float ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int i = 0; i < FF_VT; ++i) {
-          if (i < nv) {
-            const float hv = hs[j][i0 + i];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[k][i] = fmaf(ww[k], hv, acc[k][i]);
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int i = 0; i < FF_VT; ++i)
-          if (i < nv) red[part * C + 4 * cq + k][i0 + i] = acc[k][i];
     }
-    __syncthreads();
-    for (int e = tid; e < C * FF_VT; e += FF_THREADS) {
-      const int cc = e / FF_VT, i = e % FF_VT;
-      if (vb[i] < 0) continue;
-      float y = 0.f;
+  }
+  __syncthreads();
+  for (int e = tid; e < C * FF_VT; e += FF_THREADS) {
+    const int cc = e / FF_VT, i = e % FF_VT;
+    if (vb[i] < 0) continue;
+    float y = 0.f;
 #pragma unroll
-      for (int pp = 0; pp < parts; ++pp) y += red[pp * C + cc][i];
-      P.dx[((size_t)vb[i] * C + cc) * S + vv[i]] = y;
-    }
+    for (int pp = 0; pp < parts; ++pp) y += red[pp * C + cc][i];
+    P.dx[((size_t)vb[i] * C + cc) * S + vv[i]] = y;
   }
 }
 
