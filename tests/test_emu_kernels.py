@@ -139,6 +139,7 @@ PWA_CASES = [
     ((8, 8, 4), 16, [4, 4, 2], [1, 1, 1], 2, 4, 2, 2, 1),
     ((12, 12, 12), 16, [3, 3, 3], [1, 1, 1], 1, 4, 1, 1, 1),
     ((8, 8, 8), 8, [4, 4, 4], [1, 1, 1], 1, 4, 2, 2, 1),      # l = 64: the vectorised bias-gradient path of level 2
+    ((8, 8, 12), 8, [4, 4, 6], [1, 1, 1], 1, 8, 2, 2, 1),     # L = 192, 8 channels per head: the tcgen05 attention forward
 ]
 
 

@@ -11,6 +11,7 @@
 //   ln_forward, pw_forward x2   z = y + Drop(W2 Drop(GELU(W1 LN(y) + b1)) + b2)
 // Backward mirrors it; softmax is recomputed from the saved row log-sum-exp (no L x L tensor is ever stored).
 #include "vx_kernels.h"
+#include "vx_tc2.cuh"
 
 #ifdef VX_EMU
 #define __grid_constant__
@@ -457,6 +458,230 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_fwd_kernel(const __g
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Forward on the tensor cores (PWA.py:308-327 at the levels whose windows are GEMM-sized: L >= 128, L % 16 == 0, 8 channels per
+// head -- level 2 of the three configurations, L = 432).  CTA = one window x 128 query rows, 128 threads, thread = query row =
+// TMEM lane.  3xTF32 throughout (fp32-accurate scores: the backward recomputes P in fp32 from the saved log-sum-exp):
+//   S = Q K^T       A = [Q_hi | Q_lo | Q_hi] from shared memory (K-major), B = [K_hi | K_hi | K_lo]: 3 k-steps of one N = chunk MMA;
+//   softmax         two rolled passes over the chunk's TMEM columns in pieces of 16: bias + running max (scores written back),
+//                   then p = exp(s - m): row sum, dropout mask, hi / lo split written to TMEM -- P never visits shared memory;
+//   O += P V        the ".ts" form: A = P_hi / P_lo from TMEM, B = [V_hi | V_lo] as ONE N = 16 operand (8 + 8 channels), so the
+//                   N = 16 floor of the instruction carries the hi / lo products instead of padding: 2 MMAs per 8 keys;
+//                   the chunk's 16 columns come back to registers where the online-softmax rescaling lives.
+// Keys are processed in chunks of ATC_CHUNK = 112 (TMEM: S / P_hi 112 + P_lo 112 + O 16 = 240 of the 256 allocated columns, so
+// two CTAs share an SM: one CTA's softmax runs under the other's MMAs).
+// ---------------------------------------------------------------------------------------------------
+constexpr int ATC_CHUNK = 112, ATC_ROWS = 128, ATC_TS = 4, ATC_THREADS = ATC_ROWS * ATC_TS, ATC_COLS = 256, ATC_C = 8;
+constexpr uint32_t ATC_PLO = ATC_CHUNK, ATC_O = 2 * ATC_CHUNK;
+
+// K-major SWIZZLE_NONE image of an (rows x 8) operand: 8-row groups 256 B apart, the two 16-byte K halves 128 B apart
+VX_DEV int atc_kmajor(int r, int k) { return (r >> 3) * 64 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3); }      // in floats
+
+// bias of 8 consecutive keys (from key k of the window) for query token tq:  biasT[h][tk][tq], tk = key % l
+VX_DEV void atc_bias8(const float* __restrict__ bT, int k, int l, float (&b)[8]) {
+  int tk = k;
+  while (tk >= l) tk -= l;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    b[j] = __ldg(bT + (size_t)tk * l);
+    if (++tk == l) tk = 0;
+  }
+}
+
+// ATC_TS threads per query row: warp w works on TMEM lanes 32 (w % 4) .. + 31 (the hardware's lane window of a warp) and takes
+// every ATC_TS-th piece of 8 key columns, share = w / 4.  Per chunk: partial row maxima meet in shared memory, the partial row
+// sums only at the end (every share uses the same reference maximum).
+__global__ void __launch_bounds__(ATC_THREADS, 2) pwa_attn_fwd_tc_kernel(const __grid_constant__ AttnArgs A) {
+  VX_PDL_ENTRY();
+  const int N = blockIdx.y, bh = blockIdx.z, head = bh % A.heads;
+  const int L = A.L, l = A.l;
+  const int tid = threadIdx.x, warp = tid >> 5, lg = warp & 3, sh = warp >> 2;
+  const int rt = lg * 32 + (tid & 31);       // row inside the tile = TMEM lane
+  VX_DYN_SMEM(float, sm);
+  float* Qhi = sm;                          // [128 x 8] K-major
+  float* Qlo = Qhi + ATC_ROWS * ATC_C;
+  float* red = Qlo + ATC_ROWS * ATC_C;      // [ATC_TS][128] partial maxima / sums
+  float* Khi = red + ATC_TS * ATC_ROWS;     // [L x 8] K-major (rows = keys)
+  float* Klo = Khi + (size_t)L * ATC_C;
+  float* Vt = Klo + (size_t)L * ATC_C;      // [L / 8 k-steps][16 rows: V_hi channels | V_lo channels][8 keys] K-major
+  VX_TC_SHARED_BARS(bars, 2);               // scores ready, output ready
+  VX_TC_SHARED_SLOT(tmem_slot);
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)ATC_COLS);
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1);
+    tc::mbar_init_fence();
+  }
+  const size_t wbase = (size_t)bh * A.Ns + N;
+  const int i_raw = blockIdx.x * ATC_ROWS + rt;
+  const bool live = i_raw < L;
+  const int i = live ? i_raw : L - 1;
+  // ---- operand staging
+  if (sh == 0) {
+    const float4* qp = reinterpret_cast<const float4*>(A.Q + (wbase * L + i) * ATC_C);
+    float4 q[2] = {__ldg(qp), __ldg(qp + 1)};
+    if (!live) q[0] = q[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float v[4] = {q[h].x * A.scale, q[h].y * A.scale, q[h].z * A.scale, q[h].w * A.scale};
+      float hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tc::split(v[j], hi[j], lo[j]);
+      const int o = atc_kmajor(rt, 4 * h);
+      *reinterpret_cast<float4*>(Qhi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(Qlo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+  {
+    // item = (key, half of the 8 channels)
+    const float* Kg = A.K + wbase * L * ATC_C;
+    const float* Vg = A.V + wbase * L * ATC_C;
+    for (int e = tid; e < 2 * L; e += ATC_THREADS) {
+      const int r = e >> 1, h = e & 1;
+      const float4 k4 = __ldg(reinterpret_cast<const float4*>(Kg + (size_t)r * ATC_C) + h);
+      const float4 v4 = __ldg(reinterpret_cast<const float4*>(Vg + (size_t)r * ATC_C) + h);
+      const float kv[4] = {k4.x, k4.y, k4.z, k4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+      float hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tc::split(kv[j], hi[j], lo[j]);
+      const int o = atc_kmajor(r, 4 * h);
+      *reinterpret_cast<float4*>(Khi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(Klo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      // V transposed: operand row n = channel (hi) / 8 + channel (lo), k = key inside the k-step
+      float* vt = Vt + (size_t)(r >> 3) * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float vh, vl;
+        tc::split(vv[j], vh, vl);
+        vt[atc_kmajor(4 * h + j, r & 7)] = vh;
+        vt[atc_kmajor(8 + 4 * h + j, r & 7)] = vl;
+      }
+    }
+  }
+  tc::fence_async_smem();
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16);       // this thread's lane, column 0
+  const uint32_t qh = tc::smem_addr(Qhi), ql = tc::smem_addr(Qlo), kh = tc::smem_addr(Khi), kl = tc::smem_addr(Klo), vt = tc::smem_addr(Vt);
+
+  const float* bT = A.biasT + (size_t)head * l * l + (i % l);
+  const bool drop = A.drop_p > 0.f;
+  const float inv_keep = drop ? 1.0f / (1.0f - A.drop_p) : 1.f;
+  const size_t row = wbase * L + i;
+  float mx = -INFINITY, ssum = 0.f;          // ssum: this share's part of the row sum
+  float acc[ATC_C];                          // share 0 only
+#pragma unroll
+  for (int c = 0; c < ATC_C; ++c) acc[c] = 0.f;
+
+  int chunk_i = 0;
+#pragma unroll 1
+  for (int k0 = 0; k0 < L; k0 += ATC_CHUNK, ++chunk_i) {
+    const int n = L - k0 < ATC_CHUNK ? L - k0 : ATC_CHUNK;           // a multiple of 16
+    const int np = n >> 3;
+    const uint32_t par = (uint32_t)(chunk_i & 1);
+    if (tid == 0) {
+      const uint32_t idesc = tc::idesc_tf32(n, 0, 0);
+      const uint32_t ko = (uint32_t)(k0 >> 3) * 256u;
+      const uint64_t aqh = tc::desc(qh, 128u, 256u), aql = tc::desc(ql, 128u, 256u);
+      const uint64_t bkh = tc::desc(kh + ko, 128u, 256u), bkl = tc::desc(kl + ko, 128u, 256u);
+      tc::mma_tf32(tmem, aql, bkh, idesc, 0u);
+      tc::mma_tf32(tmem, aqh, bkl, idesc, 1u);
+      tc::mma_tf32(tmem, aqh, bkh, idesc, 1u);
+      tc::commit(&bars[0]);
+    }
+    // the bias of the first piece travels under the score MMA; inside the loop the next piece's under the current one
+    float bn[8];
+    if (sh < np) atc_bias8(bT, k0 + 8 * sh, l, bn);
+    tc::mbar_wait(&bars[0], par);
+    tc::fence_after();
+    // pass 1: bias, maximum; the biased scores go back to their columns
+    float cm = -INFINITY;
+#pragma unroll 1
+    for (int p = sh; p < np; p += ATC_TS) {
+      float bc[8], sv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bc[j] = bn[j];
+      if (p + ATC_TS < np) atc_bias8(bT, k0 + 8 * (p + ATC_TS), l, bn);
+      tc::tmem_ld8(trow + (uint32_t)(8 * p), sv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sv[j] += bc[j]; cm = fmaxf(cm, sv[j]); }
+      tc::tmem_st8(trow + (uint32_t)(8 * p), sv);
+    }
+    red[sh * ATC_ROWS + rt] = cm;
+    tc::tmem_wait_st();
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < ATC_TS; ++t) cm = fmaxf(cm, red[t * ATC_ROWS + rt]);
+    const float mn = fmaxf(mx, cm);
+    const float corr = mx == -INFINITY ? 0.f : att_exp(mx - mn);
+    mx = mn;
+    ssum *= corr;
+    // pass 2: probabilities; hi over the scores, lo beside them
+#pragma unroll 1
+    for (int p = sh; p < np; p += ATC_TS) {
+      float sv[8], pl[8];
+      tc::tmem_ld8(trow + (uint32_t)(8 * p), sv);
+#pragma unroll
+      for (int q4 = 0; q4 < 2; ++q4) {
+        float ms[4] = {1.f, 1.f, 1.f, 1.f};
+        if (drop) attn_drop4(A, row, (k0 + 8 * p) / 4 + q4, inv_keep, ms);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float pr = att_exp(sv[4 * q4 + j] - mn);
+          ssum += pr;
+          tc::split(pr * ms[j], sv[4 * q4 + j], pl[4 * q4 + j]);
+        }
+      }
+      tc::tmem_st8(trow + (uint32_t)(8 * p), sv);
+      tc::tmem_st8(trow + ATC_PLO + (uint32_t)(8 * p), pl);
+    }
+    tc::tmem_wait_st();
+    tc::fence_before();
+    __syncthreads();          // P complete; also orders this chunk's reads of `red` before the next chunk's writes
+    if (tid == 0) {
+      tc::fence_after();
+      const uint32_t idesc = tc::idesc_tf32(16, 0, 0);
+      for (int s = 0; s < np; ++s) {
+        const uint64_t bv = tc::desc(vt + (uint32_t)((k0 >> 3) + s) * 512u, 128u, 256u);
+        tc::mma_tf32_ts(tmem + ATC_O, tmem + (uint32_t)(8 * s), bv, idesc, s > 0 ? 1u : 0u);
+        tc::mma_tf32_ts(tmem + ATC_O, tmem + ATC_PLO + (uint32_t)(8 * s), bv, idesc, 1u);
+      }
+      tc::commit(&bars[1]);
+    }
+    if (sh == 0) {
+      // shares 1.. run ahead into the next chunk: its score MMA is issued by thread 0 (share 0) after this read, and its P
+      // MMAs (which overwrite O) after the next chunk's block-wide barrier
+      tc::mbar_wait(&bars[1], par);
+      tc::fence_after();
+      float o[16];
+      tc::tmem_ld16(trow + ATC_O, o);
+#pragma unroll
+      for (int c = 0; c < ATC_C; ++c) acc[c] = fmaf(acc[c], corr, o[c] + o[8 + c]);
+      tc::fence_before();
+    }
+  }
+  __syncthreads();
+  red[sh * ATC_ROWS + rt] = ssum;
+  __syncthreads();
+  if (live && sh == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int t = 0; t < ATC_TS; ++t) tot += red[t * ATC_ROWS + rt];
+    const float inv = 1.0f / tot;
+    float4* op = reinterpret_cast<float4*>(A.O + row * ATC_C);
+    op[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+    op[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+    A.lse[row] = mx + logf(tot);
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)ATC_COLS);
+}
+
+static int g_attn_tc = 1;
+void pwa_attn_tc_set(int on) { g_attn_tc = on; }
+
 // Backward: same CTA shape.  Phase A: a query row (ATT_TS threads, keys dealt in quads) -> dQ and the bias gradient;
 // phase B: a key row (queries dealt in turns) -> dK, dV.  P is recomputed from the saved row log-sum-exp.
 // Bias gradient (dbias is laid out [head][tq][tk]; L*L score gradients per window fold onto l*l entries):
@@ -691,6 +916,15 @@ static int launch_attn(const AttnArgs& A, bool bwd, cudaStream_t st) {
 }
 
 static int dispatch_attn(const AttnArgs& A, int cq, int cv, bool bwd, cudaStream_t st) {
+  if (!bwd && g_attn_tc && cq == ATC_C && cv == ATC_C && A.L >= 128 && A.L % 16 == 0) {
+    const size_t smem = sizeof(float) * (2 * ATC_ROWS * ATC_C + ATC_TS * ATC_ROWS + (size_t)A.L * ATC_C * 2 + (size_t)A.L * 16);
+    if (smem <= 100 * 1024) {
+      VX_SET_SMEM(pwa_attn_fwd_tc_kernel, smem);
+      prof_flops(4.0 * (double)A.B * A.heads * A.Ns * (double)A.L * A.L * ATC_C);
+      VX_LAUNCH(pwa_attn_fwd_tc_kernel, dim3(cdiv(A.L, ATC_ROWS), A.Ns, A.B * A.heads), dim3(ATC_THREADS), smem, st, A);
+      return check_launch("pwa_attn_fwd_tc_kernel");
+    }
+  }
 #define VX_ATT(a, b) if (cq == a && cv == b) return launch_attn<a, b>(A, bwd, st)
   VX_ATT(4, 4); VX_ATT(4, 8); VX_ATT(8, 8); VX_ATT(8, 16); VX_ATT(16, 16); VX_ATT(16, 32);
 #undef VX_ATT

@@ -130,6 +130,44 @@ VX_DEV void tmem_ld32(uint32_t taddr, float (&r)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(q[j]);
 }
+// 8-column variants (pieces of 8 keep the softmax passes of the attention kernel at 64 registers)
+VX_DEV void tmem_ld8(uint32_t taddr, float (&r)[8]) {
+  uint32_t q[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = __uint_as_float(q[j]);
+}
+VX_DEV void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+// the ".ts" form: A (128 x 8 tf32) read from tensor memory -- row m = lane m, element k = column tmem_a + k
+VX_DEV void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane (same addressing as tmem_ld16); complete after tmem_wait_st()
+VX_DEV void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+VX_DEV void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 #define VX_TC_SHARED_BARS(name, n) __shared__ __align__(8) uint64_t name[n]
 #define VX_TC_SHARED_SLOT(name) __shared__ uint32_t name
 
@@ -208,6 +246,35 @@ inline void tmem_ld32(uint32_t taddr, float (&r)[32]) {
   const int lane = (int)(taddr >> 16) + (vx_emu::t_lane_slot & 31), col = (int)(taddr & 0xFFFFu);
   for (int j = 0; j < 32; ++j) r[j] = emu_tmem().v[lane][col + j];
 }
+inline void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const int N = (int)((idesc >> 17) & 0x3Fu) << 3, b_mn = (idesc >> 16) & 1;
+  if (b_mn) { fprintf(stderr, "vx_emu: MN-major operands do not work with kind::tf32 on the hardware\n"); abort(); }
+  const int col = (int)(tmem_d & 0xFFFFu), acol = (int)(tmem_a & 0xFFFFu);
+  if (col + N > 512 || acol + 8 > 512) { fprintf(stderr, "vx_emu: MMA touches TMEM past column 512\n"); abort(); }
+  if (acol < col + N && col < acol + 8) { fprintf(stderr, "vx_emu: MMA accumulator overlaps its TMEM A operand\n"); abort(); }
+  for (int n = 0; n < N; ++n) {
+    float b[8];
+    for (int k = 0; k < 8; ++k) b[k] = emu_operand(bdesc, 0, n, k);
+    for (int m = 0; m < 128; ++m) {
+      float acc = accumulate ? emu_tmem().v[m][col + n] : 0.f;
+      for (int k = 0; k < 8; ++k) acc += emu_tf32(emu_tmem().v[m][acol + k]) * b[k];
+      emu_tmem().v[m][col + n] = acc;
+    }
+  }
+}
+inline void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  const int lane = (int)(taddr >> 16) + (vx_emu::t_lane_slot & 31), col = (int)(taddr & 0xFFFFu);
+  for (int j = 0; j < 16; ++j) emu_tmem().v[lane][col + j] = v[j];
+}
+inline void tmem_ld8(uint32_t taddr, float (&r)[8]) {
+  const int lane = (int)(taddr >> 16) + (vx_emu::t_lane_slot & 31), col = (int)(taddr & 0xFFFFu);
+  for (int j = 0; j < 8; ++j) r[j] = emu_tmem().v[lane][col + j];
+}
+inline void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  const int lane = (int)(taddr >> 16) + (vx_emu::t_lane_slot & 31), col = (int)(taddr & 0xFFFFu);
+  for (int j = 0; j < 8; ++j) emu_tmem().v[lane][col + j] = v[j];
+}
+inline void tmem_wait_st() {}
 #define VX_TC_SHARED_BARS(name, n) static uint64_t name[n]
 #define VX_TC_SHARED_SLOT(name) static uint32_t name
 #endif
