@@ -269,6 +269,40 @@ def test_pwa_dropout_backward_matches_forward_masks(ops, lvl):
     assert min(gaps) <= 3e-2, (gaps, an)
 
 
+@pytest.mark.parametrize("lvl", ["autopet_L2", "hecktor_L2"])
+def test_pwa_attention_tensor_core_matches_simt(ops, lvl):
+    """Windows of L >= 128 tokens with 8 channels per head (level 2: L = 432 / 512) run the attention forward on tcgen05
+    (QK^T / PV as 3xTF32 MMAs, P in tensor memory).  Same inputs through the fp32 SIMT kernel (VX_OPT_ATTN_TC = 0): outputs
+    agree to fp32 round-off, with attention dropout on as well (both kernels draw the same hashed mask words), and the profile
+    shows which kernel ran."""
+    from veloxseg_b200 import _lib
+    size, C, mb, heads, mdh, M, e = PWA_LEVELS[lvl]
+    geo = O.pwa_geometry(size, C, mb, [1, 1, 1], 2, heads, mdh)
+    torch.manual_seed(3)
+    lib, st = _lib.get_lib(), torch.cuda.current_stream().cuda_stream
+    xs = [torch.randn(2, C, *size, device=DEV) for _ in range(M)]
+    flat, pd, table, index = pwa_params(M, C, geo, e, seed=6)
+    flat, table, index = [p.to(DEV) for p in flat], table.to(DEV), index.to(DEV)
+    out = {}
+    try:
+        for on in (0, 1):
+            lib.set_option(17, on)
+            lib.profile(True)
+            z0, _ = ops.pwa_block_fwd_raw(lib, st, xs, flat, table, index, geo, e)
+            torch.cuda.synchronize()
+            kernels = {k for _, k, *_ in lib.profile_report()}
+            lib.profile(False)
+            assert ("pwa_attn_fwd_tc_kernel" in kernels) == bool(on), kernels
+            z1, _ = ops.pwa_block_fwd_raw(lib, st, xs, flat, table, index, geo, e, 0.3, 0.0, True, 91)
+            out[on] = ([z.clone() for z in z0], [z.clone() for z in z1])
+    finally:
+        lib.set_option(17, 1)
+        lib.profile(False)
+    for k in (0, 1):
+        for a, b in zip(out[0][k], out[1][k]):
+            assert rel_err(a, b) < 5e-6, (k, rel_err(a, b))
+
+
 @pytest.mark.parametrize("lvl", list(PWA_LEVELS))
 def test_pwa_block_levels(ops, lvl):
     size, C, mb, heads, mdh, M, e = PWA_LEVELS[lvl]

@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(ATT_MAX_THREADS) pwa_attn_fwd_kernel(const __g
 //   O += P V        the ".ts" form: A = P_hi / P_lo from TMEM, B = [V_hi | V_lo] as ONE N = 16 operand (8 + 8 channels), so the
 //                   N = 16 floor of the instruction carries the hi / lo products instead of padding: 2 MMAs per 8 keys;
 //                   the chunk's 16 columns come back to registers where the online-softmax rescaling lives.
-// Keys are processed in chunks of ATC_CHUNK = 112 (TMEM: S / P_hi 112 + P_lo 112 + O 16 = 240 of the 256 allocated columns, so
+// Keys are processed in chunks of ATC_CHUNK = 112 (TMEM: S / P_hi 112 + P_lo 112 + O 2 x 16 = the 256 allocated columns, so
 // two CTAs share an SM: one CTA's softmax runs under the other's MMAs).
 // ---------------------------------------------------------------------------------------------------
 constexpr int ATC_CHUNK = 112, ATC_ROWS = 128, ATC_TS = 4, ATC_THREADS = ATC_ROWS * ATC_TS, ATC_COLS = 256, ATC_C = 8;
@@ -477,15 +477,22 @@ constexpr uint32_t ATC_PLO = ATC_CHUNK, ATC_O = 2 * ATC_CHUNK;
 // K-major SWIZZLE_NONE image of an (rows x 8) operand: 8-row groups 256 B apart, the two 16-byte K halves 128 B apart
 VX_DEV int atc_kmajor(int r, int k) { return (r >> 3) * 64 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3); }      // in floats
 
-// bias of 8 consecutive keys (from key k of the window) for query token tq:  biasT[h][tk][tq], tk = key % l
-VX_DEV void atc_bias8(const float* __restrict__ bT, int k, int l, float (&b)[8]) {
+// bias of 8 consecutive keys (from key k of the window, k % 8 == 0, l % 8 == 0) of one query token's row of the query-major table
+VX_DEV void atc_bias8(const float* __restrict__ brow, int k, int l, float (&b)[8]) {
   int tk = k;
   while (tk >= l) tk -= l;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    b[j] = __ldg(bT + (size_t)tk * l);
-    if (++tk == l) tk = 0;
-  }
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(brow + tk)), b1 = __ldg(reinterpret_cast<const float4*>(brow + tk) + 1);
+  b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+}
+// 2^x (the scores are kept in log2 units: the 1/ln 2 factor rides on the query scaling and the bias FMA)
+VX_DEV float atc_exp2(float x) {
+#ifdef VX_EMU
+  return exp2f(x);
+#else
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#endif
 }
 
 // ATC_TS threads per query row: warp w works on TMEM lanes 32 (w % 4) .. + 31 (the hardware's lane window of a warp) and takes
@@ -504,11 +511,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) pwa_attn_fwd_tc_kernel(const _
   float* Khi = red + ATC_TS * ATC_ROWS;     // [L x 8] K-major (rows = keys)
   float* Klo = Khi + (size_t)L * ATC_C;
   float* Vt = Klo + (size_t)L * ATC_C;      // [L / 8 k-steps][16 rows: V_hi channels | V_lo channels][8 keys] K-major
-  VX_TC_SHARED_BARS(bars, 2);               // scores ready, output ready
+  VX_TC_SHARED_BARS(bars, 1);               // scores of the chunk (and the output columns of the one before) ready
   VX_TC_SHARED_SLOT(tmem_slot);
   if (warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)ATC_COLS);
   if (tid == 0) {
-    tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1);
+    tc::mbar_init(&bars[0], 1);
     tc::mbar_init_fence();
   }
   const size_t wbase = (size_t)bh * A.Ns + N;
@@ -522,7 +529,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) pwa_attn_fwd_tc_kernel(const _
     if (!live) q[0] = q[1] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const float v[4] = {q[h].x * A.scale, q[h].y * A.scale, q[h].z * A.scale, q[h].w * A.scale};
+      const float qs = A.scale * 1.4426950408889634f;      // scores in log2 units
+      const float v[4] = {q[h].x * qs, q[h].y * qs, q[h].z * qs, q[h].w * qs};
       float hi[4], lo[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) tc::split(v[j], hi[j], lo[j]);
@@ -565,36 +573,50 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) pwa_attn_fwd_tc_kernel(const _
   const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16);       // this thread's lane, column 0
   const uint32_t qh = tc::smem_addr(Qhi), ql = tc::smem_addr(Qlo), kh = tc::smem_addr(Khi), kl = tc::smem_addr(Klo), vt = tc::smem_addr(Vt);
 
-  const float* bT = A.biasT + (size_t)head * l * l + (i % l);
+  const float* brow = A.biasN + ((size_t)head * l + (i % l)) * l;
   const bool drop = A.drop_p > 0.f;
   const float inv_keep = drop ? 1.0f / (1.0f - A.drop_p) : 1.f;
   const size_t row = wbase * L + i;
-  float mx = -INFINITY, ssum = 0.f;          // ssum: this share's part of the row sum
+  constexpr float LOG2E = 1.4426950408889634f;
+  float mx = -INFINITY, ssum = 0.f;          // log2 units; ssum: this share's part of the row sum
+  float corr = 0.f;                          // rescaling of the chunks before the current one
   float acc[ATC_C];                          // share 0 only
 #pragma unroll
   for (int c = 0; c < ATC_C; ++c) acc[c] = 0.f;
+
+  // thread 0 issues, in order: scores of chunk 0 | P V of chunk 0, scores of chunk 1 | ... (tcgen05.mma executes in issue order,
+  // so the score MMA that overwrites the P_hi columns may follow the P V MMAs that read them without a wait in between);
+  // one commit per group: "scores of chunk n ready" also says "output columns of chunk n - 1 ready".
+  auto issue_scores = [&](int k0) {
+    const int n = L - k0 < ATC_CHUNK ? L - k0 : ATC_CHUNK;
+    const uint32_t idesc = tc::idesc_tf32(n, 0, 0);
+    const uint32_t ko = (uint32_t)(k0 >> 3) * 256u;
+    const uint64_t aqh = tc::desc(qh, 128u, 256u), aql = tc::desc(ql, 128u, 256u);
+    const uint64_t bkh = tc::desc(kh + ko, 128u, 256u), bkl = tc::desc(kl + ko, 128u, 256u);
+    tc::mma_tf32(tmem, aql, bkh, idesc, 0u);
+    tc::mma_tf32(tmem, aqh, bkl, idesc, 1u);
+    tc::mma_tf32(tmem, aqh, bkh, idesc, 1u);
+  };
+  auto take_output = [&]() {                 // acc = acc * corr + O  (share 0, after the commit that covers the P V MMAs)
+    float o[32];
+    tc::tmem_ld32(trow + ATC_O, o);
+#pragma unroll
+    for (int c = 0; c < ATC_C; ++c) acc[c] = fmaf(acc[c], corr, (o[c] + o[8 + c]) + (o[16 + c] + o[24 + c]));
+  };
+  if (tid == 0) { issue_scores(0); tc::commit(&bars[0]); }
 
   int chunk_i = 0;
 #pragma unroll 1
   for (int k0 = 0; k0 < L; k0 += ATC_CHUNK, ++chunk_i) {
     const int n = L - k0 < ATC_CHUNK ? L - k0 : ATC_CHUNK;           // a multiple of 16
     const int np = n >> 3;
-    const uint32_t par = (uint32_t)(chunk_i & 1);
-    if (tid == 0) {
-      const uint32_t idesc = tc::idesc_tf32(n, 0, 0);
-      const uint32_t ko = (uint32_t)(k0 >> 3) * 256u;
-      const uint64_t aqh = tc::desc(qh, 128u, 256u), aql = tc::desc(ql, 128u, 256u);
-      const uint64_t bkh = tc::desc(kh + ko, 128u, 256u), bkl = tc::desc(kl + ko, 128u, 256u);
-      tc::mma_tf32(tmem, aql, bkh, idesc, 0u);
-      tc::mma_tf32(tmem, aqh, bkl, idesc, 1u);
-      tc::mma_tf32(tmem, aqh, bkh, idesc, 1u);
-      tc::commit(&bars[0]);
-    }
     // the bias of the first piece travels under the score MMA; inside the loop the next piece's under the current one
     float bn[8];
-    if (sh < np) atc_bias8(bT, k0 + 8 * sh, l, bn);
-    tc::mbar_wait(&bars[0], par);
+    if (sh < np) atc_bias8(brow, k0 + 8 * sh, l, bn);
+    if (warp == 0) tc::mbar_wait(&bars[0], (uint32_t)(chunk_i & 1));      // one warp polls, the others sleep at the barrier
+    __syncthreads();
     tc::fence_after();
+    if (sh == 0 && chunk_i > 0) take_output();
     // pass 1: bias, maximum; the biased scores go back to their columns
     float cm = -INFINITY;
 #pragma unroll 1
@@ -602,10 +624,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) pwa_attn_fwd_tc_kernel(const _
       float bc[8], sv[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) bc[j] = bn[j];
-      if (p + ATC_TS < np) atc_bias8(bT, k0 + 8 * (p + ATC_TS), l, bn);
+      if (p + ATC_TS < np) atc_bias8(brow, k0 + 8 * (p + ATC_TS), l, bn);
       tc::tmem_ld8(trow + (uint32_t)(8 * p), sv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { sv[j] += bc[j]; cm = fmaxf(cm, sv[j]); }
+      for (int j = 0; j < 8; ++j) { sv[j] = fmaf(bc[j], LOG2E, sv[j]); cm = fmaxf(cm, sv[j]); }
       tc::tmem_st8(trow + (uint32_t)(8 * p), sv);
     }
     red[sh * ATC_ROWS + rt] = cm;
@@ -614,7 +636,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) pwa_attn_fwd_tc_kernel(const _
 #pragma unroll
     for (int t = 0; t < ATC_TS; ++t) cm = fmaxf(cm, red[t * ATC_ROWS + rt]);
     const float mn = fmaxf(mx, cm);
-    const float corr = mx == -INFINITY ? 0.f : att_exp(mx - mn);
+    corr = mx == -INFINITY ? 0.f : atc_exp2(mx - mn);
     mx = mn;
     ssum *= corr;
     // pass 2: probabilities; hi over the scores, lo beside them
@@ -628,9 +650,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) pwa_attn_fwd_tc_kernel(const _
         if (drop) attn_drop4(A, row, (k0 + 8 * p) / 4 + q4, inv_keep, ms);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float pr = att_exp(sv[4 * q4 + j] - mn);
+          const float pr = atc_exp2(sv[4 * q4 + j] - mn);
           ssum += pr;
-          tc::split(pr * ms[j], sv[4 * q4 + j], pl[4 * q4 + j]);
+          tc::split(drop ? pr * ms[j] : pr, sv[4 * q4 + j], pl[4 * q4 + j]);
         }
       }
       tc::tmem_st8(trow + (uint32_t)(8 * p), sv);
@@ -638,29 +660,24 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) pwa_attn_fwd_tc_kernel(const _
     }
     tc::tmem_wait_st();
     tc::fence_before();
-    __syncthreads();          // P complete; also orders this chunk's reads of `red` before the next chunk's writes
+    __syncthreads();          // P complete (and share 0 has taken the previous output columns)
     if (tid == 0) {
       tc::fence_after();
       const uint32_t idesc = tc::idesc_tf32(16, 0, 0);
       for (int s = 0; s < np; ++s) {
         const uint64_t bv = tc::desc(vt + (uint32_t)((k0 >> 3) + s) * 512u, 128u, 256u);
+        // two accumulators (P_hi V, P_lo V): consecutive MMAs are independent, the dependent chains half as long
         tc::mma_tf32_ts(tmem + ATC_O, tmem + (uint32_t)(8 * s), bv, idesc, s > 0 ? 1u : 0u);
-        tc::mma_tf32_ts(tmem + ATC_O, tmem + ATC_PLO + (uint32_t)(8 * s), bv, idesc, 1u);
+        tc::mma_tf32_ts(tmem + ATC_O + 16u, tmem + ATC_PLO + (uint32_t)(8 * s), bv, idesc, s > 0 ? 1u : 0u);
       }
-      tc::commit(&bars[1]);
-    }
-    if (sh == 0) {
-      // shares 1.. run ahead into the next chunk: its score MMA is issued by thread 0 (share 0) after this read, and its P
-      // MMAs (which overwrite O) after the next chunk's block-wide barrier
-      tc::mbar_wait(&bars[1], par);
-      tc::fence_after();
-      float o[16];
-      tc::tmem_ld16(trow + ATC_O, o);
-#pragma unroll
-      for (int c = 0; c < ATC_C; ++c) acc[c] = fmaf(acc[c], corr, o[c] + o[8 + c]);
-      tc::fence_before();
+      if (k0 + ATC_CHUNK < L) issue_scores(k0 + ATC_CHUNK);
+      tc::commit(&bars[0]);
     }
   }
+  if (warp == 0) tc::mbar_wait(&bars[0], (uint32_t)(chunk_i & 1));
+  __syncthreads();
+  tc::fence_after();
+  if (sh == 0) take_output();
   __syncthreads();
   red[sh * ATC_ROWS + rt] = ssum;
   __syncthreads();
@@ -672,7 +689,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) pwa_attn_fwd_tc_kernel(const _
     float4* op = reinterpret_cast<float4*>(A.O + row * ATC_C);
     op[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
     op[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
-    A.lse[row] = mx + logf(tot);
+    A.lse[row] = mx * 0.6931471805599453f + logf(tot);
   }
   tc::fence_before();
   __syncthreads();
@@ -681,6 +698,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 2) pwa_attn_fwd_tc_kernel(const _
 
 static int g_attn_tc = 1;
 void pwa_attn_tc_set(int on) { g_attn_tc = on; }
+// windows of at least one 128-row tile, whole 16-key MMA columns, pieces of 8 keys that never straddle a modality block
+static bool attn_tc_eligible(int L, int l, int cq, int cv) {
+  return g_attn_tc && cq == ATC_C && cv == ATC_C && L >= 128 && L % 16 == 0 && l % 8 == 0;
+}
 
 // Backward: same CTA shape.  Phase A: a query row (ATT_TS threads, keys dealt in quads) -> dQ and the bias gradient;
 // phase B: a key row (queries dealt in turns) -> dK, dV.  P is recomputed from the saved row log-sum-exp.
@@ -916,7 +937,7 @@ static int launch_attn(const AttnArgs& A, bool bwd, cudaStream_t st) {
 }
 
 static int dispatch_attn(const AttnArgs& A, int cq, int cv, bool bwd, cudaStream_t st) {
-  if (!bwd && g_attn_tc && cq == ATC_C && cv == ATC_C && A.L >= 128 && A.L % 16 == 0) {
+  if (!bwd && A.biasN && attn_tc_eligible(A.L, A.l, cq, cv)) {
     const size_t smem = sizeof(float) * (2 * ATC_ROWS * ATC_C + ATC_TS * ATC_ROWS + (size_t)A.L * ATC_C * 2 + (size_t)A.L * 16);
     if (smem <= 100 * 1024) {
       VX_SET_SMEM(pwa_attn_fwd_tc_kernel, smem);
@@ -1241,10 +1262,12 @@ extern "C" int vx_pwa_block_fwd(const vx_pwa_desc* d, const void* const* in, voi
   // attention
   {
     const int nb = G.heads * G.l * G.l;
-    VX_LAUNCH(pwa_bias_kernel, dim3(cdiv(nb, 256)), dim3(256), 0, st, table, index, biasT, (float*)nullptr, G.heads, G.l);
+    // the query-major copy feeds the tensor-core kernel (a thread = query row reads 8 consecutive keys with two 16-byte loads)
+    float* biasN = attn_tc_eligible(G.L, G.l, P.cq_h, P.cv_h) ? (float*)(ws + P.off_biasN) : nullptr;
+    VX_LAUNCH(pwa_bias_kernel, dim3(cdiv(nb, 256)), dim3(256), 0, st, table, index, biasT, biasN, G.heads, G.l);
     VX_TRY(check_launch("pwa_bias_kernel"));
     AttnArgs A{};
-    A.Q = SV(SV_QT); A.K = SV(SV_KT); A.V = SV(SV_VT); A.biasT = biasT; A.O = SV(SV_OT); A.lse = SV(SV_LSE);
+    A.Q = SV(SV_QT); A.K = SV(SV_KT); A.V = SV(SV_VT); A.biasT = biasT; A.biasN = biasN; A.O = SV(SV_OT); A.lse = SV(SV_LSE);
     A.B = B; A.heads = G.heads; A.Ns = G.Ns; A.L = G.L; A.l = G.l;
     A.scale = 1.0f / sqrtf((float)P.cq_h); A.drop_p = attn_p; A.seed = d->seed; A.seed_dev = get_seed_dev();
     VX_TRY(dispatch_attn(A, P.cq_h, P.cv_h, false, st));
