@@ -502,13 +502,16 @@ __global__ void __launch_bounds__(JlcKs<CG>::MAXT, JlcKs<CG>::MINB) jlc_conv_fwd
 // ---------------------------------------------------------------------------------------------------
 struct SmallGeo { int nsplit, VP, KS, Dp, Hp, Wp, PV; };
 
+static int g_small_threads = 512;      // CTA size of the small-volume kernels (VX_OPT_JLC_SMALL_THREADS: 256 / 512 / 1024)
+void jlc_set_small_threads(int t) { if (t == 256 || t == 512 || t == 1024) g_small_threads = t; }
+
 static SmallGeo small_geo(int CG, int D, int H, int W) {
   SmallGeo g{};
   const int S = D * H * W;
   g.nsplit = (S + 127) / 128;
   const int Vc = (S + g.nsplit - 1) / g.nsplit;
   g.VP = (Vc + 31) & ~31;
-  g.KS = 256 / g.VP;
+  g.KS = g_small_threads / g.VP;         // reduction slices: the serial (channel, tap) walk of a thread shrinks with them
   if (g.KS > CG) g.KS = CG;
   while (CG % g.KS) --g.KS;
   g.Dp = D + 4; g.Hp = H + 4; g.Wp = W + 4;
@@ -517,7 +520,7 @@ static SmallGeo small_geo(int CG, int D, int H, int W) {
 }
 
 template <int CG>
-__global__ void __launch_bounds__(256) jlc_conv_small_fwd_kernel(const __grid_constant__ ConvFwdArgs A,
+__global__ void __launch_bounds__(1024) jlc_conv_small_fwd_kernel(const __grid_constant__ ConvFwdArgs A,
                                                                  const __grid_constant__ SmallGeo G) {
   VX_PDL_ENTRY();
   constexpr int NQ = CG / 4;
@@ -1002,7 +1005,7 @@ __global__ void __launch_bounds__(JlcKs<CG>::MAXT, JlcKs<CG>::MINB) jlc_conv_dgr
 // padded volumes (k=5 and k=3 share the halo-2 layout, k=1 is read at the centre), weights are staged flipped so the
 // loop is a plain correlation.
 template <int CG>
-__global__ void __launch_bounds__(256) jlc_conv_small_dgrad_kernel(const __grid_constant__ ConvDgradArgs A,
+__global__ void __launch_bounds__(1024) jlc_conv_small_dgrad_kernel(const __grid_constant__ ConvDgradArgs A,
                                                                    const __grid_constant__ SmallGeo G) {
   VX_PDL_ENTRY();
   constexpr int NQ = CG / 4;
@@ -1332,13 +1335,16 @@ static int launch_conv_dgrad(const ConvDgradArgs& A, int groups, cudaStream_t st
   return check_launch("jlc_conv_dgrad_kernel");
 }
 
+// threads of a small-volume CTA: the slab x slices actually used, at least 256 (the staging loops are dealt to all of them)
+static int small_block(const SmallGeo& G) { const int t = G.VP * G.KS; return t < 256 ? 256 : t; }
+
 template <int CG>
 static int launch_conv_small_fwd(const ConvFwdArgs& A, int groups, cudaStream_t st) {
   const SmallGeo G = small_geo(CG, A.D, A.H, A.W);
   const size_t smem = sizeof(float) * ((size_t)CG * G.PV + (size_t)CG * 153 * 4 + (size_t)G.KS * 12 * G.VP);
   if (smem > 200 * 1024) { set_error("jlc small fwd: volume too large for shared memory"); return VX_ERR_UNSUPPORTED; }
   VX_SET_SMEM((jlc_conv_small_fwd_kernel<CG>), smem);
-  VX_LAUNCH((jlc_conv_small_fwd_kernel<CG>), dim3(G.nsplit, groups * (CG / 4), A.B), dim3(256), smem, st, A, G);
+  VX_LAUNCH((jlc_conv_small_fwd_kernel<CG>), dim3(G.nsplit, groups * (CG / 4), A.B), dim3(small_block(G)), smem, st, A, G);
   return check_launch("jlc_conv_small_fwd_kernel");
 }
 
@@ -1348,7 +1354,7 @@ static int launch_conv_small_dgrad(const ConvDgradArgs& A, int groups, cudaStrea
   const size_t smem = sizeof(float) * ((size_t)3 * CG * G.PV + (size_t)CG * 153 * 4 + (size_t)G.KS * 4 * G.VP);
   if (smem > 200 * 1024) { set_error("jlc small dgrad: volume too large for shared memory"); return VX_ERR_UNSUPPORTED; }
   VX_SET_SMEM((jlc_conv_small_dgrad_kernel<CG>), smem);
-  VX_LAUNCH((jlc_conv_small_dgrad_kernel<CG>), dim3(G.nsplit, groups * (CG / 4), A.B), dim3(256), smem, st, A, G);
+  VX_LAUNCH((jlc_conv_small_dgrad_kernel<CG>), dim3(G.nsplit, groups * (CG / 4), A.B), dim3(small_block(G)), smem, st, A, G);
   return check_launch("jlc_conv_small_dgrad_kernel");
 }
 

@@ -135,6 +135,7 @@ int pw_tc_forward(const PwBatch& batch, cudaStream_t stream);
 void pw_tc_set(int enabled);
 void jlc_force_vx(int vx);
 void pwa_attn_tc_set(int on);
+void jlc_set_small_threads(int t);
 void jlc_set_ks(int ks);                                  // tuning probe: reduction slices of the level-1/2 conv kernels
 void jlc_set_small_max(int s);                            // tuning probe: voxel threshold of the small-volume conv kernels
 void jlc_force_tile(int kind, int tz, int ty);            // tuning probe: 0 = automatic
