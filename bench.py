@@ -385,7 +385,10 @@ def run_infer(rank, world, dev, reps=3, volume=(320, 320, 256)):
             "higher_is_better": False, "scaling": "strong", "n_gpus": world,
             "config": {"workload": "VeloxSeg Hecktor2022 eval, volume 2x%s, roi 128x128x64, overlap 0.25" % "x".join(map(str, volume)),
                        "windows": nwin, "sw_batch": sw,
-                       "io": ("1/world of the host volume per rank + all-gather; reduce-scatter, arg-max per slab, label gather"
+                       "io": (("pinned host volume uploaded in (plane slab x row slab) blocks on a copy stream in window order, a batch "
+                               "of windows waits only for its blocks; finished label planes (count division + arg-max) stream back "
+                               "under the remaining windows") if sharded_io and world == 1 else
+                              "1/world of the host volume per rank + all-gather; reduce-scatter, arg-max per slab, label gather"
                               if sharded_io else "every rank copies the whole host volume; all-reduce of the logit sums"),
                        "timed": "H2D volume + windows + all-reduce + argmax + D2H labels, best of %d" % reps,
                        "fg_voxels": int(seg.sum())}}

@@ -74,6 +74,11 @@ int vx_conv3_trace(long long* out64, int n);
 /* Measurement helpers (bench.py): kind 0 = fp32 FMA throughput probe (2 * 8 * 32 * iters * 148 * 8 * 256 flops per launch,
  * `scratch` = one device float), kind 1 = one empty kernel (calibrates the per-launch overhead of the event profiler). */
 int vx_microbench(int kind, int iters, void* scratch, vx_stream_t stream);
+/* Strided block copy between a pinned host volume and its device copy (either direction; both sides share `pitch_bytes`):
+ * `rows` rows of `width_bytes` each, `pitch_bytes` apart -- one call per (slab of planes x slab of rows) of a channel, so that the
+ * sliding-window driver (utils/inference_petct.py:214-230 through veloxseg_b200.inference.sliding_window_labels) can upload the
+ * volume in the order its windows need it.  kind: 0 = host to device, 1 = device to host.  Asynchronous on `stream`. */
+int vx_copy_block_async(void* dst, const void* src, size_t pitch_bytes, size_t width_bytes, size_t rows, int kind, vx_stream_t stream);
 /* number of kernels this library has enqueued since it was loaded (all threads, all streams) */
 uint64_t vx_launch_count(void);
 /* Per-kernel timing with CUDA events on the launching stream (diagnostics for bench.py; off by default).

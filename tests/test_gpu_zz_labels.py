@@ -19,7 +19,9 @@ def test_labels_equal_argmax_of_predict():
     torch.manual_seed(G.MODEL_SEED)
     m = VeloxSeg(**cfg).to(DEV).eval()
     pred = GraphedPredictor(m, 2, 2, roi, DEV)
-    for shape in [(1, 2, 72, 64, 100), (1, 2, 60, 64, 64)]:      # ragged on two axes; smaller than the roi on one (padding)
+    # ragged on two axes (two rows of windows: the upload is staged in two slabs and the first label planes travel back
+    # before the last windows run); smaller than the roi on one axis (padding: unstaged path); three rows of windows
+    for shape in [(1, 2, 72, 64, 100), (1, 2, 60, 64, 64), (1, 2, 160, 64, 80)]:
         vol = torch.randn(*shape, generator=torch.Generator().manual_seed(1)).pin_memory()
         ref = sliding_window_predict(vol.to(DEV), pred, roi, sw_batch_size=2, overlap=0.25).argmax(1)[0].to(torch.uint8).cpu()
         out_host = torch.empty(shape[2:], dtype=torch.uint8).pin_memory()
@@ -27,3 +29,4 @@ def test_labels_equal_argmax_of_predict():
         assert got is out_host and got.shape == ref.shape
         assert torch.equal(got, ref)
         assert 0 < int(got.sum()) < got.numel()                  # both classes present: the comparison is not vacuous
+        assert torch.equal(sliding_window_labels(vol, pred, roi, DEV, sw_batch_size=2, overlap=0.25), ref)      # result allocated by the call

@@ -98,7 +98,7 @@ SYMBOLS = [
     "vx_resize_workspace", "vx_resize_trilinear_fwd", "vx_resize_trilinear_bwd",
     "vx_segloss_workspace", "vx_segloss_fwd", "vx_segloss_bwd",
     "vx_patch_embed_fwd", "vx_patch_embed_bwd", "vx_pixel_shuffle_fwd", "vx_pixel_shuffle_bwd", "vx_adamw_step",
-    "vx_conv_workspace", "vx_conv_fwd", "vx_conv_bwd", "vx_conv3_trace", "vx_microbench",
+    "vx_conv_workspace", "vx_conv_fwd", "vx_conv_bwd", "vx_conv3_trace", "vx_microbench", "vx_copy_block_async",
 ]
 
 _WS_OPS = {"jlc", "mixer", "pwa_block", "gram_fwd", "lnpw", "segloss"}
@@ -149,6 +149,8 @@ class VxLib:
             f.argtypes = [vp, vp, vp, vp]
         self.c.vx_microbench.restype = C.c_int
         self.c.vx_microbench.argtypes = [C.c_int, C.c_int, vp, vp]
+        self.c.vx_copy_block_async.restype = C.c_int
+        self.c.vx_copy_block_async.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp]
         self.c.vx_conv3_trace.restype = C.c_int
         self.c.vx_conv3_trace.argtypes = [vp, C.c_int]
         if "VX_ATTN_TC" in os.environ:          # A/B switch of the tcgen05 attention forward (VX_OPT_ATTN_TC)

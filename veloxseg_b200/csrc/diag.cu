@@ -109,3 +109,21 @@ extern "C" int vx_microbench(int kind, int iters, void* scratch, vx_stream_t str
   VX_LAUNCH(null_kernel, dim3(1), dim3(32), 0, st, 0);
   return check_launch("null_kernel");
 }
+
+// pinned host <-> device strided block copy (see include/veloxseg_abi.h)
+extern "C" int vx_copy_block_async(void* dst, const void* src, size_t pitch_bytes, size_t width_bytes, size_t rows, int kind,
+                                   vx_stream_t stream) {
+  if (!dst || !src || width_bytes == 0 || rows == 0 || width_bytes > pitch_bytes || (kind != 0 && kind != 1)) {
+    set_error("copy_block: bad arguments");
+    return VX_ERR_BAD_DESC;
+  }
+#ifdef VX_EMU
+  for (size_t r = 0; r < rows; ++r) memcpy((char*)dst + r * pitch_bytes, (const char*)src + r * pitch_bytes, width_bytes);
+  return VX_OK;
+#else
+  const cudaError_t e = cudaMemcpy2DAsync(dst, pitch_bytes, src, pitch_bytes, width_bytes, rows,
+                                          kind == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error("copy_block: %s", cudaGetErrorString(e)); return VX_ERR_LAUNCH; }
+  return VX_OK;
+#endif
+}

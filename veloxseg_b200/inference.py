@@ -100,6 +100,17 @@ def sliding_window_predict(inputs: torch.Tensor, predictor: Callable, roi_size: 
     return out[:, :, lo[0]:lo[0] + size[0], lo[1]:lo[1] + size[1], lo[2]:lo[2] + size[2]]
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device):
+    """One upload stream per device, created on first use."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[key]
+
+
 @torch.no_grad()
 def sliding_window_labels(volume_host: torch.Tensor, predictor: Callable, roi_size: Sequence[int], device,
                           sw_batch_size: int = 2, overlap: float = 0.25, group=None, dst: int = 0,
@@ -131,11 +142,41 @@ def sliding_window_labels(volume_host: torch.Tensor, predictor: Callable, roi_si
         piece[:hi_e - lo_e].copy_(host_flat[lo_e:hi_e], non_blocking=True)
         flat = torch.empty(world * chunk, dtype=volume_host.dtype, device=device)
         dist.all_gather_into_tensor(flat, piece, group=group)
-    else:
-        flat = host_flat.to(device, non_blocking=True)
-    inputs = flat[:n].view(1, C, *size)
     pads = [max(r - s, 0) for r, s in zip(roi_size, size)]
     lo = [p // 2 for p in pads]
+    slab_ready = None           # world == 1: [(first-axis extent covered, event)] of the staged upload
+    if world > 1:
+        inputs = flat[:n].view(1, C, *size)
+    elif device.type == "cuda" and not any(pads) and volume_host.is_pinned() and volume_host.is_contiguous():
+        # one GPU: the windows are visited in (first axis, second axis) order, so the volume is uploaded on a copy stream in
+        # blocks (slab of planes x slab of rows: what the next row of windows adds) and a batch of windows waits only for the
+        # blocks it reads -- the rest of the upload runs under the forward passes of the earlier windows
+        from ._lib import get_lib
+        lib = get_lib()
+        inputs = torch.empty((1, C, *size), dtype=volume_host.dtype, device=device)
+        per0 = axis_starts(size, roi_size, overlap)
+        xe = sorted({a + roi_size[0] for a in per0[0]})
+        ye = sorted({b + roi_size[1] for b in per0[1]})
+        cur = torch.cuda.current_stream(device)
+        cs = _copy_stream(device)
+        cs.wait_stream(cur)
+        esz = volume_host.element_size()
+        plane, rowb = size[1] * size[2] * esz, size[2] * esz
+        slab_ready, x0 = [], 0
+        for x1 in xe:
+            y0 = 0
+            for y1 in ye:
+                for c in range(C):
+                    off = ((c * size[0] + x0) * size[1] + y0) * size[2] * esz
+                    lib.check(lib.c.vx_copy_block_async(inputs.data_ptr() + off, volume_host.data_ptr() + off, plane, (y1 - y0) * rowb,
+                                                        x1 - x0, 0, cs.cuda_stream), "vx_copy_block_async")
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                slab_ready.append(((x1, y1), ev))
+                y0 = y1
+            x0 = x1
+    else:
+        inputs = host_flat.to(device, non_blocking=True).view(1, C, *size)
     if any(pads):
         inputs = F.pad(inputs, [lo[2], pads[2] - lo[2], lo[1], pads[1] - lo[1], lo[0], pads[0] - lo[0]])
     image = list(inputs.shape[2:])
@@ -144,8 +185,35 @@ def sliding_window_labels(volume_host: torch.Tensor, predictor: Callable, roi_si
     xs = -(-image[0] // world)                      # slab thickness; the accumulator is padded to world * xs planes
     mine = [i for i in range(len(starts)) if i % world == rank]
     acc = None
+    # one GPU with a pinned result buffer: planes no later window touches are finished (count division, arg-max) and sent back
+    # while the remaining windows run
+    stream_out = slab_ready is not None and out_host is not None and out_host.is_pinned()
+    fin, counts, keep = 0, None, []
+
+    def finish_planes(x1):
+        nonlocal fin, counts
+        if counts is None:
+            counts = axis_counts(image, roi_size, per_axis, acc.device, acc.dtype)
+        cx, cy, cz = counts
+        part = acc[:, fin:x1] / (cx[fin:x1, None, None] * cy[None, :, None] * cz[None, None, :])
+        lab = part.argmax(0).to(torch.uint8)
+        cur, cs = torch.cuda.current_stream(device), _copy_stream(device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        cs.wait_event(ev)
+        with torch.cuda.stream(cs):
+            out_host[fin:x1].copy_(lab, non_blocking=True)
+        keep.append(lab)            # alive until the final synchronisation
+        fin = x1
+
     for g in range(0, len(mine), sw_batch_size):
         ids = mine[g:g + sw_batch_size]
+        if slab_ready is not None:
+            # blocks are uploaded in (first axis, second axis) order = the order of the windows: everything up to the last
+            # block this batch touches
+            need = max((starts[i][0] + roi_size[0], starts[i][1] + roi_size[1]) for i in ids)
+            while slab_ready and slab_ready[0][0] <= need:
+                torch.cuda.current_stream(device).wait_event(slab_ready.pop(0)[1])
         win = torch.cat([inputs[:, :, a:a + roi_size[0], b:b + roi_size[1], c:c + roi_size[2]]
                          for a, b, c in (starts[i] for i in ids)])
         y = _logits(predictor(win))
@@ -154,6 +222,14 @@ def sliding_window_labels(volume_host: torch.Tensor, predictor: Callable, roi_si
         for k, i in enumerate(ids):
             a, b, c = starts[i]
             acc[:, a:a + roi_size[0], b:b + roi_size[1], c:c + roi_size[2]] += y[k]
+        if stream_out:
+            rest = mine[g + sw_batch_size:]
+            done_to = min(starts[i][0] for i in rest) if rest else image[0]
+            if done_to > fin:
+                finish_planes(done_to)
+    if stream_out and acc is not None:
+        _copy_stream(device).synchronize()
+        return out_host
     if acc is None:         # more ranks than windows
         n_cls = _logits(predictor(inputs[:, :, :roi_size[0], :roi_size[1], :roi_size[2]])).shape[1]
         acc = torch.zeros((n_cls, world * xs, image[1], image[2]), dtype=inputs.dtype, device=device)
