@@ -291,12 +291,18 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restric
 // ---------------------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------------------
-// channel tile and reduction slices: aim at >= ~64 K threads in flight, at most 8 slices and >= 8 reduction steps per slice
+// channel tile and reduction slices: aim at >= ~64 K threads in flight, at most 8 slices and >= 8 reduction steps per slice.
+// More slices do not pay: every CTA stages the whole weight tile, and at 256 K / 512 K threads the k7 s4 stem measured 113 us
+// against 74 us (profiles/r3v_conv_target.txt; VX_CONV_TARGET_THREADS is the probe)
+static long long conv_target_threads() {
+  static long long t = [] { const char* e = getenv("VX_CONV_TARGET_THREADS"); return e ? atoll(e) : 65536LL; }();
+  return t;
+}
 static void pick_tile_ks(long long nvox, int chans, int steps, int& ct, int& ks) {
   ct = chans >= 16 ? 16 : chans >= 8 ? 8 : 4;
   while (ct > 4 && nvox * cdiv(chans, ct) < 32768) ct >>= 1;
   ks = 1;
-  while (ks < 8 && nvox * cdiv(chans, ct) * ks < 65536 && steps / (2 * ks) >= 8) ks <<= 1;
+  while (ks < 8 && nvox * cdiv(chans, ct) * ks < conv_target_threads() && steps / (2 * ks) >= 8) ks <<= 1;
 }
 
 template <int KW>
