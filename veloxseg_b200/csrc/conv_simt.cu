@@ -32,7 +32,7 @@ struct ConvGeo {
 // meet in shared memory (fixed order).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int CT, int KW>      // KW = kernel width known at compile time, 0 = runtime
-__global__ void __launch_bounds__(256) conv_strided_kernel(ConvGeo G, const float* __restrict__ X, const float* __restrict__ Wt,
+__global__ void __launch_bounds__(256, 2) conv_strided_kernel(ConvGeo G, const float* __restrict__ X, const float* __restrict__ Wt,
                                                            const float* __restrict__ bias, float* __restrict__ Y, int rchunk) {
   VX_PDL_ENTRY();
   VX_DYN_SMEM(float, ws);                              // [rchunk][k][CT], reused as [KS][32][CT] for the final fold
@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(256) conv_strided_kernel(ConvGeo G, const floa
   for (int rc = 0; rc < R; rc += rchunk) {
     const int rn = min(rchunk, R - rc);
     __syncthreads();
-    for (int e = tid; e < rn * k * CT; e += nthr) {
+#pragma unroll 4
+    for (int e = tid; e < rn * k * CT; e += nthr) {      // 4 independent loads in flight per thread (17 % of the kernel's samples rolled)
       const int c = e / (rn * k), rt = e % (rn * k);   // (row, tx) fastest: contiguous reads of one output channel's taps
       const int r = rc + rt / k, tx = rt % k;
       const int i = r / k2, tzy = r % k2;
@@ -64,18 +65,21 @@ __global__ void __launch_bounds__(256) conv_strided_kernel(ConvGeo G, const floa
     }
     __syncthreads();
     if (!live) continue;
-#pragma unroll 2
+#pragma unroll 4
     for (int rr = ks; rr < rn; rr += KS) {
       const int r = rc + rr;
       const int i = r / k2, tz = (r % k2) / k, ty = r % k;
       const int z = z0 + tz, y = y0 + ty;
-      if (z < 0 || z >= G.D || y < 0 || y >= G.H) continue;
+      const bool rok = z >= 0 && z < G.D && y >= 0 && y < G.H;
+      if (!KW && !rok) continue;
       const float* xr = xb + (size_t)i * SV + ((size_t)z * G.H + y) * G.W + x0;
       const float* wr = ws + rr * k * CT;
       if (KW) {
+        // branch-free rows (an out-of-bounds row loads nothing and adds zeros): the loads of the unrolled rows can be issued
+        // together -- with a `continue` here ptxas kept each row's loads behind the previous row's FMAs
         float xv[KW ? KW : 1];
 #pragma unroll
-        for (int tx = 0; tx < KW; ++tx) xv[tx] = (x0 + tx >= 0 && x0 + tx < G.W) ? __ldg(xr + tx) : 0.f;
+        for (int tx = 0; tx < KW; ++tx) xv[tx] = (rok && x0 + tx >= 0 && x0 + tx < G.W) ? __ldg(xr + tx) : 0.f;
 #pragma unroll
         for (int tx = 0; tx < KW; ++tx) {
 #pragma unroll
@@ -299,7 +303,9 @@ static long long conv_target_threads() {
   return t;
 }
 static void pick_tile_ks(long long nvox, int chans, int steps, int& ct, int& ks) {
+  static const int ct_max = [] { const char* e = getenv("VX_CONV_CT_MAX"); return e ? atoi(e) : 16; }();      // probe
   ct = chans >= 16 ? 16 : chans >= 8 ? 8 : 4;
+  if (ct > ct_max) ct = ct_max;
   while (ct > 4 && nvox * cdiv(chans, ct) < 32768) ct >>= 1;
   ks = 1;
   while (ks < 8 && nvox * cdiv(chans, ct) * ks < conv_target_threads() && steps / (2 * ks) >= 8) ks <<= 1;
@@ -318,7 +324,7 @@ int conv_strided(const ConvGeo& G, const float* X, const float* Wt, const float*
   const int R = G.Ci * G.k * G.k;
   int ct, ks;
   pick_tile_ks(nvox, G.Co, R, ct, ks);
-  int rchunk = (40 * 1024 / 4) / (G.k * ct);
+  int rchunk = (46 * 1024 / 4) / (G.k * ct);             // the k7 s4 stem (98 rows x 7 x 16 channels = 43.9 KB) in one chunk
   if (rchunk > R) rchunk = R;
   if (rchunk < 1) rchunk = 1;
   size_t smem = sizeof(float) * (size_t)rchunk * G.k * ct;
