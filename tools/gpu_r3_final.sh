@@ -1,0 +1,17 @@
+#!/bin/bash
+# final evidence set (second session) on one B200: full GPU suite, smoke, the default bench line, the ncu launch list of the same bench
+# command (eager step so that every kernel is a launch), ncu --set full of the dominant kernel
+mkdir -p gpurun_out; O=gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q > $O/r3y_pytest_gpu.log 2>&1; echo "exit $?" >> $O/r3y_pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke > $O/r3y_smoke.log 2>&1; echo "exit $?" >> $O/r3y_smoke.log
+timeout 1200 python bench.py > $O/r3y_bench.log 2>&1; echo "exit $?" >> $O/r3y_bench.log
+VX_NCU=1 VX_GRAPH=0 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r3y_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-eager --no-cpu-baseline --no-infer > $O/r3y_ncu_bench.log 2>&1
+python tools/launch_summary.py $O/r3y_launches.csv 60 > $O/r3y_launches_summary.txt 2>&1
+bash tools/gpu_ncu_ops.sh r3y_pw_tc_L1 jlc_L1 pw_tc_kernel 4 3
+bash tools/gpu_ncu_ops.sh r3y_pw_tc_pwa_L1 pwa_L1 pw_tc_kernel 8 4
+python tools/ncu_digest.py $O/r3y_pw_tc_L1.raw.csv > $O/r3y_pw_tc_L1.digest.txt; python tools/ncu_digest.py $O/r3y_pw_tc_pwa_L1.raw.csv > $O/r3y_pw_tc_pwa_L1.digest.txt
+rm -f $O/r3y_pw_tc_pwa_L1.ncu-rep
+tail -3 $O/r3y_pytest_gpu.log; tail -1 $O/r3y_smoke.log; head -25 $O/r3y_launches_summary.txt; tail -c 600 $O/r3y_bench.log
+bash tools/gpu_ncu_ops.sh r3y_attn_tc pwa_L2 "pwa_attn_fwd_tc" 2 1
+python tools/ncu_digest.py $O/r3y_attn_tc.raw.csv > $O/r3y_attn_tc.digest.txt; rm -f $O/r3y_attn_tc.ncu-rep
