@@ -64,11 +64,14 @@ const char* vx_last_error_string(void);
  *                           runs on the tcgen05 kernel (QK^T and PV as 3xTF32 MMAs, P in tensor memory); 0: fp32 SIMT kernel.
  *   VX_OPT_JLC_SMALL_THREADS  CTA size of the small-volume JLC convolution kernels: 256 / 512 (default) / 1024 (tuning probe: more
  *                           threads = more reduction slices = a shorter serial tap walk per thread).
+ *   VX_OPT_FFN_TC           1 (default): the two-layer MLP of the level-1/2 JLC and PWA blocks (S >= 1024, fp32 mode) runs as one
+ *                           tcgen05 kernel per direction (hidden activation handed from the first accumulator to the second MMA inside
+ *                           tensor memory); 0: two contraction launches.
  *   VX_OPT_CONV3_TRACE      0 (default).  1: CTA 0 of the dense-convolution forward kernel records clock64() at its phase
  *                           boundaries; vx_conv3_trace() copies the 64 stamps out (developer diagnostics, tools/conv3_phases.py). */
 enum { VX_OPT_PW_TENSOR_CORES = 1, VX_OPT_PW_SMALL_MAX_S = 2, VX_OPT_PW_TC_MIN_S = 3, VX_OPT_JLC_TILE_FWD = 4,
        VX_OPT_JLC_TILE_WGRAD = 5, VX_OPT_JLC_SMALL_MAX_S = 8, VX_OPT_WGRAD_TC_MIN_S = 9, VX_OPT_SIDE_WGRAD = 10,
-       VX_OPT_CONV3_TRACE = 13, VX_OPT_PRECISION = 14, VX_OPT_JLC_KS = 15, VX_OPT_PDL = 16, VX_OPT_ATTN_TC = 17, VX_OPT_JLC_SMALL_THREADS = 18 };
+       VX_OPT_CONV3_TRACE = 13, VX_OPT_PRECISION = 14, VX_OPT_JLC_KS = 15, VX_OPT_PDL = 16, VX_OPT_ATTN_TC = 17, VX_OPT_JLC_SMALL_THREADS = 18, VX_OPT_FFN_TC = 19 };
 int vx_set_option(int option, int value);
 int vx_conv3_trace(long long* out64, int n);
 /* Measurement helpers (bench.py): kind 0 = fp32 FMA throughput probe (2 * 8 * 32 * iters * 148 * 8 * 256 flops per launch,

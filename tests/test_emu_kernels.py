@@ -24,7 +24,8 @@ def _oracle():
 
 @pytest.mark.parametrize("C,groups,e,shape,B", [(8, 2, 3, (5, 6, 8), 2), (16, 2, 2, (3, 4, 7), 1), (32, 2, 2, (3, 3, 3), 2),
                                                   (8, 2, 3, (9, 7, 12), 1), (16, 2, 2, (9, 8, 12), 1), (8, 2, 2, (9, 9, 7), 1),
-                                                  (8, 2, 2, (12, 14, 14), 1)])      # last: two combine chunks per row (S > 2048)
+                                                  (8, 2, 2, (12, 14, 14), 1),       # two combine chunks per row (S > 2048)
+                                                  (16, 2, 2, (7, 12, 13), 1)])      # S = 1092, C = 16: the fused tcgen05 FFN (ragged last tile)
 def test_jlc(emu, C, groups, e, shape, B):
     from veloxseg_b200 import ops
     O = _oracle()
@@ -140,6 +141,7 @@ PWA_CASES = [
     ((12, 12, 12), 16, [3, 3, 3], [1, 1, 1], 1, 4, 1, 1, 1),
     ((8, 8, 8), 8, [4, 4, 4], [1, 1, 1], 1, 4, 2, 2, 1),      # l = 64: the vectorised bias-gradient path of level 2
     ((8, 8, 12), 8, [4, 4, 6], [1, 1, 1], 1, 8, 2, 2, 1),     # L = 192, 8 channels per head: the tcgen05 attention forward
+    ((8, 8, 16), 16, [4, 4, 8], [1, 1, 1], 1, 4, 2, 2, 1),    # S = 1024, C = 16: the fused tcgen05 FFN, two modalities per launch
 ]
 
 
@@ -191,8 +193,14 @@ def test_pwa_block(emu, size, C, mb, ms, heads, mdh, M, e, B):
     dxs, dps, dtable = ops.pwa_block_bwd_raw(emu, 0, dzs, xs, flat, table, index, saved, geo, e)
     got = list(dxs) + list(dps) + [dtable]
     names = [f"dx{m}" for m in range(M)] + [n.format(m=m) for m in range(M) for n in PWA_PARAM_NAMES] + ["table"]
-    bad = [(n, rel_err(g, r)) for n, g, r in zip(names, got, grads) if not close(g, r, rtol=3e-4, atol=2e-5)]
+    # with a single modality the key bias shifts every score of a row equally: softmax-invariant, true gradient 0 -- what the
+    # kernels return there is round-off of the chain above it (same rule as tests/test_gpu_ops.py::test_pwa_block_levels)
+    zero = {"attn.qkv_proj.0.1.bias"} if M == 1 else set()
+    bad = [(n, rel_err(g, r)) for n, g, r in zip(names, got, grads) if n not in zero and not close(g, r, rtol=3e-4, atol=2e-5)]
     assert not bad, bad
+    for n, g in zip(names, got):
+        if n in zero:
+            assert float(g.abs().max()) <= 1e-3 * float(grads[names.index("attn.qkv_proj.0.1.weight")].abs().max()), n
 
 
 @pytest.mark.parametrize("src,dst", [((3, 3, 3), (12, 12, 12)), ((2, 5, 4), (8, 10, 8)), ((6, 6, 6), (12, 12, 12)), ((1, 3, 2), (4, 6, 8)),

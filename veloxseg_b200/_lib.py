@@ -157,6 +157,8 @@ class VxLib:
             self.c.vx_set_option(17, int(os.environ["VX_ATTN_TC"]))
         if "VX_JLC_SMALL_THREADS" in os.environ:
             self.c.vx_set_option(18, int(os.environ["VX_JLC_SMALL_THREADS"]))
+        if "VX_FFN_TC" in os.environ:
+            self.c.vx_set_option(19, int(os.environ["VX_FFN_TC"]))
         if "VX_PDL" in os.environ:              # A/B switch of the programmatic-dependent-launch path (VX_OPT_PDL)
             self.c.vx_set_option(16, int(os.environ["VX_PDL"]))
         self.c.vx_pwa_saved_layout.restype = C.c_int

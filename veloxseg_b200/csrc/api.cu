@@ -225,6 +225,7 @@ extern "C" int vx_set_option(int option, int value) {
   if (option == VX_OPT_JLC_SMALL_MAX_S) { vx::jlc_set_small_max(value); return VX_OK; }
   if (option == VX_OPT_JLC_KS) { vx::jlc_set_ks(value); return VX_OK; }
   if (option == VX_OPT_JLC_SMALL_THREADS) { vx::jlc_set_small_threads(value); return VX_OK; }
+  if (option == VX_OPT_FFN_TC) { vx::pw_ffn_tc_set(value ? 1 : 0); return VX_OK; }
   if (option == VX_OPT_ATTN_TC) { vx::pwa_attn_tc_set(value ? 1 : 0); return VX_OK; }
   if (option == VX_OPT_CONV3_TRACE) { vx::conv3_trace_set(value); return VX_OK; }
   if (option == VX_OPT_PRECISION) { vx::precision_set(value); return VX_OK; }

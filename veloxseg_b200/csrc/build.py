@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["api.cu", "pointwise.cu", "pw_tc.cu", "pw_wgrad_tc.cu", "jlc.cu", "conv3_tc.cu", "conv_simt.cu", "ops_misc.cu", "pwa.cu", "resize.cu", "segloss.cu", "stem.cu", "diag.cu"]
+SOURCES = ["api.cu", "pointwise.cu", "pw_tc.cu", "pw_ffn_tc.cu", "pw_wgrad_tc.cu", "jlc.cu", "conv3_tc.cu", "conv_simt.cu", "ops_misc.cu", "pwa.cu", "resize.cu", "segloss.cu", "stem.cu", "diag.cu"]
 LIB = os.path.join(os.path.dirname(HERE), "libveloxseg_sm100.so")
 EMU_LIB = os.path.join(ROOT, "tools", "emu", "libveloxseg_emu.so")
 

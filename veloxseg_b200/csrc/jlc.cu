@@ -1435,7 +1435,8 @@ extern "C" int vx_jlc_fwd(const vx_jlc_desc* d, const void* const* in, void* con
     f.W2 = (const float*)in[9]; f.b2 = (const float*)in[10];
     if (d->training && d->drop_p > 0.f) { f.drop_p = d->drop_p; f.seed = d->seed; f.site = 1; }
     f.res = o; f.res_scale = 1.f; f.y = y;
-    const int rc = pw_ffn_small(fb, st);
+    int rc = pw_ffn_small(fb, st);
+    if (rc == 1) rc = pw_ffn_tc(fb, st);
     if (rc <= 0) return rc;
   }
   // hpre = W1 IN(o) + b1
@@ -1518,7 +1519,8 @@ extern "C" int vx_jlc_bwd(const vx_jlc_desc* d, const void* const* in, void* con
     FfnBwdProblem& f = fb.p[0];
     f.dy = dy; f.C = C; f.W2 = fw2; f.eC = eC; f.hpre = hpre; f.dh = dh; f.W1 = fw1; f.dx = dohat;
     if (drop) { f.out_drop_p = d->drop_p; f.out_seed = d->seed; f.out_site = 1; }
-    const int rc = pw_ffn_small_bwd(fb, st);
+    int rc = pw_ffn_small_bwd(fb, st);
+    if (rc == 1) rc = pw_ffn_tc_bwd(fb, st);
     if (rc != VX_OK && rc != 1) return rc;
     ffn_fused = rc == VX_OK;
   }

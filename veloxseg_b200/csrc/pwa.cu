@@ -1312,7 +1312,8 @@ extern "C" int vx_pwa_block_fwd(const vx_pwa_desc* d, const void* const* in, voi
       }
       f.res = SV(SV_Y) + (size_t)m * C * BS; f.res_scale = 1.f; f.y = Z(m);
     }
-    const int rc = pw_ffn_small(fb, st);
+    int rc = pw_ffn_small(fb, st);
+    if (rc == 1) rc = pw_ffn_tc(fb, st);
     if (rc < 0) return rc;
     if (rc == 0) return VX_OK;
   }
@@ -1423,7 +1424,8 @@ extern "C" int vx_pwa_block_bwd(const vx_pwa_desc* d, const void* const* in, voi
         f.mid_drop_p = proj_p; f.mid_seed = seedm(m); f.mid_site = SITE_FFN1;
       }
     }
-    const int rc = pw_ffn_small_bwd(fb, st);
+    int rc = pw_ffn_small_bwd(fb, st);
+    if (rc == 1) rc = pw_ffn_tc_bwd(fb, st);
     if (rc != VX_OK && rc != 1) return rc;
     ffn_fused = rc == VX_OK;
   }

@@ -67,6 +67,11 @@ struct FfnBwdProblem {
 };
 struct FfnBwdBatch { FfnBwdProblem p[VX_MAX_MODAL]; int nprob; int B; int S; const unsigned long long* seed_dev; };
 int pw_ffn_small_bwd(const FfnBwdBatch& batch, cudaStream_t stream);
+// the same two ops for S >= 1024 on tcgen05 (pw_ffn_tc.cu): the first contraction's accumulator becomes the second's A operand
+// inside tensor memory.  Same return convention (1 = not eligible: bf16 mode, channel counts off the MMA grid, option off).
+int pw_ffn_tc(const FfnBatch& batch, cudaStream_t stream);
+int pw_ffn_tc_bwd(const FfnBwdBatch& batch, cudaStream_t stream);
+void pw_ffn_tc_set(int on);
 
 #if defined(__CUDACC__) || defined(VX_EMU)
 // Address of one input element of the (possibly multi-source) X operand.
