@@ -42,19 +42,34 @@ struct FfnTcBatch { FfnTcProblem p[VX_MAX_MODAL]; int nprob, B, S, bwd; const un
 // K halves 128 B apart (descriptor LBO = 128, SBO = 256, start = block of the k-step)
 VX_DEV int ft_kmajor(int N, int n, int k) { return (k >> 3) * N * 8 + (n >> 3) * 64 + ((k >> 2) & 1) * 32 + (n & 7) * 4 + (k & 3); }
 
-// weights (N x K) -> hi / lo images.  `transposed`: element (n, k) is W[k * N + n] (walk n fastest: contiguous reads), else W[n * K + k]
+// weights (N x K) -> hi / lo images, four elements of the contiguous axis per step (N, K multiples of 16, 16-byte rows).
+// `transposed`: element (n, k) is W[k * N + n] (a quad = 4 consecutive n: four 4-byte stores), else W[n * K + k] (a quad = 4
+// consecutive k = one 16-byte store into the core matrix row)
 VX_DEV void ft_stage_weights(float* hi, float* lo, const float* __restrict__ W, int N, int K, int transposed, int tid) {
-#pragma unroll 4
-  for (int e = tid; e < N * K; e += FT_THREADS) {
-    const int n = transposed ? e % N : e / K, k = transposed ? e / N : e % K;
-    float h, l;
-    tc::split(__ldg(W + e), h, l);
-    const int o = ft_kmajor(N, n, k);
-    hi[o] = h; lo[o] = l;
+  const int nq = (N * K) >> 2;
+#pragma unroll 2
+  for (int q = tid; q < nq; q += FT_THREADS) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(W) + q);
+    const float wv[4] = {w.x, w.y, w.z, w.w};
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tc::split(wv[j], h[j], l[j]);
+    const int e = q << 2;
+    if (transposed) {
+      const int n = e % N, k = e / N;
+      const int o = ft_kmajor(N, n, k);              // n .. n + 3 stay inside one 8-row group: 4 floats apart
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { hi[o + 4 * j] = h[j]; lo[o + 4 * j] = l[j]; }
+    } else {
+      const int n = e / K, k = e % K;
+      const int o = ft_kmajor(N, n, k);
+      *reinterpret_cast<float4*>(hi + o) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(lo + o) = make_float4(l[0], l[1], l[2], l[3]);
+    }
   }
 }
 
-__global__ void __launch_bounds__(FT_THREADS, 2) pw_ffn_tc_kernel(const __grid_constant__ FfnTcBatch batch) {
+__global__ void __launch_bounds__(FT_THREADS, 3) pw_ffn_tc_kernel(const __grid_constant__ FfnTcBatch batch) {
   VX_PDL_ENTRY();
   const FfnTcProblem& P = batch.p[blockIdx.z];
   const int S = batch.S, C = P.C, eC = P.eC, b = blockIdx.y, bwd = batch.bwd;
@@ -205,8 +220,8 @@ static int g_ffn_tc = 1;
 void pw_ffn_tc_set(int on) { g_ffn_tc = on; }
 
 static bool ffn_tc_shape_ok(int S, int C, int eC, const float* Wa, const float* Wb) {
-  return S >= 1024 && (C & 15) == 0 && (eC & 15) == 0 && C <= 128 && eC <= 256 && 2 * eC + 2 * C <= 512 && !((uintptr_t)Wa & 3) &&
-         !((uintptr_t)Wb & 3);
+  return S >= 1024 && (C & 15) == 0 && (eC & 15) == 0 && C <= 128 && eC <= 256 && 2 * eC + 2 * C <= 512 && !((uintptr_t)Wa & 15) &&
+         !((uintptr_t)Wb & 15);
 }
 
 static int launch_ffn_tc(FfnTcBatch& T, int Cmax, int eCmax, double bytes, double flops, cudaStream_t stream) {
