@@ -108,5 +108,6 @@ static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f
 static inline int __float_as_int(float v) { int i; memcpy(&i, &v, 4); return i; }
 #define INFINITY_F (__builtin_inff())
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }

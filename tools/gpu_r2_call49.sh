@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out; O=gpurun_out
 for L in 1 2; do
-  n=r4a_wgrad_tc_L$L
-  bash tools/gpu_ncu_ops.sh $n jlc_L$L "pw_wgrad_tc" 2 1
+  n=r4c_jlc_wgrad_L$L
+  bash tools/gpu_ncu_ops.sh $n jlc_L$L "jlc_conv_wgrad" 2 1
   python tools/ncu_digest.py $O/$n.raw.csv > $O/$n.digest.txt 2>&1
   ncu -i $O/$n.ncu-rep --page source --csv --print-source cuda,sass > $O/$n.source.csv 2>/dev/null
   python tools/ncu_source_digest.py $O/$n.source.csv 22 > $O/$n.source.txt 2>&1

@@ -787,40 +787,67 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_kernel(const __grid_const
   for (int ck = blockIdx.x; ck < B * nchunks; ck += nK) {
     const int b = ck / nchunks, vbase = (ck % nchunks) * TV;
     __syncthreads();
+    // staging in rounds of WG_U elements per thread: every load of a round is issued before the first prologue (the rolled
+    // one-load-per-iteration form made a thread wait out ~80 L2 round trips per chunk at levels 3-4); TV is a power of two
+    constexpr int WG_U = 4;
+    const int tvs = __ffs(TV) - 1;
 #pragma unroll 1
-    for (int idx = tid; idx < Co4 * TV; idx += WG_THREADS) {
-      const int co = idx / TV, v = idx % TV, gv = vbase + v;
-      float val = 0.f;
-      if (co < Co && gv < S) {
-        const size_t gi = ((size_t)b * Co + co) * S + gv;
-        val = __ldg(P.dY + gi);
-        if (P.y_drop_p > 0.f) val *= dropout_scale(P.y_seed + soff, P.y_site, gi, P.y_drop_p, yinv);
+    for (int idx0 = tid; idx0 < Co4 * TV; idx0 += WG_U * WG_THREADS) {
+      float val[WG_U];
+      size_t gi[WG_U];
+      bool ok[WG_U];
+#pragma unroll
+      for (int u = 0; u < WG_U; ++u) {
+        const int idx = idx0 + u * WG_THREADS;
+        const int co = idx >> tvs, gv = vbase + (idx & (TV - 1));
+        ok[u] = idx < Co4 * TV && co < Co && gv < S;
+        gi[u] = ok[u] ? ((size_t)b * Co + co) * S + gv : 0;
+        val[u] = ok[u] ? __ldg(P.dY + gi[u]) : 0.f;
       }
-      sY[v * CoP + co] = val;
+#pragma unroll
+      for (int u = 0; u < WG_U; ++u) {
+        const int idx = idx0 + u * WG_THREADS;
+        if (idx >= Co4 * TV) continue;
+        if (ok[u] && P.y_drop_p > 0.f) val[u] *= dropout_scale(P.y_seed + soff, P.y_site, gi[u], P.y_drop_p, yinv);
+        sY[(idx & (TV - 1)) * CoP + (idx >> tvs)] = val[u];
+      }
     }
 #pragma unroll 1
-    for (int idx = tid; idx < ccount * TV; idx += WG_THREADS) {
-      const int cl = idx / TV, v = idx % TV, gv = vbase + v;
-      const int cg = cbeg + cl;
-      float val = 0.f;
-      if (gv < S) {
-        if (cg < Ci) {
+    for (int idx0 = tid; idx0 < ccount * TV; idx0 += WG_U * WG_THREADS) {
+      float val[WG_U];
+      bool ok[WG_U];
+#pragma unroll
+      for (int u = 0; u < WG_U; ++u) {
+        const int idx = idx0 + u * WG_THREADS;
+        const int cg = cbeg + (idx >> tvs), gv = vbase + (idx & (TV - 1));
+        ok[u] = idx < ccount * TV && gv < S && cg < Ci;
+        val[u] = 0.f;
+        if (ok[u]) {
           int c = cg, s2 = 0;
           while (s2 < P.nsrc - 1 && c >= P.src[s2].C) { c -= P.src[s2].C; ++s2; }
-          val = __ldg(P.src[s2].ptr + ((size_t)b * P.src[s2].C + c) * S + gv);
-          if (P.xpro == PRO_AFFINE) {
-            const int k = b * P.x_bstride + cg;
-            val = fmaf(val, __ldg(P.xa + k), __ldg(P.xc + k));
-          } else if (P.xpro == PRO_GELU) {
-            val = gelu_f(val);
-          } else if (P.xpro == PRO_GELU_DROPOUT) {
-            val = gelu_f(val) * dropout_scale(P.x_seed + soff, P.x_site, ((uint64_t)b * Ci + cg) * (uint64_t)S + gv, P.x_drop_p, xinv);
-          }
-        } else if (cg == Ci) {
-          val = 1.f;
+          val[u] = __ldg(P.src[s2].ptr + ((size_t)b * P.src[s2].C + c) * S + gv);
+        } else if (idx < ccount * TV && gv < S && cg == Ci) {
+          val[u] = 1.f;
         }
       }
-      sX[v * CiP + cl] = val;
+#pragma unroll
+      for (int u = 0; u < WG_U; ++u) {
+        const int idx = idx0 + u * WG_THREADS;
+        if (idx >= ccount * TV) continue;
+        const int cl = idx >> tvs, v = idx & (TV - 1);
+        if (ok[u]) {
+          const int cg = cbeg + cl, gv = vbase + v;
+          if (P.xpro == PRO_AFFINE) {
+            const int k = b * P.x_bstride + cg;
+            val[u] = fmaf(val[u], __ldg(P.xa + k), __ldg(P.xc + k));
+          } else if (P.xpro == PRO_GELU) {
+            val[u] = gelu_f(val[u]);
+          } else if (P.xpro == PRO_GELU_DROPOUT) {
+            val[u] = gelu_f(val[u]) * dropout_scale(P.x_seed + soff, P.x_site, ((uint64_t)b * Ci + cg) * (uint64_t)S + gv, P.x_drop_p, xinv);
+          }
+        }
+        sX[v * CiP + cl] = val[u];
+      }
     }
     __syncthreads();
     if (active) {
