@@ -1,11 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out; O=gpurun_out
 timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_model.py -q -x 2>&1 | tail -2
-timeout 300 python tools/op_bench.py --only jlc_L --B 4 --profile --drop 0.1 2>&1 | grep "pw_wgrad\|^{"
-timeout 600 python bench.py --no-eager --no-cpu-baseline --no-infer --steps 200 > $O/r4d_bench.log 2>&1
+timeout 300 python tools/op_bench.py --only conv_down --B 4 2>&1 | grep "^{"
+timeout 600 python bench.py --no-eager --no-cpu-baseline --no-infer --steps 200 > $O/r4e_bench.log 2>&1
 python - <<'PY'
 import json
-for l in open('gpurun_out/r4d_bench.log'):
+for l in open('gpurun_out/r4e_bench.log'):
     if l.startswith('{'):
         d = json.loads(l); r = d['roofline']
         print(d['value'], d['ms_per_step'], r['kernel'], r['frac'], r['kernel_us_avg'], r['own_kernel_ms_per_step'], r['own_launches_per_step'])

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) conv_scatter_kernel(ConvGeo G, const floa
 // the CTAs of the first pair block.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int CW_CT = 16;
-__global__ void __launch_bounds__(128) conv_wgrad_kernel(ConvGeo G, const float* __restrict__ Gc, const float* __restrict__ F,
+__global__ void __launch_bounds__(128, 4) conv_wgrad_kernel(ConvGeo G, const float* __restrict__ Gc, const float* __restrict__ F,
                                                          float* __restrict__ dW, float* __restrict__ db, int vchunk) {
   VX_PDL_ENTRY();
   VX_DYN_SMEM(float, gs);                              // [vchunk][16] gradients, then [vchunk] int4 (batch offset, z, y, x origins)
@@ -251,10 +251,12 @@ __global__ void __launch_bounds__(128) conv_wgrad_kernel(ConvGeo G, const float*
 #pragma unroll
   for (int c = 0; c < CW_CT; ++c) acc[c] = 0.f;
   const float* Fi = F + (size_t)i * SV;
-  for (int v0 = 0; v0 < nv; v0 += 4) {
-    float fv[4];
+  constexpr int CW_U = 8;                              // gathered fine-grid loads in flight per thread (4: 162 us for the k7 s4 stem)
+#pragma unroll 1
+  for (int v0 = 0; v0 < nv; v0 += CW_U) {
+    float fv[CW_U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < CW_U; ++u) {
       fv[u] = 0.f;
       if (v0 + u < nv) {
         const int4 o = vo[v0 + u];
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(128) conv_wgrad_kernel(ConvGeo G, const float*
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < CW_U; ++u) {
       const float* gr = gs + (v0 + u) * CW_CT;         // rows beyond nv hold zeros
 #pragma unroll
       for (int c = 0; c < CW_CT; c += 4) {
@@ -375,7 +377,7 @@ int conv_wgrad(const ConvGeo& G, const float* Gc, const float* F, float* dW, flo
   long long vchunk = (nvox + want - 1) / want;
   if (vchunk < 64) vchunk = 64;
   if (vchunk > 512) vchunk = 512;
-  vchunk = (vchunk + 3) & ~3LL;
+  vchunk = (vchunk + 7) & ~7LL;                        // whole rounds of CW_U voxels: the rows past nv are staged as zeros
   const int gz = cdiv(nvox, vchunk);
   const size_t smem = sizeof(float) * (size_t)vchunk * CW_CT + sizeof(int) * 4 * (size_t)vchunk;
   prof_bytes(4.0 * ((double)G.B * G.Ci * G.D * G.H * G.W + (double)nvox * G.Co + (double)G.Co * npair));
