@@ -875,9 +875,14 @@ __global__ void __launch_bounds__(256) jlc_conv_dgrad_kernel(const __grid_consta
     for (int c = 0; c < 4; ++c) {
       const int ci = g * CG + cb * 4 + c;
       const size_t o = ((size_t)b * A.C + ci) * S + ((size_t)gz * A.H + gy) * A.W + gx0;
+      // every residual load before the first store (dx and dO may alias as far as the compiler knows: interleaved, each load
+      // waited for the store before it)
+      float r[VX];
+#pragma unroll
+      for (int v = 0; v < VX; ++v) r[v] = gx0 + v < A.W ? A.dO[o + v] : 0.f;
 #pragma unroll
       for (int v = 0; v < VX; ++v)
-        if (gx0 + v < A.W) A.dx[o + v] = acc[v][c] + A.dO[o + v];
+        if (gx0 + v < A.W) A.dx[o + v] = acc[v][c] + r[v];
     }
   }
 }
@@ -993,9 +998,14 @@ __global__ void __launch_bounds__(JlcKs<CG>::MAXT, JlcKs<CG>::MINB) jlc_conv_dgr
     for (int c = 0; c < 4; ++c) {
       const int ci = g * CG + cb * 4 + c;
       const size_t o = ((size_t)b * A.C + ci) * S + ((size_t)gz * A.H + gy) * A.W + gx0;
+      // every residual load before the first store (dx and dO may alias as far as the compiler knows: interleaved, each load
+      // waited for the store before it)
+      float r[VX];
+#pragma unroll
+      for (int v = 0; v < VX; ++v) r[v] = gx0 + v < A.W ? A.dO[o + v] : 0.f;
 #pragma unroll
       for (int v = 0; v < VX; ++v)
-        if (gx0 + v < A.W) A.dx[o + v] = acc[v][c] + A.dO[o + v];
+        if (gx0 + v < A.W) A.dx[o + v] = acc[v][c] + r[v];
     }
   }
 }

@@ -29,7 +29,7 @@ struct PeArgs {
 };
 
 template <int CO>
-__global__ void __launch_bounds__(256) patch_embed_fwd_kernel(const __grid_constant__ PeArgs A) {
+__global__ void __launch_bounds__(256, 2) patch_embed_fwd_kernel(const __grid_constant__ PeArgs A) {
   VX_PDL_ENTRY();
   VX_DYN_SMEM(float, ws);                         // [Ci * p^3][CO] (channels past Co are zero)
   const int p = A.p, p3 = p * p * p, K = A.Ci * p3, Co = A.Co;
@@ -51,6 +51,28 @@ __global__ void __launch_bounds__(256) patch_embed_fwd_kernel(const __grid_const
   const bool vec = p == 4 && (A.W & 3) == 0 && (((uintptr_t)A.x) & 15) == 0;
   for (int ci = 0; ci < A.Ci; ++ci) {
     const float* xb = A.x + ((size_t)b * A.Ct + A.c_off + ci) * S + ((size_t)(oz * p) * A.H + oy * p) * A.W + ox * p;
+    if (vec) {
+      // p = 4: the 16 rows of the patch as 16 independent 16-byte loads issued together (one load per rolled (tz, ty) iteration
+      // was a chain of 16 memory round trips per thread: 23 us for a kernel that moves 21 MB)
+      float4 q[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) q[r] = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)(r >> 2) * A.H + (r & 3)) * A.W));
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float4* wr = reinterpret_cast<const float4*>(ws + (size_t)(ci * 16 + r) * 4 * CO);
+        const float xv[4] = {q[r].x, q[r].y, q[r].z, q[r].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int c4 = 0; c4 < CO / 4; ++c4) {
+            const float4 w4 = wr[i * (CO / 4) + c4];
+            acc[4 * c4] = fmaf(w4.x, xv[i], acc[4 * c4]); acc[4 * c4 + 1] = fmaf(w4.y, xv[i], acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(w4.z, xv[i], acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(w4.w, xv[i], acc[4 * c4 + 3]);
+          }
+        }
+      }
+      continue;
+    }
     for (int tz = 0; tz < p; ++tz)
       for (int ty = 0; ty < p; ++ty) {
         const float* xr = xb + ((size_t)tz * A.H + ty) * A.W;
