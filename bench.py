@@ -314,7 +314,9 @@ def run_ours(args, rank, world, local_rank):
                    "launch": ("eager launches" if not used_graph else "whole step replayed as one CUDA graph" if world == 1 else
                               ("one CUDA graph per rank: fwd + bwd + NCCL all-reduce of the flat 9 MB gradient (captured) + AdamW" if os.environ.get("VX_DP_GRAPH", "one") != "split"
                                else "CUDA graph (fwd+bwd) -> eager NCCL all-reduce of the flat 9 MB gradient -> CUDA graph (AdamW)")),
-                   "pointwise": "tcgen05 3xTF32 (fp32-accurate) for S>=1024 (weight gradients S>=512), fp32 SIMT below" if pw_tc else "fp32 SIMT",
+                   "pointwise": ("tcgen05 3xTF32 (fp32-accurate) for S>=1024 (weight gradients S>=512), the level-1/2 FFN pairs as one "
+                                 "tcgen05 kernel per direction, fp32 SIMT below (levels 3-4: FFN pairs fused as well)") if pw_tc else "fp32 SIMT",
+                   "attention": "forward of windows with L>=128 tokens (level 2) on tcgen05 3xTF32 with P in tensor memory; the other levels and the backward fp32 SIMT",
                    "convolutions": "all libveloxseg: out_conv1 / RC out_conv tcgen05 3xTF32 implicit GEMM with fused bias + PixelShuffle, "
                                    "DownConv / UpConv / heads / stems fp32 SIMT; no cuDNN or cuBLAS kernel in the step",
                    },
