@@ -90,3 +90,33 @@ def test_sliding_window_blend_properties():
     assert lab.shape == (20, 17, 9) and int(lab.sum()) == 0
     lab = sliding_window_labels(-two, lambda w: w, (8, 8, 8), "cpu", sw_batch_size=2, overlap=0.25)
     assert int(lab.sum()) == 20 * 17 * 9 - 1                # class 1 everywhere but the tie at voxel 0 (first index wins)
+
+
+def test_upload_schedule_covers_every_window_batch():
+    """One-GPU sliding window: the volume is uploaded in (plane slab x row slab) blocks in window order and a batch waits for
+    the blocks up to its largest (a + r0, b + r1).  Host logic only: for ragged volumes, every overlap and batch size, the
+    blocks a batch has waited for cover every voxel its windows read, and every block is uploaded exactly once."""
+    import itertools
+    from veloxseg_b200.inference import axis_starts, blocks_ready, upload_blocks
+    for size, roi, overlap, sw in itertools.product([(20, 17, 9), (32, 32, 16), (45, 24, 8), (16, 40, 8)], [(16, 16, 8), (12, 8, 8)],
+                                                    [0.0, 0.25, 0.5], [1, 3, 4]):
+        if any(s < r for s, r in zip(size, roi)):
+            continue
+        blocks = upload_blocks(size, roi, overlap)
+        cover = torch.zeros(size[0], size[1], dtype=torch.int32)
+        for x0, x1, y0, y1 in blocks:
+            cover[x0:x1, y0:y1] += 1
+        assert bool((cover == 1).all()), (size, roi, overlap)             # a partition of the (x, y) plane
+        assert [(b[1], b[3]) for b in blocks] == sorted((b[1], b[3]) for b in blocks)      # upload order = key order
+        per = axis_starts(size, roi, overlap)
+        starts = [(a, b, c) for a in per[0] for b in per[1] for c in per[2]]
+        pending = [((b[1], b[3]), b) for b in blocks]
+        have = torch.zeros(size[0], size[1], dtype=torch.bool)
+        for g in range(0, len(starts), sw):
+            ids = starts[g:g + sw]
+            need = max((a + roi[0], b + roi[1]) for a, b, _ in ids)
+            for _, (x0, x1, y0, y1) in blocks_ready(pending, need):
+                have[x0:x1, y0:y1] = True
+            for a, b, _ in ids:
+                assert bool(have[a:a + roi[0], b:b + roi[1]].all()), (size, roi, overlap, sw, (a, b))
+        assert not pending, (size, roi, overlap)      # the last batch has waited for everything

@@ -100,6 +100,33 @@ def sliding_window_predict(inputs: torch.Tensor, predictor: Callable, roi_size: 
     return out[:, :, lo[0]:lo[0] + size[0], lo[1]:lo[1] + size[1], lo[2]:lo[2] + size[2]]
 
 
+def upload_blocks(size: Sequence[int], roi: Sequence[int], overlap: float) -> List[Tuple[int, int, int, int]]:
+    """Upload schedule of `sliding_window_labels` on one GPU: blocks (x0, x1, y0, y1) of (plane slab x row slab), in the order the
+    windows (first axis outermost, then second) first touch them.  The slab edges are the upper edges of the window rows, so a
+    window [a, a + r0) x [b, b + r1) lies inside the blocks whose key (x1, y1) is <= (a + r0, b + r1) in lexicographic order --
+    which is also the upload order (`blocks_ready` below)."""
+    per = axis_starts(size, roi, overlap)
+    xe = sorted({a + roi[0] for a in per[0]})
+    ye = sorted({b + roi[1] for b in per[1]})
+    out, x0 = [], 0
+    for x1 in xe:
+        y0 = 0
+        for y1 in ye:
+            out.append((x0, x1, y0, y1))
+            y0 = y1
+        x0 = x1
+    return out
+
+
+def blocks_ready(pending: list, need: Tuple[int, int]) -> list:
+    """Pops and returns the leading entries of `pending` ([((x1, y1), payload), ...] in upload order) a batch of windows whose
+    largest (a + r0, b + r1) is `need` has to wait for."""
+    done = []
+    while pending and pending[0][0] <= need:
+        done.append(pending.pop(0))
+    return done
+
+
 _COPY_STREAMS = {}
 
 
@@ -154,27 +181,20 @@ def sliding_window_labels(volume_host: torch.Tensor, predictor: Callable, roi_si
         from ._lib import get_lib
         lib = get_lib()
         inputs = torch.empty((1, C, *size), dtype=volume_host.dtype, device=device)
-        per0 = axis_starts(size, roi_size, overlap)
-        xe = sorted({a + roi_size[0] for a in per0[0]})
-        ye = sorted({b + roi_size[1] for b in per0[1]})
         cur = torch.cuda.current_stream(device)
         cs = _copy_stream(device)
         cs.wait_stream(cur)
         esz = volume_host.element_size()
         plane, rowb = size[1] * size[2] * esz, size[2] * esz
-        slab_ready, x0 = [], 0
-        for x1 in xe:
-            y0 = 0
-            for y1 in ye:
-                for c in range(C):
-                    off = ((c * size[0] + x0) * size[1] + y0) * size[2] * esz
-                    lib.check(lib.c.vx_copy_block_async(inputs.data_ptr() + off, volume_host.data_ptr() + off, plane, (y1 - y0) * rowb,
-                                                        x1 - x0, 0, cs.cuda_stream), "vx_copy_block_async")
-                ev = torch.cuda.Event()
-                ev.record(cs)
-                slab_ready.append(((x1, y1), ev))
-                y0 = y1
-            x0 = x1
+        slab_ready = []
+        for x0, x1, y0, y1 in upload_blocks(size, roi_size, overlap):
+            for c in range(C):
+                off = ((c * size[0] + x0) * size[1] + y0) * size[2] * esz
+                lib.check(lib.c.vx_copy_block_async(inputs.data_ptr() + off, volume_host.data_ptr() + off, plane, (y1 - y0) * rowb,
+                                                    x1 - x0, 0, cs.cuda_stream), "vx_copy_block_async")
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            slab_ready.append(((x1, y1), ev))
     else:
         inputs = host_flat.to(device, non_blocking=True).view(1, C, *size)
     if any(pads):
@@ -212,8 +232,8 @@ def sliding_window_labels(volume_host: torch.Tensor, predictor: Callable, roi_si
             # blocks are uploaded in (first axis, second axis) order = the order of the windows: everything up to the last
             # block this batch touches
             need = max((starts[i][0] + roi_size[0], starts[i][1] + roi_size[1]) for i in ids)
-            while slab_ready and slab_ready[0][0] <= need:
-                torch.cuda.current_stream(device).wait_event(slab_ready.pop(0)[1])
+            for _, ev in blocks_ready(slab_ready, need):
+                torch.cuda.current_stream(device).wait_event(ev)
         win = torch.cat([inputs[:, :, a:a + roi_size[0], b:b + roi_size[1], c:c + roi_size[2]]
                          for a, b, c in (starts[i] for i in ids)])
         y = _logits(predictor(win))
