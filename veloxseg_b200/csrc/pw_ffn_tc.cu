@@ -224,13 +224,12 @@ static bool ffn_tc_shape_ok(int S, int C, int eC, const float* Wa, const float* 
          !((uintptr_t)Wb & 15);
 }
 
-static int launch_ffn_tc(FfnTcBatch& T, int Cmax, int eCmax, double bytes, double flops, cudaStream_t stream) {
-  size_t smem = 0;
+static int launch_ffn_tc(FfnTcBatch& T, double bytes, double flops, cudaStream_t stream) {
+  size_t smem = 0;                     // hi / lo images of both weight matrices of the largest problem
   for (int i = 0; i < T.nprob; ++i) {
     const size_t s = sizeof(float) * 4 * (size_t)T.p[i].C * T.p[i].eC;
     smem = s > smem ? s : smem;
   }
-  (void)Cmax; (void)eCmax;
   if (smem > 160 * 1024) return 1;
   T.seed_dev = get_seed_dev();
   prof_bytes(bytes);
@@ -258,7 +257,7 @@ int pw_ffn_tc(const FfnBatch& batch, cudaStream_t stream) {
     bytes += 4.0 * batch.B * batch.S * (2.0 * F.C + F.eC + (F.res ? F.C : 0)) + 8.0 * F.C * F.eC;
     flops += 4.0 * batch.B * batch.S * F.C * F.eC;
   }
-  return launch_ffn_tc(T, 0, 0, bytes, flops, stream);
+  return launch_ffn_tc(T, bytes, flops, stream);
 }
 
 int pw_ffn_tc_bwd(const FfnBwdBatch& batch, cudaStream_t stream) {
@@ -277,7 +276,7 @@ int pw_ffn_tc_bwd(const FfnBwdBatch& batch, cudaStream_t stream) {
     bytes += 4.0 * batch.B * batch.S * (2.0 * F.C + 2.0 * F.eC) + 8.0 * F.C * F.eC;
     flops += 4.0 * batch.B * batch.S * F.C * F.eC;
   }
-  return launch_ffn_tc(T, 0, 0, bytes, flops, stream);
+  return launch_ffn_tc(T, bytes, flops, stream);
 }
 
 }  // namespace vx
