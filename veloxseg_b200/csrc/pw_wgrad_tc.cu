@@ -344,7 +344,9 @@ int pw_wgrad_tc(const WgBatch& batch, cudaStream_t stream) {
   const size_t smem = fl * sizeof(float);
   if (smem > 200 * 1024) return 1;          // <= 113 KB keeps two CTAs per SM (staging of one overlaps the MMAs of the other)
   const int nchunks = batch.B * cdiv(S, WT_KC);
-  int nsplit = (2 * kSMs) / batch.nprob;
+  // CTAs per SM over all problems of the batch (split-K factor); VX_WGRAD_TC_CTAS_PER_SM is the tuning probe
+  static const int per_sm = [] { const char* e = getenv("VX_WGRAD_TC_CTAS_PER_SM"); const int v = e ? atoi(e) : 2; return v >= 1 && v <= 8 ? v : 2; }();
+  int nsplit = (per_sm * kSMs) / batch.nprob;
   if (nsplit < 1) nsplit = 1;
   if (nsplit > nchunks) nsplit = nchunks;
   VX_SET_SMEM(pw_wgrad_tc_kernel, smem);
